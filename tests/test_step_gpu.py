@@ -1,0 +1,44 @@
+"""GPU parity of the whole G+D step through the drop-in (op-by-op) path against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import nets as onets
+from oracle import step as ostep
+
+pytestmark = pytest.mark.gpu
+
+
+def _copy_params(src_oracle, dst_trainer):
+    dst_trainer.parametersG.copy_(src_oracle.pG)
+    dst_trainer.parametersD.copy_(src_oracle.pD)
+
+
+@pytest.mark.parametrize("variant,extra", [("image", {}), ("video", {}), ("video", {"wtgdl": 0.5}), ("video", {"weight_nomask": 0.0})])
+def test_closure_step_matches_oracle_fp32(cenn, variant, extra):
+    from video_filler_b200 import models, train
+    cenn.set_precision("fp32")
+    kw = dict(batchSize=4, nBottleneck=96, nef=16, ngf=16, ndf=16, **extra)
+    if variant == "video":
+        kw["predLen"] = 2
+    opt = models.default_opt(variant, **kw)
+    oopt = onets.default_opt(variant, **kw)
+    orc = ostep.StepOracle(oopt, seed=1234, dtype=np.float64)
+    trn = train.ClosureTrainer(opt, seed=99)
+    _copy_params(orc, trn)
+    rng = np.random.default_rng(4321)
+    for it in range(3):
+        batch = orc.synth_batch(rng)
+        lo = orc.step(*batch)
+        lg = trn.step(*batch)
+        for k in ("errD", "errG", "errG_l2", "errG_total"):
+            assert lg[k] == pytest.approx(lo[k], rel=2e-4), (it, k)
+        if extra.get("wtgdl"):
+            assert lg["errG_gdl"] == pytest.approx(lo["errG_gdl"], rel=2e-4)
+    assert rel_err(trn.gradParametersG.numpy(), orc.gG) <= 1e-3
+    assert rel_err(trn.gradParametersD.numpy(), orc.gD) <= 1e-3
+    # Adam's first steps move every parameter by ~lr regardless of gradient scale, so compare loosely
+    assert rel_err(trn.parametersG.numpy(), orc.pG) <= 5e-3
+    assert rel_err(trn.parametersD.numpy(), orc.pD) <= 5e-3
+    # reference invariant: conv biases are zero during forward but Adam moves them afterwards (SURVEY 9.9 i)
+    assert float(np.abs(trn.netD.modules[0].bias.numpy()).max()) > 0

@@ -1,0 +1,76 @@
+// common.cuh -- shared state, error handling and small device helpers for libcenn.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/cenn.h"
+
+struct cenn_state {
+    int device = 0;
+    int precision = CENN_FP32;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int64_t launches = 0;
+    // scratch: small reduction accumulators (doubles) + a growable workspace
+    double *red = nullptr;            // [RED_SLOTS] device doubles
+    double *red_host = nullptr;       // pinned mirror
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    void *ws2 = nullptr;
+    size_t ws2_bytes = 0;
+};
+static const int RED_SLOTS = 64;
+
+void cenn_set_error(const char *fmt, ...);
+int cenn_check_cuda(cudaError_t e, const char *what, const char *file, int line);
+void *cenn_workspace(cenn_state *s, size_t bytes);   // stream-ordered reuse; grows with cudaMalloc
+void *cenn_workspace2(cenn_state *s, size_t bytes);
+
+#define CK(expr) do { if (cenn_check_cuda((expr), #expr, __FILE__, __LINE__)) return 1; } while (0)
+#define CK_LAUNCH(s) do { (s)->launches++; if (cenn_check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)) return 1; } while (0)
+#define REQUIRE(cond, ...) do { if (!(cond)) { cenn_set_error(__VA_ARGS__); return 1; } } while (0)
+#define API_BEGIN(s) do { if (!(s)) { cenn_set_error("null cenn_state"); return 1; } \
+    if (cenn_check_cuda(cudaSetDevice((s)->device), "cudaSetDevice", __FILE__, __LINE__)) return 1; } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grid size for bandwidth kernels: a multiple of the SM count (148 on B200), capped by the work
+static inline int bw_grid(const cenn_state *s, int64_t work_items, int threads, int per_sm = 8) {
+    int64_t need = ceil_div64(work_items, threads);
+    int64_t cap = (int64_t)s->sm_count * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum; result valid in thread 0.  `sh` must hold >= 32 elements.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *sh) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : T(0);
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;
+}
+#endif

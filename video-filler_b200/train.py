@@ -1,0 +1,276 @@
+"""The training step of the reference, two ways.
+
+``ClosureTrainer`` is the drop-in path: the ``fDx`` / ``fGx`` closures of ``train.lua:278-410`` and
+``train_vid_weighted.lua:373-537`` written against the nn.* mirror, op by op, with the reference's
+call pattern (four criterion:forward syncs per step, bias zeroing, gradient accumulation over the
+two D passes, fGx reusing D's fake-pass state).  It runs in either precision mode.
+
+``FusedTrainer`` wraps the C++ whole-step executor (``cenn_trainer_*``): NHWC bf16 activations,
+tcgen05 implicit-GEMM convolutions, fused BN / loss / Adam kernels, losses kept on the device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, models, nn, optim
+from .tensor import CudaTensor, api, state
+
+MEAN_FILL = (2 * 117.0 / 255.0 - 1.0, 2 * 104.0 / 255.0 - 1.0, 2 * 123.0 / 255.0 - 1.0)
+
+
+class ClosureTrainer:
+    def __init__(self, opt, seed=1234):
+        self.opt = opt
+        rng = np.random.default_rng(seed)
+        self.netG = models.build_netG(opt)
+        self.netD = models.build_netD(opt)
+        models.weights_init(self.netG, rng)
+        models.weights_init(self.netD, rng)
+        self.criterion = nn.BCECriterion()
+        self.criterionMSE = nn.MSECriterion() if opt["wtl2"] != 0 else None
+        self.criterionGDL = nn.GDLCriterion(1) if opt["wtgdl"] != 0 else None
+        wtl2 = opt["wtl2"]
+        self.optimStateG = dict(learningRate=opt["lr"] * 10 if 0 < wtl2 < 1 else opt["lr"], beta1=opt["beta1"])
+        self.optimStateD = dict(learningRate=opt["lr"], beta1=opt["beta1"])
+        self.parametersD, self.gradParametersD = self.netD.getParameters()
+        self.parametersG, self.gradParametersG = self.netG.getParameters()
+        B, F, nc = opt["batchSize"], opt["fineSize"], models.net_channels(opt)
+        self.input_ctx = CudaTensor(B, nc, F, F)
+        self.label = CudaTensor(B)
+        if opt["variant"] == "image":
+            self.input_center = CudaTensor(B, nc, F // 2, F // 2)
+            self.input_real_center = CudaTensor(B, nc, F // 2, F // 2)
+        else:
+            self.input_inpainted = CudaTensor(B, nc, F, F)
+            self.input_mask = CudaTensor(B, nc, F, F)
+            self.input_real = CudaTensor(B, nc, F, F)
+        self.errD = self.errG = self.errG_l2 = self.errG_gdl = None
+
+    # ---------------------------------------------------------------- image variant
+    def fDx_image(self, real_ctx, real_center):
+        models.zero_conv_bias(self.netD)
+        models.zero_conv_bias(self.netG)
+        self.gradParametersD.zero()
+        self.input_ctx.copy_(real_ctx)
+        self.input_center.copy_(real_center)
+        self.input_real_center.copy_(real_center)
+        self.label.fill(1)
+        out = self.netD.forward(self.input_center)
+        self.errD_real = self.criterion.forward(out, self.label)
+        df_do = self.criterion.backward(out, self.label)
+        self.netD.backward(self.input_center, df_do)
+        fake = self.netG.forward(self.input_ctx)
+        self.input_center.copy_(fake)
+        self.label.fill(0)
+        out = self.netD.forward(self.input_center)
+        self.errD_fake = self.criterion.forward(out, self.label)
+        df_do = self.criterion.backward(out, self.label)
+        self.netD.backward(self.input_center, df_do)
+        self.errD = self.errD_real + self.errD_fake
+        return self.errD, self.gradParametersD
+
+    def fGx_image(self):
+        o = self.opt
+        models.zero_conv_bias(self.netD)
+        models.zero_conv_bias(self.netG)
+        self.gradParametersG.zero()
+        self.label.fill(1)
+        out = self.netD.output
+        self.errG = self.criterion.forward(out, self.label)
+        df_do = self.criterion.backward(out, self.label)
+        df_dg = self.netD.updateGradInput(self.input_center, df_do)
+        total = self.errG
+        wtl2 = o["wtl2"]
+        if wtl2 != 0:
+            # train.lua:377-400 -- MSE forward + backward + overlap-weighted blend, one fused kernel
+            loss = C.c_float()
+            N, Cn, H, W = self.input_center.shape
+            api().cenn_WeightedMSEBlend_overlap(state(), C.c_void_p(df_dg.ptr), C.c_void_p(self.input_center.ptr),
+                                                C.c_void_p(self.input_real_center.ptr), N, Cn, H, W, wtl2,
+                                                o["overlapPred"], C.byref(loss))
+            self.errG_l2 = loss.value
+            total = (1 - wtl2) * self.errG + wtl2 * self.errG_l2 if 0 < wtl2 < 1 else self.errG + wtl2 * self.errG_l2
+        self.df_dg = df_dg
+        self.netG.backward(self.input_ctx, df_dg)
+        return total, self.gradParametersG
+
+    # ---------------------------------------------------------------- video variant
+    def fDx_video(self, real_ctx, real_full, real_mask):
+        o = self.opt
+        models.zero_conv_bias(self.netD)
+        models.zero_conv_bias(self.netG)
+        self.gradParametersD.zero()
+        self.input_ctx.copy_(real_ctx)
+        self.input_real.copy_(real_full)
+        self.label.fill(1)
+        self.input_mask.copy_(real_mask)
+        out = self.netD.forward(self.input_real)
+        self.errD_real = self.criterion.forward(out, self.label)
+        df_do = self.criterion.backward(out, self.label)
+        self.netD.backward(self.input_real, df_do)
+        fake = self.netG.forward(self.input_ctx)
+        if o["weight_nomask"] == 0:
+            self.input_inpainted.copy_(self.input_real)
+            api().cenn_MaskComposite(state(), C.c_void_p(self.input_inpainted.ptr), C.c_void_p(self.input_mask.ptr),
+                                     C.c_void_p(fake.ptr), fake.nelement())
+        else:
+            self.input_inpainted.copy_(fake)
+        self.label.fill(0)
+        out = self.netD.forward(self.input_inpainted)
+        self.errD_fake = self.criterion.forward(out, self.label)
+        df_do = self.criterion.backward(out, self.label)
+        self.netD.backward(self.input_inpainted, df_do)
+        self.errD = self.errD_real + self.errD_fake
+        return self.errD, self.gradParametersD
+
+    def fGx_video(self):
+        o = self.opt
+        models.zero_conv_bias(self.netD)
+        models.zero_conv_bias(self.netG)
+        self.gradParametersG.zero()
+        self.label.fill(1)
+        out = self.netD.output
+        self.errG = self.criterion.forward(out, self.label)
+        df_do = self.criterion.backward(out, self.label)
+        df_dg = self.netD.updateGradInput(self.input_real, df_do)
+        total = self.errG
+        wtl2 = o["wtl2"]
+        if o["overlapPred"] != 0:
+            raise ValueError("video scripts require overlapPred == 0 (train_vid_weighted.lua:509)")
+        if o["wtgdl"] != 0:
+            # loss from GDL (:524); its gradient in the script is criterionMSE:backward (:525), folded into the blend
+            self.errG_gdl = self.criterionGDL.forward(self.input_inpainted, self.input_real)
+        if wtl2 != 0:
+            loss = C.c_float()
+            api().cenn_WeightedMSEBlend_masked(state(), C.c_void_p(df_dg.ptr), C.c_void_p(self.input_inpainted.ptr),
+                                               C.c_void_p(self.input_real.ptr), C.c_void_p(self.input_mask.ptr),
+                                               df_dg.nelement(), wtl2, o["weight_nomask"], o["wtgdl"], C.byref(loss))
+            self.errG_l2 = loss.value
+            total = (1 - wtl2) * self.errG + wtl2 * self.errG_l2 if 0 < wtl2 < 1 else self.errG + wtl2 * self.errG_l2
+        if o["wtgdl"] != 0:
+            total = total + o["wtgdl"] * self.errG_gdl
+        self.df_dg = df_dg
+        self.netG.backward(self.input_ctx, df_dg)
+        return total, self.gradParametersG
+
+    # ---------------------------------------------------------------- one step (train.lua:421-424)
+    def step(self, *batch):
+        if self.opt["variant"] == "image":
+            optim.adam(lambda x: self.fDx_image(*batch), self.parametersD, self.optimStateD)
+            _, fx = optim.adam(lambda x: self.fGx_image(), self.parametersG, self.optimStateG)
+        else:
+            optim.adam(lambda x: self.fDx_video(*batch), self.parametersD, self.optimStateD)
+            _, fx = optim.adam(lambda x: self.fGx_video(), self.parametersG, self.optimStateG)
+        return dict(errD=self.errD, errG=self.errG, errG_l2=self.errG_l2, errG_gdl=self.errG_gdl,
+                    errD_real=self.errD_real, errD_fake=self.errD_fake, errG_total=fx[0])
+
+
+LOSS_NAMES = ("errD", "errG", "errG_l2", "errG_gdl", "errD_real", "errD_fake", "errG_total")
+
+
+class FusedTrainer:
+    """Whole-step executor (cenn_trainer_*): one call per G+D step, host or device inputs."""
+
+    def __init__(self, opt, precision="bf16", world_size=1, rank=0, dead_dgrad=1):
+        self.opt = opt
+        cfg = _lib.TrainerConfig(
+            variant=0 if opt["variant"] == "image" else 1, batchSize=opt["batchSize"], fineSize=opt["fineSize"],
+            nBottleneck=opt["nBottleneck"], nef=opt["nef"], ngf=opt["ngf"], ndf=opt["ndf"], nc=opt["nc"],
+            predLen=opt.get("predLen", 1), overlapPred=opt["overlapPred"], wtl2=opt["wtl2"],
+            weight_nomask=opt.get("weight_nomask", 0.0), wtgdl=opt.get("wtgdl", 0.0), lr=opt["lr"], beta1=opt["beta1"],
+            precision={"fp32": 0, "bf16": 1}[precision], world_size=world_size, rank=rank, dead_dgrad=dead_dgrad)
+        self.cfg = cfg
+        h = C.c_void_p()
+        api().cenn_trainer_create(state(), C.byref(cfg), C.byref(h))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                api().cenn_trainer_destroy(self.h)
+        except Exception:
+            pass
+
+    def param_count(self, net):
+        n = C.c_int64()
+        api().cenn_trainer_param_count(self.h, net, C.byref(n))
+        return n.value
+
+    def set_params(self, net, flat):
+        flat = np.ascontiguousarray(flat, np.float32)
+        assert flat.size == self.param_count(net)
+        api().cenn_trainer_set_params_host(self.h, net, flat.ctypes.data_as(C.c_void_p))
+
+    def get_params(self, net):
+        out = np.empty(self.param_count(net), np.float32)
+        api().cenn_trainer_get_params_host(self.h, net, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def get_grads(self, net):
+        out = np.empty(self.param_count(net), np.float32)
+        api().cenn_trainer_get_grads_host(self.h, net, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def bn_stat_count(self, net):
+        n = C.c_int64()
+        api().cenn_trainer_bn_stat_count(self.h, net, C.byref(n))
+        return n.value
+
+    def get_bn_stats(self, net):
+        out = np.empty(self.bn_stat_count(net), np.float32)
+        api().cenn_trainer_get_bn_stats_host(self.h, net, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def set_bn_stats(self, net, stats):
+        stats = np.ascontiguousarray(stats, np.float32)
+        assert stats.size == self.bn_stat_count(net)
+        api().cenn_trainer_set_bn_stats_host(self.h, net, stats.ctypes.data_as(C.c_void_p))
+
+    def step_host(self, a, b, mask=None):
+        """One step from host fp32 NCHW arrays (H2D + step + D2H of the losses)."""
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        m = np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p) if mask is not None else None
+        losses = np.zeros(8, np.float32)
+        api().cenn_trainer_step_host(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), m,
+                                     losses.ctypes.data_as(C.c_void_p))
+        return dict(zip(LOSS_NAMES, losses.tolist()))
+
+    def step_device(self, a_ptr, b_ptr, mask_ptr=None):
+        api().cenn_trainer_step_device(self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr),
+                                       C.c_void_p(mask_ptr) if mask_ptr else None)
+
+    def step_phase(self, phase, a_ptr, b_ptr, mask_ptr=None):
+        api().cenn_trainer_step_phase(self.h, int(phase), C.c_void_p(a_ptr), C.c_void_p(b_ptr),
+                                      C.c_void_p(mask_ptr) if mask_ptr else None)
+
+    def grad_buffer(self, net):
+        p, n = C.c_void_p(), C.c_int64()
+        api().cenn_trainer_grad_buffer(self.h, net, C.byref(p), C.byref(n))
+        return p.value, n.value
+
+    def read_losses(self):
+        losses = np.zeros(8, np.float32)
+        api().cenn_trainer_read_losses(self.h, losses.ctypes.data_as(C.c_void_p))
+        return dict(zip(LOSS_NAMES, losses.tolist()))
+
+    def generator_forward(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        B = x.shape[0]
+        F = self.opt["fineSize"]
+        nc = models.net_channels(self.opt)
+        oF = F // 2 if self.opt["variant"] == "image" else F
+        out = np.empty((B, nc, oF, oF), np.float32)
+        api().cenn_trainer_generator_forward_host(self.h, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), B)
+        return out
+
+    def fetch(self, name, capacity=1 << 28):
+        n = C.c_int64()
+        buf = np.empty(capacity, np.float32)
+        api().cenn_trainer_fetch_host(self.h, name.encode(), buf.ctypes.data_as(C.c_void_p), capacity, C.byref(n))
+        return buf[:n.value].copy()
+
+    def launches_per_step(self):
+        n = C.c_int64()
+        api().cenn_trainer_kernel_launches_per_step(self.h, C.byref(n))
+        return n.value
