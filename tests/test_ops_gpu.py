@@ -231,10 +231,11 @@ def test_blends_composite_adam_and_tensor_math(cenn):
     x = rng.uniform(-1, 1, shape).astype(np.float32)
     t = rng.uniform(-1, 1, shape).astype(np.float32)
     g = rng.normal(0, 1e-3, shape).astype(np.float32)
+    dx, dt = dev(T, x), dev(T, t)     # keep the device tensors alive across the raw-pointer calls
     for wtl2, ov in [(0.999, 4), (0.999, 0), (2.0, 4)]:
         d = dev(T, g)
         loss = C.c_float()
-        api.cenn_WeightedMSEBlend_overlap(st, C.c_void_p(d.ptr), C.c_void_p(dev(T, x).ptr), C.c_void_p(dev(T, t).ptr),
+        api.cenn_WeightedMSEBlend_overlap(st, C.c_void_p(d.ptr), C.c_void_p(dx.ptr), C.c_void_p(dt.ptr),
                                           *shape, wtl2, ov, C.byref(loss))
         ref = ops.blend_l2_overlap(g.astype(np.float64), x.astype(np.float64), t.astype(np.float64), wtl2, ov)
         assert rel_err(d.numpy(), ref) <= 1e-5
@@ -243,7 +244,7 @@ def test_blends_composite_adam_and_tensor_math(cenn):
     for lam, wtgdl in [(0.05, 0.0), (0.0, 0.0), (0.05, 0.5)]:
         d, dm = dev(T, g), dev(T, mask)
         loss = C.c_float()
-        api.cenn_WeightedMSEBlend_masked(st, C.c_void_p(d.ptr), C.c_void_p(dev(T, x).ptr), C.c_void_p(dev(T, t).ptr),
+        api.cenn_WeightedMSEBlend_masked(st, C.c_void_p(d.ptr), C.c_void_p(dx.ptr), C.c_void_p(dt.ptr),
                                          C.c_void_p(dm.ptr), x.size, 0.999, lam, wtgdl, C.byref(loss))
         ref, w = ops.blend_l2_masked(g.astype(np.float64), x.astype(np.float64), t.astype(np.float64),
                                      mask.astype(np.float64), 0.999, lam)
@@ -253,8 +254,8 @@ def test_blends_composite_adam_and_tensor_math(cenn):
             assert rel_err(dm.numpy(), w) <= 1e-6     # weights written in place over input_mask (:494)
         else:
             assert np.array_equal(dm.numpy(), mask)
-    d = dev(T, x)
-    api.cenn_MaskComposite(st, C.c_void_p(d.ptr), C.c_void_p(dev(T, mask).ptr), C.c_void_p(dev(T, t).ptr), x.size)
+    d, dmask = dev(T, x), dev(T, mask)
+    api.cenn_MaskComposite(st, C.c_void_p(d.ptr), C.c_void_p(dmask.ptr), C.c_void_p(dt.ptr), x.size)
     assert np.array_equal(d.numpy(), ops.mask_composite(x, mask, t))
     # adam, 3 steps on an odd-length vector
     from video_filler_b200 import optim
@@ -265,16 +266,18 @@ def test_blends_composite_adam_and_tensor_math(cenn):
     p_ref = p.astype(np.float64)
     for _ in range(3):
         gr = rng.normal(0, 1, n).astype(np.float32)
-        optim.adam(lambda xx: (0.0, dev(T, gr)), pd, st_d)
+        gd = dev(T, gr)
+        optim.adam(lambda xx: (0.0, gd), pd, st_d)
         ops.adam_step(p_ref, gr.astype(np.float64), st_o, 2e-3, 0.5)
     assert rel_err(pd.numpy(), p_ref) <= 1e-6
     # tensor math used by the scripts
     a = dev(T, x)
-    a.mul(0.5).add(0.25).add(2.0, dev(T, t)).cmul(dev(T, t))
+    a.mul(0.5).add(0.25).add(2.0, dt).cmul(dt)
     assert rel_err(a.numpy(), (x * 0.5 + 0.25 + 2.0 * t) * t) <= 1e-6
     a = dev(T, np.abs(x) + 1).sqrt()
     assert rel_err(a.numpy(), np.sqrt(np.abs(x) + 1)) <= 1e-6
-    a = dev(T, x).addcmul(0.5, dev(T, t), dev(T, g)).addcdiv(-2.0, dev(T, t), dev(T, np.abs(x) + 1))
+    dg, dden = dev(T, g), dev(T, np.abs(x) + 1)
+    a = dev(T, x).addcmul(0.5, dt, dg).addcdiv(-2.0, dt, dden)
     assert rel_err(a.numpy(), x + 0.5 * t * g - 2.0 * t / (np.abs(x) + 1)) <= 1e-6
     a = dev(T, x)
     a.fill_box(1, 2, 8, 56, 8, 56, -0.1843)   # train.lua:289 mean fill of one channel

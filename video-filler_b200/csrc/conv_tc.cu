@@ -1,6 +1,486 @@
-// conv_tc.cu -- placeholder until the tcgen05 path lands: report "shape not handled" so the op-level
-// ABI runs the fp32 SIMT kernels.
+// conv_tc.cu -- host side of the BF16 tcgen05 implicit-GEMM path: TMA tensor maps over NHWC bf16
+// activations, weight repacking, launch configuration, and NCHW-fp32 wrappers for the op-level ABI.
 #include "conv_tc.h"
-int tc_conv_fprop_nchw(cenn_state *, const float *, const float *, const float *, float *, int, int, int, int, int, int, int, int, int, int, int) { return 1; }
-int tc_conv_dgrad_nchw(cenn_state *, const float *, const float *, const float *, float *, int, int, int, int, int, int, int, int, int, int, int) { return 1; }
-int tc_conv_wgrad_nchw(cenn_state *, const float *, const float *, float *, int, int, int, int, int, int, int, int, int, int, int, float, int) { return 1; }
+#include <cudaTypedefs.h>
+#include <vector>
+#include "tc_gemm.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ tensor maps
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int get_encoder() {
+    if (g_encode) return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cenn_set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+        return 1;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return 0;
+}
+
+int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box) {
+    if (get_encoder()) return 1;
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+    REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address not 16-byte aligned");
+    for (int i = 0; i < rank - 1; ++i) REQUIRE((gs[i] & 15) == 0, "TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+    for (int i = 0; i < rank; ++i) REQUIRE(bx[i] >= 1 && bx[i] <= 256 && gd[i] >= 1, "TMA box/dim %d out of range (box %u, dim %llu)", i, bx[i], (unsigned long long)gd[i]);
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+// 5-D gather view of L [N, H2, W2, C]: (px*C + c, x', py, y', n) with x = 2x'+px, y = 2y'+py
+int map_gather(CUtensorMap *m, const bf16 *L, int N, int H2, int W2, int C, int bw, int bh, int bn) {
+    uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)W2 / 2, 2, (uint64_t)H2 / 2, (uint64_t)N};
+    uint64_t st[4] = {(uint64_t)2 * C * 2, (uint64_t)W2 * C * 2, (uint64_t)2 * W2 * C * 2, (uint64_t)H2 * W2 * C * 2};
+    uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bn};
+    return make_map(m, L, 5, dims, st, box);
+}
+// 5-D plain view of S [N, h, w, C]: (c, x, 0, y, n)
+int map_plain(CUtensorMap *m, const bf16 *S, int N, int h, int w, int C, int bw, int bh, int bn) {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)w, 1, (uint64_t)h, (uint64_t)N};
+    uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
+    uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bn};
+    return make_map(m, S, 5, dims, st, box);
+}
+int map_2d(CUtensorMap *m, const bf16 *B, uint64_t K, uint64_t rows, int box_rows) {
+    uint64_t dims[2] = {K, rows};
+    uint64_t st[1] = {K * 2};
+    uint32_t box[2] = {64, (uint32_t)box_rows};
+    return make_map(m, B, 2, dims, st, box);
+}
+
+int pow2_le(int v, int cap) { int p = 1; while (p * 2 <= v && p * 2 <= cap) p *= 2; return p; }
+// split `total` pixels per tile over (w, h, n)
+void choose_box(int w, int h, int total, int &bw, int &bh, int &bn) {
+    bw = pow2_le(w, total);
+    bh = pow2_le(h, total / bw);
+    bn = total / (bw * bh);
+}
+
+// device copy of small tables (KbDesc); tiny, cached per call via the state's workspace2 tail
+template <typename T>
+T *upload(cenn_state *s, const std::vector<T> &v, void *dst) {
+    cudaMemcpyAsync(dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream);
+    return reinterpret_cast<T *>(dst);
+}
+
+struct KbTable {       // growing device arena for k-block tables (one per state; contents are launch-ordered)
+    void *dev = nullptr;
+    size_t cap = 0, used = 0;
+};
+KbTable g_kbt;
+tc::KbDesc *kb_upload(cenn_state *s, const std::vector<tc::KbDesc> &v) {
+    size_t bytes = v.size() * sizeof(tc::KbDesc);
+    if (!g_kbt.dev) { g_kbt.cap = 4u << 20; if (cudaMalloc(&g_kbt.dev, g_kbt.cap) != cudaSuccess) { cenn_set_error("kb table alloc failed"); return nullptr; } }
+    if (g_kbt.used + bytes > g_kbt.cap) { cudaStreamSynchronize(s->stream); g_kbt.used = 0; }
+    // pageable-memory async copies are staged by the runtime before returning, so `v` may die after this call
+    void *dst = (uint8_t *)g_kbt.dev + g_kbt.used;
+    g_kbt.used += (bytes + 255) & ~size_t(255);
+    if (cudaMemcpyAsync(dst, v.data(), bytes, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) { cenn_set_error("kb table upload failed"); return nullptr; }
+    return reinterpret_cast<tc::KbDesc *>(dst);
+}
+
+const int SMEM_LIMIT = 227 * 1024;
+
+template <int BN>
+int launch_gather(cenn_state *s, const CUtensorMap &tmA, const CUtensorMap &tmB, const tc::GatherGemmParams &p, dim3 grid) {
+    const int stage_bytes = 128 * 128 + BN * 128;
+    const int fixed = 1024 /*align*/ + 8 * (2 * 8 + 1) + 16 + 2 * BN * 4 + 4 * 32 * 33 * 4 + 256;
+    int stages = (SMEM_LIMIT - fixed) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages > p.num_kb) stages = p.num_kb;
+    if (stages < 1) stages = 1;
+    size_t smem = (size_t)stages * stage_bytes + fixed;
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(tc::gather_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); attr_set = true; }
+    tc::gather_gemm_kernel<BN><<<grid, tc::GEMM_THREADS, smem, s->stream>>>(tmA, tmB, p, stages);
+    CK_LAUNCH(s);
+    return 0;
+}
+int launch_gather_bn(cenn_state *s, int BN, const CUtensorMap &tmA, const CUtensorMap &tmB, const tc::GatherGemmParams &p, dim3 grid) {
+    switch (BN) {
+        case 32: return launch_gather<32>(s, tmA, tmB, p, grid);
+        case 64: return launch_gather<64>(s, tmA, tmB, p, grid);
+        case 128: return launch_gather<128>(s, tmA, tmB, p, grid);
+        case 256: return launch_gather<256>(s, tmA, tmB, p, grid);
+    }
+    cenn_set_error("unsupported BN %d", BN);
+    return 1;
+}
+template <int BN>
+int launch_wgrad(cenn_state *s, const CUtensorMap &tmL, const CUtensorMap &tmS, const tc::WgradParams &p, dim3 grid, int nkb) {
+    const int stage_bytes = 2 * 8192 + (BN / 64) * 8192;
+    const int fixed = 1024 + 8 * (2 * 8 + 1) + 16 + 256;
+    int stages = (SMEM_LIMIT - fixed) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages > nkb) stages = nkb;
+    if (stages < 1) stages = 1;
+    size_t smem = (size_t)stages * stage_bytes + fixed;
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(tc::wgrad_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); attr_set = true; }
+    tc::wgrad_gemm_kernel<BN><<<grid, tc::GEMM_THREADS, smem, s->stream>>>(tmL, tmS, p, stages);
+    CK_LAUNCH(s);
+    return 0;
+}
+
+int pick_bn(int n_valid, int m_tiles, int sm_count) {
+    // widest tile that still gives roughly a full wave of CTAs; N tiles of 256 run the MMA at full rate
+    int bn = 256;
+    while (bn > 32 && (bn / 2 >= n_valid)) bn /= 2;
+    while (bn > 64 && (long long)m_tiles * ((n_valid + bn - 1) / bn) < sm_count) bn /= 2;
+    return bn;
+}
+
+void fill_epilogue(tc::GatherGemmParams &p, const TcEpilogue &ep, bf16 *out) {
+    p.bias = ep.bias; p.stats = ep.stats; p.stats_stride = ep.stats_stride; p.act = ep.act; p.act_param = ep.act_param;
+    p.out_bf16 = ep.no_bf16 ? nullptr : out; p.out_f32 = ep.out_f32;
+}
+
+// tap geometry of the 4x4 / stride-2 / pad-1 window: input row 2*oy - 1 + u = 2*(oy + DYS[u]) + PYS[u]
+const int DYS[4] = {-1, 0, 0, 1}, PYS[4] = {1, 0, 1, 0};
+// dgrad sub-pixel phases: output row 2y'+py receives taps u = UPH[py][a] from S row y' + DYP[py][a]
+const int UPH[2][2] = {{1, 3}, {0, 2}}, DYP[2][2] = {{0, -1}, {1, 0}};
+
+// ------------------------------------------------------------------ layout kernels
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, int N, int C, int HW, int Cp) {
+    int64_t total = (int64_t)N * HW * Cp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % Cp);
+        int64_t t = i / Cp;
+        int pix = (int)(t % HW), n = (int)(t / HW);
+        dst[i] = __float2bfloat16(c < C ? src[((int64_t)n * C + c) * HW + pix] : 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const bf16 *__restrict__ src, float *__restrict__ dst, int N, int C, int HW, int Cp) {
+    int64_t total = (int64_t)N * C * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int pix = (int)(i % HW);
+        int64_t t = i / HW;
+        int c = (int)(t % C), n = (int)(t / C);
+        dst[i] = __bfloat162float(src[((int64_t)n * HW + pix) * Cp + c]);
+    }
+}
+__global__ void __launch_bounds__(256) repack_wf_kernel(const float *__restrict__ w, bf16 *__restrict__ Wf, int Cs, int Cl, int Clp, int kk) {
+    int64_t total = (int64_t)Cs * kk * Clp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cl = (int)(i % Clp);
+        int64_t t = i / Clp;
+        int tap = (int)(t % kk), cs = (int)(t / kk);
+        Wf[i] = __float2bfloat16(cl < Cl ? w[((int64_t)cs * Cl + cl) * kk + tap] : 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) repack_wt_kernel(const float *__restrict__ w, bf16 *__restrict__ Wt, int Cs, int Cl, int Csp, int cl_rows) {
+    int64_t total = (int64_t)4 * cl_rows * 4 * Csp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cs = (int)(i % Csp);
+        int64_t t = i / Csp;
+        int ab = (int)(t % 4); t /= 4;
+        int cl = (int)(t % cl_rows), ph = (int)(t / cl_rows);
+        int py = ph >> 1, px = ph & 1, a = ab >> 1, b = ab & 1;
+        const int U[2][2] = {{1, 3}, {0, 2}};
+        int u = U[py][a], v = U[px][b];
+        Wt[i] = __float2bfloat16((cs < Cs && cl < Cl) ? w[((int64_t)cs * Cl + cl) * 16 + u * 4 + v] : 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) repack_wtp_kernel(const float *__restrict__ w, bf16 *__restrict__ Wtp, int Cs, int Cl, int Clp, int Csp, int kk) {
+    int64_t total = (int64_t)kk * Clp * Csp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cs = (int)(i % Csp);
+        int64_t t = i / Csp;
+        int cl = (int)(t % Clp), tap = (int)(t / Clp);
+        Wtp[i] = __float2bfloat16((cs < Cs && cl < Cl) ? w[((int64_t)cs * Cl + cl) * kk + tap] : 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) unpack_grad_add_kernel(const float *__restrict__ g, float *__restrict__ gw, int Cs, int Cl, int Clp, int kk) {
+    int64_t total = (int64_t)Cs * Cl * kk;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int tap = (int)(i % kk);
+        int64_t t = i / kk;
+        int cl = (int)(t % Cl), cs = (int)(t / Cl);
+        gw[i] += g[((int64_t)cs * kk + tap) * Clp + cl];
+    }
+}
+
+}  // namespace
+
+#define LAUNCH_1D(s, kern, total, ...) do { int64_t _t = (total); if (_t > 0) { kern<<<bw_grid(s, _t, 256), 256, 0, (s)->stream>>>(__VA_ARGS__); CK_LAUNCH(s); } } while (0)
+
+int tc_nchw_to_nhwc(cenn_state *s, const float *src, bf16 *dst, int N, int C, int H, int W, int Cp) {
+    LAUNCH_1D(s, nchw_to_nhwc_kernel, (int64_t)N * H * W * Cp, src, dst, N, C, H * W, Cp); return 0;
+}
+int tc_nhwc_to_nchw(cenn_state *s, const bf16 *src, float *dst, int N, int C, int H, int W, int Cp, const float *) {
+    LAUNCH_1D(s, nhwc_to_nchw_kernel, (int64_t)N * C * H * W, src, dst, N, C, H * W, Cp); return 0;
+}
+int tc_repack_wf(cenn_state *s, const float *w, bf16 *Wf, int Cs, int Cl, int Clp, int kk) {
+    LAUNCH_1D(s, repack_wf_kernel, (int64_t)Cs * kk * Clp, w, Wf, Cs, Cl, Clp, kk); return 0;
+}
+int tc_repack_wt(cenn_state *s, const float *w, bf16 *Wt, int Cs, int Cl, int Csp, int cl_rows) {
+    LAUNCH_1D(s, repack_wt_kernel, (int64_t)16 * cl_rows * Csp, w, Wt, Cs, Cl, Csp, cl_rows); return 0;
+}
+int tc_repack_wtp(cenn_state *s, const float *w, bf16 *Wtp, int Cs, int Cl, int Clp, int Csp, int kk) {
+    LAUNCH_1D(s, repack_wtp_kernel, (int64_t)kk * Clp * Csp, w, Wtp, Cs, Cl, Clp, Csp, kk); return 0;
+}
+int tc_unpack_grad_add(cenn_state *s, const float *g, float *gw, int Cs, int Cl, int Clp, int kk) {
+    LAUNCH_1D(s, unpack_grad_add_kernel, (int64_t)Cs * Cl * kk, g, gw, Cs, Cl, Clp, kk); return 0;
+}
+
+// ------------------------------------------------------------------ P1: fprop-type
+int tc_fprop_s2(cenn_state *s, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep) {
+    REQUIRE(Clp % 64 == 0 && Csp % 8 == 0, "tc_fprop_s2: Clp must be a multiple of 64 and Csp of 8 (got %d, %d)", Clp, Csp);
+    int bw, bh, bn;
+    choose_box(w, h, 128, bw, bh, bn);
+    CUtensorMap tmA, tmB;
+    if (map_gather(&tmA, L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
+    tc::GatherGemmParams p = {};
+    p.box_w = bw; p.box_h = bh; p.box_n = bn;
+    p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
+    int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
+    int BN = pick_bn(Cs, m_tiles, s->sm_count);
+    if (map_2d(&tmB, Wf, (uint64_t)16 * Clp, (uint64_t)Cs, BN)) return 1;
+    int chunks = Clp / 64;
+    std::vector<tc::KbDesc> kb;
+    for (int t = 0; t < 16; ++t) {
+        int u = t / 4, v = t % 4;
+        for (int c = 0; c < chunks; ++c) {
+            tc::KbDesc d = {};
+            d.a0 = PYS[v] * Clp + c * 64; d.a1 = DYS[v]; d.a2 = PYS[u]; d.a3 = DYS[u];
+            d.b0 = t * Clp + c * 64; d.b1 = 0;
+            kb.push_back(d);
+        }
+    }
+    p.kb = kb_upload(s, kb); if (!p.kb) return 1;
+    p.num_kb = (int)kb.size();
+    p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cs;
+    p.sX = Csp; p.sY = (long long)w * Csp; p.sN = (long long)h * w * Csp;
+    fill_epilogue(p, ep, S);
+    return launch_gather_bn(s, BN, tmA, tmB, p, dim3(m_tiles, (Cs + BN - 1) / BN, 1));
+}
+
+// ------------------------------------------------------------------ P2: dgrad-type (4 sub-pixel phases)
+int tc_dgrad_s2(cenn_state *s, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep) {
+    REQUIRE(Csp % 64 == 0 && Clp % 8 == 0, "tc_dgrad_s2: Csp must be a multiple of 64 and Clp of 8 (got %d, %d)", Csp, Clp);
+    int bw, bh, bn;
+    choose_box(w, h, 128, bw, bh, bn);
+    CUtensorMap tmA, tmB;
+    if (map_plain(&tmA, S, N, h, w, Csp, bw, bh, bn)) return 1;
+    tc::GatherGemmParams p = {};
+    p.box_w = bw; p.box_h = bh; p.box_n = bn;
+    p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
+    int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
+    int BN = pick_bn(Cl, m_tiles * 4, s->sm_count);
+    if (map_2d(&tmB, Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
+    int chunks = Csp / 64;
+    std::vector<tc::KbDesc> kb;
+    for (int ph = 0; ph < 4; ++ph) {
+        int py = ph >> 1, px = ph & 1;
+        for (int ab = 0; ab < 4; ++ab) {
+            int a = ab >> 1, b = ab & 1;
+            for (int c = 0; c < chunks; ++c) {
+                tc::KbDesc d = {};
+                d.a0 = c * 64; d.a1 = DYP[px][b]; d.a2 = 0; d.a3 = DYP[py][a];
+                d.b0 = ab * Csp + c * 64; d.b1 = ph * cl_rows;
+                kb.push_back(d);
+            }
+        }
+    }
+    p.kb = kb_upload(s, kb); if (!p.kb) return 1;
+    p.num_kb = 4 * chunks;
+    p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cl;
+    int W2 = 2 * w, H2 = 2 * h;
+    p.sX = 2LL * Clp; p.sY = 2LL * W2 * Clp; p.sN = (long long)H2 * W2 * Clp;
+    for (int ph = 0; ph < 4; ++ph) p.phase_off[ph] = ((long long)(ph >> 1) * W2 + (ph & 1)) * Clp;
+    fill_epilogue(p, ep, L);
+    return launch_gather_bn(s, BN, tmA, tmB, p, dim3(m_tiles, (Cl + BN - 1) / BN, 4));
+}
+
+// ------------------------------------------------------------------ P4: plain GEMM
+int tc_gemm(cenn_state *s, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep) {
+    REQUIRE(K % 8 == 0, "tc_gemm: K must be a multiple of 8 (got %d)", K);
+    CUtensorMap tmA, tmB;
+    uint64_t dims[5] = {(uint64_t)K, (uint64_t)M, 1, 1, 1};
+    uint64_t st[4] = {(uint64_t)K * 2, (uint64_t)K * 2 * M, (uint64_t)K * 2 * M, (uint64_t)K * 2 * M};
+    uint32_t box[5] = {64, 128, 1, 1, 1};
+    if (make_map(&tmA, A, 5, dims, st, box)) return 1;
+    tc::GatherGemmParams p = {};
+    p.box_w = 128; p.box_h = 1; p.box_n = 1;
+    p.tiles_x = (M + 127) / 128; p.tiles_y = 1;
+    int m_tiles = p.tiles_x;
+    int BN = pick_bn(Nc, m_tiles, s->sm_count);
+    if (map_2d(&tmB, B, (uint64_t)K, (uint64_t)Nc, BN)) return 1;
+    int nkb = (K + 63) / 64;
+    std::vector<tc::KbDesc> kb(nkb);
+    for (int i = 0; i < nkb; ++i) { kb[i] = tc::KbDesc{}; kb[i].a0 = i * 64; kb[i].b0 = i * 64; }
+    p.kb = kb_upload(s, kb); if (!p.kb) return 1;
+    p.num_kb = nkb;
+    p.out_w = M; p.out_h = 1; p.out_n = 1; p.n_valid = Nc;
+    p.sX = ldo; p.sY = 0; p.sN = 0;
+    fill_epilogue(p, ep, out);
+    return launch_gather_bn(s, BN, tmA, tmB, p, dim3(m_tiles, (Nc + BN - 1) / BN, 1));
+}
+
+// ------------------------------------------------------------------ P3 / P5: wgrad
+static int wgrad_common(cenn_state *s, const CUtensorMap &tmL, const CUtensorMap &tmS, tc::WgradParams &p, int num_taps, int Cs, int Clp,
+                        int num_kb_total) {
+    int chunks = Clp / 64;
+    int row_blocks = num_taps * chunks;
+    int m_tiles = (row_blocks + 1) / 2;
+    int BN = Cs > 128 ? 256 : (Cs > 64 ? 128 : 64);
+    int n_tiles = (Cs + BN - 1) / BN;
+    int tiles = m_tiles * n_tiles;
+    int splits = (2 * s->sm_count + tiles - 1) / tiles;
+    int max_splits = (num_kb_total + 3) / 4;            // at least 4 k-blocks (256 pixels) per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (!p.accumulate) splits = 1;
+    p.num_kb_total = num_kb_total;
+    p.kb_per_split = (num_kb_total + splits - 1) / splits;
+    splits = (num_kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.chunks_per_tap = chunks;
+    p.n_chunks = BN / 64;
+    dim3 grid(m_tiles, n_tiles, splits);
+    switch (BN) {
+        case 64: return launch_wgrad<64>(s, tmL, tmS, p, grid, p.kb_per_split);
+        case 128: return launch_wgrad<128>(s, tmL, tmS, p, grid, p.kb_per_split);
+        default: return launch_wgrad<256>(s, tmL, tmS, p, grid, p.kb_per_split);
+    }
+}
+
+int tc_wgrad_s2(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int N, int h, int w, int Cs, int Csp, int Clp, float scale, int accumulate) {
+    REQUIRE(Clp % 64 == 0 && Csp % 8 == 0, "tc_wgrad_s2: Clp must be a multiple of 64 and Csp of 8 (got %d, %d)", Clp, Csp);
+    int bw, bh, bn;
+    choose_box(w, h, 64, bw, bh, bn);
+    CUtensorMap tmL, tmS;
+    if (map_gather(&tmL, L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
+    if (map_plain(&tmS, S, N, h, w, Csp, bw, bh, bn)) return 1;
+    tc::WgradParams p = {};
+    p.box_w = bw; p.box_h = bh; p.box_n = bn;
+    p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
+    int tiles_n = (N + bn - 1) / bn;
+    for (int t = 0; t < 16; ++t) {
+        int u = t / 4, v = t % 4;
+        p.gx0[t] = PYS[v] * Clp; p.gdx[t] = DYS[v]; p.g2[t] = PYS[u]; p.gdy[t] = DYS[u];
+    }
+    p.num_taps = 16;
+    p.cl_stride = Clp; p.cl_valid = Clp; p.cs_valid = Cs; p.out_cs_stride = 16LL * Clp;
+    p.out = gW; p.scale = scale; p.accumulate = accumulate;
+    return wgrad_common(s, tmL, tmS, p, 16, Cs, Clp, p.tiles_x * p.tiles_y * tiles_n);
+}
+
+int tc_wgrad_plain(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int M, int Cs, int Csp, int Clp, float scale, int accumulate) {
+    REQUIRE(Clp % 64 == 0 && Csp % 8 == 0, "tc_wgrad_plain: Clp must be a multiple of 64 and Csp of 8 (got %d, %d)", Clp, Csp);
+    CUtensorMap tmL, tmS;
+    if (map_plain(&tmL, L, 1, 1, M, Clp, 64, 1, 1)) return 1;
+    if (map_plain(&tmS, S, 1, 1, M, Csp, 64, 1, 1)) return 1;
+    tc::WgradParams p = {};
+    p.box_w = 64; p.box_h = 1; p.box_n = 1;
+    p.tiles_x = (M + 63) / 64; p.tiles_y = 1;
+    p.num_taps = 1;
+    p.cl_stride = Clp; p.cl_valid = Clp; p.cs_valid = Cs; p.out_cs_stride = Clp;
+    p.out = gW; p.scale = scale; p.accumulate = accumulate;
+    return wgrad_common(s, tmL, tmS, p, 1, Cs, Clp, p.tiles_x);
+}
+
+// ------------------------------------------------------------------ NCHW fp32 wrappers (op-level ABI, CENN_BF16)
+namespace {
+struct Bump {          // bump allocator over the state's workspace
+    uint8_t *base; size_t off = 0, cap;
+    template <typename T> T *take(size_t n) { off = (off + 255) & ~size_t(255); T *p = reinterpret_cast<T *>(base + off); off += n * sizeof(T); return p; }
+};
+size_t al(size_t b) { return (b + 255) & ~size_t(255); }
+bool is_s2(int kH, int kW, int dH, int dW, int pH, int pW, int H, int W) {
+    return kH == 4 && kW == 4 && dH == 2 && dW == 2 && pH == 1 && pW == 1 && (H % 2 == 0) && (W % 2 == 0) && H >= 2 && W >= 2;
+}
+bool is_valid4(int kH, int kW, int dH, int dW, int pH, int pW, int H, int W) {   // 4x4 -> 1x1 bottleneck / head
+    return kH == 4 && kW == 4 && dH == 1 && dW == 1 && pH == 0 && pW == 0 && H == 4 && W == 4;
+}
+}  // namespace
+
+int tc_conv_fprop_nchw(cenn_state *s, const float *x, const float *w, const float *bias, float *out,
+                       int N, int C, int H, int W, int O, int kH, int kW, int dH, int dW, int pH, int pW) {
+    bool s2 = is_s2(kH, kW, dH, dW, pH, pW, H, W), v4 = is_valid4(kH, kW, dH, dW, pH, pW, H, W);
+    if (!s2 && !v4) return 1;
+    int Clp = round_up(C, 64), Op = round_up(O, 8);
+    int h = s2 ? H / 2 : 1, wd = s2 ? W / 2 : 1;
+    size_t need = al((size_t)N * H * W * Clp * 2) + al((size_t)O * 16 * Clp * 2) + al((size_t)N * h * wd * Op * 2) + 4096;
+    uint8_t *ws = (uint8_t *)cenn_workspace(s, need);
+    if (!ws) return -1;
+    Bump b{ws, 0, need};
+    bf16 *xl = b.take<bf16>((size_t)N * H * W * Clp), *wf = b.take<bf16>((size_t)O * 16 * Clp), *so = b.take<bf16>((size_t)N * h * wd * Op);
+    if (tc_nchw_to_nhwc(s, x, xl, N, C, H, W, Clp) || tc_repack_wf(s, w, wf, O, C, Clp, 16)) return -1;
+    TcEpilogue ep; ep.bias = bias;
+    int rc = s2 ? tc_fprop_s2(s, xl, wf, so, N, h, wd, O, Op, Clp, ep) : tc_gemm(s, xl, wf, so, N, O, 16 * Clp, Op, ep);
+    if (rc) return -1;
+    if (tc_nhwc_to_nchw(s, so, out, N, O, h, wd, Op, nullptr)) return -1;
+    return 0;
+}
+
+int tc_conv_dgrad_nchw(cenn_state *s, const float *gy, const float *w, const float *bias, float *gx,
+                       int N, int C, int H, int W, int O, int kH, int kW, int dH, int dW, int pH, int pW) {
+    bool s2 = is_s2(kH, kW, dH, dW, pH, pW, H, W), v4 = is_valid4(kH, kW, dH, dW, pH, pW, H, W);
+    if (!s2 && !v4) return 1;
+    int Csp = round_up(O, 64), Clp = round_up(C, 8);
+    int h = s2 ? H / 2 : 1, wd = s2 ? W / 2 : 1;
+    size_t wbytes = s2 ? (size_t)16 * Clp * Csp * 2 : (size_t)16 * Clp * Csp * 2;
+    size_t need = al((size_t)N * h * wd * Csp * 2) + al(wbytes) + al((size_t)N * H * W * Clp * 2) + 4096;
+    uint8_t *ws = (uint8_t *)cenn_workspace(s, need);
+    if (!ws) return -1;
+    Bump b{ws, 0, need};
+    bf16 *gs = b.take<bf16>((size_t)N * h * wd * Csp), *wt = b.take<bf16>(wbytes / 2), *lo = b.take<bf16>((size_t)N * H * W * Clp);
+    if (tc_nchw_to_nhwc(s, gy, gs, N, O, h, wd, Csp)) return -1;
+    TcEpilogue ep; ep.bias = bias;
+    int rc;
+    if (s2) {
+        if (tc_repack_wt(s, w, wt, O, C, Csp, Clp)) return -1;
+        rc = tc_dgrad_s2(s, gs, wt, lo, N, h, wd, Csp, C, Clp, Clp, ep);
+    } else {
+        // gx[n, (t, c)] = sum_o gy[n, o] * w[o][c][t]; bias (full-conv fprop) is per c -> expand handled by caller path below
+        if (tc_repack_wtp(s, w, wt, O, C, Clp, Csp, 16)) return -1;
+        if (bias) {
+            // per-(t,c) bias vector = bias[c] repeated over the 16 taps
+            float *bexp = (float *)cenn_workspace2(s, (size_t)16 * Clp * sizeof(float));
+            if (!bexp) return -1;
+            std::vector<float> hb(16 * Clp, 0.f), hbias(C);
+            if (cudaMemcpyAsync(hbias.data(), bias, C * sizeof(float), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return -1;
+            cudaStreamSynchronize(s->stream);
+            for (int t = 0; t < 16; ++t) for (int c = 0; c < C; ++c) hb[t * Clp + c] = hbias[c];
+            cudaMemcpyAsync(bexp, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+            cudaStreamSynchronize(s->stream);
+            ep.bias = bexp;
+        }
+        rc = tc_gemm(s, gs, wt, lo, N, 16 * Clp, Csp, 16 * Clp, ep);
+    }
+    if (rc) return -1;
+    if (tc_nhwc_to_nchw(s, lo, gx, N, C, H, W, Clp, nullptr)) return -1;
+    return 0;
+}
+
+int tc_conv_wgrad_nchw(cenn_state *s, const float *x, const float *gy, float *gw,
+                       int N, int C, int H, int W, int O, int kH, int kW, int dH, int dW, int pH, int pW, float scale, int) {
+    bool s2 = is_s2(kH, kW, dH, dW, pH, pW, H, W), v4 = is_valid4(kH, kW, dH, dW, pH, pW, H, W);
+    if (!s2 && !v4) return 1;
+    int Clp = round_up(C, 64), Csp = round_up(O, 8);
+    int h = s2 ? H / 2 : 1, wd = s2 ? W / 2 : 1;
+    size_t need = al((size_t)N * H * W * Clp * 2) + al((size_t)N * h * wd * Csp * 2) + al((size_t)O * 16 * Clp * 4) + 4096;
+    uint8_t *ws = (uint8_t *)cenn_workspace(s, need);
+    if (!ws) return -1;
+    Bump b{ws, 0, need};
+    bf16 *xl = b.take<bf16>((size_t)N * H * W * Clp), *gs = b.take<bf16>((size_t)N * h * wd * Csp);
+    float *g = b.take<float>((size_t)O * 16 * Clp);
+    if (tc_nchw_to_nhwc(s, x, xl, N, C, H, W, Clp) || tc_nchw_to_nhwc(s, gy, gs, N, O, h, wd, Csp)) return -1;
+    if (cudaMemsetAsync(g, 0, (size_t)O * 16 * Clp * 4, s->stream) != cudaSuccess) return -1;
+    int rc = s2 ? tc_wgrad_s2(s, gs, xl, g, N, h, wd, O, Csp, Clp, scale, 1) : tc_wgrad_plain(s, gs, xl, g, N, O, Csp, 16 * Clp, scale, 1);
+    if (rc) return -1;
+    if (tc_unpack_grad_add(s, g, gw, O, C, Clp, 16)) return -1;
+    return 0;
+}

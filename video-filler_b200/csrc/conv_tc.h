@@ -1,9 +1,52 @@
-// conv_tc.h -- entry points of the BF16 tcgen05 implicit-GEMM convolution path (conv_tc.cu).
-// NCHW-fp32 wrappers (op-level ABI, precision CENN_BF16) return 0 = done, >0 = shape not handled
-// by the tensor-core path (caller runs the fp32 SIMT kernel instead), <0 = error (message set).
+// conv_tc.h -- BF16 tcgen05 implicit-GEMM convolution path (conv_tc.cu): NHWC-bf16 primitives used by the
+// whole-step executor, and NCHW-fp32 wrappers used by the op-level ABI in precision mode CENN_BF16.
+//
+// Naming: every 4x4 / stride-2 / pad-1 layer relates a "small" tensor S [N,h,w,Cs] and a "large" tensor
+// L [N,2h,2w,Cl] (conv: S = output, L = input; full conv: S = input, L = output).  THNN weights are
+// [Cs][Cl][4][4] for both module types; the internal "master" layout is [Cs][tap][Clp] (tap = u*4+v).
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
+typedef __nv_bfloat16 bf16;
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct TcEpilogue {
+    const float *bias = nullptr;   // per output channel
+    float *stats = nullptr;        // [2][stats_stride] fp32 sum / sum-of-squares accumulators (atomics)
+    int stats_stride = 0;
+    int act = 0;                   // tc::ACT_*
+    float act_param = 0.f;
+    float *out_f32 = nullptr;      // optional fp32 copy of the output (same NHWC addressing)
+    bool no_bf16 = false;
+};
+
+// ---- NHWC bf16 primitives (all return 0 on success, 1 on error with message set) -------------------------
+// P1: S[pix,cs] = sum_{tap,cl} L[gather_tap(pix),cl] * Wf[cs][tap][cl]      (conv fprop, full-conv dgrad)
+int tc_fprop_s2(cenn_state *s, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep);
+// P2: L[pix',cl] = sum_{ab,cs} S[pix+d_ab,cs] * Wt[phase][cl][ab][cs]     (conv dgrad, full-conv fprop)
+int tc_dgrad_s2(cenn_state *s, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep);
+// P3: gW[cs][tap][cl] (+)= scale * sum_pix S[pix,cs] * L[gather_tap(pix),cl]
+int tc_wgrad_s2(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int N, int h, int w, int Cs, int Csp, int Clp, float scale, int accumulate);
+// P4: out[M,Nc] = A[M,K] * B[Nc,K]^T  (both K-major; K multiple of 8; ldo = output row stride in elements)
+int tc_gemm(cenn_state *s, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep);
+// P5: gW[cs][cl] (+)= scale * sum_m S[m,cs] * L[m,cl]   (S: [M,Csp], L: [M,Clp], out row stride = Clp)
+int tc_wgrad_plain(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int M, int Cs, int Csp, int Clp, float scale, int accumulate);
+
+// ---- layout / repack kernels --------------------------------------------------------------------------------
+int tc_nchw_to_nhwc(cenn_state *s, const float *src, bf16 *dst, int N, int C, int H, int W, int Cp);
+int tc_nhwc_to_nchw(cenn_state *s, const bf16 *src, float *dst, int N, int C, int H, int W, int Cp, const float *bias_unused);
+// THNN weight [Cs][Cl][kk] fp32 -> Wf bf16 [Cs][kk][Clp]
+int tc_repack_wf(cenn_state *s, const float *w, bf16 *Wf, int Cs, int Cl, int Clp, int kk);
+// THNN weight [Cs][Cl][16] -> Wt bf16 [4 phases][cl_rows][4 ab][Csp]
+int tc_repack_wt(cenn_state *s, const float *w, bf16 *Wt, int Cs, int Cl, int Csp, int cl_rows);
+// THNN weight [Cs][Cl][kk] -> plain transpose Wtp bf16 [(t,cl) rows = kk*Clp][Csp]
+int tc_repack_wtp(cenn_state *s, const float *w, bf16 *Wtp, int Cs, int Cl, int Clp, int Csp, int kk);
+// master-layout gradient [Cs][kk][Clp] fp32 -> THNN gradWeight[Cs][Cl][kk] += g
+int tc_unpack_grad_add(cenn_state *s, const float *g, float *gradWeight, int Cs, int Cl, int Clp, int kk);
+
+// ---- NCHW fp32 wrappers: 0 = done, >0 = shape not handled (caller uses the fp32 SIMT kernel), <0 = error ----
 int tc_conv_fprop_nchw(cenn_state *s, const float *x, const float *w, const float *bias, float *out,
                        int N, int C, int H, int W, int O, int kH, int kW, int dH, int dW, int pH, int pW);
 int tc_conv_dgrad_nchw(cenn_state *s, const float *gy, const float *w, const float *bias, float *gx,

@@ -1,0 +1,427 @@
+// tc_gemm.cuh -- hand-written sm_100a implicit-GEMM kernels: TMA (cp.async.bulk.tensor) stages NHWC
+// bf16 tiles into 128B-swizzled shared memory, one elected thread issues tcgen05.mma (kind::f16,
+// cta_group::1, 128 x N x 16) into a TMEM accumulator, four epilogue warps read it back with
+// tcgen05.ld.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue.
+//
+//  * gather_gemm_kernel  (both operands K-major): conv fprop-type, conv dgrad-type (4 sub-pixel phases
+//    in grid.z) and plain GEMMs.  A tile = one TMA box of 128 pixels x 64 channels per k-block, taken from a
+//    5-D view of the activation tensor at (tile origin + per-k-block offset); zero padding = TMA OOB fill.
+//  * wgrad_gemm_kernel   (both operands MN-major): gW[cs][tap][cl] = sum_pix S[pix,cs] * L[gather_tap(pix),cl];
+//    K runs over pixels, split across CTAs (grid.z), fp32 result stored or atomically accumulated.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (-> launch error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("cenn: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (SM100 "version 1"), SWIZZLE_128B; addresses/offsets in 16-byte units.
+//   K-major : rows of 128 B (64 bf16 of K), 8-row atoms of 1024 B -> SBO = 1024, LBO unused (1)
+//   MN-major: rows of 128 B (64 bf16 of M/N) per K index, 8 K-rows = 1024 B -> SBO = 1024,
+//             LBO = byte distance between consecutive 64-element M/N chunks
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version = 1 (Blackwell)
+    d |= (uint64_t)2 << 61;   // layout type SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: D fp32, A/B bf16
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ kernel parameters
+struct KbDesc {        // per k-block TMA coordinates (offsets added to the tile origin)
+    int a0, a1, a2, a3;  // A box: dim0 (channel) start, dim1 (x) offset, dim2 (parity/dummy) coord, dim3 (y) offset
+    int b0, b1;          // B box: dim0 (k) start, dim1 (row) offset added to the n-tile origin
+    int pad0, pad1;
+};
+
+enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
+
+struct GatherGemmParams {
+    const KbDesc *kb;        // [phases][num_kb]
+    int num_kb;
+    int box_w, box_h, box_n; // pixels per M tile (product == 128)
+    int tiles_x, tiles_y;    // tile grid within an image batch slab: m-tile -> (tx, ty, tn)
+    int out_w, out_h, out_n; // logical extent of the output pixel grid (for masking)
+    int n_valid;             // valid output channels (columns >= n_valid are dropped)
+    // output addressing: elem offset = n*sN + y*sY + x*sX + phase_off[phase] + column
+    long long sN, sY, sX;
+    long long phase_off[4];
+    __nv_bfloat16 *out_bf16; // [opt] bf16 output
+    float *out_f32;          // [opt] fp32 output (same addressing)
+    const float *bias;       // [opt] per-column
+    float *stats;            // [opt] per-column sum / sum of squares (fp32 atomics): stats[c], stats[stats_stride + c]
+    int stats_stride;
+    int act;                 // applied after bias, before the store (stats are taken before the activation)
+    float act_param;
+};
+
+struct WgradParams {
+    int num_kb_total;        // pixel blocks (64 pixels each)
+    int kb_per_split;
+    int box_w, box_h, box_n; // pixels per k-block (product == 64)
+    int tiles_x, tiles_y;    // pixel-block grid: kb -> (tx, ty, tn)
+    int chunks_per_tap;      // Cl / 64 (row-blocks per tap)
+    int num_taps;            // taps in the output (16 for 4x4 windows, 1 for plain GEMM)
+    int cl_stride;           // row length of one tap in the output (= Cl padded, master layout [cs][tap][cl])
+    int cl_valid;            // valid cl per tap
+    int cs_valid;
+    int n_chunks;            // cs chunks (64 each) in this N tile = BN/64
+    long long out_cs_stride; // taps * cl_stride
+    float *out;              // fp32 [cs][tap][cl]
+    float scale;
+    int accumulate;          // 1: red.add (accumulate / split-K), 0: plain store (requires a single split)
+    // gather geometry for L per tap: coords = (chunk*64 + gx0[tap], x0 + gdx[tap], g2[tap], y0 + gdy[tap], n0)
+    int gx0[16], gdx[16], g2[16], gdy[16];
+};
+
+static constexpr int GEMM_THREADS = 192;
+
+// ------------------------------------------------------------------ K-major gather GEMM
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GatherGemmParams p, int stages) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr uint32_t A_BYTES = 128 * 128;       // 128 rows x 64 bf16
+    constexpr uint32_t B_BYTES = BN * 128;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *tiles = smem;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)stages * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + stages;
+    uint64_t *acc_bar = empty_bar + stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+    float *col_acc = reinterpret_cast<float *>(tmem_slot + 2);          // [2][BN] per-CTA column sums for BN statistics
+    float *stage_f = col_acc + 2 * BN;                                  // [4 warps][32][33] transposition buffer
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int phase_id = blockIdx.z;
+    const int mt = blockIdx.x, nt = blockIdx.y;
+    const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+    const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+    const KbDesc *kbd = p.kb + (size_t)phase_id * p.num_kb;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) col_acc[i] = 0.f;
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                int s = kb % stages;
+                uint32_t ph = (uint32_t)(kb / stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                KbDesc d = kbd[kb];
+                uint8_t *a_dst = tiles + (size_t)s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                tma_load_5d(&tmA, &full_bar[s], a_dst, d.a0, x0 + d.a1, d.a2, y0 + d.a3, n0);
+                tma_load_2d(&tmB, &full_bar[s], b_dst, d.b0, nt * BN + d.b1);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            int s = kb % stages;
+            uint32_t ph = (uint32_t)(kb / stages) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide k-block; +32 B inside the swizzle atom
+                    uint64_t ad = make_desc(a_addr + k * 32, 16, 1024), bd = make_desc(b_addr + k * 32, 16, 1024);
+                    umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
+                if (kb == p.num_kb - 1) umma_commit(acc_bar);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 (= tile rows)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int rx = row % p.box_w, ry = (row / p.box_w) % p.box_h, rn = row / (p.box_w * p.box_h);
+        const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
+        const bool row_ok = px < p.out_w && py < p.out_h && pn < p.out_n;
+        const long long obase = (long long)pn * p.sN + (long long)py * p.sY + (long long)px * p.sX + p.phase_off[phase_id];
+        float *my_stage = stage_f + (size_t)(warp - 2) * 32 * 33;
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            const int colbase = nt * BN + c0;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float f = __uint_as_float(r[j]);
+                if (p.bias && colbase + j < p.n_valid) f += __ldg(p.bias + colbase + j);
+                v[j] = f;
+            }
+            if (p.stats) {
+                // transpose through smem so that lane j sums column j over this warp's 32 rows
+#pragma unroll
+                for (int j = 0; j < 32; ++j) my_stage[lane * 33 + j] = row_ok ? v[j] : 0.f;
+                __syncwarp();
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) { float t = my_stage[i * 33 + lane]; s1 += t; s2 += t * t; }
+                atomicAdd(&col_acc[c0 + lane], s1);
+                atomicAdd(&col_acc[BN + c0 + lane], s2);
+                __syncwarp();
+            }
+            if (p.act != ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float f = v[j];
+                    if (p.act == ACT_LEAKY) f = f > 0.f ? f : f * p.act_param;
+                    else if (p.act == ACT_RELU) f = f > 0.f ? f : 0.f;
+                    else if (p.act == ACT_TANH) f = tanhf(f);
+                    else if (p.act == ACT_SIGMOID) f = 1.f / (1.f + __expf(-f));
+                    v[j] = f;
+                }
+            }
+            if (row_ok) {
+                if (p.out_bf16) {
+                    __nv_bfloat16 *o = p.out_bf16 + obase + colbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (colbase + j + 8 <= p.n_valid) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                            *reinterpret_cast<uint4 *>(o + j) = pk;
+                        } else {
+                            for (int jj = j; jj < j + 8; ++jj) if (colbase + jj < p.n_valid) o[jj] = __float2bfloat16(v[jj]);
+                        }
+                    }
+                }
+                if (p.out_f32) {
+                    float *o = p.out_f32 + obase + colbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (colbase + j + 4 <= p.n_valid) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        else for (int jj = j; jj < j + 4; ++jj) if (colbase + jj < p.n_valid) o[jj] = v[jj];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (p.stats) {
+        for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+            int c = nt * BN + i;
+            if (c < p.n_valid) { atomicAdd(p.stats + c, col_acc[i]); atomicAdd(p.stats + p.stats_stride + c, col_acc[BN + i]); }
+        }
+    }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------ MN-major wgrad GEMM
+// M tile = 128 rows = 2 row-blocks of 64 (tap, cl-chunk); N tile = BN columns of cs; K = pixels.
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmS, const WgradParams p, int stages) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr uint32_t BOX_BYTES = 64 * 128;            // 64 pixels x 64 channels bf16
+    constexpr uint32_t A_BYTES = 2 * BOX_BYTES;
+    constexpr uint32_t B_BYTES = (BN / 64) * BOX_BYTES;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *tiles = smem;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)stages * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + stages;
+    uint64_t *acc_bar = empty_bar + stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x, nt = blockIdx.y, split = blockIdx.z;
+    const int kb_begin = split * p.kb_per_split;
+    const int kb_end = min(p.num_kb_total, kb_begin + p.kb_per_split);
+    const int nkb = kb_end - kb_begin;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmL);
+        prefetch_tmap(&tmS);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (nkb <= 0) { __syncthreads(); if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS); return; }
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                int kb = kb_begin + i;
+                int s = i % stages;
+                uint32_t ph = (uint32_t)(i / stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                int tx = kb % p.tiles_x, ty = (kb / p.tiles_x) % p.tiles_y, tn = kb / (p.tiles_x * p.tiles_y);
+                int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+                uint8_t *a_dst = tiles + (size_t)s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int rb = mt * 2 + h;
+                    int tap = rb / p.chunks_per_tap, chunk = rb - tap * p.chunks_per_tap;
+                    tap = min(tap, 15);
+                    tma_load_5d(&tmL, &full_bar[s], a_dst + h * BOX_BYTES, chunk * 64 + p.gx0[tap], x0 + p.gdx[tap], p.g2[tap], y0 + p.gdy[tap], n0);
+                }
+                for (int c = 0; c < BN / 64; ++c)
+                    tma_load_5d(&tmS, &full_bar[s], b_dst + c * BOX_BYTES, (nt * (BN / 64) + c) * 64, x0, 0, y0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(128, BN, 1, 1);
+        for (int i = 0; i < nkb; ++i) {
+            int s = i % stages;
+            uint32_t ph = (uint32_t)(i / stages) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {   // 16 pixels (K) per MMA = 2 groups of 8 K-rows = 2048 B
+                    uint64_t ad = make_desc(a_addr + k * 2048, BOX_BYTES, 1024), bd = make_desc(b_addr + k * 2048, BOX_BYTES, 1024);
+                    umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);
+                if (i == nkb - 1) umma_commit(acc_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;            // row within the M tile
+        const int rb = mt * 2 + (row >> 6);
+        const int tap = rb / p.chunks_per_tap, chunk = rb - tap * p.chunks_per_tap;
+        const int cl = chunk * 64 + (row & 63);
+        const bool row_ok = tap < p.num_taps && cl < p.cl_valid;
+        float *obase = p.out + (long long)tap * p.cl_stride + cl;
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    int cs = nt * BN + c0 + j;
+                    if (cs < p.cs_valid) {
+                        float f = __uint_as_float(r[j]) * p.scale;
+                        float *o = obase + (long long)cs * p.out_cs_stride;
+                        if (p.accumulate) atomicAdd(o, f); else *o = f;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+}  // namespace tc
