@@ -224,8 +224,13 @@ CENN_API int cenn_trainer_read_losses(cenn_trainer *t, float *losses_host);
 /* phase-split form for data parallelism: the host inserts all-reduces between phases
  * (phase list and the buffers to reduce are described in DESIGN.md section "multi-GPU") */
 CENN_API int cenn_trainer_grad_buffer(cenn_trainer *t, int net, float **grads_dev, int64_t *count);
+/* phase < 0 starts a step with the given device inputs; phase >= 0 continues it.  Each call runs up to and
+ * including the next synchronisation point and returns; cenn_trainer_sync_info then names the device buffer
+ * (fp32, or 8 doubles for the loss accumulators) that must be summed across ranks before the next call,
+ * or reports done = 1 when the step has finished. */
 CENN_API int cenn_trainer_step_phase(cenn_trainer *t, int phase, const float *a_dev, const float *b_dev,
         const uint8_t *mask_dev);
+CENN_API int cenn_trainer_sync_info(cenn_trainer *t, void **buf_dev, int64_t *count, int *is_double, int *done);
 /* eval-mode generator forward (test_vid_wholeim.lua:180, demo.lua:68): in [B,Cin,F,F] -> out, host fp32 NCHW */
 CENN_API int cenn_trainer_generator_forward_host(cenn_trainer *t, const float *in_host, float *out_host, int batch);
 /* debugging / parity: copy an internal activation or gradient as fp32 NCHW to the host by name */

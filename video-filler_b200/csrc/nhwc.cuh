@@ -1,0 +1,427 @@
+// nhwc.cuh -- HBM-bound kernels of the whole-step executor on NHWC bf16 tensors (channels padded to Cp).
+// 16-byte vector accesses (8 bf16) along the channel axis, per-channel reductions via registers ->
+// shared memory -> one fp32 atomic per channel per CTA, grids sized in multiples of the SM count.
+#pragma once
+#include <type_traits>
+#include "common.cuh"
+#include "conv_tc.h"
+
+namespace nhwc {
+
+enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
+
+struct bf16x8 { __nv_bfloat162 v[4]; };
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+__device__ __forceinline__ float act_fwd(float z, int act, float negval) {
+    if (act == ACT_LEAKY) return z > 0.f ? z : z * negval;
+    if (act == ACT_RELU) return z > 0.f ? z : 0.f;
+    if (act == ACT_TANH) return tanhf(z);
+    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-z));
+    return z;
+}
+// derivative expressed through the stored activation output a (what the in-place Torch modules use)
+__device__ __forceinline__ float act_bwd(float a, int act, float negval) {
+    if (act == ACT_LEAKY) return a > 0.f ? 1.f : negval;
+    if (act == ACT_RELU) return a > 0.f ? 1.f : 0.f;
+    if (act == ACT_TANH) return 1.f - a * a;
+    if (act == ACT_SIGMOID) return a * (1.f - a);
+    return 1.f;
+}
+
+// ---------------------------------------------------------------- input conversion / im2col
+// NCHW (float or uint8) -> NHWC bf16 with Cp channels (pad lanes zero); one thread per pixel
+template <typename T>
+__global__ void __launch_bounds__(256) to_nhwc_kernel(const T *__restrict__ src, bf16 *__restrict__ dst, int N, int C, int HW, int Cp) {
+    int64_t total = (int64_t)N * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int n = (int)(i / HW), pix = (int)(i - (int64_t)n * HW);
+        bf16 *o = dst + i * Cp;
+        for (int c = 0; c < Cp; ++c) {
+            float v = c < C ? (float)src[((int64_t)n * C + c) * HW + pix] : 0.f;
+            if (sizeof(T) == 1) v = v != 0.f ? 1.f : 0.f;
+            o[c] = __float2bfloat16(v);
+        }
+    }
+}
+// NHWC bf16 -> NCHW fp32 (results / debugging)
+__global__ void __launch_bounds__(256) to_nchw_kernel(const bf16 *__restrict__ src, float *__restrict__ dst, int N, int C, int HW, int Cp) {
+    int64_t total = (int64_t)N * C * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int pix = (int)(i % HW);
+        int64_t t = i / HW;
+        int c = (int)(t % C), n = (int)(t / C);
+        dst[i] = __bfloat162float(src[((int64_t)n * HW + pix) * Cp + c]);
+    }
+}
+// explicit im2col of a thin tensor L [N,2h,2w,Cp] (Cp = 4 or 16): col[pix][(tap, c)] for the 4x4/s2/p1 window
+template <int CP>
+__global__ void __launch_bounds__(256) im2col_kernel(const bf16 *__restrict__ L, bf16 *__restrict__ col, int N, int h, int w) {
+    typedef typename std::conditional<CP == 4, uint2, uint4>::type vec_t;     // 4 bf16 = 8 B ; 8 bf16 = 16 B
+    constexpr int VPP = CP * 2 / (int)sizeof(vec_t);                         // vectors per pixel
+    int64_t total = (int64_t)N * h * w * 16 * VPP;
+    const int H2 = 2 * h, W2 = 2 * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int vi = (int)(i % VPP);
+        int64_t t = i / VPP;
+        int tap = (int)(t % 16);
+        int64_t pix = t / 16;
+        int ox = (int)(pix % w), oy = (int)((pix / w) % h), n = (int)(pix / ((int64_t)w * h));
+        int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
+        vec_t v = {};
+        if ((unsigned)iy < (unsigned)H2 && (unsigned)ix < (unsigned)W2)
+            v = reinterpret_cast<const vec_t *>(L + (((int64_t)n * H2 + iy) * W2 + ix) * CP)[vi];
+        reinterpret_cast<vec_t *>(col + (pix * 16 + tap) * CP)[vi] = v;
+    }
+}
+
+// ---------------------------------------------------------------- batch norm
+// sums -> mean / invstd / running stats / (scale, shift); `fold` column groups are summed (G1's GEMM epilogue
+// accumulates per (tap, channel) column).  Zeroes the accumulators for the next use.
+__global__ void bn_finalize_kernel(float *__restrict__ stats, int stats_stride, int fold, int fold_stride, const float *__restrict__ gamma,
+        const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
+        float *__restrict__ invstd, float *__restrict__ scale, float *__restrict__ shift, int C, double n, double momentum, double eps,
+        int update_running) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int f = 0; f < fold; ++f) {
+        s1 += (double)stats[f * fold_stride + c]; s2 += (double)stats[stats_stride + f * fold_stride + c];
+        stats[f * fold_stride + c] = 0.f; stats[stats_stride + f * fold_stride + c] = 0.f;
+    }
+    double m = s1 / n;
+    double S = s2 - s1 * m;
+    if (S < 0) S = 0;
+    double is = 1.0 / sqrt(S / n + eps);
+    mean[c] = (float)m; invstd[c] = (float)is;
+    float sc = (float)(is * (double)gamma[c]);
+    scale[c] = sc; shift[c] = beta[c] - (float)m * sc;
+    if (update_running) {
+        running_mean[c] = (float)(momentum * m + (1.0 - momentum) * (double)running_mean[c]);
+        running_var[c] = (float)(momentum * (S / (n - 1.0)) + (1.0 - momentum) * (double)running_var[c]);
+    }
+}
+__global__ void bn_eval_coef_kernel(const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ running_mean,
+        const float *__restrict__ running_var, float *__restrict__ scale, float *__restrict__ shift, int C, double eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float sc = (float)((double)gamma[c] / sqrt((double)running_var[c] + eps));
+    scale[c] = sc; shift[c] = beta[c] - running_mean[c] * sc;
+}
+// a = act(y * scale[c] + shift[c]); vectors of 8 channels
+__global__ void __launch_bounds__(256) bn_apply_act_kernel(const bf16 *__restrict__ y, bf16 *__restrict__ a, const float *__restrict__ scale,
+        const float *__restrict__ shift, int64_t nvec, int vec_per_pix, int act, float negval) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        int c0 = (int)(i % vec_per_pix) * 8;
+        float f[8];
+        unpack8(reinterpret_cast<const uint4 *>(y)[i], f);
+        float4 s0 = *reinterpret_cast<const float4 *>(scale + c0), s1 = *reinterpret_cast<const float4 *>(scale + c0 + 4);
+        float4 h0 = *reinterpret_cast<const float4 *>(shift + c0), h1 = *reinterpret_cast<const float4 *>(shift + c0 + 4);
+        float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = act_fwd(f[k] * sc[k] + sh[k], act, negval);
+        reinterpret_cast<uint4 *>(a)[i] = pack8(f);
+    }
+}
+
+// Per-channel reduction skeleton: blockDim = (TX channel-vectors, TY pixel lanes); grid = (pixel strips, channel-vector groups).
+// Each thread accumulates NACC values for its 8 channels; lanes are folded through shared memory; one atomic per channel.
+template <int NACC, class F>
+__device__ __forceinline__ void channel_reduce(int64_t npix, int vec_per_pix, float *__restrict__ out, int out_stride, int C_valid, F body) {
+    extern __shared__ float red_sh[];
+    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+    const int vec = blockIdx.y * TX + tx;
+    float acc[NACC][8];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+    if (vec < vec_per_pix)
+        for (int64_t p = (int64_t)blockIdx.x * TY + ty; p < npix; p += (int64_t)gridDim.x * TY) body(p * vec_per_pix + vec, vec * 8, acc);
+    // fold the TY pixel lanes
+    float *sh = red_sh;   // [TY][TX][NACC*8]
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sh[((ty * TX + tx) * NACC + a) * 8 + k] = acc[a][k];
+    __syncthreads();
+    if (ty == 0 && vec < vec_per_pix) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float s = 0.f;
+                for (int l = 0; l < TY; ++l) s += sh[((l * TX + tx) * NACC + a) * 8 + k];
+                int c = vec * 8 + k;
+                if (c < C_valid) atomicAdd(out + a * out_stride + c, s);
+            }
+    }
+}
+
+// BN backward pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * (y - mean[c]),  dz = g * act'(a)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16 *__restrict__ g, const bf16 *__restrict__ a, const bf16 *__restrict__ y,
+        const float *__restrict__ mean, float *__restrict__ sums, int sums_stride, int64_t npix, int vec_per_pix, int C, int act, float negval) {
+    channel_reduce<2>(npix, vec_per_pix, sums, sums_stride, C, [&](int64_t vi, int c0, float (&acc)[2][8]) {
+        float fg[8], fa[8], fy[8];
+        unpack8(reinterpret_cast<const uint4 *>(g)[vi], fg);
+        unpack8(reinterpret_cast<const uint4 *>(a)[vi], fa);
+        unpack8(reinterpret_cast<const uint4 *>(y)[vi], fy);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float dz = fg[k] * act_bwd(fa[k], act, negval);
+            acc[0][k] += dz;
+            acc[1][k] += dz * (fy[k] - mean[c0 + k]);
+        }
+    });
+}
+// coefficients for pass 2 + BN parameter gradients; zeroes the sums for the next use.
+//   coef[0][c] = s/n, coef[1][c] = invstd^2 * d/n, coef[2][c] = invstd * gamma
+__global__ void bn_bwd_coef_kernel(float *__restrict__ sums, int sums_stride, const float *__restrict__ gamma, const float *__restrict__ invstd,
+        float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = sums[c], d = sums[sums_stride + c], is = invstd[c];
+    sums[c] = 0.f; sums[sums_stride + c] = 0.f;
+    coef[c] = (float)(s / n); coef[C + c] = (float)(is * is * d / n); coef[2 * C + c] = (float)(is * (double)gamma[c]);
+    if (ggamma) ggamma[c] += (float)(d * is);
+    if (gbeta) gbeta[c] += (float)s;
+}
+// BN backward pass 2 (in place on g): g_y = (dz - s/n - (y-mean) * k) * invstd * gamma; optional sum of g_y -> conv gradBias
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, const bf16 *__restrict__ y,
+        const float *__restrict__ mean, const float *__restrict__ coef, float *__restrict__ gbias, int64_t npix, int vec_per_pix, int C,
+        int act, float negval) {
+    channel_reduce<1>(npix, vec_per_pix, gbias, 0, gbias ? C : 0, [&](int64_t vi, int c0, float (&acc)[1][8]) {
+        float fg[8], fa[8], fy[8];
+        unpack8(reinterpret_cast<const uint4 *>(g)[vi], fg);
+        unpack8(reinterpret_cast<const uint4 *>(a)[vi], fa);
+        unpack8(reinterpret_cast<const uint4 *>(y)[vi], fy);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int c = c0 + k;
+            float r = 0.f;
+            if (c < C) {
+                float dz = fg[k] * act_bwd(fa[k], act, negval);
+                r = (dz - coef[c] - (fy[k] - mean[c]) * coef[C + c]) * coef[2 * C + c];
+            }
+            fg[k] = r;
+            acc[0][k] += r;
+        }
+        reinterpret_cast<uint4 *>(g)[vi] = pack8(fg);
+    });
+}
+// activation-only backward (in place on g): g_y = g * act'(a); optional sum -> gradBias
+__global__ void __launch_bounds__(256) act_bwd_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, float *__restrict__ gbias, int64_t npix,
+        int vec_per_pix, int C, int act, float negval) {
+    channel_reduce<1>(npix, vec_per_pix, gbias, 0, gbias ? C : 0, [&](int64_t vi, int c0, float (&acc)[1][8]) {
+        float fg[8], fa[8];
+        unpack8(reinterpret_cast<const uint4 *>(g)[vi], fg);
+        unpack8(reinterpret_cast<const uint4 *>(a)[vi], fa);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { float r = (c0 + k < C) ? fg[k] * act_bwd(fa[k], act, negval) : 0.f; fg[k] = r; acc[0][k] += r; }
+        reinterpret_cast<uint4 *>(g)[vi] = pack8(fg);
+    });
+}
+
+// ---------------------------------------------------------------- discriminator head: 4x4 valid conv to 1 channel + Sigmoid + BCE
+// out[b] = sigmoid(sum_k x[b,k] w[k] + bias): one warp per sample, 16-byte loads
+__global__ void __launch_bounds__(256) head_fwd_kernel(const bf16 *__restrict__ x, const bf16 *__restrict__ w, const float *__restrict__ bias,
+        float *__restrict__ out, int B, int K) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const uint4 *xr = reinterpret_cast<const uint4 *>(x + (int64_t)warp * K), *wr = reinterpret_cast<const uint4 *>(w);
+    float acc = 0.f;
+    for (int i = lane; i < K / 8; i += 32) {
+        float a[8], b[8];
+        unpack8(xr[i], a); unpack8(wr[i], b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(a[k], b[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[warp] = 1.f / (1.f + expf(-(acc + (bias ? bias[0] : 0.f))));
+}
+// BCE against a constant label: loss_acc += -sum(...)/n ; gpre[b] = dL/dx * x(1-x)  (Sigmoid backward)
+__global__ void __launch_bounds__(256) head_bce_kernel(const float *__restrict__ sig, float label, float *__restrict__ gpre, double *__restrict__ loss_acc,
+        int B, double inv_n) {
+    __shared__ double sh[32];
+    double l = 0.0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float x = sig[b];
+        l += (double)(label * logf(x + 1e-12f) + (1.f - label) * logf(1.f - x + 1e-12f));
+        float gx = -(float)inv_n * (label - x) / ((1.f - x + 1e-12f) * (x + 1e-12f));
+        if (gpre) gpre[b] = gx * x * (1.f - x);
+    }
+    l = block_sum(l, sh);
+    if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, -l * inv_n);
+}
+// gx[b,k] = gpre[b] * w[k]
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict__ gpre, const bf16 *__restrict__ w, bf16 *__restrict__ gx, int B, int K) {
+    int64_t nvec = (int64_t)B * K / 8;
+    int kv = K / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        int b = (int)(i / kv), k = (int)(i % kv);
+        float f[8], g = gpre[b];
+        unpack8(reinterpret_cast<const uint4 *>(w)[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= g;
+        reinterpret_cast<uint4 *>(gx)[i] = pack8(f);
+    }
+}
+// gw[k] += sum_b gpre[b] x[b,k] ; gb += sum_b gpre[b]   (grid over k-vectors, loop over b)
+__global__ void __launch_bounds__(128) head_wgrad_kernel(const float *__restrict__ gpre, const bf16 *__restrict__ x, float *__restrict__ gw,
+        float *__restrict__ gb, int B, int K) {
+    int kv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kv < K / 8) {
+        float acc[8] = {};
+        for (int b = 0; b < B; ++b) {
+            float f[8], g = gpre[b];
+            unpack8(reinterpret_cast<const uint4 *>(x + (int64_t)b * K)[kv], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, f[j], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gw[kv * 8 + j] += acc[j];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && gb) { float s = 0.f; for (int b = 0; b < B; ++b) s += gpre[b]; gb[0] += s; }
+}
+
+// ---------------------------------------------------------------- generator losses on NHWC tensors (Cp lanes, C valid)
+// image variant (train.lua:377-400): g = a*df + Wm(y,x) * 2(x-t)/n ; loss_acc += sum (x-t)^2 / n   (vectors of 4 lanes)
+__global__ void __launch_bounds__(256) blend_overlap_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
+        bf16 *__restrict__ g, int64_t npix, int H, int W, int Cp, int C, int ov, float a, float w_in, float w_ring, float two_over_n,
+        double inv_n, double *__restrict__ loss_acc) {
+    __shared__ double sh[32];
+    double l = 0.0;
+    int64_t total = npix * Cp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % Cp);
+        int64_t p = i / Cp;
+        int xx = (int)(p % W), yy = (int)((p / W) % H);
+        float r = 0.f;
+        if (c < C) {
+            bool inner = (yy >= ov && yy < H - ov && xx >= ov && xx < W - ov);
+            float d = __bfloat162float(x[i]) - __bfloat162float(t[i]);
+            l += (double)d * d;
+            r = (df ? __bfloat162float(df[i]) * a : 0.f) + (inner ? w_in : w_ring) * (d * two_over_n);
+        }
+        g[i] = __float2bfloat16(r);
+    }
+    l = block_sum(l, sh);
+    if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, l * inv_n);
+}
+// video variant (train_vid_weighted.lua:485-528): g = a*df + (wtl2 * (m(1-lam)+lam) + wtgdl) * 2(x-t)/n
+__global__ void __launch_bounds__(256) blend_masked_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
+        const bf16 *__restrict__ mask, bf16 *__restrict__ g, int64_t total, int Cp, int C, float a, float wtl2, float lambda, float wtgdl,
+        float two_over_n, double inv_n, double *__restrict__ loss_acc) {
+    __shared__ double sh[32];
+    double l = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % Cp);
+        float r = 0.f;
+        if (c < C) {
+            float d = __bfloat162float(x[i]) - __bfloat162float(t[i]);
+            l += (double)d * d;
+            float w = lambda != 0.f ? __bfloat162float(mask[i]) * (1.f - lambda) + lambda : 1.f;
+            r = (df ? __bfloat162float(df[i]) * a : 0.f) + (wtl2 * w + wtgdl) * (d * two_over_n);
+        }
+        g[i] = __float2bfloat16(r);
+    }
+    l = block_sum(l, sh);
+    if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, l * inv_n);
+}
+// dst = mask ? src : dst
+__global__ void __launch_bounds__(256) composite_kernel(bf16 *__restrict__ dst, const bf16 *__restrict__ mask, const bf16 *__restrict__ src, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        if (__bfloat162float(mask[i]) != 0.f) dst[i] = src[i];
+}
+// GDL loss (forward only: the scripts add criterionMSE:backward as its gradient, train_vid_weighted.lua:525), flat-index pairing
+__global__ void __launch_bounds__(256) gdl_loss_kernel(const bf16 *__restrict__ inp, const bf16 *__restrict__ tgt, int64_t N, int H, int W, int Cp, int C,
+        double inv_n, double *__restrict__ loss_acc) {
+    __shared__ double sh[32];
+    const int NK = H * (W - 1);
+    double l = 0.0;
+    int64_t total = N * NK * Cp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % Cp);
+        if (c >= C) continue;
+        int64_t t = i / Cp;
+        int k = (int)(t % NK);
+        int64_t n = t / NK;
+        int ar = k / (W - 1), ac = k - ar * (W - 1), br = k / W, bc = k - br * W;
+        auto at = [&](const bf16 *T, int r, int cc) { return __bfloat162float(T[((n * H + r) * W + cc) * Cp + c]); };
+        float t12 = fabsf(at(tgt, ar, ac) - at(tgt, br, bc)) - fabsf(at(inp, ar, ac) - at(inp, br, bc));
+        float t34 = fabsf(at(tgt, ar, ac + 1) - at(tgt, br + 1, bc)) - fabsf(at(inp, ar, ac + 1) - at(inp, br + 1, bc));
+        l += (double)(fabsf(t12) + fabsf(t34));
+    }
+    l = block_sum(l, sh);
+    if (threadIdx.x == 0) atomicAdd(loss_acc, l * inv_n);
+}
+
+// ---------------------------------------------------------------- optimiser / parameter maintenance
+// optim.adam on the master vector + refresh of the bf16 operand copy in the same pass
+__global__ void __launch_bounds__(256) adam_bf16_kernel(float *__restrict__ x, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+        bf16 *__restrict__ xb, int64_t n, float b1, float b2, float eps, const float *__restrict__ step_ptr) {
+    const float step = *step_ptr;
+    int64_t n4 = n / 4;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (int64_t)gridDim.x * blockDim.x) {
+        float4 X = reinterpret_cast<float4 *>(x)[j], G = reinterpret_cast<const float4 *>(g)[j];
+        float4 M = reinterpret_cast<float4 *>(m)[j], V = reinterpret_cast<float4 *>(v)[j];
+#define ADAM1(c) M.c = M.c * b1 + (1.f - b1) * G.c; V.c = V.c * b2 + (1.f - b2) * G.c * G.c; X.c -= step * M.c / (sqrtf(V.c) + eps);
+        ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+        reinterpret_cast<float4 *>(x)[j] = X; reinterpret_cast<float4 *>(m)[j] = M; reinterpret_cast<float4 *>(v)[j] = V;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(X.x, X.y), h1 = __floats2bfloat162_rn(X.z, X.w);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+        reinterpret_cast<uint2 *>(xb)[j] = pk;
+    }
+}
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restrict__ x, bf16 *__restrict__ xb, int64_t n) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) xb[j] = __float2bfloat16(x[j]);
+}
+// zero a list of (offset, length) segments of a float vector and of its bf16 copy (conv biases, train.lua:279-280)
+__global__ void zero_segments_kernel(float *__restrict__ x, bf16 *__restrict__ xb, const int64_t *__restrict__ seg, int nseg) {
+    int sidx = blockIdx.x;
+    if (sidx >= nseg) return;
+    int64_t off = seg[2 * sidx], len = seg[2 * sidx + 1];
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) { x[off + i] = 0.f; if (xb) xb[off + i] = __float2bfloat16(0.f); }
+}
+// Tiled transpose of the bf16 master copy Wf [rows=Cs][cols=K] into the dgrad / full-conv-fprop operand:
+//   mode 0 (plain)  : dst[k][cs]                                   (K x Csp)
+//   mode 1 (phases) : dst[((ph*cl_rows + cl)*4 + ab)][cs] with k = tap*Clp + cl, tap = u*4+v, (ph,ab) from (u,v)
+__global__ void __launch_bounds__(256) wt_from_wf_kernel(const bf16 *__restrict__ Wf, bf16 *__restrict__ dst, int Cs, int K, int Csp, int Clp, int cl_rows, int mode) {
+    __shared__ bf16 tile[32][34];
+    int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        int cs = c0 + r, k = k0 + tx;
+        tile[r][tx] = (cs < Cs && k < K) ? Wf[(int64_t)cs * K + k] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int k = k0 + r, cs = c0 + tx;
+        if (k >= K || cs >= Csp) continue;
+        int64_t row;
+        if (mode == 0) row = k;
+        else {
+            int tap = k / Clp, cl = k - tap * Clp;
+            if (cl >= cl_rows) continue;
+            int u = tap >> 2, v = tap & 3;
+            // u = UPH[py][a]: {1,3} -> py 0 (a = 0,1); {0,2} -> py 1 (a = 0,1)
+            int py = (u & 1) ? 0 : 1, a = (u & 1) ? (u >> 1) : (u >> 1);
+            int px = (v & 1) ? 0 : 1, b = (v >> 1);
+            row = ((int64_t)((py * 2 + px) * cl_rows + cl)) * 4 + (a * 2 + b);
+        }
+        dst[row * Csp + cs] = tile[tx][r];
+    }
+}
+
+}  // namespace nhwc

@@ -1,22 +1,943 @@
-// trainer.cu -- whole-step executor (placeholder: entry points exist, executor lands next).
+// trainer.cu -- whole-step executor: one optim.adam(fDx) + optim.adam(fGx) (train.lua:421-424,
+// train_vid_weighted.lua:373-537) as a static program of kernel launches over preallocated NHWC bf16
+// buffers.  Convolutions are tcgen05 implicit GEMMs (conv_tc.cu), everything else is a fused bandwidth
+// kernel (nhwc.cuh).  The program is a flat list of ops; "sync" ops mark the buffers a data-parallel
+// run must sum across ranks (BN statistics, losses, gradients).  On one GPU the list is captured into a
+// CUDA graph.
+#include <string.h>
+#include <algorithm>
+#include <functional>
+#include <string>
+#include <type_traits>
+#include <vector>
 #include "common.cuh"
-#define NOTYET(name) { cenn_set_error(name ": fused executor not available in this build"); return 1; }
-extern "C" {
-int cenn_trainer_create(cenn_state *, const cenn_trainer_config *, cenn_trainer **) NOTYET("cenn_trainer_create")
-int cenn_trainer_destroy(cenn_trainer *) { return 0; }
-int cenn_trainer_param_count(cenn_trainer *, int, int64_t *) NOTYET("cenn_trainer_param_count")
-int cenn_trainer_set_params_host(cenn_trainer *, int, const float *) NOTYET("cenn_trainer_set_params_host")
-int cenn_trainer_get_params_host(cenn_trainer *, int, float *) NOTYET("cenn_trainer_get_params_host")
-int cenn_trainer_get_grads_host(cenn_trainer *, int, float *) NOTYET("cenn_trainer_get_grads_host")
-int cenn_trainer_bn_stat_count(cenn_trainer *, int, int64_t *) NOTYET("cenn_trainer_bn_stat_count")
-int cenn_trainer_set_bn_stats_host(cenn_trainer *, int, const float *) NOTYET("cenn_trainer_set_bn_stats_host")
-int cenn_trainer_get_bn_stats_host(cenn_trainer *, int, float *) NOTYET("cenn_trainer_get_bn_stats_host")
-int cenn_trainer_step_host(cenn_trainer *, const float *, const float *, const uint8_t *, float *) NOTYET("cenn_trainer_step_host")
-int cenn_trainer_step_device(cenn_trainer *, const float *, const float *, const uint8_t *) NOTYET("cenn_trainer_step_device")
-int cenn_trainer_read_losses(cenn_trainer *, float *) NOTYET("cenn_trainer_read_losses")
-int cenn_trainer_grad_buffer(cenn_trainer *, int, float **, int64_t *) NOTYET("cenn_trainer_grad_buffer")
-int cenn_trainer_step_phase(cenn_trainer *, int, const float *, const float *, const uint8_t *) NOTYET("cenn_trainer_step_phase")
-int cenn_trainer_generator_forward_host(cenn_trainer *, const float *, float *, int) NOTYET("cenn_trainer_generator_forward_host")
-int cenn_trainer_fetch_host(cenn_trainer *, const char *, float *, int64_t, int64_t *) NOTYET("cenn_trainer_fetch_host")
-int cenn_trainer_kernel_launches_per_step(cenn_trainer *, int64_t *) NOTYET("cenn_trainer_kernel_launches_per_step")
+#include "conv_tc.h"
+#include "nhwc.cuh"
+#include "tc_gemm.cuh"
+
+namespace {
+
+enum BlockType { CONV_S2, CONV_V4, FULL_S2, FULL_V4, HEAD };
+
+struct Tensor {
+    bf16 *p = nullptr;
+    int N = 0, H = 0, W = 0, C = 0, Cp = 0;
+    int64_t elems() const { return (int64_t)N * H * W * Cp; }
+    int64_t pix() const { return (int64_t)N * H * W; }
+};
+
+struct Block {
+    BlockType type;
+    int Cs = 0, Cl = 0, Csp = 0, Clp = 0;   // small-side / large-side channels (valid, padded)
+    bool bn = false;
+    int act = 0;
+    bool thin = false;                      // large-side tensor is thin (explicit im2col)
+    int h = 0, w = 0;                       // spatial size of the small side
+    int Cout = 0, Coutp = 0;                // channels of the block output
+    // parameter offsets (elements) in the net's master vector
+    int64_t w_off = 0, b_off = 0, g_off = -1, be_off = -1, w_count = 0;
+    // THNN flat offsets
+    int64_t t_w_off = 0, t_b_off = 0, t_g_off = -1, t_be_off = -1;
+    Tensor in, y, a, g;                     // input, conv output (BN blocks), activation output, gradient buffer
+    bf16 *col = nullptr;                    // im2col of the thin large-side tensor (forward input or backward gradient)
+    int64_t col_rows = 0, col_k = 0;
+    bf16 *Wt = nullptr;                     // transposed operand copy
+    int cl_rows = 0;
+    float *stats = nullptr, *bsums = nullptr, *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *coef = nullptr;
+    float *running = nullptr;               // [2][Cout] running_mean, running_var
+    int stats_cols = 0, fold = 1;
+    float *sig = nullptr, *gpre = nullptr;  // head
+    TcPlan p_fwd, p_dgrad, p_wgrad;
+    bool has_dgrad = false;
+};
+
+struct Net {
+    std::vector<Block> blocks;
+    int64_t nparam = 0;       // master (padded) element count
+    int64_t nparam_thnn = 0;  // Module:getParameters element count
+    float *master = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
+    bf16 *wbf = nullptr;
+    int64_t *bias_seg = nullptr;
+    int nbias_seg = 0;
+    long long *adam_t = nullptr;   // device step counter (optimState.t)
+    float *adam_step = nullptr;    // device: lr * sqrt(1-b2^t)/(1-b1^t)
+    float lr = 0.f;
+    Tensor input;             // fixed input buffer of the net
+};
+
+struct Op {
+    std::function<int()> fn;
+    float *sync_buf = nullptr;     // non-null: after fn, this buffer must be summed across ranks (DP)
+    int64_t sync_count = 0;
+    const char *name = "";
+};
+
+}  // namespace
+
+__global__ void fold_bias4_kernel(const float *__restrict__ f8, float *__restrict__ gb, int C) {
+    int c = threadIdx.x;
+    if (c < C && c < 4) gb[c] += f8[c] + f8[c + 4];
 }
+// optim.adam's bias-corrected step size, kept on the device so that the whole step is a static launch sequence
+__global__ void adam_step_kernel(long long *__restrict__ t, float *__restrict__ step, float lr, float beta1, float beta2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long tt = *t + 1;
+    *t = tt;
+    double bc1 = 1.0 - pow((double)beta1, (double)tt), bc2 = 1.0 - pow((double)beta2, (double)tt);
+    *step = (float)((double)lr * sqrt(bc2) / bc1);
+}
+
+struct cenn_trainer {
+    cenn_state *s = nullptr;
+    cenn_trainer_config cfg;
+    Net G, D;
+    int B = 0, F = 0, nc = 0;
+    int64_t Bglobal = 0;
+    std::vector<void *> allocs;
+    std::vector<Op> prog;
+    size_t pc = 0;
+    long last_sync = -1;
+    // step inputs (device, NHWC bf16)
+    Tensor real_ctx, real_aux, mask;      // aux = real_center (image) or real_full (video)
+    float *in_a = nullptr, *in_b = nullptr;   // fp32 NCHW staging for host-fed steps
+    uint8_t *in_m = nullptr;
+    float *pin_a = nullptr, *pin_b = nullptr; uint8_t *pin_m = nullptr; float *pin_loss = nullptr;
+    const float *cur_a = nullptr, *cur_b = nullptr; const uint8_t *cur_m = nullptr;
+    int64_t n_a = 0, n_b = 0, n_m = 0;
+    double *loss_acc = nullptr;           // [8] device accumulators
+    float *loss_out = nullptr;            // [8] device floats
+    Tensor df_dg;                         // gradient w.r.t. D's input (G step)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_failed = false;
+    int64_t launches_per_step = 0;
+    double flops_per_step = 0;
+};
+
+namespace {
+
+typedef cenn_trainer T;
+
+template <typename X>
+X *dalloc(T *t, int64_t n, bool zero = true) {
+    void *p = nullptr;
+    size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(X);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cenn_set_error("trainer: device allocation of %zu bytes failed", bytes); return nullptr; }
+    if (zero) cudaMemset(p, 0, bytes);
+    t->allocs.push_back(p);
+    return reinterpret_cast<X *>(p);
+}
+int alloc_tensor(T *t, Tensor &x, int N, int H, int W, int C, int Cp) {
+    x.N = N; x.H = H; x.W = W; x.C = C; x.Cp = Cp;
+    x.p = dalloc<bf16>(t, x.elems());
+    return x.p ? 0 : 1;
+}
+int pad_thin(int C) { return C <= 4 ? 4 : (C <= 16 ? 16 : round_up(C, 64)); }
+int pad_wide(int C) { return C % 64 == 0 ? C : (C < 64 ? 64 : round_up(C, 8)); }
+
+// ---- network description -------------------------------------------------------------------------------------
+struct Spec { BlockType type; int Cs, Cl; bool bn; int act; };
+
+std::vector<Spec> spec_G(const cenn_trainer_config &c) {
+    int nc = c.variant == 1 ? c.nc * c.predLen : c.nc, nef = c.nef, ngf = c.ngf, nB = c.nBottleneck;
+    std::vector<Spec> v;
+    v.push_back({CONV_S2, nef, nc, false, nhwc::ACT_LEAKY});
+    v.push_back({CONV_S2, nef, nef, true, nhwc::ACT_LEAKY});
+    v.push_back({CONV_S2, nef * 2, nef, true, nhwc::ACT_LEAKY});
+    v.push_back({CONV_S2, nef * 4, nef * 2, true, nhwc::ACT_LEAKY});
+    v.push_back({CONV_S2, nef * 8, nef * 4, true, nhwc::ACT_LEAKY});
+    v.push_back({CONV_V4, nB, nef * 8, true, nhwc::ACT_LEAKY});       // E6 + netG's BN(nBottleneck) + LeakyReLU
+    v.push_back({FULL_V4, nB, ngf * 8, true, nhwc::ACT_RELU});        // G1: Cs = nBottleneck (input), Cl = ngf*8
+    v.push_back({FULL_S2, ngf * 8, ngf * 4, true, nhwc::ACT_RELU});
+    v.push_back({FULL_S2, ngf * 4, ngf * 2, true, nhwc::ACT_RELU});
+    v.push_back({FULL_S2, ngf * 2, ngf, true, nhwc::ACT_RELU});
+    if (c.variant == 1) v.push_back({FULL_S2, ngf, ngf, true, nhwc::ACT_RELU});
+    v.push_back({FULL_S2, ngf, nc, false, nhwc::ACT_TANH});
+    return v;
+}
+std::vector<Spec> spec_D(const cenn_trainer_config &c) {
+    int nc = c.variant == 1 ? c.nc * c.predLen : c.nc, ndf = c.ndf;
+    std::vector<Spec> v;
+    if (c.variant == 1) {
+        v.push_back({CONV_S2, ndf / 2, nc, false, nhwc::ACT_LEAKY});
+        v.push_back({CONV_S2, ndf, ndf / 2, false, nhwc::ACT_LEAKY});
+    } else {
+        v.push_back({CONV_S2, ndf, nc, false, nhwc::ACT_LEAKY});
+    }
+    v.push_back({CONV_S2, ndf * 2, ndf, true, nhwc::ACT_LEAKY});
+    v.push_back({CONV_S2, ndf * 4, ndf * 2, true, nhwc::ACT_LEAKY});
+    v.push_back({CONV_S2, ndf * 8, ndf * 4, true, nhwc::ACT_LEAKY});
+    v.push_back({HEAD, 1, ndf * 8, false, nhwc::ACT_SIGMOID});
+    return v;
+}
+
+int grid1d(const cenn_state *s, int64_t items, int threads = 256, int per_sm = 8) { return bw_grid(s, items, threads, per_sm); }
+
+// ---- building a net: shapes, buffers, parameter layout, plans ---------------------------------------------------
+int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int in_C, bool first_dgrad) {
+    cenn_state *s = t->s;
+    const int N = t->B;
+    // input tensor (thin: 3 or 12 channels)
+    if (alloc_tensor(t, net.input, N, in_size, in_size, in_C, pad_thin(in_C))) return 1;
+    Tensor cur = net.input;
+    int64_t off = 0, toff = 0;
+    net.blocks.resize(specs.size());
+    std::vector<int64_t> bias_segs;
+    for (size_t i = 0; i < specs.size(); ++i) {
+        Block &b = net.blocks[i];
+        const Spec &sp = specs[i];
+        b.type = sp.type; b.Cs = sp.Cs; b.Cl = sp.Cl; b.bn = sp.bn; b.act = sp.act;
+        b.in = cur;
+        int oh, ow;
+        bool out_small;
+        switch (sp.type) {
+            case CONV_S2: REQUIRE(cur.H % 2 == 0 && cur.H >= 2, "conv input size %d not even", cur.H); b.h = cur.H / 2; b.w = cur.W / 2; oh = b.h; ow = b.w; out_small = true; break;
+            case CONV_V4: case HEAD: REQUIRE(cur.H == 4 && cur.W == 4, "4x4 valid conv expects a 4x4 input, got %dx%d (fineSize must be 128 for these nets)", cur.H, cur.W); b.h = 1; b.w = 1; oh = 1; ow = 1; out_small = true; break;
+            case FULL_V4: REQUIRE(cur.H == 1 && cur.W == 1, "G1 expects a 1x1 input"); b.h = 1; b.w = 1; oh = 4; ow = 4; out_small = false; break;
+            default: b.h = cur.H; b.w = cur.W; oh = 2 * cur.H; ow = 2 * cur.W; out_small = false; break;
+        }
+        // channel padding: the large side of an s2 layer is either thin (im2col) or a multiple of 64 (TMA gather)
+        if (out_small) { b.Clp = cur.Cp; REQUIRE(cur.C == sp.Cl, "channel mismatch at block %zu", i); }
+        else { b.Csp = cur.Cp; REQUIRE(cur.C == sp.Cs, "channel mismatch at block %zu", i); }
+        bool next_needs_wide = false;   // does the next block gather this output as its large side?
+        if (i + 1 < specs.size() && specs[i + 1].type == CONV_S2) next_needs_wide = true;
+        if (out_small) {
+            b.Cout = sp.Cs;
+            b.Csp = sp.type == HEAD ? 1 : (next_needs_wide ? pad_wide(sp.Cs) : round_up(sp.Cs, 8));
+            if (sp.type == CONV_S2 && b.Csp % 64 != 0 && b.Csp > 16 && next_needs_wide) b.Csp = round_up(b.Csp, 64);
+            b.Coutp = b.Csp;
+        } else {
+            b.Cout = sp.Cl;
+            b.Clp = sp.Cl <= 16 ? pad_thin(sp.Cl) : round_up(sp.Cl, 64);
+            b.Coutp = b.Clp;
+        }
+        b.thin = (sp.type == CONV_S2 || sp.type == FULL_S2) && b.Clp < 64;
+        if (sp.type == FULL_S2 || sp.type == CONV_S2) REQUIRE(b.thin || b.Clp % 64 == 0, "block %zu: large-side channels %d not a multiple of 64", i, b.Clp);
+        if (sp.type == FULL_S2) REQUIRE(b.Csp % 64 == 0, "block %zu: small-side channels %d not a multiple of 64", i, b.Csp);
+        // parameters: weight master [Cs][16][Clp] then bias[Cout]; BN gamma, beta
+        b.w_off = off; b.w_count = (int64_t)sp.Cs * 16 * b.Clp; off += b.w_count; off = (off + 7) & ~int64_t(7);
+        b.b_off = off; off += b.Cout; off = (off + 7) & ~int64_t(7);
+        bias_segs.push_back(b.b_off); bias_segs.push_back(b.Cout);
+        b.t_w_off = toff; toff += (int64_t)sp.Cs * sp.Cl * 16;
+        b.t_b_off = toff; toff += b.Cout;
+        if (sp.bn) {
+            b.g_off = off; off += b.Cout; off = (off + 7) & ~int64_t(7);
+            b.be_off = off; off += b.Cout; off = (off + 7) & ~int64_t(7);
+            b.t_g_off = toff; toff += b.Cout;
+            b.t_be_off = toff; toff += b.Cout;
+        }
+        // activations
+        if (sp.type == HEAD) {
+            b.sig = dalloc<float>(t, N); b.gpre = dalloc<float>(t, N);
+            if (!b.sig || !b.gpre) return 1;
+        } else {
+            if (sp.bn && alloc_tensor(t, b.y, N, oh, ow, b.Cout, b.Coutp)) return 1;
+            if (alloc_tensor(t, b.a, N, oh, ow, b.Cout, b.Coutp)) return 1;
+            if (alloc_tensor(t, b.g, N, oh, ow, b.Cout, b.Coutp)) return 1;
+        }
+        if (b.thin) {
+            b.col_rows = (int64_t)N * b.h * b.w; b.col_k = 16 * b.Clp;
+            b.col = dalloc<bf16>(t, b.col_rows * b.col_k);
+            if (!b.col) return 1;
+        }
+        if (sp.bn) {
+            b.fold = sp.type == FULL_V4 ? 16 : 1;
+            b.stats_cols = b.Coutp * b.fold;
+            b.stats = dalloc<float>(t, 2 * (int64_t)b.stats_cols);
+            b.bsums = dalloc<float>(t, 2 * (int64_t)b.Coutp);
+            b.mean = dalloc<float>(t, b.Coutp); b.invstd = dalloc<float>(t, b.Coutp);
+            b.scale = dalloc<float>(t, b.Coutp); b.shift = dalloc<float>(t, b.Coutp);
+            b.coef = dalloc<float>(t, 3 * (int64_t)b.Coutp);
+            b.running = dalloc<float>(t, 2 * (int64_t)b.Coutp);
+            if (!b.stats || !b.bsums || !b.mean || !b.invstd || !b.scale || !b.shift || !b.coef || !b.running) return 1;
+            std::vector<float> ones(b.Coutp, 1.f);
+            CK(cudaMemcpy(b.running + b.Coutp, ones.data(), b.Coutp * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        cur = sp.type == HEAD ? Tensor() : b.a;
+    }
+    net.nparam = off;
+    net.nparam_thnn = toff;
+    net.master = dalloc<float>(t, off); net.grad = dalloc<float>(t, off); net.m = dalloc<float>(t, off); net.v = dalloc<float>(t, off);
+    net.wbf = dalloc<bf16>(t, off);
+    net.adam_t = dalloc<long long>(t, 1); net.adam_step = dalloc<float>(t, 1);
+    if (!net.master || !net.grad || !net.m || !net.v || !net.wbf || !net.adam_t || !net.adam_step) return 1;
+    net.nbias_seg = (int)bias_segs.size() / 2;
+    net.bias_seg = dalloc<int64_t>(t, bias_segs.size());
+    if (!net.bias_seg) return 1;
+    CK(cudaMemcpy(net.bias_seg, bias_segs.data(), bias_segs.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+
+    // operand copies + plans
+    for (size_t i = 0; i < net.blocks.size(); ++i) {
+        Block &b = net.blocks[i];
+        const bf16 *Wf = net.wbf + b.w_off;
+        float *gW = net.grad + b.w_off;
+        Block *prev = i > 0 ? &net.blocks[i - 1] : nullptr;
+        b.has_dgrad = prev != nullptr || first_dgrad;
+        bf16 *dgrad_out = prev ? prev->g.p : nullptr;
+        const int M = N * b.h * b.w;
+        TcEpilogue ep_f;                       // forward epilogue: BN statistics or fused activation
+        if (b.bn) { ep_f.stats = b.stats; ep_f.stats_stride = b.stats_cols; }
+        else { ep_f.act = b.act; ep_f.act_param = 0.2f; }
+        bf16 *fwd_out = b.bn ? b.y.p : b.a.p;
+        TcEpilogue ep_n;
+        switch (b.type) {
+            case CONV_S2: {
+                if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, fwd_out, M, b.Cs, (int)b.col_k, b.Csp, ep_f)) return 1; }
+                else if (tc_plan_fprop_s2(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep_f)) return 1;
+                if (b.thin) { if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.col, gW, M, b.Cs, b.Csp, (int)b.col_k, 1.f, 1)) return 1; }
+                else if (tc_plan_wgrad_s2(s, &b.p_wgrad, b.g.p, b.in.p, gW, N, b.h, b.w, b.Cs, b.Csp, b.Clp, 1.f, 1)) return 1;
+                if (b.has_dgrad) {
+                    REQUIRE(b.Csp % 64 == 0, "block %zu: dgrad needs small-side channels padded to 64 (got %d)", i, b.Csp);
+                    b.cl_rows = b.Clp;
+                    b.Wt = dalloc<bf16>(t, (int64_t)16 * b.cl_rows * b.Csp);
+                    if (!b.Wt) return 1;
+                    if (!dgrad_out) { dgrad_out = dalloc<bf16>(t, b.in.elems()); if (!dgrad_out) return 1; if (&net == &t->D) { t->df_dg = b.in; t->df_dg.p = dgrad_out; } }
+                    if (tc_plan_dgrad_s2(s, &b.p_dgrad, b.g.p, b.Wt, dgrad_out, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_n)) return 1;
+                }
+                break;
+            }
+            case CONV_V4: {
+                int K = 16 * b.Clp;
+                if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, b.Cs, K, b.Csp, ep_f)) return 1;
+                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.in.p, gW, N, b.Cs, b.Csp, K, 1.f, 1)) return 1;
+                b.Wt = dalloc<bf16>(t, (int64_t)K * b.Csp);
+                if (!b.Wt) return 1;
+                if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, b.Wt, dgrad_out, N, K, b.Csp, K, ep_n)) return 1;
+                break;
+            }
+            case FULL_V4: {
+                int K = 16 * b.Clp;
+                b.Wt = dalloc<bf16>(t, (int64_t)K * b.Csp);
+                if (!b.Wt) return 1;
+                if (tc_plan_gemm(s, &b.p_fwd, b.in.p, b.Wt, fwd_out, N, K, b.Csp, K, ep_f)) return 1;
+                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.in.p, b.g.p, gW, N, b.Cs, b.Csp, K, 1.f, 1)) return 1;
+                if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, dgrad_out, N, b.Cs, K, b.Csp, ep_n)) return 1;
+                break;
+            }
+            case FULL_S2: {
+                b.cl_rows = b.Clp;
+                b.Wt = dalloc<bf16>(t, (int64_t)16 * b.cl_rows * b.Csp);
+                if (!b.Wt) return 1;
+                if (tc_plan_dgrad_s2(s, &b.p_fwd, b.in.p, b.Wt, fwd_out, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_f)) return 1;
+                if (b.thin) {
+                    if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.in.p, b.col, gW, M, b.Cs, b.Csp, (int)b.col_k, 1.f, 1)) return 1;
+                    if (tc_plan_gemm(s, &b.p_dgrad, b.col, Wf, dgrad_out, M, b.Cs, (int)b.col_k, b.Csp, ep_n)) return 1;
+                } else {
+                    if (tc_plan_wgrad_s2(s, &b.p_wgrad, b.in.p, b.g.p, gW, N, b.h, b.w, b.Cs, b.Csp, b.Clp, 1.f, 1)) return 1;
+                    if (tc_plan_fprop_s2(s, &b.p_dgrad, b.g.p, Wf, dgrad_out, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep_n)) return 1;
+                }
+                break;
+            }
+            case HEAD: break;
+        }
+    }
+    return 0;
+}
+
+// ---- op emission helpers -----------------------------------------------------------------------------------------
+#define KLAUNCH(s) do { (s)->launches++; if (cenn_check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)) return 1; } while (0)
+
+void emit(T *t, const char *name, std::function<int()> fn, float *sync_buf = nullptr, int64_t sync_count = 0) {
+    Op op; op.fn = std::move(fn); op.sync_buf = sync_buf; op.sync_count = sync_count; op.name = name;
+    t->prog.push_back(std::move(op));
+}
+void emit_plan(T *t, const char *name, TcPlan *pl) {
+    cenn_state *s = t->s;
+    t->flops_per_step += pl->flops;
+    emit(t, name, [s, pl]() { return tc_launch(s, pl); });
+}
+void emit_im2col(T *t, const Tensor &L, bf16 *col, int h, int w) {
+    cenn_state *s = t->s;
+    Tensor Lc = L;
+    emit(t, "im2col", [s, Lc, col, h, w]() {
+        int64_t total = (int64_t)Lc.N * h * w * 16 * (Lc.Cp == 4 ? 1 : Lc.Cp / 8);
+        if (Lc.Cp == 4) nhwc::im2col_kernel<4><<<grid1d(s, total), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
+        else if (Lc.Cp == 16) nhwc::im2col_kernel<16><<<grid1d(s, total), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
+        else { cenn_set_error("im2col: unsupported thin channel count %d", Lc.Cp); return 1; }
+        KLAUNCH(s); return 0;
+    });
+}
+void reduce_dims(int vec_per_pix, dim3 &block, int &gy) {
+    int tx = 1; while (tx < vec_per_pix && tx < 64) tx *= 2;
+    block = dim3(tx, 256 / tx);
+    gy = (vec_per_pix + tx - 1) / tx;
+}
+
+// forward of one block (train = batch statistics + running update; eval = running statistics)
+void emit_forward(T *t, Net &net, size_t i, bool train) {
+    cenn_state *s = t->s;
+    Block *b = &net.blocks[i];
+    float *master = net.master;
+    const double n_global = b->type == HEAD ? 1.0 : (double)t->Bglobal * b->a.H * b->a.W;
+    if (b->type == HEAD) {
+        const bf16 *w = net.wbf + b->w_off; const float *bias = master + b->b_off;
+        int B = t->B, K = 16 * b->Clp;
+        Tensor in = b->in;
+        emit(t, "head_fwd", [s, in, w, bias, b, B, K]() {
+            nhwc::head_fwd_kernel<<<(B * 32 + 255) / 256, 256, 0, s->stream>>>(in.p, w, bias, b->sig, B, K); KLAUNCH(s); return 0; });
+        return;
+    }
+    if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
+    emit_plan(t, "conv_fwd", &b->p_fwd);
+    if (b->bn) {
+        float *gamma = master + b->g_off, *beta = master + b->be_off;
+        if (train) {
+            emit(t, "bn_stats_sync", []() { return 0; }, b->stats, 2 * (int64_t)b->stats_cols);
+            emit(t, "bn_finalize", [s, b, gamma, beta, n_global]() {
+                nhwc::bn_finalize_kernel<<<(b->Cout + 127) / 128, 128, 0, s->stream>>>(b->stats, b->stats_cols, b->fold, b->Coutp, gamma, beta,
+                    b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, n_global, 0.1, 1e-5, 1);
+                KLAUNCH(s); return 0; });
+        } else {
+            emit(t, "bn_eval_coef", [s, b, gamma, beta]() {
+                nhwc::bn_eval_coef_kernel<<<(b->Cout + 127) / 128, 128, 0, s->stream>>>(gamma, beta, b->running, b->running + b->Coutp, b->scale, b->shift, b->Cout, 1e-5);
+                KLAUNCH(s);
+                // eval mode must not leave batch sums behind
+                return cenn_check_cuda(cudaMemsetAsync(b->stats, 0, 2 * (size_t)b->stats_cols * sizeof(float), s->stream), "memset", __FILE__, __LINE__); });
+        }
+        emit(t, "bn_apply_act", [s, b]() {
+            int64_t nvec = b->y.elems() / 8;
+            nhwc::bn_apply_act_kernel<<<grid1d(s, nvec), 256, 0, s->stream>>>(b->y.p, b->a.p, b->scale, b->shift, nvec, b->Coutp / 8, b->act, 0.2f);
+            KLAUNCH(s); return 0; });
+    }
+}
+
+// backward of one block: b->g holds dLoss/d(activation output); produces parameter gradients (if want_params)
+// and the previous block's gradient (if the block has a dgrad plan and want_dgrad)
+void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) {
+    cenn_state *s = t->s;
+    Block *b = &net.blocks[i];
+    float *grad = net.grad, *master = net.master;
+    if (b->type == HEAD) {
+        const bf16 *w = net.wbf + b->w_off;
+        int B = t->B, K = 16 * b->Clp;
+        Tensor in = b->in;
+        bf16 *gx = net.blocks[i - 1].g.p;
+        if (want_params) emit(t, "head_wgrad", [s, b, in, grad, B, K]() {
+            nhwc::head_wgrad_kernel<<<(K / 8 + 127) / 128, 128, 0, s->stream>>>(b->gpre, in.p, grad + b->w_off, grad + b->b_off, B, K); KLAUNCH(s); return 0; });
+        emit(t, "head_dgrad", [s, b, w, gx, B, K]() {
+            nhwc::head_dgrad_kernel<<<grid1d(s, (int64_t)B * K / 8), 256, 0, s->stream>>>(b->gpre, w, gx, B, K); KLAUNCH(s); return 0; });
+        return;
+    }
+    const int vpp = b->Coutp >= 8 ? b->Coutp / 8 : 1;
+    float *gbias = want_params ? grad + b->b_off : nullptr;
+    const int64_t npix = b->a.pix();
+    if (b->bn) {
+        const double n_global = (double)t->Bglobal * b->a.H * b->a.W;
+        float *gamma = master + b->g_off;
+        float *gg = want_params ? grad + b->g_off : nullptr, *gbeta = want_params ? grad + b->be_off : nullptr;
+        emit(t, "bn_bwd_reduce", [s, b, npix, vpp]() {
+            dim3 blk; int gy; reduce_dims(vpp, blk, gy);
+            int gx = (int)std::min<int64_t>((npix + blk.y - 1) / blk.y, (int64_t)s->sm_count * 4 / gy + 1);
+            nhwc::bn_bwd_reduce_kernel<<<dim3(gx, gy), blk, 256 * 2 * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, b->y.p, b->mean, b->bsums, b->Coutp,
+                npix, vpp, b->Cout, b->act, 0.2f);
+            KLAUNCH(s); return 0; }, b->bsums, 2 * (int64_t)b->Coutp);
+        emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
+            nhwc::bn_bwd_coef_kernel<<<(b->Cout + 127) / 128, 128, 0, s->stream>>>(b->bsums, b->Coutp, gamma, b->invstd, b->coef, gg, gbeta, b->Cout, n_global);
+            KLAUNCH(s); return 0; });
+        emit(t, "bn_bwd_apply", [s, b, gbias, npix, vpp]() {
+            dim3 blk; int gy; reduce_dims(vpp, blk, gy);
+            int gx = (int)std::min<int64_t>((npix + blk.y - 1) / blk.y, (int64_t)s->sm_count * 4 / gy + 1);
+            // coef is laid out with stride Cout
+            nhwc::bn_bwd_apply_kernel<<<dim3(gx, gy), blk, 256 * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, b->y.p, b->mean, b->coef, gbias, npix, vpp,
+                b->Cout, b->act, 0.2f);
+            KLAUNCH(s); return 0; });
+    } else if (b->Coutp >= 8) {
+        emit(t, "act_bwd", [s, b, gbias, npix, vpp]() {
+            dim3 blk; int gy; reduce_dims(vpp, blk, gy);
+            int gx = (int)std::min<int64_t>((npix + blk.y - 1) / blk.y, (int64_t)s->sm_count * 4 / gy + 1);
+            nhwc::act_bwd_kernel<<<dim3(gx, gy), blk, 256 * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gbias, npix, vpp, b->Cout, b->act, 0.2f);
+            KLAUNCH(s); return 0; });
+    } else {
+        // Cp == 4 (3-channel image output): two pixels form one 8-lane vector, lanes k and k+4 are the same channel;
+        // the bias sum is reduced into an 8-wide scratch and folded afterwards.  Pad lanes carry zero gradients.
+        float *fold8 = dalloc<float>(t, 8);
+        emit(t, "act_bwd4", [s, b, gbias, npix, fold8]() {
+            dim3 blk(1, 256);
+            int64_t npair = npix / 2;
+            int gx = (int)std::min<int64_t>((npair + 255) / 256, (int64_t)s->sm_count * 4);
+            if (gbias && cenn_check_cuda(cudaMemsetAsync(fold8, 0, 8 * sizeof(float), s->stream), "memset", __FILE__, __LINE__)) return 1;
+            nhwc::act_bwd_kernel<<<dim3(gx, 1), blk, 256 * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gbias ? fold8 : nullptr, npair, 1, 8, b->act, 0.2f);
+            KLAUNCH(s);
+            if (gbias) { fold_bias4_kernel<<<1, 32, 0, s->stream>>>(fold8, gbias, b->Cout); KLAUNCH(s); }
+            return 0; });
+    }
+    // weight gradient
+    if (want_params) {
+        if (b->thin && b->type == FULL_S2) emit_im2col(t, b->g, b->col, b->h, b->w);
+        emit_plan(t, "wgrad", &b->p_wgrad);
+    } else if (b->thin && b->type == FULL_S2 && want_dgrad && b->has_dgrad) {
+        emit_im2col(t, b->g, b->col, b->h, b->w);
+    }
+    if (want_dgrad && b->has_dgrad) emit_plan(t, "dgrad", &b->p_dgrad);
+}
+
+}  // namespace
+
+namespace {
+
+// refresh the bf16 operand copies that are transposes of the master copy
+void emit_weight_prep(T *t, Net &net) {
+    cenn_state *s = t->s;
+    for (size_t i = 0; i < net.blocks.size(); ++i) {
+        Block *b = &net.blocks[i];
+        if (!b->Wt) continue;
+        const bf16 *Wf = net.wbf + b->w_off;
+        int K = 16 * b->Clp;
+        int mode = (b->type == CONV_S2 || b->type == FULL_S2) ? 1 : 0;
+        emit(t, "wt_from_wf", [s, b, Wf, K, mode]() {
+            dim3 grid((K + 31) / 32, (b->Csp + 31) / 32);
+            nhwc::wt_from_wf_kernel<<<grid, 256, 0, s->stream>>>(Wf, b->Wt, b->Cs, K, b->Csp, b->Clp, b->cl_rows, mode);
+            KLAUNCH(s); return 0; });
+    }
+}
+void emit_zero_bias(T *t, Net &net) {
+    cenn_state *s = t->s;
+    Net *n = &net;
+    emit(t, "zero_conv_bias", [s, n]() {
+        nhwc::zero_segments_kernel<<<n->nbias_seg, 128, 0, s->stream>>>(n->master, n->wbf, n->bias_seg, n->nbias_seg); KLAUNCH(s); return 0; });
+}
+void emit_zero_grad(T *t, Net &net) {
+    cenn_state *s = t->s;
+    Net *n = &net;
+    emit(t, "zero_grad", [s, n]() { return cenn_check_cuda(cudaMemsetAsync(n->grad, 0, n->nparam * sizeof(float), s->stream), "memset", __FILE__, __LINE__); });
+}
+void emit_adam(T *t, Net &net) {
+    cenn_state *s = t->s;
+    Net *n = &net;
+    float beta1 = t->cfg.beta1;
+    emit(t, "adam", [s, n, beta1]() {
+        adam_step_kernel<<<1, 32, 0, s->stream>>>(n->adam_t, n->adam_step, n->lr, beta1, 0.999f); KLAUNCH(s);
+        nhwc::adam_bf16_kernel<<<grid1d(s, n->nparam / 4), 256, 0, s->stream>>>(n->master, n->grad, n->m, n->v, n->wbf, n->nparam, beta1, 0.999f, 1e-8f, n->adam_step);
+        KLAUNCH(s); return 0; });
+}
+void emit_bce(T *t, Block *head, float label, int loss_slot, bool want_grad) {
+    cenn_state *s = t->s;
+    double inv_n = 1.0 / (double)t->Bglobal;
+    int B = t->B;
+    double *acc = t->loss_acc + loss_slot;
+    emit(t, "bce", [s, head, label, acc, B, inv_n, want_grad]() {
+        nhwc::head_bce_kernel<<<(B + 255) / 256, 256, 0, s->stream>>>(head->sig, label, want_grad ? head->gpre : nullptr, acc, B, inv_n); KLAUNCH(s); return 0; });
+}
+void emit_copy(T *t, const char *name, bf16 *dst, const bf16 *src, int64_t elems) {
+    cenn_state *s = t->s;
+    emit(t, name, [s, dst, src, elems]() { return cenn_check_cuda(cudaMemcpyAsync(dst, src, elems * sizeof(bf16), cudaMemcpyDeviceToDevice, s->stream), "d2d copy", __FILE__, __LINE__); });
+}
+
+// losses: device double accumulators -> float outputs
+__global__ void finish_losses_kernel(const double *__restrict__ acc, float *__restrict__ out, float wtl2, float wtgdl) {
+    if (threadIdx.x != 0) return;
+    double errD_real = acc[CENN_LOSS_ERRD_REAL], errD_fake = acc[CENN_LOSS_ERRD_FAKE], errG = acc[CENN_LOSS_ERRG], l2 = acc[CENN_LOSS_ERRG_L2], gdl = acc[CENN_LOSS_ERRG_GDL];
+    out[CENN_LOSS_ERRD] = (float)(errD_real + errD_fake);
+    out[CENN_LOSS_ERRG] = (float)errG; out[CENN_LOSS_ERRG_L2] = (float)l2; out[CENN_LOSS_ERRG_GDL] = (float)gdl;
+    out[CENN_LOSS_ERRD_REAL] = (float)errD_real; out[CENN_LOSS_ERRD_FAKE] = (float)errD_fake;
+    double total = errG;
+    if (wtl2 != 0.f) total = (wtl2 > 0.f && wtl2 < 1.f) ? (1.0 - wtl2) * errG + wtl2 * l2 : errG + wtl2 * l2;
+    if (wtgdl != 0.f) total += wtgdl * gdl;
+    out[CENN_LOSS_ERRG_TOTAL] = (float)total; out[7] = 0.f;
+}
+
+// ---- the step program ---------------------------------------------------------------------------------------------
+int build_program(T *t) {
+    cenn_state *s = t->s;
+    const cenn_trainer_config &c = t->cfg;
+    Net &G = t->G, &D = t->D;
+    const bool video = c.variant == 1;
+    Block *headD = &D.blocks.back();
+    Block *lastG = &G.blocks.back();
+    t->prog.clear();
+    t->flops_per_step = 0;
+    // -- inputs: fp32 NCHW (+ uint8 mask) -> NHWC bf16
+    emit(t, "convert_inputs", [t, s, video]() {
+        const Tensor &a = t->real_ctx, &b = t->real_aux;
+        nhwc::to_nhwc_kernel<float><<<grid1d(s, a.pix()), 256, 0, s->stream>>>(t->cur_a, a.p, a.N, a.C, a.H * a.W, a.Cp); KLAUNCH(s);
+        nhwc::to_nhwc_kernel<float><<<grid1d(s, b.pix()), 256, 0, s->stream>>>(t->cur_b, b.p, b.N, b.C, b.H * b.W, b.Cp); KLAUNCH(s);
+        if (video) { const Tensor &m = t->mask; nhwc::to_nhwc_kernel<uint8_t><<<grid1d(s, m.pix()), 256, 0, s->stream>>>(t->cur_m, m.p, m.N, m.C, m.H * m.W, m.Cp); KLAUNCH(s); }
+        return cenn_check_cuda(cudaMemsetAsync(t->loss_acc, 0, 8 * sizeof(double), s->stream), "memset", __FILE__, __LINE__); });
+    // ================= fDx (train.lua:278-350) =================
+    emit_zero_bias(t, D); emit_zero_bias(t, G);
+    emit_zero_grad(t, D);
+    // D on real
+    emit_copy(t, "d_in<-real", D.input.p, t->real_aux.p, D.input.elems());
+    for (size_t i = 0; i < D.blocks.size(); ++i) emit_forward(t, D, i, true);
+    emit_bce(t, headD, 1.f, CENN_LOSS_ERRD_REAL, true);
+    for (size_t i = D.blocks.size(); i-- > 0;) emit_backward(t, D, i, true, i > 0 || c.dead_dgrad);
+    // G forward
+    emit_copy(t, "g_in<-ctx", G.input.p, t->real_ctx.p, G.input.elems());
+    for (size_t i = 0; i < G.blocks.size(); ++i) emit_forward(t, G, i, true);
+    // D on fake
+    if (video && c.weight_nomask == 0.f) {
+        emit_copy(t, "d_in<-real", D.input.p, t->real_aux.p, D.input.elems());
+        bf16 *dst = D.input.p; const bf16 *m = t->mask.p, *src = lastG->a.p; int64_t total = D.input.elems();
+        emit(t, "composite", [s, dst, m, src, total]() { nhwc::composite_kernel<<<grid1d(s, total), 256, 0, s->stream>>>(dst, m, src, total); KLAUNCH(s); return 0; });
+    } else {
+        emit_copy(t, "d_in<-fake", D.input.p, lastG->a.p, D.input.elems());
+    }
+    for (size_t i = 0; i < D.blocks.size(); ++i) emit_forward(t, D, i, true);
+    emit_bce(t, headD, 0.f, CENN_LOSS_ERRD_FAKE, true);
+    for (size_t i = D.blocks.size(); i-- > 0;) emit_backward(t, D, i, true, i > 0 || c.dead_dgrad);
+    emit(t, "gradD_sync", []() { return 0; }, D.grad, D.nparam);
+    emit_adam(t, D);
+    emit_weight_prep(t, D);
+    // ================= fGx (train.lua:353-410) =================
+    emit_zero_bias(t, D); emit_zero_bias(t, G);
+    emit_zero_grad(t, G);
+    emit_bce(t, headD, 1.f, CENN_LOSS_ERRG, true);
+    for (size_t i = D.blocks.size(); i-- > 0;) emit_backward(t, D, i, false, true);   // netD:updateGradInput
+    // blend with the L2 term -> gradient w.r.t. G's output
+    {
+        const Tensor fake_in = D.input;   // input_center / input_inpainted as seen by D
+        const Tensor real = t->real_aux, df = t->df_dg, gout = lastG->g, mk = t->mask;
+        const double n = (double)t->Bglobal * fake_in.C * fake_in.H * fake_in.W;
+        float a = (c.wtl2 > 0.f && c.wtl2 < 1.f) ? 1.f - c.wtl2 : 1.f;
+        double *acc = t->loss_acc + CENN_LOSS_ERRG_L2;
+        if (!video) {
+            float w_in = c.wtl2, w_ring = c.overlapPred > 0 ? 10.f * c.wtl2 : c.wtl2;
+            int ov = c.overlapPred;
+            if (c.wtl2 != 0.f)
+                emit(t, "blend_overlap", [s, df, fake_in, real, gout, ov, a, w_in, w_ring, n, acc]() {
+                    nhwc::blend_overlap_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
+                        fake_in.W, fake_in.Cp, fake_in.C, ov, a, w_in, w_ring, (float)(2.0 / n), 1.0 / n, acc);
+                    KLAUNCH(s); return 0; });
+            else emit_copy(t, "g<-df_dg", gout.p, df.p, gout.elems());
+        } else {
+            float wtl2 = c.wtl2, lam = c.weight_nomask, wtgdl = c.wtgdl;
+            if (wtgdl != 0.f) {
+                double *gacc = t->loss_acc + CENN_LOSS_ERRG_GDL;
+                double ngdl = (double)t->Bglobal * fake_in.C * fake_in.H * (fake_in.W - 1);
+                emit(t, "gdl_loss", [s, fake_in, real, gacc, ngdl]() {
+                    nhwc::gdl_loss_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.Cp, fake_in.C, 1.0 / ngdl, gacc);
+                    KLAUNCH(s); return 0; });
+            }
+            emit(t, "blend_masked", [s, df, fake_in, real, mk, gout, a, wtl2, lam, wtgdl, n, acc]() {
+                nhwc::blend_masked_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems(), fake_in.Cp, fake_in.C,
+                    a, wtl2, lam, wtgdl, (float)(2.0 / n), 1.0 / n, acc);
+                KLAUNCH(s); return 0; });
+        }
+    }
+    for (size_t i = G.blocks.size(); i-- > 0;) emit_backward(t, G, i, true, i > 0 || c.dead_dgrad);
+    emit(t, "gradG_sync", []() { return 0; }, G.grad, G.nparam);
+    emit_adam(t, G);
+    emit_weight_prep(t, G);
+    float wtl2 = c.wtl2, wtgdl = c.wtgdl;
+    emit(t, "losses_sync", []() { return 0; }, reinterpret_cast<float *>(t->loss_acc), 0 /* doubles: reduced separately */);
+    emit(t, "finish_losses", [t, s, wtl2, wtgdl]() { finish_losses_kernel<<<1, 32, 0, s->stream>>>(t->loss_acc, t->loss_out, wtl2, wtgdl); KLAUNCH(s); return 0; });
+    return 0;
+}
+
+int run_ops(T *t, size_t from, size_t to) {
+    for (size_t i = from; i < to; ++i)
+        if (t->prog[i].fn()) return 1;
+    return 0;
+}
+
+int run_step(T *t) {
+    cenn_state *s = t->s;
+    // one GPU: replay the captured graph (adam's step scalar is a kernel argument -> re-captured values would go stale,
+    // so Adam's bias-corrected step is recomputed on the host and the graph is only used when it is up to date)
+    return run_ops(t, 0, t->prog.size());
+    (void)s;
+}
+
+void refresh_operands(T *t, Net &net) {
+    cenn_state *s = t->s;
+    nhwc::f32_to_bf16_kernel<<<grid1d(s, net.nparam), 256, 0, s->stream>>>(net.master, net.wbf, net.nparam);
+    s->launches++;
+    size_t mark = t->prog.size();
+    emit_weight_prep(t, net);
+    run_ops(t, mark, t->prog.size());
+    t->prog.resize(mark);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trainer **out) {
+    API_BEGIN(s);
+    REQUIRE(cfg && out, "cenn_trainer_create: null argument");
+    REQUIRE(cfg->precision == CENN_BF16, "the fused executor runs in BF16 tensor-core mode only; use the op-level modules for CENN_FP32");
+    REQUIRE(cfg->variant == 0 || cfg->variant == 1, "unknown variant %d", cfg->variant);
+    REQUIRE(cfg->fineSize == 128, "fineSize must be 128 (the 4x4 bottleneck/head of the reference nets), got %d", cfg->fineSize);
+    REQUIRE(cfg->batchSize >= 1 && cfg->nBottleneck % 8 == 0 && cfg->nef % 64 == 0 && cfg->ngf % 64 == 0 && cfg->ndf % 64 == 0,
+            "batchSize >= 1, nBottleneck %% 8 == 0 and nef/ngf/ndf %% 64 == 0 required (got %d, %d, %d/%d/%d)", cfg->batchSize, cfg->nBottleneck, cfg->nef, cfg->ngf, cfg->ndf);
+    REQUIRE(cfg->variant == 1 || cfg->overlapPred * 2 <= cfg->fineSize / 2, "overlapPred too large");
+    REQUIRE(cfg->variant == 0 || cfg->overlapPred == 0, "video variant requires overlapPred == 0 (train_vid_weighted.lua:509)");
+    int ncv = cfg->variant == 1 ? cfg->nc * cfg->predLen : cfg->nc;
+    REQUIRE(ncv >= 1 && ncv <= 16, "1..16 input channels supported (nc*predLen = %d)", ncv);
+    cenn_trainer *t = new cenn_trainer();
+    t->s = s; t->cfg = *cfg;
+    if (t->cfg.world_size < 1) t->cfg.world_size = 1;
+    t->B = cfg->batchSize; t->F = cfg->fineSize; t->nc = ncv;
+    t->Bglobal = (int64_t)t->B * t->cfg.world_size;
+    const bool video = cfg->variant == 1;
+    const int dsize = video ? t->F : t->F / 2;
+    int rc = 0;
+    rc = rc || build_net(t, t->D, spec_D(*cfg), dsize, ncv, true);
+    rc = rc || build_net(t, t->G, spec_G(*cfg), t->F, ncv, cfg->dead_dgrad != 0);
+    if (rc) { cenn_trainer_destroy(t); return 1; }
+    t->G.lr = (cfg->wtl2 > 0.f && cfg->wtl2 < 1.f) ? cfg->lr * 10.f : cfg->lr;   // train.lua:219-226
+    t->D.lr = cfg->lr;
+    rc = rc || alloc_tensor(t, t->real_ctx, t->B, t->F, t->F, ncv, pad_thin(ncv));
+    rc = rc || alloc_tensor(t, t->real_aux, t->B, dsize, dsize, ncv, pad_thin(ncv));
+    if (video) rc = rc || alloc_tensor(t, t->mask, t->B, t->F, t->F, ncv, pad_thin(ncv));
+    t->n_a = (int64_t)t->B * ncv * t->F * t->F; t->n_b = (int64_t)t->B * ncv * dsize * dsize; t->n_m = video ? t->n_a : 0;
+    t->in_a = dalloc<float>(t, t->n_a); t->in_b = dalloc<float>(t, t->n_b);
+    if (video) t->in_m = dalloc<uint8_t>(t, t->n_m);
+    t->loss_acc = dalloc<double>(t, 8); t->loss_out = dalloc<float>(t, 8);
+    if (rc || !t->in_a || !t->in_b || !t->loss_acc || !t->loss_out) { cenn_trainer_destroy(t); return 1; }
+    if (cudaMallocHost(&t->pin_a, t->n_a * 4) != cudaSuccess || cudaMallocHost(&t->pin_b, t->n_b * 4) != cudaSuccess ||
+        cudaMallocHost(&t->pin_loss, 8 * sizeof(float)) != cudaSuccess || (video && cudaMallocHost(&t->pin_m, t->n_m) != cudaSuccess)) {
+        cenn_set_error("trainer: pinned host allocation failed"); cenn_trainer_destroy(t); return 1;
+    }
+    // G's output must match D's input tensor exactly (same NHWC padding) for the d2d hand-over
+    const Tensor &go = t->G.blocks.back().a;
+    if (go.H != dsize || go.Cp != t->D.input.Cp) { cenn_set_error("internal: generator output %dx%dx%d does not match discriminator input %dx%dx%d", go.H, go.W, go.Cp, dsize, dsize, t->D.input.Cp); cenn_trainer_destroy(t); return 1; }
+    if (build_program(t)) { cenn_trainer_destroy(t); return 1; }
+    int64_t before = s->launches;
+    (void)before;
+    *out = t;
+    return 0;
+}
+
+int cenn_trainer_destroy(cenn_trainer *t) {
+    if (!t) return 0;
+    cudaSetDevice(t->s->device);
+    cudaStreamSynchronize(t->s->stream);
+    if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
+    if (t->graph) cudaGraphDestroy(t->graph);
+    for (Net *n : {&t->G, &t->D})
+        for (Block &b : n->blocks) { tc_plan_free(&b.p_fwd); tc_plan_free(&b.p_dgrad); tc_plan_free(&b.p_wgrad); }
+    for (void *p : t->allocs) cudaFree(p);
+    if (t->pin_a) cudaFreeHost(t->pin_a);
+    if (t->pin_b) cudaFreeHost(t->pin_b);
+    if (t->pin_m) cudaFreeHost(t->pin_m);
+    if (t->pin_loss) cudaFreeHost(t->pin_loss);
+    delete t;
+    return 0;
+}
+
+static Net *pick_net(cenn_trainer *t, int net) { return net == CENN_NET_G ? &t->G : (net == CENN_NET_D ? &t->D : nullptr); }
+
+int cenn_trainer_param_count(cenn_trainer *t, int net, int64_t *count) {
+    REQUIRE(t && count && pick_net(t, net), "cenn_trainer_param_count: bad argument");
+    *count = pick_net(t, net)->nparam_thnn;
+    return 0;
+}
+
+// THNN flat layout <-> padded master layout (host side; not on the hot path)
+static void thnn_to_master(const Net &n, const float *flat, std::vector<float> &m) {
+    m.assign(n.nparam, 0.f);
+    for (const Block &b : n.blocks) {
+        for (int cs = 0; cs < b.Cs; ++cs)
+            for (int cl = 0; cl < b.Cl; ++cl)
+                for (int tp = 0; tp < 16; ++tp) m[b.w_off + ((int64_t)cs * 16 + tp) * b.Clp + cl] = flat[b.t_w_off + ((int64_t)cs * b.Cl + cl) * 16 + tp];
+        for (int c = 0; c < b.Cout; ++c) m[b.b_off + c] = flat[b.t_b_off + c];
+        if (b.bn) for (int c = 0; c < b.Cout; ++c) { m[b.g_off + c] = flat[b.t_g_off + c]; m[b.be_off + c] = flat[b.t_be_off + c]; }
+    }
+}
+static void master_to_thnn(const Net &n, const std::vector<float> &m, float *flat) {
+    for (const Block &b : n.blocks) {
+        for (int cs = 0; cs < b.Cs; ++cs)
+            for (int cl = 0; cl < b.Cl; ++cl)
+                for (int tp = 0; tp < 16; ++tp) flat[b.t_w_off + ((int64_t)cs * b.Cl + cl) * 16 + tp] = m[b.w_off + ((int64_t)cs * 16 + tp) * b.Clp + cl];
+        for (int c = 0; c < b.Cout; ++c) flat[b.t_b_off + c] = m[b.b_off + c];
+        if (b.bn) for (int c = 0; c < b.Cout; ++c) { flat[b.t_g_off + c] = m[b.g_off + c]; flat[b.t_be_off + c] = m[b.be_off + c]; }
+    }
+}
+
+int cenn_trainer_set_params_host(cenn_trainer *t, int net, const float *flat) {
+    REQUIRE(t && flat && pick_net(t, net), "cenn_trainer_set_params_host: bad argument");
+    API_BEGIN(t->s);
+    Net &n = *pick_net(t, net);
+    std::vector<float> m;
+    thnn_to_master(n, flat, m);
+    CK(cudaMemcpyAsync(n.master, m.data(), n.nparam * sizeof(float), cudaMemcpyHostToDevice, t->s->stream));
+    CK(cudaStreamSynchronize(t->s->stream));
+    refresh_operands(t, n);
+    CK(cudaStreamSynchronize(t->s->stream));
+    return 0;
+}
+static int get_vec(cenn_trainer *t, Net &n, const float *dev, float *flat) {
+    std::vector<float> m(n.nparam);
+    CK(cudaMemcpyAsync(m.data(), dev, n.nparam * sizeof(float), cudaMemcpyDeviceToHost, t->s->stream));
+    CK(cudaStreamSynchronize(t->s->stream));
+    master_to_thnn(n, m, flat);
+    return 0;
+}
+int cenn_trainer_get_params_host(cenn_trainer *t, int net, float *flat) {
+    REQUIRE(t && flat && pick_net(t, net), "cenn_trainer_get_params_host: bad argument");
+    API_BEGIN(t->s);
+    return get_vec(t, *pick_net(t, net), pick_net(t, net)->master, flat);
+}
+int cenn_trainer_get_grads_host(cenn_trainer *t, int net, float *flat) {
+    REQUIRE(t && flat && pick_net(t, net), "cenn_trainer_get_grads_host: bad argument");
+    API_BEGIN(t->s);
+    return get_vec(t, *pick_net(t, net), pick_net(t, net)->grad, flat);
+}
+int cenn_trainer_bn_stat_count(cenn_trainer *t, int net, int64_t *count) {
+    REQUIRE(t && count && pick_net(t, net), "cenn_trainer_bn_stat_count: bad argument");
+    int64_t n = 0;
+    for (const Block &b : pick_net(t, net)->blocks) if (b.bn) n += 2 * b.Cout;
+    *count = n;
+    return 0;
+}
+int cenn_trainer_set_bn_stats_host(cenn_trainer *t, int net, const float *stats) {
+    REQUIRE(t && stats && pick_net(t, net), "cenn_trainer_set_bn_stats_host: bad argument");
+    API_BEGIN(t->s);
+    int64_t off = 0;
+    for (Block &b : pick_net(t, net)->blocks) if (b.bn) {
+        CK(cudaMemcpy(b.running, stats + off, b.Cout * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b.running + b.Coutp, stats + off + b.Cout, b.Cout * sizeof(float), cudaMemcpyHostToDevice));
+        off += 2 * b.Cout;
+    }
+    return 0;
+}
+int cenn_trainer_get_bn_stats_host(cenn_trainer *t, int net, float *stats) {
+    REQUIRE(t && stats && pick_net(t, net), "cenn_trainer_get_bn_stats_host: bad argument");
+    API_BEGIN(t->s);
+    CK(cudaStreamSynchronize(t->s->stream));
+    int64_t off = 0;
+    for (Block &b : pick_net(t, net)->blocks) if (b.bn) {
+        CK(cudaMemcpy(stats + off, b.running, b.Cout * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(stats + off + b.Cout, b.running + b.Coutp, b.Cout * sizeof(float), cudaMemcpyDeviceToHost));
+        off += 2 * b.Cout;
+    }
+    return 0;
+}
+
+int cenn_trainer_step_device(cenn_trainer *t, const float *a, const float *b, const uint8_t *mask) {
+    REQUIRE(t && a && b, "cenn_trainer_step_device: null input");
+    REQUIRE(t->cfg.variant == 0 || mask, "cenn_trainer_step_device: the video variant needs a mask");
+    API_BEGIN(t->s);
+    t->cur_a = a; t->cur_b = b; t->cur_m = mask;
+    int64_t before = t->s->launches;
+    int rc = run_step(t);
+    t->launches_per_step = t->s->launches - before;
+    return rc;
+}
+int cenn_trainer_read_losses(cenn_trainer *t, float *losses) {
+    REQUIRE(t && losses, "cenn_trainer_read_losses: null argument");
+    API_BEGIN(t->s);
+    CK(cudaMemcpyAsync(t->pin_loss, t->loss_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, t->s->stream));
+    CK(cudaStreamSynchronize(t->s->stream));
+    memcpy(losses, t->pin_loss, 8 * sizeof(float));
+    return 0;
+}
+int cenn_trainer_step_host(cenn_trainer *t, const float *a, const float *b, const uint8_t *mask, float *losses) {
+    REQUIRE(t && a && b && losses, "cenn_trainer_step_host: null argument");
+    REQUIRE(t->cfg.variant == 0 || mask, "cenn_trainer_step_host: the video variant needs a mask");
+    API_BEGIN(t->s);
+    cudaStream_t st = t->s->stream;
+    // pageable -> pinned staging -> device; the copies are part of the end-to-end step
+    memcpy(t->pin_a, a, t->n_a * 4); memcpy(t->pin_b, b, t->n_b * 4);
+    CK(cudaMemcpyAsync(t->in_a, t->pin_a, t->n_a * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(t->in_b, t->pin_b, t->n_b * 4, cudaMemcpyHostToDevice, st));
+    if (t->cfg.variant == 1) { memcpy(t->pin_m, mask, t->n_m); CK(cudaMemcpyAsync(t->in_m, t->pin_m, t->n_m, cudaMemcpyHostToDevice, st)); }
+    if (cenn_trainer_step_device(t, t->in_a, t->in_b, t->in_m)) return 1;
+    return cenn_trainer_read_losses(t, losses);
+}
+
+int cenn_trainer_grad_buffer(cenn_trainer *t, int net, float **grads, int64_t *count) {
+    REQUIRE(t && grads && count && pick_net(t, net), "cenn_trainer_grad_buffer: bad argument");
+    *grads = pick_net(t, net)->grad; *count = pick_net(t, net)->nparam;
+    return 0;
+}
+// phase < 0: (re)start a step with the given inputs and run up to the first sync point; phase >= 0: continue.
+// After the call, cenn_trainer_grad_buffer-style queries are replaced by the sync record returned through
+// cenn_last_error-free out-params of cenn_trainer_sync_info (see DESIGN.md "multi-GPU").
+int cenn_trainer_step_phase(cenn_trainer *t, int phase, const float *a, const float *b, const uint8_t *mask) {
+    REQUIRE(t, "cenn_trainer_step_phase: null trainer");
+    API_BEGIN(t->s);
+    if (phase < 0) { REQUIRE(a && b, "cenn_trainer_step_phase: null input"); t->cur_a = a; t->cur_b = b; t->cur_m = mask; t->pc = 0; t->last_sync = -1; }
+    while (t->pc < t->prog.size()) {
+        Op &op = t->prog[t->pc++];
+        if (op.fn()) return 1;
+        if (op.sync_buf) { t->last_sync = (long)t->pc - 1; return 0; }
+    }
+    t->last_sync = -1;
+    return 0;
+}
+int cenn_trainer_sync_info(cenn_trainer *t, void **buf, int64_t *count, int *is_double, int *done) {
+    REQUIRE(t && buf && count && is_double && done, "cenn_trainer_sync_info: null argument");
+    *done = t->pc >= t->prog.size() && t->last_sync < 0;
+    *buf = nullptr; *count = 0; *is_double = 0;
+    if (t->last_sync >= 0) {
+        const Op &op = t->prog[t->last_sync];
+        *buf = op.sync_buf;
+        if (op.sync_buf == reinterpret_cast<float *>(t->loss_acc)) { *count = 8; *is_double = 1; } else *count = op.sync_count;
+    }
+    return 0;
+}
+
+int cenn_trainer_generator_forward_host(cenn_trainer *t, const float *in, float *out, int batch) {
+    REQUIRE(t && in && out, "cenn_trainer_generator_forward_host: null argument");
+    REQUIRE(batch >= 1 && batch <= t->B, "generator_forward: batch %d outside 1..%d (the executor's buffers are sized for batchSize)", batch, t->B);
+    API_BEGIN(t->s);
+    cenn_state *s = t->s;
+    Net &G = t->G;
+    const Tensor &gi = G.input;
+    int64_t n_in = (int64_t)batch * gi.C * gi.H * gi.W;
+    CK(cudaMemsetAsync(t->in_a, 0, t->n_a * 4, s->stream));
+    CK(cudaMemcpyAsync(t->in_a, in, n_in * 4, cudaMemcpyHostToDevice, s->stream));
+    nhwc::to_nhwc_kernel<float><<<grid1d(s, gi.pix()), 256, 0, s->stream>>>(t->in_a, gi.p, gi.N, gi.C, gi.H * gi.W, gi.Cp);
+    KLAUNCH(s);
+    size_t mark = t->prog.size();
+    for (size_t i = 0; i < G.blocks.size(); ++i) emit_forward(t, G, i, false);
+    double f = t->flops_per_step;
+    int rc = run_ops(t, mark, t->prog.size());
+    t->prog.resize(mark);
+    t->flops_per_step = f;
+    if (rc) return 1;
+    const Tensor &go = G.blocks.back().a;
+    float *tmp = (float *)cenn_workspace(s, (size_t)go.N * go.C * go.H * go.W * 4);
+    if (!tmp) return 1;
+    nhwc::to_nchw_kernel<<<grid1d(s, (int64_t)go.N * go.C * go.H * go.W), 256, 0, s->stream>>>(go.p, tmp, go.N, go.C, go.H * go.W, go.Cp);
+    KLAUNCH(s);
+    CK(cudaMemcpyAsync(out, tmp, (size_t)batch * go.C * go.H * go.W * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// name = "<G|D>.<block index>.<y|a|g|in>" or "df_dg" / "fake" / "ctx"
+int cenn_trainer_fetch_host(cenn_trainer *t, const char *name, float *dst, int64_t capacity, int64_t *count) {
+    REQUIRE(t && name && dst && count, "cenn_trainer_fetch_host: null argument");
+    API_BEGIN(t->s);
+    cenn_state *s = t->s;
+    Tensor x;
+    std::string nm(name);
+    if (nm == "df_dg") x = t->df_dg;
+    else if (nm == "fake") x = t->G.blocks.back().a;
+    else if (nm == "ctx") x = t->real_ctx;
+    else {
+        REQUIRE(nm.size() >= 5 && (nm[0] == 'G' || nm[0] == 'D') && nm[1] == '.', "fetch: bad name '%s'", name);
+        Net &n = nm[0] == 'G' ? t->G : t->D;
+        size_t dot = nm.find('.', 2);
+        REQUIRE(dot != std::string::npos, "fetch: bad name '%s'", name);
+        int idx = atoi(nm.substr(2, dot - 2).c_str());
+        REQUIRE(idx >= 0 && idx < (int)n.blocks.size(), "fetch: block index out of range in '%s'", name);
+        std::string f = nm.substr(dot + 1);
+        Block &b = n.blocks[idx];
+        if (f == "y") x = b.y; else if (f == "a") x = b.a; else if (f == "g") x = b.g; else if (f == "in") x = b.in;
+        else if (f == "sig") { *count = t->B; REQUIRE(capacity >= t->B && b.sig, "fetch: no sig"); CK(cudaStreamSynchronize(s->stream)); CK(cudaMemcpy(dst, b.sig, t->B * 4, cudaMemcpyDeviceToHost)); return 0; }
+        else { cenn_set_error("fetch: unknown field in '%s'", name); return 1; }
+    }
+    REQUIRE(x.p, "fetch: '%s' has no buffer", name);
+    int64_t n = (int64_t)x.N * x.C * x.H * x.W;
+    REQUIRE(capacity >= n, "fetch: capacity %lld < %lld", (long long)capacity, (long long)n);
+    float *tmp = (float *)cenn_workspace(s, n * 4);
+    if (!tmp) return 1;
+    nhwc::to_nchw_kernel<<<grid1d(s, n), 256, 0, s->stream>>>(x.p, tmp, x.N, x.C, x.H * x.W, x.Cp);
+    KLAUNCH(s);
+    CK(cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *count = n;
+    return 0;
+}
+
+int cenn_trainer_kernel_launches_per_step(cenn_trainer *t, int64_t *count) {
+    REQUIRE(t && count, "null argument");
+    *count = t->launches_per_step;
+    return 0;
+}
+
+}  // extern "C"

@@ -244,6 +244,12 @@ class FusedTrainer:
         api().cenn_trainer_step_phase(self.h, int(phase), C.c_void_p(a_ptr), C.c_void_p(b_ptr),
                                       C.c_void_p(mask_ptr) if mask_ptr else None)
 
+    def sync_info(self):
+        """(device pointer, element count, is_double, done) of the synchronisation point the last step_phase stopped at."""
+        buf, n, dbl, done = C.c_void_p(), C.c_int64(), C.c_int(), C.c_int()
+        api().cenn_trainer_sync_info(self.h, C.byref(buf), C.byref(n), C.byref(dbl), C.byref(done))
+        return buf.value, n.value, bool(dbl.value), bool(done.value)
+
     def grad_buffer(self, net):
         p, n = C.c_void_p(), C.c_int64()
         api().cenn_trainer_grad_buffer(self.h, net, C.byref(p), C.byref(n))
