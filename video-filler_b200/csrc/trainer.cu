@@ -47,6 +47,7 @@ struct Block {
     float *running = nullptr;               // [2][Cout] running_mean, running_var
     int stats_cols = 0, fold = 1;
     float *sig = nullptr, *gpre = nullptr;  // head
+    float *bias_exp = nullptr;              // G1: bias expanded over the 16 taps
     TcPlan p_fwd, p_dgrad, p_wgrad;
     bool has_dgrad = false;
 };
@@ -77,6 +78,10 @@ struct Op {
 __global__ void fold_bias4_kernel(const float *__restrict__ f8, float *__restrict__ gb, int C) {
     int c = threadIdx.x;
     if (c < C && c < 4) gb[c] += f8[c] + f8[c + 4];
+}
+__global__ void expand_bias_kernel(const float *__restrict__ bias, float *__restrict__ out, int C, int Cp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 16 * Cp) { int c = i % Cp; out[i] = c < C ? bias[c] : 0.f; }
 }
 // optim.adam's bias-corrected step size, kept on the device so that the whole step is a static launch sequence
 __global__ void adam_step_kernel(long long *__restrict__ t, float *__restrict__ step, float lr, float beta1, float beta2) {
@@ -275,7 +280,14 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         b.has_dgrad = prev != nullptr || first_dgrad;
         bf16 *dgrad_out = prev ? prev->g.p : nullptr;
         const int M = N * b.h * b.w;
-        TcEpilogue ep_f;                       // forward epilogue: BN statistics or fused activation
+        TcEpilogue ep_f;                       // forward epilogue: bias, then BN statistics or fused activation
+        // (conv biases are zero in every training forward -- train.lua:279-280 -- but not when a checkpoint is evaluated)
+        ep_f.bias = net.master + b.b_off;
+        if (b.type == FULL_V4) {               // G1: GEMM columns are (tap, channel) -> per-column copy of the channel bias
+            b.bias_exp = dalloc<float>(t, 16 * (int64_t)b.Clp);
+            if (!b.bias_exp) return 1;
+            ep_f.bias = b.bias_exp;
+        }
         if (b.bn) { ep_f.stats = b.stats; ep_f.stats_stride = b.stats_cols; }
         else { ep_f.act = b.act; ep_f.act_param = 0.2f; }
         bf16 *fwd_out = b.bn ? b.y.p : b.a.p;
@@ -378,6 +390,10 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
         return;
     }
     if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
+    if (b->bias_exp) {
+        const float *bias = master + b->b_off;
+        emit(t, "expand_bias", [s, b, bias]() { expand_bias_kernel<<<(16 * b->Clp + 255) / 256, 256, 0, s->stream>>>(bias, b->bias_exp, b->Cout, b->Clp); KLAUNCH(s); return 0; });
+    }
     emit_plan(t, "conv_fwd", &b->p_fwd);
     if (b->bn) {
         float *gamma = master + b->g_off, *beta = master + b->be_off;
