@@ -236,6 +236,9 @@ CENN_API int cenn_trainer_generator_forward_host(cenn_trainer *t, const float *i
 /* debugging / parity: copy an internal activation or gradient as fp32 NCHW to the host by name */
 CENN_API int cenn_trainer_fetch_host(cenn_trainer *t, const char *name, float *dst_host, int64_t capacity, int64_t *count);
 CENN_API int cenn_trainer_kernel_launches_per_step(cenn_trainer *t, int64_t *count);
+/* one step with a CUDA-event pair around every op: '\n'-separated op names, per-op milliseconds and algorithmic FLOPs */
+CENN_API int cenn_trainer_profile_step(cenn_trainer *t, const float *a_dev, const float *b_dev, const uint8_t *mask_dev,
+        char *names, int64_t names_cap, float *ms, double *flops, int64_t cap, int64_t *nops);
 
 #ifdef __cplusplus
 }

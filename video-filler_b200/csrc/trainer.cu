@@ -71,6 +71,8 @@ struct Op {
     float *sync_buf = nullptr;     // non-null: after fn, this buffer must be summed across ranks (DP)
     int64_t sync_count = 0;
     const char *name = "";
+    double flops = 0;              // algorithmic FLOPs (tensor-core ops)
+    double bytes = 0;              // algorithmic bytes (bandwidth ops), 0 if not stated
 };
 
 }  // namespace
@@ -357,6 +359,7 @@ void emit_plan(T *t, const char *name, TcPlan *pl) {
     cenn_state *s = t->s;
     t->flops_per_step += pl->flops;
     emit(t, name, [s, pl]() { return tc_launch(s, pl); });
+    t->prog.back().flops = pl->flops;
 }
 void emit_im2col(T *t, const Tensor &L, bf16 *col, int h, int w) {
     cenn_state *s = t->s;
@@ -701,8 +704,7 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     if (video) t->in_m = dalloc<uint8_t>(t, t->n_m);
     t->loss_acc = dalloc<double>(t, 8); t->loss_out = dalloc<float>(t, 8);
     if (rc || !t->in_a || !t->in_b || !t->loss_acc || !t->loss_out) { cenn_trainer_destroy(t); return 1; }
-    if (cudaMallocHost(&t->pin_a, t->n_a * 4) != cudaSuccess || cudaMallocHost(&t->pin_b, t->n_b * 4) != cudaSuccess ||
-        cudaMallocHost(&t->pin_loss, 8 * sizeof(float)) != cudaSuccess || (video && cudaMallocHost(&t->pin_m, t->n_m) != cudaSuccess)) {
+    if (cudaMallocHost(&t->pin_loss, 8 * sizeof(float)) != cudaSuccess) {
         cenn_set_error("trainer: pinned host allocation failed"); cenn_trainer_destroy(t); return 1;
     }
     // G's output must match D's input tensor exactly (same NHWC padding) for the d2d hand-over
@@ -844,13 +846,43 @@ int cenn_trainer_step_host(cenn_trainer *t, const float *a, const float *b, cons
     REQUIRE(t->cfg.variant == 0 || mask, "cenn_trainer_step_host: the video variant needs a mask");
     API_BEGIN(t->s);
     cudaStream_t st = t->s->stream;
-    // pageable -> pinned staging -> device; the copies are part of the end-to-end step
-    memcpy(t->pin_a, a, t->n_a * 4); memcpy(t->pin_b, b, t->n_b * 4);
-    CK(cudaMemcpyAsync(t->in_a, t->pin_a, t->n_a * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(t->in_b, t->pin_b, t->n_b * 4, cudaMemcpyHostToDevice, st));
-    if (t->cfg.variant == 1) { memcpy(t->pin_m, mask, t->n_m); CK(cudaMemcpyAsync(t->in_m, t->pin_m, t->n_m, cudaMemcpyHostToDevice, st)); }
+    // host -> device copies are part of the end-to-end step (truly asynchronous when the caller's buffers are pinned,
+    // e.g. from cenn_host_alloc; staged by the driver otherwise)
+    CK(cudaMemcpyAsync(t->in_a, a, t->n_a * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(t->in_b, b, t->n_b * 4, cudaMemcpyHostToDevice, st));
+    if (t->cfg.variant == 1) CK(cudaMemcpyAsync(t->in_m, mask, t->n_m, cudaMemcpyHostToDevice, st));
     if (cenn_trainer_step_device(t, t->in_a, t->in_b, t->in_m)) return 1;
     return cenn_trainer_read_losses(t, losses);
+}
+
+// One step with a CUDA-event pair around every op of the program (on the launching stream); returns the op names
+// ('\n'-separated), their durations and algorithmic FLOPs.  Used by bench.py for the roofline of the dominant kernels.
+int cenn_trainer_profile_step(cenn_trainer *t, const float *a, const float *b, const uint8_t *mask, char *names, int64_t names_cap,
+        float *ms, double *flops, int64_t cap, int64_t *nops) {
+    REQUIRE(t && a && b && names && ms && flops && nops, "cenn_trainer_profile_step: null argument");
+    API_BEGIN(t->s);
+    cudaStream_t st = t->s->stream;
+    size_t n = t->prog.size();
+    REQUIRE((int64_t)n <= cap, "cenn_trainer_profile_step: capacity %lld < %zu ops", (long long)cap, n);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    t->cur_a = a; t->cur_b = b; t->cur_m = mask;
+    CK(cudaEventRecord(ev[0], st));
+    int rc = 0;
+    for (size_t i = 0; i < n && !rc; ++i) { rc = t->prog[i].fn(); CK(cudaEventRecord(ev[i + 1], st)); }
+    CK(cudaStreamSynchronize(st));
+    std::string all;
+    for (size_t i = 0; i < n && !rc; ++i) {
+        CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        flops[i] = t->prog[i].flops;
+        all += t->prog[i].name; all += '\n';
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (rc) return 1;
+    REQUIRE((int64_t)all.size() + 1 <= names_cap, "cenn_trainer_profile_step: names buffer too small");
+    memcpy(names, all.c_str(), all.size() + 1);
+    *nops = (int64_t)n;
+    return 0;
 }
 
 int cenn_trainer_grad_buffer(cenn_trainer *t, int net, float **grads, int64_t *count) {

@@ -276,6 +276,32 @@ class FusedTrainer:
         api().cenn_trainer_fetch_host(self.h, name.encode(), buf.ctypes.data_as(C.c_void_p), capacity, C.byref(n))
         return buf[:n.value].copy()
 
+    def profile_step(self, a_ptr, b_ptr, mask_ptr=None, repeats=3):
+        """Per-op CUDA-event timing of one step (averaged over `repeats` runs after one untimed run)."""
+        cap = 4096
+        names = C.create_string_buffer(1 << 16)
+        ms = np.zeros(cap, np.float32)
+        fl = np.zeros(cap, np.float64)
+        n = C.c_int64()
+        acc = None
+        for r in range(repeats + 1):
+            api().cenn_trainer_profile_step(self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(mask_ptr) if mask_ptr else None,
+                                            names, len(names), ms.ctypes.data_as(C.c_void_p), fl.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+            if r == 0:
+                acc = np.zeros(n.value, np.float64)
+            else:
+                acc += ms[:n.value]
+        acc /= repeats
+        nm = names.value.decode().split("\n")[:n.value]
+        flops = fl[:n.value]
+        by_op = {}
+        for k, t in zip(nm, acc):
+            by_op[k] = by_op.get(k, 0.0) + float(t)
+        tc = flops > 0
+        return {"names": nm, "ms": acc, "flops": flops, "total_ms": float(acc.sum()), "tc_ms": float(acc[tc].sum()),
+                "tc_flops": float(flops[tc].sum()), "tc_launches": int(tc.sum()),
+                "by_op": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])}}
+
     def launches_per_step(self):
         n = C.c_int64()
         api().cenn_trainer_kernel_launches_per_step(self.h, C.byref(n))
