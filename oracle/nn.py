@@ -10,6 +10,27 @@ import numpy as np
 from . import ops
 
 
+# --------------------------------------------------------------------------------------------
+# Optional storage-precision emulation.  When QUANT is a callable (e.g. ops.bf16_round) the oracle rounds
+#   * conv / full-conv weights as seen by the three conv phases (the fp32 master copy stays exact for Adam),
+#   * the outputs of conv, full-conv and activation modules (BN output is not rounded: the product fuses
+#     BN-apply with the activation and stores once),
+#   * the gradInput of conv, full-conv (dgrad outputs) and BN modules (its backward output),
+# i.e. exactly the tensors the BF16 executor stores in bf16.  Used by tests/test_fused_gpu.py so that ReLU /
+# LeakyReLU gates agree between oracle and product and whole-network gradients can be compared tightly.
+QUANT = None
+_Q_OUT = ("SpatialConvolution", "SpatialFullConvolution", "LeakyReLU", "ReLU", "Tanh")
+_Q_GIN = ("SpatialConvolution", "SpatialFullConvolution", "SpatialBatchNormalization")
+
+
+def _q(x):
+    return QUANT(x) if QUANT is not None and x is not None else x
+
+
+def _qw(w):
+    return QUANT(w) if QUANT is not None else w
+
+
 class Module:
     def __init__(self):
         self.train = True
@@ -92,6 +113,8 @@ class Sequential(Module):
     def updateOutput(self, x):
         for m in self.modules:
             x = m.updateOutput(x)
+            if QUANT is not None and type(m).__name__ in _Q_OUT:
+                x = m.output = _q(x)
         self.output = x
         return x
 
@@ -105,6 +128,8 @@ class Sequential(Module):
         ins = self._inputs(x)
         for m, xi in zip(reversed(self.modules), reversed(ins)):
             gy = m.updateGradInput(xi, gy)
+            if QUANT is not None and type(m).__name__ in _Q_GIN:
+                gy = m.gradInput = _q(gy)
         self.gradInput = gy
         return gy
 
@@ -118,6 +143,8 @@ class Sequential(Module):
         ins = self._inputs(x)
         for m, xi in zip(reversed(self.modules), reversed(ins)):
             gy = m.backward(xi, gy, scale)
+            if QUANT is not None and type(m).__name__ in _Q_GIN:
+                gy = m.gradInput = _q(gy)
         self.gradInput = gy
         return gy
 
@@ -152,11 +179,11 @@ class SpatialConvolution(Module):
         self.gradBias = np.zeros_like(self.bias)
 
     def updateOutput(self, x):
-        self.output = ops.conv_forward(x, self.weight, self.bias, self.dH, self.dW, self.padH, self.padW)
+        self.output = ops.conv_forward(x, _qw(self.weight), self.bias, self.dH, self.dW, self.padH, self.padW)
         return self.output
 
     def updateGradInput(self, x, gy):
-        self.gradInput = ops.conv_grad_input(x.shape, gy, self.weight, self.dH, self.dW, self.padH, self.padW)
+        self.gradInput = ops.conv_grad_input(x.shape, gy, _qw(self.weight), self.dH, self.dW, self.padH, self.padW)
         return self.gradInput
 
     def accGradParameters(self, x, gy, scale=1.0):
@@ -180,12 +207,12 @@ class SpatialFullConvolution(Module):
         self.gradBias = np.zeros_like(self.bias)
 
     def updateOutput(self, x):
-        self.output = ops.fullconv_forward(x, self.weight, self.bias, self.dH, self.dW, self.padH, self.padW,
+        self.output = ops.fullconv_forward(x, _qw(self.weight), self.bias, self.dH, self.dW, self.padH, self.padW,
                                            self.adjH, self.adjW)
         return self.output
 
     def updateGradInput(self, x, gy):
-        self.gradInput = ops.fullconv_grad_input(gy, self.weight, self.dH, self.dW, self.padH, self.padW)
+        self.gradInput = ops.fullconv_grad_input(gy, _qw(self.weight), self.dH, self.dW, self.padH, self.padW)
         return self.gradInput
 
     def accGradParameters(self, x, gy, scale=1.0):

@@ -7,6 +7,14 @@ Test infrastructure only -- see ``oracle/__init__.py``.
 """
 import numpy as np
 
+def bf16_round(x):
+    """Round to the nearest bfloat16 (ties to even), returned in the dtype of x."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    u = a.view(np.uint32)
+    r = ((u + (((u >> 16) & 1) + 0x7FFF)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).reshape(a.shape).astype(np.asarray(x).dtype)
+
+
 # --------------------------------------------------------------------------
 # im2col helpers (THNN SpatialConvolutionMM = unfold + sgemm; SURVEY 9.1)
 # --------------------------------------------------------------------------

@@ -40,8 +40,8 @@ class StepOracle:
         nets.zero_conv_bias(self.netG)
         self.gD[...] = 0
         B = real_ctx.shape[0]
-        self.input_ctx = real_ctx.astype(self.dtype)
-        self.input_real_center = real_center.astype(self.dtype)
+        self.input_ctx = nn._q(real_ctx.astype(self.dtype))
+        self.input_real_center = nn._q(real_center.astype(self.dtype))
         label = np.full(B, 1.0, self.dtype)
         out = self.netD.forward(self.input_real_center)
         self.errD_real = self.criterion.forward(out, label)
@@ -74,7 +74,7 @@ class StepOracle:
             self.errG_l2 = self.criterionMSE.forward(self.input_center, self.input_real_center)
             df_dg = ops.blend_l2_overlap(df_dg, self.input_center, self.input_real_center, wtl2, o['overlapPred'])
             total = ((1 - wtl2) * self.errG + wtl2 * self.errG_l2) if 0 < wtl2 < 1 else self.errG + wtl2 * self.errG_l2
-        self.df_dg = df_dg
+        self.df_dg = df_dg = nn._q(df_dg)
         self.netG.backward(self.input_ctx, df_dg)
         return total
 
@@ -84,8 +84,8 @@ class StepOracle:
         nets.zero_conv_bias(self.netG)
         self.gD[...] = 0
         B = real_ctx.shape[0]
-        self.input_ctx = real_ctx.astype(self.dtype)
-        self.input_real = real_full.astype(self.dtype)
+        self.input_ctx = nn._q(real_ctx.astype(self.dtype))
+        self.input_real = nn._q(real_full.astype(self.dtype))
         self.input_mask = real_mask.astype(self.dtype)
         label = np.full(B, 1.0, self.dtype)
         out = self.netD.forward(self.input_real)
@@ -134,7 +134,7 @@ class StepOracle:
             df_dg_gdl = self.criterionMSE.backward(self.input_inpainted, self.input_real)
             total = total + o['wtgdl'] * self.errG_gdl
             df_dg = (df_dg + np.asarray(o['wtgdl'], self.dtype) * df_dg_gdl).astype(self.dtype)
-        self.df_dg = df_dg
+        self.df_dg = df_dg = nn._q(df_dg)
         self.netG.backward(self.input_ctx, df_dg)
         return total
 

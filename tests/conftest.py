@@ -15,8 +15,9 @@ def pytest_configure(config):
 def rel_err(a, b):
     """Parity metric of SURVEY.md section 4: max|a-b| / max|b| per tensor."""
     import numpy as np
-    a = np.asarray(a, np.float64)
-    b = np.asarray(b, np.float64)
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    assert a.size == b.size, (a.size, b.size)
     d = float(np.max(np.abs(a - b))) if a.size else 0.0
     return d / max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-30)
 

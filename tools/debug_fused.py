@@ -18,7 +18,10 @@ def flat_modules(net):
     return out
 
 variant = sys.argv[1] if len(sys.argv) > 1 else "image"
-kw = dict(batchSize=8, nBottleneck=256, nef=64, ngf=64, ndf=64)
+if len(sys.argv) > 2 and sys.argv[2] == "quant":
+    from oracle import nn as onn, ops as oops
+    onn.QUANT = oops.bf16_round
+kw = dict(batchSize=int(os.environ.get("DBG_B", "8")), nBottleneck=256, nef=64, ngf=64, ndf=64)
 if variant == "video": kw["predLen"] = 2
 T.state(0)
 orc = ostep.StepOracle(onets.default_opt(variant, **kw), seed=1234, dtype=np.float64)
@@ -29,6 +32,7 @@ lo = orc.step(*batch); lg = trn.step_host(*batch)
 print({k: (round(lg[k], 5), round(lo[k], 5)) for k in lo if lo[k] is not None})
 for name, net, gref, idx in (("G", orc.netG, orc.gG, 0), ("D", orc.netD, orc.gD, 1)):
     g = trn.get_grads(idx)
+    print(f"{name} overall grads rel={rel(g, gref):9.3e} cos={float(np.dot(g, gref) / (np.linalg.norm(g) * np.linalg.norm(gref))):+.5f} norm ratio={np.linalg.norm(g) / np.linalg.norm(gref):.4f}")
     mods = flat_modules(net)
     off = 0; blk = -1
     for m in mods:
