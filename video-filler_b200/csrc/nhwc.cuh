@@ -134,55 +134,63 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const bf16 *__restric
     }
 }
 
-// Per-channel reduction skeleton: blockDim = (TX channel-vectors, TY pixel lanes); grid = (pixel strips, channel-vector groups).
-// Each thread accumulates NACC values for its 8 channels; lanes are folded through shared memory; one atomic per channel.
-template <int NACC, class F>
-__device__ __forceinline__ void channel_reduce(int64_t npix, int vec_per_pix, float *__restrict__ out, int out_stride, int C_valid, F body) {
-    extern __shared__ float red_sh[];
-    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
-    const int vec = blockIdx.y * TX + tx;
-    float acc[NACC][8];
-#pragma unroll
-    for (int a = 0; a < NACC; ++a)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
-    if (vec < vec_per_pix)
-        for (int64_t p = (int64_t)blockIdx.x * TY + ty; p < npix; p += (int64_t)gridDim.x * TY) body(p * vec_per_pix + vec, vec * 8, acc);
-    // fold the TY pixel lanes
-    float *sh = red_sh;   // [TY][TX][NACC*8]
-#pragma unroll
-    for (int a = 0; a < NACC; ++a)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sh[((ty * TX + tx) * NACC + a) * 8 + k] = acc[a][k];
+// Per-channel reductions over NHWC: blockDim = (TX channel-vectors, TY pixel lanes), grid = (pixel strips, vector groups).
+// Each thread owns one 8-channel vector position and walks pixels with stride gridDim.x*TY, U pixels per iteration with
+// all loads issued before the arithmetic (bytes in flight hide HBM latency); partial sums are folded with shared-memory
+// atomics (TY-way contention at most) and leave the CTA as one global fp32 atomic per channel.
+constexpr int RED_U = 4;
+
+template <int NACC>
+__device__ __forceinline__ void fold_and_flush(float (&acc)[NACC][8], bool active, float *__restrict__ out, int out_stride, int C_valid) {
+    extern __shared__ float red_sh[];                 // [NACC][TX*8]
+    const int TX = blockDim.x, tx = threadIdx.x, tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const int width = TX * 8;
+    for (int i = tid; i < NACC * width; i += nthr) red_sh[i] = 0.f;
     __syncthreads();
-    if (ty == 0 && vec < vec_per_pix) {
+    if (active) {
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float s = 0.f;
-                for (int l = 0; l < TY; ++l) s += sh[((l * TX + tx) * NACC + a) * 8 + k];
-                int c = vec * 8 + k;
-                if (c < C_valid) atomicAdd(out + a * out_stride + c, s);
-            }
+            for (int k = 0; k < 8; ++k) atomicAdd(&red_sh[a * width + tx * 8 + k], acc[a][k]);
+    }
+    __syncthreads();
+    const int c_base = blockIdx.y * width;
+    for (int i = tid; i < NACC * width; i += nthr) {
+        int a = i / width, c = c_base + (i - a * width);
+        if (c < C_valid) atomicAdd(out + a * out_stride + c, red_sh[i]);
     }
 }
 
 // BN backward pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * (y - mean[c]),  dz = g * act'(a)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16 *__restrict__ g, const bf16 *__restrict__ a, const bf16 *__restrict__ y,
         const float *__restrict__ mean, float *__restrict__ sums, int sums_stride, int64_t npix, int vec_per_pix, int C, int act, float negval) {
-    channel_reduce<2>(npix, vec_per_pix, sums, sums_stride, C, [&](int64_t vi, int c0, float (&acc)[2][8]) {
-        float fg[8], fa[8], fy[8];
-        unpack8(reinterpret_cast<const uint4 *>(g)[vi], fg);
-        unpack8(reinterpret_cast<const uint4 *>(a)[vi], fa);
-        unpack8(reinterpret_cast<const uint4 *>(y)[vi], fy);
+    const int vec = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = vec < vec_per_pix;
+    float acc[2][8] = {};
+    if (active) {
+        float mu[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float dz = fg[k] * act_bwd(fa[k], act, negval);
-            acc[0][k] += dz;
-            acc[1][k] += dz * (fy[k] - mean[c0 + k]);
+        for (int k = 0; k < 8; ++k) mu[k] = (vec * 8 + k < C) ? mean[vec * 8 + k] : 0.f;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * RED_U) {
+            uint4 rg[RED_U], ra[RED_U], ry[RED_U];
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) {
+                int64_t p = p0 + u * stride;
+                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ra[u] = reinterpret_cast<const uint4 *>(a)[vi]; ry[u] = reinterpret_cast<const uint4 *>(y)[vi]; }
+            }
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) {
+                if (p0 + u * stride < npix) {
+                    float fg[8], fa[8], fy[8];
+                    unpack8(rg[u], fg); unpack8(ra[u], fa); unpack8(ry[u], fy);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { float dz = fg[k] * act_bwd(fa[k], act, negval); acc[0][k] += dz; acc[1][k] += dz * (fy[k] - mu[k]); }
+                }
+            }
         }
-    });
+    }
+    fold_and_flush<2>(acc, active, sums, sums_stride, C);
 }
 // coefficients for pass 2 + BN parameter gradients; zeroes the sums for the next use.
 //   coef[0][c] = s/n, coef[1][c] = invstd^2 * d/n, coef[2][c] = invstd * gamma
@@ -200,36 +208,73 @@ __global__ void bn_bwd_coef_kernel(float *__restrict__ sums, int sums_stride, co
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, const bf16 *__restrict__ y,
         const float *__restrict__ mean, const float *__restrict__ coef, float *__restrict__ gbias, int64_t npix, int vec_per_pix, int C,
         int act, float negval) {
-    channel_reduce<1>(npix, vec_per_pix, gbias, 0, gbias ? C : 0, [&](int64_t vi, int c0, float (&acc)[1][8]) {
-        float fg[8], fa[8], fy[8];
-        unpack8(reinterpret_cast<const uint4 *>(g)[vi], fg);
-        unpack8(reinterpret_cast<const uint4 *>(a)[vi], fa);
-        unpack8(reinterpret_cast<const uint4 *>(y)[vi], fy);
+    const int vec = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = vec < vec_per_pix;
+    float acc[1][8] = {};
+    if (active) {
+        float mu[8], c0[8], c1[8], c2[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            int c = c0 + k;
-            float r = 0.f;
-            if (c < C) {
-                float dz = fg[k] * act_bwd(fa[k], act, negval);
-                r = (dz - coef[c] - (fy[k] - mean[c]) * coef[C + c]) * coef[2 * C + c];
-            }
-            fg[k] = r;
-            acc[0][k] += r;
+            int c = vec * 8 + k;
+            bool ok = c < C;
+            mu[k] = ok ? mean[c] : 0.f; c0[k] = ok ? coef[c] : 0.f; c1[k] = ok ? coef[C + c] : 0.f; c2[k] = ok ? coef[2 * C + c] : 0.f;
         }
-        reinterpret_cast<uint4 *>(g)[vi] = pack8(fg);
-    });
+        const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * RED_U) {
+            uint4 rg[RED_U], ra[RED_U], ry[RED_U];
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) {
+                int64_t p = p0 + u * stride;
+                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ra[u] = reinterpret_cast<const uint4 *>(a)[vi]; ry[u] = reinterpret_cast<const uint4 *>(y)[vi]; }
+            }
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) {
+                int64_t p = p0 + u * stride;
+                if (p < npix) {
+                    float fg[8], fa[8], fy[8];
+                    unpack8(rg[u], fg); unpack8(ra[u], fa); unpack8(ry[u], fy);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float dz = fg[k] * act_bwd(fa[k], act, negval);
+                        float r = (dz - c0[k] - (fy[k] - mu[k]) * c1[k]) * c2[k];      // c2 == 0 on padded lanes
+                        fg[k] = r; acc[0][k] += r;
+                    }
+                    reinterpret_cast<uint4 *>(g)[p * vec_per_pix + vec] = pack8(fg);
+                }
+            }
+        }
+    }
+    if (gbias) fold_and_flush<1>(acc, active, gbias, 0, C);
 }
 // activation-only backward (in place on g): g_y = g * act'(a); optional sum -> gradBias
 __global__ void __launch_bounds__(256) act_bwd_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, float *__restrict__ gbias, int64_t npix,
         int vec_per_pix, int C, int act, float negval) {
-    channel_reduce<1>(npix, vec_per_pix, gbias, 0, gbias ? C : 0, [&](int64_t vi, int c0, float (&acc)[1][8]) {
-        float fg[8], fa[8];
-        unpack8(reinterpret_cast<const uint4 *>(g)[vi], fg);
-        unpack8(reinterpret_cast<const uint4 *>(a)[vi], fa);
+    const int vec = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = vec < vec_per_pix;
+    float acc[1][8] = {};
+    if (active) {
+        const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * RED_U) {
+            uint4 rg[RED_U], ra[RED_U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { float r = (c0 + k < C) ? fg[k] * act_bwd(fa[k], act, negval) : 0.f; fg[k] = r; acc[0][k] += r; }
-        reinterpret_cast<uint4 *>(g)[vi] = pack8(fg);
-    });
+            for (int u = 0; u < RED_U; ++u) {
+                int64_t p = p0 + u * stride;
+                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ra[u] = reinterpret_cast<const uint4 *>(a)[vi]; }
+            }
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) {
+                int64_t p = p0 + u * stride;
+                if (p < npix) {
+                    float fg[8], fa[8];
+                    unpack8(rg[u], fg); unpack8(ra[u], fa);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { float r = (vec * 8 + k < C) ? fg[k] * act_bwd(fa[k], act, negval) : 0.f; fg[k] = r; acc[0][k] += r; }
+                    reinterpret_cast<uint4 *>(g)[p * vec_per_pix + vec] = pack8(fg);
+                }
+            }
+        }
+    }
+    if (gbias) fold_and_flush<1>(acc, active, gbias, 0, C);
 }
 
 // ---------------------------------------------------------------- discriminator head: 4x4 valid conv to 1 channel + Sigmoid + BCE

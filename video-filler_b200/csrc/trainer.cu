@@ -4,6 +4,7 @@
 // kernel (nhwc.cuh).  The program is a flat list of ops; "sync" ops mark the buffers a data-parallel
 // run must sum across ranks (BN statistics, losses, gradients).  On one GPU the list is captured into a
 // CUDA graph.
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <functional>
@@ -117,6 +118,8 @@ struct cenn_trainer {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     bool graph_failed = false;
+    const void *graph_key[3] = {nullptr, nullptr, nullptr}, *seen_key[3] = {nullptr, nullptr, nullptr};
+    int64_t graph_kernels = 0;
     int64_t launches_per_step = 0;
     double flops_per_step = 0;
 };
@@ -446,8 +449,8 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         float *gg = want_params ? grad + b->g_off : nullptr, *gbeta = want_params ? grad + b->be_off : nullptr;
         emit(t, "bn_bwd_reduce", [s, b, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
-            int gx = (int)std::min<int64_t>((npix + blk.y - 1) / blk.y, (int64_t)s->sm_count * 4 / gy + 1);
-            nhwc::bn_bwd_reduce_kernel<<<dim3(gx, gy), blk, 256 * 2 * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, b->y.p, b->mean, b->bsums, b->Coutp,
+            int gx = (int)std::max<int64_t>(1, std::min<int64_t>((npix + blk.y * 4 - 1) / (blk.y * 4), (int64_t)s->sm_count * 4 / gy));
+            nhwc::bn_bwd_reduce_kernel<<<dim3(gx, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, b->y.p, b->mean, b->bsums, b->Coutp,
                 npix, vpp, b->Cout, b->act, 0.2f);
             KLAUNCH(s); return 0; }, b->bsums, 2 * (int64_t)b->Coutp);
         emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
@@ -455,16 +458,16 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             KLAUNCH(s); return 0; });
         emit(t, "bn_bwd_apply", [s, b, gbias, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
-            int gx = (int)std::min<int64_t>((npix + blk.y - 1) / blk.y, (int64_t)s->sm_count * 4 / gy + 1);
+            int gx = (int)std::max<int64_t>(1, std::min<int64_t>((npix + blk.y * 4 - 1) / (blk.y * 4), (int64_t)s->sm_count * 4 / gy));
             // coef is laid out with stride Cout
-            nhwc::bn_bwd_apply_kernel<<<dim3(gx, gy), blk, 256 * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, b->y.p, b->mean, b->coef, gbias, npix, vpp,
+            nhwc::bn_bwd_apply_kernel<<<dim3(gx, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, b->y.p, b->mean, b->coef, gbias, npix, vpp,
                 b->Cout, b->act, 0.2f);
             KLAUNCH(s); return 0; });
     } else if (b->Coutp >= 8) {
         emit(t, "act_bwd", [s, b, gbias, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
-            int gx = (int)std::min<int64_t>((npix + blk.y - 1) / blk.y, (int64_t)s->sm_count * 4 / gy + 1);
-            nhwc::act_bwd_kernel<<<dim3(gx, gy), blk, 256 * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gbias, npix, vpp, b->Cout, b->act, 0.2f);
+            int gx = (int)std::max<int64_t>(1, std::min<int64_t>((npix + blk.y * 4 - 1) / (blk.y * 4), (int64_t)s->sm_count * 4 / gy));
+            nhwc::act_bwd_kernel<<<dim3(gx, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gbias, npix, vpp, b->Cout, b->act, 0.2f);
             KLAUNCH(s); return 0; });
     } else {
         // Cp == 4 (3-channel image output): two pixels form one 8-lane vector, lanes k and k+4 are the same channel;
@@ -473,9 +476,9 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         emit(t, "act_bwd4", [s, b, gbias, npix, fold8]() {
             dim3 blk(1, 256);
             int64_t npair = npix / 2;
-            int gx = (int)std::min<int64_t>((npair + 255) / 256, (int64_t)s->sm_count * 4);
+            int gx = (int)std::max<int64_t>(1, std::min<int64_t>((npair + 1023) / 1024, (int64_t)s->sm_count * 4));
             if (gbias && cenn_check_cuda(cudaMemsetAsync(fold8, 0, 8 * sizeof(float), s->stream), "memset", __FILE__, __LINE__)) return 1;
-            nhwc::act_bwd_kernel<<<dim3(gx, 1), blk, 256 * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gbias ? fold8 : nullptr, npair, 1, 8, b->act, 0.2f);
+            nhwc::act_bwd_kernel<<<dim3(gx, 1), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gbias ? fold8 : nullptr, npair, 1, 8, b->act, 0.2f);
             KLAUNCH(s);
             if (gbias) { fold_bias4_kernel<<<1, 32, 0, s->stream>>>(fold8, gbias, b->Cout); KLAUNCH(s); }
             return 0; });
@@ -651,10 +654,41 @@ int run_ops(T *t, size_t from, size_t to) {
 
 int run_step(T *t) {
     cenn_state *s = t->s;
-    // one GPU: replay the captured graph (adam's step scalar is a kernel argument -> re-captured values would go stale,
-    // so Adam's bias-corrected step is recomputed on the host and the graph is only used when it is up to date)
-    return run_ops(t, 0, t->prog.size());
-    (void)s;
+    static const bool no_graph = getenv("CENN_NO_GRAPH") != nullptr;
+    if (no_graph || t->graph_failed) return run_ops(t, 0, t->prog.size());
+    const void *key[3] = {t->cur_a, t->cur_b, t->cur_m};
+    if (t->graph_exec && memcmp(key, t->graph_key, sizeof(key)) == 0) {
+        CK(cudaGraphLaunch(t->graph_exec, s->stream));
+        s->launches += t->graph_kernels;
+        return 0;
+    }
+    // the first step with a given set of input buffers runs eagerly (it also warms lazily loaded kernels);
+    // the second one is captured, every later one replays the graph
+    if (memcmp(key, t->seen_key, sizeof(key)) != 0) {
+        memcpy(t->seen_key, key, sizeof(key));
+        return run_ops(t, 0, t->prog.size());
+    }
+    if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
+    if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
+    int64_t before = s->launches;
+    if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError(); t->graph_failed = true;
+        return run_ops(t, 0, t->prog.size());
+    }
+    int rc = run_ops(t, 0, t->prog.size());
+    cudaError_t e = cudaStreamEndCapture(s->stream, &t->graph);
+    t->graph_kernels = s->launches - before;
+    s->launches = before;
+    if (rc || e != cudaSuccess || !t->graph || cudaGraphInstantiate(&t->graph_exec, t->graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
+        t->graph_exec = nullptr; t->graph_failed = true;
+        return run_ops(t, 0, t->prog.size());
+    }
+    memcpy(t->graph_key, key, sizeof(key));
+    CK(cudaGraphLaunch(t->graph_exec, s->stream));
+    s->launches += t->graph_kernels;
+    return 0;
 }
 
 void refresh_operands(T *t, Net &net) {
