@@ -69,14 +69,6 @@ void choose_box(int w, int h, int total, int &bw, int &bh, int &bn) {
     bn = total / (bw * bh);
 }
 
-tc::KbDesc *kb_upload(cenn_state *s, TcPlan *pl, const std::vector<tc::KbDesc> &v) {
-    size_t bytes = v.size() * sizeof(tc::KbDesc);
-    if (cudaMalloc(&pl->kb_dev, bytes) != cudaSuccess) { cenn_set_error("k-block table alloc failed"); return nullptr; }
-    // synchronous copy: plans are built outside the hot path
-    if (cudaMemcpy(pl->kb_dev, v.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cenn_set_error("k-block table upload failed"); return nullptr; }
-    return reinterpret_cast<tc::KbDesc *>(pl->kb_dev);
-}
-
 const int SMEM_LIMIT = 227 * 1024;
 
 template <int BN>
@@ -91,16 +83,17 @@ int set_attr_wgrad() {
     if (!done) { CK(cudaFuncSetAttribute(tc::wgrad_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); done = true; }
     return 0;
 }
-int config_gather(TcPlan *pl, int BN, int num_kb, dim3 grid) {
+int config_gather(cenn_state *s, TcPlan *pl, int BN, int num_kb, int total_tiles) {
     const int stage_bytes = 128 * 128 + BN * 128;
-    const int fixed = 1024 /*align*/ + 8 * (2 * 8 + 1) + 16 + 2 * BN * 4 + 4 * 32 * 33 * 4 + 256;
+    const int fixed = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 2 * BN * 4 + 4 * 32 * 33 * 4 + 256;
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
-    if (stages > num_kb) stages = num_kb;
-    if (stages < 1) stages = 1;
+    if (stages < 2) stages = 2;
     pl->kind = 1; pl->BN = BN; pl->stages = stages;
     pl->smem = (size_t)stages * stage_bytes + fixed;
-    pl->grid[0] = grid.x; pl->grid[1] = grid.y; pl->grid[2] = grid.z;
+    pl->grid[0] = (unsigned)(total_tiles < s->sm_count ? total_tiles : s->sm_count);   // persistent: one CTA per SM
+    pl->grid[1] = 1; pl->grid[2] = 1;
+    (void)num_kb;
     switch (BN) {
         case 32: return set_attr_gather<32>();
         case 64: return set_attr_gather<64>();
@@ -130,7 +123,8 @@ int config_wgrad(TcPlan *pl, int BN, int nkb, dim3 grid) {
 }
 
 int pick_bn(int n_valid, int m_tiles, int sm_count) {
-    // widest tile that still gives roughly a full wave of CTAs; N tiles of 256 run the MMA at full rate
+    // widest N tile (256-wide MMAs run the tensor pipe at full rate with the least smem traffic) that still
+    // leaves at least one tile per SM for the persistent kernel
     int bn = 256;
     while (bn > 32 && (bn / 2 >= n_valid)) bn /= 2;
     while (bn > 64 && (long long)m_tiles * ((n_valid + bn - 1) / bn) < sm_count) bn /= 2;
@@ -232,7 +226,7 @@ int tc_unpack_grad_add(cenn_state *s, const float *g, float *gw, int Cs, int Cl,
 
 // ------------------------------------------------------------------ plan storage helpers
 static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap larger than the plan slot");
-static_assert(sizeof(tc::GatherGemmParams) <= 512 && sizeof(tc::WgradParams) <= 512, "kernel params larger than the plan slot");
+static_assert(sizeof(tc::GatherGemmParams) <= 1536 && sizeof(tc::WgradParams) <= 1536, "kernel params larger than the plan slot");
 static CUtensorMap *planA(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmA); }
 static CUtensorMap *planB(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmB); }
 
@@ -288,24 +282,18 @@ int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, b
     int BN = pick_bn(Cs, m_tiles, s->sm_count);
     if (map_2d(planB(pl), Wf, (uint64_t)16 * Clp, (uint64_t)Cs, BN)) return 1;
     int chunks = Clp / 64;
-    std::vector<tc::KbDesc> kb;
     for (int t = 0; t < 16; ++t) {
         int u = t / 4, v = t % 4;
-        for (int c = 0; c < chunks; ++c) {
-            tc::KbDesc d = {};
-            d.a0 = PYS[v] * Clp + c * 64; d.a1 = DYS[v]; d.a2 = PYS[u]; d.a3 = DYS[u];
-            d.b0 = t * Clp + c * 64; d.b1 = 0;
-            kb.push_back(d);
-        }
+        p.A0[0][t] = PYS[v] * Clp; p.A1[0][t] = DYS[v]; p.A2[0][t] = PYS[u]; p.A3[0][t] = DYS[u];
     }
-    p.kb = kb_upload(s, pl, kb); if (!p.kb) return 1;
-    p.num_kb = (int)kb.size();
+    p.chunks = chunks; p.bk_per_tap = Clp; p.num_kb = 16 * chunks;
+    p.m_tiles = m_tiles; p.n_tiles = (Cs + BN - 1) / BN; p.num_phases = 1;
     p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cs;
     p.sX = Csp; p.sY = (long long)w * Csp; p.sN = (long long)h * w * Csp;
     fill_epilogue(p, ep, S);
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * N * h * w * (double)Cs * 16.0 * Clp;
-    return config_gather(pl, BN, p.num_kb, dim3(m_tiles, (Cs + BN - 1) / BN, 1));
+    return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles);
 }
 
 // ------------------------------------------------------------------ P2: dgrad-type (4 sub-pixel phases)
@@ -322,21 +310,16 @@ int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, b
     REQUIRE(cl_rows >= Cl, "tc_dgrad_s2: cl_rows (%d) too small for Cl %d", cl_rows, Cl);
     if (map_2d(planB(pl), Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
     int chunks = Csp / 64;
-    std::vector<tc::KbDesc> kb;
     for (int ph = 0; ph < 4; ++ph) {
         int py = ph >> 1, px = ph & 1;
         for (int ab = 0; ab < 4; ++ab) {
             int a = ab >> 1, b = ab & 1;
-            for (int c = 0; c < chunks; ++c) {
-                tc::KbDesc d = {};
-                d.a0 = c * 64; d.a1 = DYP[px][b]; d.a2 = 0; d.a3 = DYP[py][a];
-                d.b0 = ab * Csp + c * 64; d.b1 = ph * cl_rows;
-                kb.push_back(d);
-            }
+            p.A0[ph][ab] = 0; p.A1[ph][ab] = DYP[px][b]; p.A2[ph][ab] = 0; p.A3[ph][ab] = DYP[py][a];
         }
+        p.B1[ph] = ph * cl_rows;
     }
-    p.kb = kb_upload(s, pl, kb); if (!p.kb) return 1;
-    p.num_kb = 4 * chunks;
+    p.chunks = chunks; p.bk_per_tap = Csp; p.num_kb = 4 * chunks;
+    p.m_tiles = m_tiles; p.n_tiles = (Cl + BN - 1) / BN; p.num_phases = 4;
     p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cl;
     int W2 = 2 * w, H2 = 2 * h;
     p.sX = 2LL * Clp; p.sY = 2LL * W2 * Clp; p.sN = (long long)H2 * W2 * Clp;
@@ -344,7 +327,7 @@ int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, b
     fill_epilogue(p, ep, L);
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * N * h * w * (double)Cl * 16.0 * Csp;
-    return config_gather(pl, BN, p.num_kb, dim3(m_tiles, (Cl + BN - 1) / BN, 4));
+    return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles * 4);
 }
 
 // ------------------------------------------------------------------ P4: plain GEMM
@@ -364,16 +347,14 @@ int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *
     int BN = pick_bn(Nc, m_tiles, s->sm_count);
     if (map_2d(planB(pl), B, (uint64_t)K, (uint64_t)Nc, BN)) return 1;
     int nkb = (K + 63) / 64;
-    std::vector<tc::KbDesc> kb(nkb);
-    for (int i = 0; i < nkb; ++i) { kb[i] = tc::KbDesc{}; kb[i].a0 = i * 64; kb[i].b0 = i * 64; }
-    p.kb = kb_upload(s, pl, kb); if (!p.kb) return 1;
-    p.num_kb = nkb;
+    p.chunks = nkb; p.bk_per_tap = 0; p.num_kb = nkb;          // a single "tap" whose chunks walk K
+    p.m_tiles = m_tiles; p.n_tiles = (Nc + BN - 1) / BN; p.num_phases = 1;
     p.out_w = M; p.out_h = 1; p.out_n = 1; p.n_valid = Nc;
     p.sX = ldo; p.sY = 0; p.sN = 0;
     fill_epilogue(p, ep, out);
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * M * (double)Nc * K;
-    return config_gather(pl, BN, p.num_kb, dim3(m_tiles, (Nc + BN - 1) / BN, 1));
+    return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles);
 }
 
 // ------------------------------------------------------------------ P3 / P5: wgrad

@@ -31,7 +31,7 @@ struct TcPlan {
     size_t smem = 0;
     alignas(64) unsigned char tmA[128];
     alignas(64) unsigned char tmB[128];
-    alignas(16) unsigned char params[512];
+    alignas(16) unsigned char params[1536];
     void *kb_dev = nullptr;       // owned device k-block table (gather GEMM)
     double flops = 0;             // algorithmic FLOPs of one launch
 };

@@ -107,19 +107,18 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int
 }
 
 // ------------------------------------------------------------------ kernel parameters
-struct KbDesc {        // per k-block TMA coordinates (offsets added to the tile origin)
-    int a0, a1, a2, a3;  // A box: dim0 (channel) start, dim1 (x) offset, dim2 (parity/dummy) coord, dim3 (y) offset
-    int b0, b1;          // B box: dim0 (k) start, dim1 (row) offset added to the n-tile origin
-    int pad0, pad1;
-};
-
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
 
+// K-block kb of a tile = (tap = kb / chunks, c = kb % chunks).  TMA coordinates (all tables live in kernel parameters):
+//   A box: (A0[ph][tap] + 64 c,  x0 + A1[ph][tap],  A2[ph][tap],  y0 + A3[ph][tap],  n0)
+//   B box: (tap * bk_per_tap + 64 c,  n_tile * BN + B1[ph])
 struct GatherGemmParams {
-    const KbDesc *kb;        // [phases][num_kb]
-    int num_kb;
+    int num_kb, chunks, bk_per_tap;
+    int A0[4][16], A1[4][16], A2[4][16], A3[4][16];
+    int B1[4];
+    int m_tiles, n_tiles, num_phases;   // tiles are enumerated m fastest, then n, then phase
     int box_w, box_h, box_n; // pixels per M tile (product == 128)
-    int tiles_x, tiles_y;    // tile grid within an image batch slab: m-tile -> (tx, ty, tn)
+    int tiles_x, tiles_y;    // m-tile -> (tx, ty, tn)
     int out_w, out_h, out_n; // logical extent of the output pixel grid (for masking)
     int n_valid;             // valid output channels (columns >= n_valid are dropped)
     // output addressing: elem offset = n*sN + y*sY + x*sX + phase_off[phase] + column
@@ -155,36 +154,40 @@ struct WgradParams {
 
 static constexpr int GEMM_THREADS = 192;
 
-// ------------------------------------------------------------------ K-major gather GEMM
+// ------------------------------------------------------------------ K-major gather GEMM (persistent)
+// One CTA per SM loops over output tiles (static round-robin).  Three pipelines run concurrently:
+//   TMA producer  -> smem ring (full/empty mbarriers)         -> MMA issuer
+//   MMA issuer    -> 2 TMEM accumulators (tmem_full/empty)    -> epilogue warps
+// so the epilogue of tile t (TMEM -> registers -> bias/BN-statistics/activation -> global) overlaps the MMAs of tile t+1.
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GatherGemmParams p, int stages) {
+gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GatherGemmParams p, int stages) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr uint32_t A_BYTES = 128 * 128;       // 128 rows x 64 bf16
     constexpr uint32_t B_BYTES = BN * 128;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *tiles = smem;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)stages * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + stages;
-    uint64_t *acc_bar = empty_bar + stages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+    uint64_t *tfull_bar = empty_bar + stages;      // [2] accumulator ready
+    uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
     float *col_acc = reinterpret_cast<float *>(tmem_slot + 2);          // [2][BN] per-CTA column sums for BN statistics
     float *stage_f = col_acc + 2 * BN;                                  // [4 warps][32][33] transposition buffer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int phase_id = blockIdx.z;
-    const int mt = blockIdx.x, nt = blockIdx.y;
-    const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-    const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
-    const KbDesc *kbd = p.kb + (size_t)phase_id * p.num_kb;
+    const int tiles_per_phase = p.m_tiles * p.n_tiles;
+    const int total_tiles = tiles_per_phase * p.num_phases;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(acc_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) col_acc[i] = 0.f;
@@ -196,119 +199,169 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                int s = kb % stages;
-                uint32_t ph = (uint32_t)(kb / stages) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                KbDesc d = kbd[kb];
-                uint8_t *a_dst = tiles + (size_t)s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_5d(&tmA, &full_bar[s], a_dst, d.a0, x0 + d.a1, d.a2, y0 + d.a3, n0);
-                tma_load_2d(&tmB, &full_bar[s], b_dst, d.b0, nt * BN + d.b1);
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int phase_id = t / tiles_per_phase, r = t - phase_id * tiles_per_phase;
+                const int nt = r / p.m_tiles, mt = r - nt * p.m_tiles;
+                const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+                const int brow = nt * BN + p.B1[phase_id];
+                int tap = 0, c = 0;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t *a_dst = tiles + (size_t)s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_5d(&tmA, &full_bar[s], a_dst, p.A0[phase_id][tap] + c * 64, x0 + p.A1[phase_id][tap], p.A2[phase_id][tap], y0 + p.A3[phase_id][tap], n0);
+                    tma_load_2d(&tmB, &full_bar[s], b_dst, tap * p.bk_per_tap + c * 64, brow);
+                    if (++c == p.chunks) { c = 0; ++tap; }
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-            int s = kb % stages;
-            uint32_t ph = (uint32_t)(kb / stages) & 1u;
-            mbar_wait(&full_bar[s], ph);
+        int s = 0; uint32_t ph = 0;
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);      // epilogue has drained this accumulator
             tc_fence_after();
-            if (lane == 0) {
-                uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide k-block; +32 B inside the swizzle atom
-                    uint64_t ad = make_desc(a_addr + k * 32, 16, 1024), bd = make_desc(b_addr + k * 32, 16, 1024);
-                    umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide k-block; +32 B inside the swizzle atom
+                        uint64_t ad = make_desc(a_addr + k * 32, 16, 1024), bd = make_desc(b_addr + k * 32, 16, 1024);
+                        umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);                     // frees the smem slot when these MMAs retire
+                    if (kb == p.num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
                 }
-                umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
-                if (kb == p.num_kb - 1) umma_commit(acc_bar);  // accumulator complete
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
-            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
     } else {
         // ---------------- epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 (= tile rows)
         const int q = warp & 3;
+        const int et = threadIdx.x - 64;                 // 0..127 within the epilogue group
         const int row = q * 32 + lane;
         const int rx = row % p.box_w, ry = (row / p.box_w) % p.box_h, rn = row / (p.box_w * p.box_h);
-        const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
-        const bool row_ok = px < p.out_w && py < p.out_h && pn < p.out_n;
-        const long long obase = (long long)pn * p.sN + (long long)py * p.sY + (long long)px * p.sX + p.phase_off[phase_id];
         float *my_stage = stage_f + (size_t)(warp - 2) * 32 * 33;
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
+        int acc = 0; uint32_t acc_ph = 0;
+        int stat_key = -1;                               // (phase, n-tile) the per-CTA column sums belong to
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int phase_id = t / tiles_per_phase, r = t - phase_id * tiles_per_phase;
+            const int nt = r / p.m_tiles, mt = r - nt * p.m_tiles;
+            const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+            const int px = tx * p.box_w + rx, py = ty * p.box_h + ry, pn = tn * p.box_n + rn;
+            const bool row_ok = px < p.out_w && py < p.out_h && pn < p.out_n;
+            const long long obase = (long long)pn * p.sN + (long long)py * p.sY + (long long)px * p.sX + p.phase_off[phase_id];
+            if (p.stats && nt != stat_key) {
+                // the column sums accumulated so far belong to another n-tile: flush them
+                if (stat_key >= 0) {
+                    epi_bar_sync();
+                    for (int i = et; i < BN; i += 128) {
+                        int c = stat_key * BN + i;
+                        if (c < p.n_valid) { atomicAdd(p.stats + c, col_acc[i]); atomicAdd(p.stats + p.stats_stride + c, col_acc[BN + i]); }
+                        col_acc[i] = 0.f; col_acc[BN + i] = 0.f;
+                    }
+                    epi_bar_sync();
+                }
+                stat_key = nt;
+            }
+            mbar_wait(&tfull_bar[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_ld_wait();
-            const int colbase = nt * BN + c0;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float f = __uint_as_float(r[j]);
-                if (p.bias && colbase + j < p.n_valid) f += __ldg(p.bias + colbase + j);
-                v[j] = f;
-            }
-            if (p.stats) {
-                // transpose through smem so that lane j sums column j over this warp's 32 rows
-#pragma unroll
-                for (int j = 0; j < 32; ++j) my_stage[lane * 33 + j] = row_ok ? v[j] : 0.f;
-                __syncwarp();
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) { float t = my_stage[i * 33 + lane]; s1 += t; s2 += t * t; }
-                atomicAdd(&col_acc[c0 + lane], s1);
-                atomicAdd(&col_acc[BN + c0 + lane], s2);
-                __syncwarp();
-            }
-            if (p.act != ACT_NONE) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t rr[32];
+                tmem_ld32(t_addr + (uint32_t)c0, rr);
+                tmem_ld_wait();
+                if (c0 + 32 >= BN) {                     // last read of this accumulator: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
+                const int colbase = nt * BN + c0;
+                float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float f = v[j];
-                    if (p.act == ACT_LEAKY) f = f > 0.f ? f : f * p.act_param;
-                    else if (p.act == ACT_RELU) f = f > 0.f ? f : 0.f;
-                    else if (p.act == ACT_TANH) f = tanhf(f);
-                    else if (p.act == ACT_SIGMOID) f = 1.f / (1.f + __expf(-f));
+                    float f = __uint_as_float(rr[j]);
+                    if (p.bias && colbase + j < p.n_valid) f += __ldg(p.bias + colbase + j);
                     v[j] = f;
                 }
-            }
-            if (row_ok) {
-                if (p.out_bf16) {
-                    __nv_bfloat16 *o = p.out_bf16 + obase + colbase;
+                if (p.stats) {
+                    // transpose through smem so that lane j sums column j over this warp's 32 rows
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        if (colbase + j + 8 <= p.n_valid) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-                            *reinterpret_cast<uint4 *>(o + j) = pk;
-                        } else {
-                            for (int jj = j; jj < j + 8; ++jj) if (colbase + jj < p.n_valid) o[jj] = __float2bfloat16(v[jj]);
+                    for (int j = 0; j < 32; ++j) my_stage[lane * 33 + j] = row_ok ? v[j] : 0.f;
+                    __syncwarp();
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) { float tt = my_stage[i * 33 + lane]; s1 += tt; s2 += tt * tt; }
+                    atomicAdd(&col_acc[c0 + lane], s1);
+                    atomicAdd(&col_acc[BN + c0 + lane], s2);
+                    __syncwarp();
+                }
+                if (p.act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float f = v[j];
+                        if (p.act == ACT_LEAKY) f = f > 0.f ? f : f * p.act_param;
+                        else if (p.act == ACT_RELU) f = f > 0.f ? f : 0.f;
+                        else if (p.act == ACT_TANH) f = tanhf(f);
+                        else if (p.act == ACT_SIGMOID) f = 1.f / (1.f + __expf(-f));
+                        v[j] = f;
+                    }
+                }
+                if (row_ok) {
+                    if (p.out_bf16) {
+                        __nv_bfloat16 *o = p.out_bf16 + obase + colbase;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (colbase + j + 8 <= p.n_valid) {
+                                uint4 pk;
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                                pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                                *reinterpret_cast<uint4 *>(o + j) = pk;
+                            } else if (colbase + j + 4 <= p.n_valid && ((obase + colbase + j) & 3) == 0) {
+                                uint2 pk;
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                                *reinterpret_cast<uint2 *>(o + j) = pk;
+                                for (int jj = j + 4; jj < j + 8; ++jj) if (colbase + jj < p.n_valid) o[jj] = __float2bfloat16(v[jj]);
+                            } else {
+                                for (int jj = j; jj < j + 8; ++jj) if (colbase + jj < p.n_valid) o[jj] = __float2bfloat16(v[jj]);
+                            }
+                        }
+                    }
+                    if (p.out_f32) {
+                        float *o = p.out_f32 + obase + colbase;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (colbase + j + 4 <= p.n_valid) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            else for (int jj = j; jj < j + 4; ++jj) if (colbase + jj < p.n_valid) o[jj] = v[jj];
                         }
                     }
                 }
-                if (p.out_f32) {
-                    float *o = p.out_f32 + obase + colbase;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (colbase + j + 4 <= p.n_valid) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        else for (int jj = j; jj < j + 4; ++jj) if (colbase + jj < p.n_valid) o[jj] = v[jj];
-                    }
-                }
+            }
+            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+        }
+        if (p.stats && stat_key >= 0) {
+            epi_bar_sync();
+            for (int i = et; i < BN; i += 128) {
+                int c = stat_key * BN + i;
+                if (c < p.n_valid) { atomicAdd(p.stats + c, col_acc[i]); atomicAdd(p.stats + p.stats_stride + c, col_acc[BN + i]); }
             }
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (p.stats) {
-        for (int i = threadIdx.x; i < BN; i += blockDim.x) {
-            int c = nt * BN + i;
-            if (c < p.n_valid) { atomicAdd(p.stats + c, col_acc[i]); atomicAdd(p.stats + p.stats_stride + c, col_acc[BN + i]); }
-        }
-    }
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
