@@ -2,6 +2,7 @@
 // activations, weight repacking, launch configuration, and NCHW-fp32 wrappers for the op-level ABI.
 #include "conv_tc.h"
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "tc_gemm.cuh"
@@ -61,6 +62,7 @@ int map_2d(CUtensorMap *m, const bf16 *B, uint64_t K, uint64_t rows, int box_row
     return make_map(m, B, 2, dims, st, box);
 }
 
+int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
 int pow2_le(int v, int cap) { int p = 1; while (p * 2 <= v && p * 2 <= cap) p *= 2; return p; }
 // split `total` pixels per tile over (w, h, n)
 void choose_box(int w, int h, int total, int &bw, int &bh, int &bn) {
@@ -132,6 +134,7 @@ int pick_bn(int n_valid, int m_tiles, int sm_count) {
 }
 
 void fill_epilogue(tc::GatherGemmParams &p, const TcEpilogue &ep, bf16 *out) {
+    p.dbg = reinterpret_cast<unsigned long long *>(ep.dbg);
     p.bias = ep.bias; p.stats = ep.stats; p.stats_stride = ep.stats_stride; p.act = ep.act; p.act_param = ep.act_param;
     p.out_bf16 = ep.no_bf16 ? nullptr : out; p.out_f32 = ep.out_f32;
 }
@@ -276,7 +279,7 @@ int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, b
     choose_box(w, h, 128, bw, bh, bn);
     if (map_gather(planA(pl), L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
     tc::GatherGemmParams p = {};
-    p.box_w = bw; p.box_h = bh; p.box_n = bn;
+    p.box_w = bw; p.box_h = bh; p.box_n = bn; p.bw_log2 = ilog2(bw); p.bh_log2 = ilog2(bh);
     p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
     int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
     int BN = pick_bn(Cs, m_tiles, s->sm_count);
@@ -303,7 +306,7 @@ int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, b
     choose_box(w, h, 128, bw, bh, bn);
     if (map_plain(planA(pl), S, N, h, w, Csp, bw, bh, bn)) return 1;
     tc::GatherGemmParams p = {};
-    p.box_w = bw; p.box_h = bh; p.box_n = bn;
+    p.box_w = bw; p.box_h = bh; p.box_n = bn; p.bw_log2 = ilog2(bw); p.bh_log2 = ilog2(bh);
     p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
     int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
     int BN = pick_bn(Cl, m_tiles * 4, s->sm_count);
@@ -341,7 +344,7 @@ int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *
     dims[1] = (uint64_t)M;                 // the true extent: rows >= M are out of bounds -> zero filled
     if (make_map(planA(pl), A, 5, dims, st, box)) return 1;
     tc::GatherGemmParams p = {};
-    p.box_w = 128; p.box_h = 1; p.box_n = 1;
+    p.box_w = 128; p.box_h = 1; p.box_n = 1; p.bw_log2 = 7; p.bh_log2 = 0;
     p.tiles_x = (M + 127) / 128; p.tiles_y = 1;
     int m_tiles = p.tiles_x;
     int BN = pick_bn(Nc, m_tiles, s->sm_count);
@@ -524,5 +527,43 @@ int tc_conv_wgrad_nchw(cenn_state *s, const float *x, const float *gy, float *gw
     int rc = s2 ? tc_wgrad_s2(s, gs, xl, g, N, h, wd, O, Csp, Clp, scale, 1) : tc_wgrad_plain(s, gs, xl, g, N, O, Csp, 16 * Clp, scale, 1);
     if (rc) return -1;
     if (tc_unpack_grad_add(s, g, gw, O, C, Clp, 16)) return -1;
+    return 0;
+}
+
+// ------------------------------------------------------------------ debug probe (tools/gemm_probe.py)
+// Runs one primitive on zero-filled operands `iters` times; returns the mean duration and CTA 0's per-role cycle counters:
+//   dbg[0] producer wait(empty) [1] producer total | [2] MMA wait(full) [3] MMA wait(tmem empty) [4] MMA total |
+//   [5] epilogue wait(tmem full) [6] epilogue total [7] tiles of CTA 0 [8] epilogue tcgen05.ld cycles
+extern "C" CENN_API int cenn_debug_gemm_probe(cenn_state *s, int kind, int N, int h, int w, int Cs, int Cl, int with_stats, int act,
+                                              int iters, float *ms_out, unsigned long long *dbg_out) {
+    API_BEGIN(s);
+    size_t nL, nS, nW;
+    int Csp = round_up(Cs, 8), Clp = round_up(Cl, 64);
+    if (kind == 0) { nL = (size_t)N * 4 * h * w * Clp; nS = (size_t)N * h * w * Csp; nW = (size_t)Cs * 16 * Clp; }          // fprop_s2
+    else if (kind == 1) { Csp = round_up(Cs, 64); Clp = round_up(Cl, 8); nL = (size_t)N * 4 * h * w * Clp; nS = (size_t)N * h * w * Csp; nW = (size_t)16 * Clp * Csp; }  // dgrad_s2
+    else { nL = (size_t)N * Cl; nS = (size_t)N * Csp; nW = (size_t)Cs * Cl; }                                              // gemm: M=N, K=Cl, Nc=Cs
+    bf16 *L, *S, *W; float *stats; unsigned long long *dbg;
+    CK(cudaMalloc(&L, nL * 2)); CK(cudaMalloc(&S, nS * 2)); CK(cudaMalloc(&W, nW * 2)); CK(cudaMalloc(&stats, 2 * 4096 * 4)); CK(cudaMalloc(&dbg, 16 * 8));
+    CK(cudaMemset(L, 0, nL * 2)); CK(cudaMemset(S, 0, nS * 2)); CK(cudaMemset(W, 0, nW * 2)); CK(cudaMemset(stats, 0, 2 * 4096 * 4)); CK(cudaMemset(dbg, 0, 16 * 8));
+    TcEpilogue ep; ep.act = act; ep.act_param = 0.2f; ep.dbg = dbg;
+    if (getenv("PROBE_NO_OUT")) ep.no_bf16 = true;
+    if (with_stats) { ep.stats = stats; ep.stats_stride = 4096; }
+    TcPlan pl; int rc;
+    if (kind == 0) rc = tc_plan_fprop_s2(s, &pl, L, W, S, N, h, w, Cs, Csp, Clp, ep);
+    else if (kind == 1) rc = tc_plan_dgrad_s2(s, &pl, S, W, L, N, h, w, Csp, Cl, Clp, Clp, ep);
+    else rc = tc_plan_gemm(s, &pl, L, W, S, N, Cs, Cl, Csp, ep);
+    if (rc) return 1;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) if (tc_launch(s, &pl)) return 1;
+    CK(cudaEventRecord(e0, s->stream));
+    for (int i = 0; i < iters; ++i) if (tc_launch(s, &pl)) return 1;
+    CK(cudaEventRecord(e1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    CK(cudaMemcpy(dbg_out, dbg, 16 * 8, cudaMemcpyDeviceToHost));
+    dbg_out[15] = ((unsigned long long)pl.grid[0] << 32) | (unsigned)(pl.BN << 8) | (unsigned)pl.stages;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(L); cudaFree(S); cudaFree(W); cudaFree(stats); cudaFree(dbg);
     return 0;
 }

@@ -20,6 +20,7 @@ struct TcEpilogue {
     float act_param = 0.f;
     float *out_f32 = nullptr;      // optional fp32 copy of the output (same NHWC addressing)
     bool no_bf16 = false;
+    void *dbg = nullptr;           // optional per-role cycle counters (debug probe)
 };
 
 // A prepared launch: tensor maps, kernel parameters, k-block table and grid are built once (shapes and

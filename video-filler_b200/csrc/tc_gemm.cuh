@@ -85,6 +85,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor (SM100 "version 1"), SWIZZLE_128B; addresses/offsets in 16-byte units.
@@ -117,7 +121,8 @@ struct GatherGemmParams {
     int A0[4][16], A1[4][16], A2[4][16], A3[4][16];
     int B1[4];
     int m_tiles, n_tiles, num_phases;   // tiles are enumerated m fastest, then n, then phase
-    int box_w, box_h, box_n; // pixels per M tile (product == 128)
+    int box_w, box_h, box_n; // pixels per M tile (product == 128), all powers of two
+    int bw_log2, bh_log2;
     int tiles_x, tiles_y;    // m-tile -> (tx, ty, tn)
     int out_w, out_h, out_n; // logical extent of the output pixel grid (for masking)
     int n_valid;             // valid output channels (columns >= n_valid are dropped)
@@ -131,6 +136,7 @@ struct GatherGemmParams {
     int stats_stride;
     int act;                 // applied after bias, before the store (stats are taken before the activation)
     float act_param;
+    unsigned long long *dbg; // [opt] per-role cycle counters of CTA 0 (tools/gemm_probe.py)
 };
 
 struct WgradParams {
@@ -169,7 +175,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr uint32_t B_BYTES = BN * 128;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, still a __shared__ pointer
     uint8_t *tiles = smem;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)stages * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + stages;
@@ -200,6 +206,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
+            long long w_empty = 0, t_begin = clock64();
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int phase_id = t / tiles_per_phase, r = t - phase_id * tiles_per_phase;
                 const int nt = r / p.m_tiles, mt = r - nt * p.m_tiles;
@@ -208,7 +215,9 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int brow = nt * BN + p.B1[phase_id];
                 int tap = 0, c = 0;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
+                    long long t0 = clock64();
                     mbar_wait(&empty_bar[s], ph ^ 1u);
+                    w_empty += clock64() - t0;
                     uint8_t *a_dst = tiles + (size_t)s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
                     mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     tma_load_5d(&tmA, &full_bar[s], a_dst, p.A0[phase_id][tap] + c * 64, x0 + p.A1[phase_id][tap], p.A2[phase_id][tap], y0 + p.A3[phase_id][tap], n0);
@@ -217,17 +226,23 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
+            if (p.dbg && blockIdx.x == 0) { p.dbg[0] = (unsigned long long)w_empty; p.dbg[1] = (unsigned long long)(clock64() - t_begin); }
         }
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
         int s = 0; uint32_t ph = 0;
         int acc = 0; uint32_t acc_ph = 0;
+        long long w_full = 0, w_tempty = 0, t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            long long t0 = clock64();
             mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);      // epilogue has drained this accumulator
+            w_tempty += clock64() - t0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
             for (int kb = 0; kb < p.num_kb; ++kb) {
+                t0 = clock64();
                 mbar_wait(&full_bar[s], ph);
+                w_full += clock64() - t0;
                 tc_fence_after();
                 if (lane == 0) {
                     uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
@@ -244,25 +259,36 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
+        if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = (unsigned long long)w_full; p.dbg[3] = (unsigned long long)w_tempty; p.dbg[4] = (unsigned long long)(clock64() - t_begin); }
     } else {
         // ---------------- epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 (= tile rows)
         const int q = warp & 3;
         const int et = threadIdx.x - 64;                 // 0..127 within the epilogue group
-        const int row = q * 32 + lane;
-        const int rx = row % p.box_w, ry = (row / p.box_w) % p.box_h, rn = row / (p.box_w * p.box_h);
         float *my_stage = stage_f + (size_t)(warp - 2) * 32 * 33;
+        const int bw_mask = p.box_w - 1, bh_mask = p.box_h - 1, bwh_log2 = p.bw_log2 + p.bh_log2;
+        // rows this lane touches: its own TMEM lane (staging / masking) and the 4 rows it stores (8 columns each)
+        const int row = q * 32 + lane;
+        const int rx = row & bw_mask, ry = (row >> p.bw_log2) & bh_mask, rn = row >> bwh_log2;
+        int sx[4], sy[4], sn[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int r = q * 32 + g * 8 + (lane >> 2);
+            sx[g] = r & bw_mask; sy[g] = (r >> p.bw_log2) & bh_mask; sn[g] = r >> bwh_log2;
+        }
+        const int cseg = (lane & 3) * 8;
         int acc = 0; uint32_t acc_ph = 0;
-        int stat_key = -1;                               // (phase, n-tile) the per-CTA column sums belong to
+        int stat_key = -1;                               // n-tile the per-CTA column sums belong to
+        long long w_tfull = 0, t_begin = clock64();
+        int ntile = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int phase_id = t / tiles_per_phase, r = t - phase_id * tiles_per_phase;
-            const int nt = r / p.m_tiles, mt = r - nt * p.m_tiles;
+            ++ntile;
+            const int phase_id = t / tiles_per_phase, r0 = t - phase_id * tiles_per_phase;
+            const int nt = r0 / p.m_tiles, mt = r0 - nt * p.m_tiles;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-            const int px = tx * p.box_w + rx, py = ty * p.box_h + ry, pn = tn * p.box_n + rn;
-            const bool row_ok = px < p.out_w && py < p.out_h && pn < p.out_n;
-            const long long obase = (long long)pn * p.sN + (long long)py * p.sY + (long long)px * p.sX + p.phase_off[phase_id];
+            const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+            const bool row_ok = (x0 + rx) < p.out_w && (y0 + ry) < p.out_h && (n0 + rn) < p.out_n;
             if (p.stats && nt != stat_key) {
-                // the column sums accumulated so far belong to another n-tile: flush them
-                if (stat_key >= 0) {
+                if (stat_key >= 0) {                     // the column sums so far belong to another n-tile: flush them
                     epi_bar_sync();
                     for (int i = et; i < BN; i += 128) {
                         int c = stat_key * BN + i;
@@ -273,81 +299,171 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 stat_key = nt;
             }
+            long long t0 = clock64();
             mbar_wait(&tfull_bar[acc], acc_ph);
+            w_tfull += clock64() - t0;
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t rr[32];
-                tmem_ld32(t_addr + (uint32_t)c0, rr);
+            int ncols = p.n_valid - nt * BN; ncols = ncols > BN ? BN : ncols;
+            const long long tile_base = p.phase_off[phase_id] + (long long)nt * BN;
+            if (ncols <= 8 && !p.stats) {
+                // ---- thin output (<= 8 valid columns, e.g. the 3-channel image): narrow TMEM read, one row per lane
+                uint32_t r8[8];
+                tmem_ld8(t_addr, r8);
                 tmem_ld_wait();
-                if (c0 + 32 >= BN) {                     // last read of this accumulator: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                }
-                const int colbase = nt * BN + c0;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float f = __uint_as_float(rr[j]);
-                    if (p.bias && colbase + j < p.n_valid) f += __ldg(p.bias + colbase + j);
-                    v[j] = f;
-                }
-                if (p.stats) {
-                    // transpose through smem so that lane j sums column j over this warp's 32 rows
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) my_stage[lane * 33 + j] = row_ok ? v[j] : 0.f;
-                    __syncwarp();
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) { float tt = my_stage[i * 33 + lane]; s1 += tt; s2 += tt * tt; }
-                    atomicAdd(&col_acc[c0 + lane], s1);
-                    atomicAdd(&col_acc[BN + c0 + lane], s2);
-                    __syncwarp();
-                }
-                if (p.act != ACT_NONE) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float f = v[j];
-                        if (p.act == ACT_LEAKY) f = f > 0.f ? f : f * p.act_param;
-                        else if (p.act == ACT_RELU) f = f > 0.f ? f : 0.f;
-                        else if (p.act == ACT_TANH) f = tanhf(f);
-                        else if (p.act == ACT_SIGMOID) f = 1.f / (1.f + __expf(-f));
-                        v[j] = f;
-                    }
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (row_ok) {
-                    if (p.out_bf16) {
-                        __nv_bfloat16 *o = p.out_bf16 + obase + colbase;
+                    float w8[8];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (colbase + j + 8 <= p.n_valid) {
-                                uint4 pk;
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                                pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-                                *reinterpret_cast<uint4 *>(o + j) = pk;
-                            } else if (colbase + j + 4 <= p.n_valid && ((obase + colbase + j) & 3) == 0) {
-                                uint2 pk;
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                                *reinterpret_cast<uint2 *>(o + j) = pk;
-                                for (int jj = j + 4; jj < j + 8; ++jj) if (colbase + jj < p.n_valid) o[jj] = __float2bfloat16(v[jj]);
-                            } else {
-                                for (int jj = j; jj < j + 8; ++jj) if (colbase + jj < p.n_valid) o[jj] = __float2bfloat16(v[jj]);
-                            }
+                    for (int k = 0; k < 8; ++k) {
+                        float f = __uint_as_float(r8[k]);
+                        if (k < ncols) {
+                            if (p.bias) f += __ldg(p.bias + nt * BN + k);
+                            if (p.act == ACT_LEAKY) f = f > 0.f ? f : f * p.act_param;
+                            else if (p.act == ACT_RELU) f = fmaxf(f, 0.f);
+                            else if (p.act == ACT_TANH) f = tanhf(f);
+                            else if (p.act == ACT_SIGMOID) f = 1.f / (1.f + __expf(-f));
+                        }
+                        w8[k] = f;
+                    }
+                    const long long ro = (long long)(n0 + rn) * p.sN + (long long)(y0 + ry) * p.sY + (long long)(x0 + rx) * p.sX + tile_base;
+                    if (p.out_bf16) {
+                        __nv_bfloat16 *o = p.out_bf16 + ro;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(w8[0], w8[1]), h1 = __floats2bfloat162_rn(w8[2], w8[3]);
+                        if (ncols == 4 && (ro & 3) == 0) {
+                            uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                            *reinterpret_cast<uint2 *>(o) = pk;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) if (k < ncols) o[k] = __float2bfloat16(w8[k]);
                         }
                     }
                     if (p.out_f32) {
-                        float *o = p.out_f32 + obase + colbase;
+                        float *o = p.out_f32 + ro;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (colbase + j + 4 <= p.n_valid) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            else for (int jj = j; jj < j + 4; ++jj) if (colbase + jj < p.n_valid) o[jj] = v[jj];
+                        for (int k = 0; k < 8; ++k) if (k < ncols) o[k] = w8[k];
+                    }
+                }
+            } else {
+                const int nchunks = (ncols + 31) >> 5;
+                const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+                const float nrows_ok = (float)__popc(okmask);
+                long long srow[4]; bool sok[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    sok[g] = (x0 + sx[g]) < p.out_w && (y0 + sy[g]) < p.out_h && (n0 + sn[g]) < p.out_n;
+                    srow[g] = (long long)(n0 + sn[g]) * p.sN + (long long)(y0 + sy[g]) * p.sY + (long long)(x0 + sx[g]) * p.sX + tile_base + cseg;
+                }
+#pragma unroll 1
+                for (int ci = 0; ci < nchunks; ++ci) {
+                    const int c0 = ci * 32;
+                    uint32_t rr[32];
+                    tmem_ld32(t_addr + (uint32_t)c0, rr);
+                    tmem_ld_wait();
+                    if (ci == nchunks - 1) {             // last read of this accumulator: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    if (!row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) rr[j] = 0u;
+                    }
+                    // stage the raw fp32 chunk in smem: row = lane, 33-float pitch (conflict-free both ways)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) my_stage[lane * 33 + j] = __uint_as_float(rr[j]);
+                    __syncwarp();
+                    const int col_l = nt * BN + c0 + lane;                 // the column this lane sums
+                    if (p.stats) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                        for (int i = 0; i < 32; ++i) { float tt = my_stage[i * 33 + lane]; s1 += tt; s2 += tt * tt; }
+                        if (p.bias && col_l < p.n_valid) {                 // statistics of (x + b) from those of x
+                            const float bb = __ldg(p.bias + col_l);
+                            s2 += 2.f * bb * s1 + nrows_ok * bb * bb; s1 += nrows_ok * bb;
+                        }
+                        atomicAdd(&col_acc[c0 + lane], s1);
+                        atomicAdd(&col_acc[BN + c0 + lane], s2);
+                    }
+                    // coalesced stores: 4 lanes cover the 32 columns of one row (full 32-byte sectors), 8 rows per pass
+                    const int colseg = nt * BN + c0 + cseg;
+                    const int cvalid = p.n_valid - colseg;                 // valid columns in this lane's 8-wide segment
+                    if (cvalid > 0) {
+                        float w8[4][8];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) w8[g][k] = my_stage[(g * 8 + (lane >> 2)) * 33 + cseg + k];
+                        if (p.bias) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const float bb = k < cvalid ? __ldg(p.bias + colseg + k) : 0.f;
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) w8[g][k] += bb;
+                            }
+                        }
+                        switch (p.act) {                                    // uniform: one activation loop is executed
+                            case ACT_LEAKY: {
+                                const float nv = p.act_param;
+#pragma unroll
+                                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) w8[g][k] = w8[g][k] > 0.f ? w8[g][k] : w8[g][k] * nv;
+                            } break;
+                            case ACT_RELU:
+#pragma unroll
+                                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) w8[g][k] = fmaxf(w8[g][k], 0.f);
+                                break;
+                            case ACT_TANH:
+#pragma unroll 1
+                                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) if (k < cvalid) w8[g][k] = tanhf(w8[g][k]);
+                                break;
+                            case ACT_SIGMOID:
+#pragma unroll 1
+                                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) if (k < cvalid) w8[g][k] = 1.f / (1.f + __expf(-w8[g][k]));
+                                break;
+                            default: break;
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (!sok[g]) continue;
+                            const long long ro = srow[g] + c0;
+                            if (p.out_bf16) {
+                                __nv_bfloat16 *o = p.out_bf16 + ro;
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(w8[g][0], w8[g][1]), h1 = __floats2bfloat162_rn(w8[g][2], w8[g][3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(w8[g][4], w8[g][5]), h3 = __floats2bfloat162_rn(w8[g][6], w8[g][7]);
+                                if (cvalid >= 8 && (ro & 7) == 0) {
+                                    uint4 pk;
+                                    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                                    pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                                    *reinterpret_cast<uint4 *>(o) = pk;
+                                } else if (cvalid >= 4 && (ro & 3) == 0) {
+                                    uint2 pk;
+                                    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                                    *reinterpret_cast<uint2 *>(o) = pk;
+#pragma unroll
+                                    for (int k = 4; k < 8; ++k) if (k < cvalid) o[k] = __float2bfloat16(w8[g][k]);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) if (k < cvalid) o[k] = __float2bfloat16(w8[g][k]);
+                                }
+                            }
+                            if (p.out_f32) {
+                                float *o = p.out_f32 + ro;
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) if (k < cvalid) o[k] = w8[g][k];
+                            }
                         }
                     }
+                    __syncwarp();
                 }
             }
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
@@ -359,6 +475,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (c < p.n_valid) { atomicAdd(p.stats + c, col_acc[i]); atomicAdd(p.stats + p.stats_stride + c, col_acc[BN + i]); }
             }
         }
+        if (p.dbg && blockIdx.x == 0 && et == 0) { p.dbg[5] = (unsigned long long)w_tfull; p.dbg[6] = (unsigned long long)(clock64() - t_begin); p.dbg[7] = (unsigned long long)ntile; }
         tc_fence_before();
     }
     __syncthreads();
@@ -376,7 +493,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
     constexpr uint32_t B_BYTES = (BN / 64) * BOX_BYTES;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = BN;
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, still a __shared__ pointer
     uint8_t *tiles = smem;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)stages * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + stages;
