@@ -146,8 +146,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import video_filler_b200.tensor as T
-    from video_filler_b200 import train
-    from oracle import nets as onets      # synthetic inputs + weight init only (host-side data generation)
+    from video_filler_b200 import synth, train, util
     T.state(local_rank)
     api, st = T.api(), T.state()
     stream = torch.cuda.Stream()
@@ -160,20 +159,15 @@ def main():
     rng = np.random.default_rng(1234)
     nG, nD = trn.param_count(0), trn.param_count(1)
 
-    def init_flat(net_builder):
-        net = net_builder(onets.default_opt("image", batchSize=1))
-        onets.weights_init(net, rng)
-        p, _ = net.getParameters()
-        return p
-    trn.set_params(0, init_flat(onets.build_netG))
-    trn.set_params(1, init_flat(onets.build_netD))
+    trn.set_params(0, util.params_flat(util.weights_init(util.describe_netG(opt), rng)))
+    trn.set_params(1, util.params_flat(util.weights_init(util.describe_netD(opt), rng)))
     assert nG == 71118691 + 2 * (64 + 128 + 256 + 512 + 4000 + 512 + 256 + 128 + 64) and nD > 2764737
 
     drng = np.random.default_rng(1000 + rank)
     n_batches = 2
     host = []
     for _ in range(n_batches):
-        ctx, center = onets.synth_image_batch(B, 128, 4, drng)
+        ctx, center = synth.image_batch(B, 128, 4, drng)
         pa, pb = C.c_void_p(), C.c_void_p()
         api.cenn_host_alloc(st, ctx.nbytes, C.byref(pa)); api.cenn_host_alloc(st, center.nbytes, C.byref(pb))
         ha = np.ctypeslib.as_array((C.c_float * ctx.size).from_address(pa.value)); ha[:] = ctx.ravel()
@@ -186,14 +180,7 @@ def main():
         if world == 1:
             trn.step_device(da.ptr, db.ptr)
             return
-        trn.step_phase(-1, da.ptr, db.ptr)
-        while True:
-            buf, n, dbl, done = trn.sync_info()
-            if done:
-                break
-            if buf and n:
-                dist.all_reduce(wrap_device(buf, n, "f8" if dbl else "f4", torch))
-            trn.step_phase(0, da.ptr, db.ptr)
+        train.dp_step(trn, da.ptr, db.ptr, None, lambda buf, n, dbl: dist.all_reduce(wrap_device(buf, n, "f8" if dbl else "f4", torch)))
 
     losses = None
     with torch.cuda.stream(stream):

@@ -1,0 +1,115 @@
+"""CPU: the Torch7 .t7 format and the util.save / util.load semantics (util.lua:25-105)."""
+import io
+import struct
+
+import numpy as np
+import pytest
+
+from video_filler_b200 import models, t7, util
+
+
+def _i(v): return struct.pack("<i", v)
+def _l(v): return struct.pack("<q", v)
+def _s(s): return _i(len(s)) + s.encode()
+
+
+def test_reader_on_hand_built_bytes(tmp_path):
+    """A file assembled by hand from the format description: {weight = FloatTensor(2,3), n = 4, ok = true, name = 'x'}
+    wrapped in an nn.Identity-like torch object; the tensor is referenced twice (second time by index only)."""
+    data = np.arange(6, dtype="<f4")
+    tensor = (_i(4) + _i(3) + _s("V 1") + _s("torch.FloatTensor") + _i(2) + _l(2) + _l(3) + _l(3) + _l(1) + _l(1)
+              + _i(4) + _i(4) + _s("V 1") + _s("torch.FloatStorage") + _l(6) + data.tobytes())
+    table = (_i(3) + _i(2) + _i(5)
+             + _i(2) + _s("weight") + tensor
+             + _i(2) + _s("n") + _i(1) + struct.pack("<d", 4.0)
+             + _i(2) + _s("ok") + _i(5) + _i(1)
+             + _i(2) + _s("name") + _i(2) + _s("x")
+             + _i(2) + _s("alias") + _i(4) + _i(3))
+    blob = _i(4) + _i(1) + _s("V 1") + _s("nn.Identity") + table
+    p = tmp_path / "hand.t7"
+    p.write_bytes(blob)
+    o = t7.load(str(p))
+    assert isinstance(o, t7.TorchObject) and o.classname == "nn.Identity"
+    assert np.array_equal(o["weight"], np.arange(6, dtype=np.float32).reshape(2, 3))
+    assert o["n"] == 4 and o["ok"] is True and o["name"] == "x"
+    assert o["alias"] is o["weight"]                      # shared reference index
+
+
+def test_writer_bytes_of_small_objects(tmp_path):
+    p = tmp_path / "n.t7"
+    t7.save(str(p), 2.5)
+    assert p.read_bytes() == _i(1) + struct.pack("<d", 2.5)
+    t7.save(str(p), "ab")
+    assert p.read_bytes() == _i(2) + _s("ab")
+    t7.save(str(p), [True, None])
+    assert p.read_bytes() == _i(3) + _i(1) + _i(2) + _i(1) + struct.pack("<d", 1.0) + _i(5) + _i(1) + _i(1) + struct.pack("<d", 2.0) + _i(0)
+    a = np.arange(4, dtype=np.float32).reshape(2, 2)
+    t7.save(str(p), a)
+    assert p.read_bytes() == (_i(4) + _i(1) + _s("V 1") + _s("torch.FloatTensor") + _i(2) + _l(2) + _l(2) + _l(2) + _l(1) + _l(1)
+                              + _i(4) + _i(2) + _s("V 1") + _s("torch.FloatStorage") + _l(4) + a.tobytes())
+
+
+def test_roundtrip_types(tmp_path):
+    obj = {"a": [1, 2.5, "s", False, None], "t": np.random.default_rng(0).normal(size=(3, 1, 2)).astype(np.float32),
+           "b": np.array([1, 0, 1], np.uint8), "empty": np.zeros([0], np.float32), "size": t7.Storage([1]),
+           "o": t7.TorchObject("nn.Tanh", {"train": True})}
+    p = tmp_path / "r.t7"
+    t7.save(str(p), obj)
+    r = t7.load(str(p))
+    assert r["a"] == [1, 2.5, "s", False, None]
+    assert np.array_equal(r["t"], obj["t"]) and r["t"].dtype == np.float32
+    assert np.array_equal(r["b"], obj["b"]) and r["b"].dtype == np.uint8
+    assert r["empty"].size == 0
+    assert isinstance(r["size"], t7.Storage) and list(r["size"]) == [1]
+    assert r["o"].classname == "nn.Tanh" and r["o"]["train"] is True
+
+
+@pytest.mark.parametrize("variant", ["image", "video"])
+def test_util_save_load_roundtrip(tmp_path, variant):
+    opt = models.default_opt(variant, nBottleneck=32, nef=8, ngf=8, ndf=8)
+    rng = np.random.default_rng(1)
+    for describe in (util.describe_netG, util.describe_netD):
+        net = describe(opt)
+        flat = rng.normal(0, 0.02, util.params_flat(net).size).astype(np.float32)
+        util.set_params_flat(net, flat)
+        stats = rng.uniform(0.5, 1.5, util.bn_stats_flat(net).size).astype(np.float32)
+        util.set_bn_stats_flat(net, stats)
+        p = tmp_path / "net.t7"
+        util.save(str(p), net)
+        raw = t7.load(str(p))
+        # util.save semantics: nn.* class names, emptied buffers, no gradient tensors
+        assert raw.classname == "nn.Sequential" and raw["output"].size == 0
+        first = raw["modules"][0]
+        conv = first["modules"][0] if first.classname == "nn.Sequential" else first
+        assert conv.classname == "nn.SpatialConvolution" and "gradWeight" not in conv and conv["finput"].size == 0
+        assert conv["weight"].dtype == np.float32 and conv["weight"].shape[2:] == (4, 4)
+        back = util.load(str(p))
+        assert np.array_equal(util.params_flat(back), flat)            # tensor-bit-identical after load
+        assert np.array_equal(util.bn_stats_flat(back), stats)
+        assert [m.classname for m in back.walk()] == [m.classname for m in net.walk()]
+
+
+def test_param_counts_match_reference_nets():
+    # cfg1/2 conv parameters G 71,118,691, D 2,764,737 (+ 2C per BN layer)
+    opt = models.default_opt("image")
+    g = util.params_flat(util.describe_netG(opt)).size
+    d = util.params_flat(util.describe_netD(opt)).size
+    assert g == 71118691 + 2 * (64 + 128 + 256 + 512 + 4000 + 512 + 256 + 128 + 64)
+    assert d == 2764737 + 2 * (128 + 256 + 512)
+    opt = models.default_opt("video")
+    assert util.params_flat(util.describe_netG(opt)).size == 71202732 + 2 * (64 + 128 + 256 + 512 + 4000 + 512 + 256 + 128 + 64 + 64)
+    assert util.params_flat(util.describe_netD(opt)).size == 2800609 + 2 * (128 + 256 + 512)
+
+
+def test_load_converts_legacy_classes(tmp_path):
+    old = t7.TorchObject("nn.Sequential", {"modules": [
+        t7.TorchObject("cudnn.SpatialConvolution", dict(nInputPlane=3, nOutputPlane=2, kW=4, kH=4, dW=2, dH=2, padW=1, padH=1,
+                                                         weight=np.ones((2, 3, 4, 4), np.float32), bias=np.zeros(2, np.float32))),
+        t7.TorchObject("fbnn.SpatialBatchNormalization", dict(eps=1e-5, momentum=0.1, affine=True, weight=np.ones(2, np.float32),
+                                                              bias=np.zeros(2, np.float32), running_mean=np.zeros(2, np.float32),
+                                                              running_std=np.full(2, 0.5, np.float32)))]})
+    p = tmp_path / "old.t7"
+    t7.save(str(p), old)
+    net = util.load(str(p))
+    assert [m.classname for m in net.modules] == ["nn.SpatialConvolution", "nn.SpatialBatchNormalization"]
+    assert np.allclose(net.modules[1].tensors["running_var"], 1 / 0.25 - 1e-5)

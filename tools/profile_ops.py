@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import video_filler_b200.tensor as T
 from video_filler_b200 import models, train
-from oracle import nets as onets
+from video_filler_b200 import synth, util
 
 B = int(os.environ.get("B", "256"))
 variant = os.environ.get("VARIANT", "image")
@@ -12,13 +12,12 @@ T.state(0)
 opt = models.default_opt(variant, batchSize=B)
 trn = train.FusedTrainer(opt)
 rng = np.random.default_rng(1234)
-oo = onets.default_opt(variant, batchSize=1)
-for idx, build in ((0, onets.build_netG), (1, onets.build_netD)):
-    net = build(oo); onets.weights_init(net, rng); p, _ = net.getParameters(); trn.set_params(idx, p)
+for idx, describe in ((0, util.describe_netG), (1, util.describe_netD)):
+    trn.set_params(idx, util.params_flat(util.weights_init(describe(opt), rng)))
 if variant == "image":
-    a, b = onets.synth_image_batch(B, 128, 4, rng); m = None
+    a, b = synth.image_batch(B, 128, 4, rng); m = None
 else:
-    a, b, m = onets.synth_video_batch(B, 12, 128, 110 / 255.0, rng)
+    a, b, m = synth.video_batch(B, 12, 128, 110 / 255.0, rng)
 da, db = T.CudaTensor.from_numpy(a), T.CudaTensor.from_numpy(b)
 dm = None
 if m is not None:

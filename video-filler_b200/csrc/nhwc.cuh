@@ -147,7 +147,20 @@ __device__ __forceinline__ void fold_and_flush(float (&acc)[NACC][8], bool activ
     const int width = TX * 8;
     for (int i = tid; i < NACC * width; i += nthr) red_sh[i] = 0.f;
     __syncthreads();
-    if (active) {
+    // lanes of a warp that share the same channel vector (TX < 32) are combined with shuffles first, so at most
+    // (threads / 32) atomics hit one shared address
+    if (TX < 32) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float v = active ? acc[a][k] : 0.f;
+                for (int o = 16; o >= TX; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                acc[a][k] = v;
+            }
+    }
+    const bool leader = TX >= 32 || (tid & 31) < TX;
+    if (active && leader) {
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
 #pragma unroll

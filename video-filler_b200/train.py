@@ -168,6 +168,24 @@ class ClosureTrainer:
 LOSS_NAMES = ("errD", "errG", "errG_l2", "errG_gdl", "errD_real", "errD_fake", "errG_total")
 
 
+def dp_step(trainer, a_ptr, b_ptr, mask_ptr, all_reduce):
+    """One data-parallel step: run the executor's program phase by phase; after each phase sum the buffer it names
+    (BN batch statistics, BN backward sums, the D / G gradient vectors, the loss accumulators) across ranks with
+    ``all_reduce(device_ptr, count, is_double)``.  Every rank holds full parameters and B/world samples; criteria
+    and BN use the global batch size, so the summed quantities equal the single-process ones.  Returns the number
+    of collectives issued."""
+    trainer.step_phase(-1, a_ptr, b_ptr, mask_ptr)
+    n = 0
+    while True:
+        buf, count, is_double, done = trainer.sync_info()
+        if done:
+            return n
+        if buf and count:
+            all_reduce(buf, count, is_double)
+            n += 1
+        trainer.step_phase(0, a_ptr, b_ptr, mask_ptr)
+
+
 class FusedTrainer:
     """Whole-step executor (cenn_trainer_*): one call per G+D step, host or device inputs."""
 
