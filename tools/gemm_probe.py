@@ -20,13 +20,17 @@ cases = [  # name, kind, N, h, w, Cs, Cl, stats, act, flops
     ("G4 dgrad-type 128->64 @16->32", 1, B, 16, 16, 128, 64, 1, 0, 2.0 * B * 16 * 16 * 64 * 16 * 128),
     ("G5 dgrad-type 64->4 @32->64 tanh", 1, B, 32, 32, 64, 4, 0, 3, 2.0 * B * 32 * 32 * 4 * 16 * 64),
 ]
-for name, kind, N, h, w, Cs, Cl, stats, act, flops in cases:
+variants = [(0, "full"), (1, "no MMA"), (3, "B only, no MMA"), (5, "A only, no MMA"), (6, "MMA only")] if "--variants" in sys.argv else [(0, "full")]
+for name, kind, N, h, w, Cs, Cl, stats, act, flops in [c for c in cases for _ in variants]:
+    flag, vname = variants[0]; variants = variants[1:] + variants[:1]
+    os.environ["PROBE_FLAGS"] = str(flag)
+    name = "%s [%s]" % (name, vname)
     ms = C.c_float(); dbg = (C.c_uint64 * 16)()
     rc = fn(st, kind, N, h, w, Cs, Cl, stats, act, 10, C.byref(ms), dbg)
     if rc:
         print(name, "FAILED", _lib.last_error()); continue
     d = list(dbg)
     grid, bn, stg = d[15] >> 32, (d[15] >> 8) & 0xffff, d[15] & 0xff
-    print("%-36s %8.1f us %7.1f TF/s grid=%d BN=%d stages=%d tiles/cta0=%d | prod wait %5.1f%% | mma wait full %5.1f%% tempty %5.1f%% | epi wait %5.1f%% (%d cyc/tile)" % (
+    print("%-56s %8.1f us %7.1f TF/s grid=%d BN=%d stages=%d tiles/cta0=%d | prod wait %5.1f%% | mma wait full %5.1f%% tempty %5.1f%% | epi wait %5.1f%% (%d cyc/tile)" % (
         name, ms.value * 1e3, flops / ms.value / 1e9, grid, bn, stg, d[7], 100.0 * d[0] / max(d[1], 1), 100.0 * d[2] / max(d[4], 1), 100.0 * d[3] / max(d[4], 1),
         100.0 * d[5] / max(d[6], 1), d[6] // max(d[7], 1)))

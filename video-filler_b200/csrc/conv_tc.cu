@@ -134,7 +134,7 @@ int pick_bn(int n_valid, int m_tiles, int sm_count) {
 }
 
 void fill_epilogue(tc::GatherGemmParams &p, const TcEpilogue &ep, bf16 *out) {
-    p.dbg = reinterpret_cast<unsigned long long *>(ep.dbg);
+    p.dbg = reinterpret_cast<unsigned long long *>(ep.dbg); p.dbg_flags = ep.dbg_flags;
     p.bias = ep.bias; p.stats = ep.stats; p.stats_stride = ep.stats_stride; p.act = ep.act; p.act_param = ep.act_param;
     p.out_bf16 = ep.no_bf16 ? nullptr : out; p.out_f32 = ep.out_f32;
 }
@@ -547,6 +547,7 @@ extern "C" CENN_API int cenn_debug_gemm_probe(cenn_state *s, int kind, int N, in
     CK(cudaMemset(L, 0, nL * 2)); CK(cudaMemset(S, 0, nS * 2)); CK(cudaMemset(W, 0, nW * 2)); CK(cudaMemset(stats, 0, 2 * 4096 * 4)); CK(cudaMemset(dbg, 0, 16 * 8));
     TcEpilogue ep; ep.act = act; ep.act_param = 0.2f; ep.dbg = dbg;
     if (getenv("PROBE_NO_OUT")) ep.no_bf16 = true;
+    if (getenv("PROBE_FLAGS")) ep.dbg_flags = atoi(getenv("PROBE_FLAGS"));
     if (with_stats) { ep.stats = stats; ep.stats_stride = 4096; }
     TcPlan pl; int rc;
     if (kind == 0) rc = tc_plan_fprop_s2(s, &pl, L, W, S, N, h, w, Cs, Csp, Clp, ep);
@@ -565,5 +566,77 @@ extern "C" CENN_API int cenn_debug_gemm_probe(cenn_state *s, int kind, int N, in
     dbg_out[15] = ((unsigned long long)pl.grid[0] << 32) | (unsigned)(pl.BN << 8) | (unsigned)pl.stages;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(L); cudaFree(S); cudaFree(W); cudaFree(stats); cudaFree(dbg);
+    return 0;
+}
+
+// ------------------------------------------------------------------ descriptor probe (tools/desc_probe.py)
+// What does a UMMA shared-memory descriptor (K-major, SWIZZLE_128B) read when its start address is a whole number of
+// 128-byte rows past the 1024-byte swizzle atom, and when the stride between 8-row groups (SBO) is not a multiple of
+// 1024?  A [160 x 64] patch is written by ONE TMA box (so the swizzle phase of every row follows its absolute
+// address); B is a 64 x 64 identity, so D[r][n] = A_patch[source_row(r)][n]: the output shows which element was read.
+namespace {
+__global__ void __launch_bounds__(128, 1)
+desc_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float *out, int start_row, int base_off, int sbo_bytes) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *a_s = smem, *b_s = smem + 160 * 128;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(b_s + 64 * 128);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc(slot, 64);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (threadIdx.x == 0) {
+        tc::mbar_expect_tx(&bar[0], 160 * 128 + 64 * 128);
+        tc::tma_load_2d(&tmA, &bar[0], a_s, 0, 0);
+        tc::tma_load_2d(&tmB, &bar[0], b_s, 0, 0);
+        tc::mbar_wait(&bar[0], 0);
+        tc::tc_fence_after();
+        const uint32_t idesc = tc::make_idesc(128, 64, 0, 0);
+        const uint32_t a_addr = tc::smem_u32(a_s) + (uint32_t)start_row * 128u, b_addr = tc::smem_u32(b_s);
+        for (int k = 0; k < 4; ++k) {
+            uint64_t ad = tc::make_desc(a_addr + k * 32, 16, (uint32_t)sbo_bytes) | ((uint64_t)(base_off & 7) << 49);
+            uint64_t bd = tc::make_desc(b_addr + k * 32, 16, 1024);
+            tc::umma_f16(tmem, ad, bd, idesc, k != 0);
+        }
+        tc::umma_commit(&bar[1]);
+    }
+    __syncwarp();
+    tc::mbar_wait(&bar[1], 0);
+    tc::tc_fence_after();
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        tc::tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, 64); }
+}
+}  // namespace
+
+// a_host: [160][64] bf16 bit patterns, out_host: [128][64] fp32
+extern "C" CENN_API int cenn_debug_desc_probe(cenn_state *s, const uint16_t *a_host, int start_row, int base_off, int sbo_bytes, float *out_host) {
+    API_BEGIN(s);
+    bf16 *A, *B; float *out;
+    CK(cudaMalloc(&A, 160 * 64 * 2)); CK(cudaMalloc(&B, 64 * 64 * 2)); CK(cudaMalloc(&out, 128 * 64 * 4));
+    std::vector<uint16_t> eye(64 * 64, 0);
+    for (int i = 0; i < 64; ++i) eye[i * 64 + i] = 0x3F80;   // bf16 1.0
+    CK(cudaMemcpy(A, a_host, 160 * 64 * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(B, eye.data(), 64 * 64 * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(out, 0, 128 * 64 * 4));
+    CUtensorMap ta, tb;
+    { uint64_t d[2] = {64, 160}, st[1] = {128}; uint32_t bx[2] = {64, 160}; if (make_map(&ta, A, 2, d, st, bx)) return 1; }
+    { uint64_t d[2] = {64, 64}, st[1] = {128}; uint32_t bx[2] = {64, 64}; if (make_map(&tb, B, 2, d, st, bx)) return 1; }
+    size_t smem = 1024 + 160 * 128 + 64 * 128 + 64;
+    desc_probe_kernel<<<1, 128, smem, s->stream>>>(ta, tb, out, start_row, base_off, sbo_bytes);
+    CK_LAUNCH(s);
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy(out_host, out, 128 * 64 * 4, cudaMemcpyDeviceToHost));
+    cudaFree(A); cudaFree(B); cudaFree(out);
     return 0;
 }

@@ -21,6 +21,7 @@ struct TcEpilogue {
     float *out_f32 = nullptr;      // optional fp32 copy of the output (same NHWC addressing)
     bool no_bf16 = false;
     void *dbg = nullptr;           // optional per-role cycle counters (debug probe)
+    int dbg_flags = 0;             // probe only, see tc::GatherGemmParams::dbg_flags
 };
 
 // A prepared launch: tensor maps, kernel parameters, k-block table and grid are built once (shapes and

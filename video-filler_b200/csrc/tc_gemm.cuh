@@ -137,6 +137,7 @@ struct GatherGemmParams {
     int act;                 // applied after bias, before the store (stats are taken before the activation)
     float act_param;
     unsigned long long *dbg; // [opt] per-role cycle counters of CTA 0 (tools/gemm_probe.py)
+    int dbg_flags;           // probe only: 1 = issue no MMAs, 2 = no A loads, 4 = no B loads (isolates the TMA feed / the MMA rate)
 };
 
 struct WgradParams {
@@ -219,9 +220,16 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     w_empty += clock64() - t0;
                     uint8_t *a_dst = tiles + (size_t)s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
+                    if (p.dbg_flags & 6) {           // probe: drop one or both operand streams
+                        const uint32_t bytes = ((p.dbg_flags & 2) ? 0u : A_BYTES) + ((p.dbg_flags & 4) ? 0u : B_BYTES);
+                        if (bytes) mbar_expect_tx(&full_bar[s], bytes); else mbar_arrive(&full_bar[s]);
+                        if (!(p.dbg_flags & 2)) tma_load_5d(&tmA, &full_bar[s], a_dst, p.A0[phase_id][tap] + c * 64, x0 + p.A1[phase_id][tap], p.A2[phase_id][tap], y0 + p.A3[phase_id][tap], n0);
+                        if (!(p.dbg_flags & 4)) tma_load_2d(&tmB, &full_bar[s], b_dst, tap * p.bk_per_tap + c * 64, brow);
+                    } else {
                     mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     tma_load_5d(&tmA, &full_bar[s], a_dst, p.A0[phase_id][tap] + c * 64, x0 + p.A1[phase_id][tap], p.A2[phase_id][tap], y0 + p.A3[phase_id][tap], n0);
                     tma_load_2d(&tmB, &full_bar[s], b_dst, tap * p.bk_per_tap + c * 64, brow);
+                    }
                     if (++c == p.chunks) { c = 0; ++tap; }
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
@@ -249,7 +257,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide k-block; +32 B inside the swizzle atom
                         uint64_t ad = make_desc(a_addr + k * 32, 16, 1024), bd = make_desc(b_addr + k * 32, 16, 1024);
-                        umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                        if (!(p.dbg_flags & 1)) umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[s]);                     // frees the smem slot when these MMAs retire
                     if (kb == p.num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
