@@ -21,6 +21,14 @@ cases = [  # name, kind, N, h, w, Cs, Cl, stats, act, flops
     ("G5 dgrad-type 64->4 @32->64 tanh", 1, B, 32, 32, 64, 4, 0, 3, 2.0 * B * 32 * 32 * 4 * 16 * 64),
 ]
 variants = [(0, "full"), (1, "no MMA"), (3, "B only, no MMA"), (5, "A only, no MMA"), (6, "MMA only")] if "--variants" in sys.argv else [(0, "full")]
+if "--stages" in sys.argv:
+    os.environ["PROBE_STAGES"] = sys.argv[sys.argv.index("--stages") + 1]
+if "--commit" in sys.argv:
+    variants = [(7, "empty loop, commit"), (7 + 32, "empty loop, sw arrive"), (6, "MMA only, commit"), (6 + 32, "MMA only, sw arrive")]
+if "--nodbg" in sys.argv:
+    os.environ["PROBE_NO_DBG"] = "1"
+if "--mma" in sys.argv:
+    variants = [(6, "MMA only"), (7, "no MMA no TMA"), (7 + 8, "4 MMA alternating acc"), (7 + 16, "8 MMA same acc"), (7 + 24, "8 MMA alternating acc")]
 for name, kind, N, h, w, Cs, Cl, stats, act, flops in [c for c in cases for _ in variants]:
     flag, vname = variants[0]; variants = variants[1:] + variants[:1]
     os.environ["PROBE_FLAGS"] = str(flag)
@@ -31,6 +39,6 @@ for name, kind, N, h, w, Cs, Cl, stats, act, flops in [c for c in cases for _ in
         print(name, "FAILED", _lib.last_error()); continue
     d = list(dbg)
     grid, bn, stg = d[15] >> 32, (d[15] >> 8) & 0xffff, d[15] & 0xff
-    print("%-56s %8.1f us %7.1f TF/s grid=%d BN=%d stages=%d tiles/cta0=%d | prod wait %5.1f%% | mma wait full %5.1f%% tempty %5.1f%% | epi wait %5.1f%% (%d cyc/tile)" % (
+    print("%-56s %8.1f us %7.1f TF/s grid=%d BN=%d stages=%d tiles/cta0=%d | prod wait %5.1f%% | mma wait full %5.1f%% tempty %5.1f%% | epi wait %5.1f%% (%d cyc/tile) | mma thread per k-block: wait %d fence %d issue %d commit %d" % (
         name, ms.value * 1e3, flops / ms.value / 1e9, grid, bn, stg, d[7], 100.0 * d[0] / max(d[1], 1), 100.0 * d[2] / max(d[4], 1), 100.0 * d[3] / max(d[4], 1),
-        100.0 * d[5] / max(d[6], 1), d[6] // max(d[7], 1)))
+        100.0 * d[5] / max(d[6], 1), d[6] // max(d[7], 1), d[2] // max(d[11], 1), d[10] // max(d[11], 1), d[9] // max(d[11], 1), d[8] // max(d[11], 1)))

@@ -76,7 +76,8 @@ const int SMEM_LIMIT = 227 * 1024;
 template <int BN>
 int set_attr_gather() {
     static bool done = false;
-    if (!done) { CK(cudaFuncSetAttribute(tc::gather_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); done = true; }
+    if (!done) { CK(cudaFuncSetAttribute(tc::gather_gemm_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CK(cudaFuncSetAttribute(tc::gather_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); done = true; }
     return 0;
 }
 template <int BN>
@@ -87,7 +88,8 @@ int set_attr_wgrad() {
 }
 int config_gather(cenn_state *s, TcPlan *pl, int BN, int num_kb, int total_tiles) {
     const int stage_bytes = 128 * 128 + BN * 128;
-    const int fixed = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 2 * BN * 4 + 4 * 32 * 33 * 4 + 256;
+    const int out_bytes = BN >= 64 ? 128 * BN * 2 : 0;
+    const int fixed = 1024 /*align*/ + out_bytes + 176 /*barriers, tmem slot*/ + 68 * 16 /*tap tables*/ + 3 * BN * 4 + (BN == 32 ? 4 * 32 * 33 * 4 : 0) + 64;
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -136,7 +138,7 @@ int pick_bn(int n_valid, int m_tiles, int sm_count) {
 void fill_epilogue(tc::GatherGemmParams &p, const TcEpilogue &ep, bf16 *out) {
     p.dbg = reinterpret_cast<unsigned long long *>(ep.dbg); p.dbg_flags = ep.dbg_flags;
     p.bias = ep.bias; p.stats = ep.stats; p.stats_stride = ep.stats_stride; p.act = ep.act; p.act_param = ep.act_param;
-    p.out_bf16 = ep.no_bf16 ? nullptr : out; p.out_f32 = ep.out_f32;
+    p.out_bf16 = ep.no_bf16 ? nullptr : out;
 }
 
 // tap geometry of the 4x4 / stride-2 / pad-1 window: input row 2*oy - 1 + u = 2*(oy + DYS[u]) + PYS[u]
@@ -232,6 +234,7 @@ static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap larger than the plan slot
 static_assert(sizeof(tc::GatherGemmParams) <= 1536 && sizeof(tc::WgradParams) <= 1536, "kernel params larger than the plan slot");
 static CUtensorMap *planA(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmA); }
 static CUtensorMap *planB(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmB); }
+static CUtensorMap *planO(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmO); }
 
 void tc_plan_free(TcPlan *pl) {
     if (pl && pl->kb_dev) { cudaFree(pl->kb_dev); pl->kb_dev = nullptr; }
@@ -240,8 +243,12 @@ void tc_plan_free(TcPlan *pl) {
 template <int BN>
 static int launch_gather_t(cenn_state *s, const TcPlan *pl) {
     const tc::GatherGemmParams &p = *reinterpret_cast<const tc::GatherGemmParams *>(pl->params);
-    tc::gather_gemm_kernel<BN><<<dim3(pl->grid[0], pl->grid[1], pl->grid[2]), tc::GEMM_THREADS, pl->smem, s->stream>>>(
-        *reinterpret_cast<const CUtensorMap *>(pl->tmA), *reinterpret_cast<const CUtensorMap *>(pl->tmB), p, pl->stages);
+    if (p.dbg || p.dbg_flags)   // tools/gemm_probe.py only
+        tc::gather_gemm_kernel<BN, true><<<dim3(pl->grid[0], pl->grid[1], pl->grid[2]), tc::GEMM_THREADS, pl->smem, s->stream>>>(
+            *reinterpret_cast<const CUtensorMap *>(pl->tmA), *reinterpret_cast<const CUtensorMap *>(pl->tmB), *reinterpret_cast<const CUtensorMap *>(pl->tmO), p, pl->stages);
+    else
+        tc::gather_gemm_kernel<BN, false><<<dim3(pl->grid[0], pl->grid[1], pl->grid[2]), tc::GEMM_THREADS, pl->smem, s->stream>>>(
+            *reinterpret_cast<const CUtensorMap *>(pl->tmA), *reinterpret_cast<const CUtensorMap *>(pl->tmB), *reinterpret_cast<const CUtensorMap *>(pl->tmO), p, pl->stages);
     CK_LAUNCH(s);
     return 0;
 }
@@ -283,7 +290,11 @@ int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, b
     p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
     int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
     int BN = pick_bn(Cs, m_tiles, s->sm_count);
+    if (Csp < 64) BN = 32;                          // output rows narrower than one 128-byte slab: direct-store path
     if (map_2d(planB(pl), Wf, (uint64_t)16 * Clp, (uint64_t)Cs, BN)) return 1;
+    memset(pl->tmO, 0, sizeof(pl->tmO));
+    if (BN >= 64 && map_plain(planO(pl), S, N, h, w, Csp, bw, bh, bn)) return 1;
+    p.o_cols = Csp; p.num_taps = 16;
     int chunks = Clp / 64;
     for (int t = 0; t < 16; ++t) {
         int u = t / 4, v = t % 4;
@@ -310,8 +321,13 @@ int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, b
     p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
     int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
     int BN = pick_bn(Cl, m_tiles * 4, s->sm_count);
+    if (Clp % 64 != 0) BN = 32;                     // a 64-column slab would spill into the neighbouring sub-pixel: direct-store path
     REQUIRE(cl_rows >= Cl, "tc_dgrad_s2: cl_rows (%d) too small for Cl %d", cl_rows, Cl);
     if (map_2d(planB(pl), Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
+    memset(pl->tmO, 0, sizeof(pl->tmO));
+    if (BN >= 64 && map_gather(planO(pl), L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
+    p.o_cols = Clp; p.num_taps = 4;
+    for (int ph = 0; ph < 4; ++ph) { p.O0[ph] = (ph & 1) * Clp; p.O2[ph] = ph >> 1; }
     int chunks = Csp / 64;
     for (int ph = 0; ph < 4; ++ph) {
         int py = ph >> 1, px = ph & 1;
@@ -348,7 +364,16 @@ int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *
     p.tiles_x = (M + 127) / 128; p.tiles_y = 1;
     int m_tiles = p.tiles_x;
     int BN = pick_bn(Nc, m_tiles, s->sm_count);
+    if (ldo < 64 || ldo % 8 != 0) BN = 32;
     if (map_2d(planB(pl), B, (uint64_t)K, (uint64_t)Nc, BN)) return 1;
+    memset(pl->tmO, 0, sizeof(pl->tmO));
+    if (BN >= 64) {
+        uint64_t od[5] = {(uint64_t)ldo, (uint64_t)M, 1, 1, 1};
+        uint64_t os[4] = {(uint64_t)ldo * 2, (uint64_t)ldo * 2 * M, (uint64_t)ldo * 2 * M, (uint64_t)ldo * 2 * M};
+        uint32_t ob[5] = {64, 128, 1, 1, 1};
+        if (make_map(planO(pl), out, 5, od, os, ob)) return 1;
+    }
+    p.o_cols = ldo; p.num_taps = 1;
     int nkb = (K + 63) / 64;
     p.chunks = nkb; p.bk_per_tap = 0; p.num_kb = nkb;          // a single "tap" whose chunks walk K
     p.m_tiles = m_tiles; p.n_tiles = (Nc + BN - 1) / BN; p.num_phases = 1;
@@ -545,7 +570,7 @@ extern "C" CENN_API int cenn_debug_gemm_probe(cenn_state *s, int kind, int N, in
     bf16 *L, *S, *W; float *stats; unsigned long long *dbg;
     CK(cudaMalloc(&L, nL * 2)); CK(cudaMalloc(&S, nS * 2)); CK(cudaMalloc(&W, nW * 2)); CK(cudaMalloc(&stats, 2 * 4096 * 4)); CK(cudaMalloc(&dbg, 16 * 8));
     CK(cudaMemset(L, 0, nL * 2)); CK(cudaMemset(S, 0, nS * 2)); CK(cudaMemset(W, 0, nW * 2)); CK(cudaMemset(stats, 0, 2 * 4096 * 4)); CK(cudaMemset(dbg, 0, 16 * 8));
-    TcEpilogue ep; ep.act = act; ep.act_param = 0.2f; ep.dbg = dbg;
+    TcEpilogue ep; ep.act = act; ep.act_param = 0.2f; ep.dbg = getenv("PROBE_NO_DBG") ? nullptr : dbg;
     if (getenv("PROBE_NO_OUT")) ep.no_bf16 = true;
     if (getenv("PROBE_FLAGS")) ep.dbg_flags = atoi(getenv("PROBE_FLAGS"));
     if (with_stats) { ep.stats = stats; ep.stats_stride = 4096; }
@@ -554,6 +579,7 @@ extern "C" CENN_API int cenn_debug_gemm_probe(cenn_state *s, int kind, int N, in
     else if (kind == 1) rc = tc_plan_dgrad_s2(s, &pl, S, W, L, N, h, w, Csp, Cl, Clp, Clp, ep);
     else rc = tc_plan_gemm(s, &pl, L, W, S, N, Cs, Cl, Csp, ep);
     if (rc) return 1;
+    if (getenv("PROBE_STAGES")) { int st = atoi(getenv("PROBE_STAGES")); if (st >= 1 && st < pl.stages) pl.stages = st; }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 2; ++i) if (tc_launch(s, &pl)) return 1;
     CK(cudaEventRecord(e0, s->stream));

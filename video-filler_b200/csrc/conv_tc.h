@@ -18,7 +18,6 @@ struct TcEpilogue {
     int stats_stride = 0;
     int act = 0;                   // tc::ACT_*
     float act_param = 0.f;
-    float *out_f32 = nullptr;      // optional fp32 copy of the output (same NHWC addressing)
     bool no_bf16 = false;
     void *dbg = nullptr;           // optional per-role cycle counters (debug probe)
     int dbg_flags = 0;             // probe only, see tc::GatherGemmParams::dbg_flags
@@ -33,6 +32,7 @@ struct TcPlan {
     size_t smem = 0;
     alignas(64) unsigned char tmA[128];
     alignas(64) unsigned char tmB[128];
+    alignas(64) unsigned char tmO[128];   // output tile store (gather GEMM, BN >= 64)
     alignas(16) unsigned char params[1536];
     void *kb_dev = nullptr;       // owned device k-block table (gather GEMM)
     double flops = 0;             // algorithmic FLOPs of one launch

@@ -42,8 +42,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) { printf("cenn: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
     }
 }
+// shared-space (32-bit) address forms: the single-thread pipeline loops keep their barrier / tile addresses as integers
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_slow_u32(uint32_t bar, uint32_t parity) {
+    long long t0 = clock64();
+    while (!mbar_try_wait_u32(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("cenn: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_u32(bar, parity)) return;
+    if (mbar_try_wait_u32(bar, parity)) return;
+    mbar_wait_slow_u32(bar, parity);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -58,6 +84,22 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap *m, uint64_t *bar,
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+
+__device__ __forceinline__ void tma_load_2d_u32(const CUtensorMap *m, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_u32(const CUtensorMap *m, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -74,6 +116,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -116,21 +161,23 @@ enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 
 // K-block kb of a tile = (tap = kb / chunks, c = kb % chunks).  TMA coordinates (all tables live in kernel parameters):
 //   A box: (A0[ph][tap] + 64 c,  x0 + A1[ph][tap],  A2[ph][tap],  y0 + A3[ph][tap],  n0)
 //   B box: (tap * bk_per_tap + 64 c,  n_tile * BN + B1[ph])
+//   O box: (O0[ph] + n_tile * BN + 64 slab,  x0,  O2[ph],  y0,  n0)        (TMA store of the bf16 output tile, BN >= 64)
 struct GatherGemmParams {
-    int num_kb, chunks, bk_per_tap;
+    int num_kb, chunks, bk_per_tap, num_taps;
     int A0[4][16], A1[4][16], A2[4][16], A3[4][16];
     int B1[4];
+    int O0[4], O2[4];
+    int o_cols;              // columns of one phase in the output map's dim 0 (slabs starting at or beyond it are not stored)
     int m_tiles, n_tiles, num_phases;   // tiles are enumerated m fastest, then n, then phase
     int box_w, box_h, box_n; // pixels per M tile (product == 128), all powers of two
     int bw_log2, bh_log2;
     int tiles_x, tiles_y;    // m-tile -> (tx, ty, tn)
     int out_w, out_h, out_n; // logical extent of the output pixel grid (for masking)
-    int n_valid;             // valid output channels (columns >= n_valid are dropped)
-    // output addressing: elem offset = n*sN + y*sY + x*sX + phase_off[phase] + column
+    int n_valid;             // valid output channels (columns >= n_valid are written as zero / dropped)
+    // output addressing of the direct-store path (BN == 32): elem offset = n*sN + y*sY + x*sX + phase_off[phase] + column
     long long sN, sY, sX;
     long long phase_off[4];
-    __nv_bfloat16 *out_bf16; // [opt] bf16 output
-    float *out_f32;          // [opt] fp32 output (same addressing)
+    __nv_bfloat16 *out_bf16; // [opt] bf16 output (NULL: results are discarded; probe only)
     const float *bias;       // [opt] per-column
     float *stats;            // [opt] per-column sum / sum of squares (fp32 atomics): stats[c], stats[stats_stride + c]
     int stats_stride;
@@ -163,39 +210,80 @@ static constexpr int GEMM_THREADS = 192;
 
 // ------------------------------------------------------------------ K-major gather GEMM (persistent)
 // One CTA per SM loops over output tiles (static round-robin).  Three pipelines run concurrently:
-//   TMA producer  -> smem ring (full/empty mbarriers)         -> MMA issuer
-//   MMA issuer    -> 2 TMEM accumulators (tmem_full/empty)    -> epilogue warps
-// so the epilogue of tile t (TMEM -> registers -> bias/BN-statistics/activation -> global) overlaps the MMAs of tile t+1.
+//   TMA producer (1 thread) -> smem ring (full/empty mbarriers)      -> MMA issuer (1 thread)
+//   MMA issuer              -> 2 TMEM accumulators (tmem_full/empty) -> 4 epilogue warps
+//   epilogue warps          -> bf16 tile in swizzled smem            -> TMA store (bulk async group)
+// so the epilogue of tile t overlaps the MMAs of tile t+1 and its global stores overlap the epilogue of tile t+1.
+// The two single-thread loops are kept to a few dozen instructions per k-block (descriptors advanced by integer adds,
+// tap tables in shared memory): at N = 64 the four MMAs of a k-block occupy the tensor pipe for only 128 cycles.
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN>
+struct TileCoord { int phase, nt, x0, y0, n0; };
+__device__ __forceinline__ TileCoord tile_coord(const GatherGemmParams &p, int t, int tiles_per_phase) {
+    TileCoord c;
+    c.phase = t / tiles_per_phase;
+    const int r = t - c.phase * tiles_per_phase;
+    c.nt = r / p.m_tiles;
+    const int mt = r - c.nt * p.m_tiles;
+    const int txy = p.tiles_x * p.tiles_y;
+    const int tn = mt / txy, rem = mt - tn * txy;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    c.x0 = tx * p.box_w; c.y0 = ty * p.box_h; c.n0 = tn * p.box_n;
+    return c;
+}
+
+__device__ __forceinline__ float apply_act(float f, int act, float param) {
+    if (act == ACT_LEAKY) return f > 0.f ? f : f * param;
+    if (act == ACT_RELU) return fmaxf(f, 0.f);
+    if (act == ACT_TANH) return tanhf(f);
+    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-f));
+    return f;
+}
+
+template <int BN, bool kProbe>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GatherGemmParams p, int stages) {
+gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                   const __grid_constant__ GatherGemmParams p, int stages) {
+    // kProbe = true compiles in the per-role cycle counters and the stream-dropping flags of tools/gemm_probe.py; the
+    // production instantiation carries none of it (the two single-thread loops are instruction-issue bound).
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr bool kTma = BN >= 64;               // bf16 tile -> swizzled smem -> TMA store; BN == 32 stores directly (thin outputs)
     constexpr uint32_t A_BYTES = 128 * 128;       // 128 rows x 64 bf16
     constexpr uint32_t B_BYTES = BN * 128;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t OUT_BYTES = kTma ? 128u * BN * 2u : 0u;
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, still a __shared__ pointer
     uint8_t *tiles = smem;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)stages * STAGE_BYTES);
-    uint64_t *empty_bar = full_bar + stages;
-    uint64_t *tfull_bar = empty_bar + stages;      // [2] accumulator ready
+    uint8_t *out_stage = smem + (size_t)stages * STAGE_BYTES;                      // [BN/64 slabs][128 rows][128 B], SWIZZLE_128B
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(out_stage + OUT_BYTES);
+    uint64_t *empty_bar = full_bar + 8;
+    uint64_t *tfull_bar = empty_bar + 8;           // [2] accumulator ready
     uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
-    float *col_acc = reinterpret_cast<float *>(tmem_slot + 2);          // [2][BN] per-CTA column sums for BN statistics
-    float *stage_f = col_acc + 2 * BN;                                  // [4 warps][32][33] transposition buffer
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);            // +160 B
+    int4 *tapc = reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(full_bar) + 176);   // [4][16] A-box coordinates per (phase, tap)
+    int4 *phc = tapc + 64;                                                         // [4] (B1, O0, O2, -) per phase
+    float *col_acc = reinterpret_cast<float *>(phc + 4);                           // [2][BN] per-CTA column sums for BN statistics
+    float *bias_s = col_acc + 2 * BN;                                              // [BN] bias of the current n-tile
+    float *stage_f = bias_s + BN;                                                  // BN == 32 only: [4 warps][32][33] transposition buffer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_phase = p.m_tiles * p.n_tiles;
     const int total_tiles = tiles_per_phase * p.num_phases;
+    const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (kTma) prefetch_tmap(&tmO);
         for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
         fence_barrier_init();
+    }
+    if (threadIdx.x < 64) {
+        const int ph = threadIdx.x >> 4, tp = threadIdx.x & 15;
+        tapc[threadIdx.x] = make_int4(p.A0[ph][tp], p.A1[ph][tp], p.A2[ph][tp], p.A3[ph][tp]);
+        if (tp == 0) phc[ph] = make_int4(p.B1[ph], p.O0[ph], p.O2[ph], 0);
     }
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) col_acc[i] = 0.f;
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -207,95 +295,109 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            long long w_empty = 0, t_begin = clock64();
+            long long w_empty = 0, t_begin = prof ? clock64() : 0;
+            const int chunks = p.chunks, num_taps = p.num_taps, bk_per_tap = p.bk_per_tap;
+            const int flags = kProbe ? p.dbg_flags : 0;
+            const uint32_t tiles_u32 = smem_u32(tiles), full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int phase_id = t / tiles_per_phase, r = t - phase_id * tiles_per_phase;
-                const int nt = r / p.m_tiles, mt = r - nt * p.m_tiles;
-                const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
-                const int brow = nt * BN + p.B1[phase_id];
-                int tap = 0, c = 0;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    long long t0 = clock64();
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
-                    w_empty += clock64() - t0;
-                    uint8_t *a_dst = tiles + (size_t)s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
-                    if (p.dbg_flags & 6) {           // probe: drop one or both operand streams
-                        const uint32_t bytes = ((p.dbg_flags & 2) ? 0u : A_BYTES) + ((p.dbg_flags & 4) ? 0u : B_BYTES);
-                        if (bytes) mbar_expect_tx(&full_bar[s], bytes); else mbar_arrive(&full_bar[s]);
-                        if (!(p.dbg_flags & 2)) tma_load_5d(&tmA, &full_bar[s], a_dst, p.A0[phase_id][tap] + c * 64, x0 + p.A1[phase_id][tap], p.A2[phase_id][tap], y0 + p.A3[phase_id][tap], n0);
-                        if (!(p.dbg_flags & 4)) tma_load_2d(&tmB, &full_bar[s], b_dst, tap * p.bk_per_tap + c * 64, brow);
-                    } else {
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                    tma_load_5d(&tmA, &full_bar[s], a_dst, p.A0[phase_id][tap] + c * 64, x0 + p.A1[phase_id][tap], p.A2[phase_id][tap], y0 + p.A3[phase_id][tap], n0);
-                    tma_load_2d(&tmB, &full_bar[s], b_dst, tap * p.bk_per_tap + c * 64, brow);
+                const TileCoord tc = tile_coord(p, t, tiles_per_phase);
+                const int4 *tp = tapc + tc.phase * 16;
+                const int brow = tc.nt * BN + phc[tc.phase].x;
+                for (int tap = 0; tap < num_taps; ++tap) {
+                    const int4 c4 = tp[tap];
+                    const int ax = tc.x0 + c4.y, ay = tc.y0 + c4.w, bk = tap * bk_per_tap;
+                    for (int c = 0; c < chunks; ++c) {
+                        long long t0 = prof ? clock64() : 0;
+                        mbar_wait_u32(empty_u32 + 8u * s, ph ^ 1u);
+                        if (prof) w_empty += clock64() - t0;
+                        const uint32_t a_dst = tiles_u32 + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES, fb = full_u32 + 8u * s;
+                        if (kProbe && (flags & 6)) {   // probe: drop one or both operand streams
+                            const uint32_t bytes = ((flags & 2) ? 0u : A_BYTES) + ((flags & 4) ? 0u : B_BYTES);
+                            if (bytes) mbar_expect_tx_u32(fb, bytes); else mbar_arrive(&full_bar[s]);
+                            if (!(flags & 2)) tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ax, c4.z, ay, tc.n0);
+                            if (!(flags & 4)) tma_load_2d_u32(&tmB, fb, b_dst, bk + c * 64, brow);
+                        } else {
+                            mbar_expect_tx_u32(fb, STAGE_BYTES);
+                            tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ax, c4.z, ay, tc.n0);
+                            tma_load_2d_u32(&tmB, fb, b_dst, bk + c * 64, brow);
+                        }
+                        if (++s == stages) { s = 0; ph ^= 1u; }
                     }
-                    if (++c == p.chunks) { c = 0; ++tap; }
-                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
-            if (p.dbg && blockIdx.x == 0) { p.dbg[0] = (unsigned long long)w_empty; p.dbg[1] = (unsigned long long)(clock64() - t_begin); }
+            if (prof) { p.dbg[0] = (unsigned long long)w_empty; p.dbg[1] = (unsigned long long)(clock64() - t_begin); }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
-        int s = 0; uint32_t ph = 0;
-        int acc = 0; uint32_t acc_ph = 0;
-        long long w_full = 0, w_tempty = 0, t_begin = clock64();
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            long long t0 = clock64();
-            mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);      // epilogue has drained this accumulator
-            w_tempty += clock64() - t0;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                t0 = clock64();
-                mbar_wait(&full_bar[s], ph);
-                w_full += clock64() - t0;
+        {   // warp-uniform loop: every lane waits on the barriers, one elected lane issues the MMAs and commits
+            const uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
+            // descriptor words: lo = start address (16-B units) | LBO << 16 ; hi = SBO (1024 B) | version 1 | SWIZZLE_128B
+            const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo0 = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar), tfull_u32 = smem_u32(tfull_bar), tempty_u32 = smem_u32(tempty_bar);
+            const int num_kb = p.num_kb;
+            const int flags = kProbe ? p.dbg_flags : 0;
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            long long w_full = 0, w_tempty = 0, t_begin = prof ? clock64() : 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                long long t0 = prof ? clock64() : 0;
+                mbar_wait_u32(tempty_u32 + 8u * acc, acc_ph ^ 1u);      // epilogue has drained this accumulator
+                if (prof) w_tempty += clock64() - t0;
                 tc_fence_after();
-                if (lane == 0) {
-                    uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (prof) t0 = clock64();
+                    mbar_wait_u32(full_u32 + 8u * s, ph);
+                    if (prof) w_full += clock64() - t0;
+                    tc_fence_after();
+                    const uint32_t a_lo = a_lo0 + (uint32_t)s * (STAGE_BYTES >> 4), b_lo = a_lo + (A_BYTES >> 4);
+                    if (elect_one()) {
+                        if (!(kProbe && (flags & 1))) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide k-block; +32 B inside the swizzle atom
-                        uint64_t ad = make_desc(a_addr + k * 32, 16, 1024), bd = make_desc(b_addr + k * 32, 16, 1024);
-                        if (!(p.dbg_flags & 1)) umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                            for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide k-block; +32 B inside the swizzle atom
+                                const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), bd = ((uint64_t)desc_hi << 32) | (b_lo + 2u * k);
+                                umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                            }
+                        }
+                        if (kProbe && (flags & 24)) {       // probe: timing experiments only (results are garbage)
+                            const int reps = (flags & 16) ? 2 : 1;
+                            for (int r = 0; r < reps; ++r)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), bd = ((uint64_t)desc_hi << 32) | (b_lo + 2u * k);
+                                    const uint32_t dd = (flags & 8) ? tmem_base + (uint32_t)(((acc + (k & 1)) & 1) * BN) : d_tmem;
+                                    umma_f16(dd, ad, bd, idesc, 1);
+                                }
+                        }
+                        umma_commit_u32(empty_u32 + 8u * s);                        // frees the smem slot when these MMAs retire
+                        if (kb == num_kb - 1) umma_commit_u32(tfull_u32 + 8u * acc);   // accumulator complete
                     }
-                    umma_commit(&empty_bar[s]);                     // frees the smem slot when these MMAs retire
-                    if (kb == p.num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+                    __syncwarp();
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++s == stages) { s = 0; ph ^= 1u; }
+                acc ^= 1; acc_ph ^= (uint32_t)(acc == 0);
             }
-            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+            if (prof && lane == 0) { p.dbg[2] = (unsigned long long)w_full; p.dbg[3] = (unsigned long long)w_tempty; p.dbg[4] = (unsigned long long)(clock64() - t_begin); }
         }
-        if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = (unsigned long long)w_full; p.dbg[3] = (unsigned long long)w_tempty; p.dbg[4] = (unsigned long long)(clock64() - t_begin); }
     } else {
         // ---------------- epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 (= tile rows)
         const int q = warp & 3;
         const int et = threadIdx.x - 64;                 // 0..127 within the epilogue group
-        float *my_stage = stage_f + (size_t)(warp - 2) * 32 * 33;
         const int bw_mask = p.box_w - 1, bh_mask = p.box_h - 1, bwh_log2 = p.bw_log2 + p.bh_log2;
-        // rows this lane touches: its own TMEM lane (staging / masking) and the 4 rows it stores (8 columns each)
-        const int row = q * 32 + lane;
+        const int row = q * 32 + lane;                   // this lane's TMEM lane = tile row
         const int rx = row & bw_mask, ry = (row >> p.bw_log2) & bh_mask, rn = row >> bwh_log2;
-        int sx[4], sy[4], sn[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int r = q * 32 + g * 8 + (lane >> 2);
-            sx[g] = r & bw_mask; sy[g] = (r >> p.bw_log2) & bh_mask; sn[g] = r >> bwh_log2;
-        }
-        const int cseg = (lane & 3) * 8;
+        const int act = p.act; const float act_param = p.act_param;
+        const bool has_bias = p.bias != nullptr, has_stats = p.stats != nullptr;
         int acc = 0; uint32_t acc_ph = 0;
         int stat_key = -1;                               // n-tile the per-CTA column sums belong to
-        long long w_tfull = 0, t_begin = clock64();
+        long long w_tfull = 0, t_begin = prof ? clock64() : 0;
         int ntile = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             ++ntile;
-            const int phase_id = t / tiles_per_phase, r0 = t - phase_id * tiles_per_phase;
-            const int nt = r0 / p.m_tiles, mt = r0 - nt * p.m_tiles;
-            const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-            const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+            const TileCoord tc = tile_coord(p, t, tiles_per_phase);
+            const int nt = tc.nt, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
             const bool row_ok = (x0 + rx) < p.out_w && (y0 + ry) < p.out_h && (n0 + rn) < p.out_n;
-            if (p.stats && nt != stat_key) {
+            if (has_stats && nt != stat_key) {
                 if (stat_key >= 0) {                     // the column sums so far belong to another n-tile: flush them
                     epi_bar_sync();
                     for (int i = et; i < BN; i += 128) {
@@ -307,183 +409,180 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 stat_key = nt;
             }
-            long long t0 = clock64();
+            long long t0 = prof ? clock64() : 0;
             mbar_wait(&tfull_bar[acc], acc_ph);
-            w_tfull += clock64() - t0;
+            if (prof) w_tfull += clock64() - t0;
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             int ncols = p.n_valid - nt * BN; ncols = ncols > BN ? BN : ncols;
-            const long long tile_base = p.phase_off[phase_id] + (long long)nt * BN;
-            if (ncols <= 8 && !p.stats) {
-                // ---- thin output (<= 8 valid columns, e.g. the 3-channel image): narrow TMEM read, one row per lane
-                uint32_t r8[8];
-                tmem_ld8(t_addr, r8);
+            if constexpr (kTma) {
+                // ---- bf16 tile -> swizzled smem slabs -> one TMA store per 64-column slab
+                if (has_bias) for (int i = et; i < BN; i += 128) { const int c = nt * BN + i; bias_s[i] = c < p.n_valid ? __ldg(p.bias + c) : 0.f; }
+                if (et == 0) bulk_wait_read0();          // the previous tile's stores have finished reading out_stage
+                epi_bar_sync();
+                const int last_c0 = ((ncols + 31) >> 5) * 32 - 32;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    float v[32];
+                    if (c0 < ncols) {
+                        uint32_t rr[32];
+                        tmem_ld32(t_addr + (uint32_t)c0, rr);
+                        tmem_ld_wait();
+                        if (c0 == last_c0) {             // last read of this accumulator: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+                        if (has_bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c0 + j);
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        }
+                        switch (act) {                   // uniform: one activation loop is executed
+                            case ACT_LEAKY:
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * act_param;
+                                break;
+                            case ACT_RELU:
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                break;
+                            case ACT_TANH:
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+                                break;
+                            case ACT_SIGMOID:
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+                                break;
+                            default: break;
+                        }
+                        if (!row_ok) {                   // rows outside the image: zero (kept out of the statistics; the store clips them)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        } else if (c0 + 32 > ncols) {    // pad columns stay zero
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (c0 + j >= ncols) v[j] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+                    uint8_t *slab_row = out_stage + (size_t)(c0 >> 6) * (128 * 128) + (size_t)row * 128;
+                    const int cb = (c0 & 63) >> 3;       // first 16-byte chunk of this 32-column group within the 128-byte row
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                        *reinterpret_cast<uint4 *>(slab_row + (((cb + i) ^ (row & 7)) << 4)) = pk;
+                    }
+                }
+                if (has_stats) {
+                    // column sums of the STORED (bf16-rounded) values: lane l owns columns 2l, 2l+1 of each slab, over this warp's 32 rows
+                    __syncwarp();
+                    for (int sl = 0; sl * 64 < ncols; ++sl) {
+                        const uint8_t *slab = out_stage + (size_t)sl * (128 * 128) + (size_t)(q * 32) * 128;
+                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const uint32_t wv = *reinterpret_cast<const uint32_t *>(slab + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2));
+                            const float a = __uint_as_float(wv << 16), b = __uint_as_float(wv & 0xFFFF0000u);
+                            s1a += a; s2a = fmaf(a, a, s2a); s1b += b; s2b = fmaf(b, b, s2b);
+                        }
+                        atomicAdd(&col_acc[sl * 64 + 2 * lane], s1a); atomicAdd(&col_acc[sl * 64 + 2 * lane + 1], s1b);
+                        atomicAdd(&col_acc[BN + sl * 64 + 2 * lane], s2a); atomicAdd(&col_acc[BN + sl * 64 + 2 * lane + 1], s2b);
+                    }
+                }
+                fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA store
+                epi_bar_sync();
+                if (et == 0 && p.out_bf16) {
+                    const int4 pc = phc[tc.phase];
+                    for (int sl = 0; sl < BN / 64; ++sl) {
+                        const int col = nt * BN + sl * 64;
+                        if (col < p.o_cols) tma_store_5d(&tmO, out_stage + (size_t)sl * (128 * 128), pc.y + col, x0, pc.z, y0, n0);
+                    }
+                    bulk_commit();
+                }
+            } else {
+                // ---- BN == 32: direct stores (thin outputs: 3 / 4 / 12 / 16 channels)
+                const long long tile_base = p.phase_off[tc.phase] + (long long)nt * BN;
+                float *my_stage = stage_f + (size_t)(warp - 2) * 32 * 33;
+                uint32_t rr[32];
+                if (ncols <= 8) { uint32_t r8[8]; tmem_ld8(t_addr, r8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rr[j] = r8[j];
+                } else tmem_ld32(t_addr, rr);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                if (row_ok) {
-                    float w8[8];
+                if (has_stats) {                         // rare (no thin layer is followed by BN): transpose through smem
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        float f = __uint_as_float(r8[k]);
-                        if (k < ncols) {
-                            if (p.bias) f += __ldg(p.bias + nt * BN + k);
-                            if (p.act == ACT_LEAKY) f = f > 0.f ? f : f * p.act_param;
-                            else if (p.act == ACT_RELU) f = fmaxf(f, 0.f);
-                            else if (p.act == ACT_TANH) f = tanhf(f);
-                            else if (p.act == ACT_SIGMOID) f = 1.f / (1.f + __expf(-f));
+                    for (int j = 0; j < 32; ++j) my_stage[lane * 33 + j] = row_ok ? __uint_as_float(rr[j]) : 0.f;
+                    __syncwarp();
+                    const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+                    const float nrows_ok = (float)__popc(okmask);
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) { float tt = my_stage[i * 33 + lane]; s1 += tt; s2 += tt * tt; }
+                    const int col_l = nt * BN + lane;
+                    if (has_bias && col_l < p.n_valid) { const float bb = __ldg(p.bias + col_l); s2 += 2.f * bb * s1 + nrows_ok * bb * bb; s1 += nrows_ok * bb; }
+                    atomicAdd(&col_acc[lane], s1); atomicAdd(&col_acc[BN + lane], s2);
+                    __syncwarp();
+                }
+                if (row_ok && p.out_bf16) {
+                    __nv_bfloat16 *o = p.out_bf16 + (long long)(n0 + rn) * p.sN + (long long)(y0 + ry) * p.sY + (long long)(x0 + rx) * p.sX + tile_base;
+                    const bool al16 = (reinterpret_cast<uintptr_t>(o) & 15) == 0, al8 = (reinterpret_cast<uintptr_t>(o) & 7) == 0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {        // 8 columns per group
+                        if (g * 8 >= ncols) break;
+                        float w8[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            float f = __uint_as_float(rr[g * 8 + k]);
+                            const int c = g * 8 + k;
+                            if (c < ncols) { if (has_bias) f += __ldg(p.bias + nt * BN + c); f = apply_act(f, act, act_param); } else f = 0.f;
+                            w8[k] = f;
                         }
-                        w8[k] = f;
-                    }
-                    const long long ro = (long long)(n0 + rn) * p.sN + (long long)(y0 + ry) * p.sY + (long long)(x0 + rx) * p.sX + tile_base;
-                    if (p.out_bf16) {
-                        __nv_bfloat16 *o = p.out_bf16 + ro;
                         __nv_bfloat162 h0 = __floats2bfloat162_rn(w8[0], w8[1]), h1 = __floats2bfloat162_rn(w8[2], w8[3]);
-                        if (ncols == 4 && (ro & 3) == 0) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(w8[4], w8[5]), h3 = __floats2bfloat162_rn(w8[6], w8[7]);
+                        const int cv = ncols - g * 8;
+                        if (cv >= 8 && al16) {
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                            *reinterpret_cast<uint4 *>(o + g * 8) = pk;
+                        } else if (cv >= 4 && al8) {
                             uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                            *reinterpret_cast<uint2 *>(o) = pk;
+                            *reinterpret_cast<uint2 *>(o + g * 8) = pk;
+                            __nv_bfloat16 hh[4] = {__float2bfloat16(w8[4]), __float2bfloat16(w8[5]), __float2bfloat16(w8[6]), __float2bfloat16(w8[7])};
+#pragma unroll
+                            for (int k = 4; k < 8; ++k) if (k < cv) o[g * 8 + k] = hh[k - 4];
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) if (k < ncols) o[k] = __float2bfloat16(w8[k]);
+                            for (int k = 0; k < 8; ++k) if (k < cv) o[g * 8 + k] = __float2bfloat16(w8[k]);
                         }
                     }
-                    if (p.out_f32) {
-                        float *o = p.out_f32 + ro;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) if (k < ncols) o[k] = w8[k];
-                    }
-                }
-            } else {
-                const int nchunks = (ncols + 31) >> 5;
-                const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
-                const float nrows_ok = (float)__popc(okmask);
-                long long srow[4]; bool sok[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    sok[g] = (x0 + sx[g]) < p.out_w && (y0 + sy[g]) < p.out_h && (n0 + sn[g]) < p.out_n;
-                    srow[g] = (long long)(n0 + sn[g]) * p.sN + (long long)(y0 + sy[g]) * p.sY + (long long)(x0 + sx[g]) * p.sX + tile_base + cseg;
-                }
-#pragma unroll 1
-                for (int ci = 0; ci < nchunks; ++ci) {
-                    const int c0 = ci * 32;
-                    uint32_t rr[32];
-                    tmem_ld32(t_addr + (uint32_t)c0, rr);
-                    tmem_ld_wait();
-                    if (ci == nchunks - 1) {             // last read of this accumulator: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                    }
-                    if (!row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) rr[j] = 0u;
-                    }
-                    // stage the raw fp32 chunk in smem: row = lane, 33-float pitch (conflict-free both ways)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) my_stage[lane * 33 + j] = __uint_as_float(rr[j]);
-                    __syncwarp();
-                    const int col_l = nt * BN + c0 + lane;                 // the column this lane sums
-                    if (p.stats) {
-                        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                        for (int i = 0; i < 32; ++i) { float tt = my_stage[i * 33 + lane]; s1 += tt; s2 += tt * tt; }
-                        if (p.bias && col_l < p.n_valid) {                 // statistics of (x + b) from those of x
-                            const float bb = __ldg(p.bias + col_l);
-                            s2 += 2.f * bb * s1 + nrows_ok * bb * bb; s1 += nrows_ok * bb;
-                        }
-                        atomicAdd(&col_acc[c0 + lane], s1);
-                        atomicAdd(&col_acc[BN + c0 + lane], s2);
-                    }
-                    // coalesced stores: 4 lanes cover the 32 columns of one row (full 32-byte sectors), 8 rows per pass
-                    const int colseg = nt * BN + c0 + cseg;
-                    const int cvalid = p.n_valid - colseg;                 // valid columns in this lane's 8-wide segment
-                    if (cvalid > 0) {
-                        float w8[4][8];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) w8[g][k] = my_stage[(g * 8 + (lane >> 2)) * 33 + cseg + k];
-                        if (p.bias) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const float bb = k < cvalid ? __ldg(p.bias + colseg + k) : 0.f;
-#pragma unroll
-                                for (int g = 0; g < 4; ++g) w8[g][k] += bb;
-                            }
-                        }
-                        switch (p.act) {                                    // uniform: one activation loop is executed
-                            case ACT_LEAKY: {
-                                const float nv = p.act_param;
-#pragma unroll
-                                for (int g = 0; g < 4; ++g)
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) w8[g][k] = w8[g][k] > 0.f ? w8[g][k] : w8[g][k] * nv;
-                            } break;
-                            case ACT_RELU:
-#pragma unroll
-                                for (int g = 0; g < 4; ++g)
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) w8[g][k] = fmaxf(w8[g][k], 0.f);
-                                break;
-                            case ACT_TANH:
-#pragma unroll 1
-                                for (int g = 0; g < 4; ++g)
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) if (k < cvalid) w8[g][k] = tanhf(w8[g][k]);
-                                break;
-                            case ACT_SIGMOID:
-#pragma unroll 1
-                                for (int g = 0; g < 4; ++g)
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) if (k < cvalid) w8[g][k] = 1.f / (1.f + __expf(-w8[g][k]));
-                                break;
-                            default: break;
-                        }
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (!sok[g]) continue;
-                            const long long ro = srow[g] + c0;
-                            if (p.out_bf16) {
-                                __nv_bfloat16 *o = p.out_bf16 + ro;
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(w8[g][0], w8[g][1]), h1 = __floats2bfloat162_rn(w8[g][2], w8[g][3]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(w8[g][4], w8[g][5]), h3 = __floats2bfloat162_rn(w8[g][6], w8[g][7]);
-                                if (cvalid >= 8 && (ro & 7) == 0) {
-                                    uint4 pk;
-                                    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                                    pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-                                    *reinterpret_cast<uint4 *>(o) = pk;
-                                } else if (cvalid >= 4 && (ro & 3) == 0) {
-                                    uint2 pk;
-                                    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                                    *reinterpret_cast<uint2 *>(o) = pk;
-#pragma unroll
-                                    for (int k = 4; k < 8; ++k) if (k < cvalid) o[k] = __float2bfloat16(w8[g][k]);
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) if (k < cvalid) o[k] = __float2bfloat16(w8[g][k]);
-                                }
-                            }
-                            if (p.out_f32) {
-                                float *o = p.out_f32 + ro;
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) if (k < cvalid) o[k] = w8[g][k];
-                            }
-                        }
-                    }
-                    __syncwarp();
                 }
             }
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
-        if (p.stats && stat_key >= 0) {
+        if (has_stats && stat_key >= 0) {
             epi_bar_sync();
             for (int i = et; i < BN; i += 128) {
                 int c = stat_key * BN + i;
                 if (c < p.n_valid) { atomicAdd(p.stats + c, col_acc[i]); atomicAdd(p.stats + p.stats_stride + c, col_acc[BN + i]); }
             }
         }
-        if (p.dbg && blockIdx.x == 0 && et == 0) { p.dbg[5] = (unsigned long long)w_tfull; p.dbg[6] = (unsigned long long)(clock64() - t_begin); p.dbg[7] = (unsigned long long)ntile; }
+        if (kTma && et == 0) bulk_wait_all();            // smem must outlive the last TMA store
+        if (prof && et == 0) { p.dbg[5] = (unsigned long long)w_tfull; p.dbg[6] = (unsigned long long)(clock64() - t_begin); p.dbg[7] = (unsigned long long)ntile; }
         tc_fence_before();
     }
     __syncthreads();
