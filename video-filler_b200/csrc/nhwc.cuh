@@ -139,8 +139,9 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const bf16 *__restric
 // all loads issued before the arithmetic (bytes in flight hide HBM latency); partial sums are folded with shared-memory
 // atomics (TY-way contention at most) and leave the CTA as one global fp32 atomic per channel.
 constexpr int RED_U = 4;
+constexpr int BN_U = 2;   // BN backward keeps 24-40 per-channel constants in registers: 2 vectors of each tensor in flight per thread
 
-template <int NACC>
+template <int NACC, bool kAtomic = true>
 __device__ __forceinline__ void fold_and_flush(float (&acc)[NACC][8], bool active, float *__restrict__ out, int out_stride, int C_valid) {
     extern __shared__ float red_sh[];                 // [NACC][TX*8]
     const int TX = blockDim.x, tx = threadIdx.x, tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
@@ -170,86 +171,136 @@ __device__ __forceinline__ void fold_and_flush(float (&acc)[NACC][8], bool activ
     const int c_base = blockIdx.y * width;
     for (int i = tid; i < NACC * width; i += nthr) {
         int a = i / width, c = c_base + (i - a * width);
-        if (c < C_valid) atomicAdd(out + a * out_stride + c, red_sh[i]);
+        if (kAtomic) { if (c < C_valid) atomicAdd(out + a * out_stride + c, red_sh[i]); }
+        else if (c < out_stride) out[a * out_stride + c] = c < C_valid ? red_sh[i] : 0.f;   // this CTA's own partial row
     }
 }
 
-// BN backward pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * (y - mean[c]),  dz = g * act'(a)
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16 *__restrict__ g, const bf16 *__restrict__ a, const bf16 *__restrict__ y,
-        const float *__restrict__ mean, float *__restrict__ sums, int sums_stride, int64_t npix, int vec_per_pix, int C, int act, float negval) {
+// The per-channel sums of the backward kernels leave each CTA as one PARTIAL ROW (plain stores): hundreds of CTAs adding
+// into the same few cache lines serialise in the L2 atomic unit and used to cost more than the streaming pass itself.
+//   part[blockIdx.x][a][c],  row stride = NACC * Cp;  a later kernel (bn_bwd_coef / fold_rows) sums the rows.
+// activation derivative from the PRE-activation z = y * scale + shift (recomputed: saves re-reading the activation output)
+__device__ __forceinline__ float act_bwd_z(float z, int act, float negval) {
+    if (act == ACT_LEAKY) return z > 0.f ? 1.f : negval;
+    if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    if (act == ACT_TANH) { float t = tanhf(z); return 1.f - t * t; }
+    if (act == ACT_SIGMOID) { float t = 1.f / (1.f + __expf(-z)); return t * (1.f - t); }
+    return 1.f;
+}
+__device__ __forceinline__ void load8f(const float *__restrict__ p, int c0, int C, float (&o)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (c0 + k < C) ? p[c0 + k] : 0.f;
+}
+
+// compile-time activation derivative from the pre-activation z
+template <int ACT>
+__device__ __forceinline__ float dact_z(float z, float negval) {
+    if (ACT == ACT_LEAKY) return z > 0.f ? 1.f : negval;
+    if (ACT == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    return act_bwd_z(z, ACT, negval);
+}
+// bf16 pair -> two floats with two integer ops (a bf16 is the upper half of the fp32 bit pattern)
+__device__ __forceinline__ void unpack8b(const uint4 &u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+
+// BN backward pass 1: part[cta][0][c] = sum dz, part[cta][1][c] = sum dz * (y - mean[c]),  dz = g * act'(y*scale+shift)
+template <int ACT>
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce2_kernel(const bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
+        const float *__restrict__ shift, const float *__restrict__ mean, float *__restrict__ part, int Cp, int64_t npix, int vec_per_pix, int C,
+        float negval) {
     const int vec = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = vec < vec_per_pix;
     float acc[2][8] = {};
     if (active) {
-        float mu[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) mu[k] = (vec * 8 + k < C) ? mean[vec * 8 + k] : 0.f;
+        float mu[8], sc[8], sh[8];
+        load8f(mean, vec * 8, C, mu); load8f(scale, vec * 8, C, sc); load8f(shift, vec * 8, C, sh);
         const int64_t stride = (int64_t)gridDim.x * blockDim.y;
-        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * RED_U) {
-            uint4 rg[RED_U], ra[RED_U], ry[RED_U];
+        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * BN_U) {
+            uint4 rg[BN_U], ry[BN_U];
 #pragma unroll
-            for (int u = 0; u < RED_U; ++u) {
+            for (int u = 0; u < BN_U; ++u) {
                 int64_t p = p0 + u * stride;
-                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ra[u] = reinterpret_cast<const uint4 *>(a)[vi]; ry[u] = reinterpret_cast<const uint4 *>(y)[vi]; }
+                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = __ldg(reinterpret_cast<const uint4 *>(g) + vi); ry[u] = __ldg(reinterpret_cast<const uint4 *>(y) + vi); }
             }
 #pragma unroll
-            for (int u = 0; u < RED_U; ++u) {
+            for (int u = 0; u < BN_U; ++u) {
                 if (p0 + u * stride < npix) {
-                    float fg[8], fa[8], fy[8];
-                    unpack8(rg[u], fg); unpack8(ra[u], fa); unpack8(ry[u], fy);
+                    float fg[8], fy[8];
+                    unpack8b(rg[u], fg); unpack8b(ry[u], fy);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { float dz = fg[k] * act_bwd(fa[k], act, negval); acc[0][k] += dz; acc[1][k] += dz * (fy[k] - mu[k]); }
+                    for (int k = 0; k < 8; ++k) { float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval); acc[0][k] += dz; acc[1][k] = fmaf(dz, fy[k] - mu[k], acc[1][k]); }
                 }
             }
         }
     }
-    fold_and_flush<2>(acc, active, sums, sums_stride, C);
+    fold_and_flush<2, false>(acc, active, part + (size_t)blockIdx.x * 2 * Cp, Cp, C);
 }
-// coefficients for pass 2 + BN parameter gradients; zeroes the sums for the next use.
-//   coef[0][c] = s/n, coef[1][c] = invstd^2 * d/n, coef[2][c] = invstd * gamma
-__global__ void bn_bwd_coef_kernel(float *__restrict__ sums, int sums_stride, const float *__restrict__ gamma, const float *__restrict__ invstd,
-        float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = sums[c], d = sums[sums_stride + c], is = invstd[c];
-    sums[c] = 0.f; sums[sums_stride + c] = 0.f;
-    coef[c] = (float)(s / n); coef[C + c] = (float)(is * is * d / n); coef[2 * C + c] = (float)(is * (double)gamma[c]);
+// sums the partial rows; coefficients for pass 2 + BN parameter gradients.
+// sums_io [2][Cp]: rows > 0: written with the folded sums (the buffer a data-parallel run all-reduces); rows == 0: read.
+// block = (32 channels, 8 row lanes); grid = ceil(C / 32).  coef for pass 2 is stored pre-combined:
+//   g_y = dz * A - y * B + D  with  A = invstd*gamma, B = A * invstd^2 * d/n, D = (mean * invstd^2 * d/n - s/n) * A
+__global__ void __launch_bounds__(256) bn_bwd_coef2_kernel(const float *__restrict__ part, int rows, float *__restrict__ sums_io, int Cp, const float *__restrict__ gamma,
+        const float *__restrict__ invstd, const float *__restrict__ mean, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n, int emit_coef) {
+    __shared__ float sh_s[8][33], sh_d[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
+    float s0 = 0.f, d0 = 0.f, s1 = 0.f, d1 = 0.f;
+    if (c < C && rows > 0) {
+        int r = ry;
+        for (; r + 8 < rows; r += 16) {
+            const float *q = part + (size_t)r * 2 * Cp + c, *q2 = q + (size_t)16 * Cp;
+            s0 += q[0]; d0 += q[Cp]; s1 += q2[0]; d1 += q2[Cp];
+        }
+        if (r < rows) { const float *q = part + (size_t)r * 2 * Cp + c; s0 += q[0]; d0 += q[Cp]; }
+    }
+    sh_s[ry][threadIdx.x] = s0 + s1; sh_d[ry][threadIdx.x] = d0 + d1;
+    __syncthreads();
+    if (ry != 0 || c >= C) return;
+    double s = 0.0, d = 0.0;
+    if (rows > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s += (double)sh_s[i][threadIdx.x]; d += (double)sh_d[i][threadIdx.x]; }
+        if (sums_io) { sums_io[c] = (float)s; sums_io[Cp + c] = (float)d; }
+    } else { s = sums_io[c]; d = sums_io[Cp + c]; }
+    if (!emit_coef) return;
+    const double is = invstd[c], A = is * (double)gamma[c], k1 = is * is * d / n;
+    coef[c] = (float)A; coef[C + c] = (float)(A * k1); coef[2 * C + c] = (float)(((double)mean[c] * k1 - s / n) * A);
     if (ggamma) ggamma[c] += (float)(d * is);
     if (gbeta) gbeta[c] += (float)s;
 }
-// BN backward pass 2 (in place on g): g_y = (dz - s/n - (y-mean) * k) * invstd * gamma; optional sum of g_y -> conv gradBias
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, const bf16 *__restrict__ y,
-        const float *__restrict__ mean, const float *__restrict__ coef, float *__restrict__ gbias, int64_t npix, int vec_per_pix, int C,
-        int act, float negval) {
+// BN backward pass 2 (in place on g): g_y = dz * A - y * B + D (coefficients above); optional per-CTA partial sums of g_y
+// (-> conv gradBias, folded by fold_rows_kernel)
+template <int ACT>
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply2_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
+        const float *__restrict__ shift, const float *__restrict__ coef, float *__restrict__ gb_part, int Cp,
+        int64_t npix, int vec_per_pix, int C, float negval) {
     const int vec = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = vec < vec_per_pix;
     float acc[1][8] = {};
     if (active) {
-        float mu[8], c0[8], c1[8], c2[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            int c = vec * 8 + k;
-            bool ok = c < C;
-            mu[k] = ok ? mean[c] : 0.f; c0[k] = ok ? coef[c] : 0.f; c1[k] = ok ? coef[C + c] : 0.f; c2[k] = ok ? coef[2 * C + c] : 0.f;
-        }
+        float sc[8], sh[8], cA[8], cB[8], cD[8];
+        load8f(scale, vec * 8, C, sc); load8f(shift, vec * 8, C, sh);
+        load8f(coef, vec * 8, C, cA); load8f(coef + C, vec * 8, C, cB); load8f(coef + 2 * C, vec * 8, C, cD);
         const int64_t stride = (int64_t)gridDim.x * blockDim.y;
-        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * RED_U) {
-            uint4 rg[RED_U], ra[RED_U], ry[RED_U];
+        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * BN_U) {
+            uint4 rg[BN_U], ry[BN_U];
 #pragma unroll
-            for (int u = 0; u < RED_U; ++u) {
+            for (int u = 0; u < BN_U; ++u) {
                 int64_t p = p0 + u * stride;
-                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ra[u] = reinterpret_cast<const uint4 *>(a)[vi]; ry[u] = reinterpret_cast<const uint4 *>(y)[vi]; }
+                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ry[u] = __ldg(reinterpret_cast<const uint4 *>(y) + vi); }
             }
 #pragma unroll
-            for (int u = 0; u < RED_U; ++u) {
+            for (int u = 0; u < BN_U; ++u) {
                 int64_t p = p0 + u * stride;
                 if (p < npix) {
-                    float fg[8], fa[8], fy[8];
-                    unpack8(rg[u], fg); unpack8(ra[u], fa); unpack8(ry[u], fy);
+                    float fg[8], fy[8];
+                    unpack8b(rg[u], fg); unpack8b(ry[u], fy);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        float dz = fg[k] * act_bwd(fa[k], act, negval);
-                        float r = (dz - c0[k] - (fy[k] - mu[k]) * c1[k]) * c2[k];      // c2 == 0 on padded lanes
+                        float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval);
+                        float r = fmaf(dz, cA[k], fmaf(-fy[k], cB[k], cD[k]));          // all three are 0 on padded lanes
                         fg[k] = r; acc[0][k] += r;
                     }
                     reinterpret_cast<uint4 *>(g)[p * vec_per_pix + vec] = pack8(fg);
@@ -257,37 +308,71 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(bf16 *__restrict__ g,
             }
         }
     }
-    if (gbias) fold_and_flush<1>(acc, active, gbias, 0, C);
+    if (gb_part) fold_and_flush<1, false>(acc, active, gb_part + (size_t)blockIdx.x * Cp, Cp, C);
 }
-// activation-only backward (in place on g): g_y = g * act'(a); optional sum -> gradBias
-__global__ void __launch_bounds__(256) act_bwd_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, float *__restrict__ gbias, int64_t npix,
-        int vec_per_pix, int C, int act, float negval) {
+// activation-only backward (in place on g): g_y = g * act'(a); optional per-CTA partial sums -> gradBias
+template <int ACT>
+__global__ void __launch_bounds__(256, 4) act_bwd2_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, float *__restrict__ gb_part, int Cp, int64_t npix,
+        int vec_per_pix, int C, float negval) {
     const int vec = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = vec < vec_per_pix;
     float acc[1][8] = {};
     if (active) {
+        float keep[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) keep[k] = (vec * 8 + k < C) ? 1.f : 0.f;
         const int64_t stride = (int64_t)gridDim.x * blockDim.y;
         for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * RED_U) {
             uint4 rg[RED_U], ra[RED_U];
 #pragma unroll
             for (int u = 0; u < RED_U; ++u) {
                 int64_t p = p0 + u * stride;
-                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ra[u] = reinterpret_cast<const uint4 *>(a)[vi]; }
+                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ra[u] = __ldg(reinterpret_cast<const uint4 *>(a) + vi); }
             }
 #pragma unroll
             for (int u = 0; u < RED_U; ++u) {
                 int64_t p = p0 + u * stride;
                 if (p < npix) {
                     float fg[8], fa[8];
-                    unpack8(rg[u], fg); unpack8(ra[u], fa);
+                    unpack8b(rg[u], fg); unpack8b(ra[u], fa);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { float r = (vec * 8 + k < C) ? fg[k] * act_bwd(fa[k], act, negval) : 0.f; fg[k] = r; acc[0][k] += r; }
+                    for (int k = 0; k < 8; ++k) {
+                        float d;
+                        if (ACT == ACT_LEAKY) d = fa[k] > 0.f ? 1.f : negval; else if (ACT == ACT_RELU) d = fa[k] > 0.f ? 1.f : 0.f; else d = act_bwd(fa[k], ACT, negval);
+                        float r = fg[k] * d * keep[k]; fg[k] = r; acc[0][k] += r;
+                    }
                     reinterpret_cast<uint4 *>(g)[p * vec_per_pix + vec] = pack8(fg);
                 }
             }
         }
     }
-    if (gbias) fold_and_flush<1>(acc, active, gbias, 0, C);
+    if (gb_part) fold_and_flush<1, false>(acc, active, gb_part + (size_t)blockIdx.x * Cp, Cp, C);
+}
+// dst[c] += sum_r src[r][c] for a list of jobs (one CTA per job): folds the per-CTA partial rows of a whole backward sweep
+struct FoldJob { const float *src; float *dst; int rows, C, stride, fold, fold_stride; };   // fold > 1: column c also sums columns c + k*fold_stride (k < fold)
+__global__ void __launch_bounds__(256) fold_rows_kernel(const FoldJob *__restrict__ jobs) {
+    __shared__ float sh[8][33];
+    const FoldJob j = jobs[blockIdx.x];
+    const int tx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    for (int c0 = blockIdx.y * 32; c0 < j.C; c0 += gridDim.y * 32) {      // uniform per CTA
+        const int c = c0 + tx;
+        float s0 = 0.f, s1 = 0.f;
+        if (c < j.C) {
+            for (int f = 0; f < j.fold; ++f) {
+                const float *q = j.src + c + f * j.fold_stride;
+                int r = ry;
+                for (; r + 8 < j.rows; r += 16) { s0 += q[(size_t)r * j.stride]; s1 += q[(size_t)(r + 8) * j.stride]; }
+                if (r < j.rows) s0 += q[(size_t)r * j.stride];
+            }
+        }
+        sh[ry][tx] = s0 + s1;
+        __syncthreads();
+        if (ry == 0 && c < j.C) { float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += sh[i][tx];
+            j.dst[c] += t; }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------- discriminator head: 4x4 valid conv to 1 channel + Sigmoid + BCE

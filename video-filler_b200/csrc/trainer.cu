@@ -44,6 +44,8 @@ struct Block {
     int64_t col_rows = 0, col_k = 0;
     bf16 *Wt = nullptr;                     // transposed operand copy
     int cl_rows = 0;
+    float *part = nullptr;                  // per-CTA partial rows of the backward reductions [part_rows][2*Coutp]
+    int part_rows = 0;
     float *stats = nullptr, *bsums = nullptr, *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *coef = nullptr;
     float *running = nullptr;               // [2][Cout] running_mean, running_var
     int stats_cols = 0, fold = 1;
@@ -61,6 +63,8 @@ struct Net {
     bf16 *wbf = nullptr;
     int64_t *bias_seg = nullptr;
     int nbias_seg = 0;
+    nhwc::FoldJob *fold_jobs = nullptr;   // device: one job per block (conv gradBias <- partial rows)
+    std::vector<nhwc::FoldJob> fold_host;
     long long *adam_t = nullptr;   // device step counter (optimState.t)
     float *adam_step = nullptr;    // device: lr * sqrt(1-b2^t)/(1-b1^t)
     float lr = 0.f;
@@ -245,6 +249,16 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             if (alloc_tensor(t, b.a, N, oh, ow, b.Cout, b.Coutp)) return 1;
             if (alloc_tensor(t, b.g, N, oh, ow, b.Cout, b.Coutp)) return 1;
         }
+        if (sp.type != HEAD) {
+            // backward reductions: one partial row per CTA of the (pixel-strip x vector-group) grid
+            const int vpp = b.Coutp >= 8 ? b.Coutp / 8 : 1;
+            int tx = 1; while (tx < vpp && tx < 64) tx *= 2;
+            const int ty = 256 / tx, gy = (vpp + tx - 1) / tx;
+            const int64_t npix = b.Coutp >= 8 ? (int64_t)N * oh * ow : (int64_t)N * oh * ow / 2;
+            b.part_rows = (int)std::max<int64_t>(1, std::min<int64_t>((npix + ty * 4 - 1) / (ty * 4), (int64_t)s->sm_count * 4 / gy));
+            b.part = dalloc<float>(t, (int64_t)b.part_rows * 2 * std::max(b.Coutp, 8));
+            if (!b.part) return 1;
+        }
         if (b.thin) {
             b.col_rows = (int64_t)N * b.h * b.w; b.col_k = 16 * b.Clp;
             b.col = dalloc<bf16>(t, b.col_rows * b.col_k);
@@ -275,6 +289,17 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
     net.bias_seg = dalloc<int64_t>(t, bias_segs.size());
     if (!net.bias_seg) return 1;
     CK(cudaMemcpy(net.bias_seg, bias_segs.data(), bias_segs.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+
+    for (Block &b : net.blocks) {
+        if (b.type == HEAD) continue;
+        nhwc::FoldJob j;
+        j.src = b.part; j.dst = net.grad + b.b_off; j.rows = b.part_rows; j.C = b.Cout;
+        if (b.Coutp >= 8) { j.stride = b.Coutp; j.fold = 1; j.fold_stride = 0; } else { j.stride = 8; j.fold = 2; j.fold_stride = 4; }
+        net.fold_host.push_back(j);
+    }
+    net.fold_jobs = dalloc<nhwc::FoldJob>(t, net.fold_host.size());
+    if (!net.fold_jobs) return 1;
+    CK(cudaMemcpy(net.fold_jobs, net.fold_host.data(), net.fold_host.size() * sizeof(nhwc::FoldJob), cudaMemcpyHostToDevice));
 
     // operand copies + plans
     for (size_t i = 0; i < net.blocks.size(); ++i) {
@@ -441,47 +466,52 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         return;
     }
     const int vpp = b->Coutp >= 8 ? b->Coutp / 8 : 1;
-    float *gbias = want_params ? grad + b->b_off : nullptr;
+    float *gb_part = want_params ? b->part : nullptr;     // per-CTA partial sums of g_y -> conv gradBias (fold_gbias at the end of the sweep)
     const int64_t npix = b->a.pix();
+    const bool dp = t->cfg.world_size > 1;
     if (b->bn) {
         const double n_global = (double)t->Bglobal * b->a.H * b->a.W;
         float *gamma = master + b->g_off;
         float *gg = want_params ? grad + b->g_off : nullptr, *gbeta = want_params ? grad + b->be_off : nullptr;
         emit(t, "bn_bwd_reduce", [s, b, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
-            int gx = (int)std::max<int64_t>(1, std::min<int64_t>((npix + blk.y * 4 - 1) / (blk.y * 4), (int64_t)s->sm_count * 4 / gy));
-            nhwc::bn_bwd_reduce_kernel<<<dim3(gx, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, b->y.p, b->mean, b->bsums, b->Coutp,
-                npix, vpp, b->Cout, b->act, 0.2f);
-            KLAUNCH(s); return 0; }, b->bsums, 2 * (int64_t)b->Coutp);
-        emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
-            nhwc::bn_bwd_coef_kernel<<<(b->Cout + 127) / 128, 128, 0, s->stream>>>(b->bsums, b->Coutp, gamma, b->invstd, b->coef, gg, gbeta, b->Cout, n_global);
+            auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_RELU>;
+            kern<<<dim3(b->part_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->mean,
+                b->part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
-        emit(t, "bn_bwd_apply", [s, b, gbias, npix, vpp]() {
+        if (dp) {   // fold the partial rows into bsums, all-reduce bsums across ranks, then the coefficients
+            emit(t, "bn_bwd_fold", [s, b]() {
+                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0);
+                KLAUNCH(s); return 0; }, b->bsums, 2 * (int64_t)b->Coutp);
+            emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
+                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(nullptr, 0, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1);
+                KLAUNCH(s); return 0; });
+        } else {
+            emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
+                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, nullptr, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1);
+                KLAUNCH(s); return 0; });
+        }
+        emit(t, "bn_bwd_apply", [s, b, gb_part, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
-            int gx = (int)std::max<int64_t>(1, std::min<int64_t>((npix + blk.y * 4 - 1) / (blk.y * 4), (int64_t)s->sm_count * 4 / gy));
             // coef is laid out with stride Cout
-            nhwc::bn_bwd_apply_kernel<<<dim3(gx, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, b->y.p, b->mean, b->coef, gbias, npix, vpp,
-                b->Cout, b->act, 0.2f);
+            auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_apply2_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_apply2_kernel<nhwc::ACT_RELU>;
+            kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->coef,
+                gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
     } else if (b->Coutp >= 8) {
-        emit(t, "act_bwd", [s, b, gbias, npix, vpp]() {
+        emit(t, "act_bwd", [s, b, gb_part, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
-            int gx = (int)std::max<int64_t>(1, std::min<int64_t>((npix + blk.y * 4 - 1) / (blk.y * 4), (int64_t)s->sm_count * 4 / gy));
-            nhwc::act_bwd_kernel<<<dim3(gx, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gbias, npix, vpp, b->Cout, b->act, 0.2f);
+            auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::act_bwd2_kernel<nhwc::ACT_LEAKY> : (b->act == nhwc::ACT_RELU ? nhwc::act_bwd2_kernel<nhwc::ACT_RELU> : nhwc::act_bwd2_kernel<nhwc::ACT_TANH>);
+            kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
     } else {
-        // Cp == 4 (3-channel image output): two pixels form one 8-lane vector, lanes k and k+4 are the same channel;
-        // the bias sum is reduced into an 8-wide scratch and folded afterwards.  Pad lanes carry zero gradients.
-        float *fold8 = dalloc<float>(t, 8);
-        emit(t, "act_bwd4", [s, b, gbias, npix, fold8]() {
+        // Cp == 4 (3-channel image output): two pixels form one 8-lane vector, lanes k and k+4 are the same channel
+        // (the fold job adds the two halves).  Pad lanes carry zero gradients.
+        emit(t, "act_bwd4", [s, b, gb_part, npix]() {
             dim3 blk(1, 256);
-            int64_t npair = npix / 2;
-            int gx = (int)std::max<int64_t>(1, std::min<int64_t>((npair + 1023) / 1024, (int64_t)s->sm_count * 4));
-            if (gbias && cenn_check_cuda(cudaMemsetAsync(fold8, 0, 8 * sizeof(float), s->stream), "memset", __FILE__, __LINE__)) return 1;
-            nhwc::act_bwd_kernel<<<dim3(gx, 1), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gbias ? fold8 : nullptr, npair, 1, 8, b->act, 0.2f);
-            KLAUNCH(s);
-            if (gbias) { fold_bias4_kernel<<<1, 32, 0, s->stream>>>(fold8, gbias, b->Cout); KLAUNCH(s); }
-            return 0; });
+            auto kern = b->act == nhwc::ACT_TANH ? nhwc::act_bwd2_kernel<nhwc::ACT_TANH> : (b->act == nhwc::ACT_LEAKY ? nhwc::act_bwd2_kernel<nhwc::ACT_LEAKY> : nhwc::act_bwd2_kernel<nhwc::ACT_RELU>);
+            kern<<<dim3(b->part_rows, 1), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gb_part, 8, npix / 2, 1, 8, 0.2f);
+            KLAUNCH(s); return 0; });
     }
     // weight gradient
     if (want_params) {
@@ -517,6 +547,12 @@ void emit_zero_bias(T *t, Net &net) {
     Net *n = &net;
     emit(t, "zero_conv_bias", [s, n]() {
         nhwc::zero_segments_kernel<<<n->nbias_seg, 128, 0, s->stream>>>(n->master, n->wbf, n->bias_seg, n->nbias_seg); KLAUNCH(s); return 0; });
+}
+void emit_fold_gbias(T *t, Net &net) {
+    cenn_state *s = t->s;
+    Net *n = &net;
+    emit(t, "fold_gbias", [s, n]() {
+        nhwc::fold_rows_kernel<<<dim3((unsigned)n->fold_host.size(), 8), 256, 0, s->stream>>>(n->fold_jobs); KLAUNCH(s); return 0; });
 }
 void emit_zero_grad(T *t, Net &net) {
     cenn_state *s = t->s;
@@ -583,6 +619,7 @@ int build_program(T *t) {
     for (size_t i = 0; i < D.blocks.size(); ++i) emit_forward(t, D, i, true);
     emit_bce(t, headD, 1.f, CENN_LOSS_ERRD_REAL, true);
     for (size_t i = D.blocks.size(); i-- > 0;) emit_backward(t, D, i, true, i > 0 || c.dead_dgrad);
+    emit_fold_gbias(t, D);
     // G forward
     emit_copy(t, "g_in<-ctx", G.input.p, t->real_ctx.p, G.input.elems());
     for (size_t i = 0; i < G.blocks.size(); ++i) emit_forward(t, G, i, true);
@@ -597,6 +634,7 @@ int build_program(T *t) {
     for (size_t i = 0; i < D.blocks.size(); ++i) emit_forward(t, D, i, true);
     emit_bce(t, headD, 0.f, CENN_LOSS_ERRD_FAKE, true);
     for (size_t i = D.blocks.size(); i-- > 0;) emit_backward(t, D, i, true, i > 0 || c.dead_dgrad);
+    emit_fold_gbias(t, D);
     emit(t, "gradD_sync", []() { return 0; }, D.grad, D.nparam);
     emit_adam(t, D);
     emit_weight_prep(t, D);
@@ -637,6 +675,7 @@ int build_program(T *t) {
         }
     }
     for (size_t i = G.blocks.size(); i-- > 0;) emit_backward(t, G, i, true, i > 0 || c.dead_dgrad);
+    emit_fold_gbias(t, G);
     emit(t, "gradG_sync", []() { return 0; }, G.grad, G.nparam);
     emit_adam(t, G);
     emit_weight_prep(t, G);
