@@ -397,7 +397,9 @@ static int wgrad_common(cenn_state *s, TcPlan *pl, tc::WgradParams &p, int num_t
     int max_splits = (num_kb_total + 3) / 4;            // at least 4 k-blocks (256 pixels) per split
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
+    if (p.accumulate == 2) p.accumulate = splits == 1 ? 0 : 1;
     if (!p.accumulate) splits = 1;
+    pl->overwrites = p.accumulate ? 0 : 1;
     p.num_kb_total = num_kb_total;
     p.kb_per_split = (num_kb_total + splits - 1) / splits;
     splits = (num_kb_total + p.kb_per_split - 1) / p.kb_per_split;

@@ -36,6 +36,7 @@ struct TcPlan {
     alignas(16) unsigned char params[1536];
     void *kb_dev = nullptr;       // owned device k-block table (gather GEMM)
     double flops = 0;             // algorithmic FLOPs of one launch
+    int overwrites = 0;           // wgrad: 1 = the launch stores its result (no accumulation; the target need not be zeroed)
 };
 int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep);
 int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep);
@@ -51,6 +52,8 @@ int tc_fprop_s2(cenn_state *s, const bf16 *L, const bf16 *Wf, bf16 *S, int N, in
 // P2: L[pix',cl] = sum_{ab,cs} S[pix+d_ab,cs] * Wt[phase][cl][ab][cs]     (conv dgrad, full-conv fprop)
 int tc_dgrad_s2(cenn_state *s, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep);
 // P3: gW[cs][tap][cl] (+)= scale * sum_pix S[pix,cs] * L[gather_tap(pix),cl]
+//     accumulate: 1 = add into gW (red.add, split-K allowed); 0 = store (single split forced); 2 = store when one split
+//     covers K anyway, otherwise add (the plan's `overwrites` says which)
 int tc_wgrad_s2(cenn_state *s, const bf16 *S, const bf16 *L, float *gW, int N, int h, int w, int Cs, int Csp, int Clp, float scale, int accumulate);
 // P4: out[M,Nc] = A[M,K] * B[Nc,K]^T  (both K-major; K multiple of 8; ldo = output row stride in elements)
 int tc_gemm(cenn_state *s, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep);

@@ -629,44 +629,53 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                int kb = kb_begin + i;
-                int s = i % stages;
-                uint32_t ph = (uint32_t)(i / stages) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                int tx = kb % p.tiles_x, ty = (kb / p.tiles_x) % p.tiles_y, tn = kb / (p.tiles_x * p.tiles_y);
-                int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
-                uint8_t *a_dst = tiles + (size_t)s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            const uint32_t tiles_u32 = smem_u32(tiles), full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
+            // the two (tap, chunk) row-blocks of this M tile: gather coordinates are fixed for the whole K loop
+            int ac0[2], adx[2], a2[2], ady[2];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    int rb = mt * 2 + h;
-                    int tap = rb / p.chunks_per_tap, chunk = rb - tap * p.chunks_per_tap;
-                    tap = min(tap, 15);
-                    tma_load_5d(&tmL, &full_bar[s], a_dst + h * BOX_BYTES, chunk * 64 + p.gx0[tap], x0 + p.gdx[tap], p.g2[tap], y0 + p.gdy[tap], n0);
-                }
-                for (int c = 0; c < BN / 64; ++c)
-                    tma_load_5d(&tmS, &full_bar[s], b_dst + c * BOX_BYTES, (nt * (BN / 64) + c) * 64, x0, 0, y0, n0);
+            for (int h = 0; h < 2; ++h) {
+                const int rb = mt * 2 + h;
+                int tap = rb / p.chunks_per_tap; const int chunk = rb - tap * p.chunks_per_tap;
+                tap = min(tap, 15);
+                ac0[h] = chunk * 64 + p.gx0[tap]; adx[h] = p.gdx[tap]; a2[h] = p.g2[tap]; ady[h] = p.gdy[tap];
+            }
+            int tx = kb_begin % p.tiles_x, ty = (kb_begin / p.tiles_x) % p.tiles_y, tn = kb_begin / (p.tiles_x * p.tiles_y);
+            int s = 0; uint32_t ph = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait_u32(empty_u32 + 8u * s, ph ^ 1u);
+                const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+                const uint32_t a_dst = tiles_u32 + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES, fb = full_u32 + 8u * s;
+                mbar_expect_tx_u32(fb, STAGE_BYTES);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) tma_load_5d_u32(&tmL, fb, a_dst + h * BOX_BYTES, ac0[h], x0 + adx[h], a2[h], y0 + ady[h], n0);
+#pragma unroll
+                for (int c = 0; c < BN / 64; ++c) tma_load_5d_u32(&tmS, fb, b_dst + c * BOX_BYTES, (nt * (BN / 64) + c) * 64, x0, 0, y0, n0);
+                if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++tn; } }
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc(128, BN, 1, 1);
+        // MN-major descriptors: lo = start address | LBO (distance between the two 64-element M/N chunks) << 16 ; hi = SBO 1024 | v1 | SW128
+        const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t a_lo0 = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | ((BOX_BYTES >> 4) << 16);
+        const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
+        int s = 0; uint32_t ph = 0;
         for (int i = 0; i < nkb; ++i) {
-            int s = i % stages;
-            uint32_t ph = (uint32_t)(i / stages) & 1u;
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait_u32(full_u32 + 8u * s, ph);
             tc_fence_after();
-            if (lane == 0) {
-                uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+            if (elect_one()) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)s * (STAGE_BYTES >> 4), b_lo = a_lo + (A_BYTES >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {   // 16 pixels (K) per MMA = 2 groups of 8 K-rows = 2048 B
-                    uint64_t ad = make_desc(a_addr + k * 2048, BOX_BYTES, 1024), bd = make_desc(b_addr + k * 2048, BOX_BYTES, 1024);
+                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + 128u * k), bd = ((uint64_t)desc_hi << 32) | (b_lo + 128u * k);
                     umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
                 }
-                umma_commit(&empty_bar[s]);
+                umma_commit_u32(empty_u32 + 8u * s);
                 if (i == nkb - 1) umma_commit(acc_bar);
             }
             __syncwarp();
+            if (++s == stages) { s = 0; ph ^= 1u; }
         }
     } else {
         const int q = warp & 3;

@@ -188,7 +188,7 @@ std::vector<Spec> spec_D(const cenn_trainer_config &c) {
 int grid1d(const cenn_state *s, int64_t items, int threads = 256, int per_sm = 8) { return bw_grid(s, items, threads, per_sm); }
 
 // ---- building a net: shapes, buffers, parameter layout, plans ---------------------------------------------------
-int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int in_C, bool first_dgrad) {
+int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int in_C, bool first_dgrad, bool single_pass) {
     cenn_state *s = t->s;
     const int N = t->B;
     // input tensor (thin: 3 or 12 channels)
@@ -301,6 +301,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
     if (!net.fold_jobs) return 1;
     CK(cudaMemcpy(net.fold_jobs, net.fold_host.data(), net.fold_host.size() * sizeof(nhwc::FoldJob), cudaMemcpyHostToDevice));
 
+    const int acc_mode = single_pass ? 2 : 1;   // gradients of a net with one backward pass per step may be stored instead of accumulated
     // operand copies + plans
     for (size_t i = 0; i < net.blocks.size(); ++i) {
         Block &b = net.blocks[i];
@@ -341,7 +342,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             case CONV_V4: {
                 int K = 16 * b.Clp;
                 if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, b.Cs, K, b.Csp, ep_f)) return 1;
-                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.in.p, gW, N, b.Cs, b.Csp, K, 1.f, 1)) return 1;
+                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.in.p, gW, N, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
                 b.Wt = dalloc<bf16>(t, (int64_t)K * b.Csp);
                 if (!b.Wt) return 1;
                 if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, b.Wt, dgrad_out, N, K, b.Csp, K, ep_n)) return 1;
@@ -352,7 +353,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                 b.Wt = dalloc<bf16>(t, (int64_t)K * b.Csp);
                 if (!b.Wt) return 1;
                 if (tc_plan_gemm(s, &b.p_fwd, b.in.p, b.Wt, fwd_out, N, K, b.Csp, K, ep_f)) return 1;
-                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.in.p, b.g.p, gW, N, b.Cs, b.Csp, K, 1.f, 1)) return 1;
+                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.in.p, b.g.p, gW, N, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
                 if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, dgrad_out, N, b.Cs, K, b.Csp, ep_n)) return 1;
                 break;
             }
@@ -557,7 +558,16 @@ void emit_fold_gbias(T *t, Net &net) {
 void emit_zero_grad(T *t, Net &net) {
     cenn_state *s = t->s;
     Net *n = &net;
-    emit(t, "zero_grad", [s, n]() { return cenn_check_cuda(cudaMemsetAsync(n->grad, 0, n->nparam * sizeof(float), s->stream), "memset", __FILE__, __LINE__); });
+    // zero everything except the weight ranges whose wgrad launch stores its result
+    std::vector<std::pair<int64_t, int64_t>> segs;
+    int64_t cur = 0;
+    for (const Block &b : net.blocks)
+        if (b.p_wgrad.overwrites && b.w_count > 0) { if (b.w_off > cur) segs.push_back({cur, b.w_off - cur}); cur = b.w_off + b.w_count; }
+    if (net.nparam > cur) segs.push_back({cur, net.nparam - cur});
+    emit(t, "zero_grad", [s, n, segs]() {
+        for (const auto &sg : segs)
+            if (cenn_check_cuda(cudaMemsetAsync(n->grad + sg.first, 0, sg.second * sizeof(float), s->stream), "memset", __FILE__, __LINE__)) return 1;
+        return 0; });
 }
 void emit_adam(T *t, Net &net) {
     cenn_state *s = t->s;
@@ -764,8 +774,8 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     const bool video = cfg->variant == 1;
     const int dsize = video ? t->F : t->F / 2;
     int rc = 0;
-    rc = rc || build_net(t, t->D, spec_D(*cfg), dsize, ncv, true);
-    rc = rc || build_net(t, t->G, spec_G(*cfg), t->F, ncv, cfg->dead_dgrad != 0);
+    rc = rc || build_net(t, t->D, spec_D(*cfg), dsize, ncv, true, false);
+    rc = rc || build_net(t, t->G, spec_G(*cfg), t->F, ncv, cfg->dead_dgrad != 0, true);
     if (rc) { cenn_trainer_destroy(t); return 1; }
     t->G.lr = (cfg->wtl2 > 0.f && cfg->wtl2 < 1.f) ? cfg->lr * 10.f : cfg->lr;   // train.lua:219-226
     t->D.lr = cfg->lr;
