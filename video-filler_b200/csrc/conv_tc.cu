@@ -231,7 +231,7 @@ int tc_unpack_grad_add(cenn_state *s, const float *g, float *gw, int Cs, int Cl,
 
 // ------------------------------------------------------------------ plan storage helpers
 static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap larger than the plan slot");
-static_assert(sizeof(tc::GatherGemmParams) <= 1536 && sizeof(tc::WgradParams) <= 1536, "kernel params larger than the plan slot");
+static_assert(sizeof(tc::GatherGemmParams) <= 1536 && sizeof(tc::WgradParams) <= 1536 && sizeof(tc::PatchDgradParams) <= 1536, "kernel params larger than the plan slot");
 static CUtensorMap *planA(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmA); }
 static CUtensorMap *planB(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmB); }
 static CUtensorMap *planO(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmO); }
@@ -260,7 +260,22 @@ static int launch_wgrad_t(cenn_state *s, const TcPlan *pl) {
     CK_LAUNCH(s);
     return 0;
 }
+template <int BN>
+static int launch_patch_dgrad_t(cenn_state *s, const TcPlan *pl) {
+    const tc::PatchDgradParams &p = *reinterpret_cast<const tc::PatchDgradParams *>(pl->params);
+    tc::patch_dgrad_kernel<BN><<<dim3(pl->grid[0], 1, 1), tc::GEMM_THREADS, pl->smem, s->stream>>>(
+        *reinterpret_cast<const CUtensorMap *>(pl->tmA), *reinterpret_cast<const CUtensorMap *>(pl->tmB), *reinterpret_cast<const CUtensorMap *>(pl->tmO), p, pl->stages);
+    CK_LAUNCH(s);
+    return 0;
+}
 int tc_launch(cenn_state *s, const TcPlan *pl) {
+    if (pl->kind == 3) {
+        switch (pl->BN) {
+            case 16: return launch_patch_dgrad_t<16>(s, pl);
+            case 64: return launch_patch_dgrad_t<64>(s, pl);
+            case 128: return launch_patch_dgrad_t<128>(s, pl);
+        }
+    }
     if (pl->kind == 1) {
         switch (pl->BN) {
             case 32: return launch_gather_t<32>(s, pl);
@@ -313,6 +328,10 @@ int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, b
 // ------------------------------------------------------------------ P2: dgrad-type (4 sub-pixel phases)
 int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep) {
     REQUIRE(Csp % 64 == 0, "tc_dgrad_s2: Csp must be a multiple of 64 (got %d)", Csp);
+    if (!ep.dbg && !ep.dbg_flags) {      // the patch kernel covers every layer with an 8 x 8 or larger small side
+        int rc = tc_plan_dgrad_patch(s, pl, S, Wt, L, N, h, w, Csp, Cl, Clp, cl_rows, ep);
+        if (rc != 2) return rc;
+    }
     int bw, bh, bn;
     choose_box(w, h, 128, bw, bh, bn);
     if (map_plain(planA(pl), S, N, h, w, Csp, bw, bh, bn)) return 1;
@@ -347,6 +366,69 @@ int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, b
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * N * h * w * (double)Cl * 16.0 * Csp;
     return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles * 4);
+}
+
+// ------------------------------------------------------------------ P2b: dgrad-type, patch kernel
+template <int BN>
+static int set_attr_patch_dgrad() {
+    static bool done = false;
+    if (!done) { CK(cudaFuncSetAttribute(tc::patch_dgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); done = true; }
+    return 0;
+}
+int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep) {
+    const bool thin = Clp == 4 || Clp == 16;
+    if (w < 8 || h < 8 || Csp % 64 != 0 || !(thin || Clp % 64 == 0) || (thin && ep.stats) || getenv("CENN_NO_PATCH")) return 2;
+    const int bh = pow2_le(h, 16), bn = 16 / bh;
+    const int BN = thin ? 16 : (Clp % 128 == 0 ? 128 : 64);
+    REQUIRE(cl_rows >= Cl, "tc_dgrad_patch: cl_rows (%d) too small for Cl %d", cl_rows, Cl);
+    {   // S patch: dims (c, x, n, y) so that shared memory holds [y][n][x] rows of 64 channels
+        uint64_t d[4] = {(uint64_t)Csp, (uint64_t)w, (uint64_t)N, (uint64_t)h};
+        uint64_t st[3] = {(uint64_t)Csp * 2, (uint64_t)h * w * Csp * 2, (uint64_t)w * Csp * 2};
+        uint32_t bx[4] = {64, 10, (uint32_t)bn, (uint32_t)bh + 2};
+        if (make_map(planA(pl), S, 4, d, st, bx)) return 1;
+    }
+    if (map_2d(planB(pl), Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
+    memset(pl->tmO, 0, sizeof(pl->tmO));
+    const int H2 = 2 * h, W2 = 2 * w;
+    if (BN >= 64) {   // output: dims (px*Clp + c, x', n, y', py)
+        uint64_t d[5] = {(uint64_t)2 * Clp, (uint64_t)w, (uint64_t)N, (uint64_t)h, 2};
+        uint64_t st[4] = {(uint64_t)2 * Clp * 2, (uint64_t)H2 * W2 * Clp * 2, (uint64_t)2 * W2 * Clp * 2, (uint64_t)W2 * Clp * 2};
+        uint32_t bx[5] = {64, 8, (uint32_t)bn, (uint32_t)bh, 1};
+        if (make_map(planO(pl), L, 5, d, st, bx)) return 1;
+    }
+    tc::PatchDgradParams p = {};
+    p.chunks = Csp / 64;
+    p.tiles_x = (w + 7) / 8; p.tiles_y = (h + bh - 1) / bh;
+    p.m_tiles = p.tiles_x * p.tiles_y * ((N + bn - 1) / bn);
+    p.n_tiles = thin ? 1 : (Cl + BN - 1) / BN;
+    p.bh = bh; p.bn = bn; p.bn_log2 = ilog2(bn);
+    p.patch_bytes = 128 * 10 * bn * (bh + 2);
+    p.patch_stride = (p.patch_bytes + 1023) / 1024 * 1024;
+    for (int ph = 0; ph < 4; ++ph)
+        for (int ab = 0; ab < 4; ++ab) {
+            const int dy = DYP[ph >> 1][ab >> 1], dx = DYP[ph & 1][ab & 1];
+            p.a_off[ph][ab] = (((1 + dy) * bn) * 10 + (1 + dx)) * 128;
+        }
+    p.Csp = Csp; p.cl_rows = cl_rows;
+    p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cl; p.Clp = Clp; p.H2 = H2; p.W2 = W2;
+    p.out = ep.no_bf16 ? nullptr : L;
+    p.bias = ep.bias; p.stats = ep.stats; p.stats_stride = ep.stats_stride; p.act = ep.act; p.act_param = ep.act_param;
+    memcpy(pl->params, &p, sizeof(p));
+    pl->flops = 2.0 * N * h * w * (double)Cl * 16.0 * Csp;
+    const int bstage = 4 * BN * 128, out_bytes = BN >= 64 ? 128 * BN * 2 * (BN >= 128 ? 1 : 2) : 0;
+    const int fixed = 1024 + 2 * p.patch_stride + out_bytes + 26 * 8 + 3 * BN * 4 + 64;
+    int stages = (SMEM_LIMIT - fixed) / bstage;
+    if (stages > 8) stages = 8;
+    REQUIRE(stages >= 2, "tc_dgrad_patch: shared memory too small (BN %d)", BN);
+    pl->kind = 3; pl->BN = BN; pl->stages = stages;
+    pl->smem = (size_t)stages * bstage + fixed;
+    const int total = p.m_tiles * p.n_tiles;
+    pl->grid[0] = (unsigned)(total < s->sm_count ? total : s->sm_count); pl->grid[1] = 1; pl->grid[2] = 1;
+    switch (BN) {
+        case 16: return set_attr_patch_dgrad<16>();
+        case 64: return set_attr_patch_dgrad<64>();
+        default: return set_attr_patch_dgrad<128>();
+    }
 }
 
 // ------------------------------------------------------------------ P4: plain GEMM

@@ -26,7 +26,7 @@ struct TcEpilogue {
 // A prepared launch: tensor maps, kernel parameters, k-block table and grid are built once (shapes and
 // buffer addresses are static in the executor) and replayed every step / captured into a CUDA graph.
 struct TcPlan {
-    int kind = 0;                 // 1 = K-major gather GEMM, 2 = MN-major wgrad GEMM
+    int kind = 0;                 // 1 = K-major gather GEMM, 2 = MN-major wgrad GEMM, 3 = patch kernel (dgrad type)
     int BN = 0, stages = 0;
     unsigned grid[3] = {1, 1, 1};
     size_t smem = 0;
@@ -40,6 +40,8 @@ struct TcPlan {
 };
 int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep);
 int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep);
+// patch variant of the dgrad type (w, h >= 8; Csp % 64 == 0; Clp % 64 == 0 or Clp in {4, 16}); returns 2 if the shape is not covered
+int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep);
 int tc_plan_wgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *L, float *gW, int N, int h, int w, int Cs, int Csp, int Clp, float scale, int accumulate);
 int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep);
 int tc_plan_wgrad_plain(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *L, float *gW, int M, int Cs, int Csp, int Clp, float scale, int accumulate);

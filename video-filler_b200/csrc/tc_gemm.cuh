@@ -93,12 +93,17 @@ __device__ __forceinline__ void tma_load_5d_u32(const CUtensorMap *m, uint32_t b
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_u32(const CUtensorMap *m, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
@@ -129,6 +134,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -583,6 +593,308 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         if (kTma && et == 0) bulk_wait_all();            // smem must outlive the last TMA store
         if (prof && et == 0) { p.dbg[5] = (unsigned long long)w_tfull; p.dbg[6] = (unsigned long long)(clock64() - t_begin); p.dbg[7] = (unsigned long long)ntile; }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------ patch kernel, dgrad type (4 sub-pixel phases)
+// L[n, 2y+py, 2x+px, cl] = sum_{a,b,cs} S[n, y+dy(py,a), x+dx(px,b), cs] * Wt[ph][cl][ab][cs]        (conv dgrad, full-conv fprop)
+// All 16 (phase, tap) MMAs of a 128-pixel tile read SHIFTED WINDOWS of one shared-memory patch of S (halo of one pixel),
+// loaded once per 64-channel chunk: the 16 per-tap operand loads of the gather kernel (the L2 -> SM traffic that bounded
+// it) collapse into one.  A UMMA descriptor may start any whole number of 128-byte rows into a TMA-written SWIZZLE_128B
+// region and step between 8-row groups by any multiple of 16 bytes (profiles/r1_desc_probe.log), so a window is just a
+// start address: the tile's rows are ordered (y, n, x) with 8 x-positions per group and the patch is stored [y][n][x]
+// with a pitch of 10 pixels, which makes the group stride uniform (1280 B) even when a tile spans several samples.
+// Warp roles as in the gather kernel.  Pipelines: patch (2 buffers) and weight stages (one stage = the 4 taps of one
+// phase, 16 MMAs per barrier round trip) -> 4 accumulators per tile (one per phase) -> epilogue per phase.
+struct PatchDgradParams {
+    int chunks;                  // Csp / 64
+    int m_tiles, n_tiles;        // tiles enumerated m fastest
+    int tiles_x, tiles_y;        // m-tile -> (tx, ty, tn); box = 8 (x) x bn (samples) x bh (y)
+    int bh, bn, bn_log2;
+    int patch_bytes;             // TMA box bytes: 128 * 10 * bn * (bh + 2)
+    int patch_stride;            // patch_bytes rounded up to 1024
+    int a_off[4][4];             // byte offset of window (phase, tap ab) inside the patch
+    int Csp, cl_rows;            // B coordinates: column ab*Csp + 64*c, row ph*cl_rows + nt*BN
+    int out_w, out_h, out_n;     // extent of the S pixel grid
+    int n_valid, Clp;            // valid / padded output channels of one phase
+    int H2, W2;                  // output image size (direct-store path)
+    __nv_bfloat16 *out;          // output tensor (direct-store path, BN == 16)
+    const float *bias;
+    float *stats; int stats_stride;
+    int act; float act_param;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                   const __grid_constant__ PatchDgradParams p, int stages) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr bool kTma = BN >= 64;
+    constexpr int NSETS = (8 * BN <= 512) ? 2 : 1;            // accumulator sets (4 phases x BN columns each)
+    constexpr uint32_t TMEM_COLS = NSETS * 4 * BN < 32 ? 32 : NSETS * 4 * BN;
+    constexpr uint32_t BTAP_BYTES = BN * 128;                 // one tap of one phase: BN rows x 64 cs
+    constexpr uint32_t BSTAGE_BYTES = 4 * BTAP_BYTES;
+    constexpr uint32_t OUT_BYTES = kTma ? 128u * BN * 2u : 0u; // one phase tile
+    constexpr int NOUT = BN >= 128 ? 1 : 2;                    // staging buffers (BN = 128: shared memory allows one)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *patch = smem;                                                    // [2][patch_stride]
+    uint8_t *bst = patch + 2 * (size_t)p.patch_stride;                        // [stages][BSTAGE_BYTES]
+    uint8_t *out_stage = bst + (size_t)stages * BSTAGE_BYTES;                 // [NOUT][OUT_BYTES]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + NOUT * OUT_BYTES);
+    uint64_t *pfull = bars, *pempty = bars + 2, *bfull = bars + 4, *bempty = bars + 12, *tfull = bars + 20, *tempty = bars + 22;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);            // +192 B
+    float *col_acc = reinterpret_cast<float *>(bars + 26);                    // [2][BN]
+    float *bias_s = col_acc + 2 * BN;                                         // [BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int txy = p.tiles_x * p.tiles_y;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmS); prefetch_tmap(&tmB);
+        if (kTma) prefetch_tmap(&tmO);
+        for (int i = 0; i < 2; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], 1); mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < stages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) col_acc[i] = 0.f;
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t patch_u32 = smem_u32(patch), bst_u32 = smem_u32(bst);
+            const uint32_t pfull_u32 = smem_u32(pfull), pempty_u32 = smem_u32(pempty), bfull_u32 = smem_u32(bfull), bempty_u32 = smem_u32(bempty);
+            const int chunks = p.chunks, Csp = p.Csp, cl_rows = p.cl_rows;
+            int pb = 0; uint32_t pph = 0; int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+                const int tn = mt / txy, rem = mt - tn * txy, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                const int x0 = tx * 8, y0 = ty * p.bh, n0 = tn * p.bn;
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait_u32(pempty_u32 + 8u * pb, pph ^ 1u);
+                    mbar_expect_tx_u32(pfull_u32 + 8u * pb, (uint32_t)p.patch_bytes);
+                    tma_load_4d_u32(&tmS, pfull_u32 + 8u * pb, patch_u32 + (uint32_t)pb * (uint32_t)p.patch_stride, c * 64, x0 - 1, n0, y0 - 1);
+                    if (++pb == 2) { pb = 0; pph ^= 1u; }
+                    for (int phs = 0; phs < 4; ++phs) {
+                        mbar_wait_u32(bempty_u32 + 8u * s, ph ^ 1u);
+                        const uint32_t fb = bfull_u32 + 8u * s, dst = bst_u32 + (uint32_t)s * BSTAGE_BYTES;
+                        mbar_expect_tx_u32(fb, BSTAGE_BYTES);
+                        const int brow = phs * cl_rows + nt * BN;
+#pragma unroll
+                        for (int ab = 0; ab < 4; ++ab) tma_load_2d_u32(&tmB, fb, dst + ab * BTAP_BYTES, ab * Csp + c * 64, brow);
+                        if (++s == stages) { s = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(128, BN, 0, 0);
+        const uint32_t hiA = (1280u >> 4) | (1u << 14) | (2u << 29);          // group stride = one patch row of 10 pixels
+        const uint32_t hiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t patch_lo = ((smem_u32(patch) & 0x3FFFFu) >> 4) | (1u << 16), bst_lo = ((smem_u32(bst) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t pfull_u32 = smem_u32(pfull), pempty_u32 = smem_u32(pempty), bfull_u32 = smem_u32(bfull), bempty_u32 = smem_u32(bempty);
+        const uint32_t tfull_u32 = smem_u32(tfull), tempty_u32 = smem_u32(tempty);
+        uint32_t aoff[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) aoff[i][j] = (uint32_t)p.a_off[i][j] >> 4;
+        const int chunks = p.chunks;
+        int pb = 0; uint32_t pph = 0; int s = 0; uint32_t ph = 0; int set = 0; uint32_t set_ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait_u32(tempty_u32 + 8u * set, set_ph ^ 1u);
+            tc_fence_after();
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait_u32(pfull_u32 + 8u * pb, pph);
+                const uint32_t a_base = patch_lo + (((uint32_t)pb * (uint32_t)p.patch_stride) >> 4);
+#pragma unroll
+                for (int phs = 0; phs < 4; ++phs) {
+                    mbar_wait_u32(bfull_u32 + 8u * s, ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((set * 4 + phs) * BN);
+                        const uint32_t b_base = bst_lo + (uint32_t)s * (BSTAGE_BYTES >> 4);
+#pragma unroll
+                        for (int ab = 0; ab < 4; ++ab)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t ad = ((uint64_t)hiA << 32) | (a_base + aoff[phs][ab] + 2u * k);
+                                const uint64_t bd = ((uint64_t)hiB << 32) | (b_base + (uint32_t)ab * (BTAP_BYTES >> 4) + 2u * k);
+                                umma_f16(d_tmem, ad, bd, idesc, (c | ab | k) != 0);
+                            }
+                        umma_commit_u32(bempty_u32 + 8u * s);
+                        if (phs == 3) {
+                            umma_commit_u32(pempty_u32 + 8u * pb);
+                            if (c == chunks - 1) umma_commit_u32(tfull_u32 + 8u * set);
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+                if (++pb == 2) { pb = 0; pph ^= 1u; }
+            }
+            if (NSETS == 2) { set ^= 1; set_ph ^= (uint32_t)(set == 0); } else set_ph ^= 1u;
+        }
+    } else {
+        const int q = warp & 3, et = threadIdx.x - 64;
+        const int row = q * 32 + lane;
+        const int rx = row & 7, rn = (row >> 3) & (p.bn - 1), ry = row >> (3 + p.bn_log2);
+        const int act = p.act; const float act_param = p.act_param;
+        const bool has_bias = p.bias != nullptr, has_stats = p.stats != nullptr;
+        int set = 0; uint32_t set_ph = 0;
+        int stat_key = -1;
+        int ob = 0;                                       // staging buffer of the next phase tile
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+            const int tn = mt / txy, rem = mt - tn * txy, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            const int x0 = tx * 8, y0 = ty * p.bh, n0 = tn * p.bn;
+            const bool row_ok = (x0 + rx) < p.out_w && (y0 + ry) < p.out_h && (n0 + rn) < p.out_n;
+            if (has_stats && nt != stat_key) {
+                if (stat_key >= 0) {
+                    epi_bar_sync();
+                    for (int i = et; i < BN; i += 128) {
+                        int c = stat_key * BN + i;
+                        if (c < p.n_valid) { atomicAdd(p.stats + c, col_acc[i]); atomicAdd(p.stats + p.stats_stride + c, col_acc[BN + i]); }
+                        col_acc[i] = 0.f; col_acc[BN + i] = 0.f;
+                    }
+                    epi_bar_sync();
+                }
+                stat_key = nt;
+            }
+            mbar_wait(&tfull[set], set_ph);
+            tc_fence_after();
+            int ncols = p.n_valid - nt * BN; ncols = ncols > BN ? BN : ncols;
+            if constexpr (kTma) {
+                if (has_bias) for (int i = et; i < BN; i += 128) { const int c = nt * BN + i; bias_s[i] = c < p.n_valid ? __ldg(p.bias + c) : 0.f; }
+                const int last_c0 = ((ncols + 31) >> 5) * 32 - 32;
+#pragma unroll 1
+                for (int phs = 0; phs < 4; ++phs) {
+                    uint8_t *stage = out_stage + (size_t)ob * OUT_BYTES;
+                    if (et == 0) { if (NOUT == 2) bulk_wait_read1(); else bulk_wait_read0(); }   // earlier stores have finished reading this buffer
+                    epi_bar_sync();
+                    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * 4 + phs) * BN);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        float v[32];
+                        if (c0 < ncols) {
+                            uint32_t rr[32];
+                            tmem_ld32(t_addr + (uint32_t)c0, rr);
+                            tmem_ld_wait();
+                            if (phs == 3 && c0 == last_c0) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&tempty[set]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+                            if (has_bias) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c0 + j);
+                                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                                }
+                            }
+                            if (act != ACT_NONE) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], act, act_param);
+                            }
+                            if (!row_ok) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                            } else if (c0 + 32 > ncols) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (c0 + j >= ncols) v[j] = 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        }
+                        uint8_t *slab_row = stage + (size_t)(c0 >> 6) * (128 * 128) + (size_t)row * 128;
+                        const int cb = (c0 & 63) >> 3;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                            *reinterpret_cast<uint4 *>(slab_row + (((cb + i) ^ (row & 7)) << 4)) = pk;
+                        }
+                    }
+                    if (has_stats) {
+                        __syncwarp();
+                        for (int sl = 0; sl * 64 < ncols; ++sl) {
+                            const uint8_t *slab = stage + (size_t)sl * (128 * 128) + (size_t)(q * 32) * 128;
+                            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 8
+                            for (int r = 0; r < 32; ++r) {
+                                const uint32_t wv = *reinterpret_cast<const uint32_t *>(slab + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2));
+                                const float a = __uint_as_float(wv << 16), b = __uint_as_float(wv & 0xFFFF0000u);
+                                s1a += a; s2a = fmaf(a, a, s2a); s1b += b; s2b = fmaf(b, b, s2b);
+                            }
+                            atomicAdd(&col_acc[sl * 64 + 2 * lane], s1a); atomicAdd(&col_acc[sl * 64 + 2 * lane + 1], s1b);
+                            atomicAdd(&col_acc[BN + sl * 64 + 2 * lane], s2a); atomicAdd(&col_acc[BN + sl * 64 + 2 * lane + 1], s2b);
+                        }
+                    }
+                    fence_proxy_async();
+                    epi_bar_sync();
+                    if (et == 0) {
+                        for (int sl = 0; sl < BN / 64; ++sl) {
+                            const int col = nt * BN + sl * 64;
+                            if (col < p.Clp) tma_store_5d(&tmO, stage + (size_t)sl * (128 * 128), (phs & 1) * p.Clp + col, x0, n0, y0, phs >> 1);
+                        }
+                        bulk_commit();
+                    }
+                    if (NOUT == 2) ob ^= 1;
+                }
+            } else {
+                // ---- thin outputs (Clp = 4 or 16): every lane owns one S pixel = a 2x2 block of output pixels
+                uint32_t r4[4][16];
+#pragma unroll
+                for (int phs = 0; phs < 4; ++phs) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * 4 + phs) * BN), r4[phs]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[set]);
+                if (row_ok) {
+                    const int Clp = p.Clp;
+                    float bv[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) bv[k] = (has_bias && k < ncols) ? __ldg(p.bias + k) : 0.f;
+#pragma unroll
+                    for (int phs = 0; phs < 4; ++phs) {
+                        const int py = phs >> 1, px = phs & 1;
+                        __nv_bfloat16 *o = p.out + (((long long)(n0 + rn) * p.H2 + 2 * (y0 + ry) + py) * p.W2 + 2 * (x0 + rx) + px) * Clp;
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int k = 0; k < 16; k += 2) {
+                            float f0 = k < ncols ? apply_act(__uint_as_float(r4[phs][k]) + bv[k], act, act_param) : 0.f;
+                            float f1 = k + 1 < ncols ? apply_act(__uint_as_float(r4[phs][k + 1]) + bv[k + 1], act, act_param) : 0.f;
+                            __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                            pk[k >> 1] = *reinterpret_cast<uint32_t *>(&h);
+                        }
+                        if (Clp == 4) *reinterpret_cast<uint2 *>(o) = make_uint2(pk[0], pk[1]);
+                        else { reinterpret_cast<uint4 *>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); reinterpret_cast<uint4 *>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]); }
+                    }
+                }
+            }
+            if (NSETS == 2) { set ^= 1; set_ph ^= (uint32_t)(set == 0); } else set_ph ^= 1u;
+        }
+        if (has_stats && stat_key >= 0) {
+            epi_bar_sync();
+            for (int i = et; i < BN; i += 128) {
+                int c = stat_key * BN + i;
+                if (c < p.n_valid) { atomicAdd(p.stats + c, col_acc[i]); atomicAdd(p.stats + p.stats_stride + c, col_acc[BN + i]); }
+            }
+        }
+        if (kTma && et == 0) bulk_wait_all();
         tc_fence_before();
     }
     __syncthreads();
