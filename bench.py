@@ -175,12 +175,20 @@ def main():
         da, db = T.CudaTensor.from_numpy(ctx), T.CudaTensor.from_numpy(center)
         host.append((ha, hb, da, db, ctx.nbytes + center.nbytes))
 
+    if world > 1:
+        # library-owned NCCL communicator: rank 0 creates the id, torch.distributed carries it to the other ranks
+        idbuf = np.zeros(128, np.uint8)
+        if rank == 0:
+            api.cenn_dist_unique_id(idbuf.ctypes.data_as(C.c_void_p))
+        idt = torch.from_numpy(idbuf).cuda()
+        dist.broadcast(idt, src=0)
+        idbuf = idt.cpu().numpy()
+        api.cenn_dist_init(st, idbuf.ctypes.data_as(C.c_void_p), world, rank)
+
     def step_device(i):
+        # world > 1: the executor all-reduces BN statistics, gradients and losses itself (NCCL, inside its CUDA graph)
         _, _, da, db, _ = host[i % n_batches]
-        if world == 1:
-            trn.step_device(da.ptr, db.ptr)
-            return
-        train.dp_step(trn, da.ptr, db.ptr, None, lambda buf, n, dbl: dist.all_reduce(wrap_device(buf, n, "f8" if dbl else "f4", torch)))
+        trn.step_device(da.ptr, db.ptr)
 
     losses = None
     with torch.cuda.stream(stream):
@@ -205,26 +213,28 @@ def main():
         losses = trn.read_losses()
         # ---- end-to-end: host buffers in, losses out, every step (single-process API call)
         e2e_ms = None
-        if world == 1:
-            for i in range(2):
-                trn.step_host(host[i % n_batches][0], host[i % n_batches][1])
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for i in range(args.steps):
-                losses = trn.step_host(host[i % n_batches][0], host[i % n_batches][1])
-            torch.cuda.synchronize()
-            e2e_ms = (time.perf_counter() - t0) * 1e3
+        for i in range(2):
+            trn.step_host(host[i % n_batches][0], host[i % n_batches][1])
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            losses = trn.step_host(host[i % n_batches][0], host[i % n_batches][1])
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
         # ---- per-op CUDA-event profile for the roofline of the dominant kernels
-        prof = None
-        if rank == 0:
-            prof = trn.profile_step(host[0][2].ptr, host[0][3].ptr, repeats=3)
+        prof = trn.profile_step(host[0][2].ptr, host[0][3].ptr, repeats=3)    # every rank runs it (it contains the all-reduces)
 
-    t_ms = torch.tensor([ms], device="cuda")
+    t_ms = torch.tensor([ms, e2e_ms], device="cuda")
     if dist:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
+    ms, e2e_ms = float(t_ms[0].item()), float(t_ms[1].item())
     if rank != 0:
         if dist:
+            api.cenn_dist_shutdown(st)
             dist.destroy_process_group()
         return
     hbm, tf_burst, tf_sus, peak_src = peaks()
@@ -243,11 +253,11 @@ def main():
         "step_frac_of_bf16_sustained": STEP_GFLOP_PER_SAMPLE * 1e-3 * value / (tf_sus * world),
     }
     if e2e_ms is not None:
-        line["e2e"] = {"value": B * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
+        line["e2e"] = {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
                        "h2d_bytes_per_step": int(host[0][4]), "d2h_bytes_per_step": 32}
     else:
         line["e2e"] = None
-    if prof:
+    if prof and rank == 0:
         tc_ms, tc_flops, tc_n = prof["tc_ms"], prof["tc_flops"], prof["tc_launches"]
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
@@ -261,6 +271,7 @@ def main():
                                 "sample": "one 64-sample step of the oracle port (numpy restatement of the Torch7 gpu=0 path), %.1f s" % sec}
     print(json.dumps(line))
     if dist:
+        api.cenn_dist_shutdown(st)
         dist.destroy_process_group()
 
 

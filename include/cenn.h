@@ -58,6 +58,17 @@ CENN_API int cenn_get_stream(cenn_state *s, void **cuda_stream);
 CENN_API int cenn_synchronize(cenn_state *s);                   /* cutorch.synchronize() */
 CENN_API int cenn_kernel_launches(cenn_state *s, int64_t *count); /* kernels launched so far */
 
+/* ------------------------------------------------- data parallelism (one process per GPU) -- */
+/* The reference is single-device (cutorch.setDevice(opt.gpu), train.lua:250); these calls are what a multi-GPU launcher
+ * adds: rank 0 creates an id, every rank receives it out of band (file, env, torch.distributed broadcast) and joins.
+ * Once a communicator exists, a cenn_trainer created with world_size > 1 all-reduces its BN statistics, gradients and
+ * loss accumulators itself (NCCL over NVLink, enqueued on the state's stream and captured in the step's CUDA graph). */
+CENN_API int cenn_dist_unique_id(void *id128_host);                       /* rank 0: 128-byte ncclUniqueId */
+CENN_API int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int rank);
+CENN_API int cenn_dist_all_reduce(cenn_state *s, void *buf_dev, int64_t count, int is_double);   /* in-place sum, fp32 / fp64 */
+CENN_API int cenn_dist_broadcast(cenn_state *s, void *buf_dev, int64_t bytes, int root);
+CENN_API int cenn_dist_shutdown(cenn_state *s);
+
 /* ------------------------------------------------- storage (tensor:cuda(), :float()) -- */
 CENN_API int cenn_malloc(cenn_state *s, size_t bytes, void **dptr);
 CENN_API int cenn_free(cenn_state *s, void *dptr);

@@ -22,6 +22,10 @@ struct cenn_state {
     size_t ws_bytes = 0;
     void *ws2 = nullptr;
     size_t ws2_bytes = 0;
+    // data parallelism (dist.cu): NCCL communicator of this process's GPU
+    void *comm = nullptr;
+    int world = 1, rank = 0;
+    cudaStream_t comm_stream = nullptr;   // gradient all-reduces overlapped with the backward sweep
 };
 static const int RED_SLOTS = 64;
 
@@ -29,6 +33,7 @@ void cenn_set_error(const char *fmt, ...);
 int cenn_check_cuda(cudaError_t e, const char *what, const char *file, int line);
 void *cenn_workspace(cenn_state *s, size_t bytes);   // stream-ordered reuse; grows with cudaMalloc
 void *cenn_workspace2(cenn_state *s, size_t bytes);
+int cenn_dist_all_reduce_on(cenn_state *s, void *buf, int64_t count, int is_double, cudaStream_t stream);
 
 #define CK(expr) do { if (cenn_check_cuda((expr), #expr, __FILE__, __LINE__)) return 1; } while (0)
 #define CK_LAUNCH(s) do { (s)->launches++; if (cenn_check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)) return 1; } while (0)

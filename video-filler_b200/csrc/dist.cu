@@ -1,0 +1,102 @@
+// dist.cu -- data-parallel plumbing: one process per GPU, an NCCL communicator owned by the library so that the
+// all-reduces of the step (BN batch statistics, BN backward sums, gradients, loss accumulators) are enqueued on the
+// state's stream between the kernels -- and captured into the step's CUDA graph with them.
+// The reference has no multi-GPU code; equivalence target = the single-process step at the global batch.
+// NCCL is resolved at run time (dlopen of libnccl.so.2: the copy PyTorch already loaded, else the system one), so the
+// library has no link-time dependency and single-GPU users never touch it.
+#include <dlfcn.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void *NcclComm;
+typedef int (*fn_get_id)(NcclUniqueId *);
+typedef int (*fn_init_rank)(NcclComm *, int, NcclUniqueId, int);
+typedef int (*fn_all_reduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_broadcast)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_destroy)(NcclComm);
+typedef const char *(*fn_errstr)(int);
+typedef int (*fn_group)(void);
+struct NcclApi {
+    void *handle = nullptr;
+    fn_get_id get_id = nullptr; fn_init_rank init_rank = nullptr; fn_all_reduce all_reduce = nullptr; fn_broadcast broadcast = nullptr;
+    fn_destroy destroy = nullptr; fn_errstr errstr = nullptr; fn_group group_start = nullptr, group_end = nullptr;
+} g_nccl;
+enum { NCCL_SUM = 0, NCCL_UINT8 = 1, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };
+
+int load_nccl() {
+    if (g_nccl.handle) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    void *h = nullptr;
+    for (const char *n : names) { h = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (h) break; }
+    if (!h) { cenn_set_error("NCCL not found (dlopen libnccl.so.2: %s)", dlerror()); return 1; }
+    g_nccl.get_id = (fn_get_id)dlsym(h, "ncclGetUniqueId");
+    g_nccl.init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
+    g_nccl.all_reduce = (fn_all_reduce)dlsym(h, "ncclAllReduce");
+    g_nccl.broadcast = (fn_broadcast)dlsym(h, "ncclBroadcast");
+    g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
+    g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
+    g_nccl.group_start = (fn_group)dlsym(h, "ncclGroupStart");
+    g_nccl.group_end = (fn_group)dlsym(h, "ncclGroupEnd");
+    if (!g_nccl.get_id || !g_nccl.init_rank || !g_nccl.all_reduce || !g_nccl.broadcast || !g_nccl.destroy || !g_nccl.errstr) {
+        cenn_set_error("libnccl.so.2 lacks an expected symbol"); dlclose(h); return 1;
+    }
+    g_nccl.handle = h;
+    return 0;
+}
+int nccl_check(int rc, const char *what) {
+    if (rc == 0) return 0;
+    cenn_set_error("NCCL error in %s: %s", what, g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    return 1;
+}
+}  // namespace
+
+int cenn_dist_all_reduce_on(cenn_state *s, void *buf, int64_t count, int is_double, cudaStream_t stream) {
+    if (!s->comm) { cenn_set_error("cenn_dist_all_reduce: no communicator (call cenn_dist_init)"); return 1; }
+    if (count <= 0) return 0;
+    return nccl_check(g_nccl.all_reduce(buf, buf, (size_t)count, is_double ? NCCL_FLOAT64 : NCCL_FLOAT32, NCCL_SUM, s->comm, stream), "ncclAllReduce");
+}
+
+extern "C" {
+
+int cenn_dist_unique_id(void *id128_host) {
+    if (!id128_host) { cenn_set_error("null id buffer"); return 1; }
+    if (load_nccl()) return 1;
+    NcclUniqueId id;
+    if (nccl_check(g_nccl.get_id(&id), "ncclGetUniqueId")) return 1;
+    memcpy(id128_host, &id, sizeof(id));
+    return 0;
+}
+
+int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int rank) {
+    API_BEGIN(s);
+    REQUIRE(id128_host && world_size >= 1 && rank >= 0 && rank < world_size, "cenn_dist_init: bad arguments (world %d, rank %d)", world_size, rank);
+    REQUIRE(!s->comm, "cenn_dist_init: communicator already initialised");
+    if (load_nccl()) return 1;
+    NcclUniqueId id;
+    memcpy(&id, id128_host, sizeof(id));
+    NcclComm comm = nullptr;
+    if (nccl_check(g_nccl.init_rank(&comm, world_size, id, rank), "ncclCommInitRank")) return 1;
+    s->comm = comm; s->world = world_size; s->rank = rank;
+    return 0;
+}
+
+int cenn_dist_all_reduce(cenn_state *s, void *buf_dev, int64_t count, int is_double) {
+    API_BEGIN(s);
+    return cenn_dist_all_reduce_on(s, buf_dev, count, is_double, s->stream);
+}
+
+int cenn_dist_broadcast(cenn_state *s, void *buf_dev, int64_t bytes, int root) {
+    API_BEGIN(s);
+    REQUIRE(s->comm, "cenn_dist_broadcast: no communicator (call cenn_dist_init)");
+    return nccl_check(g_nccl.broadcast(buf_dev, buf_dev, (size_t)bytes, NCCL_UINT8, root, s->comm, s->stream), "ncclBroadcast");
+}
+
+int cenn_dist_shutdown(cenn_state *s) {
+    API_BEGIN(s);
+    if (s->comm) { cudaStreamSynchronize(s->stream); g_nccl.destroy(s->comm); s->comm = nullptr; s->world = 1; s->rank = 0; }
+    return 0;
+}
+
+}  // extern "C"

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce2_kernel(const bf16 *__re
 // block = (32 channels, 8 row lanes); grid = ceil(C / 32).  coef for pass 2 is stored pre-combined:
 //   g_y = dz * A - y * B + D  with  A = invstd*gamma, B = A * invstd^2 * d/n, D = (mean * invstd^2 * d/n - s/n) * A
 __global__ void __launch_bounds__(256) bn_bwd_coef2_kernel(const float *__restrict__ part, int rows, float *__restrict__ sums_io, int Cp, const float *__restrict__ gamma,
-        const float *__restrict__ invstd, const float *__restrict__ mean, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n, int emit_coef) {
+        const float *__restrict__ invstd, const float *__restrict__ mean, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n, int emit_coef, float grad_scale) {
     __shared__ float sh_s[8][33], sh_d[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
     float s0 = 0.f, d0 = 0.f, s1 = 0.f, d1 = 0.f;
@@ -267,8 +267,9 @@ __global__ void __launch_bounds__(256) bn_bwd_coef2_kernel(const float *__restri
     if (!emit_coef) return;
     const double is = invstd[c], A = is * (double)gamma[c], k1 = is * is * d / n;
     coef[c] = (float)A; coef[C + c] = (float)(A * k1); coef[2 * C + c] = (float)(((double)mean[c] * k1 - s / n) * A);
-    if (ggamma) ggamma[c] += (float)(d * is);
-    if (gbeta) gbeta[c] += (float)s;
+    // data parallel: s and d are already GLOBAL sums and the gradient vector is summed over ranks later -> 1/world here
+    if (ggamma) ggamma[c] += (float)(d * is) * grad_scale;
+    if (gbeta) gbeta[c] += (float)s * grad_scale;
 }
 // BN backward pass 2 (in place on g): g_y = dz * A - y * B + D (coefficients above); optional per-CTA partial sums of g_y
 // (-> conv gradBias, folded by fold_rows_kernel)

@@ -482,14 +482,15 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             KLAUNCH(s); return 0; });
         if (dp) {   // fold the partial rows into bsums, all-reduce bsums across ranks, then the coefficients
             emit(t, "bn_bwd_fold", [s, b]() {
-                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0);
+                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0, 1.f);
                 KLAUNCH(s); return 0; }, b->bsums, 2 * (int64_t)b->Coutp);
-            emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
-                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(nullptr, 0, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1);
+            const float inv_world = 1.f / (float)t->cfg.world_size;
+            emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global, inv_world]() {
+                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(nullptr, 0, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1, inv_world);
                 KLAUNCH(s); return 0; });
         } else {
             emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
-                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, nullptr, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1);
+                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, nullptr, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1, 1.f);
                 KLAUNCH(s); return 0; });
         }
         emit(t, "bn_bwd_apply", [s, b, gb_part, npix, vpp]() {
@@ -695,9 +696,18 @@ int build_program(T *t) {
     return 0;
 }
 
+// sum a sync point's buffer across the data-parallel ranks (library-owned NCCL communicator, same stream as the kernels)
+int reduce_sync_point(T *t, const Op &op) {
+    cenn_state *s = t->s;
+    if (!op.sync_buf || t->cfg.world_size <= 1 || !s->comm) return 0;
+    const bool is_loss = op.sync_buf == reinterpret_cast<float *>(t->loss_acc);
+    return cenn_dist_all_reduce_on(s, op.sync_buf, is_loss ? 8 : op.sync_count, is_loss ? 1 : 0, s->stream);
+}
 int run_ops(T *t, size_t from, size_t to) {
-    for (size_t i = from; i < to; ++i)
+    for (size_t i = from; i < to; ++i) {
         if (t->prog[i].fn()) return 1;
+        if (reduce_sync_point(t, t->prog[i])) return 1;
+    }
     return 0;
 }
 
@@ -952,7 +962,7 @@ int cenn_trainer_profile_step(cenn_trainer *t, const float *a, const float *b, c
     t->cur_a = a; t->cur_b = b; t->cur_m = mask;
     CK(cudaEventRecord(ev[0], st));
     int rc = 0;
-    for (size_t i = 0; i < n && !rc; ++i) { rc = t->prog[i].fn(); CK(cudaEventRecord(ev[i + 1], st)); }
+    for (size_t i = 0; i < n && !rc; ++i) { rc = t->prog[i].fn() || reduce_sync_point(t, t->prog[i]); CK(cudaEventRecord(ev[i + 1], st)); }
     CK(cudaStreamSynchronize(st));
     std::string all;
     for (size_t i = 0; i < n && !rc; ++i) {
