@@ -232,11 +232,19 @@ def main():
     if dist:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t_ms[0].item()), float(t_ms[1].item())
-    if rank != 0:
+    def finish():
+        # the step's CUDA graph holds the NCCL communicator: release the executor first, then the communicator
+        nonlocal trn
+        trn.close()
+        trn = None
         if dist:
             api.cenn_dist_shutdown(st)
             dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        os._exit(0)         # nothing left to do; do not depend on interpreter-exit ordering of CUDA / NCCL teardown
+
+    if rank != 0:
+        finish()
     hbm, tf_burst, tf_sus, peak_src = peaks()
     total_samples = B * world * args.steps
     value = total_samples / (ms / 1e3)
@@ -270,9 +278,7 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                                 "sample": "one 64-sample step of the oracle port (numpy restatement of the Torch7 gpu=0 path), %.1f s" % sec}
     print(json.dumps(line))
-    if dist:
-        api.cenn_dist_shutdown(st)
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

@@ -202,10 +202,15 @@ class FusedTrainer:
         api().cenn_trainer_create(state(), C.byref(cfg), C.byref(h))
         self.h = h
 
+    def close(self):
+        """Destroy the executor (buffers, CUDA graph).  Must precede cenn_dist_shutdown: the graph references the communicator."""
+        if getattr(self, "h", None):
+            api().cenn_trainer_destroy(self.h)
+            self.h = None
+
     def __del__(self):
         try:
-            if getattr(self, "h", None):
-                api().cenn_trainer_destroy(self.h)
+            self.close()
         except Exception:
             pass
 
