@@ -1,0 +1,251 @@
+--[[ cenn.lua -- LuaJIT-FFI binding of libcenn.so for the UNCHANGED reference scripts
+     (train.lua, train_vid_weighted.lua, train_deepernet.lua, test*.lua, demo.lua of MKimiSH/video-filler).
+
+NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no LuaJIT / Torch7 (SURVEY.md 8c).  It is the binding a
+maintainer adds on a machine that has them; every C entry point it calls is declared in include/cenn.h and exercised by
+the Python ctypes mirror (video-filler_b200/nn.py) that the parity tests drive.  INTEGRATION.md walks through it.
+
+What it does
+  * `require 'cunn'` / `require 'cutorch'` stand-ins: cutorch.setDevice(i) -> cenn_init(i-1); tensor:cuda() gives a
+    torch.CudaTensor-like userdata (device pointer + sizes) backed by cenn_malloc / cenn_copy_h2d.
+  * re-points the THNN entry of every module class on the hot path: nn.SpatialConvolution, nn.SpatialFullConvolution,
+    nn.SpatialBatchNormalization, nn.LeakyReLU, nn.ReLU (nn.Threshold), nn.Tanh, nn.Sigmoid, nn.BCECriterion,
+    nn.MSECriterion, nn.AbsCriterion, plus fused nn.MaskedMSECriterion and nn.GDLCriterion.  Class type names are
+    kept ('nn.SpatialConvolution', ...) so weights_init (train.lua:58-67), the per-closure bias zeroing
+    (train.lua:279-280) and util.save (util.lua:33-50) keep working.
+  * optional fast path: cenn.Trainer wraps the whole-step executor (cenn_trainer_*) behind the two closures.
+]]
+local ffi = require 'ffi'
+
+ffi.cdef[[
+typedef struct cenn_state cenn_state;
+typedef struct cenn_trainer cenn_trainer;
+int cenn_init(int device, cenn_state **out);
+int cenn_shutdown(cenn_state *s);
+const char *cenn_last_error(void);
+int cenn_set_precision(cenn_state *s, int mode);
+int cenn_synchronize(cenn_state *s);
+int cenn_malloc(cenn_state *s, size_t bytes, void **dptr);
+int cenn_free(cenn_state *s, void *dptr);
+int cenn_copy_h2d(cenn_state *s, void *dst, const void *src_host, size_t bytes);
+int cenn_copy_d2h(cenn_state *s, void *dst_host, const void *src, size_t bytes);
+int cenn_copy_d2d(cenn_state *s, void *dst, const void *src, size_t bytes);
+int cenn_fill(cenn_state *s, float *x, int64_t n, float v);
+int cenn_mul(cenn_state *s, float *x, int64_t n, float a);
+int cenn_axpy(cenn_state *s, float *y, const float *x, int64_t n, float a);
+int cenn_addcmul(cenn_state *s, float *y, float a, const float *p, const float *q, int64_t n);
+int cenn_addcdiv(cenn_state *s, float *y, float a, const float *p, const float *q, int64_t n);
+int cenn_sqrt(cenn_state *s, float *x, int64_t n);
+int cenn_normal(cenn_state *s, float *x, int64_t n, float mean, float std, uint64_t seed);
+int cenn_SpatialConvolutionMM_updateOutput(cenn_state *s, const float *input, float *output, const float *weight, const float *bias,
+    int64_t batch, int64_t nInputPlane, int64_t inH, int64_t inW, int64_t nOutputPlane, int kW, int kH, int dW, int dH, int padW, int padH);
+int cenn_SpatialConvolutionMM_updateGradInput(cenn_state *s, const float *gradOutput, float *gradInput, const float *weight,
+    int64_t batch, int64_t nInputPlane, int64_t inH, int64_t inW, int64_t nOutputPlane, int kW, int kH, int dW, int dH, int padW, int padH);
+int cenn_SpatialConvolutionMM_accGradParameters(cenn_state *s, const float *input, const float *gradOutput, float *gradWeight, float *gradBias,
+    int64_t batch, int64_t nInputPlane, int64_t inH, int64_t inW, int64_t nOutputPlane, int kW, int kH, int dW, int dH, int padW, int padH, float scale);
+int cenn_SpatialFullConvolution_updateOutput(cenn_state *s, const float *input, float *output, const float *weight, const float *bias,
+    int64_t batch, int64_t nInputPlane, int64_t inH, int64_t inW, int64_t nOutputPlane, int kW, int kH, int dW, int dH, int padW, int padH, int adjW, int adjH);
+int cenn_SpatialFullConvolution_updateGradInput(cenn_state *s, const float *gradOutput, float *gradInput, const float *weight,
+    int64_t batch, int64_t nInputPlane, int64_t inH, int64_t inW, int64_t nOutputPlane, int kW, int kH, int dW, int dH, int padW, int padH, int adjW, int adjH);
+int cenn_SpatialFullConvolution_accGradParameters(cenn_state *s, const float *input, const float *gradOutput, float *gradWeight, float *gradBias,
+    int64_t batch, int64_t nInputPlane, int64_t inH, int64_t inW, int64_t nOutputPlane, int kW, int kH, int dW, int dH, int padW, int padH, int adjW, int adjH, float scale);
+int cenn_BatchNormalization_updateOutput(cenn_state *s, const float *input, float *output, const float *weight, const float *bias,
+    float *runningMean, float *runningVar, float *saveMean, float *saveStd, int64_t batch, int64_t C, int64_t spatial, int train, double momentum, double eps);
+int cenn_BatchNormalization_backward(cenn_state *s, const float *input, const float *gradOutput, float *gradInput, float *gradWeight, float *gradBias,
+    const float *weight, const float *runningMean, const float *runningVar, const float *saveMean, const float *saveStd,
+    int64_t batch, int64_t C, int64_t spatial, int train, double scale, double eps);
+int cenn_LeakyReLU_updateOutput(cenn_state *s, const float *input, float *output, int64_t n, double negval, int inplace);
+int cenn_LeakyReLU_updateGradInput(cenn_state *s, const float *input, const float *gradOutput, float *gradInput, int64_t n, double negval, int inplace);
+int cenn_Threshold_updateOutput(cenn_state *s, const float *input, float *output, int64_t n, double threshold, double val, int inplace);
+int cenn_Threshold_updateGradInput(cenn_state *s, const float *input, const float *gradOutput, float *gradInput, int64_t n, double threshold, int inplace);
+int cenn_Tanh_updateOutput(cenn_state *s, const float *input, float *output, int64_t n);
+int cenn_Tanh_updateGradInput(cenn_state *s, const float *gradOutput, float *gradInput, const float *output, int64_t n);
+int cenn_Sigmoid_updateOutput(cenn_state *s, const float *input, float *output, int64_t n);
+int cenn_Sigmoid_updateGradInput(cenn_state *s, const float *gradOutput, float *gradInput, const float *output, int64_t n);
+int cenn_BCECriterion_updateOutput(cenn_state *s, const float *input, const float *target, int64_t n, int sizeAverage, float *loss_host);
+int cenn_BCECriterion_updateGradInput(cenn_state *s, const float *input, const float *target, float *gradInput, int64_t n, int sizeAverage);
+int cenn_MSECriterion_updateOutput(cenn_state *s, const float *input, const float *target, int64_t n, int sizeAverage, float *loss_host);
+int cenn_MSECriterion_updateGradInput(cenn_state *s, const float *input, const float *target, float *gradInput, int64_t n, int sizeAverage);
+int cenn_MaskedMSECriterion_forward_backward(cenn_state *s, const float *input, const float *target, const float *mask, float *gradInput,
+    int64_t n, double mWeight, float *loss_host);
+int cenn_GDLCriterion_forward_backward(cenn_state *s, const float *input, const float *target, float *gradInput,
+    int64_t batch, int64_t C, int64_t H, int64_t W, float *loss_host);
+int cenn_AdamFlat(cenn_state *s, float *x, const float *g, float *m, float *v, int64_t n, double lr, double beta1, double beta2, double eps, int64_t t);
+]]
+
+local lib = ffi.load(os.getenv('CENN_LIB') or 'libcenn.so')
+local cenn = { lib = lib, state = nil }
+
+-- THNN functions return void and raise through THError; libcenn returns a status and a thread-local message.
+local function check(rc) if rc ~= 0 then error(ffi.string(lib.cenn_last_error()), 3) end end
+
+---------------------------------------------------------------------------------------------- cutorch stand-in
+local cutorch = {}
+function cutorch.setDevice(i)                       -- train.lua:250 (1-based)
+  local out = ffi.new('cenn_state*[1]')
+  check(lib.cenn_init(i - 1, out)); cenn.state = out[0]
+end
+function cutorch.synchronize() check(lib.cenn_synchronize(cenn.state)) end
+package.loaded['cutorch'] = cutorch
+_G.cutorch = cutorch
+
+---------------------------------------------------------------------------------------------- CudaTensor (fp32, contiguous)
+local CudaTensor = {}; CudaTensor.__index = CudaTensor
+local function numel(sz) local n = 1; for _, d in ipairs(sz) do n = n * d end; return n end
+function cenn.CudaTensor(...)
+  local sz = {...}; if type(sz[1]) == 'table' then sz = sz[1] end
+  local p = ffi.new('void*[1]')
+  check(lib.cenn_malloc(cenn.state, math.max(1, numel(sz)) * 4, p))
+  local t = setmetatable({ sz = sz, ptr = ffi.cast('float*', p[0]) }, CudaTensor)
+  t.gc = ffi.gc(p[0], function(q) lib.cenn_free(cenn.state, q) end)
+  return t
+end
+function CudaTensor:nElement() return numel(self.sz) end
+function CudaTensor:size(d) if d then return self.sz[d] end; return torch.LongStorage(self.sz) end
+function CudaTensor:dim() return #self.sz end
+function CudaTensor:fill(v) check(lib.cenn_fill(cenn.state, self.ptr, self:nElement(), v)); return self end
+function CudaTensor:zero() return self:fill(0) end
+function CudaTensor:mul(a) check(lib.cenn_mul(cenn.state, self.ptr, self:nElement(), a)); return self end
+function CudaTensor:add(a, x) check(lib.cenn_axpy(cenn.state, self.ptr, x.ptr, self:nElement(), a)); return self end
+function CudaTensor:copy(src)                         -- from torch.FloatTensor (H2D) or another CudaTensor (D2D)
+  if getmetatable(src) == CudaTensor then check(lib.cenn_copy_d2d(cenn.state, self.ptr, src.ptr, self:nElement() * 4))
+  else src = src:contiguous(); check(lib.cenn_copy_h2d(cenn.state, self.ptr, src:data(), self:nElement() * 4)) end
+  return self
+end
+function CudaTensor:float()
+  local t = torch.FloatTensor(unpack(self.sz))
+  check(lib.cenn_copy_d2h(cenn.state, t:data(), self.ptr, self:nElement() * 4)); return t
+end
+function CudaTensor:resize(...) local sz = {...}
+  if numel(sz) ~= self:nElement() then local n = cenn.CudaTensor(sz); self.ptr, self.gc = n.ptr, n.gc end
+  self.sz = sz; return self
+end
+function CudaTensor:resizeAs(o) return self:resize(unpack(o.sz)) end
+torch.FloatTensor.cuda = function(self) return cenn.CudaTensor(self:size():totable()):copy(self) end
+
+---------------------------------------------------------------------------------------------- nn modules: THNN -> libcenn
+-- Each updateOutput / updateGradInput / accGradParameters below replaces the `input.THNN.<Op>_<phase>(...)` call of
+-- the stock Lua method (same argument meaning; THCudaTensor* becomes pointer + explicit sizes).
+require 'nn'
+local S = function() return cenn.state end
+
+local Conv = nn.SpatialConvolution
+function Conv:updateOutput(input)                   -- THNN SpatialConvolutionMM_updateOutput (train.lua:89-104,183-196)
+  local N, C, H, W = unpack(input.sz)
+  local oH = math.floor((H + 2 * self.padH - self.kH) / self.dH) + 1
+  local oW = math.floor((W + 2 * self.padW - self.kW) / self.dW) + 1
+  self.output:resize(N, self.nOutputPlane, oH, oW)
+  check(lib.cenn_SpatialConvolutionMM_updateOutput(S(), input.ptr, self.output.ptr, self.weight.ptr, self.bias and self.bias.ptr,
+        N, C, H, W, self.nOutputPlane, self.kW, self.kH, self.dW, self.dH, self.padW, self.padH))
+  return self.output
+end
+function Conv:updateGradInput(input, gradOutput)
+  local N, C, H, W = unpack(input.sz)
+  self.gradInput:resizeAs(input)
+  check(lib.cenn_SpatialConvolutionMM_updateGradInput(S(), gradOutput.ptr, self.gradInput.ptr, self.weight.ptr,
+        N, C, H, W, self.nOutputPlane, self.kW, self.kH, self.dW, self.dH, self.padW, self.padH))
+  return self.gradInput
+end
+function Conv:accGradParameters(input, gradOutput, scale)
+  local N, C, H, W = unpack(input.sz)
+  check(lib.cenn_SpatialConvolutionMM_accGradParameters(S(), input.ptr, gradOutput.ptr, self.gradWeight.ptr, self.gradBias and self.gradBias.ptr,
+        N, C, H, W, self.nOutputPlane, self.kW, self.kH, self.dW, self.dH, self.padW, self.padH, scale or 1))
+end
+
+local Full = nn.SpatialFullConvolution               -- train.lua:134-146; weight [nInputPlane][nOutputPlane][kH][kW]
+function Full:updateOutput(input)
+  local N, C, H, W = unpack(input.sz)
+  local oH = (H - 1) * self.dH - 2 * self.padH + self.kH + self.adjH
+  local oW = (W - 1) * self.dW - 2 * self.padW + self.kW + self.adjW
+  self.output:resize(N, self.nOutputPlane, oH, oW)
+  check(lib.cenn_SpatialFullConvolution_updateOutput(S(), input.ptr, self.output.ptr, self.weight.ptr, self.bias and self.bias.ptr,
+        N, C, H, W, self.nOutputPlane, self.kW, self.kH, self.dW, self.dH, self.padW, self.padH, self.adjW, self.adjH))
+  return self.output
+end
+function Full:updateGradInput(input, gradOutput)
+  local N, C, H, W = unpack(input.sz)
+  self.gradInput:resizeAs(input)
+  check(lib.cenn_SpatialFullConvolution_updateGradInput(S(), gradOutput.ptr, self.gradInput.ptr, self.weight.ptr,
+        N, C, H, W, self.nOutputPlane, self.kW, self.kH, self.dW, self.dH, self.padW, self.padH, self.adjW, self.adjH))
+  return self.gradInput
+end
+function Full:accGradParameters(input, gradOutput, scale)
+  local N, C, H, W = unpack(input.sz)
+  check(lib.cenn_SpatialFullConvolution_accGradParameters(S(), input.ptr, gradOutput.ptr, self.gradWeight.ptr, self.gradBias and self.gradBias.ptr,
+        N, C, H, W, self.nOutputPlane, self.kW, self.kH, self.dW, self.dH, self.padW, self.padH, self.adjW, self.adjH, scale or 1))
+end
+
+local BN = nn.BatchNormalization                     -- nn.SpatialBatchNormalization inherits (train.lua:79)
+function BN:updateOutput(input)
+  local N, C = input.sz[1], input.sz[2]
+  local spatial = input:nElement() / (N * C)
+  self.output:resizeAs(input); self.save_mean = self.save_mean or cenn.CudaTensor(C); self.save_std = self.save_std or cenn.CudaTensor(C)
+  check(lib.cenn_BatchNormalization_updateOutput(S(), input.ptr, self.output.ptr, self.weight and self.weight.ptr, self.bias and self.bias.ptr,
+        self.running_mean.ptr, self.running_var.ptr, self.save_mean.ptr, self.save_std.ptr, N, C, spatial, self.train and 1 or 0, self.momentum, self.eps))
+  return self.output
+end
+local function bn_backward(self, input, gradOutput, scale, gradInput, gradWeight, gradBias)
+  local N, C = input.sz[1], input.sz[2]
+  check(lib.cenn_BatchNormalization_backward(S(), input.ptr, gradOutput.ptr, gradInput and gradInput.ptr, gradWeight and gradWeight.ptr,
+        gradBias and gradBias.ptr, self.weight and self.weight.ptr, self.running_mean.ptr, self.running_var.ptr, self.save_mean.ptr,
+        self.save_std.ptr, N, C, input:nElement() / (N * C), self.train and 1 or 0, scale or 1, self.eps))
+end
+function BN:backward(input, gradOutput, scale) self.gradInput:resizeAs(input); bn_backward(self, input, gradOutput, scale, self.gradInput, self.gradWeight, self.gradBias); return self.gradInput end
+function BN:updateGradInput(input, gradOutput) self.gradInput:resizeAs(input); bn_backward(self, input, gradOutput, 1, self.gradInput); return self.gradInput end
+function BN:accGradParameters(input, gradOutput, scale) bn_backward(self, input, gradOutput, scale, nil, self.gradWeight, self.gradBias) end
+
+function nn.LeakyReLU:updateOutput(input)
+  if not self.inplace then self.output:resizeAs(input) else self.output = input end
+  check(lib.cenn_LeakyReLU_updateOutput(S(), input.ptr, self.output.ptr, input:nElement(), self.negval, self.inplace and 1 or 0)); return self.output
+end
+function nn.LeakyReLU:updateGradInput(input, gradOutput)
+  if not self.inplace then self.gradInput:resizeAs(input) else self.gradInput = gradOutput end
+  check(lib.cenn_LeakyReLU_updateGradInput(S(), input.ptr, gradOutput.ptr, self.gradInput.ptr, input:nElement(), self.negval, self.inplace and 1 or 0)); return self.gradInput
+end
+function nn.Threshold:updateOutput(input)            -- nn.ReLU = nn.Threshold(0, 0, inplace)
+  if not self.inplace then self.output:resizeAs(input) else self.output = input end
+  check(lib.cenn_Threshold_updateOutput(S(), input.ptr, self.output.ptr, input:nElement(), self.threshold, self.val, self.inplace and 1 or 0)); return self.output
+end
+function nn.Threshold:updateGradInput(input, gradOutput)
+  if not self.inplace then self.gradInput:resizeAs(input) else self.gradInput = gradOutput end
+  check(lib.cenn_Threshold_updateGradInput(S(), input.ptr, gradOutput.ptr, self.gradInput.ptr, input:nElement(), self.threshold, self.inplace and 1 or 0)); return self.gradInput
+end
+function nn.Tanh:updateOutput(input) self.output:resizeAs(input); check(lib.cenn_Tanh_updateOutput(S(), input.ptr, self.output.ptr, input:nElement())); return self.output end
+function nn.Tanh:updateGradInput(input, gradOutput) self.gradInput:resizeAs(input); check(lib.cenn_Tanh_updateGradInput(S(), gradOutput.ptr, self.gradInput.ptr, self.output.ptr, input:nElement())); return self.gradInput end
+function nn.Sigmoid:updateOutput(input) self.output:resizeAs(input); check(lib.cenn_Sigmoid_updateOutput(S(), input.ptr, self.output.ptr, input:nElement())); return self.output end
+function nn.Sigmoid:updateGradInput(input, gradOutput) self.gradInput:resizeAs(input); check(lib.cenn_Sigmoid_updateGradInput(S(), gradOutput.ptr, self.gradInput.ptr, self.output.ptr, input:nElement())); return self.gradInput end
+
+---------------------------------------------------------------------------------------------- criteria
+local loss = ffi.new('float[1]')
+function nn.BCECriterion:updateOutput(input, target)  -- returns a Lua number (the only mandatory sync, SURVEY.md 8b)
+  check(lib.cenn_BCECriterion_updateOutput(S(), input.ptr, target.ptr, input:nElement(), self.sizeAverage and 1 or 0, loss)); self.output = loss[0]; return self.output
+end
+function nn.BCECriterion:updateGradInput(input, target)
+  self.gradInput:resizeAs(input); check(lib.cenn_BCECriterion_updateGradInput(S(), input.ptr, target.ptr, self.gradInput.ptr, input:nElement(), self.sizeAverage and 1 or 0)); return self.gradInput
+end
+function nn.MSECriterion:updateOutput(input, target)
+  check(lib.cenn_MSECriterion_updateOutput(S(), input.ptr, target.ptr, input:nElement(), self.sizeAverage and 1 or 0, loss)); self.output = loss[0]; return self.output
+end
+function nn.MSECriterion:updateGradInput(input, target)
+  self.gradInput:resizeAs(input); check(lib.cenn_MSECriterion_updateGradInput(S(), input.ptr, target.ptr, self.gradInput.ptr, input:nElement(), self.sizeAverage and 1 or 0)); return self.gradInput
+end
+
+-- repo-local criteria (MaskedMSECriterion.lua:4-42, gdl_criterion.lua:4-53): one fused kernel each instead of an nngraph
+local MaskedMSE, mparent = torch.class('nn.MaskedMSECriterion', 'nn.Criterion')
+function MaskedMSE:__init(mWeight) mparent.__init(self); assert(mWeight, 'mWeight required (MaskedMSECriterion.lua:15)'); self.mWeight = mWeight; self.gradInput = cenn.CudaTensor(1) end
+function MaskedMSE:setMask(m) assert(torch.type(m) == 'torch.ByteTensor'); self.mask = m:float():cuda() end   -- MaskedMSECriterion.lua:24-27
+function MaskedMSE:updateOutput(input, target)
+  self.gradInput:resizeAs(input)
+  check(lib.cenn_MaskedMSECriterion_forward_backward(S(), input.ptr, target.ptr, self.mask.ptr, self.gradInput.ptr, input:nElement(), self.mWeight, loss)); self.output = loss[0]; return self.output
+end
+function MaskedMSE:updateGradInput() return self.gradInput end
+local GDL, gparent = torch.class('nn.GDLCriterion', 'nn.Criterion')
+function GDL:__init(alpha) gparent.__init(self); assert((alpha or 1) == 1, 'alpha must be 1 (gdl_criterion.lua:9)'); self.gradInput = cenn.CudaTensor(1) end
+function GDL:updateOutput(input, target)
+  local N, C, H, W = unpack(input.sz); self.gradInput:resizeAs(input)
+  check(lib.cenn_GDLCriterion_forward_backward(S(), input.ptr, target.ptr, self.gradInput.ptr, N, C, H, W, loss)); self.output = loss[0]; return self.output
+end
+function GDL:updateGradInput() return self.gradInput end
+
+package.loaded['cunn'] = cenn                         -- `require 'cunn'` (train.lua:249) resolves to this module
+return cenn
