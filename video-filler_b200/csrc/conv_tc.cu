@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include "tc_gemm.cuh"
 
 namespace {
@@ -62,6 +63,13 @@ int map_2d(CUtensorMap *m, const bf16 *B, uint64_t K, uint64_t rows, int box_row
     return make_map(m, B, 2, dims, st, box);
 }
 
+int map_bmn(CUtensorMap *m, const bf16 *B, uint64_t Ncols, uint64_t Krows) {
+    uint64_t dims[2] = {Ncols, Krows};
+    uint64_t st[1] = {Ncols * 2};
+    uint32_t box[2] = {64, 64};
+    return make_map(m, B, 2, dims, st, box);
+}
+const int UPH[2][2] = {{1, 3}, {0, 2}};   // dgrad sub-pixel phase p, tap index a -> window row/column u
 int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
 int pow2_le(int v, int cap) { int p = 1; while (p * 2 <= v && p * 2 <= cap) p *= 2; return p; }
 // split `total` pixels per tile over (w, h, n)
@@ -89,7 +97,7 @@ int set_attr_wgrad() {
 int config_gather(cenn_state *s, TcPlan *pl, int BN, int num_kb, int total_tiles) {
     const int stage_bytes = 128 * 128 + BN * 128;
     const int out_bytes = BN >= 64 ? 128 * BN * 2 : 0;
-    const int fixed = 1024 /*align*/ + out_bytes + 176 /*barriers, tmem slot*/ + 68 * 16 /*tap tables*/ + 3 * BN * 4 + (BN == 32 ? 4 * 32 * 33 * 4 : 0) + 64;
+    const int fixed = 1024 /*align*/ + out_bytes + 176 /*barriers, tmem slot*/ + 68 * 16 + 256 /*tap tables*/ + 3 * BN * 4 + (BN == 32 ? 4 * 32 * 33 * 4 : 0) + 64;
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -113,6 +121,7 @@ int config_wgrad(TcPlan *pl, int BN, int nkb, dim3 grid) {
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages > nkb) stages = nkb;
+    if (nkb <= 4 && stages > 2) stages = 2;   // short K (E6 / G1: 256 samples): two co-resident CTAs per SM overlap epilogue and main loop
     if (stages < 1) stages = 1;
     pl->kind = 2; pl->BN = BN; pl->stages = stages;
     pl->smem = (size_t)stages * stage_bytes + fixed;
@@ -342,10 +351,12 @@ int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, b
     int BN = pick_bn(Cl, m_tiles * 4, s->sm_count);
     if (Clp % 64 != 0) BN = 32;                     // a 64-column slab would spill into the neighbouring sub-pixel: direct-store path
     REQUIRE(cl_rows >= Cl, "tc_dgrad_s2: cl_rows (%d) too small for Cl %d", cl_rows, Cl);
-    if (map_2d(planB(pl), Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
+    const bool b_mn = ep.b_mn && BN >= 64;
+    REQUIRE(!ep.b_mn || b_mn, "tc_dgrad_s2: MN-major weights need an N tile of 64 or more (Clp %d)", Clp);
+    if (b_mn ? map_bmn(planB(pl), Wt, (uint64_t)16 * Clp, (uint64_t)Csp) : map_2d(planB(pl), Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
     memset(pl->tmO, 0, sizeof(pl->tmO));
     if (BN >= 64 && map_gather(planO(pl), L, N, 2 * h, 2 * w, Clp, bw, bh, bn)) return 1;
-    p.o_cols = Clp; p.num_taps = 4;
+    p.o_cols = Clp; p.num_taps = 4; p.b_mn = b_mn ? 1 : 0;
     for (int ph = 0; ph < 4; ++ph) { p.O0[ph] = (ph & 1) * Clp; p.O2[ph] = ph >> 1; }
     int chunks = Csp / 64;
     for (int ph = 0; ph < 4; ++ph) {
@@ -353,6 +364,7 @@ int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, b
         for (int ab = 0; ab < 4; ++ab) {
             int a = ab >> 1, b = ab & 1;
             p.A0[ph][ab] = 0; p.A1[ph][ab] = DYP[px][b]; p.A2[ph][ab] = 0; p.A3[ph][ab] = DYP[py][a];
+            p.Bc[ph][ab] = (UPH[py][a] * 4 + UPH[px][b]) * Clp;
         }
         p.B1[ph] = ph * cl_rows;
     }
@@ -387,7 +399,9 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
         uint32_t bx[4] = {64, 10, (uint32_t)bn, (uint32_t)bh + 2};
         if (make_map(planA(pl), S, 4, d, st, bx)) return 1;
     }
-    if (map_2d(planB(pl), Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
+    const bool b_mn = ep.b_mn && BN >= 64;
+    REQUIRE(!ep.b_mn || b_mn, "tc_dgrad_patch: MN-major weights need an N tile of 64 or more (Clp %d)", Clp);
+    if (b_mn ? map_bmn(planB(pl), Wt, (uint64_t)16 * Clp, (uint64_t)Csp) : map_2d(planB(pl), Wt, (uint64_t)4 * Csp, (uint64_t)4 * cl_rows, BN)) return 1;
     memset(pl->tmO, 0, sizeof(pl->tmO));
     const int H2 = 2 * h, W2 = 2 * w;
     if (BN >= 64) {   // output: dims (px*Clp + c, x', n, y', py)
@@ -408,7 +422,9 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
         for (int ab = 0; ab < 4; ++ab) {
             const int dy = DYP[ph >> 1][ab >> 1], dx = DYP[ph & 1][ab & 1];
             p.a_off[ph][ab] = (((1 + dy) * bn) * 10 + (1 + dx)) * 128;
+            p.b_col[ph][ab] = (UPH[ph >> 1][ab >> 1] * 4 + UPH[ph & 1][ab & 1]) * Clp;
         }
+    p.b_mn = b_mn ? 1 : 0;
     p.Csp = Csp; p.cl_rows = cl_rows;
     p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cl; p.Clp = Clp; p.H2 = H2; p.W2 = W2;
     p.out = ep.no_bf16 ? nullptr : L;
@@ -447,7 +463,9 @@ int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *
     int m_tiles = p.tiles_x;
     int BN = pick_bn(Nc, m_tiles, s->sm_count);
     if (ldo < 64 || ldo % 8 != 0) BN = 32;
-    if (map_2d(planB(pl), B, (uint64_t)K, (uint64_t)Nc, BN)) return 1;
+    const bool b_mn = ep.b_mn && BN >= 64;     // B given as [K][Nc] (row stride Nc)
+    REQUIRE(!ep.b_mn || b_mn, "tc_gemm: MN-major B needs an N tile of 64 or more");
+    if (b_mn ? map_bmn(planB(pl), B, (uint64_t)Nc, (uint64_t)K) : map_2d(planB(pl), B, (uint64_t)K, (uint64_t)Nc, BN)) return 1;
     memset(pl->tmO, 0, sizeof(pl->tmO));
     if (BN >= 64) {
         uint64_t od[5] = {(uint64_t)ldo, (uint64_t)M, 1, 1, 1};
@@ -455,7 +473,7 @@ int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *
         uint32_t ob[5] = {64, 128, 1, 1, 1};
         if (make_map(planO(pl), out, 5, od, os, ob)) return 1;
     }
-    p.o_cols = ldo; p.num_taps = 1;
+    p.o_cols = ldo; p.num_taps = 1; p.b_mn = b_mn ? 1 : 0;
     int nkb = (K + 63) / 64;
     p.chunks = nkb; p.bk_per_tap = 0; p.num_kb = nkb;          // a single "tap" whose chunks walk K
     p.m_tiles = m_tiles; p.n_tiles = (Nc + BN - 1) / BN; p.num_phases = 1;
@@ -475,10 +493,15 @@ static int wgrad_common(cenn_state *s, TcPlan *pl, tc::WgradParams &p, int num_t
     int BN = Cs > 128 ? 256 : (Cs > 64 ? 128 : 64);
     int n_tiles = (Cs + BN - 1) / BN;
     int tiles = m_tiles * n_tiles;
-    int splits = (2 * s->sm_count + tiles - 1) / tiles;
-    int max_splits = (num_kb_total + 3) / 4;            // at least 4 k-blocks (256 pixels) per split
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    // split K (pixels) over CTAs: minimise waves x (k-blocks per CTA + fixed per-CTA cost), one CTA per SM at a time
+    const int max_splits = std::max(1, (num_kb_total + 3) / 4);            // at least 4 k-blocks (256 pixels) per split
+    const int fixed_kb = 10;                                               // prologue + epilogue of a CTA, in k-block units
+    int splits = 1; long long best = -1;
+    for (int sp = 1; sp <= max_splits && sp <= 4 * s->sm_count; ++sp) {
+        const long long waves = ((long long)tiles * sp + s->sm_count - 1) / s->sm_count;
+        const long long cost = waves * ((num_kb_total + sp - 1) / sp + fixed_kb);
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
     if (p.accumulate == 2) p.accumulate = splits == 1 ? 0 : 1;
     if (!p.accumulate) splits = 1;
     pl->overwrites = p.accumulate ? 0 : 1;

@@ -21,6 +21,8 @@ struct TcEpilogue {
     bool no_bf16 = false;
     void *dbg = nullptr;           // optional per-role cycle counters (debug probe)
     int dbg_flags = 0;             // probe only, see tc::GatherGemmParams::dbg_flags
+    bool b_mn = false;             // dgrad-type / plain GEMM: the weight operand is the MASTER layout Wf [Cs][16*Clp] (or [K][Nc], row stride
+                                   // = Nc) read MN-major, instead of a transposed K-major copy (N tile >= 64 only)
 };
 
 // A prepared launch: tensor maps, kernel parameters, k-block table and grid are built once (shapes and

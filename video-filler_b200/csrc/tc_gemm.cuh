@@ -176,6 +176,8 @@ struct GatherGemmParams {
     int num_kb, chunks, bk_per_tap, num_taps;
     int A0[4][16], A1[4][16], A2[4][16], A3[4][16];
     int B1[4];
+    int b_mn;                // 1: B is read MN-major straight from the master layout Wf [K rows][N cols] (no transposed copy):
+    int Bc[4][16];           //    box (64 n, 64 k) at column Bc[ph][tap] + n_tile*BN + 64*chunk, row 64*c
     int O0[4], O2[4];
     int o_cols;              // columns of one phase in the output map's dim 0 (slabs starting at or beyond it are not stored)
     int m_tiles, n_tiles, num_phases;   // tiles are enumerated m fastest, then n, then phase
@@ -275,7 +277,8 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);            // +160 B
     int4 *tapc = reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(full_bar) + 176);   // [4][16] A-box coordinates per (phase, tap)
     int4 *phc = tapc + 64;                                                         // [4] (B1, O0, O2, -) per phase
-    float *col_acc = reinterpret_cast<float *>(phc + 4);                           // [2][BN] per-CTA column sums for BN statistics
+    int *bcs = reinterpret_cast<int *>(phc + 4);                                   // [4][16] B column offsets (MN-major B)
+    float *col_acc = reinterpret_cast<float *>(bcs + 64);                           // [2][BN] per-CTA column sums for BN statistics
     float *bias_s = col_acc + 2 * BN;                                              // [BN] bias of the current n-tile
     float *stage_f = bias_s + BN;                                                  // BN == 32 only: [4 warps][32][33] transposition buffer
 
@@ -296,6 +299,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int ph = threadIdx.x >> 4, tp = threadIdx.x & 15;
         tapc[threadIdx.x] = make_int4(p.A0[ph][tp], p.A1[ph][tp], p.A2[ph][tp], p.A3[ph][tp]);
         if (tp == 0) phc[ph] = make_int4(p.B1[ph], p.O0[ph], p.O2[ph], 0);
+        bcs[threadIdx.x] = p.Bc[ph][tp];
     }
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) col_acc[i] = 0.f;
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -309,6 +313,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int s = 0; uint32_t ph = 0;
             long long w_empty = 0, t_begin = prof ? clock64() : 0;
             const int chunks = p.chunks, num_taps = p.num_taps, bk_per_tap = p.bk_per_tap;
+            const bool b_mn = p.b_mn != 0;
             const int flags = kProbe ? p.dbg_flags : 0;
             const uint32_t tiles_u32 = smem_u32(tiles), full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -328,6 +333,12 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             if (bytes) mbar_expect_tx_u32(fb, bytes); else mbar_arrive(&full_bar[s]);
                             if (!(flags & 2)) tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ax, c4.z, ay, tc.n0);
                             if (!(flags & 4)) tma_load_2d_u32(&tmB, fb, b_dst, bk + c * 64, brow);
+                        } else if (b_mn) {
+                            mbar_expect_tx_u32(fb, STAGE_BYTES);
+                            tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ax, c4.z, ay, tc.n0);
+                            const int bcol = bcs[tc.phase * 16 + tap] + tc.nt * BN;
+#pragma unroll
+                            for (int ch = 0; ch < (BN >= 64 ? BN / 64 : 1); ++ch) tma_load_2d_u32(&tmB, fb, b_dst + ch * 8192, bcol + ch * 64, c * 64);
                         } else {
                             mbar_expect_tx_u32(fb, STAGE_BYTES);
                             tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ax, c4.z, ay, tc.n0);
@@ -341,10 +352,14 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else if (warp == 1) {
         {   // warp-uniform loop: every lane waits on the barriers, one elected lane issues the MMAs and commits
-            const uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, 0);
+            const bool b_mn = p.b_mn != 0;
+            const uint32_t idesc = make_idesc(128, BN < 16 ? 16 : BN, 0, b_mn ? 1 : 0);
             // descriptor words: lo = start address (16-B units) | LBO << 16 ; hi = SBO (1024 B) | version 1 | SWIZZLE_128B
+            // MN-major B: 64-column chunks of [64 k][128 B], LBO = chunk stride (8 KB), 16 k-rows (one MMA) = 2048 B
             const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t a_lo0 = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lbo_fix = b_mn ? (((8192u >> 4) - 1u) << 16) : 0u;      // replaces LBO = 1 by LBO = 512
+            const uint32_t b_kstep = b_mn ? 128u : 2u;
             const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar), tfull_u32 = smem_u32(tfull_bar), tempty_u32 = smem_u32(tempty_bar);
             const int num_kb = p.num_kb;
             const int flags = kProbe ? p.dbg_flags : 0;
@@ -362,12 +377,12 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     mbar_wait_u32(full_u32 + 8u * s, ph);
                     if (prof) w_full += clock64() - t0;
                     tc_fence_after();
-                    const uint32_t a_lo = a_lo0 + (uint32_t)s * (STAGE_BYTES >> 4), b_lo = a_lo + (A_BYTES >> 4);
+                    const uint32_t a_lo = a_lo0 + (uint32_t)s * (STAGE_BYTES >> 4), b_lo = a_lo + (A_BYTES >> 4) + b_lbo_fix;
                     if (elect_one()) {
                         if (!(kProbe && (flags & 1))) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide k-block; +32 B inside the swizzle atom
-                                const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), bd = ((uint64_t)desc_hi << 32) | (b_lo + 2u * k);
+                                const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + 2u * k), bd = ((uint64_t)desc_hi << 32) | (b_lo + b_kstep * k);
                                 umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
                             }
                         }
@@ -619,7 +634,9 @@ struct PatchDgradParams {
     int patch_bytes;             // TMA box bytes: 128 * 10 * bn * (bh + 2)
     int patch_stride;            // patch_bytes rounded up to 1024
     int a_off[4][4];             // byte offset of window (phase, tap ab) inside the patch
-    int Csp, cl_rows;            // B coordinates: column ab*Csp + 64*c, row ph*cl_rows + nt*BN
+    int Csp, cl_rows;            // B coordinates (K-major Wt): column ab*Csp + 64*c, row ph*cl_rows + nt*BN
+    int b_mn;                    // 1: B taps are read MN-major from Wf [Cs rows][16*Clp cols]: column b_col[ph][ab] + nt*BN + 64*chunk, row 64*c
+    int b_col[4][4];
     int out_w, out_h, out_n;     // extent of the S pixel grid
     int n_valid, Clp;            // valid / padded output channels of one phase
     int H2, W2;                  // output image size (direct-store path)
@@ -674,6 +691,7 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
             const uint32_t patch_u32 = smem_u32(patch), bst_u32 = smem_u32(bst);
             const uint32_t pfull_u32 = smem_u32(pfull), pempty_u32 = smem_u32(pempty), bfull_u32 = smem_u32(bfull), bempty_u32 = smem_u32(bempty);
             const int chunks = p.chunks, Csp = p.Csp, cl_rows = p.cl_rows;
+            const bool b_mn = p.b_mn != 0;
             int pb = 0; uint32_t pph = 0; int s = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
@@ -684,20 +702,31 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
                     mbar_expect_tx_u32(pfull_u32 + 8u * pb, (uint32_t)p.patch_bytes);
                     tma_load_4d_u32(&tmS, pfull_u32 + 8u * pb, patch_u32 + (uint32_t)pb * (uint32_t)p.patch_stride, c * 64, x0 - 1, n0, y0 - 1);
                     if (++pb == 2) { pb = 0; pph ^= 1u; }
+#pragma unroll
                     for (int phs = 0; phs < 4; ++phs) {
                         mbar_wait_u32(bempty_u32 + 8u * s, ph ^ 1u);
                         const uint32_t fb = bfull_u32 + 8u * s, dst = bst_u32 + (uint32_t)s * BSTAGE_BYTES;
                         mbar_expect_tx_u32(fb, BSTAGE_BYTES);
                         const int brow = phs * cl_rows + nt * BN;
+                        if (b_mn) {
 #pragma unroll
-                        for (int ab = 0; ab < 4; ++ab) tma_load_2d_u32(&tmB, fb, dst + ab * BTAP_BYTES, ab * Csp + c * 64, brow);
+                            for (int ab = 0; ab < 4; ++ab)
+#pragma unroll
+                                for (int ch = 0; ch < (BN >= 64 ? BN / 64 : 1); ++ch)
+                                    tma_load_2d_u32(&tmB, fb, dst + ab * BTAP_BYTES + ch * 8192, p.b_col[phs][ab] + nt * BN + ch * 64, c * 64);
+                        } else {
+#pragma unroll
+                            for (int ab = 0; ab < 4; ++ab) tma_load_2d_u32(&tmB, fb, dst + ab * BTAP_BYTES, ab * Csp + c * 64, brow);
+                        }
                         if (++s == stages) { s = 0; ph ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = make_idesc(128, BN, 0, 0);
+        const bool b_mn = p.b_mn != 0;
+        const uint32_t idesc = make_idesc(128, BN, 0, b_mn ? 1 : 0);
+        const uint32_t b_lbo_fix = b_mn ? (((8192u >> 4) - 1u) << 16) : 0u, b_kstep = b_mn ? 128u : 2u;
         const uint32_t hiA = (1280u >> 4) | (1u << 14) | (2u << 29);          // group stride = one patch row of 10 pixels
         const uint32_t hiB = (1024u >> 4) | (1u << 14) | (2u << 29);
         const uint32_t patch_lo = ((smem_u32(patch) & 0x3FFFFu) >> 4) | (1u << 16), bst_lo = ((smem_u32(bst) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -722,13 +751,13 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)((set * 4 + phs) * BN);
-                        const uint32_t b_base = bst_lo + (uint32_t)s * (BSTAGE_BYTES >> 4);
+                        const uint32_t b_base = bst_lo + (uint32_t)s * (BSTAGE_BYTES >> 4) + b_lbo_fix;
 #pragma unroll
                         for (int ab = 0; ab < 4; ++ab)
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t ad = ((uint64_t)hiA << 32) | (a_base + aoff[phs][ab] + 2u * k);
-                                const uint64_t bd = ((uint64_t)hiB << 32) | (b_base + (uint32_t)ab * (BTAP_BYTES >> 4) + 2u * k);
+                                const uint64_t bd = ((uint64_t)hiB << 32) | (b_base + (uint32_t)ab * (BTAP_BYTES >> 4) + b_kstep * k);
                                 umma_f16(d_tmem, ad, bd, idesc, (c | ab | k) != 0);
                             }
                         umma_commit_u32(bempty_u32 + 8u * s);

@@ -332,10 +332,15 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                 if (b.has_dgrad) {
                     REQUIRE(b.Csp % 64 == 0, "block %zu: dgrad needs small-side channels padded to 64 (got %d)", i, b.Csp);
                     b.cl_rows = b.Clp;
-                    b.Wt = dalloc<bf16>(t, (int64_t)16 * b.cl_rows * b.Csp);
-                    if (!b.Wt) return 1;
                     if (!dgrad_out) { dgrad_out = dalloc<bf16>(t, b.in.elems()); if (!dgrad_out) return 1; if (&net == &t->D) { t->df_dg = b.in; t->df_dg.p = dgrad_out; } }
-                    if (tc_plan_dgrad_s2(s, &b.p_dgrad, b.g.p, b.Wt, dgrad_out, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_n)) return 1;
+                    if (b.Clp % 64 == 0) {           // weights read MN-major straight from the master copy: no transposed operand
+                        TcEpilogue ep_m = ep_n; ep_m.b_mn = true;
+                        if (tc_plan_dgrad_s2(s, &b.p_dgrad, b.g.p, Wf, dgrad_out, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_m)) return 1;
+                    } else {
+                        b.Wt = dalloc<bf16>(t, (int64_t)16 * b.cl_rows * b.Csp);
+                        if (!b.Wt) return 1;
+                        if (tc_plan_dgrad_s2(s, &b.p_dgrad, b.g.p, b.Wt, dgrad_out, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_n)) return 1;
+                    }
                 }
                 break;
             }
@@ -343,25 +348,28 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                 int K = 16 * b.Clp;
                 if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, b.Cs, K, b.Csp, ep_f)) return 1;
                 if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.in.p, gW, N, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
-                b.Wt = dalloc<bf16>(t, (int64_t)K * b.Csp);
-                if (!b.Wt) return 1;
-                if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, b.Wt, dgrad_out, N, K, b.Csp, K, ep_n)) return 1;
+                { TcEpilogue ep_m = ep_n; ep_m.b_mn = true;     // dgrad = g [N,Cs] x Wf [Cs][K]
+                  if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, dgrad_out, N, K, b.Csp, K, ep_m)) return 1; }
                 break;
             }
             case FULL_V4: {
                 int K = 16 * b.Clp;
-                b.Wt = dalloc<bf16>(t, (int64_t)K * b.Csp);
-                if (!b.Wt) return 1;
-                if (tc_plan_gemm(s, &b.p_fwd, b.in.p, b.Wt, fwd_out, N, K, b.Csp, K, ep_f)) return 1;
+                { TcEpilogue ep_m = ep_f; ep_m.b_mn = true;     // G1 = in [N,Cs] x Wf [Cs][K]
+                  if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, K, b.Csp, K, ep_m)) return 1; }
                 if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.in.p, b.g.p, gW, N, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
                 if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, dgrad_out, N, b.Cs, K, b.Csp, ep_n)) return 1;
                 break;
             }
             case FULL_S2: {
                 b.cl_rows = b.Clp;
-                b.Wt = dalloc<bf16>(t, (int64_t)16 * b.cl_rows * b.Csp);
-                if (!b.Wt) return 1;
-                if (tc_plan_dgrad_s2(s, &b.p_fwd, b.in.p, b.Wt, fwd_out, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_f)) return 1;
+                if (b.Clp % 64 == 0) {
+                    TcEpilogue ep_m = ep_f; ep_m.b_mn = true;
+                    if (tc_plan_dgrad_s2(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_m)) return 1;
+                } else {
+                    b.Wt = dalloc<bf16>(t, (int64_t)16 * b.cl_rows * b.Csp);
+                    if (!b.Wt) return 1;
+                    if (tc_plan_dgrad_s2(s, &b.p_fwd, b.in.p, b.Wt, fwd_out, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_f)) return 1;
+                }
                 if (b.thin) {
                     if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.in.p, b.col, gW, M, b.Cs, b.Csp, (int)b.col_k, 1.f, 1)) return 1;
                     if (tc_plan_gemm(s, &b.p_dgrad, b.col, Wf, dgrad_out, M, b.Cs, (int)b.col_k, b.Csp, ep_n)) return 1;
