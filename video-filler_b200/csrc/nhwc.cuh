@@ -420,22 +420,35 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
         reinterpret_cast<uint4 *>(gx)[i] = pack8(f);
     }
 }
-// gw[k] += sum_b gpre[b] x[b,k] ; gb += sum_b gpre[b]   (grid over k-vectors, loop over b)
+// gw[k] += sum_b gpre[b] x[b,k] ; gb += sum_b gpre[b]   (grid.x over k-vectors, grid.y over batch slices; fp32 atomics)
 __global__ void __launch_bounds__(128) head_wgrad_kernel(const float *__restrict__ gpre, const bf16 *__restrict__ x, float *__restrict__ gw,
         float *__restrict__ gb, int B, int K) {
-    int kv = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kv = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = (B + gridDim.y - 1) / gridDim.y, b0 = blockIdx.y * per, b1 = min(B, b0 + per);
     if (kv < K / 8) {
         float acc[8] = {};
-        for (int b = 0; b < B; ++b) {
-            float f[8], g = gpre[b];
-            unpack8(reinterpret_cast<const uint4 *>(x + (int64_t)b * K)[kv], f);
+        int b = b0;
+        for (; b + 4 <= b1; b += 4) {             // 4 independent 16-byte loads in flight
+            uint4 r[4]; float g[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, f[j], acc[j]);
+            for (int u = 0; u < 4; ++u) { r[u] = __ldg(reinterpret_cast<const uint4 *>(x + (int64_t)(b + u) * K) + kv); g[u] = gpre[b + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { float f[8]; unpack8(r[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[u], f[j], acc[j]); }
         }
+        for (; b < b1; ++b) { float f[8], g = gpre[b]; unpack8(reinterpret_cast<const uint4 *>(x + (int64_t)b * K)[kv], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gw[kv * 8 + j] += acc[j];
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, f[j], acc[j]); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(gw + kv * 8 + j, acc[j]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && gb) { float s = 0.f; for (int b = 0; b < B; ++b) s += gpre[b]; gb[0] += s; }
+    if (blockIdx.x == 0 && gb && threadIdx.x < 32) {
+        float sacc = 0.f;
+        for (int b = b0 + threadIdx.x; b < b1; b += 32) sacc += gpre[b];
+        sacc = warp_sum(sacc);
+        if (threadIdx.x == 0) atomicAdd(gb, sacc);
+    }
 }
 
 // ---------------------------------------------------------------- generator losses on NHWC tensors (Cp lanes, C valid)

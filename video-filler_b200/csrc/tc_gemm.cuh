@@ -1030,8 +1030,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
         float *obase = p.out + (long long)tap * p.cl_stride + cl;
         mbar_wait(acc_bar, 0);
         tc_fence_after();
+        // column chunks are visited in an order rotated by the CTA index: neighbouring CTAs (same cs rows, adjacent 512-byte
+        // row segments, 32 KB apart per cs) would otherwise walk the same address pattern in lock step
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int ci = 0; ci < BN; ci += 32) {
+            const int c0 = (ci + 32 * (int)(blockIdx.x + blockIdx.z)) % BN;
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             tmem_ld_wait();

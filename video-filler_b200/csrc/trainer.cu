@@ -469,7 +469,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         Tensor in = b->in;
         bf16 *gx = net.blocks[i - 1].g.p;
         if (want_params) emit(t, "head_wgrad", [s, b, in, grad, B, K]() {
-            nhwc::head_wgrad_kernel<<<(K / 8 + 127) / 128, 128, 0, s->stream>>>(b->gpre, in.p, grad + b->w_off, grad + b->b_off, B, K); KLAUNCH(s); return 0; });
+            nhwc::head_wgrad_kernel<<<dim3((K / 8 + 127) / 128, 16), 128, 0, s->stream>>>(b->gpre, in.p, grad + b->w_off, grad + b->b_off, B, K); KLAUNCH(s); return 0; });
         emit(t, "head_dgrad", [s, b, w, gx, B, K]() {
             nhwc::head_dgrad_kernel<<<grid1d(s, (int64_t)B * K / 8), 256, 0, s->stream>>>(b->gpre, w, gx, B, K); KLAUNCH(s); return 0; });
         return;
