@@ -154,6 +154,16 @@ def main():
 
     B = args.batch
     opt = opt_for(B)
+    if world > 1:
+        # library-owned NCCL communicator: rank 0 creates the id, torch.distributed carries it to the other ranks
+        idbuf = np.zeros(128, np.uint8)
+        if rank == 0:
+            api.cenn_dist_unique_id(idbuf.ctypes.data_as(C.c_void_p))
+        idt = torch.from_numpy(idbuf).cuda()
+        dist.broadcast(idt, src=0)
+        idbuf = idt.cpu().numpy()
+        api.cenn_dist_init(st, idbuf.ctypes.data_as(C.c_void_p), world, rank)
+
     trn = train.FusedTrainer(opt, precision="bf16", world_size=world, rank=rank)
     # identical random-init weights on every rank (parameter broadcast = same seed), train.lua:58-67
     rng = np.random.default_rng(1234)
@@ -174,16 +184,6 @@ def main():
         hb = np.ctypeslib.as_array((C.c_float * center.size).from_address(pb.value)); hb[:] = center.ravel()
         da, db = T.CudaTensor.from_numpy(ctx), T.CudaTensor.from_numpy(center)
         host.append((ha, hb, da, db, ctx.nbytes + center.nbytes))
-
-    if world > 1:
-        # library-owned NCCL communicator: rank 0 creates the id, torch.distributed carries it to the other ranks
-        idbuf = np.zeros(128, np.uint8)
-        if rank == 0:
-            api.cenn_dist_unique_id(idbuf.ctypes.data_as(C.c_void_p))
-        idt = torch.from_numpy(idbuf).cuda()
-        dist.broadcast(idt, src=0)
-        idbuf = idt.cpu().numpy()
-        api.cenn_dist_init(st, idbuf.ctypes.data_as(C.c_void_p), world, rank)
 
     def step_device(i):
         # world > 1: the executor all-reduces BN statistics, gradients and losses itself (NCCL, inside its CUDA graph)

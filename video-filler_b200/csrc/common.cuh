@@ -8,6 +8,17 @@
 #include <vector>
 #include "../../include/cenn.h"
 
+// One-shot all-reduce over NVLink peer memory (dist.cu / nhwc.cuh xr_sum_inplace): every rank owns a mailbox
+// [2 parities][XR_MAXF floats] + [2] epoch flags; peers' mailboxes are mapped with CUDA IPC.
+static const int XR_MAXF = 16384;       // floats per exchange (2 x 8192 statistics columns)
+static const int XR_MAX_WORLD = 16;
+struct XrCtx {
+    float *data[XR_MAX_WORLD];                  // data[r]: rank r's mailbox payload (data[rank] is local memory)
+    unsigned long long *flags[XR_MAX_WORLD];    // flags[r][parity]: last epoch rank r has published
+    unsigned long long *epoch;                  // this rank's exchange counter (device memory)
+    int world, rank;
+};
+
 struct cenn_state {
     int device = 0;
     int precision = CENN_FP32;
@@ -23,9 +34,13 @@ struct cenn_state {
     void *ws2 = nullptr;
     size_t ws2_bytes = 0;
     // data parallelism (dist.cu): NCCL communicator of this process's GPU
-    void *comm = nullptr;
+    void *comm = nullptr;                 // latency-critical small reductions, on the compute stream
+    void *comm2 = nullptr;                // bulk gradient buckets, on comm_stream
     int world = 1, rank = 0;
     cudaStream_t comm_stream = nullptr;   // gradient all-reduces overlapped with the backward sweep
+    bool xr_enabled = false;              // peer mailboxes mapped: BN statistics are exchanged inside the finalize kernels
+    XrCtx xr = {};
+    void *xr_own = nullptr;
 };
 static const int RED_SLOTS = 64;
 
@@ -34,6 +49,7 @@ int cenn_check_cuda(cudaError_t e, const char *what, const char *file, int line)
 void *cenn_workspace(cenn_state *s, size_t bytes);   // stream-ordered reuse; grows with cudaMalloc
 void *cenn_workspace2(cenn_state *s, size_t bytes);
 int cenn_dist_all_reduce_on(cenn_state *s, void *buf, int64_t count, int is_double, cudaStream_t stream);
+int cenn_dist_all_reduce_bulk(cenn_state *s, float *buf, int64_t count);   // second communicator, s->comm_stream
 
 #define CK(expr) do { if (cenn_check_cuda((expr), #expr, __FILE__, __LINE__)) return 1; } while (0)
 #define CK_LAUNCH(s) do { (s)->launches++; if (cenn_check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)) return 1; } while (0)

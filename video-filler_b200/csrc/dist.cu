@@ -5,7 +5,9 @@
 // NCCL is resolved at run time (dlopen of libnccl.so.2: the copy PyTorch already loaded, else the system one), so the
 // library has no link-time dependency and single-GPU users never touch it.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -15,12 +17,13 @@ typedef int (*fn_get_id)(NcclUniqueId *);
 typedef int (*fn_init_rank)(NcclComm *, int, NcclUniqueId, int);
 typedef int (*fn_all_reduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*fn_broadcast)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_all_gather)(const void *, void *, size_t, int, NcclComm, cudaStream_t);
 typedef int (*fn_destroy)(NcclComm);
 typedef const char *(*fn_errstr)(int);
 typedef int (*fn_group)(void);
 struct NcclApi {
     void *handle = nullptr;
-    fn_get_id get_id = nullptr; fn_init_rank init_rank = nullptr; fn_all_reduce all_reduce = nullptr; fn_broadcast broadcast = nullptr;
+    fn_get_id get_id = nullptr; fn_init_rank init_rank = nullptr; fn_all_reduce all_reduce = nullptr; fn_broadcast broadcast = nullptr; fn_all_gather all_gather = nullptr;
     fn_destroy destroy = nullptr; fn_errstr errstr = nullptr; fn_group group_start = nullptr, group_end = nullptr;
 } g_nccl;
 enum { NCCL_SUM = 0, NCCL_UINT8 = 1, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };
@@ -35,6 +38,7 @@ int load_nccl() {
     g_nccl.init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
     g_nccl.all_reduce = (fn_all_reduce)dlsym(h, "ncclAllReduce");
     g_nccl.broadcast = (fn_broadcast)dlsym(h, "ncclBroadcast");
+    g_nccl.all_gather = (fn_all_gather)dlsym(h, "ncclAllGather");
     g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
     g_nccl.group_start = (fn_group)dlsym(h, "ncclGroupStart");
@@ -58,6 +62,12 @@ int cenn_dist_all_reduce_on(cenn_state *s, void *buf, int64_t count, int is_doub
     return nccl_check(g_nccl.all_reduce(buf, buf, (size_t)count, is_double ? NCCL_FLOAT64 : NCCL_FLOAT32, NCCL_SUM, s->comm, stream), "ncclAllReduce");
 }
 
+int cenn_dist_all_reduce_bulk(cenn_state *s, float *buf, int64_t count) {
+    if (!s->comm2 || !s->comm_stream) { cenn_set_error("cenn_dist_all_reduce_bulk: no bulk communicator"); return 1; }
+    if (count <= 0) return 0;
+    return nccl_check(g_nccl.all_reduce(buf, buf, (size_t)count, NCCL_FLOAT32, NCCL_SUM, s->comm2, s->comm_stream), "ncclAllReduce (bulk)");
+}
+
 extern "C" {
 
 int cenn_dist_unique_id(void *id128_host) {
@@ -79,6 +89,60 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
     NcclComm comm = nullptr;
     if (nccl_check(g_nccl.init_rank(&comm, world_size, id, rank), "ncclCommInitRank")) return 1;
     s->comm = comm; s->world = world_size; s->rank = rank;
+    // second communicator for the gradient buckets (its own channels: a 285 MB all-reduce must not queue in front of the
+    // BN-statistics reductions): rank 0 draws another id and broadcasts it over the first communicator
+    NcclUniqueId id2;
+    void *dbuf = nullptr;
+    CK(cudaMalloc(&dbuf, sizeof(id2)));
+    if (rank == 0) { if (nccl_check(g_nccl.get_id(&id2), "ncclGetUniqueId")) return 1; CK(cudaMemcpy(dbuf, &id2, sizeof(id2), cudaMemcpyHostToDevice)); }
+    if (nccl_check(g_nccl.broadcast(dbuf, dbuf, sizeof(id2), NCCL_UINT8, 0, s->comm, s->stream), "ncclBroadcast")) return 1;
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy(&id2, dbuf, sizeof(id2), cudaMemcpyDeviceToHost));
+    cudaFree(dbuf);
+    NcclComm comm2 = nullptr;
+    if (nccl_check(g_nccl.init_rank(&comm2, world_size, id2, rank), "ncclCommInitRank (bulk)")) return 1;
+    s->comm2 = comm2;
+    CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    // peer mailboxes for the latency-bound BN-statistics exchanges (35 per step): CUDA IPC over NVLink.  Any failure
+    // here just leaves xr_enabled = false and those exchanges stay on NCCL.
+    do {
+        if (!g_nccl.all_gather || world_size > XR_MAX_WORLD || getenv("CENN_NO_XR")) break;
+        const size_t bytes = (size_t)2 * XR_MAXF * sizeof(float) + 256;
+        void *own = nullptr, *hbuf = nullptr;
+        if (cudaMalloc(&own, bytes) != cudaSuccess) { cudaGetLastError(); break; }
+        cudaMemset(own, 0, bytes);
+        cudaIpcMemHandle_t mine;
+        if (cudaIpcGetMemHandle(&mine, own) != cudaSuccess) { cudaGetLastError(); cudaFree(own); break; }
+        std::vector<cudaIpcMemHandle_t> all(world_size);
+        if (cudaMalloc(&hbuf, sizeof(mine) * (world_size + 1)) != cudaSuccess) { cudaGetLastError(); cudaFree(own); break; }
+        char *send = (char *)hbuf + sizeof(mine) * world_size;
+        cudaMemcpy(send, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+        cudaDeviceSynchronize();
+        int rc = g_nccl.all_gather(send, hbuf, sizeof(mine), NCCL_UINT8, s->comm, s->stream);
+        cudaStreamSynchronize(s->stream);
+        cudaMemcpy(all.data(), hbuf, sizeof(mine) * world_size, cudaMemcpyDeviceToHost);
+        cudaFree(hbuf);
+        bool ok = rc == 0;
+        XrCtx x = {};
+        x.world = world_size; x.rank = rank;
+        for (int r = 0; r < world_size && ok; ++r) {
+            void *base = own;
+            if (r != rank && cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            x.data[r] = reinterpret_cast<float *>(base);
+            x.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + (size_t)2 * XR_MAXF * sizeof(float));
+        }
+        // every rank must learn whether ALL ranks succeeded (a partial set-up would deadlock the exchange)
+        float *flag_dev = nullptr; float flag_host = ok ? 0.f : 1.f;
+        cudaMalloc(&flag_dev, sizeof(float)); cudaMemcpy(flag_dev, &flag_host, sizeof(float), cudaMemcpyHostToDevice);
+        g_nccl.all_reduce(flag_dev, flag_dev, 1, NCCL_FLOAT32, NCCL_SUM, s->comm, s->stream);
+        cudaStreamSynchronize(s->stream);
+        cudaMemcpy(&flag_host, flag_dev, sizeof(float), cudaMemcpyDeviceToHost); cudaFree(flag_dev);
+        if (flag_host != 0.f) { for (int r = 0; r < world_size; ++r) if (r != rank && x.data[r]) cudaIpcCloseMemHandle(x.data[r]); cudaFree(own); break; }
+        unsigned long long *ep = nullptr;
+        cudaMalloc(&ep, sizeof(*ep)); cudaMemset(ep, 0, sizeof(*ep));
+        x.epoch = ep;
+        s->xr = x; s->xr_own = own; s->xr_enabled = true;
+    } while (0);
     return 0;
 }
 
@@ -95,6 +159,14 @@ int cenn_dist_broadcast(cenn_state *s, void *buf_dev, int64_t bytes, int root) {
 
 int cenn_dist_shutdown(cenn_state *s) {
     API_BEGIN(s);
+    if (s->xr_enabled) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < s->xr.world; ++r) if (r != s->xr.rank && s->xr.data[r]) cudaIpcCloseMemHandle(s->xr.data[r]);
+        cudaFree(s->xr_own); cudaFree(s->xr.epoch); s->xr_enabled = false; s->xr_own = nullptr;
+    }
+    if (s->comm_stream) { cudaStreamSynchronize(s->comm_stream); }
+    if (s->comm2) { g_nccl.destroy(s->comm2); s->comm2 = nullptr; }
+    if (s->comm_stream) { cudaStreamDestroy(s->comm_stream); s->comm_stream = nullptr; }
     if (s->comm) { cudaStreamSynchronize(s->stream); g_nccl.destroy(s->comm); s->comm = nullptr; s->world = 1; s->rank = 0; }
     return 0;
 }

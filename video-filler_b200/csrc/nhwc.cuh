@@ -88,12 +88,9 @@ __global__ void __launch_bounds__(256) im2col_kernel(const bf16 *__restrict__ L,
 // ---------------------------------------------------------------- batch norm
 // sums -> mean / invstd / running stats / (scale, shift); `fold` column groups are summed (G1's GEMM epilogue
 // accumulates per (tap, channel) column).  Zeroes the accumulators for the next use.
-__global__ void bn_finalize_kernel(float *__restrict__ stats, int stats_stride, int fold, int fold_stride, const float *__restrict__ gamma,
+__device__ __forceinline__ void bn_finalize_channel(float *__restrict__ stats, int stats_stride, int fold, int fold_stride, const float *__restrict__ gamma,
         const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
-        float *__restrict__ invstd, float *__restrict__ scale, float *__restrict__ shift, int C, double n, double momentum, double eps,
-        int update_running) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+        float *__restrict__ invstd, float *__restrict__ scale, float *__restrict__ shift, int c, double n, double momentum, double eps, int update_running) {
     double s1 = 0.0, s2 = 0.0;
     for (int f = 0; f < fold; ++f) {
         s1 += (double)stats[f * fold_stride + c]; s2 += (double)stats[stats_stride + f * fold_stride + c];
@@ -109,6 +106,91 @@ __global__ void bn_finalize_kernel(float *__restrict__ stats, int stats_stride, 
     if (update_running) {
         running_mean[c] = (float)(momentum * m + (1.0 - momentum) * (double)running_mean[c]);
         running_var[c] = (float)(momentum * (S / (n - 1.0)) + (1.0 - momentum) * (double)running_var[c]);
+    }
+}
+__global__ void bn_finalize_kernel(float *__restrict__ stats, int stats_stride, int fold, int fold_stride, const float *__restrict__ gamma,
+        const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
+        float *__restrict__ invstd, float *__restrict__ scale, float *__restrict__ shift, int C, double n, double momentum, double eps,
+        int update_running) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    bn_finalize_channel(stats, stats_stride, fold, fold_stride, gamma, beta, running_mean, running_var, mean, invstd, scale, shift, c, n, momentum, eps, update_running);
+}
+
+// ---------------------------------------------------------------- one-shot all-reduce over NVLink peer memory
+// buf[0..n) <- sum over ranks, in place, by ONE CTA: publish the local values in this rank's mailbox (parity slot of
+// the exchange counter), release a flag, wait for every peer's flag, add the peers' payloads read straight from their
+// HBM over NVLink.  All ranks add in rank order, so replicas get bit-identical sums.  Two parity slots suffice: a
+// rank can publish exchange e+2 only after it saw every peer's flag e+1, which a peer raises after reading e.
+// Replaces a NCCL all-reduce launch (~10-25 us at 8 ranks) by ~3 us inside the consumer kernel.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float *p) {
+    float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v;
+}
+__device__ void xr_sum_inplace(float *__restrict__ buf, int n, const XrCtx &x) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const unsigned long long e = *x.epoch + 1;
+    const int par = (int)(e & 1);
+    float *own = x.data[x.rank] + (size_t)par * XR_MAXF;
+    for (int i = tid; i < n; i += nthr) own[i] = buf[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) st_release_sys(x.flags[x.rank] + par, e);
+    if (tid < x.world && tid != x.rank) {
+        const unsigned long long *f = x.flags[tid] + par;
+        long long t0 = clock64();
+        while (ld_acquire_sys(f) < e) {
+            if (clock64() - t0 > 4000000000LL) { printf("cenn: peer exchange timeout (rank %d waiting for rank %d, epoch %llu)\n", x.rank, tid, e); __trap(); }
+        }
+    }
+    __syncthreads();
+    // all ranks' values are loaded before the first add: up to 16 peer loads in flight per thread (a peer load is ~2 us)
+    for (int i = tid; i < n; i += nthr) {
+        float v[XR_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < XR_MAX_WORLD; ++r) v[r] = r < x.world ? ld_relaxed_sys(x.data[r] + (size_t)par * XR_MAXF + i) : 0.f;
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < XR_MAX_WORLD; ++r) acc += v[r];
+        buf[i] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) *x.epoch = e;
+}
+// BN forward statistics: exchange + finalise in one single-CTA kernel (data parallel)
+__global__ void __launch_bounds__(1024) bn_finalize_xr_kernel(const XrCtx x, float *__restrict__ stats, int stats_stride, int fold, int fold_stride, float *__restrict__ cmp,
+        const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
+        float *__restrict__ invstd, float *__restrict__ scale, float *__restrict__ shift, int C, int Cp, double n, double momentum, double eps) {
+    // fold the column groups (G1: 16 taps per channel) locally first: the exchange carries 2*Cp floats
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+        float s1 = 0.f, s2 = 0.f;
+        if (c < C)
+            for (int f = 0; f < fold; ++f) {
+                s1 += stats[f * fold_stride + c]; s2 += stats[stats_stride + f * fold_stride + c];
+                stats[f * fold_stride + c] = 0.f; stats[stats_stride + f * fold_stride + c] = 0.f;
+            }
+        cmp[c] = s1; cmp[Cp + c] = s2;
+    }
+    __syncthreads();
+    xr_sum_inplace(cmp, 2 * Cp, x);
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        bn_finalize_channel(cmp, Cp, 1, 0, gamma, beta, running_mean, running_var, mean, invstd, scale, shift, c, n, momentum, eps, 1);
+}
+// BN backward sums [2][Cp] (already folded over this rank's CTAs): exchange + coefficients + affine gradients
+__global__ void __launch_bounds__(1024) bn_bwd_coef_xr_kernel(const XrCtx x, float *__restrict__ sums, int Cp, const float *__restrict__ gamma, const float *__restrict__ invstd,
+        const float *__restrict__ mean, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n, float grad_scale) {
+    xr_sum_inplace(sums, 2 * Cp, x);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double s = sums[c], d = sums[Cp + c];
+        const double is = invstd[c], A = is * (double)gamma[c], k1 = is * is * d / n;
+        coef[c] = (float)A; coef[C + c] = (float)(A * k1); coef[2 * C + c] = (float)(((double)mean[c] * k1 - s / n) * A);
+        if (ggamma) ggamma[c] += (float)(d * is) * grad_scale;
+        if (gbeta) gbeta[c] += (float)s * grad_scale;
     }
 }
 __global__ void bn_eval_coef_kernel(const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ running_mean,
