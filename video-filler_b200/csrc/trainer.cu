@@ -126,7 +126,9 @@ struct cenn_trainer {
     int64_t graph_kernels = 0;
     int64_t launches_per_step = 0;
     double flops_per_step = 0;
-    std::vector<cudaEvent_t> events;      // fork / join events of the overlapped gradient buckets
+    std::vector<cudaEvent_t> events;      // fork / join events (side stream, overlapped gradient buckets)
+    cudaStream_t side = nullptr;          // weight-gradient GEMMs run here, beside the dgrad / BN-backward chain of the next layer
+    bool serial = false;                  // per-op profiling: everything on the main stream
     std::vector<std::pair<int64_t, int64_t>> g_buckets;   // (offset, count) of G's gradient ranges reduced on the bulk communicator
 };
 
@@ -544,15 +546,31 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
     // weight gradient
     if (want_params) {
         if (b->thin && b->type == FULL_S2) emit_im2col(t, b->g, b->col, b->h, b->w);
-        emit_plan(t, "wgrad", &b->p_wgrad);
+        // The weight gradient of this block depends only on g_y and the block input; the critical path continues with this
+        // block's dgrad and the previous block's BN backward (small kernels, and in data-parallel runs a peer exchange).
+        // It therefore runs on a side stream (joined at the end of the sweep) and fills the gaps of that chain.
+        {
+            cudaEvent_t evf; cudaEventCreateWithFlags(&evf, cudaEventDisableTiming); t->events.push_back(evf);
+            TcPlan *pl = &b->p_wgrad;
+            t->flops_per_step += pl->flops;
+            emit(t, "wgrad", [t, s, evf, pl]() {
+                if (t->serial) return tc_launch(s, pl);
+                if (cenn_check_cuda(cudaEventRecord(evf, s->stream), "event record", __FILE__, __LINE__)) return 1;
+                if (cenn_check_cuda(cudaStreamWaitEvent(t->side, evf, 0), "stream wait", __FILE__, __LINE__)) return 1;
+                cudaStream_t keep = s->stream; s->stream = t->side;
+                int rc = tc_launch(s, pl);
+                s->stream = keep;
+                return rc; });
+            t->prog.back().flops = pl->flops;
+        }
         // data parallel, generator: the big weight gradients start their all-reduce now, on the bulk communicator's stream,
         // and overlap the rest of the backward sweep (E6 + G1 are 92 % of the 285 MB)
         if (dp && s->comm2 && &net == &t->G && b->w_count >= (1 << 20)) {
             cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
             float *ptr = grad + b->w_off; int64_t cnt = b->w_count;
             t->g_buckets.push_back({b->w_off, b->w_count});
-            emit(t, "grad_bucket_ar", [s, ev, ptr, cnt]() {
-                if (cenn_check_cuda(cudaEventRecord(ev, s->stream), "event record", __FILE__, __LINE__)) return 1;
+            emit(t, "grad_bucket_ar", [t, s, ev, ptr, cnt]() {
+                if (cenn_check_cuda(cudaEventRecord(ev, t->serial ? s->stream : t->side), "event record", __FILE__, __LINE__)) return 1;
                 if (cenn_check_cuda(cudaStreamWaitEvent(s->comm_stream, ev, 0), "stream wait", __FILE__, __LINE__)) return 1;
                 return cenn_dist_all_reduce_bulk(s, ptr, cnt); });
         }
@@ -590,6 +608,13 @@ void emit_zero_bias(T *t, Net &net) {
 void emit_fold_gbias(T *t, Net &net) {
     cenn_state *s = t->s;
     Net *n = &net;
+    {   // join the side stream (weight gradients of this sweep)
+        cudaEvent_t evj; cudaEventCreateWithFlags(&evj, cudaEventDisableTiming); t->events.push_back(evj);
+        emit(t, "join_wgrad", [t, s, evj]() {
+            if (t->serial) return 0;
+            if (cenn_check_cuda(cudaEventRecord(evj, t->side), "event record", __FILE__, __LINE__)) return 1;
+            return cenn_check_cuda(cudaStreamWaitEvent(s->stream, evj, 0), "stream wait", __FILE__, __LINE__); });
+    }
     emit(t, "fold_gbias", [s, n]() {
         nhwc::fold_rows_kernel<<<dim3((unsigned)n->fold_host.size(), 8), 256, 0, s->stream>>>(n->fold_jobs); KLAUNCH(s); return 0; });
 }
@@ -855,6 +880,7 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     // G's output must match D's input tensor exactly (same NHWC padding) for the d2d hand-over
     const Tensor &go = t->G.blocks.back().a;
     if (go.H != dsize || go.Cp != t->D.input.Cp) { cenn_set_error("internal: generator output %dx%dx%d does not match discriminator input %dx%dx%d", go.H, go.W, go.Cp, dsize, dsize, t->D.input.Cp); cenn_trainer_destroy(t); return 1; }
+    if (cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
     if (build_program(t)) { cenn_trainer_destroy(t); return 1; }
     int64_t before = s->launches;
     (void)before;
@@ -870,6 +896,7 @@ int cenn_trainer_destroy(cenn_trainer *t) {
     if (t->graph) cudaGraphDestroy(t->graph);
     for (Net *n : {&t->G, &t->D})
         for (Block &b : n->blocks) { tc_plan_free(&b.p_fwd); tc_plan_free(&b.p_dgrad); tc_plan_free(&b.p_wgrad); }
+    if (t->side) { cudaStreamSynchronize(t->side); cudaStreamDestroy(t->side); }
     for (cudaEvent_t e : t->events) cudaEventDestroy(e);
     for (void *p : t->allocs) cudaFree(p);
     if (t->pin_a) cudaFreeHost(t->pin_a);
@@ -1013,10 +1040,12 @@ int cenn_trainer_profile_step(cenn_trainer *t, const float *a, const float *b, c
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto &e : ev) CK(cudaEventCreate(&e));
     t->cur_a = a; t->cur_b = b; t->cur_m = mask;
+    t->serial = true;                 // per-op timing: no side stream
     CK(cudaEventRecord(ev[0], st));
     int rc = 0;
     for (size_t i = 0; i < n && !rc; ++i) { rc = t->prog[i].fn() || reduce_sync_point(t, t->prog[i]); CK(cudaEventRecord(ev[i + 1], st)); }
     CK(cudaStreamSynchronize(st));
+    t->serial = false;
     std::string all;
     for (size_t i = 0; i < n && !rc; ++i) {
         CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
@@ -1042,13 +1071,15 @@ int cenn_trainer_grad_buffer(cenn_trainer *t, int net, float **grads, int64_t *c
 int cenn_trainer_step_phase(cenn_trainer *t, int phase, const float *a, const float *b, const uint8_t *mask) {
     REQUIRE(t, "cenn_trainer_step_phase: null trainer");
     API_BEGIN(t->s);
+    t->serial = true;
     if (phase < 0) { REQUIRE(a && b, "cenn_trainer_step_phase: null input"); t->cur_a = a; t->cur_b = b; t->cur_m = mask; t->pc = 0; t->last_sync = -1; }
     while (t->pc < t->prog.size()) {
         Op &op = t->prog[t->pc++];
-        if (op.fn()) return 1;
-        if (op.sync_buf) { t->last_sync = (long)t->pc - 1; return 0; }
+        if (op.fn()) { t->serial = false; return 1; }
+        if (op.sync_buf) { t->last_sync = (long)t->pc - 1; t->serial = false; return 0; }
     }
     t->last_sync = -1;
+    t->serial = false;
     return 0;
 }
 int cenn_trainer_sync_info(cenn_trainer *t, void **buf, int64_t *count, int *is_double, int *done) {
