@@ -39,7 +39,8 @@ struct cenn_state {
     int world = 1, rank = 0;
     cudaStream_t comm_stream = nullptr;   // gradient all-reduces overlapped with the backward sweep
     bool xr_enabled = false;              // peer mailboxes mapped: BN statistics are exchanged inside the finalize kernels
-    XrCtx xr = {};
+    XrCtx xr = {};                        // exchanges issued from the compute stream
+    XrCtx xr2 = {};                       // a second, independent mailbox sequence for a concurrent chain (trainer side stream)
     void *xr_own = nullptr;
 };
 static const int RED_SLOTS = 64;

@@ -107,7 +107,8 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
     // here just leaves xr_enabled = false and those exchanges stay on NCCL.
     do {
         if (!g_nccl.all_gather || world_size > XR_MAX_WORLD || getenv("CENN_NO_XR")) break;
-        const size_t bytes = (size_t)2 * XR_MAXF * sizeof(float) + 256;
+        const size_t half = (size_t)2 * XR_MAXF * sizeof(float) + 256;   // one mailbox: 2 parity payloads + flags
+        const size_t bytes = 2 * half;                                  // two independent mailbox sequences
         void *own = nullptr, *hbuf = nullptr;
         if (cudaMalloc(&own, bytes) != cudaSuccess) { cudaGetLastError(); break; }
         cudaMemset(own, 0, bytes);
@@ -123,13 +124,15 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
         cudaMemcpy(all.data(), hbuf, sizeof(mine) * world_size, cudaMemcpyDeviceToHost);
         cudaFree(hbuf);
         bool ok = rc == 0;
-        XrCtx x = {};
-        x.world = world_size; x.rank = rank;
+        XrCtx x = {}, x2 = {};
+        x.world = x2.world = world_size; x.rank = x2.rank = rank;
         for (int r = 0; r < world_size && ok; ++r) {
             void *base = own;
             if (r != rank && cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
             x.data[r] = reinterpret_cast<float *>(base);
             x.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + (size_t)2 * XR_MAXF * sizeof(float));
+            x2.data[r] = reinterpret_cast<float *>(reinterpret_cast<char *>(base) + half);
+            x2.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + half + (size_t)2 * XR_MAXF * sizeof(float));
         }
         // every rank must learn whether ALL ranks succeeded (a partial set-up would deadlock the exchange)
         float *flag_dev = nullptr; float flag_host = ok ? 0.f : 1.f;
@@ -139,9 +142,9 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
         cudaMemcpy(&flag_host, flag_dev, sizeof(float), cudaMemcpyDeviceToHost); cudaFree(flag_dev);
         if (flag_host != 0.f) { for (int r = 0; r < world_size; ++r) if (r != rank && x.data[r]) cudaIpcCloseMemHandle(x.data[r]); cudaFree(own); break; }
         unsigned long long *ep = nullptr;
-        cudaMalloc(&ep, sizeof(*ep)); cudaMemset(ep, 0, sizeof(*ep));
-        x.epoch = ep;
-        s->xr = x; s->xr_own = own; s->xr_enabled = true;
+        cudaMalloc(&ep, 2 * sizeof(*ep)); cudaMemset(ep, 0, 2 * sizeof(*ep));
+        x.epoch = ep; x2.epoch = ep + 1;
+        s->xr = x; s->xr2 = x2; s->xr_own = own; s->xr_enabled = true;
     } while (0);
     return 0;
 }

@@ -76,6 +76,7 @@ struct Op {
     float *sync_buf = nullptr;     // non-null: after fn, this buffer must be summed across ranks (DP)
     int64_t sync_count = 0;
     const char *name = "";
+    int chain = 0;                 // 1: runs on the trainer's second chain stream (generator forward beside the D-real sweep)
     double flops = 0;              // algorithmic FLOPs (tensor-core ops)
     double bytes = 0;              // algorithmic bytes (bandwidth ops), 0 if not stated
 };
@@ -127,6 +128,8 @@ struct cenn_trainer {
     int64_t launches_per_step = 0;
     double flops_per_step = 0;
     std::vector<cudaEvent_t> events;      // fork / join events (side stream, overlapped gradient buckets)
+    cudaStream_t side2 = nullptr;         // second chain: generator forward beside the discriminator's real sweep
+    int emit_chain = 0;                   // chain id given to the ops being emitted
     cudaStream_t side = nullptr;          // weight-gradient GEMMs run here, beside the dgrad / BN-backward chain of the next layer
     bool serial = false;                  // per-op profiling: everything on the main stream
     std::vector<std::pair<int64_t, int64_t>> g_buckets;   // (offset, count) of G's gradient ranges reduced on the bulk communicator
@@ -393,7 +396,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
 #define KLAUNCH(s) do { (s)->launches++; if (cenn_check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)) return 1; } while (0)
 
 void emit(T *t, const char *name, std::function<int()> fn, float *sync_buf = nullptr, int64_t sync_count = 0) {
-    Op op; op.fn = std::move(fn); op.sync_buf = sync_buf; op.sync_count = sync_count; op.name = name;
+    Op op; op.fn = std::move(fn); op.sync_buf = sync_buf; op.sync_count = sync_count; op.name = name; op.chain = t->emit_chain;
     t->prog.push_back(std::move(op));
 }
 void emit_plan(T *t, const char *name, TcPlan *pl) {
@@ -444,8 +447,9 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
         if (train) {
             if (t->cfg.world_size > 1 && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {
                 // data parallel: the statistics cross NVLink inside the finalize kernel (peer mailboxes), no collective launch
-                emit(t, "bn_finalize_xr", [s, b, gamma, beta, n_global]() {
-                    nhwc::bn_finalize_xr_kernel<<<1, 1024, 0, s->stream>>>(s->xr, b->stats, b->stats_cols, b->fold, b->Coutp, b->bsums, gamma, beta,
+                const int chain = t->emit_chain;
+                emit(t, "bn_finalize_xr", [t, s, b, gamma, beta, n_global, chain]() {
+                    nhwc::bn_finalize_xr_kernel<<<1, 1024, 0, s->stream>>>((chain == 1 && !t->serial) ? s->xr2 : s->xr, b->stats, b->stats_cols, b->fold, b->Coutp, b->bsums, gamma, beta,
                         b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, b->Coutp, n_global, 0.1, 1e-5);
                     KLAUNCH(s); return 0; });
             } else {
@@ -688,6 +692,23 @@ int build_program(T *t) {
     // ================= fDx (train.lua:278-350) =================
     emit_zero_bias(t, D); emit_zero_bias(t, G);
     emit_zero_grad(t, D);
+    // The generator forward does not depend on the discriminator's real sweep (and vice versa): it runs as a second chain
+    // on its own stream; each chain's small BN kernels / peer exchanges fill the other's gaps.  (Not with NCCL-only
+    // data parallelism: one communicator must not be driven from two streams.)
+    const bool two_chains = !(c.world_size > 1 && !s->xr_enabled) && getenv("CENN_ONE_CHAIN") == nullptr;
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+    if (two_chains) {
+        cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming);
+        t->events.push_back(ev_fork2); t->events.push_back(ev_join2);
+        emit(t, "fork_G_fwd", [t, s, ev_fork2]() {
+            if (t->serial) return 0;
+            if (cenn_check_cuda(cudaEventRecord(ev_fork2, s->stream), "event record", __FILE__, __LINE__)) return 1;
+            return cenn_check_cuda(cudaStreamWaitEvent(t->side2, ev_fork2, 0), "stream wait", __FILE__, __LINE__); });
+        t->emit_chain = 1;
+        emit_copy(t, "g_in<-ctx", G.input.p, t->real_ctx.p, G.input.elems());
+        for (size_t i = 0; i < G.blocks.size(); ++i) emit_forward(t, G, i, true);
+        t->emit_chain = 0;
+    }
     // D on real
     emit_copy(t, "d_in<-real", D.input.p, t->real_aux.p, D.input.elems());
     for (size_t i = 0; i < D.blocks.size(); ++i) emit_forward(t, D, i, true);
@@ -695,8 +716,15 @@ int build_program(T *t) {
     for (size_t i = D.blocks.size(); i-- > 0;) emit_backward(t, D, i, true, i > 0 || c.dead_dgrad);
     emit_fold_gbias(t, D);
     // G forward
-    emit_copy(t, "g_in<-ctx", G.input.p, t->real_ctx.p, G.input.elems());
-    for (size_t i = 0; i < G.blocks.size(); ++i) emit_forward(t, G, i, true);
+    if (two_chains) {
+        emit(t, "join_G_fwd", [t, s, ev_join2]() {
+            if (t->serial) return 0;
+            if (cenn_check_cuda(cudaEventRecord(ev_join2, t->side2), "event record", __FILE__, __LINE__)) return 1;
+            return cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev_join2, 0), "stream wait", __FILE__, __LINE__); });
+    } else {
+        emit_copy(t, "g_in<-ctx", G.input.p, t->real_ctx.p, G.input.elems());
+        for (size_t i = 0; i < G.blocks.size(); ++i) emit_forward(t, G, i, true);
+    }
     // D on fake
     if (video && c.weight_nomask == 0.f) {
         emit_copy(t, "d_in<-real", D.input.p, t->real_aux.p, D.input.elems());
@@ -781,9 +809,14 @@ int reduce_sync_point(T *t, const Op &op) {
     return cenn_dist_all_reduce_on(s, op.sync_buf, is_loss ? 8 : op.sync_count, is_loss ? 1 : 0, s->stream);
 }
 int run_ops(T *t, size_t from, size_t to) {
+    cenn_state *s = t->s;
     for (size_t i = from; i < to; ++i) {
-        if (t->prog[i].fn()) return 1;
-        if (reduce_sync_point(t, t->prog[i])) return 1;
+        const Op &op = t->prog[i];
+        cudaStream_t keep = s->stream;
+        if (op.chain == 1 && !t->serial) s->stream = t->side2;
+        int rc = op.fn() || reduce_sync_point(t, op);
+        s->stream = keep;
+        if (rc) return 1;
     }
     return 0;
 }
@@ -880,6 +913,7 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     // G's output must match D's input tensor exactly (same NHWC padding) for the d2d hand-over
     const Tensor &go = t->G.blocks.back().a;
     if (go.H != dsize || go.Cp != t->D.input.Cp) { cenn_set_error("internal: generator output %dx%dx%d does not match discriminator input %dx%dx%d", go.H, go.W, go.Cp, dsize, dsize, t->D.input.Cp); cenn_trainer_destroy(t); return 1; }
+    if (cudaStreamCreateWithFlags(&t->side2, cudaStreamNonBlocking) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
     if (cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
     if (build_program(t)) { cenn_trainer_destroy(t); return 1; }
     int64_t before = s->launches;
@@ -897,6 +931,7 @@ int cenn_trainer_destroy(cenn_trainer *t) {
     for (Net *n : {&t->G, &t->D})
         for (Block &b : n->blocks) { tc_plan_free(&b.p_fwd); tc_plan_free(&b.p_dgrad); tc_plan_free(&b.p_wgrad); }
     if (t->side) { cudaStreamSynchronize(t->side); cudaStreamDestroy(t->side); }
+    if (t->side2) { cudaStreamSynchronize(t->side2); cudaStreamDestroy(t->side2); }
     for (cudaEvent_t e : t->events) cudaEventDestroy(e);
     for (void *p : t->allocs) cudaFree(p);
     if (t->pin_a) cudaFreeHost(t->pin_a);
