@@ -587,14 +587,20 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
     // single GPU, generator: once this block's wgrad (side stream) and dgrad (this stream, the last reader of its weights)
     // are queued, its slice of the flat vector can take its Adam update on a third stream while the sweep goes on
     // (E6 + G1 hold 92 % of the parameters: ~0.3 ms of HBM-bound work moved off the critical path)
-    if (want_params && !dp && &net == &t->G && b->w_count >= (1 << 20) && getenv("CENN_NO_EARLY_ADAM") == nullptr) {
+    // (data parallel: same, chained behind the block's bucket all-reduce on the bulk communicator's stream)
+    const bool dp_bulk = dp && s->comm2 != nullptr;
+    if (want_params && (!dp || dp_bulk) && &net == &t->G && b->w_count >= (1 << 20) && getenv("CENN_NO_EARLY_ADAM") == nullptr) {
         cudaEvent_t e1, e2; cudaEventCreateWithFlags(&e1, cudaEventDisableTiming); cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
         t->events.push_back(e1); t->events.push_back(e2);
         Net *n = &net; const int64_t off = b->w_off, cnt = b->w_count; const float beta1 = t->cfg.beta1;
         t->g_early.push_back({off, cnt});
-        emit(t, "adam_early", [t, s, n, e1, e2, off, cnt, beta1]() {
+        emit(t, "adam_early", [t, s, n, e1, e2, off, cnt, beta1, dp_bulk]() {
             cudaStream_t st = s->stream;
-            if (!t->serial) {
+            if (dp_bulk) {                           // comm_stream: [wait wgrad] all-reduce -> [wait dgrad] Adam; joined at gradG_sync
+                if (cenn_check_cuda(cudaEventRecord(e1, s->stream), "event record", __FILE__, __LINE__)) return 1;
+                if (cenn_check_cuda(cudaStreamWaitEvent(s->comm_stream, e1, 0), "stream wait", __FILE__, __LINE__)) return 1;
+                st = s->comm_stream;
+            } else if (!t->serial) {
                 if (cenn_check_cuda(cudaEventRecord(e1, s->stream), "event record", __FILE__, __LINE__)) return 1;   // after dgrad
                 if (cenn_check_cuda(cudaEventRecord(e2, t->side), "event record", __FILE__, __LINE__)) return 1;     // after wgrad
                 if (cenn_check_cuda(cudaStreamWaitEvent(t->side3, e1, 0), "stream wait", __FILE__, __LINE__)) return 1;
@@ -817,7 +823,7 @@ int build_program(T *t) {
     emit_adam_step(t, G);          // optimState.t / step size first: the big blocks are updated as soon as their gradient exists
     t->g_early.clear();
     for (size_t i = G.blocks.size(); i-- > 0;) emit_backward(t, G, i, true, i > 0 || c.dead_dgrad);
-    if (!t->g_early.empty()) {
+    if (!t->g_early.empty() && c.world_size <= 1) {
         cudaEvent_t evj; cudaEventCreateWithFlags(&evj, cudaEventDisableTiming); t->events.push_back(evj);
         emit(t, "join_adam", [t, s, evj]() {
             if (t->serial) return 0;
