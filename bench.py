@@ -47,6 +47,11 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
         self.proc = None
+        self.t_begin = None
+
+    def mark_begin(self):
+        """Samples taken from now on are inside the timed region."""
+        self.t_begin = time.time()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -57,7 +62,7 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.samples.append([x.strip() for x in line.split(",")])
+                self.samples.append((time.time(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
 
@@ -66,7 +71,10 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         sm, reasons, smax = [], set(), None
-        for s in self.samples:
+        inside = [v for (ts, v) in self.samples if self.t_begin is None or ts >= self.t_begin]
+        if not inside:                      # timed region shorter than one sampling period: use the last sample before it ended
+            inside = [v for (_, v) in self.samples[-1:]]
+        for s in inside:
             try:
                 sm.append(float(s[0])); smax = float(s[1])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
@@ -100,7 +108,8 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 32       # bounded sample of the 256-sample step (a full step takes ~30 s on 8 cores)
+    # bounded sample of the 256-sample step: the port runs ~8 samples/s on 16 cores, so size each step for ~90 s in total
+    batch = int(max(2, min(32, 90 * 8 // max(1, args.steps + args.warmup))))
     rate, sec = cpu_port_step_rate(batch, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": "train samples/sec (G+D step)", "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
@@ -126,8 +135,8 @@ def wrap_device(ptr, count, dtype, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -191,6 +200,7 @@ def main():
         trn.step_device(da.ptr, db.ptr)
 
     losses = None
+    sampler = ClockSampler(local_rank); sampler.start()
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step_device(i)
@@ -198,7 +208,7 @@ def main():
         if dist:
             dist.barrier()
         launches0 = C.c_int64(); api.cenn_kernel_launches(st, C.byref(launches0))
-        sampler = ClockSampler(local_rank); sampler.start()
+        sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(args.steps):
