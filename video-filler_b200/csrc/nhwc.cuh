@@ -216,6 +216,58 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const bf16 *__restric
     }
 }
 
+// bn_finalize + bn_apply_act in ONE launch (training mode, C <= 1024): every CTA derives scale / shift of all channels from
+// the epilogue sums into shared memory (a few hundred fp64 operations per thread), CTA 0 also publishes mean / invstd /
+// scale / shift / running statistics for the backward pass, and the last CTA to have read the sums zeroes them for the
+// next use.  Removes one dependent launch (~5 us on the critical path) per BN layer and sweep.
+__global__ void __launch_bounds__(256) bn_finalize_apply_act_kernel(float *__restrict__ stats, int stats_stride, int fold, int fold_stride,
+        const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var,
+        float *__restrict__ mean, float *__restrict__ invstd, float *__restrict__ scale_g, float *__restrict__ shift_g, int C, int Cp, double n,
+        double momentum, double eps, const bf16 *__restrict__ y, bf16 *__restrict__ a, int64_t nvec, int vec_per_pix, int act, float negval,
+        unsigned int *__restrict__ done_counter) {
+    extern __shared__ float sm_ss[];                   // [2][Cp]
+    __shared__ int is_last;
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+        float sc = 0.f, sh = 0.f;
+        if (c < C) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int f = 0; f < fold; ++f) { s1 += (double)stats[f * fold_stride + c]; s2 += (double)stats[stats_stride + f * fold_stride + c]; }
+            const double m = s1 / n;
+            double S = s2 - s1 * m;
+            if (S < 0) S = 0;
+            const double is = 1.0 / sqrt(S / n + eps);
+            sc = (float)(is * (double)gamma[c]); sh = beta[c] - (float)m * sc;
+            if (blockIdx.x == 0) {
+                mean[c] = (float)m; invstd[c] = (float)is; scale_g[c] = sc; shift_g[c] = sh;
+                running_mean[c] = (float)(momentum * m + (1.0 - momentum) * (double)running_mean[c]);
+                running_var[c] = (float)(momentum * (S / (n - 1.0)) + (1.0 - momentum) * (double)running_var[c]);
+            }
+        }
+        sm_ss[c] = sc; sm_ss[Cp + c] = sh;
+    }
+    __syncthreads();                                   // all reads of `stats` by this CTA are done
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int k = atomicAdd(done_counter, 1u);
+        is_last = (k == gridDim.x - 1);
+        if (is_last) *done_counter = 0u;
+    }
+    __syncthreads();
+    if (is_last)
+        for (int i = threadIdx.x; i < fold * fold_stride; i += blockDim.x) { stats[i] = 0.f; stats[stats_stride + i] = 0.f; }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % vec_per_pix) * 8;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(y) + i), f);
+        const float4 s0 = *reinterpret_cast<const float4 *>(sm_ss + c0), s1 = *reinterpret_cast<const float4 *>(sm_ss + c0 + 4);
+        const float4 h0 = *reinterpret_cast<const float4 *>(sm_ss + Cp + c0), h1 = *reinterpret_cast<const float4 *>(sm_ss + Cp + c0 + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = act_fwd(fmaf(f[k], sc[k], sh[k]), act, negval);
+        reinterpret_cast<uint4 *>(a)[i] = pack8(f);
+    }
+}
+
 // Per-channel reductions over NHWC: blockDim = (TX channel-vectors, TY pixel lanes), grid = (pixel strips, vector groups).
 // Each thread owns one 8-channel vector position and walks pixels with stride gridDim.x*TY, U pixels per iteration with
 // all loads issued before the arithmetic (bytes in flight hide HBM latency); partial sums are folded with shared-memory

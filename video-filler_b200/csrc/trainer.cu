@@ -44,6 +44,7 @@ struct Block {
     int64_t col_rows = 0, col_k = 0;
     bf16 *Wt = nullptr;                     // transposed operand copy
     int cl_rows = 0;
+    unsigned int *done_ctr = nullptr;       // bn_finalize_apply_act: CTAs that have consumed the statistics
     float *part = nullptr;                  // per-CTA partial rows of the backward reductions [part_rows][2*Coutp]
     int part_rows = 0;
     float *stats = nullptr, *bsums = nullptr, *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *coef = nullptr;
@@ -282,6 +283,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             b.scale = dalloc<float>(t, b.Coutp); b.shift = dalloc<float>(t, b.Coutp);
             b.coef = dalloc<float>(t, 3 * (int64_t)b.Coutp);
             b.running = dalloc<float>(t, 2 * (int64_t)b.Coutp);
+            b.done_ctr = dalloc<unsigned int>(t, 1);
             if (!b.stats || !b.bsums || !b.mean || !b.invstd || !b.scale || !b.shift || !b.coef || !b.running) return 1;
             std::vector<float> ones(b.Coutp, 1.f);
             CK(cudaMemcpy(b.running + b.Coutp, ones.data(), b.Coutp * sizeof(float), cudaMemcpyHostToDevice));
@@ -444,6 +446,16 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
         emit(t, "expand_bias", [s, b, bias]() { expand_bias_kernel<<<(16 * b->Clp + 255) / 256, 256, 0, s->stream>>>(bias, b->bias_exp, b->Cout, b->Clp); KLAUNCH(s); return 0; });
     }
     emit_plan(t, "conv_fwd", &b->p_fwd);
+    if (b->bn && train && t->cfg.world_size <= 1 && b->Coutp <= 1024 && b->fold == 1 && getenv("CENN_NO_BN_FUSE") == nullptr) {
+        float *gamma = master + b->g_off, *beta = master + b->be_off;
+        emit(t, "bn_fin_apply", [s, b, gamma, beta, n_global]() {
+            int64_t nvec = b->y.elems() / 8;
+            nhwc::bn_finalize_apply_act_kernel<<<grid1d(s, nvec), 256, 2 * b->Coutp * sizeof(float), s->stream>>>(b->stats, b->stats_cols, b->fold, b->Coutp, gamma, beta,
+                b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, b->Coutp, n_global, 0.1, 1e-5,
+                b->y.p, b->a.p, nvec, b->Coutp / 8, b->act, 0.2f, b->done_ctr);
+            KLAUNCH(s); return 0; });
+        return;
+    }
     if (b->bn) {
         float *gamma = master + b->g_off, *beta = master + b->be_off;
         if (train) {
