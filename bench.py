@@ -229,8 +229,13 @@ def main():
         if dist:
             dist.barrier()
         t0 = time.perf_counter()
+        # public pipelined API: every step copies ITS inputs from pinned host memory and its losses are read back;
+        # the copy of step k+1 overlaps the compute of step k, the losses of step k are read while step k+1 runs
         for i in range(args.steps):
-            losses = trn.step_host(host[i % n_batches][0], host[i % n_batches][1])
+            trn.step_host_async(host[i % n_batches][0], host[i % n_batches][1])
+            if i > 0:
+                losses = trn.wait_losses()
+        losses = trn.wait_losses()
         torch.cuda.synchronize()
         if dist:
             dist.barrier()

@@ -228,6 +228,11 @@ CENN_API int cenn_trainer_get_bn_stats_host(cenn_trainer *t, int net, float *sta
  * Copies inputs H2D, runs the step, copies the CENN_LOSS_COUNT losses back. */
 CENN_API int cenn_trainer_step_host(cenn_trainer *t, const float *a_host, const float *b_host,
         const uint8_t *mask_host, float *losses_host /*[CENN_LOSS_COUNT]*/);
+/* pipelined form: enqueue step k (H2D of its inputs on a copy stream overlaps step k-1), read the losses one call later.
+ * At most two steps may be in flight; host buffers (pinned for true overlap, cenn_host_alloc) must stay valid until the
+ * matching cenn_trainer_wait_losses returns.  Results are identical to cenn_trainer_step_host. */
+CENN_API int cenn_trainer_step_host_async(cenn_trainer *t, const float *a_host, const float *b_host, const uint8_t *mask_host);
+CENN_API int cenn_trainer_wait_losses(cenn_trainer *t, float *losses_host /*[CENN_LOSS_COUNT]*/);
 /* same with inputs already resident in HBM (fp32 NCHW device pointers, mask as uint8 device pointer);
  * losses stay on the device until cenn_trainer_read_losses */
 CENN_API int cenn_trainer_step_device(cenn_trainer *t, const float *a_dev, const float *b_dev, const uint8_t *mask_dev);

@@ -210,3 +210,33 @@ def test_fused_rejects_bad_config(cenn):
         train.FusedTrainer(models.default_opt("image", fineSize=64, batchSize=2))
     with pytest.raises(CennError, match="BF16 tensor-core mode only"):
         train.FusedTrainer(models.default_opt("image", batchSize=2), precision="fp32")
+
+
+def test_pipelined_host_steps_match_blocking_steps(cenn):
+    """cenn_trainer_step_host_async / wait_losses (copy of step k+1 overlapped with step k, losses read one call late)
+    against cenn_trainer_step_host on the same inputs."""
+    from video_filler_b200 import models, synth, train, util
+    kw = dict(batchSize=8, nBottleneck=128, nef=64, ngf=64, ndf=64)
+    opt = models.default_opt("image", **kw)
+    rng = np.random.default_rng(5)
+    pG = util.params_flat(util.weights_init(util.describe_netG(opt), rng))
+    pD = util.params_flat(util.weights_init(util.describe_netD(opt), rng))
+    blocking, piped = train.FusedTrainer(opt), train.FusedTrainer(opt)
+    for t in (blocking, piped):
+        t.set_params(0, pG); t.set_params(1, pD)
+    batches = [synth.image_batch(8, 128, 4, np.random.default_rng(100 + i)) for i in range(4)]
+    ref = [blocking.step_host(*b) for b in batches]
+    got = []
+    for i, b in enumerate(batches):
+        piped.step_host_async(*b)
+        if i > 0:
+            got.append(piped.wait_losses())
+    got.append(piped.wait_losses())
+    assert len(got) == len(ref)
+    for k in ("errD", "errG", "errG_l2"):                          # step 1: same arithmetic, up to the executor's atomics order
+        assert got[0][k] == pytest.approx(ref[0][k], rel=1e-2), k
+    for g, r in zip(got, ref):
+        assert all(np.isfinite(v) for v in g.values())
+        assert g["errG_l2"] == pytest.approx(r["errG_l2"], rel=5e-2)
+    with pytest.raises(Exception, match="no step in flight"):
+        piped.wait_losses()

@@ -121,8 +121,18 @@ struct cenn_trainer {
     double *loss_acc = nullptr;           // [8] device accumulators
     float *loss_out = nullptr;            // [8] device floats
     Tensor df_dg;                         // gradient w.r.t. D's input (G step)
+    struct GraphEntry { const void *key[3]; cudaGraph_t graph; cudaGraphExec_t exec; int seen; int64_t kernels; unsigned long long last_use; };
+    std::vector<GraphEntry> graphs;       // one captured step per set of input buffers (at most GRAPH_CACHE)
+    unsigned long long use_clock = 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    // pipelined host-fed steps: two staging sets, a copy stream, per-set events, pinned loss slots
+    float *in_a2 = nullptr, *in_b2 = nullptr; uint8_t *in_m2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_loss[2] = {nullptr, nullptr};
+    bool consumed_valid[2] = {false, false};
+    float *pin_loss2 = nullptr;           // [2][8]
+    long long async_issued = 0, async_read = 0;
     bool graph_failed = false;
     const void *graph_key[3] = {nullptr, nullptr, nullptr}, *seen_key[3] = {nullptr, nullptr, nullptr};
     int64_t graph_kernels = 0;
@@ -886,42 +896,53 @@ int run_ops(T *t, size_t from, size_t to) {
     return 0;
 }
 
+static const int GRAPH_CACHE = 4;
 int run_step(T *t) {
     cenn_state *s = t->s;
     static const bool no_graph = getenv("CENN_NO_GRAPH") != nullptr;
     if (no_graph || t->graph_failed) return run_ops(t, 0, t->prog.size());
     const void *key[3] = {t->cur_a, t->cur_b, t->cur_m};
-    if (t->graph_exec && memcmp(key, t->graph_key, sizeof(key)) == 0) {
-        CK(cudaGraphLaunch(t->graph_exec, s->stream));
-        s->launches += t->graph_kernels;
+    T::GraphEntry *ent = nullptr;
+    for (auto &g : t->graphs) if (memcmp(key, g.key, sizeof(key)) == 0) { ent = &g; break; }
+    if (ent && ent->exec) {
+        ent->last_use = ++t->use_clock;
+        CK(cudaGraphLaunch(ent->exec, s->stream));
+        s->launches += ent->kernels;
         return 0;
     }
     // the first step with a given set of input buffers runs eagerly (it also warms lazily loaded kernels);
-    // the second one is captured, every later one replays the graph
-    if (memcmp(key, t->seen_key, sizeof(key)) != 0) {
-        memcpy(t->seen_key, key, sizeof(key));
+    // the second one is captured, every later one replays its graph
+    if (!ent) {
+        if ((int)t->graphs.size() >= GRAPH_CACHE) {        // evict the least recently used entry
+            size_t lru = 0;
+            for (size_t i = 1; i < t->graphs.size(); ++i) if (t->graphs[i].last_use < t->graphs[lru].last_use) lru = i;
+            if (t->graphs[lru].exec) cudaGraphExecDestroy(t->graphs[lru].exec);
+            if (t->graphs[lru].graph) cudaGraphDestroy(t->graphs[lru].graph);
+            t->graphs.erase(t->graphs.begin() + lru);
+        }
+        T::GraphEntry g = {};
+        memcpy(g.key, key, sizeof(key)); g.seen = 1; g.last_use = ++t->use_clock;
+        t->graphs.push_back(g);
         return run_ops(t, 0, t->prog.size());
     }
-    if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
-    if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
     int64_t before = s->launches;
     if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError(); t->graph_failed = true;
         return run_ops(t, 0, t->prog.size());
     }
     int rc = run_ops(t, 0, t->prog.size());
-    cudaError_t e = cudaStreamEndCapture(s->stream, &t->graph);
-    t->graph_kernels = s->launches - before;
+    cudaError_t e = cudaStreamEndCapture(s->stream, &ent->graph);
+    ent->kernels = s->launches - before;
     s->launches = before;
-    if (rc || e != cudaSuccess || !t->graph || cudaGraphInstantiate(&t->graph_exec, t->graph, 0) != cudaSuccess) {
+    if (rc || e != cudaSuccess || !ent->graph || cudaGraphInstantiate(&ent->exec, ent->graph, 0) != cudaSuccess) {
         cudaGetLastError();
-        if (t->graph) { cudaGraphDestroy(t->graph); t->graph = nullptr; }
-        t->graph_exec = nullptr; t->graph_failed = true;
+        if (ent->graph) { cudaGraphDestroy(ent->graph); ent->graph = nullptr; }
+        ent->exec = nullptr; t->graph_failed = true;
         return run_ops(t, 0, t->prog.size());
     }
-    memcpy(t->graph_key, key, sizeof(key));
-    CK(cudaGraphLaunch(t->graph_exec, s->stream));
-    s->launches += t->graph_kernels;
+    ent->last_use = ++t->use_clock;
+    CK(cudaGraphLaunch(ent->exec, s->stream));
+    s->launches += ent->kernels;
     return 0;
 }
 
@@ -992,8 +1013,10 @@ int cenn_trainer_destroy(cenn_trainer *t) {
     if (!t) return 0;
     cudaSetDevice(t->s->device);
     cudaStreamSynchronize(t->s->stream);
-    if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
-    if (t->graph) cudaGraphDestroy(t->graph);
+    for (auto &g : t->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
+    if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
+    for (int i = 0; i < 2; ++i) { if (t->ev_copied[i]) cudaEventDestroy(t->ev_copied[i]); if (t->ev_consumed[i]) cudaEventDestroy(t->ev_consumed[i]); if (t->ev_loss[i]) cudaEventDestroy(t->ev_loss[i]); }
+    if (t->pin_loss2) cudaFreeHost(t->pin_loss2);
     for (Net *n : {&t->G, &t->D})
         for (Block &b : n->blocks) { tc_plan_free(&b.p_fwd); tc_plan_free(&b.p_dgrad); tc_plan_free(&b.p_wgrad); }
     if (t->side) { cudaStreamSynchronize(t->side); cudaStreamDestroy(t->side); }
@@ -1128,6 +1151,48 @@ int cenn_trainer_step_host(cenn_trainer *t, const float *a, const float *b, cons
     if (t->cfg.variant == 1) CK(cudaMemcpyAsync(t->in_m, mask, t->n_m, cudaMemcpyHostToDevice, st));
     if (cenn_trainer_step_device(t, t->in_a, t->in_b, t->in_m)) return 1;
     return cenn_trainer_read_losses(t, losses);
+}
+
+// Pipelined host-fed steps: step k's inputs are copied (copy stream, staging set k & 1) while step k-1 computes; losses
+// are read one call later.  Host buffers must stay valid until the matching cenn_trainer_wait_losses returns.
+int cenn_trainer_step_host_async(cenn_trainer *t, const float *a, const float *b, const uint8_t *mask) {
+    REQUIRE(t && a && b, "cenn_trainer_step_host_async: null argument");
+    REQUIRE(t->cfg.variant == 0 || mask, "cenn_trainer_step_host_async: the video variant needs a mask");
+    API_BEGIN(t->s);
+    REQUIRE(t->async_issued - t->async_read < 2, "cenn_trainer_step_host_async: two steps already in flight; call cenn_trainer_wait_losses");
+    cudaStream_t st = t->s->stream;
+    if (!t->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&t->ev_copied[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&t->ev_consumed[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&t->ev_loss[i], cudaEventDisableTiming)); }
+        t->in_a2 = dalloc<float>(t, t->n_a); t->in_b2 = dalloc<float>(t, t->n_b);
+        if (t->cfg.variant == 1) t->in_m2 = dalloc<uint8_t>(t, t->n_m);
+        REQUIRE(t->in_a2 && t->in_b2, "trainer: staging allocation failed");
+        CK(cudaMallocHost(&t->pin_loss2, 2 * 8 * sizeof(float)));
+    }
+    const int i = (int)(t->async_issued & 1);
+    float *da = i ? t->in_a2 : t->in_a, *db = i ? t->in_b2 : t->in_b; uint8_t *dm = i ? t->in_m2 : t->in_m;
+    if (t->consumed_valid[i]) CK(cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[i], 0));
+    CK(cudaMemcpyAsync(da, a, t->n_a * 4, cudaMemcpyHostToDevice, t->copy_stream));
+    CK(cudaMemcpyAsync(db, b, t->n_b * 4, cudaMemcpyHostToDevice, t->copy_stream));
+    if (t->cfg.variant == 1) CK(cudaMemcpyAsync(dm, mask, t->n_m, cudaMemcpyHostToDevice, t->copy_stream));
+    CK(cudaEventRecord(t->ev_copied[i], t->copy_stream));
+    CK(cudaStreamWaitEvent(st, t->ev_copied[i], 0));
+    if (cenn_trainer_step_device(t, da, db, dm)) return 1;
+    CK(cudaEventRecord(t->ev_consumed[i], st)); t->consumed_valid[i] = true;
+    CK(cudaMemcpyAsync(t->pin_loss2 + 8 * i, t->loss_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(t->ev_loss[i], st));
+    t->async_issued++;
+    return 0;
+}
+int cenn_trainer_wait_losses(cenn_trainer *t, float *losses) {
+    REQUIRE(t && losses, "cenn_trainer_wait_losses: null argument");
+    API_BEGIN(t->s);
+    REQUIRE(t->async_read < t->async_issued, "cenn_trainer_wait_losses: no step in flight");
+    const int i = (int)(t->async_read & 1);
+    CK(cudaEventSynchronize(t->ev_loss[i]));
+    memcpy(losses, t->pin_loss2 + 8 * i, 8 * sizeof(float));
+    t->async_read++;
+    return 0;
 }
 
 // One step with a CUDA-event pair around every op of the program (on the launching stream); returns the op names

@@ -259,6 +259,17 @@ class FusedTrainer:
                                      losses.ctypes.data_as(C.c_void_p))
         return dict(zip(LOSS_NAMES, losses.tolist()))
 
+    def step_host_async(self, a, b, mask=None):
+        """Enqueue one step from host arrays (must stay alive until the matching wait_losses); at most two in flight."""
+        assert a.dtype == np.float32 and b.dtype == np.float32 and a.flags.c_contiguous and b.flags.c_contiguous
+        m = mask.ctypes.data_as(C.c_void_p) if mask is not None else None
+        api().cenn_trainer_step_host_async(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), m)
+
+    def wait_losses(self):
+        losses = np.zeros(8, np.float32)
+        api().cenn_trainer_wait_losses(self.h, losses.ctypes.data_as(C.c_void_p))
+        return dict(zip(LOSS_NAMES, losses.tolist()))
+
     def step_device(self, a_ptr, b_ptr, mask_ptr=None):
         api().cenn_trainer_step_device(self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr),
                                        C.c_void_p(mask_ptr) if mask_ptr else None)
