@@ -605,7 +605,24 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
     } else if (b->thin && b->type == FULL_S2 && want_dgrad && b->has_dgrad) {
         emit_im2col(t, b->g, b->col, b->h, b->w);
     }
-    if (want_dgrad && b->has_dgrad) emit_plan(t, "dgrad", &b->p_dgrad);
+    if (want_dgrad && b->has_dgrad) {
+        if (i == 0 && want_params) {
+            // first block of a net in a parameter sweep: the reference computes this gradInput and discards it (dead_dgrad); nothing waits for
+            // it, so it runs on the side stream after the block's wgrad instead of on the critical path
+            cudaEvent_t evf; cudaEventCreateWithFlags(&evf, cudaEventDisableTiming); t->events.push_back(evf);
+            TcPlan *pl = &b->p_dgrad;
+            t->flops_per_step += pl->flops;
+            emit(t, "dgrad", [t, s, evf, pl]() {
+                if (t->serial) return tc_launch(s, pl);
+                if (cenn_check_cuda(cudaEventRecord(evf, s->stream), "event record", __FILE__, __LINE__)) return 1;
+                if (cenn_check_cuda(cudaStreamWaitEvent(t->side, evf, 0), "stream wait", __FILE__, __LINE__)) return 1;
+                cudaStream_t keep = s->stream; s->stream = t->side;
+                int rc = tc_launch(s, pl);
+                s->stream = keep;
+                return rc; });
+            t->prog.back().flops = pl->flops;
+        } else emit_plan(t, "dgrad", &b->p_dgrad);
+    }
     // single GPU, generator: once this block's wgrad (side stream) and dgrad (this stream, the last reader of its weights)
     // are queued, its slice of the flat vector can take its Adam update on a third stream while the sweep goes on
     // (E6 + G1 hold 92 % of the parameters: ~0.3 ms of HBM-bound work moved off the critical path)
