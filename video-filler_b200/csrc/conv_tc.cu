@@ -98,12 +98,18 @@ int config_gather(cenn_state *s, TcPlan *pl, int BN, int num_kb, int total_tiles
     const int stage_bytes = 128 * 128 + BN * 128;
     const int out_bytes = BN >= 64 ? 128 * BN * 2 : 0;
     const int fixed = 1024 /*align*/ + out_bytes + 176 /*barriers, tmem slot*/ + 68 * 16 + 256 /*tap tables*/ + 3 * BN * 4 + (BN == 32 ? 4 * 32 * 33 * 4 : 0) + 64;
-    int stages = (SMEM_LIMIT - fixed) / stage_bytes;
+    // Two co-resident CTAs per SM when the tile is narrow (BN <= 128: 2 x 2*BN TMEM columns fit): the two single-thread
+    // loops of a CTA (TMA issue, MMA issue) are instruction-latency bound, a second CTA doubles the issue capacity.
+    int per_sm = (BN <= 128 && total_tiles > s->sm_count) ? 2 : 1;
+    if (getenv("CENN_CTAS_PER_SM")) per_sm = atoi(getenv("CENN_CTAS_PER_SM")) == 2 && BN <= 128 ? 2 : 1;
+    const int budget = per_sm == 2 ? (SMEM_LIMIT + 1024) / 2 - 1024 : SMEM_LIMIT;     // 227 KB usable + 1 KB reserved per CTA
+    int stages = (budget - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
-    if (stages < 2) stages = 2;
+    if (stages < 2) { per_sm = 1; stages = (SMEM_LIMIT - fixed) / stage_bytes; if (stages > 8) stages = 8; if (stages < 2) stages = 2; }
     pl->kind = 1; pl->BN = BN; pl->stages = stages;
     pl->smem = (size_t)stages * stage_bytes + fixed;
-    pl->grid[0] = (unsigned)(total_tiles < s->sm_count ? total_tiles : s->sm_count);   // persistent: one CTA per SM
+    const int ctas = s->sm_count * per_sm;
+    pl->grid[0] = (unsigned)(total_tiles < ctas ? total_tiles : ctas);   // persistent
     pl->grid[1] = 1; pl->grid[2] = 1;
     (void)num_kb;
     switch (BN) {
@@ -118,10 +124,13 @@ int config_gather(cenn_state *s, TcPlan *pl, int BN, int num_kb, int total_tiles
 int config_wgrad(TcPlan *pl, int BN, int nkb, dim3 grid) {
     const int stage_bytes = 2 * 8192 + (BN / 64) * 8192;
     const int fixed = 1024 + 8 * (2 * 8 + 1) + 16 + 256;
-    int stages = (SMEM_LIMIT - fixed) / stage_bytes;
+    // two co-resident CTAs per SM (TMEM: BN <= 256 columns each): one's epilogue overlaps the other's main loop and the
+    // single-thread issue loops get twice the capacity
+    const int budget = getenv("CENN_WGRAD_ONE_CTA") ? SMEM_LIMIT : (SMEM_LIMIT + 1024) / 2 - 1024;
+    int stages = (budget - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages > nkb) stages = nkb;
-    if (nkb <= 4 && stages > 2) stages = 2;   // short K (E6 / G1: 256 samples): two co-resident CTAs per SM overlap epilogue and main loop
+    if (stages < 2) { stages = (SMEM_LIMIT - fixed) / stage_bytes; if (stages > 8) stages = 8; if (stages > nkb) stages = nkb; }
     if (stages < 1) stages = 1;
     pl->kind = 2; pl->BN = BN; pl->stages = stages;
     pl->smem = (size_t)stages * stage_bytes + fixed;
@@ -498,7 +507,8 @@ static int wgrad_common(cenn_state *s, TcPlan *pl, tc::WgradParams &p, int num_t
     const int fixed_kb = 10;                                               // prologue + epilogue of a CTA, in k-block units
     int splits = 1; long long best = -1;
     for (int sp = 1; sp <= max_splits && sp <= 4 * s->sm_count; ++sp) {
-        const long long waves = ((long long)tiles * sp + s->sm_count - 1) / s->sm_count;
+        const long long slots = 2LL * s->sm_count;                          // two CTAs per SM
+        const long long waves = ((long long)tiles * sp + slots - 1) / slots;
         const long long cost = waves * ((num_kb_total + sp - 1) / sp + fixed_kb);
         if (best < 0 || cost < best) { best = cost; splits = sp; }
     }

@@ -255,7 +255,7 @@ __device__ __forceinline__ float apply_act(float f, int act, float param) {
 }
 
 template <int BN, bool kProbe>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, BN <= 128 ? 2 : 1)
 gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ GatherGemmParams p, int stages) {
     // kProbe = true compiles in the per-role cycle counters and the stream-dropping flags of tools/gemm_probe.py; the
@@ -935,7 +935,7 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
 // ------------------------------------------------------------------ MN-major wgrad GEMM
 // M tile = 128 rows = 2 row-blocks of 64 (tap, cl-chunk); N tile = BN columns of cs; K = pixels.
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmS, const WgradParams p, int stages) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr uint32_t BOX_BYTES = 64 * 128;            // 64 pixels x 64 channels bf16
