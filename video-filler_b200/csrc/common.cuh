@@ -9,7 +9,7 @@
 #include "../../include/cenn.h"
 
 // One-shot all-reduce over NVLink peer memory (dist.cu / nhwc.cuh xr_sum_inplace): every rank owns a mailbox
-// [2 parities][XR_MAXF floats] + [2] epoch flags; peers' mailboxes are mapped with CUDA IPC.
+// [2 parities][XR_MAXF] 8-byte {value, exchange tag} words; peers' mailboxes are mapped with CUDA IPC.
 static const int XR_MAXF = 16384;       // floats per exchange (2 x 8192 statistics columns)
 static const int XR_MAX_WORLD = 16;
 struct XrCtx {

@@ -119,8 +119,8 @@ __global__ void bn_finalize_kernel(float *__restrict__ stats, int stats_stride, 
 
 // ---------------------------------------------------------------- one-shot all-reduce over NVLink peer memory
 // buf[0..n) <- sum over ranks, in place, by ONE CTA: publish the local values in this rank's mailbox (parity slot of
-// the exchange counter), release a flag, wait for every peer's flag, add the peers' payloads read straight from their
-// HBM over NVLink.  All ranks add in rank order, so replicas get bit-identical sums.  Two parity slots suffice: a
+// the exchange counter) and add the peers' payloads read straight from their HBM over NVLink as soon as they carry
+// this exchange's tag.  All ranks add in rank order, so replicas get bit-identical sums.  Two parity slots suffice: a
 // rank can publish exchange e+2 only after it saw every peer's flag e+1, which a peer raises after reading e.
 // Replaces a NCCL all-reduce launch (~10-25 us at 8 ranks) by ~3 us inside the consumer kernel.
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -132,31 +132,37 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 __device__ __forceinline__ float ld_relaxed_sys(const float *p) {
     float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v;
 }
+// LL-style payload: every float travels as an 8-byte {value, exchange tag} word written with ONE store, so a reader that
+// sees the tag also sees the value -- no flag, no system fence, one NVLink round trip after the slowest peer has written.
+__device__ __forceinline__ void st_ll(uint2 *p, float v, unsigned int tag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2 *p) {
+    uint2 v; asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory"); return v;
+}
 __device__ void xr_sum_inplace(float *__restrict__ buf, int n, const XrCtx &x) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const unsigned long long e = *x.epoch + 1;
-    const int par = (int)(e & 1);
-    float *own = x.data[x.rank] + (size_t)par * XR_MAXF;
-    for (int i = tid; i < n; i += nthr) own[i] = buf[i];
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) st_release_sys(x.flags[x.rank] + par, e);
-    if (tid < x.world && tid != x.rank) {
-        const unsigned long long *f = x.flags[tid] + par;
-        long long t0 = clock64();
-        while (ld_acquire_sys(f) < e) {
-            if (clock64() - t0 > 4000000000LL) { printf("cenn: peer exchange timeout (rank %d waiting for rank %d, epoch %llu)\n", x.rank, tid, e); __trap(); }
-        }
-    }
-    __syncthreads();
-    // all ranks' values are loaded before the first add: up to 16 peer loads in flight per thread (a peer load is ~2 us)
+    const unsigned int tag = (unsigned int)e;           // never 0 within 2^32 exchanges; mailboxes start zeroed
+    const size_t slot = (size_t)(e & 1) * XR_MAXF;
+    uint2 *own = reinterpret_cast<uint2 *>(x.data[x.rank]) + slot;
+    for (int i = tid; i < n; i += nthr) st_ll(own + i, buf[i], tag);
     for (int i = tid; i < n; i += nthr) {
-        float v[XR_MAX_WORLD];
+        uint2 v[XR_MAX_WORLD];
+        unsigned int pending = 0;
 #pragma unroll
-        for (int r = 0; r < XR_MAX_WORLD; ++r) v[r] = r < x.world ? ld_relaxed_sys(x.data[r] + (size_t)par * XR_MAXF + i) : 0.f;
-        float acc = 0.f;
+        for (int r = 0; r < XR_MAX_WORLD; ++r)
+            if (r < x.world && r != x.rank) { v[r] = ld_ll(reinterpret_cast<const uint2 *>(x.data[r]) + slot + i); if (v[r].y != tag) pending |= 1u << r; }
+        long long t0 = clock64();
+        while (pending) {
 #pragma unroll
-        for (int r = 0; r < XR_MAX_WORLD; ++r) acc += v[r];
+            for (int r = 0; r < XR_MAX_WORLD; ++r)
+                if (pending & (1u << r)) { v[r] = ld_ll(reinterpret_cast<const uint2 *>(x.data[r]) + slot + i); if (v[r].y == tag) pending &= ~(1u << r); }
+            if (clock64() - t0 > 4000000000LL) { printf("cenn: peer exchange timeout (rank %d, exchange %llu, pending mask %x)\n", x.rank, e, pending); __trap(); }
+        }
+        float acc = 0.f;                                 // rank order: every replica adds in the same order -> bit-identical sums
+#pragma unroll
+        for (int r = 0; r < XR_MAX_WORLD; ++r) if (r < x.world) acc += (r == x.rank) ? buf[i] : __uint_as_float(v[r].x);
         buf[i] = acc;
     }
     __syncthreads();
