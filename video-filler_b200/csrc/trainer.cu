@@ -146,6 +146,8 @@ struct cenn_trainer {
     cudaStream_t side = nullptr;          // weight-gradient GEMMs run here, beside the dgrad / BN-backward chain of the next layer
     bool serial = false;                  // per-op profiling: everything on the main stream
     std::vector<std::pair<int64_t, int64_t>> g_buckets;   // (offset, count) of G's gradient ranges reduced on the bulk communicator
+    std::vector<std::pair<int64_t, int64_t>> d_buckets;   // same for D (second sweep of the step only: the first one just accumulates)
+    bool d_bucket_sweep = false;
 };
 
 namespace {
@@ -593,10 +595,11 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         }
         // data parallel, generator: the big weight gradients start their all-reduce now, on the bulk communicator's stream,
         // and overlap the rest of the backward sweep (E6 + G1 are 92 % of the 285 MB)
-        if (dp && s->comm2 && &net == &t->G && b->w_count >= (1 << 20)) {
+        const bool bucket_g = &net == &t->G && b->w_count >= (1 << 20), bucket_d = &net == &t->D && t->d_bucket_sweep && b->w_count >= (1 << 18);
+        if (dp && s->comm2 && (bucket_g || bucket_d)) {
             cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
             float *ptr = grad + b->w_off; int64_t cnt = b->w_count;
-            t->g_buckets.push_back({b->w_off, b->w_count});
+            (bucket_g ? t->g_buckets : t->d_buckets).push_back({b->w_off, b->w_count});
             emit(t, "grad_bucket_ar", [t, s, ev, ptr, cnt]() {
                 if (cenn_check_cuda(cudaEventRecord(ev, t->serial ? s->stream : t->side), "event record", __FILE__, __LINE__)) return 1;
                 if (cenn_check_cuda(cudaStreamWaitEvent(s->comm_stream, ev, 0), "stream wait", __FILE__, __LINE__)) return 1;
@@ -762,7 +765,7 @@ int build_program(T *t) {
     Block *headD = &D.blocks.back();
     Block *lastG = &G.blocks.back();
     t->prog.clear();
-    t->g_buckets.clear();
+    t->g_buckets.clear(); t->d_buckets.clear();
     t->flops_per_step = 0;
     // -- inputs: fp32 NCHW (+ uint8 mask) -> NHWC bf16
     emit(t, "convert_inputs", [t, s, video]() {
@@ -817,9 +820,24 @@ int build_program(T *t) {
     }
     for (size_t i = 0; i < D.blocks.size(); ++i) emit_forward(t, D, i, true);
     emit_bce(t, headD, 0.f, CENN_LOSS_ERRD_FAKE, true);
+    t->d_bucket_sweep = true;      // D's gradients are complete after this sweep: the big blocks start their all-reduce as they finish
     for (size_t i = D.blocks.size(); i-- > 0;) emit_backward(t, D, i, true, i > 0 || c.dead_dgrad);
+    t->d_bucket_sweep = false;
     emit_fold_gbias(t, D);
-    emit(t, "gradD_sync", []() { return 0; }, D.grad, D.nparam);
+    if (t->d_buckets.empty()) emit(t, "gradD_sync", []() { return 0; }, D.grad, D.nparam);
+    else {
+        std::vector<std::pair<int64_t, int64_t>> bk = t->d_buckets, rest;
+        std::sort(bk.begin(), bk.end());
+        int64_t cur = 0;
+        for (auto &x : bk) { if (x.first > cur) rest.push_back({cur, x.first - cur}); cur = x.first + x.second; }
+        if (D.nparam > cur) rest.push_back({cur, D.nparam - cur});
+        cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
+        float *g = D.grad;
+        emit(t, "gradD_sync", [s, rest, g, ev]() {
+            for (auto &x : rest) if (cenn_dist_all_reduce_on(s, g + x.first, x.second, 0, s->stream)) return 1;
+            if (cenn_check_cuda(cudaEventRecord(ev, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
+            return cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev, 0), "stream wait", __FILE__, __LINE__); });
+    }
     emit_adam_step(t, D);
     emit_adam(t, D);
     emit_weight_prep(t, D);
