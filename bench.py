@@ -158,7 +158,7 @@ def main():
     from video_filler_b200 import synth, train, util
     T.state(local_rank)
     api, st = T.api(), T.state()
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.Stream(priority=-1)      # the step's critical path; the executor's side streams run at lowest priority
     api.cenn_set_stream(st, C.c_void_p(stream.cuda_stream))
 
     B = args.batch

@@ -62,7 +62,9 @@ int cenn_init(int device, cenn_state **out) {
     cenn_state *s = new cenn_state();
     s->device = device;
     s->sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    // the compute stream carries the critical path of the step program: highest priority, so that its (short) kernels are
+    // dispatched ahead of the side streams' queued GEMM CTAs
+    { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&s->own_stream, cudaStreamNonBlocking, hi)); }
     s->stream = s->own_stream;
     CK(cudaMalloc(&s->red, RED_SLOTS * sizeof(double)));
     CK(cudaMemset(s->red, 0, RED_SLOTS * sizeof(double)));

@@ -1034,9 +1034,11 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     // G's output must match D's input tensor exactly (same NHWC padding) for the d2d hand-over
     const Tensor &go = t->G.blocks.back().a;
     if (go.H != dsize || go.Cp != t->D.input.Cp) { cenn_set_error("internal: generator output %dx%dx%d does not match discriminator input %dx%dx%d", go.H, go.W, go.Cp, dsize, dsize, t->D.input.Cp); cenn_trainer_destroy(t); return 1; }
-    if (cudaStreamCreateWithFlags(&t->side3, cudaStreamNonBlocking) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
-    if (cudaStreamCreateWithFlags(&t->side2, cudaStreamNonBlocking) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
-    if (cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // side streams: lowest priority (the critical path is on the state's stream)
+    if (cudaStreamCreateWithPriority(&t->side3, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
+    if (cudaStreamCreateWithPriority(&t->side2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
+    if (cudaStreamCreateWithPriority(&t->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
     if (build_program(t)) { cenn_trainer_destroy(t); return 1; }
     int64_t before = s->launches;
     (void)before;
@@ -1242,10 +1244,17 @@ int cenn_trainer_profile_step(cenn_trainer *t, const float *a, const float *b, c
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto &e : ev) CK(cudaEventCreate(&e));
     t->cur_a = a; t->cur_b = b; t->cur_m = mask;
-    t->serial = true;                 // per-op timing: no side stream
+    static const bool timeline = getenv("CENN_TIMELINE") != nullptr;   // keep the side streams: events then show the MAIN stream's time line
+    t->serial = !timeline;            // per-op timing: no side stream
     CK(cudaEventRecord(ev[0], st));
     int rc = 0;
-    for (size_t i = 0; i < n && !rc; ++i) { rc = t->prog[i].fn() || reduce_sync_point(t, t->prog[i]); CK(cudaEventRecord(ev[i + 1], st)); }
+    for (size_t i = 0; i < n && !rc; ++i) {
+        cudaStream_t keep = t->s->stream;
+        if (t->prog[i].chain == 1 && !t->serial) t->s->stream = t->side2;
+        rc = t->prog[i].fn() || reduce_sync_point(t, t->prog[i]);
+        t->s->stream = keep;
+        CK(cudaEventRecord(ev[i + 1], st));
+    }
     CK(cudaStreamSynchronize(st));
     t->serial = false;
     std::string all;
