@@ -287,6 +287,13 @@ def main():
                             "kernel": "tc::gather_gemm_kernel / tc::wgrad_gemm_kernel (all conv fprop/dgrad/wgrad launches)",
                             "launches_per_step": tc_n, "share_of_step": tc_ms / prof["total_ms"], "peak_source": peak_src + " bf16_tflops_sustained",
                             "by_op_ms": prof["by_op"]}
+    if prof and rank == 0:
+        # the dominant bandwidth kernel (fused Adam + bf16 operand refresh over the flat parameter vectors): 30 B per parameter
+        adam_ms = prof["by_op"].get("adam", 0.0) + prof["by_op"].get("adam_early", 0.0)
+        if adam_ms > 0:
+            gbs = 30.0 * (nG + nD) / (adam_ms * 1e-3) / 1e9
+            line["roofline_hbm"] = {"bound": "hbm", "kernel": "nhwc::adam_bf16_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                    "traffic": None, "bytes_per_param": 30, "params": int(nG + nD), "peak_source": peak_src + " hbm_gbs"}
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         rate, sec = cpu_port_step_rate(64, 1, 0, threads)
