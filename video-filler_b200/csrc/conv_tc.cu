@@ -400,7 +400,7 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
     const bool thin = Clp == 4 || Clp == 16;
     if (w < 8 || h < 8 || Csp % 64 != 0 || !(thin || Clp % 64 == 0) || (thin && ep.stats) || getenv("CENN_NO_PATCH")) return 2;
     const int bh = pow2_le(h, 16), bn = 16 / bh;
-    const int BN = thin ? 16 : (Clp % 128 == 0 ? 128 : 64);
+    const int BN = thin ? 16 : ((Clp % 128 == 0 && !getenv("CENN_PATCH_BN64")) ? 128 : 64);
     REQUIRE(cl_rows >= Cl, "tc_dgrad_patch: cl_rows (%d) too small for Cl %d", cl_rows, Cl);
     {   // S patch: dims (c, x, n, y) so that shared memory holds [y][n][x] rows of 64 channels
         uint64_t d[4] = {(uint64_t)Csp, (uint64_t)w, (uint64_t)N, (uint64_t)h};
