@@ -50,7 +50,8 @@ int cenn_check_cuda(cudaError_t e, const char *what, const char *file, int line)
 void *cenn_workspace(cenn_state *s, size_t bytes);   // stream-ordered reuse; grows with cudaMalloc
 void *cenn_workspace2(cenn_state *s, size_t bytes);
 int cenn_dist_all_reduce_on(cenn_state *s, void *buf, int64_t count, int is_double, cudaStream_t stream);
-int cenn_dist_all_reduce_bulk(cenn_state *s, float *buf, int64_t count);   // second communicator, s->comm_stream
+int cenn_dist_all_reduce_bulk(cenn_state *s, float *buf, int64_t count);
+int cenn_dist_group(int begin);       // ncclGroupStart / ncclGroupEnd   // second communicator, s->comm_stream
 
 #define CK(expr) do { if (cenn_check_cuda((expr), #expr, __FILE__, __LINE__)) return 1; } while (0)
 #define CK_LAUNCH(s) do { (s)->launches++; if (cenn_check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)) return 1; } while (0)

@@ -62,6 +62,11 @@ int cenn_dist_all_reduce_on(cenn_state *s, void *buf, int64_t count, int is_doub
     return nccl_check(g_nccl.all_reduce(buf, buf, (size_t)count, is_double ? NCCL_FLOAT64 : NCCL_FLOAT32, NCCL_SUM, s->comm, stream), "ncclAllReduce");
 }
 
+// several small all-reduces as ONE NCCL launch (the leftover ranges of a gradient vector)
+int cenn_dist_group(int begin) {
+    if (!g_nccl.handle || !g_nccl.group_start || !g_nccl.group_end) return 0;
+    return nccl_check(begin ? g_nccl.group_start() : g_nccl.group_end(), begin ? "ncclGroupStart" : "ncclGroupEnd");
+}
 int cenn_dist_all_reduce_bulk(cenn_state *s, float *buf, int64_t count) {
     if (!s->comm2 || !s->comm_stream) { cenn_set_error("cenn_dist_all_reduce_bulk: no bulk communicator"); return 1; }
     if (count <= 0) return 0;

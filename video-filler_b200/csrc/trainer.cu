@@ -638,10 +638,12 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         t->g_early.push_back({off, cnt});
         emit(t, "adam_early", [t, s, n, e1, e2, off, cnt, beta1, dp_bulk]() {
             cudaStream_t st = s->stream;
-            if (dp_bulk) {                           // comm_stream: [wait wgrad] all-reduce -> [wait dgrad] Adam; joined at gradG_sync
+            if (dp_bulk) {                           // third stream: waits for this block's bucket all-reduce (comm_stream) and its dgrad
                 if (cenn_check_cuda(cudaEventRecord(e1, s->stream), "event record", __FILE__, __LINE__)) return 1;
-                if (cenn_check_cuda(cudaStreamWaitEvent(s->comm_stream, e1, 0), "stream wait", __FILE__, __LINE__)) return 1;
-                st = s->comm_stream;
+                if (cenn_check_cuda(cudaEventRecord(e2, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;   // after the all-reduce
+                if (cenn_check_cuda(cudaStreamWaitEvent(t->side3, e1, 0), "stream wait", __FILE__, __LINE__)) return 1;
+                if (cenn_check_cuda(cudaStreamWaitEvent(t->side3, e2, 0), "stream wait", __FILE__, __LINE__)) return 1;
+                st = t->side3;                       // the next bucket's all-reduce does not queue behind this Adam
             } else if (!t->serial) {
                 if (cenn_check_cuda(cudaEventRecord(e1, s->stream), "event record", __FILE__, __LINE__)) return 1;   // after dgrad
                 if (cenn_check_cuda(cudaEventRecord(e2, t->side), "event record", __FILE__, __LINE__)) return 1;     // after wgrad
@@ -834,7 +836,9 @@ int build_program(T *t) {
         cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
         float *g = D.grad;
         emit(t, "gradD_sync", [s, rest, g, ev]() {
+            if (cenn_dist_group(1)) return 1;
             for (auto &x : rest) if (cenn_dist_all_reduce_on(s, g + x.first, x.second, 0, s->stream)) return 1;
+            if (cenn_dist_group(0)) return 1;
             if (cenn_check_cuda(cudaEventRecord(ev, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
             return cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev, 0), "stream wait", __FILE__, __LINE__); });
     }
@@ -880,10 +884,11 @@ int build_program(T *t) {
     emit_adam_step(t, G);          // optimState.t / step size first: the big blocks are updated as soon as their gradient exists
     t->g_early.clear();
     for (size_t i = G.blocks.size(); i-- > 0;) emit_backward(t, G, i, true, i > 0 || c.dead_dgrad);
-    if (!t->g_early.empty() && c.world_size <= 1) {
+    if (!t->g_early.empty()) {
         cudaEvent_t evj; cudaEventCreateWithFlags(&evj, cudaEventDisableTiming); t->events.push_back(evj);
-        emit(t, "join_adam", [t, s, evj]() {
-            if (t->serial) return 0;
+        const bool dp_bulk = c.world_size > 1 && s->comm2 != nullptr;    // data parallel: the early Adams always run on the third stream
+        emit(t, "join_adam", [t, s, evj, dp_bulk]() {
+            if (t->serial && !dp_bulk) return 0;
             if (cenn_check_cuda(cudaEventRecord(evj, t->side3), "event record", __FILE__, __LINE__)) return 1;
             return cenn_check_cuda(cudaStreamWaitEvent(s->stream, evj, 0), "stream wait", __FILE__, __LINE__); });
     }
@@ -899,7 +904,9 @@ int build_program(T *t) {
         cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
         float *g = G.grad;
         emit(t, "gradG_sync", [s, rest, g, ev]() {
+            if (cenn_dist_group(1)) return 1;
             for (auto &x : rest) if (cenn_dist_all_reduce_on(s, g + x.first, x.second, 0, s->stream)) return 1;
+            if (cenn_dist_group(0)) return 1;
             if (cenn_check_cuda(cudaEventRecord(ev, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
             return cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev, 0), "stream wait", __FILE__, __LINE__); });
     }
