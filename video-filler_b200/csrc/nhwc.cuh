@@ -64,24 +64,32 @@ __global__ void __launch_bounds__(256) to_nchw_kernel(const bf16 *__restrict__ s
         dst[i] = __bfloat162float(src[((int64_t)n * HW + pix) * Cp + c]);
     }
 }
-// explicit im2col of a thin tensor L [N,2h,2w,Cp] (Cp = 4 or 16): col[pix][(tap, c)] for the 4x4/s2/p1 window
+// explicit im2col of a thin tensor L [N,2h,2w,Cp] (Cp = 4 or 16): col[pix][(tap, c)] for the 4x4/s2/p1 window.
+// One thread moves one window ROW (4 taps = 4 consecutive input pixels): 8-byte loads (the row starts at an odd pixel),
+// 16-byte stores (the destination row segment is 32-byte aligned).
 template <int CP>
 __global__ void __launch_bounds__(256) im2col_kernel(const bf16 *__restrict__ L, bf16 *__restrict__ col, int N, int h, int w) {
-    typedef typename std::conditional<CP == 4, uint2, uint4>::type vec_t;     // 4 bf16 = 8 B ; 8 bf16 = 16 B
-    constexpr int VPP = CP * 2 / (int)sizeof(vec_t);                         // vectors per pixel
-    int64_t total = (int64_t)N * h * w * 16 * VPP;
+    constexpr int V8 = CP / 4;                                   // 8-byte vectors per pixel
+    const int64_t total = (int64_t)N * h * w * 4;                // (pixel, window row u)
     const int H2 = 2 * h, W2 = 2 * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int vi = (int)(i % VPP);
-        int64_t t = i / VPP;
-        int tap = (int)(t % 16);
-        int64_t pix = t / 16;
-        int ox = (int)(pix % w), oy = (int)((pix / w) % h), n = (int)(pix / ((int64_t)w * h));
-        int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
-        vec_t v = {};
-        if ((unsigned)iy < (unsigned)H2 && (unsigned)ix < (unsigned)W2)
-            v = reinterpret_cast<const vec_t *>(L + (((int64_t)n * H2 + iy) * W2 + ix) * CP)[vi];
-        reinterpret_cast<vec_t *>(col + (pix * 16 + tap) * CP)[vi] = v;
+        const int u = (int)(i & 3);
+        const int64_t pix = i >> 2;
+        const int ox = (int)(pix % w), oy = (int)((pix / w) % h), n = (int)(pix / ((int64_t)w * h));
+        const int iy = 2 * oy - 1 + u, ix0 = 2 * ox - 1;
+        uint2 v[4 * V8];
+        const bool row_ok = (unsigned)iy < (unsigned)H2;
+        const uint2 *src = reinterpret_cast<const uint2 *>(L + (((int64_t)n * H2 + (row_ok ? iy : 0)) * W2) * CP);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int ix = ix0 + t;
+            const bool ok = row_ok && (unsigned)ix < (unsigned)W2;
+#pragma unroll
+            for (int k = 0; k < V8; ++k) v[t * V8 + k] = ok ? __ldg(src + (int64_t)ix * V8 + k) : make_uint2(0u, 0u);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(col + (pix * 16 + u * 4) * CP);
+#pragma unroll
+        for (int k = 0; k < 2 * V8; ++k) dst[k] = make_uint4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
     }
 }
 

@@ -425,7 +425,7 @@ void emit_im2col(T *t, const Tensor &L, bf16 *col, int h, int w) {
     cenn_state *s = t->s;
     Tensor Lc = L;
     emit(t, "im2col", [s, Lc, col, h, w]() {
-        int64_t total = (int64_t)Lc.N * h * w * 16 * (Lc.Cp == 4 ? 1 : Lc.Cp / 8);
+        int64_t total = (int64_t)Lc.N * h * w * 4;            // one thread per (pixel, window row)
         if (Lc.Cp == 4) nhwc::im2col_kernel<4><<<grid1d(s, total), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
         else if (Lc.Cp == 16) nhwc::im2col_kernel<16><<<grid1d(s, total), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
         else { cenn_set_error("im2col: unsupported thin channel count %d", Lc.Cp); return 1; }
