@@ -54,6 +54,27 @@ __global__ void __launch_bounds__(256) to_nhwc_kernel(const T *__restrict__ src,
         }
     }
 }
+// fast path for 3-channel images (Cp == 4, HW % 4 == 0): one thread converts 4 consecutive pixels -- float4 loads per
+// channel plane, two 16-byte stores
+__global__ void __launch_bounds__(256) to_nhwc4_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, int N, int C, int HW) {
+    const int64_t total = (int64_t)N * HW / 4;
+    const int q = HW / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / q), p4 = (int)(i - (int64_t)n * q);
+        float4 ch[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ch[c] = c < C ? __ldg(reinterpret_cast<const float4 *>(src + ((int64_t)n * C + c) * HW) + p4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float px[4][4] = {{ch[0].x, ch[1].x, ch[2].x, ch[3].x}, {ch[0].y, ch[1].y, ch[2].y, ch[3].y}, {ch[0].z, ch[1].z, ch[2].z, ch[3].z}, {ch[0].w, ch[1].w, ch[2].w, ch[3].w}};
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(px[k][0], px[k][1]), h1 = __floats2bfloat162_rn(px[k][2], px[k][3]);
+            w[2 * k] = *reinterpret_cast<uint32_t *>(&h0); w[2 * k + 1] = *reinterpret_cast<uint32_t *>(&h1);
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(dst + i * 16);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]); o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
 // NHWC bf16 -> NCHW fp32 (results / debugging)
 __global__ void __launch_bounds__(256) to_nchw_kernel(const bf16 *__restrict__ src, float *__restrict__ dst, int N, int C, int HW, int Cp) {
     int64_t total = (int64_t)N * C * HW;

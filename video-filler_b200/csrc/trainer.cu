@@ -772,8 +772,14 @@ int build_program(T *t) {
     // -- inputs: fp32 NCHW (+ uint8 mask) -> NHWC bf16
     emit(t, "convert_inputs", [t, s, video]() {
         const Tensor &a = t->real_ctx, &b = t->real_aux;
-        nhwc::to_nhwc_kernel<float><<<grid1d(s, a.pix()), 256, 0, s->stream>>>(t->cur_a, a.p, a.N, a.C, a.H * a.W, a.Cp); KLAUNCH(s);
-        nhwc::to_nhwc_kernel<float><<<grid1d(s, b.pix()), 256, 0, s->stream>>>(t->cur_b, b.p, b.N, b.C, b.H * b.W, b.Cp); KLAUNCH(s);
+        for (const Tensor *x : {&a, &b}) {
+            const float *src = x == &a ? t->cur_a : t->cur_b;
+            if (x->Cp == 4 && (x->H * x->W) % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+                nhwc::to_nhwc4_kernel<<<grid1d(s, x->pix() / 4), 256, 0, s->stream>>>(src, x->p, x->N, x->C, x->H * x->W);
+            else
+                nhwc::to_nhwc_kernel<float><<<grid1d(s, x->pix()), 256, 0, s->stream>>>(src, x->p, x->N, x->C, x->H * x->W, x->Cp);
+            KLAUNCH(s);
+        }
         if (video) { const Tensor &m = t->mask; nhwc::to_nhwc_kernel<uint8_t><<<grid1d(s, m.pix()), 256, 0, s->stream>>>(t->cur_m, m.p, m.N, m.C, m.H * m.W, m.Cp); KLAUNCH(s); }
         return cenn_check_cuda(cudaMemsetAsync(t->loss_acc, 0, 8 * sizeof(double), s->stream), "memset", __FILE__, __LINE__); });
     // ================= fDx (train.lua:278-350) =================
