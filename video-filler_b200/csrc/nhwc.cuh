@@ -644,6 +644,36 @@ __global__ void __launch_bounds__(256) blend_overlap_kernel(const bf16 *__restri
     l = block_sum(l, sh);
     if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, l * inv_n);
 }
+// Cp == 4 fast path of blend_overlap: one thread handles two pixels (16-byte vectors of df, x, t and g)
+__global__ void __launch_bounds__(256) blend_overlap4_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
+        bf16 *__restrict__ g, int64_t npix, int H, int W, int C, int ov, float a, float w_in, float w_ring, float two_over_n,
+        double inv_n, double *__restrict__ loss_acc) {
+    __shared__ double sh[32];
+    float l = 0.f;
+    const int64_t npair = npix / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += (int64_t)gridDim.x * blockDim.x) {
+        float fd[8] = {}, fx[8], ft[8], r[8];
+        if (df) unpack8(__ldg(reinterpret_cast<const uint4 *>(df) + i), fd);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(x) + i), fx); unpack8(__ldg(reinterpret_cast<const uint4 *>(t) + i), ft);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t p = 2 * i + h;
+            const int xx = (int)(p % W), yy = (int)((p / W) % H);
+            const float wgt = (yy >= ov && yy < H - ov && xx >= ov && xx < W - ov) ? w_in : w_ring;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = 4 * h + c;
+                float d = fx[k] - ft[k];
+                if (c >= C) d = 0.f;
+                l = fmaf(d, d, l);
+                r[k] = c < C ? fmaf(fd[k], a, wgt * (d * two_over_n)) : 0.f;
+            }
+        }
+        reinterpret_cast<uint4 *>(g)[i] = pack8(r);
+    }
+    double ld = block_sum((double)l, sh);
+    if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, ld * inv_n);
+}
 // video variant (train_vid_weighted.lua:485-528): g = a*df + (wtl2 * (m(1-lam)+lam) + wtgdl) * 2(x-t)/n
 __global__ void __launch_bounds__(256) blend_masked_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
         const bf16 *__restrict__ mask, bf16 *__restrict__ g, int64_t total, int Cp, int C, float a, float wtl2, float lambda, float wtgdl,

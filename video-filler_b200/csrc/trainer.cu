@@ -868,6 +868,10 @@ int build_program(T *t) {
             int ov = c.overlapPred;
             if (c.wtl2 != 0.f)
                 emit(t, "blend_overlap", [s, df, fake_in, real, gout, ov, a, w_in, w_ring, n, acc]() {
+                    if (fake_in.Cp == 4 && fake_in.pix() % 2 == 0)
+                        nhwc::blend_overlap4_kernel<<<grid1d(s, fake_in.pix() / 2, 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
+                            fake_in.W, fake_in.C, ov, a, w_in, w_ring, (float)(2.0 / n), 1.0 / n, acc);
+                    else
                     nhwc::blend_overlap_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
                         fake_in.W, fake_in.Cp, fake_in.C, ov, a, w_in, w_ring, (float)(2.0 / n), 1.0 / n, acc);
                     KLAUNCH(s); return 0; });
