@@ -23,7 +23,7 @@ dm = None
 if m is not None:
     import ctypes as C
     dm = C.c_void_p(); T.api().cenn_malloc(T.state(), m.size, C.byref(dm)); T.api().cenn_copy_h2d(T.state(), dm, m.ctypes.data_as(C.c_void_p), m.size); dm = dm.value
-for _ in range(3):
+for _ in range(int(os.environ.get("STEPS", "3"))):
     trn.step_device(da.ptr, db.ptr, dm)
 prof = trn.profile_step(da.ptr, db.ptr, dm, repeats=5)
 lines = ["%4s %-16s %9s %10s %9s" % ("#", "op", "ms", "GFLOP", "TFLOP/s")]
