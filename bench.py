@@ -25,6 +25,10 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "inpaintCenter 128x128 G+D training step, batch 256/GPU, nBottleneck 4000, overlapPred 4, wtl2 0.999"
 STEP_GFLOP_PER_SAMPLE = 3.552          # 3 F_G + 7 F_D per sample
+# non-default workloads (--workload): BASELINE.json configs[2] per GPU and configs[4]
+WORKLOAD_VIDEO = "train_vid_weighted 128x128 clips, predLen 4 (12 stacked channels), mask-weighted L2 + GDL (wtgdl %s), batch %d/GPU"
+VIDEO_GFLOP_PER_SAMPLE = 5.242         # cfg3, 3 F_G + 7 F_D per sample
+INFER_GFLOP_PER_TILE = 0.853           # cfg5 generator forward per 128x128 tile
 
 
 def opt_for(batch, variant="image"):
@@ -123,6 +127,115 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_infer(args, torch, dist, api, st, stream, rank, local_rank, world):
+    """BASELINE.json configs[4]: eval-mode generator over 128x128 tiles (test_vid_wholeim.lua:159-205), batch 1..1024 tiles per
+    forward, tiles resident in HBM (fp32 NCHW in / out, converted inside the timed region); replicas only at N > 1 (no collective).
+    e2e = the whole device-side sweep of 32 frames of 360x480 (12 tiles per frame) from host frames to host composites."""
+    from video_filler_b200 import infer, models, util
+    import video_filler_b200.tensor as T
+    opt = models.default_opt("video", predLen=1)
+    rng = np.random.default_rng(1234)
+    flat = util.params_flat(util.weights_init(util.describe_netG(opt), rng))
+    batches = [args.batch] if args.batch else [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024]
+    hbm, tf_burst, tf_sus, peak_src = peaks()
+    sweep, stats = [], None
+    sampler = ClockSampler(local_rank); sampler.start(); sampler.mark_begin()
+    launches0 = C.c_int64(); api.cenn_kernel_launches(st, C.byref(launches0))
+    with torch.cuda.stream(stream):
+        for Bt in batches:
+            eng = infer.Inpainter(opt, Bt)
+            if stats is None:
+                n_stats = eng.counts()[1]
+                srng = np.random.default_rng(7)
+                stats = np.concatenate([srng.normal(0, 0.1, n_stats // 2), srng.uniform(0.5, 1.5, n_stats - n_stats // 2)]).astype(np.float32)
+                # [mean(C), var(C)] per layer: keep every variance slot positive whatever the interleaving
+                stats = np.abs(stats) + 0.25
+            eng.load(flat, stats)
+            xs = [T.CudaTensor.from_numpy(rng.uniform(-1, 1, (Bt, 3, 128, 128)).astype(np.float32)) for _ in range(2)]
+            y = T.CudaTensor.from_numpy(np.zeros((Bt, 3, 128, 128), np.float32))
+            for i in range(max(3, args.warmup)):
+                eng.forward_device(xs[i % 2].ptr, y.ptr, Bt)
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(args.steps):
+                eng.forward_device(xs[i % 2].ptr, y.ptr, Bt)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t_ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if dist:
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            ms = float(t_ms.item()) / args.steps
+            sweep.append({"batch": Bt, "latency_ms": ms, "tiles_per_s": Bt * world / (ms * 1e-3),
+                          "tflops": INFER_GFLOP_PER_TILE * 1e-3 * Bt / (ms * 1e-3)})
+            eng.close()
+            del xs, y
+        launches1 = C.c_int64(); api.cenn_kernel_launches(st, C.byref(launches1))
+        clocks = sampler.finish()
+        # ---- end to end: host frames -> device sweep -> host composites
+        P, inh, inw = 32, 360, 480
+        def pinned(shape):
+            n = int(np.prod(shape)); ptr = C.c_void_p()
+            api.cenn_host_alloc(st, n * 4, C.byref(ptr))
+            return np.ctypeslib.as_array((C.c_float * n).from_address(ptr.value)).reshape(shape)
+        frames = pinned((P, 3, inh, inw)); frames[:] = rng.uniform(0, 1, frames.shape)
+        result = {"inpaint": pinned((P, 3, 384, 512))}
+        mask = np.zeros((inh, inw), bool); mask[120:220, 180:330] = True
+        eng = infer.Inpainter(opt, 12 * P)
+        eng.load(flat, stats)
+        sweep_once = lambda: eng.sweep(frames, mask, opt["maskValue"], want=("inpaint",), buffers=result)
+        for _ in range(2):
+            sweep_once()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        reps = max(3, min(20, args.steps))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sweep_once()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        e2e_s = (time.perf_counter() - t0) / reps
+        eng.close()
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        sys.stdout.flush(); os._exit(0)
+    best = max(sweep, key=lambda r: r["tiles_per_s"])
+    line = {
+        "metric": "inference tiles/sec (eval-mode generator forward, 128x128 tiles)", "value": best["tiles_per_s"], "unit": "tiles/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": best["latency_ms"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "test_vid_wholeim tile forward, inputLen 1, nBottleneck 4000; batch sweep %s tiles/GPU, value = best batch (%d)" % (batches, best["batch"]),
+                   "parallelism": "replicas x%d (no collective)" % world,
+                   "l2": "small batches are L2-resident by nature (latency case); from 64 tiles up the activations exceed the 126 MB L2"},
+        "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks, "sweep": sweep,
+        "e2e": {"value": 12 * P * world / e2e_s, "unit": "tiles/s", "frames_per_s": P * world / e2e_s, "ms_per_sweep": e2e_s * 1e3,
+                "workload": "cenn_inpainter_sweep_host: %d frames of %dx%d (12 tiles each) pinned host frames -> device sweep -> pinned host inpaintImages" % (P, inh, inw),
+                "h2d_bytes_per_step": int(frames.nbytes + mask.size), "d2h_bytes_per_step": int(P * 3 * 384 * 512 * 4)},
+        "roofline": {"bound": "tensor", "achieved": best["tflops"], "peak": tf_sus, "unit": "TFLOP/s", "frac": best["tflops"] / tf_sus, "traffic": None,
+                     "kernel": "whole forward (12 tcgen05 GEMM launches + layout conversion) at the best batch", "peak_source": peak_src + " bf16_tflops_sustained"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import nets as onets
+        from oracle import step as ostep
+        torch.set_num_threads(os.cpu_count() or 1)
+        orc = ostep.StepOracle(onets.default_opt("video", predLen=1, batchSize=8), seed=1234, dtype=np.float32)
+        orc.netG.evaluate()
+        x = rng.uniform(-1, 1, (8, 3, 128, 128)).astype(np.float32)
+        orc.netG.forward(x)
+        t0 = time.perf_counter(); orc.netG.forward(x); dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 8 / dt, "unit": "tiles/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "one 8-tile eval forward of the oracle generator, %.2f s" % dt}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    sys.stdout.flush(); os._exit(0)
+
+
 def wrap_device(ptr, count, dtype, torch):
     """A torch view of a raw device buffer (for torch.distributed collectives on the executor's buffers)."""
     class _Holder:
@@ -138,11 +251,17 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default 256 image / 64 video)")
+    ap.add_argument("--workload", default="image", choices=["image", "video", "infer"],
+                    help="image = BASELINE.json configs[1] (the headline); video = configs[2] per GPU; infer = configs[4] sweep")
+    ap.add_argument("--wtgdl", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    video = args.workload == "video"
+    if args.batch is None and args.workload != "infer":
+        args.batch = 64 if video else 256
 
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -161,8 +280,12 @@ def main():
     stream = torch.cuda.Stream(priority=-1)      # the step's critical path; the executor's side streams run at lowest priority
     api.cenn_set_stream(st, C.c_void_p(stream.cuda_stream))
 
+    if args.workload == "infer":
+        return run_infer(args, torch, dist, api, st, stream, rank, local_rank, world)
     B = args.batch
-    opt = opt_for(B)
+    opt = opt_for(B, "video" if video else "image")
+    if video:
+        opt["wtgdl"] = args.wtgdl
     if world > 1:
         # library-owned NCCL communicator: rank 0 creates the id, torch.distributed carries it to the other ranks
         idbuf = np.zeros(128, np.uint8)
@@ -180,24 +303,35 @@ def main():
 
     trn.set_params(0, util.params_flat(util.weights_init(util.describe_netG(opt), rng)))
     trn.set_params(1, util.params_flat(util.weights_init(util.describe_netD(opt), rng)))
-    assert nG == 71118691 + 2 * (64 + 128 + 256 + 512 + 4000 + 512 + 256 + 128 + 64) and nD > 2764737
+    assert video or (nG == 71118691 + 2 * (64 + 128 + 256 + 512 + 4000 + 512 + 256 + 128 + 64) and nD > 2764737)
 
     drng = np.random.default_rng(1000 + rank)
     n_batches = 2
     host = []
     for _ in range(n_batches):
-        ctx, center = synth.image_batch(B, 128, 4, drng)
+        if video:
+            ctx, center, mask = synth.video_batch(B, 12, 128, opt["maskValue"], drng)
+        else:
+            ctx, center = synth.image_batch(B, 128, 4, drng)
+            mask = None
         pa, pb = C.c_void_p(), C.c_void_p()
         api.cenn_host_alloc(st, ctx.nbytes, C.byref(pa)); api.cenn_host_alloc(st, center.nbytes, C.byref(pb))
         ha = np.ctypeslib.as_array((C.c_float * ctx.size).from_address(pa.value)); ha[:] = ctx.ravel()
         hb = np.ctypeslib.as_array((C.c_float * center.size).from_address(pb.value)); hb[:] = center.ravel()
         da, db = T.CudaTensor.from_numpy(ctx), T.CudaTensor.from_numpy(center)
-        host.append((ha, hb, da, db, ctx.nbytes + center.nbytes))
+        hm, dm, nbytes = None, None, ctx.nbytes + center.nbytes
+        if mask is not None:
+            pm = C.c_void_p(); api.cenn_host_alloc(st, mask.nbytes, C.byref(pm))
+            hm = np.ctypeslib.as_array((C.c_uint8 * mask.size).from_address(pm.value)); hm[:] = mask.ravel()
+            dmp = C.c_void_p(); api.cenn_malloc(st, mask.nbytes, C.byref(dmp)); api.cenn_copy_h2d(st, dmp, pm, mask.nbytes)
+            dm = dmp.value
+            nbytes += mask.nbytes
+        host.append((ha, hb, da, db, nbytes, hm, dm))
 
     def step_device(i):
         # world > 1: the executor all-reduces BN statistics, gradients and losses itself (NCCL, inside its CUDA graph)
-        _, _, da, db, _ = host[i % n_batches]
-        trn.step_device(da.ptr, db.ptr)
+        h = host[i % n_batches]
+        trn.step_device(h[2].ptr, h[3].ptr, h[6])
 
     losses = None
     sampler = ClockSampler(local_rank); sampler.start()
@@ -224,7 +358,7 @@ def main():
         # ---- end-to-end: host buffers in, losses out, every step (single-process API call)
         e2e_ms = None
         for i in range(2):
-            trn.step_host(host[i % n_batches][0], host[i % n_batches][1])
+            trn.step_host(host[i % n_batches][0], host[i % n_batches][1], host[i % n_batches][5])
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
@@ -232,7 +366,7 @@ def main():
         # public pipelined API: every step copies ITS inputs from pinned host memory and its losses are read back;
         # the copy of step k+1 overlaps the compute of step k, the losses of step k are read while step k+1 runs
         for i in range(args.steps):
-            trn.step_host_async(host[i % n_batches][0], host[i % n_batches][1])
+            trn.step_host_async(host[i % n_batches][0], host[i % n_batches][1], host[i % n_batches][5])
             if i > 0:
                 losses = trn.wait_losses()
         losses = trn.wait_losses()
@@ -241,7 +375,7 @@ def main():
             dist.barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         # ---- per-op CUDA-event profile for the roofline of the dominant kernels
-        prof = trn.profile_step(host[0][2].ptr, host[0][3].ptr, repeats=3)    # every rank runs it (it contains the all-reduces)
+        prof = trn.profile_step(host[0][2].ptr, host[0][3].ptr, host[0][6], repeats=3)    # every rank runs it (it contains the all-reduces)
 
     t_ms = torch.tensor([ms, e2e_ms], device="cuda")
     if dist:
@@ -262,18 +396,19 @@ def main():
         finish()
     hbm, tf_burst, tf_sus, peak_src = peaks()
     total_samples = B * world * args.steps
+    gflop_per_sample = VIDEO_GFLOP_PER_SAMPLE if video else STEP_GFLOP_PER_SAMPLE
     value = total_samples / (ms / 1e3)
     line = {
         "metric": "train samples/sec (G+D step)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": "dp%d" % world,
+        "config": {"workload": (WORKLOAD_VIDEO % (args.wtgdl, B)) if video else WORKLOAD.replace("batch 256", "batch %d" % B), "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (>3 GB of activations, weights and optimizer state) exceeds the 126 MB L2; no explicit flush",
                    "losses_last_step": {k: round(v, 5) for k, v in losses.items()} if losses else None},
         "gpu_launches": int(launches1.value - launches0.value),
         "clocks": clocks,
-        "step_tflops": STEP_GFLOP_PER_SAMPLE * 1e-3 * value,
-        "step_frac_of_bf16_sustained": STEP_GFLOP_PER_SAMPLE * 1e-3 * value / (tf_sus * world),
+        "step_tflops": gflop_per_sample * 1e-3 * value,
+        "step_frac_of_bf16_sustained": gflop_per_sample * 1e-3 * value / (tf_sus * world),
     }
     if e2e_ms is not None:
         line["e2e"] = {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
@@ -294,7 +429,7 @@ def main():
             gbs = 30.0 * (nG + nD) / (adam_ms * 1e-3) / 1e9
             line["roofline_hbm"] = {"bound": "hbm", "kernel": "nhwc::adam_bf16_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                     "traffic": None, "bytes_per_param": 30, "params": int(nG + nD), "peak_source": peak_src + " hbm_gbs"}
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not video:
         threads = os.cpu_count() or 1
         rate, sec = cpu_port_step_rate(64, 1, 0, threads)
         line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",

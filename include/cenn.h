@@ -256,6 +256,37 @@ CENN_API int cenn_trainer_kernel_launches_per_step(cenn_trainer *t, int64_t *cou
 CENN_API int cenn_trainer_profile_step(cenn_trainer *t, const float *a_dev, const float *b_dev, const uint8_t *mask_dev,
         char *names, int64_t names_cap, float *ms, double *flops, int64_t cap, int64_t *nops);
 
+/* ------------------------------ inference engine ---------------
+ * Eval-mode generator for test.lua:92 / demo.lua:68 (variant 0: [n,3,128,128] -> [n,3,64,64]) and for the full-frame
+ * sweep of test_vid_wholeim.lua:98-226 (variant 1: [n,nc*inputLen,128,128] -> same shape).  BatchNorm running statistics
+ * are folded into the bf16 operands and the epilogue bias when the parameters are loaded, so a forward is one tensor-core
+ * GEMM launch per layer, replayed as a CUDA graph.  Tiles are independent in eval mode: `batch` is the number of tiles
+ * one forward processes. */
+typedef struct cenn_inpainter cenn_inpainter;
+typedef struct cenn_inpainter_config {
+    int variant;       /* 0: train.lua generator (centre prediction)   1: train_vid_weighted.lua generator */
+    int batch;         /* tiles per forward */
+    int fineSize;      /* 128 */
+    int nBottleneck, nef, ngf;
+    int nc;            /* channels per frame (3) */
+    int inputLen;      /* frames stacked along the channel axis (the training scripts' predLen) */
+} cenn_inpainter_config;
+CENN_API int cenn_inpainter_create(cenn_state *s, const cenn_inpainter_config *cfg, cenn_inpainter **out);
+CENN_API int cenn_inpainter_destroy(cenn_inpainter *p);
+/* element counts of netG:getParameters() and of the concatenated [running_mean, running_var] per BN layer */
+CENN_API int cenn_inpainter_param_count(cenn_inpainter *p, int64_t *params, int64_t *bn_stats);
+/* flat parameters (Module:getParameters order, THNN layouts = what a *_net_G.t7 holds) + running statistics; folds BN */
+CENN_API int cenn_inpainter_load_host(cenn_inpainter *p, const float *flat_host, const float *bn_stats_host);
+/* n <= batch tiles, fp32 NCHW in and out; the device variant neither copies nor synchronises */
+CENN_API int cenn_inpainter_forward_device(cenn_inpainter *p, const float *in_dev, float *out_dev, int n);
+CENN_API int cenn_inpainter_forward_host(cenn_inpainter *p, const float *in_host, float *out_host, int n);
+/* whole sweep on the device: pad to a multiple of fineSize, gather (+ vertical flip of the first three top tiles), forward,
+ * write back, composite under the mask.  frames01 [P,nc,inh,inw] in [0,1] (P %% inputLen == 0), mask [inh,inw] (non-zero =
+ * hole); out01 / full01 / inpaint01 [P,nc,outh,outw] in [0,1] (test_vid_wholeim.lua:222-224), any of them may be NULL.
+ * init (may be NULL) = the optional initializer net of withInit (:179-190), same geometry as p. */
+CENN_API int cenn_inpainter_sweep_host(cenn_inpainter *p, cenn_inpainter *init, const float *frames01_host, const uint8_t *mask_host,
+        int P, int inh, int inw, float maskValue, float *out01_host, float *full01_host, float *inpaint01_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,12 @@ class TrainerConfig(C.Structure):
                 ("rank", C.c_int), ("dead_dgrad", C.c_int)]
 
 
+class InpainterConfig(C.Structure):
+    """struct cenn_inpainter_config (include/cenn.h)."""
+    _fields_ = [("variant", C.c_int), ("batch", C.c_int), ("fineSize", C.c_int), ("nBottleneck", C.c_int),
+                ("nef", C.c_int), ("ngf", C.c_int), ("nc", C.c_int), ("inputLen", C.c_int)]
+
+
 _TYPES = {
     "int": C.c_int, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "size_t": C.c_size_t, "float": C.c_float,
     "double": C.c_double, "void": None,

@@ -47,6 +47,20 @@ __global__ void __launch_bounds__(256) to_nhwc_kernel(const T *__restrict__ src,
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int n = (int)(i / HW), pix = (int)(i - (int64_t)n * HW);
         bf16 *o = dst + i * Cp;
+        if ((Cp & 7) == 0) {                 // 16-byte stores (12 stacked channels -> Cp = 16)
+            for (int c0 = 0; c0 < Cp; c0 += 8) {
+                float f[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int c = c0 + k;
+                    float v = c < C ? (float)src[((int64_t)n * C + c) * HW + pix] : 0.f;
+                    if (sizeof(T) == 1) v = v != 0.f ? 1.f : 0.f;
+                    f[k] = v;
+                }
+                reinterpret_cast<uint4 *>(o)[c0 >> 3] = pack8(f);
+            }
+            continue;
+        }
         for (int c = 0; c < Cp; ++c) {
             float v = c < C ? (float)src[((int64_t)n * C + c) * HW + pix] : 0.f;
             if (sizeof(T) == 1) v = v != 0.f ? 1.f : 0.f;
@@ -694,6 +708,31 @@ __global__ void __launch_bounds__(256) blend_masked_kernel(const bf16 *__restric
     l = block_sum(l, sh);
     if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, l * inv_n);
 }
+// Cp % 8 == 0 fast path of blend_masked: 16-byte vectors of df, x, t, mask and g
+__global__ void __launch_bounds__(256) blend_masked8_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
+        const bf16 *__restrict__ mask, bf16 *__restrict__ g, int64_t nvec, int vec_per_pix, int C, float a, float wtl2, float lambda, float wtgdl,
+        float two_over_n, double inv_n, double *__restrict__ loss_acc) {
+    __shared__ double sh[32];
+    float l = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % vec_per_pix) * 8;
+        float fd[8] = {}, fx[8], ft[8], fm[8] = {}, r[8];
+        if (df) unpack8(__ldg(reinterpret_cast<const uint4 *>(df) + i), fd);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(x) + i), fx); unpack8(__ldg(reinterpret_cast<const uint4 *>(t) + i), ft);
+        if (lambda != 0.f) unpack8(__ldg(reinterpret_cast<const uint4 *>(mask) + i), fm);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float d = fx[k] - ft[k];
+            if (c0 + k >= C) d = 0.f;
+            l = fmaf(d, d, l);
+            const float w = lambda != 0.f ? fm[k] * (1.f - lambda) + lambda : 1.f;
+            r[k] = c0 + k < C ? fd[k] * a + (wtl2 * w + wtgdl) * (d * two_over_n) : 0.f;
+        }
+        reinterpret_cast<uint4 *>(g)[i] = pack8(r);
+    }
+    double ld = block_sum((double)l, sh);
+    if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, ld * inv_n);
+}
 // dst = mask ? src : dst
 __global__ void __launch_bounds__(256) composite_kernel(bf16 *__restrict__ dst, const bf16 *__restrict__ mask, const bf16 *__restrict__ src, int64_t total) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -720,6 +759,47 @@ __global__ void __launch_bounds__(256) gdl_loss_kernel(const bf16 *__restrict__ 
     }
     l = block_sum(l, sh);
     if (threadIdx.x == 0) atomicAdd(loss_acc, l * inv_n);
+}
+// the same with one thread per (sample, pair index k): all CP channels of the four pixels involved come in as 8- or 16-byte vectors
+template <int CP>
+__global__ void __launch_bounds__(256) gdl_loss_vec_kernel(const bf16 *__restrict__ inp, const bf16 *__restrict__ tgt, int64_t N, int H, int W, int C,
+        double inv_n, double *__restrict__ loss_acc) {
+    __shared__ double sh[32];
+    const int NK = H * (W - 1);
+    float l = 0.f;
+    const int64_t total = N * NK;
+    auto load = [&](const bf16 *T, int64_t n, int r, int cc, float (&f)[CP]) {
+        const bf16 *p = T + ((n * H + r) * W + cc) * CP;
+        if (CP == 4) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2 *>(p));
+            const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162 *>(&u.x), h1 = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
+            f[0] = __low2float(h0); f[1] = __high2float(h0); f[2] = __low2float(h1); f[3] = __high2float(h1);
+        } else {
+#pragma unroll
+            for (int v = 0; v < CP / 8; ++v) {
+                float e[8];
+                unpack8(__ldg(reinterpret_cast<const uint4 *>(p) + v), e);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[(v * 8 + k) % CP] = e[k];
+            }
+        }
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % NK);
+        const int64_t n = i / NK;
+        const int ar = k / (W - 1), ac = k - ar * (W - 1), br = k / W, bc = k - br * W;
+        float ta[CP], tb[CP], xa[CP], xb[CP];
+        load(tgt, n, ar, ac, ta); load(tgt, n, br, bc, tb); load(inp, n, ar, ac, xa); load(inp, n, br, bc, xb);
+        float part = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) if (c < C) part += fabsf(fabsf(ta[c] - tb[c]) - fabsf(xa[c] - xb[c]));
+        load(tgt, n, ar, ac + 1, ta); load(tgt, n, br + 1, bc, tb); load(inp, n, ar, ac + 1, xa); load(inp, n, br + 1, bc, xb);
+#pragma unroll
+        for (int c = 0; c < CP; ++c) if (c < C) part += fabsf(fabsf(ta[c] - tb[c]) - fabsf(xa[c] - xb[c]));
+        l += part;
+    }
+    double ld = block_sum((double)l, sh);
+    if (threadIdx.x == 0) atomicAdd(loss_acc, ld * inv_n);
 }
 
 // ---------------------------------------------------------------- optimiser / parameter maintenance
@@ -777,6 +857,105 @@ __global__ void __launch_bounds__(256) wt_from_wf_kernel(const bf16 *__restrict_
             row = ((int64_t)((py * 2 + px) * cl_rows + cl)) * 4 + (a * 2 + b);
         }
         dst[row * Csp + cs] = tile[tx][r];
+    }
+}
+
+
+// ---------------------------------------------------------------- inference engine (cenn_inpainter_*)
+// eval-mode BN folded into the operands: w'[.., c] = w[.., c] * gamma[c] / sqrt(running_var[c] + eps) (bf16 operand copy) and
+// bias'[c] = (bias[c] - running_mean[c]) * that scale + beta[c] (fp32, added to the fp32 accumulator in the GEMM epilogue)
+__global__ void __launch_bounds__(256) fold_bn_weights_kernel(const float *__restrict__ w, bf16 *__restrict__ wb, int64_t count, int Clp, int chan_is_row,
+        const float *__restrict__ gamma, const float *__restrict__ running_var, int Cout, double eps) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = chan_is_row ? (int)(i / (16 * (int64_t)Clp)) : (int)(i % Clp);
+        const float sc = c < Cout ? (float)((double)gamma[c] / sqrt((double)running_var[c] + eps)) : 0.f;
+        wb[i] = __float2bfloat16(w[i] * sc);
+    }
+}
+// out[rep][Cp]: the folded bias, repeated `reps` times (G1's GEMM columns are (tap, channel)); gamma == nullptr: plain conv bias
+__global__ void fold_bn_bias_kernel(const float *__restrict__ bias, const float *__restrict__ gamma, const float *__restrict__ beta,
+        const float *__restrict__ running_mean, const float *__restrict__ running_var, float *__restrict__ out, int Cout, int Cp, int reps, double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= reps * Cp) return;
+    const int c = i % Cp;
+    float v = 0.f;
+    if (c < Cout) {
+        if (gamma) { const double sc = (double)gamma[c] / sqrt((double)running_var[c] + eps); v = (float)(((double)bias[c] - (double)running_mean[c]) * sc + (double)beta[c]); }
+        else v = bias[c];
+    }
+    out[i] = v;
+}
+
+// Full-frame sweep of test_vid_wholeim.lua:98-226.  Tile j = ti * groups + g: ti walks the padded frame row-major in FxF tiles,
+// g is the frame group (ncin = nc * inputLen stacked channels); the first three tiles of the top row are fed upside down (:167-170).
+struct SweepGeom { int P, nc, inh, inw, outh, outw, F, ncin, Cp, groups, tiles_w; };
+__device__ __forceinline__ void sweep_tile(const SweepGeom &q, int j, int &h0, int &w0, int &g, bool &flip) {
+    const int ti = j / q.groups; g = j - ti * q.groups;
+    const int tr = ti / q.tiles_w, tc = ti - tr * q.tiles_w;
+    h0 = tr * q.F; w0 = tc * q.F; flip = tr == 0 && tc < 3;
+}
+// frames01 [P][nc][inh][inw] in [0,1], mask [inh][inw] -> generator input tiles [n][F][F][Cp] bf16 in [-1,1]: masked pixels = maskValue,
+// bottom/right padding = 0 (:60-72,109-111).  mid != nullptr (withInit, :179-190): pixels under the tile's slice of the padded mask -- taken
+// UN-flipped, as the reference does -- come from the initializer net's output for the same tile.
+template <int CP>
+__global__ void __launch_bounds__(256) wholeim_gather_kernel(const float *__restrict__ frames01, const uint8_t *__restrict__ mask, float maskValue, SweepGeom q,
+        int j0, int n, bf16 *__restrict__ dst, const bf16 *__restrict__ mid) {
+    const int FF = q.F * q.F;
+    const int64_t total = (int64_t)n * FF;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / FF), r = (int)(i - (int64_t)t * FF), y = r / q.F, x = r - y * q.F;
+        int h0, w0, g; bool flip;
+        sweep_tile(q, j0 + t, h0, w0, g, flip);
+        const int Y = h0 + (flip ? q.F - 1 - y : y), X = w0 + x;
+        const bool inside = Y < q.inh && X < q.inw;
+        const bool m = inside && mask[(int64_t)Y * q.inw + X] != 0;
+        const int Yu = h0 + y;
+        const bool fill = mid != nullptr && Yu < q.inh && X < q.inw && mask[(int64_t)Yu * q.inw + X] != 0;
+        __align__(16) bf16 v[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            float f = 0.f;
+            if (c < q.ncin) {
+                const int cc = g * q.ncin + c;
+                const float s = inside ? (m ? maskValue : __ldg(frames01 + ((int64_t)cc * q.inh + Y) * q.inw + X)) : 0.f;
+                f = s * 2.f - 1.f;
+            }
+            v[c] = __float2bfloat16(f);
+        }
+        if (fill) {
+            const bf16 *ms = mid + i * CP;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) if (c < q.ncin) v[c] = ms[c];
+        }
+        if (CP == 4) *reinterpret_cast<uint2 *>(dst + i * CP) = *reinterpret_cast<const uint2 *>(v);
+        else {
+#pragma unroll
+            for (int k = 0; k < CP / 8; ++k) reinterpret_cast<uint4 *>(dst + i * CP)[k] = reinterpret_cast<const uint4 *>(v)[k];
+        }
+    }
+}
+// generator output tiles [n][F][F][Cp] -> outImages / fullImages / inpaintImages [P*nc][outh][outw] fp32 in [0,1] (:194-224):
+// un-flip, write back, composite under the padded mask, rescale.
+__global__ void __launch_bounds__(256) wholeim_scatter_kernel(const bf16 *__restrict__ gout, const float *__restrict__ frames01, const uint8_t *__restrict__ mask,
+        float maskValue, SweepGeom q, int j0, int n, float *__restrict__ out01, float *__restrict__ full01, float *__restrict__ inpaint01) {
+    const int FF = q.F * q.F;
+    const int64_t total = (int64_t)n * FF;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / FF), r = (int)(i - (int64_t)t * FF), y = r / q.F, x = r - y * q.F;
+        int h0, w0, g; bool flip;
+        sweep_tile(q, j0 + t, h0, w0, g, flip);
+        const int Y = h0 + (flip ? q.F - 1 - y : y), X = w0 + x;
+        const bool inside = Y < q.inh && X < q.inw;
+        const bool m = inside && mask[(int64_t)Y * q.inw + X] != 0;
+        const bf16 *o = gout + i * q.Cp;
+        for (int c = 0; c < q.ncin; ++c) {
+            const int cc = g * q.ncin + c;
+            const float s = inside ? (m ? maskValue : __ldg(frames01 + ((int64_t)cc * q.inh + Y) * q.inw + X)) : 0.f;
+            const float full = ((s * 2.f - 1.f) + 1.f) * 0.5f;
+            const float ov = (__bfloat162float(o[c]) + 1.f) * 0.5f;
+            const int64_t idx = ((int64_t)cc * q.outh + Y) * q.outw + X;
+            out01[idx] = ov; full01[idx] = full; inpaint01[idx] = m ? ov : full;
+        }
     }
 }
 

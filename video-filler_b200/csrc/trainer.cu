@@ -52,6 +52,7 @@ struct Block {
     int stats_cols = 0, fold = 1;
     float *sig = nullptr, *gpre = nullptr;  // head
     float *bias_exp = nullptr;              // G1: bias expanded over the 16 taps
+    float *bias_inf = nullptr;              // inference engine: conv bias with the BN shift folded in (per GEMM column)
     TcPlan p_fwd, p_dgrad, p_wgrad;
     bool has_dgrad = false;
 };
@@ -148,6 +149,8 @@ struct cenn_trainer {
     std::vector<std::pair<int64_t, int64_t>> g_buckets;   // (offset, count) of G's gradient ranges reduced on the bulk communicator
     std::vector<std::pair<int64_t, int64_t>> d_buckets;   // same for D (second sweep of the step only: the first one just accumulates)
     bool d_bucket_sweep = false;
+    bool infer = false;                   // inference engine (cenn_inpainter_*): forward plans only, BN folded into weights and bias
+    int infer_n = 0;                      // tiles converted in / out by the current forward call
 };
 
 namespace {
@@ -267,11 +270,11 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             b.sig = dalloc<float>(t, N); b.gpre = dalloc<float>(t, N);
             if (!b.sig || !b.gpre) return 1;
         } else {
-            if (sp.bn && alloc_tensor(t, b.y, N, oh, ow, b.Cout, b.Coutp)) return 1;
+            if (sp.bn && !t->infer && alloc_tensor(t, b.y, N, oh, ow, b.Cout, b.Coutp)) return 1;
             if (alloc_tensor(t, b.a, N, oh, ow, b.Cout, b.Coutp)) return 1;
-            if (alloc_tensor(t, b.g, N, oh, ow, b.Cout, b.Coutp)) return 1;
+            if (!t->infer && alloc_tensor(t, b.g, N, oh, ow, b.Cout, b.Coutp)) return 1;
         }
-        if (sp.type != HEAD) {
+        if (sp.type != HEAD && !t->infer) {
             // backward reductions: one partial row per CTA of the (pixel-strip x vector-group) grid
             const int vpp = b.Coutp >= 8 ? b.Coutp / 8 : 1;
             int tx = 1; while (tx < vpp && tx < 64) tx *= 2;
@@ -281,12 +284,21 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             b.part = dalloc<float>(t, (int64_t)b.part_rows * 2 * std::max(b.Coutp, 8));
             if (!b.part) return 1;
         }
-        if (b.thin) {
+        if (b.thin && !(t->infer && sp.type != CONV_S2)) {
             b.col_rows = (int64_t)N * b.h * b.w; b.col_k = 16 * b.Clp;
             b.col = dalloc<bf16>(t, b.col_rows * b.col_k);
             if (!b.col) return 1;
         }
-        if (sp.bn) {
+        if (t->infer) {
+            b.bias_inf = dalloc<float>(t, sp.type == FULL_V4 ? 16 * (int64_t)b.Clp : b.Coutp);
+            if (!b.bias_inf) return 1;
+            if (sp.bn) {
+                b.running = dalloc<float>(t, 2 * (int64_t)b.Coutp);
+                if (!b.running) return 1;
+                std::vector<float> ones(b.Coutp, 1.f);
+                CK(cudaMemcpy(b.running + b.Coutp, ones.data(), b.Coutp * sizeof(float), cudaMemcpyHostToDevice));
+            }
+        } else if (sp.bn) {
             b.fold = sp.type == FULL_V4 ? 16 : 1;
             b.stats_cols = b.Coutp * b.fold;
             b.stats = dalloc<float>(t, 2 * (int64_t)b.stats_cols);
@@ -307,10 +319,46 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
     // The Adam kernel streams these five arrays at identical offsets; with identically aligned bases all five streams
     // would walk the same HBM channel sequence in lock step (observed: 3x slower).  Skew the bases by odd multiples of 256 B.
     auto skewed = [&](int k) -> float * { float *p = dalloc<float>(t, off + 8 * 65536); return p ? p + (size_t)k * (33856 + 64) : nullptr; };
-    net.master = skewed(0); net.grad = skewed(1); net.m = skewed(2); net.v = skewed(3);
+    net.master = skewed(0);
+    if (!t->infer) { net.grad = skewed(1); net.m = skewed(2); net.v = skewed(3); }
     { bf16 *p = dalloc<bf16>(t, off + 8 * 65536); net.wbf = p ? p + (size_t)4 * (33856 + 64) * 2 : nullptr; }
     net.adam_t = dalloc<long long>(t, 1); net.adam_step = dalloc<float>(t, 1);
-    if (!net.master || !net.grad || !net.m || !net.v || !net.wbf || !net.adam_t || !net.adam_step) return 1;
+    if (!net.master || !net.wbf || !net.adam_t || !net.adam_step) return 1;
+    if (t->infer) {
+        // forward plans only: bias (with the BN shift folded in) and the activation in the GEMM epilogue, straight into `a`
+        for (size_t i = 0; i < net.blocks.size(); ++i) {
+            Block &b = net.blocks[i];
+            const bf16 *Wf = net.wbf + b.w_off;
+            const int M = N * b.h * b.w;
+            TcEpilogue ep; ep.bias = b.bias_inf; ep.act = b.act; ep.act_param = 0.2f;
+            TcEpilogue ep_m = ep; ep_m.b_mn = true;
+            switch (b.type) {
+                case CONV_S2:
+                    if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, b.a.p, M, b.Cs, (int)b.col_k, b.Csp, ep)) return 1; }
+                    else if (tc_plan_fprop_s2(s, &b.p_fwd, b.in.p, Wf, b.a.p, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep)) return 1;
+                    break;
+                case CONV_V4:
+                    if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, b.a.p, N, b.Cs, 16 * b.Clp, b.Csp, ep)) return 1;
+                    break;
+                case FULL_V4:
+                    if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, b.a.p, N, 16 * b.Clp, b.Csp, 16 * b.Clp, ep_m)) return 1;
+                    break;
+                case FULL_S2:
+                    b.cl_rows = b.Clp;
+                    if (b.Clp % 64 == 0) {
+                        if (tc_plan_dgrad_s2(s, &b.p_fwd, b.in.p, Wf, b.a.p, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep_m)) return 1;
+                    } else {
+                        b.Wt = dalloc<bf16>(t, (int64_t)16 * b.cl_rows * b.Csp);
+                        if (!b.Wt) return 1;
+                        if (tc_plan_dgrad_s2(s, &b.p_fwd, b.in.p, b.Wt, b.a.p, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep)) return 1;
+                    }
+                    break;
+                case HEAD: REQUIRE(false, "the inference engine builds generators only");
+            }
+        }
+        return 0;
+    }
+    if (!net.grad || !net.m || !net.v) return 1;
     net.nbias_seg = (int)bias_segs.size() / 2;
     net.bias_seg = dalloc<int64_t>(t, bias_segs.size());
     if (!net.bias_seg) return 1;
@@ -885,10 +933,18 @@ int build_program(T *t) {
                 double *gacc = t->loss_acc + CENN_LOSS_ERRG_GDL;
                 double ngdl = (double)t->Bglobal * fake_in.C * fake_in.H * (fake_in.W - 1);
                 emit(t, "gdl_loss", [s, fake_in, real, gacc, ngdl]() {
+                    const int64_t pairs = (int64_t)fake_in.N * fake_in.H * (fake_in.W - 1);
+                    if (fake_in.Cp == 16) nhwc::gdl_loss_vec_kernel<16><<<grid1d(s, pairs, 256, 4), 256, 0, s->stream>>>(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.C, 1.0 / ngdl, gacc);
+                    else if (fake_in.Cp == 4) nhwc::gdl_loss_vec_kernel<4><<<grid1d(s, pairs, 256, 4), 256, 0, s->stream>>>(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.C, 1.0 / ngdl, gacc);
+                    else
                     nhwc::gdl_loss_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.Cp, fake_in.C, 1.0 / ngdl, gacc);
                     KLAUNCH(s); return 0; });
             }
             emit(t, "blend_masked", [s, df, fake_in, real, mk, gout, a, wtl2, lam, wtgdl, n, acc]() {
+                if (fake_in.Cp % 8 == 0)
+                    nhwc::blend_masked8_kernel<<<grid1d(s, fake_in.elems() / 8, 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems() / 8, fake_in.Cp / 8, fake_in.C,
+                        a, wtl2, lam, wtgdl, (float)(2.0 / n), 1.0 / n, acc);
+                else
                 nhwc::blend_masked_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems(), fake_in.Cp, fake_in.C,
                     a, wtl2, lam, wtgdl, (float)(2.0 / n), 1.0 / n, acc);
                 KLAUNCH(s); return 0; });
@@ -1393,6 +1449,227 @@ int cenn_trainer_fetch_host(cenn_trainer *t, const char *name, float *dst, int64
 int cenn_trainer_kernel_launches_per_step(cenn_trainer *t, int64_t *count) {
     REQUIRE(t && count, "null argument");
     *count = t->launches_per_step;
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// inference engine: eval-mode generator with BN folded into the operands, full-frame sweep on the device
+// ------------------------------------------------------------------------------------------------------------------
+struct cenn_inpainter {
+    cenn_trainer *t = nullptr;          // generator only, t->infer
+    cenn_inpainter_config cfg;
+    int ncin = 0;
+    bool loaded = false;
+    float *stage_in = nullptr, *stage_out = nullptr;   // fp32 NCHW staging of forward_host
+    // sweep buffers (grown on demand)
+    float *frames = nullptr, *img[3] = {nullptr, nullptr, nullptr};
+    uint8_t *mask = nullptr;
+    size_t frames_cap = 0, img_cap = 0, mask_cap = 0;
+};
+
+namespace {
+
+int inpainter_build_program(cenn_inpainter *p) {
+    T *t = p->t;
+    cenn_state *s = t->s;
+    Net &G = t->G;
+    t->prog.clear();
+    // cur_a / cur_b: fp32 NCHW device input / output (nullptr: the tiles are already in / stay in the NHWC buffers)
+    emit(t, "tiles<-nchw", [t, s]() {
+        if (!t->cur_a) return 0;
+        const Tensor &gi = t->G.input;
+        const int n = t->infer_n;
+        if (gi.Cp == 4 && (gi.H * gi.W) % 4 == 0) nhwc::to_nhwc4_kernel<<<grid1d(s, (int64_t)n * gi.H * gi.W / 4), 256, 0, s->stream>>>(t->cur_a, gi.p, n, gi.C, gi.H * gi.W);
+        else nhwc::to_nhwc_kernel<float><<<grid1d(s, (int64_t)n * gi.H * gi.W), 256, 0, s->stream>>>(t->cur_a, gi.p, n, gi.C, gi.H * gi.W, gi.Cp);
+        KLAUNCH(s); return 0; });
+    for (size_t i = 0; i < G.blocks.size(); ++i) {
+        Block *b = &G.blocks[i];
+        if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
+        emit_plan(t, "conv_fwd", &b->p_fwd);
+    }
+    emit(t, "tiles->nchw", [t, s]() {
+        if (!t->cur_b) return 0;
+        const Tensor &go = t->G.blocks.back().a;
+        const int n = t->infer_n;
+        nhwc::to_nchw_kernel<<<grid1d(s, (int64_t)n * go.C * go.H * go.W), 256, 0, s->stream>>>(go.p, const_cast<float *>(t->cur_b), n, go.C, go.H * go.W, go.Cp);
+        KLAUNCH(s); return 0; });
+    return 0;
+}
+
+int inpainter_run(cenn_inpainter *p, const float *in_dev, float *out_dev, int n) {
+    T *t = p->t;
+    t->cur_a = in_dev; t->cur_b = out_dev; t->infer_n = n;
+    t->cur_m = reinterpret_cast<const uint8_t *>((uintptr_t)n);     // part of the graph-cache key
+    return run_step(t);
+}
+
+template <typename X>
+int grow(X *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    if (cudaMalloc(&ptr, need * sizeof(X)) != cudaSuccess) { cenn_set_error("inpainter: device allocation of %zu bytes failed", need * sizeof(X)); return 1; }
+    cap = need;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cenn_inpainter_create(cenn_state *s, const cenn_inpainter_config *cfg, cenn_inpainter **out) {
+    API_BEGIN(s);
+    REQUIRE(cfg && out, "cenn_inpainter_create: null argument");
+    REQUIRE(cfg->variant == 0 || cfg->variant == 1, "unknown variant %d", cfg->variant);
+    REQUIRE(cfg->fineSize == 128, "fineSize must be 128 (the 4x4 bottleneck of the reference generators), got %d", cfg->fineSize);
+    REQUIRE(cfg->batch >= 1 && cfg->nBottleneck % 8 == 0 && cfg->nBottleneck >= 8 && cfg->nef % 64 == 0 && cfg->ngf % 64 == 0 && cfg->nef >= 64 && cfg->ngf >= 64,
+            "batch >= 1, nBottleneck %% 8 == 0 and nef/ngf %% 64 == 0 required (got %d, %d, %d/%d)", cfg->batch, cfg->nBottleneck, cfg->nef, cfg->ngf);
+    const int ncin = cfg->variant == 1 ? cfg->nc * cfg->inputLen : cfg->nc;
+    REQUIRE(cfg->nc >= 1 && cfg->inputLen >= 1 && ncin <= 16, "1..16 input channels supported (nc*inputLen = %d)", ncin);
+    cenn_inpainter *p = new cenn_inpainter();
+    p->cfg = *cfg; p->ncin = ncin;
+    cenn_trainer *t = new cenn_trainer();
+    p->t = t;
+    t->s = s; t->infer = true;
+    cenn_trainer_config tc = {};
+    tc.variant = cfg->variant; tc.batchSize = cfg->batch; tc.fineSize = cfg->fineSize; tc.nBottleneck = cfg->nBottleneck;
+    tc.nef = cfg->nef; tc.ngf = cfg->ngf; tc.ndf = 64; tc.nc = cfg->nc; tc.predLen = cfg->inputLen; tc.precision = CENN_BF16; tc.world_size = 1;
+    t->cfg = tc;
+    t->B = cfg->batch; t->F = cfg->fineSize; t->nc = ncin; t->Bglobal = t->B;
+    if (build_net(t, t->G, spec_G(tc), t->F, ncin, false, true) || inpainter_build_program(p)) { cenn_inpainter_destroy(p); return 1; }
+    *out = p;
+    return 0;
+}
+
+int cenn_inpainter_destroy(cenn_inpainter *p) {
+    if (!p) return 0;
+    if (p->t) {
+        cudaSetDevice(p->t->s->device);
+        cudaStreamSynchronize(p->t->s->stream);
+        for (void *q : {(void *)p->stage_in, (void *)p->stage_out, (void *)p->frames, (void *)p->img[0], (void *)p->img[1], (void *)p->img[2], (void *)p->mask}) if (q) cudaFree(q);
+        cenn_trainer_destroy(p->t);
+    }
+    delete p;
+    return 0;
+}
+
+int cenn_inpainter_param_count(cenn_inpainter *p, int64_t *params, int64_t *bn_stats) {
+    REQUIRE(p && p->t, "cenn_inpainter_param_count: null argument");
+    if (params) *params = p->t->G.nparam_thnn;
+    if (bn_stats) return cenn_trainer_bn_stat_count(p->t, CENN_NET_G, bn_stats);
+    return 0;
+}
+
+int cenn_inpainter_load_host(cenn_inpainter *p, const float *flat, const float *bn_stats) {
+    REQUIRE(p && p->t && flat && bn_stats, "cenn_inpainter_load_host: null argument");
+    T *t = p->t;
+    API_BEGIN(t->s);
+    cenn_state *s = t->s;
+    Net &n = t->G;
+    std::vector<float> m;
+    thnn_to_master(n, flat, m);
+    CK(cudaMemcpyAsync(n.master, m.data(), n.nparam * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (cenn_trainer_set_bn_stats_host(t, CENN_NET_G, bn_stats)) return 1;
+    nhwc::f32_to_bf16_kernel<<<grid1d(s, n.nparam), 256, 0, s->stream>>>(n.master, n.wbf, n.nparam);
+    KLAUNCH(s);
+    for (Block &b : n.blocks) {
+        const float *gamma = b.bn ? n.master + b.g_off : nullptr, *beta = b.bn ? n.master + b.be_off : nullptr;
+        const float *rm = b.bn ? b.running : nullptr, *rv = b.bn ? b.running + b.Coutp : nullptr;
+        const bool chan_is_row = b.type == CONV_S2 || b.type == CONV_V4;     // output channel = small side = operand row
+        if (b.bn) {
+            nhwc::fold_bn_weights_kernel<<<grid1d(s, b.w_count), 256, 0, s->stream>>>(n.master + b.w_off, n.wbf + b.w_off, b.w_count, b.Clp, chan_is_row ? 1 : 0, gamma, rv, b.Cout, 1e-5);
+            KLAUNCH(s);
+        }
+        const int Cp = b.type == FULL_V4 ? b.Clp : b.Coutp, reps = b.type == FULL_V4 ? 16 : 1;
+        nhwc::fold_bn_bias_kernel<<<(reps * Cp + 255) / 256, 256, 0, s->stream>>>(n.master + b.b_off, gamma, beta, rm, rv, b.bias_inf, b.Cout, Cp, reps, 1e-5);
+        KLAUNCH(s);
+    }
+    size_t mark = t->prog.size();
+    emit_weight_prep(t, n);                                  // transposed operand copies of the thin layers, from the folded bf16 copy
+    int rc = run_ops(t, mark, t->prog.size());
+    t->prog.resize(mark);
+    if (rc) return 1;
+    CK(cudaStreamSynchronize(s->stream));
+    p->loaded = true;
+    return 0;
+}
+
+int cenn_inpainter_forward_device(cenn_inpainter *p, const float *in, float *out, int n) {
+    REQUIRE(p && p->t && in && out, "cenn_inpainter_forward_device: null argument");
+    REQUIRE(p->loaded, "cenn_inpainter_forward: no parameters loaded (cenn_inpainter_load_host)");
+    REQUIRE(n >= 1 && n <= p->t->B, "cenn_inpainter_forward: %d tiles outside 1..%d (the engine's batch)", n, p->t->B);
+    API_BEGIN(p->t->s);
+    return inpainter_run(p, in, out, n);
+}
+
+int cenn_inpainter_forward_host(cenn_inpainter *p, const float *in, float *out, int n) {
+    REQUIRE(p && p->t && in && out, "cenn_inpainter_forward_host: null argument");
+    REQUIRE(p->loaded, "cenn_inpainter_forward: no parameters loaded (cenn_inpainter_load_host)");
+    T *t = p->t;
+    REQUIRE(n >= 1 && n <= t->B, "cenn_inpainter_forward: %d tiles outside 1..%d (the engine's batch)", n, t->B);
+    API_BEGIN(t->s);
+    cenn_state *s = t->s;
+    const Tensor &gi = t->G.input, &go = t->G.blocks.back().a;
+    const size_t per_in = (size_t)gi.C * gi.H * gi.W, per_out = (size_t)go.C * go.H * go.W;
+    if (!p->stage_in) {
+        if (cudaMalloc(&p->stage_in, per_in * t->B * 4) != cudaSuccess || cudaMalloc(&p->stage_out, per_out * t->B * 4) != cudaSuccess) { cenn_set_error("inpainter: staging allocation failed"); return 1; }
+    }
+    CK(cudaMemcpyAsync(p->stage_in, in, per_in * n * 4, cudaMemcpyHostToDevice, s->stream));
+    if (inpainter_run(p, p->stage_in, p->stage_out, n)) return 1;
+    CK(cudaMemcpyAsync(out, p->stage_out, per_out * n * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int cenn_inpainter_sweep_host(cenn_inpainter *p, cenn_inpainter *init, const float *frames01, const uint8_t *mask, int P, int inh, int inw,
+                              float maskValue, float *out01, float *full01, float *inpaint01) {
+    REQUIRE(p && p->t && frames01 && mask, "cenn_inpainter_sweep_host: null argument");
+    REQUIRE(p->loaded && (!init || init->loaded), "cenn_inpainter_sweep: no parameters loaded (cenn_inpainter_load_host)");
+    REQUIRE(p->cfg.variant == 1, "the full-frame sweep needs a generator whose output has the input's size (variant 1)");
+    REQUIRE(P >= 1 && P % p->cfg.inputLen == 0, "I don't do padding in time dim: %d frames, inputLen %d (test_vid_wholeim.lua:41)", P, p->cfg.inputLen);
+    REQUIRE(inh >= 1 && inw >= 1, "empty frames");
+    T *t = p->t;
+    if (init) REQUIRE(init->t->s == t->s && init->ncin == p->ncin && init->t->B == t->B && init->cfg.variant == 1, "initializer net must share the state, channel count and batch of the main engine");
+    API_BEGIN(t->s);
+    cenn_state *s = t->s;
+    const int F = t->F, nc = p->cfg.nc;
+    nhwc::SweepGeom q;
+    q.P = P; q.nc = nc; q.inh = inh; q.inw = inw; q.F = F; q.ncin = p->ncin; q.Cp = t->G.input.Cp;
+    q.outh = (inh + F - 1) / F * F; q.outw = (inw + F - 1) / F * F;
+    q.groups = P * nc / p->ncin; q.tiles_w = q.outw / F;
+    const int total_tiles = (q.outh / F) * q.tiles_w * q.groups;
+    const size_t n_frames = (size_t)P * nc * inh * inw, n_img = (size_t)P * nc * q.outh * q.outw, n_mask = (size_t)inh * inw;
+    if (grow(p->frames, p->frames_cap, n_frames) || grow(p->mask, p->mask_cap, n_mask)) return 1;
+    if (n_img > p->img_cap) { size_t c0 = p->img_cap, c1 = p->img_cap, c2 = p->img_cap; if (grow(p->img[0], c0, n_img) || grow(p->img[1], c1, n_img) || grow(p->img[2], c2, n_img)) return 1; p->img_cap = n_img; }
+    CK(cudaMemcpyAsync(p->frames, frames01, n_frames * 4, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(p->mask, mask, n_mask, cudaMemcpyHostToDevice, s->stream));
+    const Tensor &gi = t->G.input, &go = t->G.blocks.back().a;
+    REQUIRE(go.H == F && go.Cp == gi.Cp, "internal: generator output %dx%dx%d does not match its input", go.H, go.W, go.Cp);
+    for (int j0 = 0; j0 < total_tiles; j0 += t->B) {
+        const int n = std::min(t->B, total_tiles - j0);
+        const int64_t px = (int64_t)n * F * F;
+        const bf16 *mid = nullptr;
+        if (init) {
+            const Tensor &ii = init->t->G.input;
+            if (q.Cp == 4) nhwc::wholeim_gather_kernel<4><<<grid1d(s, px), 256, 0, s->stream>>>(p->frames, p->mask, maskValue, q, j0, n, ii.p, nullptr);
+            else nhwc::wholeim_gather_kernel<16><<<grid1d(s, px), 256, 0, s->stream>>>(p->frames, p->mask, maskValue, q, j0, n, ii.p, nullptr);
+            KLAUNCH(s);
+            if (inpainter_run(init, nullptr, nullptr, n)) return 1;
+            mid = init->t->G.blocks.back().a.p;
+        }
+        if (q.Cp == 4) nhwc::wholeim_gather_kernel<4><<<grid1d(s, px), 256, 0, s->stream>>>(p->frames, p->mask, maskValue, q, j0, n, gi.p, mid);
+        else nhwc::wholeim_gather_kernel<16><<<grid1d(s, px), 256, 0, s->stream>>>(p->frames, p->mask, maskValue, q, j0, n, gi.p, mid);
+        KLAUNCH(s);
+        if (inpainter_run(p, nullptr, nullptr, n)) return 1;
+        nhwc::wholeim_scatter_kernel<<<grid1d(s, px), 256, 0, s->stream>>>(go.p, p->frames, p->mask, maskValue, q, j0, n, p->img[0], p->img[1], p->img[2]);
+        KLAUNCH(s);
+    }
+    float *dst[3] = {out01, full01, inpaint01};
+    for (int k = 0; k < 3; ++k) if (dst[k]) CK(cudaMemcpyAsync(dst[k], p->img[k], n_img * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
     return 0;
 }
 
