@@ -247,5 +247,96 @@ function GDL:updateOutput(input, target)
 end
 function GDL:updateGradInput() return self.gradInput end
 
+---------------------------------------------------------------------------------------------- optional fast paths
+-- Both are opt-in: the unchanged scripts never touch them.  A maintainer selects them with two lines in train.lua
+-- (`local fast = cenn.Trainer(opt, netG, netD)` ... `fast:step(real_ctx, real_center)`) or in test_vid_wholeim.lua
+-- (`local eng = cenn.Inpainter(opt, net)` ... `eng:sweep(images01, mask)`).
+ffi.cdef[[
+typedef struct cenn_trainer_config { int variant, batchSize, fineSize, nBottleneck, nef, ngf, ndf, nc, predLen, overlapPred;
+    float wtl2, weight_nomask, wtgdl, lr, beta1; int precision, world_size, rank, dead_dgrad; } cenn_trainer_config;
+int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trainer **out);
+int cenn_trainer_destroy(cenn_trainer *t);
+int cenn_trainer_param_count(cenn_trainer *t, int net, int64_t *count);
+int cenn_trainer_set_params_host(cenn_trainer *t, int net, const float *flat_host);
+int cenn_trainer_get_params_host(cenn_trainer *t, int net, float *flat_host);
+int cenn_trainer_bn_stat_count(cenn_trainer *t, int net, int64_t *count);
+int cenn_trainer_set_bn_stats_host(cenn_trainer *t, int net, const float *stats_host);
+int cenn_trainer_get_bn_stats_host(cenn_trainer *t, int net, float *stats_host);
+int cenn_trainer_step_host(cenn_trainer *t, const float *a_host, const float *b_host, const uint8_t *mask_host, float *losses_host);
+int cenn_trainer_step_host_async(cenn_trainer *t, const float *a_host, const float *b_host, const uint8_t *mask_host);
+int cenn_trainer_wait_losses(cenn_trainer *t, float *losses_host);
+typedef struct cenn_inpainter cenn_inpainter;
+typedef struct cenn_inpainter_config { int variant, batch, fineSize, nBottleneck, nef, ngf, nc, inputLen; } cenn_inpainter_config;
+int cenn_inpainter_create(cenn_state *s, const cenn_inpainter_config *cfg, cenn_inpainter **out);
+int cenn_inpainter_destroy(cenn_inpainter *p);
+int cenn_inpainter_param_count(cenn_inpainter *p, int64_t *params, int64_t *bn_stats);
+int cenn_inpainter_load_host(cenn_inpainter *p, const float *flat_host, const float *bn_stats_host);
+int cenn_inpainter_forward_host(cenn_inpainter *p, const float *in_host, float *out_host, int n);
+int cenn_inpainter_sweep_host(cenn_inpainter *p, cenn_inpainter *init, const float *frames01_host, const uint8_t *mask_host,
+    int P, int inh, int inw, float maskValue, float *out01_host, float *full01_host, float *inpaint01_host);
+]]
+
+-- [running_mean, running_var] of every BN module in execution order, as one FloatTensor (what the *_bn_stats_* calls carry)
+local function bn_stats_of(net)
+  local parts = {}
+  for _, m in ipairs(net:findModules('nn.SpatialBatchNormalization')) do
+    parts[#parts + 1] = m.running_mean:float(); parts[#parts + 1] = (m.running_var or torch.pow(m.running_std, -2):add(-m.eps)):float()  -- util.lua:40-44
+  end
+  return torch.cat(parts)
+end
+
+-- whole-step executor behind fDx/fGx + the two optim.adam calls (train.lua:278-424; train_vid_weighted.lua:373-537)
+local Trainer = torch.class('cenn.Trainer')
+function Trainer:__init(opt, netG, netD, world_size, rank)
+  local video = opt.predLen ~= nil
+  local cfg = ffi.new('cenn_trainer_config', {video and 1 or 0, opt.batchSize, opt.fineSize, opt.nBottleneck, opt.nef, opt.ngf, opt.ndf, opt.nc or 3,
+    opt.predLen or 1, opt.overlapPred or 0, opt.wtl2, opt.weight_nomask or 0, opt.wtgdl or 0, opt.lr, opt.beta1, 1, world_size or 1, rank or 0, 1})
+  local h = ffi.new('cenn_trainer*[1]'); check(lib.cenn_trainer_create(S(), cfg, h)); self.h = ffi.gc(h[0], lib.cenn_trainer_destroy)
+  self.netG, self.netD = netG, netD
+  self.pG, self.pD = netG:getParameters(), netD:getParameters()          -- train.lua:262-263: the flat vectors are the interchange format
+  check(lib.cenn_trainer_set_params_host(self.h, 0, self.pG:float():data())); check(lib.cenn_trainer_set_params_host(self.h, 1, self.pD:float():data()))
+  self.losses = torch.FloatTensor(8)
+end
+-- one G+D step; returns errD, errG, errG_l2 as printed at train.lua:443-450 (host FloatTensors in, like the data loader delivers them)
+function Trainer:step(a, b, mask)
+  check(lib.cenn_trainer_step_host(self.h, a:data(), b:data(), mask and mask:data() or nil, self.losses:data()))
+  return self.losses[1], self.losses[2], self.losses[3]
+end
+-- write parameters and running statistics back into the nn modules (before util.save, util.lua:72-97)
+function Trainer:sync()
+  local f = torch.FloatTensor(self.pG:nElement()); check(lib.cenn_trainer_get_params_host(self.h, 0, f:data())); self.pG:copy(f)
+  f = torch.FloatTensor(self.pD:nElement()); check(lib.cenn_trainer_get_params_host(self.h, 1, f:data())); self.pD:copy(f)
+  for idx, net in ipairs{self.netG, self.netD} do
+    local n = ffi.new('int64_t[1]'); check(lib.cenn_trainer_bn_stat_count(self.h, idx - 1, n))
+    local st = torch.FloatTensor(tonumber(n[0])); check(lib.cenn_trainer_get_bn_stats_host(self.h, idx - 1, st:data()))
+    local off = 1
+    for _, m in ipairs(net:findModules('nn.SpatialBatchNormalization')) do
+      local C = m.running_mean:nElement()
+      m.running_mean:copy(st:narrow(1, off, C)); m.running_var:copy(st:narrow(1, off + C, C)); off = off + 2 * C
+    end
+  end
+end
+
+-- eval-mode generator + full-frame sweep (test_vid_wholeim.lua:98-226, demo.lua:68, test.lua:92)
+local Inpainter = torch.class('cenn.Inpainter')
+function Inpainter:__init(opt, net, batch)
+  local video = opt.predLen ~= nil or opt.inputLen ~= nil
+  local cfg = ffi.new('cenn_inpainter_config', {video and 1 or 0, batch or 64, opt.fineSize, opt.nBottleneck, opt.nef or 64, opt.ngf or 64, opt.nc or 3, opt.inputLen or opt.predLen or 1})
+  local h = ffi.new('cenn_inpainter*[1]'); check(lib.cenn_inpainter_create(S(), cfg, h)); self.h = ffi.gc(h[0], lib.cenn_inpainter_destroy)
+  check(lib.cenn_inpainter_load_host(self.h, net:getParameters():float():data(), bn_stats_of(net):data()))
+  self.maskValue, self.F = opt.maskValue, opt.fineSize
+end
+function Inpainter:forward(x)          -- x: FloatTensor [n, nc*inputLen, F, F] -> same shape (video) or [n, nc, F/2, F/2] (image)
+  local out = x.new():resizeAs(x)
+  check(lib.cenn_inpainter_forward_host(self.h, x:data(), out:data(), x:size(1))); return out
+end
+function Inpainter:sweep(images01, mask, init)   -- images01 [P, nc, inh, inw] in [0,1], mask ByteTensor [inh, inw] -> outImages, fullImages, inpaintImages
+  local P, nc, inh, inw = images01:size(1), images01:size(2), images01:size(3), images01:size(4)
+  local outh, outw = math.ceil(inh / self.F) * self.F, math.ceil(inw / self.F) * self.F
+  local o, f, i = torch.FloatTensor(P, nc, outh, outw), torch.FloatTensor(P, nc, outh, outw), torch.FloatTensor(P, nc, outh, outw)
+  check(lib.cenn_inpainter_sweep_host(self.h, init and init.h or nil, images01:data(), mask:data(), P, inh, inw, self.maskValue, o:data(), f:data(), i:data()))
+  return o, f, i
+end
+
 package.loaded['cunn'] = cenn                         -- `require 'cunn'` (train.lua:249) resolves to this module
 return cenn

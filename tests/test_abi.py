@@ -61,3 +61,61 @@ def test_fails_loudly_without_gpu():
     import video_filler_b200.tensor as T
     with pytest.raises(_lib.CennError):
         T.CudaTensor(4)
+
+
+def _struct_fields(src, name):
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            typ, names = decl.split(None, 1)
+            fields += [(n.strip(), typ) for n in names.split(",")]
+    return fields
+
+
+def test_inpainter_config_layout_matches_header():
+    fields = _struct_fields(open(_lib.HEADER).read(), "cenn_inpainter_config")
+    assert [f[0] for f in fields] == [f[0] for f in _lib.InpainterConfig._fields_]
+    assert all(t == "int" for _, t in fields) and C.sizeof(_lib.InpainterConfig) == 4 * len(fields)
+
+
+def test_lua_shim_prototypes_match_header():
+    """lua/cenn.lua cannot be executed here (no LuaJIT / Torch7): check statically that every prototype in its ffi.cdef
+    blocks names an exported function with the same parameter list, and that its struct declarations match the header."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lua = open(os.path.join(root, "lua", "cenn.lua")).read()
+    cdefs = "\n".join(re.findall(r"ffi\.cdef\[\[(.*?)\]\]", lua, re.S))
+    header = re.sub(r"/\*.*?\*/", " ", open(_lib.HEADER).read(), flags=re.S)
+
+    def norm(args):
+        out = []
+        for a in args.split(","):
+            a = re.sub(r"\s+", " ", a.strip())
+            m = re.match(r"(.*?)(\w+)$", a)
+            out.append(re.sub(r"\s*\*\s*", "*", m.group(1).strip()))
+        return out
+
+    hdr = {m.group(1): norm(m.group(2)) for m in re.finditer(r"CENN_API\s+[\w\s\*]+?\b(cenn_\w+)\s*\(([^;]*?)\)\s*;", header, re.S)}
+    seen = 0
+    for m in re.finditer(r"\b(?:int|const char \*)\s*(cenn_\w+)\s*\(([^;]*?)\)\s*;", cdefs, re.S):
+        name, args = m.group(1), m.group(2)
+        assert name in hdr, "lua/cenn.lua declares %s, which include/cenn.h does not export" % name
+        if args.strip() != "void":
+            assert norm(args) == hdr[name], name
+        seen += 1
+    assert seen >= 50
+    for struct in ("cenn_trainer_config", "cenn_inpainter_config"):
+        lua_fields = []
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), cdefs, re.S).group(1)
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                typ, names = decl.split(None, 1)
+                lua_fields += [(n.strip(), typ) for n in names.split(",")]
+        assert lua_fields == _struct_fields(open(_lib.HEADER).read(), struct), struct
+    # every lib.cenn_* call in the shim is declared in its cdef
+    declared = set(re.findall(r"\b(cenn_\w+)\s*\(", cdefs))
+    for call in set(re.findall(r"\blib\.(cenn_\w+)", lua)):
+        assert call in declared, "lua/cenn.lua calls %s without declaring it" % call

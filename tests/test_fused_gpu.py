@@ -175,7 +175,7 @@ def test_fused_losses_track_oracle_over_steps(cenn):
     assert np.all(np.isfinite(hg))
     # the L2 term (what the generator is actually trained on at wtl2 = 0.999): every step within 5 %, and the
     # mean over the last 10 steps within 2 % (trajectories separate through Adam's sign-like updates; the
-    # 100-step / 1 % north-star figure is measured at batch 64 by tools/parity_steps.py)
+    # 100-step / 1 % north-star figure is checked at batch 64 by test_losses_after_100_steps_match_oracle_fixture)
     assert np.max(np.abs(hg[:, 2] - ho[:, 2]) / ho[:, 2]) <= 5e-2
     assert abs(hg[-10:, 2].mean() - ho[-10:, 2].mean()) <= 2e-2 * ho[-10:, 2].mean()
     # the adversarial losses are chaotic in the GAN game at batch 8 (who is "winning" flips on tiny perturbations):
@@ -255,3 +255,25 @@ def test_fused_step_ragged_batch(cenn, variant, B):
         assert lg[k] == pytest.approx(lo[k], rel=8e-2), k          # tiny batches: BN over 3-5 samples at the bottleneck
     gG = trn.get_grads(0)
     assert np.all(np.isfinite(gG)) and _cos(gG, orc.gG) >= 0.9
+
+
+def test_losses_after_100_steps_match_oracle_fixture(cenn):
+    """north_star: losses after 100 steps within 1 %.  The oracle's 100 fp32 steps at the CPU config (batch 64, nBottleneck
+    4000) are a committed fixture (tools/parity_steps.py --make-golden); the executor replays the same seeded batches."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import parity_steps
+    if not os.path.exists(parity_steps.GOLDEN):
+        pytest.skip("tests/golden/losses_100.npz not generated")
+    ours, gold = parity_steps.run_executor()
+    s = parity_steps.summarize(ours, gold)
+    print(s)
+    assert len(ours) == 100 and np.all(np.isfinite(ours))
+    # the L2 term is what the generator is trained on at wtl2 = 0.999 (errG_total = 0.001 errG + 0.999 errG_l2 up to the edge weighting)
+    assert s["errG_l2"]["rel_at_last_step"] <= 1e-2 and s["errG_l2"]["rel_of_mean_last10"] <= 1e-2
+    assert s["errG_total"]["rel_at_last_step"] <= 1e-2
+    assert s["errG_l2"]["max_rel_all_steps"] <= 2e-2
+    # adversarial terms: the first step is a pure function of the inputs; later the GAN game amplifies rounding differences
+    assert abs(ours[0, 0] - gold[0, 0]) <= 1e-2 * gold[0, 0] and abs(ours[0, 1] - gold[0, 1]) <= 1e-2 * gold[0, 1]

@@ -51,6 +51,7 @@ void *cenn_workspace(cenn_state *s, size_t bytes);   // stream-ordered reuse; gr
 void *cenn_workspace2(cenn_state *s, size_t bytes);
 int cenn_dist_all_reduce_on(cenn_state *s, void *buf, int64_t count, int is_double, cudaStream_t stream);
 int cenn_dist_all_reduce_bulk(cenn_state *s, float *buf, int64_t count);
+int cenn_dist_all_reduce_bulk_bf16(cenn_state *s, void *buf, int64_t count);
 int cenn_dist_group(int begin);       // ncclGroupStart / ncclGroupEnd   // second communicator, s->comm_stream
 
 #define CK(expr) do { if (cenn_check_cuda((expr), #expr, __FILE__, __LINE__)) return 1; } while (0)

@@ -26,7 +26,7 @@ struct NcclApi {
     fn_get_id get_id = nullptr; fn_init_rank init_rank = nullptr; fn_all_reduce all_reduce = nullptr; fn_broadcast broadcast = nullptr; fn_all_gather all_gather = nullptr;
     fn_destroy destroy = nullptr; fn_errstr errstr = nullptr; fn_group group_start = nullptr, group_end = nullptr;
 } g_nccl;
-enum { NCCL_SUM = 0, NCCL_UINT8 = 1, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };
+enum { NCCL_SUM = 0, NCCL_UINT8 = 1, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_BFLOAT16 = 9 };
 
 int load_nccl() {
     if (g_nccl.handle) return 0;
@@ -71,6 +71,13 @@ int cenn_dist_all_reduce_bulk(cenn_state *s, float *buf, int64_t count) {
     if (!s->comm2 || !s->comm_stream) { cenn_set_error("cenn_dist_all_reduce_bulk: no bulk communicator"); return 1; }
     if (count <= 0) return 0;
     return nccl_check(g_nccl.all_reduce(buf, buf, (size_t)count, NCCL_FLOAT32, NCCL_SUM, s->comm2, s->comm_stream), "ncclAllReduce (bulk)");
+}
+
+// bf16 gradient bucket (in-place sum) on the bulk communicator
+int cenn_dist_all_reduce_bulk_bf16(cenn_state *s, void *buf, int64_t count) {
+    if (!s->comm2 || !s->comm_stream) { cenn_set_error("cenn_dist_all_reduce_bulk_bf16: no bulk communicator"); return 1; }
+    if (count <= 0) return 0;
+    return nccl_check(g_nccl.all_reduce(buf, buf, (size_t)count, NCCL_BFLOAT16, NCCL_SUM, s->comm2, s->comm_stream), "ncclAllReduce (bulk, bf16)");
 }
 
 extern "C" {

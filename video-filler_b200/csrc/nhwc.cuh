@@ -127,6 +127,22 @@ __global__ void __launch_bounds__(256) im2col_kernel(const bf16 *__restrict__ L,
         for (int k = 0; k < 2 * V8; ++k) dst[k] = make_uint4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
     }
 }
+// Cp == 16 (12 stacked channels): one thread per 16-byte chunk of the col row -- (tap, channel half) in K order -- so that
+// both the load (half a pixel, 16-byte aligned) and the store (consecutive threads, consecutive 16 bytes) are full vectors.
+__global__ void __launch_bounds__(256) im2col16_kernel(const bf16 *__restrict__ L, bf16 *__restrict__ col, int N, int h, int w) {
+    const int64_t total = (int64_t)N * h * w * 32;               // (pixel, tap, half)
+    const int H2 = 2 * h, W2 = 2 * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i & 31), tap = r >> 1, half = r & 1;
+        const int64_t pix = i >> 5;
+        const int ox = (int)(pix % w), oy = (int)((pix / w) % h), n = (int)(pix / ((int64_t)w * h));
+        const int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)iy < (unsigned)H2 && (unsigned)ix < (unsigned)W2)
+            v = __ldg(reinterpret_cast<const uint4 *>(L + (((int64_t)n * H2 + iy) * W2 + ix) * 16) + half);
+        reinterpret_cast<uint4 *>(col)[i] = v;
+    }
+}
 
 // ---------------------------------------------------------------- batch norm
 // sums -> mean / invstd / running stats / (scale, shift); `fold` column groups are summed (G1's GEMM epilogue
@@ -815,6 +831,35 @@ __global__ void __launch_bounds__(256) adam_bf16_kernel(float *__restrict__ x, c
         ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
 #undef ADAM1
         reinterpret_cast<float4 *>(x)[j] = X; reinterpret_cast<float4 *>(m)[j] = M; reinterpret_cast<float4 *>(v)[j] = V;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(X.x, X.y), h1 = __floats2bfloat162_rn(X.z, X.w);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+        reinterpret_cast<uint2 *>(xb)[j] = pk;
+    }
+}
+// Adam with the gradient read from a bf16 bucket (data parallel: the big generator blocks are all-reduced in bf16)
+__global__ void __launch_bounds__(256) adam_bf16g_kernel(float *__restrict__ x, const bf16 *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+        bf16 *__restrict__ xb, int64_t n, float b1, float b2, float eps, const float *__restrict__ step_ptr) {
+    const float step = *step_ptr;
+    int64_t n4 = n / 4;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (int64_t)gridDim.x * blockDim.x) {
+        float4 X = reinterpret_cast<float4 *>(x)[j];
+        const uint2 gp = reinterpret_cast<const uint2 *>(g)[j];
+        const __nv_bfloat162 g0 = *reinterpret_cast<const __nv_bfloat162 *>(&gp.x), g1 = *reinterpret_cast<const __nv_bfloat162 *>(&gp.y);
+        const float4 G = make_float4(__low2float(g0), __high2float(g0), __low2float(g1), __high2float(g1));
+        float4 M = reinterpret_cast<float4 *>(m)[j], V = reinterpret_cast<float4 *>(v)[j];
+#define ADAM1(c) M.c = M.c * b1 + (1.f - b1) * G.c; V.c = V.c * b2 + (1.f - b2) * G.c * G.c; X.c -= step * M.c / (sqrtf(V.c) + eps);
+        ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+        reinterpret_cast<float4 *>(x)[j] = X; reinterpret_cast<float4 *>(m)[j] = M; reinterpret_cast<float4 *>(v)[j] = V;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(X.x, X.y), h1 = __floats2bfloat162_rn(X.z, X.w);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+        reinterpret_cast<uint2 *>(xb)[j] = pk;
+    }
+}
+// fp32 -> bf16, 4 elements per thread (n % 4 == 0)
+__global__ void __launch_bounds__(256) f32_to_bf16_vec_kernel(const float *__restrict__ x, bf16 *__restrict__ xb, int64_t n4) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (int64_t)gridDim.x * blockDim.x) {
+        const float4 X = __ldg(reinterpret_cast<const float4 *>(x) + j);
         __nv_bfloat162 h0 = __floats2bfloat162_rn(X.x, X.y), h1 = __floats2bfloat162_rn(X.z, X.w);
         uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
         reinterpret_cast<uint2 *>(xb)[j] = pk;

@@ -63,6 +63,7 @@ struct Net {
     int64_t nparam_thnn = 0;  // Module:getParameters element count
     float *master = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
     bf16 *wbf = nullptr;
+    bf16 *gradbf = nullptr;   // data parallel: bf16 copies of the big weight-gradient blocks (what crosses NVLink)
     int64_t *bias_seg = nullptr;
     int nbias_seg = 0;
     nhwc::FoldJob *fold_jobs = nullptr;   // device: one job per block (conv gradBias <- partial rows)
@@ -359,6 +360,10 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         return 0;
     }
     if (!net.grad || !net.m || !net.v) return 1;
+    if (t->cfg.world_size > 1 && s->comm2 && single_pass && getenv("CENN_FP32_BUCKETS") == nullptr) {
+        net.gradbf = dalloc<bf16>(t, off);
+        if (!net.gradbf) return 1;
+    }
     net.nbias_seg = (int)bias_segs.size() / 2;
     net.bias_seg = dalloc<int64_t>(t, bias_segs.size());
     if (!net.bias_seg) return 1;
@@ -478,7 +483,7 @@ void emit_im2col(T *t, const Tensor &L, bf16 *col, int h, int w) {
     emit(t, "im2col", [s, Lc, col, h, w]() {
         int64_t total = (int64_t)Lc.N * h * w * 4;            // one thread per (pixel, window row)
         if (Lc.Cp == 4) nhwc::im2col_kernel<4><<<grid1d(s, total), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
-        else if (Lc.Cp == 16) nhwc::im2col_kernel<16><<<grid1d(s, total), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
+        else if (Lc.Cp == 16) nhwc::im2col16_kernel<<<grid1d(s, total * 8), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
         else { cenn_set_error("im2col: unsupported thin channel count %d", Lc.Cp); return 1; }
         KLAUNCH(s); return 0;
     });
@@ -651,10 +656,15 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
             float *ptr = grad + b->w_off; int64_t cnt = b->w_count;
             (bucket_g ? t->g_buckets : t->d_buckets).push_back({b->w_off, b->w_count});
-            emit(t, "grad_bucket_ar", [t, s, ev, ptr, cnt]() {
+            // generator buckets with an early Adam behind them travel as bf16 (half the NVLink bytes); Adam reads the bf16 sum
+            bf16 *pbf = (net.gradbf && cnt % 4 == 0 && getenv("CENN_NO_EARLY_ADAM") == nullptr) ? net.gradbf + b->w_off : nullptr;
+            emit(t, "grad_bucket_ar", [t, s, ev, ptr, pbf, cnt]() {
                 if (cenn_check_cuda(cudaEventRecord(ev, t->serial ? s->stream : t->side), "event record", __FILE__, __LINE__)) return 1;
                 if (cenn_check_cuda(cudaStreamWaitEvent(s->comm_stream, ev, 0), "stream wait", __FILE__, __LINE__)) return 1;
-                return cenn_dist_all_reduce_bulk(s, ptr, cnt); });
+                if (!pbf) return cenn_dist_all_reduce_bulk(s, ptr, cnt);
+                nhwc::f32_to_bf16_vec_kernel<<<grid1d(s, cnt / 4), 256, 0, s->comm_stream>>>(ptr, pbf, cnt / 4);
+                KLAUNCH(s);
+                return cenn_dist_all_reduce_bulk_bf16(s, pbf, cnt); });
         }
     } else if (b->thin && b->type == FULL_S2 && want_dgrad && b->has_dgrad) {
         emit_im2col(t, b->g, b->col, b->h, b->w);
@@ -702,6 +712,9 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
                 if (cenn_check_cuda(cudaStreamWaitEvent(t->side3, e2, 0), "stream wait", __FILE__, __LINE__)) return 1;
                 st = t->side3;
             }
+            if (dp_bulk && n->gradbf && cnt % 4 == 0)
+                nhwc::adam_bf16g_kernel<<<grid1d(s, cnt / 4), 256, 0, st>>>(n->master + off, n->gradbf + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
+            else
             nhwc::adam_bf16_kernel<<<grid1d(s, cnt / 4), 256, 0, st>>>(n->master + off, n->grad + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
             KLAUNCH(s); return 0; });
     }
