@@ -359,6 +359,11 @@ def main():
         e2e_ms = None
         for i in range(2):
             trn.step_host(host[i % n_batches][0], host[i % n_batches][1], host[i % n_batches][5])
+        for i in range(4):      # both staging sets of the pipelined path: first use runs eagerly, second captures its CUDA graph
+            trn.step_host_async(host[i % n_batches][0], host[i % n_batches][1], host[i % n_batches][5])
+            if i > 0:
+                trn.wait_losses()
+        trn.wait_losses()
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
