@@ -307,7 +307,7 @@ def main():
 
     drng = np.random.default_rng(1000 + rank)
     n_batches = 2
-    host = []
+    host, clips = [], []
     for _ in range(n_batches):
         if video:
             ctx, center, mask = synth.video_batch(B, 12, 128, opt["maskValue"], drng)
@@ -325,7 +325,15 @@ def main():
             hm = np.ctypeslib.as_array((C.c_uint8 * mask.size).from_address(pm.value)); hm[:] = mask.ravel()
             dmp = C.c_void_p(); api.cenn_malloc(st, mask.nbytes, C.byref(dmp)); api.cenn_copy_h2d(st, dmp, pm, mask.nbytes)
             dm = dmp.value
-            nbytes += mask.nbytes
+            # clip mode (the e2e call of the video workload): frames in [0,1] + ONE mask plane per sample + hflip flags;
+            # the device derives real_full, real_ctx and the expanded mask (datavid/donkey_folder.lua:161-187)
+            pf = C.c_void_p(); api.cenn_host_alloc(st, center.nbytes, C.byref(pf))
+            hf = np.ctypeslib.as_array((C.c_float * center.size).from_address(pf.value)); hf[:] = ((center + 1) * 0.5).ravel()
+            m1 = np.ascontiguousarray(mask[:, 0]); p1 = C.c_void_p(); api.cenn_host_alloc(st, m1.nbytes + B, C.byref(p1))
+            h1 = np.ctypeslib.as_array((C.c_uint8 * (m1.size + B)).from_address(p1.value)); h1[:m1.size] = m1.ravel()
+            h1[m1.size:] = drng.integers(0, 2, B).astype(np.uint8)
+            clips.append((hf, h1[:m1.size], h1[m1.size:], center.nbytes + m1.nbytes + B))
+            nbytes = clips[-1][3]
         host.append((ha, hb, da, db, nbytes, hm, dm))
 
     def step_device(i):
@@ -359,8 +367,15 @@ def main():
         e2e_ms = None
         for i in range(2):
             trn.step_host(host[i % n_batches][0], host[i % n_batches][1], host[i % n_batches][5])
+
+        def step_async(i):
+            if video:
+                c = clips[i % n_batches]
+                trn.step_clips_host_async(c[0], c[1], c[2], opt["maskValue"])
+            else:
+                trn.step_host_async(host[i % n_batches][0], host[i % n_batches][1])
         for i in range(4):      # both staging sets of the pipelined path: first use runs eagerly, second captures its CUDA graph
-            trn.step_host_async(host[i % n_batches][0], host[i % n_batches][1], host[i % n_batches][5])
+            step_async(i)
             if i > 0:
                 trn.wait_losses()
         trn.wait_losses()
@@ -371,7 +386,7 @@ def main():
         # public pipelined API: every step copies ITS inputs from pinned host memory and its losses are read back;
         # the copy of step k+1 overlaps the compute of step k, the losses of step k are read while step k+1 runs
         for i in range(args.steps):
-            trn.step_host_async(host[i % n_batches][0], host[i % n_batches][1], host[i % n_batches][5])
+            step_async(i)
             if i > 0:
                 losses = trn.wait_losses()
         losses = trn.wait_losses()

@@ -247,6 +247,15 @@ CENN_API int cenn_trainer_grad_buffer(cenn_trainer *t, int net, float **grads_de
 CENN_API int cenn_trainer_step_phase(cenn_trainer *t, int phase, const float *a_dev, const float *b_dev,
         const uint8_t *mask_dev);
 CENN_API int cenn_trainer_sync_info(cenn_trainer *t, void **buf_dev, int64_t *count, int *is_double, int *done);
+/* Clip-mode steps of the video variant: the per-sample hook of the video loader after its crop
+ * (datavid/donkey_folder.lua:161-187) runs on the device.  frames01 [B, nc*predLen, F, F] in [0,1]; mask1 [B, F, F], ONE plane
+ * per sample (non-zero = hole; the loader expands it over the channels); flip [B] (opt, non-zero = image.hflip of frames and
+ * mask).  The device derives real_full = 2f-1, real_ctx = maskedFill(maskValue) and the expanded mask -- less than half the
+ * host-to-device bytes of cenn_trainer_step_host.  The async form pairs with cenn_trainer_wait_losses. */
+CENN_API int cenn_trainer_step_clips_host(cenn_trainer *t, const float *frames01_host, const uint8_t *mask1_host,
+        const uint8_t *flip_host, float maskValue, float *losses_host);
+CENN_API int cenn_trainer_step_clips_host_async(cenn_trainer *t, const float *frames01_host, const uint8_t *mask1_host,
+        const uint8_t *flip_host, float maskValue);
 /* eval-mode generator forward (test_vid_wholeim.lua:180, demo.lua:68): in [B,Cin,F,F] -> out, host fp32 NCHW */
 CENN_API int cenn_trainer_generator_forward_host(cenn_trainer *t, const float *in_host, float *out_host, int batch);
 /* debugging / parity: copy an internal activation or gradient as fp32 NCHW to the host by name */

@@ -277,3 +277,50 @@ def test_losses_after_100_steps_match_oracle_fixture(cenn):
     assert s["errG_l2"]["max_rel_all_steps"] <= 2e-2
     # adversarial terms: the first step is a pure function of the inputs; later the GAN game amplifies rounding differences
     assert abs(ours[0, 0] - gold[0, 0]) <= 1e-2 * gold[0, 0] and abs(ours[0, 1] - gold[0, 1]) <= 1e-2 * gold[0, 1]
+
+
+def test_clip_mode_step_equals_three_tensor_step(cenn):
+    """cenn_trainer_step_clips_host (device-side maskedFill / expand / hflip / [0,1]->[-1,1], datavid/donkey_folder.lua:161-187)
+    against cenn_trainer_step_host fed with the same clips prepared on the host the way the loader does."""
+    from video_filler_b200 import models, train
+    kw = dict(batchSize=6, nBottleneck=128, nef=64, ngf=64, ndf=64, predLen=2, wtgdl=0.5)
+    opt = models.default_opt("video", **kw)
+    orc = ostep.StepOracle(onets.default_opt("video", **kw), seed=5, dtype=np.float64)
+    rng = np.random.default_rng(9)
+    frames = rng.uniform(0, 1, (6, 6, 128, 128)).astype(np.float32)
+    mask1 = np.zeros((6, 128, 128), np.uint8)
+    for b in range(6):
+        y, x = rng.integers(3, 80, 2)
+        mask1[b, y:y + 30, x:x + 40] = 1
+    flip = np.array([0, 1, 0, 1, 1, 0], np.uint8)
+    # the loader's hook on the host: maskedFill in [0,1], hflip of all three, then *2-1
+    mv = opt["maskValue"]
+    maskx = np.repeat(mask1[:, None], 6, axis=1)
+    masked01 = np.where(maskx != 0, np.float32(mv), frames)
+    f = flip.astype(bool)
+    full, masked, maskh = frames.copy(), masked01.copy(), maskx.copy()
+    full[f], masked[f], maskh[f] = full[f][..., ::-1], masked[f][..., ::-1], maskh[f][..., ::-1]
+    full, masked = full * 2 - 1, masked * 2 - 1
+    res = []
+    for mode in ("host", "clips", "clips_noflip"):
+        trn = train.FusedTrainer(opt, precision="bf16")
+        trn.set_params(0, orc.pG); trn.set_params(1, orc.pD)
+        if mode == "host":
+            losses = trn.step_host(masked, full, maskh)
+        elif mode == "clips":
+            losses = trn.step_clips_host(frames, mask1, flip)
+            losses2 = trn.step_clips_host(frames, mask1, flip)          # second call: captured graph, updated weights
+            assert np.isfinite(list(losses2.values())).all() and losses2["errG_l2"] != losses["errG_l2"]
+        else:
+            losses = trn.step_clips_host(frames, mask1, None)
+        res.append((losses, trn.fetch("ctx"), trn.get_grads(1)))
+        trn.close()
+    (l0, ctx0, g0), (l1, ctx1, g1), (l2, ctx2, _) = res
+    assert np.array_equal(ctx0, ctx1)                                    # identical bf16 inputs on both paths
+    assert not np.array_equal(ctx1, ctx2)                                # the flags do something
+    for k in ("errG_l2", "errG_gdl", "errD", "errG"):
+        assert abs(l0[k] - l1[k]) <= 2e-3 * max(abs(l0[k]), 1e-3), (k, l0[k], l1[k])   # run-to-run spread of the executor (atomics order)
+    assert _cos(g0, g1) >= 0.97
+    with pytest.raises(Exception, match="video variant"):
+        img = train.FusedTrainer(models.default_opt("image", batchSize=2, nBottleneck=128), precision="bf16")
+        img.step_clips_host(frames[:2, :3], mask1[:2], None, maskValue=0.4)

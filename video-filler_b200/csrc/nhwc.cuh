@@ -931,6 +931,44 @@ __global__ void fold_bn_bias_kernel(const float *__restrict__ bias, const float 
     out[i] = v;
 }
 
+// Device-side clip preparation of the video loader's per-sample hook (datavid/donkey_folder.lua:161-187), after the crop:
+// frames01 [N][C][H][W] in [0,1] and ONE mask plane per sample [N][H][W] -> the three step inputs as NHWC bf16:
+//   full = 2f-1, masked = mask ? 2*maskValue-1 : full, mask expanded over the channels; flip[n] != 0 mirrors all three (hflip).
+template <int CP>
+__global__ void __launch_bounds__(256) clip_prepare_kernel(const float *__restrict__ frames01, const uint8_t *__restrict__ mask1, const uint8_t *__restrict__ flip,
+        float maskValue, int N, int C, int H, int W, bf16 *__restrict__ masked, bf16 *__restrict__ full, bf16 *__restrict__ maskx) {
+    const int HW = H * W;
+    const int64_t total = (int64_t)N * HW;
+    const float fillv = 2.f * maskValue - 1.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / HW), r = (int)(i - (int64_t)n * HW), y = r / W, x = r - y * W;
+        const int xs = (flip && flip[n]) ? W - 1 - x : x;
+        const bool m = mask1[(int64_t)n * HW + y * W + xs] != 0;
+        __align__(16) bf16 vf[CP], vm[CP], vk[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            float f = 0.f, k = 0.f, mk = 0.f;
+            if (c < C) {
+                f = __ldg(frames01 + ((int64_t)n * C + c) * HW + y * W + xs) * 2.f - 1.f;
+                k = m ? fillv : f; mk = m ? 1.f : 0.f;
+            }
+            vf[c] = __float2bfloat16(f); vk[c] = __float2bfloat16(k); vm[c] = __float2bfloat16(mk);
+        }
+        if (CP == 4) {
+            *reinterpret_cast<uint2 *>(full + i * CP) = *reinterpret_cast<const uint2 *>(vf);
+            *reinterpret_cast<uint2 *>(masked + i * CP) = *reinterpret_cast<const uint2 *>(vk);
+            *reinterpret_cast<uint2 *>(maskx + i * CP) = *reinterpret_cast<const uint2 *>(vm);
+        } else {
+#pragma unroll
+            for (int q = 0; q < CP / 8; ++q) {
+                reinterpret_cast<uint4 *>(full + i * CP)[q] = reinterpret_cast<const uint4 *>(vf)[q];
+                reinterpret_cast<uint4 *>(masked + i * CP)[q] = reinterpret_cast<const uint4 *>(vk)[q];
+                reinterpret_cast<uint4 *>(maskx + i * CP)[q] = reinterpret_cast<const uint4 *>(vm)[q];
+            }
+        }
+    }
+}
+
 // Full-frame sweep of test_vid_wholeim.lua:98-226.  Tile j = ti * groups + g: ti walks the padded frame row-major in FxF tiles,
 // g is the frame group (ncin = nc * inputLen stacked channels); the first three tiles of the top row are fed upside down (:167-170).
 struct SweepGeom { int P, nc, inh, inw, outh, outw, F, ncin, Cp, groups, tiles_w; };

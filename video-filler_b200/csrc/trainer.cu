@@ -150,6 +150,10 @@ struct cenn_trainer {
     std::vector<std::pair<int64_t, int64_t>> g_buckets;   // (offset, count) of G's gradient ranges reduced on the bulk communicator
     std::vector<std::pair<int64_t, int64_t>> d_buckets;   // same for D (second sweep of the step only: the first one just accumulates)
     bool d_bucket_sweep = false;
+    // clip mode (cenn_trainer_step_clips_*): cur_a == nullptr, cur_b = frames01 [B,C,F,F], cur_m = one mask plane per sample, cur_f = hflip flags
+    uint8_t *in_f = nullptr, *in_f2 = nullptr;
+    const uint8_t *cur_f = nullptr;
+    float clip_mv = -1.f;                 // maskValue baked into the captured clip-mode graphs
     bool infer = false;                   // inference engine (cenn_inpainter_*): forward plans only, BN folded into weights and bias
     int infer_n = 0;                      // tiles converted in / out by the current forward call
 };
@@ -836,6 +840,15 @@ int build_program(T *t) {
     // -- inputs: fp32 NCHW (+ uint8 mask) -> NHWC bf16
     emit(t, "convert_inputs", [t, s, video]() {
         const Tensor &a = t->real_ctx, &b = t->real_aux;
+        if (video && !t->cur_a) {       // clip mode: masked / full / expanded mask derived on the device from the frames and one mask plane
+            const Tensor &m = t->mask;
+            const float mv = t->clip_mv;
+            if (a.Cp == 16) nhwc::clip_prepare_kernel<16><<<grid1d(s, a.pix()), 256, 0, s->stream>>>(t->cur_b, t->cur_m, t->cur_f, mv, a.N, a.C, a.H, a.W, a.p, b.p, m.p);
+            else if (a.Cp == 4) nhwc::clip_prepare_kernel<4><<<grid1d(s, a.pix()), 256, 0, s->stream>>>(t->cur_b, t->cur_m, t->cur_f, mv, a.N, a.C, a.H, a.W, a.p, b.p, m.p);
+            else { cenn_set_error("clip mode: unsupported channel padding %d", a.Cp); return 1; }
+            KLAUNCH(s);
+            return cenn_check_cuda(cudaMemsetAsync(t->loss_acc, 0, 8 * sizeof(double), s->stream), "memset", __FILE__, __LINE__);
+        }
         for (const Tensor *x : {&a, &b}) {
             const float *src = x == &a ? t->cur_a : t->cur_b;
             if (x->Cp == 4 && (x->H * x->W) % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
@@ -1257,6 +1270,19 @@ int cenn_trainer_step_device(cenn_trainer *t, const float *a, const float *b, co
     t->launches_per_step = t->s->launches - before;
     return rc;
 }
+static int step_clips_device(cenn_trainer *t, const float *frames, const uint8_t *mask1, const uint8_t *flip, float maskValue) {
+    if (maskValue != t->clip_mv) {        // the value is a kernel argument inside the captured graphs: a new value invalidates them
+        cudaStreamSynchronize(t->s->stream);
+        for (auto &g : t->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
+        t->graphs.clear();
+        t->clip_mv = maskValue;
+    }
+    t->cur_a = nullptr; t->cur_b = frames; t->cur_m = mask1; t->cur_f = flip;
+    int64_t before = t->s->launches;
+    int rc = run_step(t);
+    t->launches_per_step = t->s->launches - before;
+    return rc;
+}
 int cenn_trainer_read_losses(cenn_trainer *t, float *losses) {
     REQUIRE(t && losses, "cenn_trainer_read_losses: null argument");
     API_BEGIN(t->s);
@@ -1318,6 +1344,53 @@ int cenn_trainer_wait_losses(cenn_trainer *t, float *losses) {
     CK(cudaEventSynchronize(t->ev_loss[i]));
     memcpy(losses, t->pin_loss2 + 8 * i, 8 * sizeof(float));
     t->async_read++;
+    return 0;
+}
+
+// Clip-mode steps (video variant): the host hands over what the loader has after its crop -- frames in [0,1], ONE mask plane per
+// sample, hflip flags -- and the device derives real_full, real_ctx (masked fill) and the expanded mask
+// (datavid/donkey_folder.lua:161-187).  Less than half the H2D bytes of the three-tensor form.
+int cenn_trainer_step_clips_host(cenn_trainer *t, const float *frames01, const uint8_t *mask1, const uint8_t *flip, float maskValue, float *losses) {
+    REQUIRE(t && frames01 && mask1 && losses, "cenn_trainer_step_clips_host: null argument");
+    REQUIRE(t->cfg.variant == 1, "cenn_trainer_step_clips_host: clips belong to the video variant");
+    API_BEGIN(t->s);
+    cudaStream_t st = t->s->stream;
+    if (!t->in_f) { t->in_f = dalloc<uint8_t>(t, t->B); REQUIRE(t->in_f, "trainer: staging allocation failed"); }
+    CK(cudaMemcpyAsync(t->in_b, frames01, t->n_b * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(t->in_m, mask1, (size_t)t->B * t->F * t->F, cudaMemcpyHostToDevice, st));
+    if (flip) CK(cudaMemcpyAsync(t->in_f, flip, t->B, cudaMemcpyHostToDevice, st)); else CK(cudaMemsetAsync(t->in_f, 0, t->B, st));
+    if (step_clips_device(t, t->in_b, t->in_m, t->in_f, maskValue)) return 1;   // always a flag buffer: the pointer is baked into the captured graph
+    return cenn_trainer_read_losses(t, losses);
+}
+int cenn_trainer_step_clips_host_async(cenn_trainer *t, const float *frames01, const uint8_t *mask1, const uint8_t *flip, float maskValue) {
+    REQUIRE(t && frames01 && mask1, "cenn_trainer_step_clips_host_async: null argument");
+    REQUIRE(t->cfg.variant == 1, "cenn_trainer_step_clips_host_async: clips belong to the video variant");
+    API_BEGIN(t->s);
+    REQUIRE(t->async_issued - t->async_read < 2, "cenn_trainer_step_clips_host_async: two steps already in flight; call cenn_trainer_wait_losses");
+    cudaStream_t st = t->s->stream;
+    if (!t->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&t->ev_copied[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&t->ev_consumed[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&t->ev_loss[i], cudaEventDisableTiming)); }
+        t->in_a2 = dalloc<float>(t, t->n_a); t->in_b2 = dalloc<float>(t, t->n_b);
+        t->in_m2 = dalloc<uint8_t>(t, t->n_m);
+        REQUIRE(t->in_a2 && t->in_b2 && t->in_m2, "trainer: staging allocation failed");
+        CK(cudaMallocHost(&t->pin_loss2, 2 * 8 * sizeof(float)));
+    }
+    if (!t->in_f) { t->in_f = dalloc<uint8_t>(t, t->B); REQUIRE(t->in_f, "trainer: staging allocation failed"); }
+    if (!t->in_f2) { t->in_f2 = dalloc<uint8_t>(t, t->B); REQUIRE(t->in_f2, "trainer: staging allocation failed"); }
+    const int i = (int)(t->async_issued & 1);
+    float *db = i ? t->in_b2 : t->in_b; uint8_t *dm = i ? t->in_m2 : t->in_m, *df = i ? t->in_f2 : t->in_f;
+    if (t->consumed_valid[i]) CK(cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[i], 0));
+    CK(cudaMemcpyAsync(db, frames01, t->n_b * 4, cudaMemcpyHostToDevice, t->copy_stream));
+    CK(cudaMemcpyAsync(dm, mask1, (size_t)t->B * t->F * t->F, cudaMemcpyHostToDevice, t->copy_stream));
+    if (flip) CK(cudaMemcpyAsync(df, flip, t->B, cudaMemcpyHostToDevice, t->copy_stream)); else CK(cudaMemsetAsync(df, 0, t->B, t->copy_stream));
+    CK(cudaEventRecord(t->ev_copied[i], t->copy_stream));
+    CK(cudaStreamWaitEvent(st, t->ev_copied[i], 0));
+    if (step_clips_device(t, db, dm, df, maskValue)) return 1;
+    CK(cudaEventRecord(t->ev_consumed[i], st)); t->consumed_valid[i] = true;
+    CK(cudaMemcpyAsync(t->pin_loss2 + 8 * i, t->loss_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(t->ev_loss[i], st));
+    t->async_issued++;
     return 0;
 }
 

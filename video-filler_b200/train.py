@@ -270,6 +270,24 @@ class FusedTrainer:
         api().cenn_trainer_wait_losses(self.h, losses.ctypes.data_as(C.c_void_p))
         return dict(zip(LOSS_NAMES, losses.tolist()))
 
+    def step_clips_host(self, frames01, mask1, flip=None, maskValue=None):
+        """Clip-mode step (video variant): frames01 [B, nc*predLen, F, F] in [0,1], mask1 [B, F, F] uint8 (one plane per
+        sample), flip [B] uint8 or None; the device derives real_full, real_ctx and the expanded mask."""
+        frames01 = np.ascontiguousarray(frames01, np.float32)
+        mask1 = np.ascontiguousarray(mask1, np.uint8)
+        f = np.ascontiguousarray(flip, np.uint8).ctypes.data_as(C.c_void_p) if flip is not None else None
+        mv = float(self.opt["maskValue"] if maskValue is None else maskValue)
+        losses = np.zeros(8, np.float32)
+        api().cenn_trainer_step_clips_host(self.h, frames01.ctypes.data_as(C.c_void_p), mask1.ctypes.data_as(C.c_void_p), f, mv,
+                                           losses.ctypes.data_as(C.c_void_p))
+        return dict(zip(LOSS_NAMES, losses.tolist()))
+
+    def step_clips_host_async(self, frames01, mask1, flip=None, maskValue=None):
+        assert frames01.dtype == np.float32 and frames01.flags.c_contiguous and mask1.dtype == np.uint8 and mask1.flags.c_contiguous
+        f = flip.ctypes.data_as(C.c_void_p) if flip is not None else None
+        mv = float(self.opt["maskValue"] if maskValue is None else maskValue)
+        api().cenn_trainer_step_clips_host_async(self.h, frames01.ctypes.data_as(C.c_void_p), mask1.ctypes.data_as(C.c_void_p), f, mv)
+
     def step_device(self, a_ptr, b_ptr, mask_ptr=None):
         api().cenn_trainer_step_device(self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr),
                                        C.c_void_p(mask_ptr) if mask_ptr else None)
