@@ -95,6 +95,13 @@ CENN_API int cenn_fill_box(cenn_state *s, float *x, int64_t N, int64_t C, int64_
 /* dst = src[:, :, y0:y0+h, x0:x0+w] cloned contiguous (train.lua:287 centre crop) */
 CENN_API int cenn_crop(cenn_state *s, float *dst, const float *src, int64_t N, int64_t C, int64_t H, int64_t W,
                        int64_t y0, int64_t x0, int64_t h, int64_t w);
+/* nn.JoinTable(2) on batch-mode tensors (train.lua:120,177; noiseGen / conditionAdv): each sample of `joined` is
+ * `joined_per_sample` contiguous floats, of which [offset, offset + part_per_sample) belong to `part`.
+ * updateOutput copies part -> joined, updateGradInput copies the matching narrow of gradOutput -> gradPart. */
+CENN_API int cenn_JoinTable_updateOutput(cenn_state *s, float *joined, const float *part, int64_t batch,
+        int64_t joined_per_sample, int64_t offset, int64_t part_per_sample);
+CENN_API int cenn_JoinTable_updateGradInput(cenn_state *s, const float *gradJoined, float *gradPart, int64_t batch,
+        int64_t joined_per_sample, int64_t offset, int64_t part_per_sample);
 /* Philox-based :normal(mean,std) / :uniform(a,b) (train.lua:61,64,269-272) */
 CENN_API int cenn_normal(cenn_state *s, float *x, int64_t n, float mean, float std, uint64_t seed);
 CENN_API int cenn_uniform(cenn_state *s, float *x, int64_t n, float a, float b, uint64_t seed);

@@ -37,9 +37,18 @@ def build_netG(opt, dtype=np.float32):
     netE.add(C(nef * 4, nef * 8, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(BN(nef * 8, dtype=dtype)).add(nn.LeakyReLU(0.2, True))
     netE.add(C(nef * 8, nB, 4, 4, dtype=dtype))
     netG = nn.Sequential()
-    netG.add(netE)
-    netG.add(BN(nB, dtype=dtype)).add(nn.LeakyReLU(0.2, True))
-    netG.add(FC(nB, ngf * 8, 4, 4, dtype=dtype)).add(BN(ngf * 8, dtype=dtype)).add(nn.ReLU(True))
+    nz_size = nB
+    if opt.get('noiseGen'):
+        # train.lua:109-124: a 1x1 conv on the noise vector runs beside the encoder, joined along the channel axis
+        nz = opt.get('nz', 100)
+        netG_noise = nn.Sequential().add(C(nz, nz, 1, 1, 1, 1, 0, 0, dtype=dtype))
+        netG.add(nn.ParallelTable().add(netE).add(netG_noise))
+        netG.add(nn.JoinTable(2))
+        nz_size = nB + nz
+    else:
+        netG.add(netE)
+    netG.add(BN(nz_size, dtype=dtype)).add(nn.LeakyReLU(0.2, True))
+    netG.add(FC(nz_size, ngf * 8, 4, 4, dtype=dtype)).add(BN(ngf * 8, dtype=dtype)).add(nn.ReLU(True))
     netG.add(FC(ngf * 8, ngf * 4, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(BN(ngf * 4, dtype=dtype)).add(nn.ReLU(True))
     netG.add(FC(ngf * 4, ngf * 2, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(BN(ngf * 2, dtype=dtype)).add(nn.ReLU(True))
     netG.add(FC(ngf * 2, ngf, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(BN(ngf, dtype=dtype)).add(nn.ReLU(True))
@@ -60,6 +69,14 @@ def build_netD(opt, dtype=np.float32):
         mylayer = ndf // 2
         netD.add(C(nc, mylayer, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(nn.LeakyReLU(0.2, True))
         netD.add(C(mylayer, ndf, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(nn.LeakyReLU(0.2, True))
+    elif opt.get('conditionAdv'):
+        # train.lua:158-180: D also sees the context; the 64x64 prediction is padded by 32 so that both branches give 64x64 maps
+        netD_ctx = nn.Sequential().add(C(nc, ndf, 5, 5, 2, 2, 2, 2, dtype=dtype))
+        netD_pred = nn.Sequential().add(C(nc, ndf, 5, 5, 2, 2, 2 + 32, 2 + 32, dtype=dtype))
+        netD.add(nn.ParallelTable().add(netD_ctx).add(netD_pred))
+        netD.add(nn.JoinTable(2))
+        netD.add(nn.LeakyReLU(0.2, True))
+        netD.add(C(ndf * 2, ndf, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(BN(ndf, dtype=dtype)).add(nn.LeakyReLU(0.2, True))
     else:
         netD.add(C(nc, ndf, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(nn.LeakyReLU(0.2, True))
     netD.add(C(ndf, ndf * 2, 4, 4, 2, 2, 1, 1, dtype=dtype)).add(BN(ndf * 2, dtype=dtype)).add(nn.LeakyReLU(0.2, True))

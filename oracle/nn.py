@@ -166,6 +166,70 @@ class Sequential(Module):
             m._collect_holders(out)
 
 
+class ParallelTable(Module):
+    """nn.ParallelTable: the i-th member module is applied to the i-th element of the input table
+    (train.lua:115-118 noiseGen, :170-174 conditionAdv)."""
+
+    def __init__(self):
+        super().__init__()
+        self.modules = []
+
+    def add(self, m):
+        self.modules.append(m)
+        return self
+
+    def updateOutput(self, xs):
+        self.output = [m.updateOutput(x) for m, x in zip(self.modules, xs)]
+        return self.output
+
+    def updateGradInput(self, xs, gys):
+        self.gradInput = [m.updateGradInput(x, gy) for m, x, gy in zip(self.modules, xs, gys)]
+        return self.gradInput
+
+    def accGradParameters(self, xs, gys, scale=1.0):
+        for m, x, gy in zip(self.modules, xs, gys):
+            m.accGradParameters(x, gy, scale)
+
+    def backward(self, xs, gys, scale=1.0):
+        self.gradInput = [m.backward(x, gy, scale) for m, x, gy in zip(self.modules, xs, gys)]
+        return self.gradInput
+
+    def parameters(self):
+        ps, gs = [], []
+        for m in self.modules:
+            p, g = m.parameters()
+            ps += p
+            gs += g
+        return ps, gs
+
+    def apply(self, fn):
+        fn(self)
+        for m in self.modules:
+            m.apply(fn)
+
+    def _collect_holders(self, out):
+        for m in self.modules:
+            m._collect_holders(out)
+
+
+class JoinTable(Module):
+    """nn.JoinTable(dimension): concatenates the tensors of the input table along `dimension` (1-based; the scripts use
+    JoinTable(2) on batch-mode 4-D tensors = the channel axis, train.lua:120,177); gradInput = the matching narrows."""
+
+    def __init__(self, dimension):
+        super().__init__()
+        self.dimension = dimension
+
+    def updateOutput(self, xs):
+        self.output = np.concatenate(xs, axis=self.dimension - 1)
+        return self.output
+
+    def updateGradInput(self, xs, gy):
+        sizes = [x.shape[self.dimension - 1] for x in xs]
+        self.gradInput = [g.copy() for g in np.split(gy, np.cumsum(sizes)[:-1], axis=self.dimension - 1)]
+        return self.gradInput
+
+
 class SpatialConvolution(Module):
     def __init__(self, nIn, nOut, kW, kH, dW=1, dH=1, padW=0, padH=None, dtype=np.float32):
         super().__init__()

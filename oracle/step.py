@@ -34,8 +34,17 @@ class StepOracle:
         self.errD_real = self.errD_fake = None
 
     # -- closures --------------------------------------------------------
-    def fDx_image(self, real_ctx, real_center):
+    def _d_in(self, center):
+        return [self.input_ctx, center] if self.opt.get('conditionAdv') else center      # train.lua:300-311
+
+    def _g_in(self):
+        return [self.input_ctx, self.noise] if self.opt.get('noiseGen') else self.input_ctx   # train.lua:325-329
+
+    def fDx_image(self, real_ctx, real_center, noise=None):
         o = self.opt
+        if o.get('noiseGen'):
+            assert noise is not None, "noiseGen: the step takes the noise tensor [B, nz, 1, 1] drawn at train.lua:319-323"
+            self.noise = nn._q(noise.astype(self.dtype))
         nets.zero_conv_bias(self.netD)
         nets.zero_conv_bias(self.netG)
         self.gD[...] = 0
@@ -43,17 +52,17 @@ class StepOracle:
         self.input_ctx = nn._q(real_ctx.astype(self.dtype))
         self.input_real_center = nn._q(real_center.astype(self.dtype))
         label = np.full(B, 1.0, self.dtype)
-        out = self.netD.forward(self.input_real_center)
+        out = self.netD.forward(self._d_in(self.input_real_center))
         self.errD_real = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
-        self.netD.backward(self.input_real_center, df_do)
-        fake = self.netG.forward(self.input_ctx)
+        self.netD.backward(self._d_in(self.input_real_center), df_do)
+        fake = self.netG.forward(self._g_in())
         self.input_center = fake.copy()
         label[...] = 0.0
-        out = self.netD.forward(self.input_center)
+        out = self.netD.forward(self._d_in(self.input_center))
         self.errD_fake = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
-        self.netD.backward(self.input_center, df_do)
+        self.netD.backward(self._d_in(self.input_center), df_do)
         self.errD = self.errD_real + self.errD_fake
         return self.errD
 
@@ -67,7 +76,9 @@ class StepOracle:
         out = self.netD.output
         self.errG = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
-        df_dg = self.netD.updateGradInput(self.input_center, df_do)
+        df_dg = self.netD.updateGradInput(self._d_in(self.input_center), df_do)
+        if o.get('conditionAdv'):
+            df_dg = df_dg[1]            # train.lua:371: df_dg[2], the prediction branch
         total = self.errG
         wtl2 = o['wtl2']
         if wtl2 != 0:
@@ -75,7 +86,7 @@ class StepOracle:
             df_dg = ops.blend_l2_overlap(df_dg, self.input_center, self.input_real_center, wtl2, o['overlapPred'])
             total = ((1 - wtl2) * self.errG + wtl2 * self.errG_l2) if 0 < wtl2 < 1 else self.errG + wtl2 * self.errG_l2
         self.df_dg = df_dg = nn._q(df_dg)
-        self.netG.backward(self.input_ctx, df_dg)
+        self.netG.backward(self._g_in(), df_dg)
         return total
 
     def fDx_video(self, real_ctx, real_full, real_mask):

@@ -167,3 +167,32 @@ def test_blend_and_composite_and_adam():
         v_ = 0.999 * v_ + 0.001 * gr * gr
         p -= 2e-4 * np.sqrt(1 - 0.999 ** step) / (1 - 0.5 ** step) * m_ / (np.sqrt(v_) + 1e-8)
     assert np.allclose(p1, p, atol=1e-15)
+
+
+def test_parallel_join_tables_match_autograd():
+    """nn.ParallelTable + nn.JoinTable(2) as used by conditionAdv (train.lua:158-180): two 5x5/s2 convs (pad 2 on the 16x16
+    'context', pad 2+4 on the 8x8 'prediction' so that both give 8x8 maps), joined along the channel axis, LeakyReLU."""
+    from oracle import nn as onn
+    net = onn.Sequential()
+    a = onn.SpatialConvolution(3, 4, 5, 5, 2, 2, 2, 2, dtype=np.float64)
+    b = onn.SpatialConvolution(3, 4, 5, 5, 2, 2, 2 + 4, 2 + 4, dtype=np.float64)
+    net.add(onn.ParallelTable().add(onn.Sequential().add(a)).add(onn.Sequential().add(b))).add(onn.JoinTable(2)).add(onn.LeakyReLU(0.2, False))
+    for m in (a, b):
+        m.weight[...] = RNG.normal(size=m.weight.shape)
+        m.bias[...] = RNG.normal(size=m.bias.shape)
+    xa, xb = RNG.normal(size=(2, 3, 16, 16)), RNG.normal(size=(2, 3, 8, 8))
+    ta, tb = T(xa, True), T(xb, True)
+    wa, ba, wb, bb = T(a.weight, True), T(a.bias, True), T(b.weight, True), T(b.bias, True)
+    y = F.leaky_relu(torch.cat([F.conv2d(ta, wa, ba, stride=2, padding=2), F.conv2d(tb, wb, bb, stride=2, padding=6)], dim=1), 0.2)
+    out = net.forward([xa, xb])
+    assert out.shape == (2, 8, 8, 8) and np.allclose(out, y.detach().numpy(), atol=1e-12)
+    gy = RNG.normal(size=out.shape)
+    y.backward(T(gy))
+    net.zeroGradParameters()
+    gin = net.backward([xa, xb], gy)
+    assert np.allclose(gin[0], ta.grad.numpy(), atol=1e-11) and np.allclose(gin[1], tb.grad.numpy(), atol=1e-11)
+    assert np.allclose(a.gradWeight, wa.grad.numpy(), atol=1e-10) and np.allclose(b.gradWeight, wb.grad.numpy(), atol=1e-10)
+    assert np.allclose(a.gradBias, ba.grad.numpy(), atol=1e-10) and np.allclose(b.gradBias, bb.grad.numpy(), atol=1e-10)
+    # getParameters walks the table members in order (train.lua:262-263)
+    flat, _ = net.getParameters()
+    assert flat.size == 2 * (4 * 3 * 25 + 4)

@@ -212,6 +212,23 @@ int cenn_crop(cenn_state *s, float *dst, const float *src, int64_t N, int64_t C,
     if (total > 0) { crop_kernel<<<bw_grid(s, total, 256), 256, 0, s->stream>>>(dst, src, N * C, H, W, y0, x0, h, w); CK_LAUNCH(s); }
     return 0;
 }
+// nn.JoinTable(2): strided device-to-device copies (one 2-D copy per table member; no kernel)
+int cenn_JoinTable_updateOutput(cenn_state *s, float *joined, const float *part, int64_t batch, int64_t joined_per_sample, int64_t offset, int64_t part_per_sample) {
+    API_BEGIN(s);
+    REQUIRE(joined && part && batch >= 0 && offset >= 0 && part_per_sample >= 0 && offset + part_per_sample <= joined_per_sample, "JoinTable: slice [%lld, %lld) outside %lld",
+            (long long)offset, (long long)(offset + part_per_sample), (long long)joined_per_sample);
+    if (batch == 0 || part_per_sample == 0) return 0;
+    CK(cudaMemcpy2DAsync(joined + offset, (size_t)joined_per_sample * 4, part, (size_t)part_per_sample * 4, (size_t)part_per_sample * 4, (size_t)batch, cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+int cenn_JoinTable_updateGradInput(cenn_state *s, const float *gradJoined, float *gradPart, int64_t batch, int64_t joined_per_sample, int64_t offset, int64_t part_per_sample) {
+    API_BEGIN(s);
+    REQUIRE(gradJoined && gradPart && batch >= 0 && offset >= 0 && part_per_sample >= 0 && offset + part_per_sample <= joined_per_sample, "JoinTable: slice [%lld, %lld) outside %lld",
+            (long long)offset, (long long)(offset + part_per_sample), (long long)joined_per_sample);
+    if (batch == 0 || part_per_sample == 0) return 0;
+    CK(cudaMemcpy2DAsync(gradPart, (size_t)part_per_sample * 4, gradJoined + offset, (size_t)joined_per_sample * 4, (size_t)part_per_sample * 4, (size_t)batch, cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
 int cenn_normal(cenn_state *s, float *x, int64_t n, float mean, float std, uint64_t seed) {
     API_BEGIN(s);
     if (n > 0) { rng_kernel<<<bw_grid(s, n / 4 + 1, 256), 256, 0, s->stream>>>(x, n, mean, std, seed, 1); CK_LAUNCH(s); }

@@ -31,9 +31,17 @@ def build_netG(opt):
         netE.add(Conv(cin, cout, 4, 4, 2, 2, 1, 1)).add(BN(cout)).add(nn.LeakyReLU(0.2, True))
     netE.add(Conv(nef * 8, nB, 4, 4))
     netG = nn.Sequential()
-    netG.add(netE)
-    netG.add(BN(nB)).add(nn.LeakyReLU(0.2, True))
-    netG.add(Full(nB, ngf * 8, 4, 4)).add(BN(ngf * 8)).add(nn.ReLU(True))
+    nz_size = nB
+    if opt.get("noiseGen"):               # train.lua:109-124
+        nz = opt.get("nz", 100)
+        netG_noise = nn.Sequential().add(Conv(nz, nz, 1, 1, 1, 1, 0, 0))
+        netG.add(nn.ParallelTable().add(netE).add(netG_noise))
+        netG.add(nn.JoinTable(2))
+        nz_size = nB + nz
+    else:
+        netG.add(netE)
+    netG.add(BN(nz_size)).add(nn.LeakyReLU(0.2, True))
+    netG.add(Full(nz_size, ngf * 8, 4, 4)).add(BN(ngf * 8)).add(nn.ReLU(True))
     chain = [(ngf * 8, ngf * 4), (ngf * 4, ngf * 2), (ngf * 2, ngf)]
     if opt["variant"] == "video":
         chain.append((ngf, ngf))          # train_vid_weighted.lua:171-172
@@ -52,6 +60,13 @@ def build_netD(opt):
         mylayer = ndf // 2                # train_vid_weighted.lua:213-221
         netD.add(Conv(nc, mylayer, 4, 4, 2, 2, 1, 1)).add(nn.LeakyReLU(0.2, True))
         netD.add(Conv(mylayer, ndf, 4, 4, 2, 2, 1, 1)).add(nn.LeakyReLU(0.2, True))
+    elif opt.get("conditionAdv"):         # train.lua:158-180
+        netD_ctx = nn.Sequential().add(Conv(nc, ndf, 5, 5, 2, 2, 2, 2))
+        netD_pred = nn.Sequential().add(Conv(nc, ndf, 5, 5, 2, 2, 2 + 32, 2 + 32))
+        netD.add(nn.ParallelTable().add(netD_ctx).add(netD_pred))
+        netD.add(nn.JoinTable(2))
+        netD.add(nn.LeakyReLU(0.2, True))
+        netD.add(Conv(ndf * 2, ndf, 4, 4, 2, 2, 1, 1)).add(BN(ndf)).add(nn.LeakyReLU(0.2, True))
     else:
         netD.add(Conv(nc, ndf, 4, 4, 2, 2, 1, 1)).add(nn.LeakyReLU(0.2, True))
     for cin, cout in ((ndf, ndf * 2), (ndf * 2, ndf * 4), (ndf * 4, ndf * 8)):

@@ -145,6 +145,100 @@ class Sequential(Module):
             m._holders(out)
 
 
+class ParallelTable(Module):
+    """nn.ParallelTable: member i is applied to element i of the input table (train.lua:115-118, 170-174)."""
+
+    def __init__(self):
+        super().__init__()
+        self.modules = []
+
+    def add(self, m):
+        self.modules.append(m)
+        return self
+
+    def _check(self, xs):
+        if not isinstance(xs, (list, tuple)) or len(xs) != len(self.modules):
+            raise ValueError("ParallelTable: table of %d tensors expected" % len(self.modules))
+
+    def updateOutput(self, xs):
+        self._check(xs)
+        self.output = [m.updateOutput(x) for m, x in zip(self.modules, xs)]
+        return self.output
+
+    def updateGradInput(self, xs, gys):
+        self._check(xs)
+        self.gradInput = [m.updateGradInput(x, gy) for m, x, gy in zip(self.modules, xs, gys)]
+        return self.gradInput
+
+    def accGradParameters(self, xs, gys, scale=1.0):
+        for m, x, gy in zip(self.modules, xs, gys):
+            m.accGradParameters(x, gy, scale)
+
+    def backward(self, xs, gys, scale=1.0):
+        self._check(xs)
+        self.gradInput = [m.backward(x, gy, scale) for m, x, gy in zip(self.modules, xs, gys)]
+        return self.gradInput
+
+    def parameters(self):
+        ps, gs = [], []
+        for m in self.modules:
+            p, g = m.parameters()
+            ps += p
+            gs += g
+        return ps, gs
+
+    def apply(self, fn):
+        fn(self)
+        for m in self.modules:
+            m.apply(fn)
+
+    def _holders(self, out):
+        for m in self.modules:
+            m._holders(out)
+
+
+class JoinTable(Module):
+    """nn.JoinTable(dimension) for batch-mode tensors; the scripts use dimension 2 = the channel axis (train.lua:120,177)."""
+
+    def __init__(self, dimension):
+        super().__init__()
+        if dimension != 2:
+            raise ValueError("JoinTable: only dimension 2 (channels of batch-mode tensors) is used by the reference scripts")
+        self.dimension = dimension
+        self._grads = None
+
+    @staticmethod
+    def _per_sample(x):
+        n = 1
+        for d in x.shape[1:]:
+            n *= d
+        return n
+
+    def updateOutput(self, xs):
+        N, rest = xs[0].shape[0], xs[0].shape[2:]
+        for x in xs:
+            if x.shape[0] != N or x.shape[2:] != rest:
+                raise ValueError("JoinTable: inconsistent tensor sizes %s vs %s" % (xs[0].shape, x.shape))
+        self.output = _buf(self.output, (N, sum(x.shape[1] for x in xs)) + tuple(rest))
+        total, off = self._per_sample(self.output), 0
+        for x in xs:
+            k = self._per_sample(x)
+            api().cenn_JoinTable_updateOutput(state(), _p(self.output), _p(x), N, total, off, k)
+            off += k
+        return self.output
+
+    def updateGradInput(self, xs, gy):
+        if self._grads is None or [g.shape for g in self._grads] != [x.shape for x in xs]:
+            self._grads = [CudaTensor(x.shape) for x in xs]
+        total, off = self._per_sample(gy), 0
+        for x, g in zip(xs, self._grads):
+            k = self._per_sample(x)
+            api().cenn_JoinTable_updateGradInput(state(), _p(gy), _p(g), x.shape[0], total, off, k)
+            off += k
+        self.gradInput = self._grads
+        return self.gradInput
+
+
 def _check4(x, planes, what):
     if x.dim() != 4:
         raise ValueError("%s: 4D (batch mode) tensor expected, got %dD" % (what, x.dim()))

@@ -47,7 +47,20 @@ class ClosureTrainer:
         self.errD = self.errG = self.errG_l2 = self.errG_gdl = None
 
     # ---------------------------------------------------------------- image variant
-    def fDx_image(self, real_ctx, real_center):
+    def _d_in(self, center):
+        return [self.input_ctx, center] if self.opt.get("conditionAdv") else center       # train.lua:300-311
+
+    def _g_in(self):
+        return [self.input_ctx, self.noise] if self.opt.get("noiseGen") else self.input_ctx    # train.lua:325-329
+
+    def fDx_image(self, real_ctx, real_center, noise=None):
+        if self.opt.get("noiseGen"):
+            # train.lua:319-323 redraws the noise here; the caller passes the draw so that both sides of a parity test see the same one
+            if noise is None:
+                raise ValueError("noiseGen: pass the noise tensor [B, nz, 1, 1] (train.lua:319-323)")
+            if getattr(self, "noise", None) is None:
+                self.noise = CudaTensor(self.opt["batchSize"], self.opt.get("nz", 100), 1, 1)
+            self.noise.copy_(noise)
         models.zero_conv_bias(self.netD)
         models.zero_conv_bias(self.netG)
         self.gradParametersD.zero()
@@ -55,17 +68,17 @@ class ClosureTrainer:
         self.input_center.copy_(real_center)
         self.input_real_center.copy_(real_center)
         self.label.fill(1)
-        out = self.netD.forward(self.input_center)
+        out = self.netD.forward(self._d_in(self.input_center))
         self.errD_real = self.criterion.forward(out, self.label)
         df_do = self.criterion.backward(out, self.label)
-        self.netD.backward(self.input_center, df_do)
-        fake = self.netG.forward(self.input_ctx)
+        self.netD.backward(self._d_in(self.input_center), df_do)
+        fake = self.netG.forward(self._g_in())
         self.input_center.copy_(fake)
         self.label.fill(0)
-        out = self.netD.forward(self.input_center)
+        out = self.netD.forward(self._d_in(self.input_center))
         self.errD_fake = self.criterion.forward(out, self.label)
         df_do = self.criterion.backward(out, self.label)
-        self.netD.backward(self.input_center, df_do)
+        self.netD.backward(self._d_in(self.input_center), df_do)
         self.errD = self.errD_real + self.errD_fake
         return self.errD, self.gradParametersD
 
@@ -78,7 +91,9 @@ class ClosureTrainer:
         out = self.netD.output
         self.errG = self.criterion.forward(out, self.label)
         df_do = self.criterion.backward(out, self.label)
-        df_dg = self.netD.updateGradInput(self.input_center, df_do)
+        df_dg = self.netD.updateGradInput(self._d_in(self.input_center), df_do)
+        if o.get("conditionAdv"):
+            df_dg = df_dg[1]              # train.lua:371: df_dg[2], the prediction branch
         total = self.errG
         wtl2 = o["wtl2"]
         if wtl2 != 0:
@@ -91,7 +106,7 @@ class ClosureTrainer:
             self.errG_l2 = loss.value
             total = (1 - wtl2) * self.errG + wtl2 * self.errG_l2 if 0 < wtl2 < 1 else self.errG + wtl2 * self.errG_l2
         self.df_dg = df_dg
-        self.netG.backward(self.input_ctx, df_dg)
+        self.netG.backward(self._g_in(), df_dg)
         return total, self.gradParametersG
 
     # ---------------------------------------------------------------- video variant
