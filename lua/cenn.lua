@@ -71,6 +71,8 @@ int cenn_MaskedMSECriterion_forward_backward(cenn_state *s, const float *input, 
 int cenn_GDLCriterion_forward_backward(cenn_state *s, const float *input, const float *target, float *gradInput,
     int64_t batch, int64_t C, int64_t H, int64_t W, float *loss_host);
 int cenn_AdamFlat(cenn_state *s, float *x, const float *g, float *m, float *v, int64_t n, double lr, double beta1, double beta2, double eps, int64_t t);
+int cenn_JoinTable_updateOutput(cenn_state *s, float *joined, const float *part, int64_t batch, int64_t joined_per_sample, int64_t offset, int64_t part_per_sample);
+int cenn_JoinTable_updateGradInput(cenn_state *s, const float *gradJoined, float *gradPart, int64_t batch, int64_t joined_per_sample, int64_t offset, int64_t part_per_sample);
 ]]
 
 local lib = ffi.load(os.getenv('CENN_LIB') or 'libcenn.so')
@@ -214,6 +216,30 @@ function nn.Tanh:updateOutput(input) self.output:resizeAs(input); check(lib.cenn
 function nn.Tanh:updateGradInput(input, gradOutput) self.gradInput:resizeAs(input); check(lib.cenn_Tanh_updateGradInput(S(), gradOutput.ptr, self.gradInput.ptr, self.output.ptr, input:nElement())); return self.gradInput end
 function nn.Sigmoid:updateOutput(input) self.output:resizeAs(input); check(lib.cenn_Sigmoid_updateOutput(S(), input.ptr, self.output.ptr, input:nElement())); return self.output end
 function nn.Sigmoid:updateGradInput(input, gradOutput) self.gradInput:resizeAs(input); check(lib.cenn_Sigmoid_updateGradInput(S(), gradOutput.ptr, self.gradInput.ptr, self.output.ptr, input:nElement())); return self.gradInput end
+
+-- nn.JoinTable(2) of the noiseGen / conditionAdv nets (train.lua:120,177): stock nn.JoinTable narrows and copies through tensor
+-- methods the stand-in tensor does not have; here each table member is one strided device copy.  nn.ParallelTable is pure Lua.
+local function per_sample(t) local n = 1; for d = 2, t:dim() do n = n * t.sz[d] end; return n end
+function nn.JoinTable:updateOutput(input)
+  assert(self.dimension == 2, 'JoinTable: the scripts join along dimension 2 (channels) only')
+  local sz = {unpack(input[1].sz)}; sz[2] = 0
+  for _, x in ipairs(input) do sz[2] = sz[2] + x.sz[2] end
+  self.output = self.output.ptr and self.output or cenn.CudaTensor(1); self.output:resize(unpack(sz))
+  local total, off = per_sample(self.output), 0
+  for _, x in ipairs(input) do
+    check(lib.cenn_JoinTable_updateOutput(S(), self.output.ptr, x.ptr, sz[1], total, off, per_sample(x))); off = off + per_sample(x)
+  end
+  return self.output
+end
+function nn.JoinTable:updateGradInput(input, gradOutput)
+  local total, off = per_sample(gradOutput), 0
+  self.gradInput = type(self.gradInput) == 'table' and self.gradInput or {}
+  for i, x in ipairs(input) do
+    self.gradInput[i] = self.gradInput[i] or cenn.CudaTensor(1); self.gradInput[i]:resizeAs(x)
+    check(lib.cenn_JoinTable_updateGradInput(S(), gradOutput.ptr, self.gradInput[i].ptr, x.sz[1], total, off, per_sample(x))); off = off + per_sample(x)
+  end
+  return self.gradInput
+end
 
 ---------------------------------------------------------------------------------------------- criteria
 local loss = ffi.new('float[1]')
