@@ -328,3 +328,27 @@ def test_clip_mode_step_equals_three_tensor_step(cenn):
     with pytest.raises(Exception, match="video variant"):
         img = train.FusedTrainer(models.default_opt("image", batchSize=2, nBottleneck=128), precision="bf16")
         img.step_clips_host(frames[:2, :3], mask1[:2], None, maskValue=0.4)
+
+
+def test_fused_wide_net_matches_oracle(cenn):
+    """The wide nets of train_wholeim_input.lua:36-48 (nef = ngf = 192, ndf = 128, predLen 1, weight_nomask 1; bottleneck reduced
+    from 6400 to 640 to keep the fp64 oracle affordable): channel counts that are multiples of 64 but not powers of two
+    (192 / 384 / 768 / 1536) through every tile shape of the executor."""
+    from video_filler_b200 import models, train
+    kw = dict(batchSize=4, nBottleneck=640, nef=192, ngf=192, ndf=128, predLen=1, weight_nomask=1.0)
+    orc = ostep.StepOracle(onets.default_opt("video", **kw), seed=77, dtype=np.float64)
+    trn = train.FusedTrainer(models.default_opt("video", **kw), precision="bf16")
+    assert trn.param_count(0) == orc.pG.size and trn.param_count(1) == orc.pD.size
+    trn.set_params(0, orc.pG); trn.set_params(1, orc.pD)
+    batch = orc.synth_batch(np.random.default_rng(5))
+    lo, lg = orc.step(*batch), trn.step_host(*batch)
+    for k in ("errD_real", "errG_l2", "errG_total"):
+        assert lg[k] == pytest.approx(lo[k], rel=2e-2), k
+    for k in ("errD_fake", "errD", "errG"):
+        assert lg[k] == pytest.approx(lo[k], rel=5e-2), k
+    # 13 bf16 layers with contractions up to K = 16 * 1536: measured 4.2e-2 of the output range (the 12-layer image net stays under 4e-2)
+    assert rel_err(trn.fetch("fake").reshape(orc.netG.output.shape), orc.netG.output) <= 6e-2
+    gG, gD = trn.get_grads(0), trn.get_grads(1)
+    assert _cos(gG, orc.gG) >= 0.9 and _cos(gD, orc.gD) >= 0.9
+    assert np.linalg.norm(gG) == pytest.approx(np.linalg.norm(orc.gG), rel=5e-2)
+    trn.close()
