@@ -153,7 +153,7 @@ def run_infer(args, torch, dist, api, st, stream, rank, local_rank, world):
             eng.load(flat, stats)
             xs = [T.CudaTensor.from_numpy(rng.uniform(-1, 1, (Bt, 3, 128, 128)).astype(np.float32)) for _ in range(2)]
             y = T.CudaTensor.from_numpy(np.zeros((Bt, 3, 128, 128), np.float32))
-            for i in range(max(3, args.warmup)):
+            for i in range(max(4, args.warmup)):
                 eng.forward_device(xs[i % 2].ptr, y.ptr, Bt)
             torch.cuda.synchronize()
             if dist:
@@ -207,7 +207,7 @@ def run_infer(args, torch, dist, api, st, stream, rank, local_rank, world):
     best = max(sweep, key=lambda r: r["tiles_per_s"])
     line = {
         "metric": "inference tiles/sec (eval-mode generator forward, 128x128 tiles)", "value": best["tiles_per_s"], "unit": "tiles/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": best["latency_ms"], "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": max(4, args.warmup), "ms_per_step": best["latency_ms"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "test_vid_wholeim tile forward, inputLen 1, nBottleneck 4000; batch sweep %s tiles/GPU, value = best batch (%d)" % (batches, best["batch"]),
                    "parallelism": "replicas x%d (no collective)" % world,
