@@ -510,6 +510,99 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply2_kernel(bf16 *__restrict_
     }
     if (gb_part) fold_and_flush<1, false>(acc, active, gb_part + (size_t)blockIdx.x * Cp, Cp, C);
 }
+// ---- EXPERIMENTAL, off by default (CENN_BN_BWD_FUSED=1; written at the end of round 1 without GPU time left to validate it) ----
+// The three BN-backward launches of a SMALL layer (reduce -> coefficients -> apply: ~12 + 8 + 10 us of mostly launch latency)
+// as ONE kernel with two grid barriers.  The whole grid must be able to become co-resident (<= 2 CTAs per SM: the host
+// caps the grid); the barrier counter only grows, so it needs no reset between launches, and a CTA that waits longer than
+// ~2 s traps instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned int total) {
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(ctr, 1ULL);
+        const unsigned long long target = (old / total + 1ULL) * total;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+            if (v >= target) break;
+            if (clock64() - t0 > 4000000000LL) { printf("cenn: grid barrier timeout (cta %d,%d)\n", blockIdx.x, blockIdx.y); __trap(); }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+template <int ACT>
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
+        const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
+        float *__restrict__ part, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int want_gb, int Cp,
+        int64_t npix, int vec_per_pix, int C, float negval, double n, unsigned long long *__restrict__ bar) {
+    const int vec = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = vec < vec_per_pix;
+    const unsigned int total = gridDim.x * gridDim.y;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+    float sc[8], sh[8];
+    load8f(scale, vec * 8, active ? C : 0, sc); load8f(shift, vec * 8, active ? C : 0, sh);
+    {   // ---- phase A: this CTA's partial row of (sum dz, sum dz * (y - mean))
+        float acc[2][8] = {};
+        if (active) {
+            float mu[8];
+            load8f(mean, vec * 8, C, mu);
+            for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < npix; p += stride) {
+                float fg[8], fy[8];
+                const int64_t vi = p * vec_per_pix + vec;
+                unpack8b(reinterpret_cast<const uint4 *>(g)[vi], fg); unpack8b(__ldg(reinterpret_cast<const uint4 *>(y) + vi), fy);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval); acc[0][k] += dz; acc[1][k] = fmaf(dz, fy[k] - mu[k], acc[1][k]); }
+            }
+        }
+        fold_and_flush<2, false>(acc, active, part + (size_t)blockIdx.x * 2 * Cp, Cp, C);
+    }
+    grid_barrier(bar, total);
+    {   // ---- phase B: the first ceil(C / 32) CTAs fold the rows of 32 channels each and publish the coefficients
+        __shared__ float sh_s[8][33], sh_d[8][33];
+        const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, ry = tid >> 5;
+        if ((int)cta * 32 < C) {
+            const int c = cta * 32 + lane, rows = gridDim.x;
+            float s0 = 0.f, d0 = 0.f;
+            if (c < C) for (int r = ry; r < rows; r += 8) { const float *q = part + (size_t)r * 2 * Cp + c; s0 += __ldcg(q); d0 += __ldcg(q + Cp); }
+            sh_s[ry][lane] = s0; sh_d[ry][lane] = d0;
+            __syncthreads();
+            if (ry == 0 && c < C) {
+                double s = 0.0, d = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s += (double)sh_s[i][lane]; d += (double)sh_d[i][lane]; }
+                const double is = invstd[c], A = is * (double)gamma[c], k1 = is * is * d / n;
+                coef[c] = (float)A; coef[C + c] = (float)(A * k1); coef[2 * C + c] = (float)(((double)mean[c] * k1 - s / n) * A);
+                if (ggamma) ggamma[c] += (float)(d * is);
+                if (gbeta) gbeta[c] += (float)s;
+            }
+        }
+    }
+    grid_barrier(bar, total);
+    {   // ---- phase C: g_y = dz * A - y * B + D in place; this CTA's partial row of sum g_y (-> conv gradBias)
+        float acc[1][8] = {};
+        if (active) {
+            float cA[8], cB[8], cD[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int c = vec * 8 + k; const bool ok = c < C; cA[k] = ok ? __ldcg(coef + c) : 0.f; cB[k] = ok ? __ldcg(coef + C + c) : 0.f; cD[k] = ok ? __ldcg(coef + 2 * C + c) : 0.f; }
+            for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < npix; p += stride) {
+                float fg[8], fy[8];
+                const int64_t vi = p * vec_per_pix + vec;
+                unpack8b(reinterpret_cast<const uint4 *>(g)[vi], fg); unpack8b(__ldg(reinterpret_cast<const uint4 *>(y) + vi), fy);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval);
+                    const float r = fmaf(dz, cA[k], fmaf(-fy[k], cB[k], cD[k]));
+                    fg[k] = r; acc[0][k] += r;
+                }
+                reinterpret_cast<uint4 *>(g)[vi] = pack8(fg);
+            }
+        }
+        if (want_gb) fold_and_flush<1, false>(acc, active, part + (size_t)blockIdx.x * Cp, Cp, C);
+    }
+}
 // activation-only backward (in place on g): g_y = g * act'(a); optional per-CTA partial sums -> gradBias
 template <int ACT>
 __global__ void __launch_bounds__(256, 4) act_bwd2_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, float *__restrict__ gb_part, int Cp, int64_t npix,

@@ -45,6 +45,7 @@ struct Block {
     bf16 *Wt = nullptr;                     // transposed operand copy
     int cl_rows = 0;
     unsigned int *done_ctr = nullptr;       // bn_finalize_apply_act: CTAs that have consumed the statistics
+    unsigned long long *bar = nullptr;      // experimental fused BN backward (CENN_BN_BWD_FUSED=1): grid-barrier counter
     float *part = nullptr;                  // per-CTA partial rows of the backward reductions [part_rows][2*Coutp]
     int part_rows = 0;
     float *stats = nullptr, *bsums = nullptr, *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *coef = nullptr;
@@ -286,6 +287,13 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             const int ty = 256 / tx, gy = (vpp + tx - 1) / tx;
             const int64_t npix = b.Coutp >= 8 ? (int64_t)N * oh * ow : (int64_t)N * oh * ow / 2;
             b.part_rows = (int)std::max<int64_t>(1, std::min<int64_t>((npix + ty * 4 - 1) / (ty * 4), (int64_t)s->sm_count * 4 / gy));
+            // experimental (off by default): small BN layers run their backward as one kernel with grid barriers -> the grid
+            // (part_rows x gy CTAs) must fit 2 CTAs per SM
+            if (sp.bn && getenv("CENN_BN_BWD_FUSED") && t->cfg.world_size <= 1 && b.Coutp >= 8 && (int64_t)N * oh * ow * b.Coutp <= (6 << 20)) {
+                b.part_rows = (int)std::max<int64_t>(1, std::min<int64_t>(b.part_rows, (int64_t)s->sm_count * 2 / gy));
+                b.bar = dalloc<unsigned long long>(t, 1);
+                if (!b.bar) return 1;
+            }
             b.part = dalloc<float>(t, (int64_t)b.part_rows * 2 * std::max(b.Coutp, 8));
             if (!b.part) return 1;
         }
@@ -584,6 +592,15 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         const double n_global = (double)t->Bglobal * b->a.H * b->a.W;
         float *gamma = master + b->g_off;
         float *gg = want_params ? grad + b->g_off : nullptr, *gbeta = want_params ? grad + b->be_off : nullptr;
+        if (b->bar && !dp) {       // experimental single-launch path (see nhwc::bn_bwd_fused_kernel)
+            const int want_gb = want_params ? 1 : 0;
+            emit(t, "bn_bwd_fused", [s, b, gamma, gg, gbeta, want_gb, npix, vpp, n_global]() {
+                dim3 blk; int gy; reduce_dims(vpp, blk, gy);
+                auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_fused_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_fused_kernel<nhwc::ACT_RELU>;
+                kern<<<dim3(b->part_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->mean, b->invstd, gamma,
+                    b->part, b->coef, gg, gbeta, want_gb, b->Coutp, npix, vpp, b->Cout, 0.2f, n_global, b->bar);
+                KLAUNCH(s); return 0; });
+        } else {
         emit(t, "bn_bwd_reduce", [s, b, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
             auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_RELU>;
@@ -618,6 +635,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->coef,
                 gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
+        }   // three-launch path
     } else if (b->Coutp >= 8) {
         emit(t, "act_bwd", [s, b, gb_part, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
