@@ -783,3 +783,143 @@ extern "C" CENN_API int cenn_debug_desc_probe(cenn_state *s, const uint16_t *a_h
     cudaFree(A); cudaFree(B); cudaFree(out);
     return 0;
 }
+
+// ------------------------------------------------------------------ CTA-pair GEMM probe (tools/gemm2sm_probe.py)
+// EXPERIMENTAL bring-up vehicle for the next round's kernels; no product path calls it, and at the end
+// of round 1 it had only been through ptxas, not through a GPU.  C[M,N] (fp32) = A[M,K] * B[N,K]^T, bf16 operands, K-major,
+// M % 256 == 0, N % 256 == 0, K % 64 == 0.  One cluster of two CTAs owns a 256 x 256 tile: each CTA loads ITS 128 rows of A
+// and ITS 128 rows of B per k-block, the leader's elected thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256) and every
+// CTA reads its own 128 accumulator rows back from its own TMEM.
+//   full[s]  (leader's copy only, 2 arrivals + 64 KB of transactions): leader arrive.expect_tx + peer remote arrive; both CTAs'
+//            TMA loads complete on it (cta_group::2 load form, barrier address with the peer bit cleared)
+//   empty[s] (one per CTA, 1 arrival): tcgen05.commit.cta_group::2 ... multicast::cluster, mask 0b11
+//   done     (one per CTA, 1 arrival): same multicast commit after the last k-block
+namespace {
+constexpr int P2_STAGES = 4;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap *m, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm2sm_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float *__restrict__ C, int M, int N, int K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *a_s = smem, *b_s = smem + P2_STAGES * 16384;
+    uint64_t *full = reinterpret_cast<uint64_t *>(b_s + P2_STAGES * 16384), *empty = full + P2_STAGES, *done = empty + P2_STAGES;
+    uint32_t *slot = reinterpret_cast<uint32_t *>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int m0 = (blockIdx.x >> 1) * 256 + (int)rank * 128, n0 = blockIdx.y * 256 + (int)rank * 128, num_kb = K / 64;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P2_STAGES; ++i) { tc::mbar_init(&full[i], 2); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(done, 1);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmA); tc::prefetch_tmap(&tmB);
+    }
+    if (warp == 1) tmem_alloc_2sm(slot, 256);          // one warp of EACH CTA of the pair
+    tc::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // the peer's barriers are initialised before anyone signals them
+    tc::tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (warp == 0) {
+        if (tc::elect_one()) {                         // ---- TMA producer (both CTAs)
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int st = kb % P2_STAGES; const uint32_t ph = (kb / P2_STAGES) & 1;
+                tc::mbar_wait(&empty[st], ph ^ 1);
+                const uint32_t leader_full = tc::smem_u32(&full[st]) & 0xFEFFFFFFu;      // same offset in the even CTA of the pair
+                if (leader) tc::mbar_expect_tx(&full[st], 2 * 32768); else mbar_arrive_remote(tc::smem_u32(&full[st]), 0);
+                tma_load_2d_2sm(&tmA, leader_full, tc::smem_u32(a_s + st * 16384), kb * 64, m0);
+                tma_load_2d_2sm(&tmB, leader_full, tc::smem_u32(b_s + st * 16384), kb * 64, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && tc::elect_one()) {               // ---- MMA issuer (leader CTA only)
+            const uint32_t idesc = tc::make_idesc(256, 256, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int st = kb % P2_STAGES; const uint32_t ph = (kb / P2_STAGES) & 1;
+                tc::mbar_wait(&full[st], ph);
+                tc::tc_fence_after();
+                const uint32_t a_addr = tc::smem_u32(a_s + st * 16384), b_addr = tc::smem_u32(b_s + st * 16384);
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_2sm(tmem, tc::make_desc(a_addr + k * 32, 16, 1024), tc::make_desc(b_addr + k * 32, 16, 1024), idesc, (kb | k) != 0);
+                umma_commit_2sm(tc::smem_u32(&empty[st]), 3);
+            }
+            umma_commit_2sm(tc::smem_u32(done), 3);
+        }
+    } else {                                           // ---- epilogue: warps 2..5 of both CTAs, 32 accumulator rows each
+        const int q = warp & 3;
+        tc::mbar_wait(done, 0);
+        tc::tc_fence_after();
+        float *crow = C + (size_t)(m0 + q * 32 + lane) * N + blockIdx.y * 256;
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) crow[c0 + j] = __uint_as_float(r[j]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // nobody frees TMEM while the peer may still be read by an MMA
+    if (warp == 1) { tc::tc_fence_after(); tmem_dealloc_2sm(tmem, 256); }
+}
+}  // namespace
+
+// a_host [M][K], b_host [N][K] bf16 bit patterns; c_host [M][N] fp32; ms_out = mean kernel time over `iters` launches
+extern "C" CENN_API int cenn_debug_gemm2sm_probe(cenn_state *s, const uint16_t *a_host, const uint16_t *b_host, int M, int N, int K, int iters,
+                                                 float *c_host, float *ms_out) {
+    API_BEGIN(s);
+    REQUIRE(a_host && b_host && c_host && ms_out && M > 0 && N > 0 && K > 0 && M % 256 == 0 && N % 256 == 0 && K % 64 == 0, "gemm2sm probe: M, N multiples of 256 and K of 64 required");
+    bf16 *A, *B; float *Cd;
+    CK(cudaMalloc(&A, (size_t)M * K * 2)); CK(cudaMalloc(&B, (size_t)N * K * 2)); CK(cudaMalloc(&Cd, (size_t)M * N * 4));
+    CK(cudaMemcpy(A, a_host, (size_t)M * K * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(B, b_host, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(Cd, 0, (size_t)M * N * 4));
+    CUtensorMap ta, tb;
+    if (map_2d(&ta, A, (uint64_t)K, (uint64_t)M, 128) || map_2d(&tb, B, (uint64_t)K, (uint64_t)N, 128)) return 1;
+    const size_t smem = 1024 + 2 * P2_STAGES * 16384 + (2 * P2_STAGES + 1) * 8 + 16;
+    CK(cudaFuncSetAttribute(gemm2sm_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(2 * (M / 256), N / 256);
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    gemm2sm_probe_kernel<<<grid, 192, smem, s->stream>>>(ta, tb, Cd, M, N, K);
+    CK_LAUNCH(s);
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaEventRecord(e0, s->stream));
+    for (int i = 0; i < iters; ++i) { gemm2sm_probe_kernel<<<grid, 192, smem, s->stream>>>(ta, tb, Cd, M, N, K); CK_LAUNCH(s); }
+    CK(cudaEventRecord(e1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    float ms = 0.f; if (iters > 0) CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = iters > 0 ? ms / iters : 0.f;
+    CK(cudaMemcpy(c_host, Cd, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(A); cudaFree(B); cudaFree(Cd);
+    return 0;
+}
