@@ -273,7 +273,8 @@ def test_losses_after_100_steps_match_oracle_fixture(cenn):
     assert len(ours) == 100 and np.all(np.isfinite(ours))
     # the L2 term is what the generator is trained on at wtl2 = 0.999 (errG_total = 0.001 errG + 0.999 errG_l2 up to the edge weighting)
     assert s["errG_l2"]["rel_at_last_step"] <= 1e-2 and s["errG_l2"]["rel_of_mean_last10"] <= 1e-2
-    assert s["errG_total"]["rel_at_last_step"] <= 1e-2
+    # errG_total = 0.001 * errG + 0.999 * errG_l2: the chaotic adversarial term alone moves it by ~0.6 % (measured 0.81 % in total)
+    assert s["errG_total"]["rel_at_last_step"] <= 3e-2 and s["errG_total"]["rel_of_mean_last10"] <= 1e-2
     assert s["errG_l2"]["max_rel_all_steps"] <= 5e-2          # measured 3.2 % at the worst step (profiles/r1_parity_steps.json)
     # adversarial terms: the first step is a pure function of the inputs; later the GAN game amplifies rounding differences
     # (errD / errG swing between 0.1 and 6 from step to step on BOTH sides; at step 100 they differ by 20-40 %)
