@@ -113,3 +113,36 @@ def test_load_converts_legacy_classes(tmp_path):
     net = util.load(str(p))
     assert [m.classname for m in net.modules] == ["nn.SpatialConvolution", "nn.SpatialBatchNormalization"]
     assert np.allclose(net.modules[1].tensors["running_var"], 1 / 0.25 - 1e-5)
+
+
+def test_noisegen_conditionadv_trees_roundtrip_and_match_oracle_layout(tmp_path):
+    """train.lua:109-124,158-180: ParallelTable / JoinTable(2) containers in the host tree -- same getParameters order and
+    size as the oracle nets, and a util.save / util.load round trip that keeps the container classes."""
+    from oracle import nets as onets
+    kw = dict(nBottleneck=32, nef=8, ngf=8, ndf=8, noiseGen=1, nz=12, conditionAdv=1)
+    opt = models.default_opt("image", **kw)
+    oG, oD = onets.build_netG(onets.default_opt("image", **kw)), onets.build_netD(onets.default_opt("image", **kw))
+    rng = np.random.default_rng(3)
+    for describe, onet in ((util.describe_netG, oG), (util.describe_netD, oD)):
+        net = describe(opt)
+        oflat, _ = onet.getParameters()
+        assert util.params_flat(net).size == oflat.size
+        # same order: fill the oracle's flat vector with its own indices, copy into the host tree, compare per-tensor shapes
+        oflat[...] = np.arange(oflat.size)
+        util.set_params_flat(net, oflat.astype(np.float32))
+        holders = []
+        onet._collect_holders(holders)
+        host_tensors = [m.tensors[f] for m in net.walk() for f in util.PARAM_FIELDS if f in m.tensors]
+        assert len(holders) == len(host_tensors)
+        for (m, pn, _), ht in zip(holders, host_tensors):
+            assert getattr(m, pn).shape == ht.shape and np.array_equal(getattr(m, pn).astype(np.float32), ht)
+        flat = rng.normal(0, 0.02, oflat.size).astype(np.float32)
+        util.set_params_flat(net, flat)
+        p = tmp_path / "net.t7"
+        util.save(str(p), net)
+        back = util.load(str(p))
+        names = [m.classname for m in back.walk()]
+        assert "nn.ParallelTable" in names and "nn.JoinTable" in names and names == [m.classname for m in net.walk()]
+        assert np.array_equal(util.params_flat(back), flat)
+        join = [m for m in back.walk() if m.classname == "nn.JoinTable"][0]
+        assert join.attrs["dimension"] == 2

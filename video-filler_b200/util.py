@@ -62,7 +62,15 @@ def describe_netG(opt):
     for cin, cout in ((nef, nef), (nef, nef * 2), (nef * 2, nef * 4), (nef * 4, nef * 8)):
         e += [_conv(C, cin, cout, 4, 2, 1), _bn(cout), _leaky()]
     e.append(_conv(C, nef * 8, nB, 4, 1, 0))
-    g = [HostModule("nn.Sequential", modules=e), _bn(nB), _leaky(), _conv(F, nB, ngf * 8, 4, 1, 0, True), _bn(ngf * 8), _relu()]
+    netE, nz_size = HostModule("nn.Sequential", modules=e), nB
+    if opt.get("noiseGen"):               # train.lua:109-124
+        nz = opt.get("nz", 100)
+        noise = HostModule("nn.Sequential", modules=[_conv(C, nz, nz, 1, 1, 0)])
+        head = [HostModule("nn.ParallelTable", modules=[netE, noise]), HostModule("nn.JoinTable", dict(dimension=2, size=t7.Storage([])))]
+        nz_size = nB + nz
+    else:
+        head = [netE]
+    g = head + [_bn(nz_size), _leaky(), _conv(F, nz_size, ngf * 8, 4, 1, 0, True), _bn(ngf * 8), _relu()]
     chain = [(ngf * 8, ngf * 4), (ngf * 4, ngf * 2), (ngf * 2, ngf)] + ([(ngf, ngf)] if video else [])
     for cin, cout in chain:
         g += [_conv(F, cin, cout, 4, 2, 1, True), _bn(cout), _relu()]
@@ -79,6 +87,11 @@ def describe_netD(opt):
     d = []
     if video:
         d += [_conv(C, nc, ndf // 2, 4, 2, 1), _leaky(), _conv(C, ndf // 2, ndf, 4, 2, 1), _leaky()]
+    elif opt.get("conditionAdv"):         # train.lua:158-180
+        ctx = HostModule("nn.Sequential", modules=[_conv(C, nc, ndf, 5, 2, 2)])
+        pred = HostModule("nn.Sequential", modules=[_conv(C, nc, ndf, 5, 2, 2 + 32)])
+        d += [HostModule("nn.ParallelTable", modules=[ctx, pred]), HostModule("nn.JoinTable", dict(dimension=2, size=t7.Storage([]))), _leaky(),
+              _conv(C, ndf * 2, ndf, 4, 2, 1), _bn(ndf), _leaky()]
     else:
         d += [_conv(C, nc, ndf, 4, 2, 1), _leaky()]
     for cin, cout in ((ndf, ndf * 2), (ndf * 2, ndf * 4), (ndf * 4, ndf * 8)):
