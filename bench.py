@@ -438,7 +438,7 @@ def main():
     if prof and rank == 0:
         tc_ms, tc_flops, tc_n = prof["tc_ms"], prof["tc_flops"], prof["tc_launches"]
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "frac_of_burst_peak": ach / tf_burst, "traffic": None,
                             "kernel": "tc::gather_gemm_kernel / tc::wgrad_gemm_kernel (all conv fprop/dgrad/wgrad launches)",
                             "launches_per_step": tc_n, "share_of_step": tc_ms / prof["total_ms"], "peak_source": peak_src + " bf16_tflops_sustained",
                             "by_op_ms": prof["by_op"]}
