@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(bf16 *__restrict__
         __shared__ float sh_s[8][33], sh_d[8][33];
         const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
         const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, ry = tid >> 5;
-        if ((int)cta * 32 < C) {
-            const int c = cta * 32 + lane, rows = gridDim.x;
+        for (unsigned int grp = cta; (int)grp * 32 < C; grp += total) {      // 32-channel groups, round-robin over the CTAs
+            const int c = grp * 32 + lane, rows = gridDim.x;
             float s0 = 0.f, d0 = 0.f;
             if (c < C) for (int r = ry; r < rows; r += 8) { const float *q = part + (size_t)r * 2 * Cp + c; s0 += __ldcg(q); d0 += __ldcg(q + Cp); }
             sh_s[ry][lane] = s0; sh_d[ry][lane] = d0;
@@ -578,6 +578,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(bf16 *__restrict__
                 if (ggamma) ggamma[c] += (float)(d * is);
                 if (gbeta) gbeta[c] += (float)s;
             }
+            __syncthreads();                                                  // sh_s / sh_d are reused by the next group
         }
     }
     grid_barrier(bar, total);
