@@ -45,57 +45,100 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md), polled in-process through NVML every
+    few milliseconds so that even a 60 ms region holds several samples; falls back to `nvidia-smi -lms` when NVML is missing."""
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.004):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.period = index, [], False, period_s
         self.proc = None
-        self.t_begin = None
+        self.t_begin = self.t_end = None
+        self.source = "nvml"
 
     def mark_begin(self):
         """Samples taken from now on are inside the timed region."""
         self.t_begin = time.time()
 
+    def mark_end(self):
+        self.t_end = time.time()
+
+    def _handle(self, nv):
+        try:                                  # honour CUDA_VISIBLE_DEVICES: look the device up by UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return nv.nvmlDeviceGetHandleByIndex(self.index)
+
     def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = self._handle(nv)
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+            while not self.stop_flag:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((time.time(), sm, smax, pw, [n for n, b in names if mask & b]))
+                time.sleep(self.period)
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.samples.append((time.time(), [x.strip() for x in line.split(",")]))
+                v = [x.strip() for x in line.split(",")]
+                try:
+                    rs = [n for n, x in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), v[3:7]) if x.lower().startswith("active")]
+                    self.samples.append((time.time(), float(v[0]), float(v[1]), float(v[2]), rs))
+                except Exception:
+                    continue
         except Exception:
             pass
 
     def finish(self):
+        if self.t_end is None:
+            self.mark_end()
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        sm, reasons, smax = [], set(), None
-        inside = [v for (ts, v) in self.samples if self.t_begin is None or ts >= self.t_begin]
-        if not inside:                      # timed region shorter than one sampling period: use the last sample before it ended
-            inside = [v for (_, v) in self.samples[-1:]]
-        for s in inside:
-            try:
-                sm.append(float(s[0])); smax = float(s[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        if self.is_alive():
+            self.join(timeout=1.0)
+        inside = [x for x in self.samples if (self.t_begin is None or x[0] >= self.t_begin) and x[0] <= self.t_end + self.period]
+        sm = [x[1] for x in inside]
+        reasons = sorted({r for x in inside for r in x[4]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": inside[0][2] if inside else (self.samples[-1][2] if self.samples else None),
+                "reasons": reasons, "samples": len(sm), "power_w_max": max([x[3] for x in inside]) if inside else None, "source": self.source}
 
 
-def cpu_port_step_rate(batch, steps, warmup, threads):
-    """The reference's gpu=0 path restated (oracle port, fp32) on the host cores: samples/s over `steps` steps."""
-    import torch
-    torch.set_num_threads(threads)
+def host_threads():
+    """Host threads this process may use (affinity-aware; torchrun's OMP_NUM_THREADS=1 is overridden explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_port_step_rate(batch, steps, warmup, threads, variant="image", wtgdl=0.0):
+    """The reference's gpu=0 path restated on the host cores: the oracle's fDx / fGx / optim.adam step sequence (oracle/step.py,
+    train.lua:278-410) with its heavy ops on the PyTorch-CPU engine (oracle/torch_engine.py: oneDNN / MKL -- BASELINE.md section 4).
+    Returns (samples/s over `steps` steps, seconds per step, threads in use)."""
     from oracle import nets as onets
     from oracle import step as ostep
-    orc = ostep.StepOracle(onets.default_opt("image", batchSize=batch), seed=1234, dtype=np.float32)
+    from oracle import torch_engine
+    n_thr = torch_engine.enable(threads)
+    kw = dict(batchSize=batch)
+    if variant == "video":
+        kw["wtgdl"] = wtgdl
+    orc = ostep.StepOracle(onets.default_opt(variant, **kw), seed=1234, dtype=np.float32)
     rng = np.random.default_rng(1234)
     batches = [orc.synth_batch(rng) for _ in range(min(2, steps + warmup))]
     for i in range(warmup):
@@ -104,24 +147,40 @@ def cpu_port_step_rate(batch, steps, warmup, threads):
     for i in range(steps):
         orc.step(*batches[i % len(batches)])
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    return batch * steps / dt, dt / steps, n_thr
+
+
+REF_BUDGET_S = 240.0     # the whole reference run (warm-up + timed steps) is sized to end within a few minutes
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the step on this box's host cores, all threads, on the SAME
+    workload string as our arm.  Each step processes the full per-GPU batch when `steps + warmup` of them fit REF_BUDGET_S
+    (probed with one small step first); otherwise a bounded sample of the batch, and the line says which."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    # bounded sample of the 256-sample step: the port runs ~8 samples/s on 16 cores, so size each step for ~90 s in total
-    batch = int(max(2, min(32, 90 * 8 // max(1, args.steps + args.warmup))))
-    rate, sec = cpu_port_step_rate(batch, args.steps, args.warmup, threads)
+    video = getattr(args, "workload", "image") == "video"
+    full = getattr(args, "batch", None) or (64 if video else 256)
+    threads = host_threads()
+    variant = "video" if video else "image"
+    wtgdl = getattr(args, "wtgdl", 0.5) if video else 0.0
+    nsteps = max(1, args.steps + args.warmup)
+    probe_b = min(16, full)
+    probe_rate, _, _ = cpu_port_step_rate(probe_b, 1, 1, threads, variant, wtgdl)    # per-step fixed costs (Adam over 74 M params) make this pessimistic
+    batch = full
+    if full * nsteps / probe_rate > REF_BUDGET_S:
+        batch = int(max(2, min(full, REF_BUDGET_S * probe_rate // nsteps)))
+    rate, sec, n_thr = cpu_port_step_rate(batch, args.steps, args.warmup, threads, variant, wtgdl)
+    workload = (WORKLOAD_VIDEO % (wtgdl, full)) if video else WORKLOAD.replace("batch 256", "batch %d" % full)
+    sample = ("each step = the full %d-sample batch" % full) if batch == full else ("each step = %d samples of the %d-sample batch (bounded sample)" % (batch, full))
     line = {
         "impl": "reference", "metric": "train samples/sec (G+D step)", "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "each step = %d samples of the 256-sample batch" % batch},
-        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": "oracle port (numpy im2col+sgemm restatement of the Torch7 gpu=0 path), %d-sample steps" % batch},
+        "config": {"workload": workload, "sample": sample, "batch_per_step": batch},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": n_thr, "kind": "port",
+                         "sample": "oracle step sequence on the PyTorch-CPU engine (oneDNN/MKL; faster than Torch7's im2col+sgemm gpu=0 path would be), fp32, %d threads, %s" % (n_thr, sample)},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -203,7 +262,7 @@ def run_infer(args, torch, dist, api, st, stream, rank, local_rank, world):
     if rank != 0:
         if dist:
             dist.destroy_process_group()
-        sys.stdout.flush(); os._exit(0)
+        return
     best = max(sweep, key=lambda r: r["tiles_per_s"])
     line = {
         "metric": "inference tiles/sec (eval-mode generator forward, 128x128 tiles)", "value": best["tiles_per_s"], "unit": "tiles/s", "n_gpus": world,
@@ -231,9 +290,9 @@ def run_infer(args, torch, dist, api, st, stream, rank, local_rank, world):
         line["cpu_baseline"] = {"value": 8 / dt, "unit": "tiles/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "one 8-tile eval forward of the oracle generator, %.2f s" % dt}
     print(json.dumps(line))
+    sys.stdout.flush()
     if dist:
         dist.destroy_process_group()
-    sys.stdout.flush(); os._exit(0)
 
 
 def wrap_device(ptr, count, dtype, torch):
@@ -245,91 +304,52 @@ def wrap_device(ptr, count, dtype, torch):
     return torch.as_tensor(h, device="cuda")
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default 256 image / 64 video)")
-    ap.add_argument("--workload", default="image", choices=["image", "video", "infer"],
-                    help="image = BASELINE.json configs[1] (the headline); video = configs[2] per GPU; infer = configs[4] sweep")
-    ap.add_argument("--wtgdl", type=float, default=0.5)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    video = args.workload == "video"
-    if args.batch is None and args.workload != "infer":
-        args.batch = 64 if video else 256
 
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    import video_filler_b200.tensor as T
+def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, steps, warmup, want_profile=True):
+    """Time `steps` G+D steps of one workload on this rank.  Returns a dict of raw measurements (device-timed region, end-to-end
+    region through the pipelined host API, per-op profile, launch count, clocks); the executor is closed before returning."""
     from video_filler_b200 import synth, train, util
-    T.state(local_rank)
-    api, st = T.api(), T.state()
-    stream = torch.cuda.Stream(priority=-1)      # the step's critical path; the executor's side streams run at lowest priority
-    api.cenn_set_stream(st, C.c_void_p(stream.cuda_stream))
-
-    if args.workload == "infer":
-        return run_infer(args, torch, dist, api, st, stream, rank, local_rank, world)
-    B = args.batch
+    import video_filler_b200.tensor as T
     opt = opt_for(B, "video" if video else "image")
     if video:
         opt["wtgdl"] = args.wtgdl
-    if world > 1:
-        # library-owned NCCL communicator: rank 0 creates the id, torch.distributed carries it to the other ranks
-        idbuf = np.zeros(128, np.uint8)
-        if rank == 0:
-            api.cenn_dist_unique_id(idbuf.ctypes.data_as(C.c_void_p))
-        idt = torch.from_numpy(idbuf).cuda()
-        dist.broadcast(idt, src=0)
-        idbuf = idt.cpu().numpy()
-        api.cenn_dist_init(st, idbuf.ctypes.data_as(C.c_void_p), world, rank)
-
     trn = train.FusedTrainer(opt, precision="bf16", world_size=world, rank=rank)
     # identical random-init weights on every rank (parameter broadcast = same seed), train.lua:58-67
     rng = np.random.default_rng(1234)
     nG, nD = trn.param_count(0), trn.param_count(1)
-
     trn.set_params(0, util.params_flat(util.weights_init(util.describe_netG(opt), rng)))
     trn.set_params(1, util.params_flat(util.weights_init(util.describe_netD(opt), rng)))
     assert video or (nG == 71118691 + 2 * (64 + 128 + 256 + 512 + 4000 + 512 + 256 + 128 + 64) and nD > 2764737)
 
     drng = np.random.default_rng(1000 + rank)
     n_batches = 2
-    host, clips = [], []
+    host, clips, pinned = [], [], []
+
+    def pin(nbytes):
+        p = C.c_void_p(); api.cenn_host_alloc(st, nbytes, C.byref(p)); pinned.append(p); return p
+
     for _ in range(n_batches):
         if video:
             ctx, center, mask = synth.video_batch(B, 12, 128, opt["maskValue"], drng)
         else:
             ctx, center = synth.image_batch(B, 128, 4, drng)
             mask = None
-        pa, pb = C.c_void_p(), C.c_void_p()
-        api.cenn_host_alloc(st, ctx.nbytes, C.byref(pa)); api.cenn_host_alloc(st, center.nbytes, C.byref(pb))
+        pa, pb = pin(ctx.nbytes), pin(center.nbytes)
         ha = np.ctypeslib.as_array((C.c_float * ctx.size).from_address(pa.value)); ha[:] = ctx.ravel()
         hb = np.ctypeslib.as_array((C.c_float * center.size).from_address(pb.value)); hb[:] = center.ravel()
         da, db = T.CudaTensor.from_numpy(ctx), T.CudaTensor.from_numpy(center)
         hm, dm, nbytes = None, None, ctx.nbytes + center.nbytes
         if mask is not None:
-            pm = C.c_void_p(); api.cenn_host_alloc(st, mask.nbytes, C.byref(pm))
+            pm = pin(mask.nbytes)
             hm = np.ctypeslib.as_array((C.c_uint8 * mask.size).from_address(pm.value)); hm[:] = mask.ravel()
             dmp = C.c_void_p(); api.cenn_malloc(st, mask.nbytes, C.byref(dmp)); api.cenn_copy_h2d(st, dmp, pm, mask.nbytes)
             dm = dmp.value
             # clip mode (the e2e call of the video workload): frames in [0,1] + ONE mask plane per sample + hflip flags;
             # the device derives real_full, real_ctx and the expanded mask (datavid/donkey_folder.lua:161-187)
-            pf = C.c_void_p(); api.cenn_host_alloc(st, center.nbytes, C.byref(pf))
+            pf = pin(center.nbytes)
             hf = np.ctypeslib.as_array((C.c_float * center.size).from_address(pf.value)); hf[:] = ((center + 1) * 0.5).ravel()
-            m1 = np.ascontiguousarray(mask[:, 0]); p1 = C.c_void_p(); api.cenn_host_alloc(st, m1.nbytes + B, C.byref(p1))
+            m1 = np.ascontiguousarray(mask[:, 0]); p1 = pin(m1.nbytes + B)
             h1 = np.ctypeslib.as_array((C.c_uint8 * (m1.size + B)).from_address(p1.value)); h1[:m1.size] = m1.ravel()
             h1[m1.size:] = drng.integers(0, 2, B).astype(np.uint8)
             clips.append((hf, h1[:m1.size], h1[m1.size:], center.nbytes + m1.nbytes + B))
@@ -337,14 +357,13 @@ def main():
         host.append((ha, hb, da, db, nbytes, hm, dm))
 
     def step_device(i):
-        # world > 1: the executor all-reduces BN statistics, gradients and losses itself (NCCL, inside its CUDA graph)
+        # world > 1: the executor all-reduces BN statistics, gradients and losses itself (NCCL / peer mailboxes, inside its CUDA graph)
         h = host[i % n_batches]
         trn.step_device(h[2].ptr, h[3].ptr, h[6])
 
-    losses = None
     sampler = ClockSampler(local_rank); sampler.start()
     with torch.cuda.stream(stream):
-        for i in range(max(4, args.warmup)):      # two input sets x (first use runs eagerly, second captures its CUDA graph): never fewer than 4
+        for i in range(max(4, warmup)):      # two input sets x (first use runs eagerly, second captures its CUDA graph): never fewer than 4
             step_device(i)
         torch.cuda.synchronize()
         if dist:
@@ -353,10 +372,11 @@ def main():
         sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(args.steps):
+        for i in range(steps):
             step_device(i)
         e1.record(stream)
         torch.cuda.synchronize()
+        sampler.mark_end()
         if dist:
             dist.barrier()
         ms = e0.elapsed_time(e1)
@@ -364,7 +384,6 @@ def main():
         launches1 = C.c_int64(); api.cenn_kernel_launches(st, C.byref(launches1))
         losses = trn.read_losses()
         # ---- end-to-end: host buffers in, losses out, every step (single-process API call)
-        e2e_ms = None
         for i in range(2):
             trn.step_host(host[i % n_batches][0], host[i % n_batches][1], host[i % n_batches][5])
 
@@ -385,7 +404,7 @@ def main():
         t0 = time.perf_counter()
         # public pipelined API: every step copies ITS inputs from pinned host memory and its losses are read back;
         # the copy of step k+1 overlaps the compute of step k, the losses of step k are read while step k+1 runs
-        for i in range(args.steps):
+        for i in range(steps):
             step_async(i)
             if i > 0:
                 losses = trn.wait_losses()
@@ -394,68 +413,177 @@ def main():
         if dist:
             dist.barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        # ---- per-op CUDA-event profile for the roofline of the dominant kernels
-        prof = trn.profile_step(host[0][2].ptr, host[0][3].ptr, host[0][6], repeats=3)    # every rank runs it (it contains the all-reduces)
-
+        # ---- per-op CUDA-event profile for the rooflines of the dominant kernels (every rank runs it: it contains the exchanges)
+        prof = trn.profile_step(host[0][2].ptr, host[0][3].ptr, host[0][6], repeats=3) if want_profile else None
+        torch.cuda.synchronize()
     t_ms = torch.tensor([ms, e2e_ms], device="cuda")
     if dist:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t_ms[0].item()), float(t_ms[1].item())
-    def finish():
-        # the step's CUDA graph holds the NCCL communicator: release the executor first, then the communicator
-        nonlocal trn
-        trn.close()
-        trn = None
+    out = {"ms": float(t_ms[0].item()), "e2e_ms": float(t_ms[1].item()), "losses": losses, "launches": int(launches1.value - launches0.value),
+           "clocks": clocks, "prof": prof, "h2d_bytes": int(host[0][4]), "nG": nG, "nD": nD, "B": B, "steps": steps}
+    # the step's CUDA graph holds the NCCL communicator: release the executor (and this workload's buffers) before anything else
+    trn.close()
+    del host, clips
+    for p in pinned:
+        try:
+            api.cenn_host_free(st, p)
+        except Exception:
+            pass
+    return out
+
+
+def class_rooflines(prof, hbm, peak_src):
+    """Achieved GB/s per class of bandwidth kernel = algorithmic bytes (stated per op by the executor) / CUDA-event time."""
+    if not prof or prof.get("bytes") is None:
+        return None
+    classes = {"bn_fwd": ("bn_fin_apply", "bn_apply_act"), "bn_bwd": ("bn_bwd_reduce", "bn_bwd_apply", "bn_bwd_fused", "bn_bwd_coef"),
+               "act_bwd": ("act_bwd", "act_bwd4"), "loss_blend": ("blend_overlap", "blend_masked", "gdl_loss"), "adam": ("adam", "adam_early")}
+    out = {}
+    for cls, names in classes.items():
+        sel = [i for i, n in enumerate(prof["names"]) if n in names]
+        ms = float(sum(prof["ms"][i] for i in sel)); by = float(sum(prof["bytes"][i] for i in sel))
+        if ms > 0 and by > 0:
+            gbs = by / (ms * 1e-3) / 1e9
+            out[cls] = {"achieved": round(gbs, 1), "frac": round(gbs / hbm, 4), "ms": round(ms, 4), "launches": len(sel), "algorithmic_mb": round(by / 1e6, 2)}
+    # the largest single launch of the BN / activation chain (the small layers are L2-resident and launch-latency bound)
+    best = None
+    for i, n in enumerate(prof["names"]):
+        if n.startswith("bn_") or n.startswith("act_bwd"):
+            by, ms = float(prof["bytes"][i]), float(prof["ms"][i])
+            if by >= 32e6 and ms > 0:
+                gbs = by / (ms * 1e-3) / 1e9
+                if best is None or gbs > best["achieved"]:
+                    best = {"kernel": n, "achieved": round(gbs, 1), "frac": round(gbs / hbm, 4), "algorithmic_mb": round(by / 1e6, 2), "ms": round(ms, 4)}
+    return {"bound": "hbm", "peak": hbm, "unit": "GB/s", "peak_source": peak_src + " hbm_gbs", "classes": out, "best_large_layer_launch": best}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default 256 image / 64 video)")
+    ap.add_argument("--workload", default="image", choices=["image", "video", "infer"],
+                    help="image = BASELINE.json configs[1] (the headline); video = configs[2] per GPU; infer = configs[4] sweep")
+    ap.add_argument("--wtgdl", type=float, default=0.5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-video-block", action="store_true", help="skip the `video` sub-block (cfg3 at the same N) of the image line")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    video = args.workload == "video"
+    if args.batch is None and args.workload != "infer":
+        args.batch = 64 if video else 256
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import video_filler_b200.tensor as T
+    T.state(local_rank)
+    api, st = T.api(), T.state()
+    stream = torch.cuda.Stream(priority=-1)      # the step's critical path; the executor's side streams run at lowest priority
+    api.cenn_set_stream(st, C.c_void_p(stream.cuda_stream))
+
+    if args.workload == "infer":
+        run_infer(args, torch, dist, api, st, stream, rank, local_rank, world)
+        return
+    B = args.batch
+    if world > 1:
+        # library-owned NCCL communicator: rank 0 creates the id, torch.distributed carries it to the other ranks
+        idbuf = np.zeros(128, np.uint8)
+        if rank == 0:
+            api.cenn_dist_unique_id(idbuf.ctypes.data_as(C.c_void_p))
+        idt = torch.from_numpy(idbuf).cuda()
+        dist.broadcast(idt, src=0)
+        idbuf = idt.cpu().numpy()
+        api.cenn_dist_init(st, idbuf.ctypes.data_as(C.c_void_p), world, rank)
+
+    m = measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, args.steps, args.warmup)
+    vid = None
+    if not video and not args.no_video_block:
+        # the config the >= 7x scaling target is quoted on (BASELINE.json configs[2]): 64 clips of 12 stacked channels per GPU, at the same N
+        vid = measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, True, 64, args.steps, args.warmup, want_profile=False)
+
+    def teardown():
+        # ordered teardown, then a NORMAL interpreter exit (atexit hooks run): executors are already closed by measure_train
         if dist:
             api.cenn_dist_shutdown(st)
+            dist.barrier()
             dist.destroy_process_group()
         sys.stdout.flush()
-        os._exit(0)         # nothing left to do; do not depend on interpreter-exit ordering of CUDA / NCCL teardown
 
     if rank != 0:
-        finish()
+        teardown()
+        return
     hbm, tf_burst, tf_sus, peak_src = peaks()
-    total_samples = B * world * args.steps
     gflop_per_sample = VIDEO_GFLOP_PER_SAMPLE if video else STEP_GFLOP_PER_SAMPLE
-    value = total_samples / (ms / 1e3)
+    ms, e2e_ms, prof, losses = m["ms"], m["e2e_ms"], m["prof"], m["losses"]
+    value = B * world * args.steps / (ms / 1e3)
     line = {
         "metric": "train samples/sec (G+D step)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(4, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": (WORKLOAD_VIDEO % (args.wtgdl, B)) if video else WORKLOAD.replace("batch 256", "batch %d" % B), "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (>3 GB of activations, weights and optimizer state) exceeds the 126 MB L2; no explicit flush",
+                   "timed_region_s": round(ms / 1e3, 4),
                    "losses_last_step": {k: round(v, 5) for k, v in losses.items()} if losses else None},
-        "gpu_launches": int(launches1.value - launches0.value),
-        "clocks": clocks,
+        "gpu_launches": m["launches"],
+        "clocks": m["clocks"],
         "step_tflops": gflop_per_sample * 1e-3 * value,
         "step_frac_of_bf16_sustained": gflop_per_sample * 1e-3 * value / (tf_sus * world),
+        "step_frac_of_bf16_burst": gflop_per_sample * 1e-3 * value / (tf_burst * world),
     }
-    if e2e_ms is not None:
-        line["e2e"] = {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
-                       "h2d_bytes_per_step": int(host[0][4]), "d2h_bytes_per_step": 32}
-    else:
-        line["e2e"] = None
-    if prof and rank == 0:
+    line["e2e"] = {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": 32}
+    if vid is not None:
+        vvalue = 64 * world * args.steps / (vid["ms"] / 1e3)
+        line["video"] = {"workload": WORKLOAD_VIDEO % (args.wtgdl, 64), "value": vvalue, "unit": "samples/s", "ms_per_step": vid["ms"] / args.steps,
+                         "global_batch": 64 * world, "step_tflops": VIDEO_GFLOP_PER_SAMPLE * 1e-3 * vvalue, "gpu_launches": vid["launches"],
+                         "e2e": {"value": 64 * world * args.steps / (vid["e2e_ms"] / 1e3), "unit": "samples/s", "h2d_bytes_per_step": vid["h2d_bytes"], "d2h_bytes_per_step": 32},
+                         "clocks": vid["clocks"]}
+    if prof:
         tc_ms, tc_flops, tc_n = prof["tc_ms"], prof["tc_flops"], prof["tc_launches"]
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "frac_of_burst_peak": ach / tf_burst, "traffic": None,
-                            "kernel": "tc::gather_gemm_kernel / tc::wgrad_gemm_kernel (all conv fprop/dgrad/wgrad launches)",
-                            "launches_per_step": tc_n, "share_of_step": tc_ms / prof["total_ms"], "peak_source": peak_src + " bf16_tflops_sustained",
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")     # dram__bytes_read + dram__bytes_write of the conv launches of one step (ncu --set full)
+        if os.path.exists(tp) and not video and B == 256:
+            try:
+                traffic = json.load(open(tp)).get("conv_launch_dram_bytes_mean")
+            except Exception:
+                traffic = None
+        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst, "frac_of_sustained_peak": ach / tf_sus, "traffic": traffic,
+                            "kernel": "tc::gather_gemm_kernel / tc::patch_dgrad_kernel / tc::wgrad_gemm_kernel (all conv fprop/dgrad/wgrad launches of one step; algorithmic FLOPs / summed CUDA-event durations)",
+                            "launches_per_step": tc_n, "share_of_step": tc_ms / prof["total_ms"], "peak_source": peak_src + " bf16_tflops (burst: each launch is timed alone)",
                             "by_op_ms": prof["by_op"]}
-    if prof and rank == 0:
-        # the dominant bandwidth kernel (fused Adam + bf16 operand refresh over the flat parameter vectors): 30 B per parameter
+        best = prof.get("best_tc")
+        if best:
+            line["roofline"]["best_launch"] = best
+        cr = class_rooflines(prof, hbm, peak_src)
+        if cr:
+            line["roofline_hbm"] = cr
         adam_ms = prof["by_op"].get("adam", 0.0) + prof["by_op"].get("adam_early", 0.0)
         if adam_ms > 0:
-            gbs = 30.0 * (nG + nD) / (adam_ms * 1e-3) / 1e9
-            line["roofline_hbm"] = {"bound": "hbm", "kernel": "nhwc::adam_bf16_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                                    "traffic": None, "bytes_per_param": 30, "params": int(nG + nD), "peak_source": peak_src + " hbm_gbs"}
+            gbs = 30.0 * (m["nG"] + m["nD"]) / (adam_ms * 1e-3) / 1e9
+            line.setdefault("roofline_hbm", {"bound": "hbm", "peak": hbm, "unit": "GB/s", "peak_source": peak_src + " hbm_gbs"}).update(
+                {"kernel": "nhwc::adam_bf16_kernel", "achieved": gbs, "frac": gbs / hbm, "traffic": None, "bytes_per_param": 30, "params": int(m["nG"] + m["nD"])})
     if not args.no_cpu_baseline and world == 1 and not video:
-        threads = os.cpu_count() or 1
-        rate, sec = cpu_port_step_rate(64, 1, 0, threads)
-        line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-                                "sample": "one 64-sample step of the oracle port (numpy restatement of the Torch7 gpu=0 path), %.1f s" % sec}
+        threads = host_threads()
+        rate, sec, n_thr = cpu_port_step_rate(64, 3, 1, threads)
+        rate1, sec1, _ = cpu_port_step_rate(16, 1, 1, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": n_thr, "kind": "port",
+                                "sample": "BASELINE.json configs[0] (batch 64): 1 warm-up + 3 timed steps of the oracle step sequence on the PyTorch-CPU engine "
+                                          "(oneDNN/MKL, fp32; faster than Torch7's im2col+sgemm gpu=0 path), %.2f s/step on %d threads" % (sec, n_thr),
+                                "one_thread": {"value": rate1, "unit": "samples/s", "cores": 1,
+                                               "sample": "torch.setnumthreads(1) as train.lua:47: 1 warm-up + 1 timed 16-sample step, %.2f s" % sec1}}
     print(json.dumps(line))
-    finish()
+    teardown()
 
 
 if __name__ == "__main__":

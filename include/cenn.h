@@ -271,6 +271,17 @@ CENN_API int cenn_trainer_kernel_launches_per_step(cenn_trainer *t, int64_t *cou
 /* one step with a CUDA-event pair around every op: '\n'-separated op names, per-op milliseconds and algorithmic FLOPs */
 CENN_API int cenn_trainer_profile_step(cenn_trainer *t, const float *a_dev, const float *b_dev, const uint8_t *mask_dev,
         char *names, int64_t names_cap, float *ms, double *flops, int64_t cap, int64_t *nops);
+/* test / debugging hook: run the step program up to and including the `occurrence`-th (0-based) op named `op_name`
+ * (names as returned by cenn_trainer_profile_step), serially, and synchronise: stored tensors can then be fetched mid-step */
+CENN_API int cenn_trainer_step_until(cenn_trainer *t, const float *a_dev, const float *b_dev, const uint8_t *mask_dev,
+        const char *op_name, int occurrence, int64_t *ops_run);
+/* algorithmic bytes of every op of the step program (0 where not stated), same order as cenn_trainer_profile_step:
+ * the numerators of the HBM rooflines of the BN / activation / loss / Adam kernels */
+CENN_API int cenn_trainer_op_bytes(cenn_trainer *t, double *bytes, int64_t cap, int64_t *nops);
+/* one eager step on the executor's own streams: start / end (ms since the step began) of every op and the stream it ran on
+ * (0 = compute stream, 1 = weight-gradient side stream, 2 = generator-forward chain, 3 = early-Adam stream) */
+CENN_API int cenn_trainer_timeline_step(cenn_trainer *t, const float *a_dev, const float *b_dev, const uint8_t *mask_dev,
+        float *t_start, float *t_end, int *stream_id, int64_t cap, int64_t *nops);
 
 /* ------------------------------ inference engine ---------------
  * Eval-mode generator for test.lua:92 / demo.lua:68 (variant 0: [n,3,128,128] -> [n,3,64,64]) and for the full-frame

@@ -63,6 +63,47 @@ def make_golden(args):
     print("wrote", GOLDEN)
 
 
+def run_control(args):
+    """CONTROL for the adversarial terms: how far do errD / errG of two CPU runs of the SAME oracle step
+    sequence drift apart over 100 steps when they differ only at rounding level?  Arms, all from the golden fixture's seeded
+    batches and initial weights:
+      torch_fp32   the oracle on the PyTorch-CPU engine, fp32 (other summation order than the numpy fp32 golden run)
+      perturbed    the same, initial weights multiplied by (1 +- 2^-23) (one fp32 ulp)
+      fp64         the same in fp64
+    Written to profiles/r2_parity_control.json with the same summary the executor gets."""
+    import time
+    from oracle import nets as onets
+    from oracle import step as ostep
+    from oracle import torch_engine
+    from video_filler_b200 import models
+    torch_engine.enable(os.cpu_count() or 1)
+    g = np.load(GOLDEN)
+    batch, nB, n = int(g["batch"]), int(g["nBottleneck"]), min(int(g["steps"]), args.steps)
+    gold = g["losses"][:n]
+    opt = models.default_opt("image", **config(batch, nB))
+    pG, pD = init_params(opt)
+    out = {"steps": n, "batch": batch, "nBottleneck": nB, "arms": {}}
+    for arm in args.arms.split(","):
+        dt = np.float64 if arm == "fp64" else np.float32
+        orc = ostep.StepOracle(onets.default_opt("image", **config(batch, nB)), seed=1, dtype=dt)
+        orc.pG[:] = pG; orc.pD[:] = pD
+        if arm == "perturbed":
+            prng = np.random.default_rng(99)
+            orc.pG *= (1 + np.float32(2.0 ** -23) * prng.choice([-1.0, 1.0], orc.pG.size)).astype(np.float32)
+            orc.pD *= (1 + np.float32(2.0 ** -23) * prng.choice([-1.0, 1.0], orc.pD.size)).astype(np.float32)
+        hist, t0 = [], time.time()
+        for it, (ctx, center) in enumerate(batches(batch, n)):
+            lo = orc.step(ctx.astype(dt), center.astype(dt))
+            hist.append([lo[k] for k in NAMES])
+            if it % 10 == 0:
+                print(arm, it, ["%.4f" % v for v in hist[-1]], "%.0fs" % (time.time() - t0), flush=True)
+        hist = np.array(hist, np.float64)
+        out["arms"][arm] = {"vs_numpy_fp32_golden": summarize(hist, gold), "losses": hist.tolist()}
+        with open(os.path.join(ROOT, "profiles", "r2_parity_control.json"), "w") as f:
+            json.dump(out, f)
+    print(json.dumps({a: {k: v["vs_numpy_fp32_golden"][k]["rel_at_last_step"] for k in NAMES} for a, v in out["arms"].items()}, indent=1))
+
+
 def run_executor(steps=None):
     """Executor losses on the fixture's batches: returns (ours [steps, 6], golden [steps, 6])."""
     g = np.load(GOLDEN)
@@ -98,12 +139,16 @@ def summarize(ours, gold):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--make-golden", action="store_true")
+    ap.add_argument("--control", action="store_true", help="CPU control arms for the adversarial terms -> profiles/r2_parity_control.json")
+    ap.add_argument("--arms", default="torch_fp32,perturbed,fp64")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--nBottleneck", type=int, default=4000)
     ap.add_argument("--steps", type=int, default=100)
     args = ap.parse_args()
     if args.make_golden:
         return make_golden(args)
+    if args.control:
+        return run_control(args)
     ours, gold = run_executor()
     s = summarize(ours, gold)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

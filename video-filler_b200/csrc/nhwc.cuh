@@ -217,7 +217,7 @@ __device__ void xr_sum_inplace(float *__restrict__ buf, int n, const XrCtx &x) {
 #pragma unroll
             for (int r = 0; r < XR_MAX_WORLD; ++r)
                 if (pending & (1u << r)) { v[r] = ld_ll(reinterpret_cast<const uint2 *>(x.data[r]) + slot + i); if (v[r].y == tag) pending &= ~(1u << r); }
-            if (clock64() - t0 > 4000000000LL) { printf("cenn: peer exchange timeout (rank %d, exchange %llu, pending mask %x)\n", x.rank, e, pending); __trap(); }
+            if (clock64() - t0 > 240000000000LL) { printf("cenn: peer exchange timeout (rank %d, exchange %llu, pending mask %x)\n", x.rank, e, pending); __trap(); }
         }
         float acc = 0.f;                                 // rank order: every replica adds in the same order -> bit-identical sums
 #pragma unroll
@@ -510,11 +510,12 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply2_kernel(bf16 *__restrict_
     }
     if (gb_part) fold_and_flush<1, false>(acc, active, gb_part + (size_t)blockIdx.x * Cp, Cp, C);
 }
-// ---- EXPERIMENTAL, off by default (CENN_BN_BWD_FUSED=1; written at the end of round 1 without GPU time left to validate it) ----
-// The three BN-backward launches of a SMALL layer (reduce -> coefficients -> apply: ~12 + 8 + 10 us of mostly launch latency)
-// as ONE kernel with two grid barriers.  The whole grid must be able to become co-resident (<= 2 CTAs per SM: the host
-// caps the grid); the barrier counter only grows, so it needs no reset between launches, and a CTA that waits longer than
-// ~2 s traps instead of hanging the GPU.
+// The three BN-backward launches of a layer (reduce -> coefficients -> apply: ~12 + 8 + 10 us of mostly launch latency on the
+// small layers, and a second HBM read of g and y on the large ones) as ONE kernel with two grid barriers.  Launched
+// COOPERATIVELY (cudaLaunchAttributeCooperative: the grid starts only when every CTA can be co-resident), grid capped by the
+// host at the kernel's occupancy; the barrier counter only grows, so it needs no reset between launches.  Between phase A
+// and phase C the layer's g and y (<= 2 x 33 MB) stay in the 126 MB L2, so phase C's reads do not go back to HBM.
+// A CTA that waits longer than ~1 minute traps (protocol bug) instead of hanging the GPU.
 __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned int total) {
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -526,14 +527,14 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned i
             unsigned long long v;
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
             if (v >= target) break;
-            if (clock64() - t0 > 4000000000LL) { printf("cenn: grid barrier timeout (cta %d,%d)\n", blockIdx.x, blockIdx.y); __trap(); }
+            if (clock64() - t0 > 120000000000LL) { printf("cenn: grid barrier timeout (cta %d,%d)\n", blockIdx.x, blockIdx.y); __trap(); }
         }
         __threadfence();
     }
     __syncthreads();
 }
 template <int ACT>
-__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
+__global__ void __launch_bounds__(256, 3) bn_bwd_fused_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
         const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
         float *__restrict__ part, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int want_gb, int Cp,
         int64_t npix, int vec_per_pix, int C, float negval, double n, unsigned long long *__restrict__ bar) {
@@ -548,22 +549,32 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(bf16 *__restrict__
         if (active) {
             float mu[8];
             load8f(mean, vec * 8, C, mu);
-            for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < npix; p += stride) {
-                float fg[8], fy[8];
-                const int64_t vi = p * vec_per_pix + vec;
-                unpack8b(reinterpret_cast<const uint4 *>(g)[vi], fg); unpack8b(__ldg(reinterpret_cast<const uint4 *>(y) + vi), fy);
+            for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * BN_U) {
+                uint4 rg[BN_U], ry[BN_U];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { const float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval); acc[0][k] += dz; acc[1][k] = fmaf(dz, fy[k] - mu[k], acc[1][k]); }
+                for (int u = 0; u < BN_U; ++u) {
+                    const int64_t p = p0 + u * stride;
+                    if (p < npix) { const int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ry[u] = reinterpret_cast<const uint4 *>(y)[vi]; }
+                }
+#pragma unroll
+                for (int u = 0; u < BN_U; ++u) {
+                    if (p0 + u * stride < npix) {
+                        float fg[8], fy[8];
+                        unpack8b(rg[u], fg); unpack8b(ry[u], fy);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { const float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval); acc[0][k] += dz; acc[1][k] = fmaf(dz, fy[k] - mu[k], acc[1][k]); }
+                    }
+                }
             }
         }
         fold_and_flush<2, false>(acc, active, part + (size_t)blockIdx.x * 2 * Cp, Cp, C);
     }
     grid_barrier(bar, total);
-    {   // ---- phase B: the first ceil(C / 32) CTAs fold the rows of 32 channels each and publish the coefficients
+    {   // ---- phase B: 32-channel groups, round-robin over the CTAs: fold the rows and publish the coefficients
         __shared__ float sh_s[8][33], sh_d[8][33];
         const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
         const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, ry = tid >> 5;
-        for (unsigned int grp = cta; (int)grp * 32 < C; grp += total) {      // 32-channel groups, round-robin over the CTAs
+        for (unsigned int grp = cta; (int)grp * 32 < C; grp += total) {
             const int c = grp * 32 + lane, rows = gridDim.x;
             float s0 = 0.f, d0 = 0.f;
             if (c < C) for (int r = ry; r < rows; r += 8) { const float *q = part + (size_t)r * 2 * Cp + c; s0 += __ldcg(q); d0 += __ldcg(q + Cp); }
@@ -588,17 +599,28 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(bf16 *__restrict__
             float cA[8], cB[8], cD[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { const int c = vec * 8 + k; const bool ok = c < C; cA[k] = ok ? __ldcg(coef + c) : 0.f; cB[k] = ok ? __ldcg(coef + C + c) : 0.f; cD[k] = ok ? __ldcg(coef + 2 * C + c) : 0.f; }
-            for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < npix; p += stride) {
-                float fg[8], fy[8];
-                const int64_t vi = p * vec_per_pix + vec;
-                unpack8b(reinterpret_cast<const uint4 *>(g)[vi], fg); unpack8b(__ldg(reinterpret_cast<const uint4 *>(y) + vi), fy);
+            for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * BN_U) {
+                uint4 rg[BN_U], ry[BN_U];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval);
-                    const float r = fmaf(dz, cA[k], fmaf(-fy[k], cB[k], cD[k]));
-                    fg[k] = r; acc[0][k] += r;
+                for (int u = 0; u < BN_U; ++u) {
+                    const int64_t p = p0 + u * stride;
+                    if (p < npix) { const int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ry[u] = reinterpret_cast<const uint4 *>(y)[vi]; }
                 }
-                reinterpret_cast<uint4 *>(g)[vi] = pack8(fg);
+#pragma unroll
+                for (int u = 0; u < BN_U; ++u) {
+                    const int64_t p = p0 + u * stride;
+                    if (p < npix) {
+                        float fg[8], fy[8];
+                        unpack8b(rg[u], fg); unpack8b(ry[u], fy);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval);
+                            const float r = fmaf(dz, cA[k], fmaf(-fy[k], cB[k], cD[k]));
+                            fg[k] = r; acc[0][k] += r;
+                        }
+                        reinterpret_cast<uint4 *>(g)[p * vec_per_pix + vec] = pack8(fg);
+                    }
+                }
             }
         }
         if (want_gb) fold_and_flush<1, false>(acc, active, part + (size_t)blockIdx.x * Cp, Cp, C);

@@ -287,12 +287,21 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             const int ty = 256 / tx, gy = (vpp + tx - 1) / tx;
             const int64_t npix = b.Coutp >= 8 ? (int64_t)N * oh * ow : (int64_t)N * oh * ow / 2;
             b.part_rows = (int)std::max<int64_t>(1, std::min<int64_t>((npix + ty * 4 - 1) / (ty * 4), (int64_t)s->sm_count * 4 / gy));
-            // experimental (off by default): small BN layers run their backward as one kernel with grid barriers -> the grid
-            // (part_rows x gy CTAs) must fit 2 CTAs per SM
-            if (sp.bn && getenv("CENN_BN_BWD_FUSED") && t->cfg.world_size <= 1 && b.Coutp >= 8 && (int64_t)N * oh * ow * b.Coutp <= (6 << 20)) {
-                b.part_rows = (int)std::max<int64_t>(1, std::min<int64_t>(b.part_rows, (int64_t)s->sm_count * 2 / gy));
-                b.bar = dalloc<unsigned long long>(t, 1);
-                if (!b.bar) return 1;
+            // single GPU: a BN layer's backward (reduce -> coefficients -> apply) is ONE cooperatively launched kernel with two grid
+            // barriers (nhwc::bn_bwd_fused_kernel) -> the grid (part_rows x gy CTAs) must be co-resident.  CENN_BN_BWD_FUSED=0
+            // restores the three-launch path; CENN_BN_FUSED_MAX_ELEMS bounds the layer size (default: every layer).
+            {
+                const char *e = getenv("CENN_BN_BWD_FUSED"), *m = getenv("CENN_BN_FUSED_MAX_ELEMS");
+                const int64_t max_elems = m ? atoll(m) : (int64_t)1 << 40;
+                if (sp.bn && !(e && atoi(e) == 0) && t->cfg.world_size <= 1 && b.Coutp >= 8 && (int64_t)N * oh * ow * b.Coutp <= max_elems) {
+                    int per_sm_l = 0, per_sm_r = 0;
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, nhwc::bn_bwd_fused_kernel<nhwc::ACT_LEAKY>, 256, 2 * tx * 8 * sizeof(float)));
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, nhwc::bn_bwd_fused_kernel<nhwc::ACT_RELU>, 256, 2 * tx * 8 * sizeof(float)));
+                    const int per_sm = std::max(1, std::min(per_sm_l, per_sm_r));
+                    b.part_rows = (int)std::max<int64_t>(1, std::min<int64_t>(b.part_rows, (int64_t)s->sm_count * per_sm / gy));
+                    b.bar = dalloc<unsigned long long>(t, 1);
+                    if (!b.bar) return 1;
+                }
             }
             b.part = dalloc<float>(t, (int64_t)b.part_rows * 2 * std::max(b.Coutp, 8));
             if (!b.part) return 1;
@@ -534,6 +543,7 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
                 b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, b->Coutp, n_global, 0.1, 1e-5,
                 b->y.p, b->a.p, nvec, b->Coutp / 8, b->act, 0.2f, b->done_ctr);
             KLAUNCH(s); return 0; });
+        t->prog.back().bytes = 2.0 * 2.0 * (double)b->a.pix() * b->Cout;     // read y, write a
         return;
     }
     if (b->bn) {
@@ -564,6 +574,7 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
             int64_t nvec = b->y.elems() / 8;
             nhwc::bn_apply_act_kernel<<<grid1d(s, nvec), 256, 0, s->stream>>>(b->y.p, b->a.p, b->scale, b->shift, nvec, b->Coutp / 8, b->act, 0.2f);
             KLAUNCH(s); return 0; });
+        t->prog.back().bytes = 2.0 * 2.0 * (double)b->a.pix() * b->Cout;
     }
 }
 
@@ -592,14 +603,22 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         const double n_global = (double)t->Bglobal * b->a.H * b->a.W;
         float *gamma = master + b->g_off;
         float *gg = want_params ? grad + b->g_off : nullptr, *gbeta = want_params ? grad + b->be_off : nullptr;
-        if (b->bar && !dp) {       // experimental single-launch path (see nhwc::bn_bwd_fused_kernel)
+        if (b->bar && !dp) {       // single-launch path (nhwc::bn_bwd_fused_kernel), cooperative launch
             const int want_gb = want_params ? 1 : 0;
             emit(t, "bn_bwd_fused", [s, b, gamma, gg, gbeta, want_gb, npix, vpp, n_global]() {
                 dim3 blk; int gy; reduce_dims(vpp, blk, gy);
                 auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_fused_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_fused_kernel<nhwc::ACT_RELU>;
-                kern<<<dim3(b->part_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->mean, b->invstd, gamma,
-                    b->part, b->coef, gg, gbeta, want_gb, b->Coutp, npix, vpp, b->Cout, 0.2f, n_global, b->bar);
-                KLAUNCH(s); return 0; });
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(b->part_rows, gy); cfg.blockDim = blk; cfg.dynamicSmemBytes = 2 * blk.x * 8 * sizeof(float); cfg.stream = s->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                bf16 *gp = b->g.p; const bf16 *yp = b->y.p;
+                const float *scale = b->scale, *shift = b->shift, *mean = b->mean, *invstd = b->invstd;
+                if (cenn_check_cuda(cudaLaunchKernelEx(&cfg, kern, gp, yp, scale, shift, mean, invstd, (const float *)gamma, b->part, b->coef, gg, gbeta, want_gb,
+                        b->Coutp, (int64_t)npix, vpp, b->Cout, 0.2f, n_global, b->bar), "cooperative launch", __FILE__, __LINE__)) return 1;
+                s->launches++; return 0; });
+            t->prog.back().bytes = 5.0 * 2.0 * (double)npix * b->Cout;      // read g, y; (re-read from L2); write g_y: 5 s bytes per element
         } else {
         emit(t, "bn_bwd_reduce", [s, b, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
@@ -607,6 +626,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             kern<<<dim3(b->part_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->mean,
                 b->part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
+        t->prog.back().bytes = 2.0 * 2.0 * (double)npix * b->Cout;            // read g, y
         if (dp && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {   // fold this rank's partial rows, then exchange + coefficients in one kernel
             const float inv_world = 1.f / (float)t->cfg.world_size;
             emit(t, "bn_bwd_fold", [s, b]() {
@@ -635,6 +655,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->coef,
                 gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
+        t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;            // read g, y; write g_y
         }   // three-launch path
     } else if (b->Coutp >= 8) {
         emit(t, "act_bwd", [s, b, gb_part, npix, vpp]() {
@@ -642,6 +663,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::act_bwd2_kernel<nhwc::ACT_LEAKY> : (b->act == nhwc::ACT_RELU ? nhwc::act_bwd2_kernel<nhwc::ACT_RELU> : nhwc::act_bwd2_kernel<nhwc::ACT_TANH>);
             kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
+        t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;            // read g, a; write g_y
     } else {
         // Cp == 4 (3-channel image output): two pixels form one 8-lane vector, lanes k and k+4 are the same channel
         // (the fold job adds the two halves).  Pad lanes carry zero gradients.
@@ -650,6 +672,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             auto kern = b->act == nhwc::ACT_TANH ? nhwc::act_bwd2_kernel<nhwc::ACT_TANH> : (b->act == nhwc::ACT_LEAKY ? nhwc::act_bwd2_kernel<nhwc::ACT_LEAKY> : nhwc::act_bwd2_kernel<nhwc::ACT_RELU>);
             kern<<<dim3(b->part_rows, 1), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gb_part, 8, npix / 2, 1, 8, 0.2f);
             KLAUNCH(s); return 0; });
+        t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;
     }
     // weight gradient
     if (want_params) {
@@ -739,6 +762,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             else
             nhwc::adam_bf16_kernel<<<grid1d(s, cnt / 4), 256, 0, st>>>(n->master + off, n->grad + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
             KLAUNCH(s); return 0; });
+        t->prog.back().bytes = 30.0 * (double)cnt;
     }
 }
 
@@ -817,6 +841,7 @@ void emit_adam(T *t, Net &net, std::vector<std::pair<int64_t, int64_t>> done = {
             KLAUNCH(s);
         }
         return 0; });
+    { double by = 0; for (auto &x : rest) by += 30.0 * (double)x.second; t->prog.back().bytes = by; }
 }
 void emit_bce(T *t, Block *head, float label, int loss_slot, bool want_grad) {
     cenn_state *s = t->s;
@@ -961,7 +986,7 @@ int build_program(T *t) {
         if (!video) {
             float w_in = c.wtl2, w_ring = c.overlapPred > 0 ? 10.f * c.wtl2 : c.wtl2;
             int ov = c.overlapPred;
-            if (c.wtl2 != 0.f)
+            if (c.wtl2 != 0.f) {
                 emit(t, "blend_overlap", [s, df, fake_in, real, gout, ov, a, w_in, w_ring, n, acc]() {
                     if (fake_in.Cp == 4 && fake_in.pix() % 2 == 0)
                         nhwc::blend_overlap4_kernel<<<grid1d(s, fake_in.pix() / 2, 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
@@ -970,7 +995,8 @@ int build_program(T *t) {
                     nhwc::blend_overlap_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
                         fake_in.W, fake_in.Cp, fake_in.C, ov, a, w_in, w_ring, (float)(2.0 / n), 1.0 / n, acc);
                     KLAUNCH(s); return 0; });
-            else emit_copy(t, "g<-df_dg", gout.p, df.p, gout.elems());
+                t->prog.back().bytes = 4.0 * 2.0 * (double)fake_in.pix() * fake_in.C;   // read df, x, t; write df (edge weight from indices)
+            } else emit_copy(t, "g<-df_dg", gout.p, df.p, gout.elems());
         } else {
             float wtl2 = c.wtl2, lam = c.weight_nomask, wtgdl = c.wtgdl;
             if (wtgdl != 0.f) {
@@ -992,6 +1018,7 @@ int build_program(T *t) {
                 nhwc::blend_masked_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems(), fake_in.Cp, fake_in.C,
                     a, wtl2, lam, wtgdl, (float)(2.0 / n), 1.0 / n, acc);
                 KLAUNCH(s); return 0; });
+            t->prog.back().bytes = 5.0 * 2.0 * (double)fake_in.pix() * fake_in.C;   // read df, x, t, mask; write df
         }
     }
     emit_adam_step(t, G);          // optimState.t / step size first: the big blocks are updated as soon as their gradient exists
@@ -1034,7 +1061,8 @@ int build_program(T *t) {
 // sum a sync point's buffer across the data-parallel ranks (library-owned NCCL communicator, same stream as the kernels)
 int reduce_sync_point(T *t, const Op &op) {
     cenn_state *s = t->s;
-    if (!op.sync_buf || t->cfg.world_size <= 1 || !s->comm) return 0;
+    if (!op.sync_buf || t->cfg.world_size <= 1) return 0;
+    if (!s->comm) { cenn_set_error("data-parallel step (world_size %d) without a communicator: call cenn_dist_init first, or drive the step with cenn_trainer_step_phase and reduce the sync points yourself", t->cfg.world_size); return 1; }
     const bool is_loss = op.sync_buf == reinterpret_cast<float *>(t->loss_acc);
     return cenn_dist_all_reduce_on(s, op.sync_buf, is_loss ? 8 : op.sync_count, is_loss ? 1 : 0, s->stream);
 }
@@ -1093,6 +1121,7 @@ int run_step(T *t) {
         cudaGetLastError();
         if (ent->graph) { cudaGraphDestroy(ent->graph); ent->graph = nullptr; }
         ent->exec = nullptr; t->graph_failed = true;
+        fprintf(stderr, "cenn: CUDA graph capture / instantiation of the step failed (%s); the executor keeps launching eagerly\n", cudaGetErrorString(e));
         return run_ops(t, 0, t->prog.size());
     }
     ent->last_use = ++t->use_clock;
@@ -1421,7 +1450,11 @@ int cenn_trainer_profile_step(cenn_trainer *t, const float *a, const float *b, c
     cudaStream_t st = t->s->stream;
     size_t n = t->prog.size();
     REQUIRE((int64_t)n <= cap, "cenn_trainer_profile_step: capacity %lld < %zu ops", (long long)cap, n);
-    std::vector<cudaEvent_t> ev(n + 1);
+    std::vector<cudaEvent_t> ev(n + 1, nullptr);
+    struct Guard {      // every exit path: events destroyed, the executor back on its streams
+        cenn_trainer *t; std::vector<cudaEvent_t> &ev;
+        ~Guard() { t->serial = false; for (auto &e : ev) if (e) cudaEventDestroy(e); }
+    } guard{t, ev};
     for (auto &e : ev) CK(cudaEventCreate(&e));
     t->cur_a = a; t->cur_b = b; t->cur_m = mask;
     static const bool timeline = getenv("CENN_TIMELINE") != nullptr;   // keep the side streams: events then show the MAIN stream's time line
@@ -1436,18 +1469,94 @@ int cenn_trainer_profile_step(cenn_trainer *t, const float *a, const float *b, c
         CK(cudaEventRecord(ev[i + 1], st));
     }
     CK(cudaStreamSynchronize(st));
-    t->serial = false;
+    if (rc) return 1;
     std::string all;
-    for (size_t i = 0; i < n && !rc; ++i) {
+    for (size_t i = 0; i < n; ++i) {
         CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
         flops[i] = t->prog[i].flops;
         all += t->prog[i].name; all += '\n';
     }
-    for (auto &e : ev) cudaEventDestroy(e);
-    if (rc) return 1;
     REQUIRE((int64_t)all.size() + 1 <= names_cap, "cenn_trainer_profile_step: names buffer too small");
     memcpy(names, all.c_str(), all.size() + 1);
     *nops = (int64_t)n;
+    return 0;
+}
+
+// One EAGER step on the executor's real streams with an event pair around every op on the stream that op launches on:
+// start / end of every op in milliseconds since the step began -> which chain is the critical path, where the streams idle.
+int cenn_trainer_timeline_step(cenn_trainer *t, const float *a, const float *b, const uint8_t *mask, float *t_start, float *t_end, int *stream_id, int64_t cap, int64_t *nops) {
+    REQUIRE(t && a && b && t_start && t_end && stream_id && nops, "cenn_trainer_timeline_step: null argument");
+    API_BEGIN(t->s);
+    cenn_state *s = t->s;
+    cudaStream_t st = s->stream;
+    const size_t n = t->prog.size();
+    REQUIRE((int64_t)n <= cap, "cenn_trainer_timeline_step: capacity %lld < %zu ops", (long long)cap, n);
+    std::vector<cudaEvent_t> ev(2 * n + 1, nullptr);
+    struct Guard { std::vector<cudaEvent_t> &ev; ~Guard() { for (auto &e : ev) if (e) cudaEventDestroy(e); } } guard{ev};
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    t->cur_a = a; t->cur_b = b; t->cur_m = mask;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(ev[2 * n], st));
+    // the side streams start behind the base event so that every elapsed time is non-negative
+    for (cudaStream_t x : {t->side, t->side2, t->side3}) CK(cudaStreamWaitEvent(x, ev[2 * n], 0));
+    for (size_t i = 0; i < n; ++i) {
+        const Op &op = t->prog[i];
+        // ops that hop to a side stream themselves (wgrad, dead dgrad, early Adam) are bracketed on that stream
+        const bool on_side = !strcmp(op.name, "wgrad") || (!strcmp(op.name, "dgrad") && false);
+        const bool on_side3 = !strcmp(op.name, "adam_early");
+        cudaStream_t run = op.chain == 1 ? t->side2 : st;
+        cudaStream_t where = on_side ? t->side : (on_side3 ? t->side3 : run);
+        stream_id[i] = where == st ? 0 : (where == t->side ? 1 : (where == t->side2 ? 2 : 3));
+        cudaStream_t keep = s->stream;
+        s->stream = run;
+        if (where == run) CK(cudaEventRecord(ev[2 * i], where));
+        int rc = op.fn() || reduce_sync_point(t, op);
+        s->stream = keep;
+        if (rc) return 1;
+        if (where != run) CK(cudaEventRecord(ev[2 * i], where));     // start unknown on a hop: recorded after the launch, start := previous end on that stream
+        CK(cudaEventRecord(ev[2 * i + 1], where));
+    }
+    CK(cudaDeviceSynchronize());
+    float last_end[4] = {0.f, 0.f, 0.f, 0.f};
+    for (size_t i = 0; i < n; ++i) {
+        float a0 = 0.f, a1 = 0.f;
+        CK(cudaEventElapsedTime(&a1, ev[2 * n], ev[2 * i + 1]));
+        const Op &op = t->prog[i];
+        const bool hop = !strcmp(op.name, "wgrad") || !strcmp(op.name, "adam_early");
+        if (hop) a0 = last_end[stream_id[i]]; else CK(cudaEventElapsedTime(&a0, ev[2 * n], ev[2 * i]));
+        t_start[i] = a0; t_end[i] = a1;
+        last_end[stream_id[i]] = a1;
+    }
+    *nops = (int64_t)n;
+    return 0;
+}
+
+// Test / debugging hook: run the step program from its first op up to and including the `occurrence`-th (0-based) op named
+// `op_name`, serially on the compute stream, then synchronise -- the stored tensors and gradient vectors can then be fetched
+// mid-step (e.g. after the discriminator's real sweep, before the fake sweep overwrites its activations).
+int cenn_trainer_step_until(cenn_trainer *t, const float *a, const float *b, const uint8_t *mask, const char *op_name, int occurrence, int64_t *ops_run) {
+    REQUIRE(t && a && b && op_name, "cenn_trainer_step_until: null argument");
+    API_BEGIN(t->s);
+    long idx = -1; int seen = 0;
+    for (size_t i = 0; i < t->prog.size(); ++i)
+        if (!strcmp(t->prog[i].name, op_name) && seen++ == occurrence) { idx = (long)i; break; }
+    REQUIRE(idx >= 0, "cenn_trainer_step_until: the step program has no op '%s' #%d", op_name, occurrence);
+    t->cur_a = a; t->cur_b = b; t->cur_m = mask;
+    t->serial = true;
+    int rc = 0;
+    for (long i = 0; i <= idx && !rc; ++i) rc = t->prog[i].fn() || reduce_sync_point(t, t->prog[i]);
+    t->serial = false;
+    if (rc) return 1;
+    CK(cudaStreamSynchronize(t->s->stream));
+    if (ops_run) *ops_run = idx + 1;
+    return 0;
+}
+
+int cenn_trainer_op_bytes(cenn_trainer *t, double *bytes, int64_t cap, int64_t *nops) {
+    REQUIRE(t && bytes && nops, "cenn_trainer_op_bytes: null argument");
+    REQUIRE((int64_t)t->prog.size() <= cap, "cenn_trainer_op_bytes: capacity %lld < %zu ops", (long long)cap, t->prog.size());
+    for (size_t i = 0; i < t->prog.size(); ++i) bytes[i] = t->prog[i].bytes;
+    *nops = (int64_t)t->prog.size();
     return 0;
 }
 

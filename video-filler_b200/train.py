@@ -365,9 +365,40 @@ class FusedTrainer:
         for k, t in zip(nm, acc):
             by_op[k] = by_op.get(k, 0.0) + float(t)
         tc = flops > 0
-        return {"names": nm, "ms": acc, "flops": flops, "total_ms": float(acc.sum()), "tc_ms": float(acc[tc].sum()),
-                "tc_flops": float(flops[tc].sum()), "tc_launches": int(tc.sum()),
+        by = np.zeros(cap, np.float64)
+        nb = C.c_int64()
+        api().cenn_trainer_op_bytes(self.h, by.ctypes.data_as(C.c_void_p), cap, C.byref(nb))
+        best = None
+        for i in np.nonzero(tc)[0]:
+            tf = flops[i] / (acc[i] * 1e-3) / 1e12 if acc[i] > 0 else 0.0
+            if flops[i] >= 1e10 and (best is None or tf > best["tflops"]):
+                best = {"op": nm[i], "index": int(i), "ms": round(float(acc[i]), 4), "gflop": round(float(flops[i]) / 1e9, 2), "tflops": round(float(tf), 1)}
+        return {"names": nm, "ms": acc, "flops": flops, "bytes": by[:n.value].copy(), "total_ms": float(acc.sum()), "tc_ms": float(acc[tc].sum()),
+                "tc_flops": float(flops[tc].sum()), "tc_launches": int(tc.sum()), "best_tc": best,
                 "by_op": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])}}
+
+    def timeline(self, a_ptr, b_ptr, mask_ptr=None):
+        """One eager step on the executor's own streams: [(name, stream id, start ms, end ms)] per op (cenn_trainer_timeline_step)."""
+        cap = 4096
+        names = C.create_string_buffer(1 << 16)
+        ms = np.zeros(cap, np.float32)
+        fl = np.zeros(cap, np.float64)
+        n = C.c_int64()
+        api().cenn_trainer_profile_step(self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(mask_ptr) if mask_ptr else None,
+                                        names, len(names), ms.ctypes.data_as(C.c_void_p), fl.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+        nm = names.value.decode().split("\n")[:n.value]
+        t0, t1, sid = np.zeros(cap, np.float32), np.zeros(cap, np.float32), np.zeros(cap, np.int32)
+        for _ in range(2):      # second run: warm
+            api().cenn_trainer_timeline_step(self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(mask_ptr) if mask_ptr else None,
+                                             t0.ctypes.data_as(C.c_void_p), t1.ctypes.data_as(C.c_void_p), sid.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+        return [(nm[i], int(sid[i]), float(t0[i]), float(t1[i])) for i in range(n.value)]
+
+    def step_until(self, a_ptr, b_ptr, mask_ptr, op_name, occurrence=0):
+        """Run the step program up to and including the `occurrence`-th op named `op_name` (test hook, cenn_trainer_step_until)."""
+        n = C.c_int64()
+        api().cenn_trainer_step_until(self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(mask_ptr) if mask_ptr else None,
+                                      op_name.encode(), int(occurrence), C.byref(n))
+        return n.value
 
     def launches_per_step(self):
         n = C.c_int64()
