@@ -56,6 +56,25 @@ int map_plain(CUtensorMap *m, const bf16 *S, int N, int h, int w, int C, int bw,
     uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bn};
     return make_map(m, S, 5, dims, st, box);
 }
+// Implicit im2col of a THIN large-side tensor stored with a physical one-pixel zero border, Lpad [N, H2+2, W2+2, Cp] (Cp = 4 or 16):
+// the 4x4 / stride-2 / pad-1 window of output pixel (ox, oy) is rows 2oy .. 2oy+3, pixels 2ox .. 2ox+3 of the padded tensor, and one
+// window row (4 pixels x Cp channels) is contiguous in memory.  TMA strides may overlap, so the window becomes a box:
+//   Cp == 4 : dims (16 [v,c], 4 [u], w [ox, stride 2 px], h [oy, stride 2 rows], N), box (16, 4, bw, bh, bn): one 128-byte K row (u,v,c)
+//             per output pixel -- the whole K = 64 in ONE k-block (coordinates in `a_order`: (k0, u0, x0, y0, n0));
+//   Cp == 16: dims (64 [v,c], w, 4 [u, stride 1 row], h, N), box (64, bw, 1, bh, bn): one k-block per window row u (existing order).
+int map_thin_gather(CUtensorMap *m, const bf16 *Lpad, int N, int H2, int W2, int Cp, int bw, int bh, int bn) {
+    const uint64_t px = (uint64_t)Cp * 2, row = (uint64_t)(W2 + 2) * px, img = (uint64_t)(H2 + 2) * row;
+    if (Cp == 4) {
+        uint64_t dims[5] = {16, 4, (uint64_t)W2 / 2, (uint64_t)H2 / 2, (uint64_t)N};
+        uint64_t st[4] = {row, 2 * px, 2 * row, img};
+        uint32_t box[5] = {16, 4, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+        return make_map(m, Lpad, 5, dims, st, box);
+    }
+    uint64_t dims[5] = {64, (uint64_t)W2 / 2, 4, (uint64_t)H2 / 2, (uint64_t)N};
+    uint64_t st[4] = {2 * px, row, 2 * row, img};
+    uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bn};
+    return make_map(m, Lpad, 5, dims, st, box);
+}
 int map_2d(CUtensorMap *m, const bf16 *B, uint64_t K, uint64_t rows, int box_rows) {
     uint64_t dims[2] = {K, rows};
     uint64_t st[1] = {K * 2};
@@ -147,9 +166,10 @@ int config_wgrad(TcPlan *pl, int BN, int nkb, dim3 grid) {
 int pick_bn(int n_valid, int m_tiles, int sm_count) {
     // widest N tile (256-wide MMAs run the tensor pipe at full rate with the least smem traffic) that still
     // leaves at least one tile per SM for the persistent kernel
+    static const double frac = getenv("CENN_BN_FRAC") ? atof(getenv("CENN_BN_FRAC")) : 1.0;   // tiles >= frac * SMs keeps the wider tile
     int bn = 256;
     while (bn > 32 && (bn / 2 >= n_valid)) bn /= 2;
-    while (bn > 64 && (long long)m_tiles * ((n_valid + bn - 1) / bn) < sm_count) bn /= 2;
+    while (bn > 64 && (double)m_tiles * ((n_valid + bn - 1) / bn) < frac * sm_count) bn /= 2;
     return bn;
 }
 
@@ -340,6 +360,40 @@ int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, b
     fill_epilogue(p, ep, S);
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * N * h * w * (double)Cs * 16.0 * Clp;
+    return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles);
+}
+
+// ------------------------------------------------------------------ P1t: fprop-type on a thin (3 / 12 channel) large side, implicit im2col
+// S[pix,cs] = sum_{u,v,c} Lpad[n, 2oy+u, 2ox+v, c] * Wf[cs][(u,v)][c]: the first layers of G and D (train.lua:89,183; train_vid_weighted.lua:114,213)
+// without the explicit col buffer (16x the input: 134 MB per use at 256 images).  K = 16*Cp: one k-block (Cp = 4) or four (Cp = 16).
+int tc_plan_fprop_thin(cenn_state *s, TcPlan *pl, const bf16 *Lpad, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Cp, const TcEpilogue &ep) {
+    REQUIRE(Cp == 4 || Cp == 16, "tc_fprop_thin: Cp must be 4 or 16 (got %d)", Cp);
+    REQUIRE(w % 2 == 0 || w == 1, "tc_fprop_thin: odd output width %d", w);
+    int bw, bh, bn;
+    choose_box(w, h, 128, bw, bh, bn);
+    if (map_thin_gather(planA(pl), Lpad, N, 2 * h, 2 * w, Cp, bw, bh, bn)) return 1;
+    tc::GatherGemmParams p = {};
+    p.box_w = bw; p.box_h = bh; p.box_n = bn; p.bw_log2 = ilog2(bw); p.bh_log2 = ilog2(bh);
+    p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
+    const int tiles_n = (N + bn - 1) / bn, m_tiles = p.tiles_x * p.tiles_y * tiles_n;
+    int BN = pick_bn(Cs, m_tiles, s->sm_count);
+    if (Csp < 64) BN = 32;
+    const int K = 16 * Cp;
+    if (map_2d(planB(pl), Wf, (uint64_t)K, (uint64_t)Cs, BN)) return 1;
+    memset(pl->tmO, 0, sizeof(pl->tmO));
+    if (BN >= 64 && map_plain(planO(pl), S, N, h, w, Csp, bw, bh, bn)) return 1;
+    p.o_cols = Csp;
+    if (Cp == 4) { p.a_order = 1; p.num_taps = 1; p.chunks = 1; p.bk_per_tap = 0; p.num_kb = 1; }
+    else {
+        p.num_taps = 4; p.chunks = 1; p.bk_per_tap = 64; p.num_kb = 4;
+        for (int u = 0; u < 4; ++u) p.A2[0][u] = u;
+    }
+    p.m_tiles = m_tiles; p.n_tiles = (Cs + BN - 1) / BN; p.num_phases = 1;
+    p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cs;
+    p.sX = Csp; p.sY = (long long)w * Csp; p.sN = (long long)h * w * Csp;
+    fill_epilogue(p, ep, S);
+    memcpy(pl->params, &p, sizeof(p));
+    pl->flops = 2.0 * N * h * w * (double)Cs * K;
     return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles);
 }
 
@@ -543,6 +597,29 @@ int tc_plan_wgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *L, fl
     p.out = gW; p.scale = scale; p.accumulate = accumulate;
     pl->flops = 2.0 * N * h * w * (double)Cs * 16.0 * Clp;
     return wgrad_common(s, pl, p, 16, Cs, Clp, p.tiles_x * p.tiles_y * tiles_n);
+}
+
+// gW[cs][(u,v)][c] (+)= sum_pix S[pix,cs] * Lpad[window(pix)][(u,v),c] for a thin large side: the L operand rows are the implicit
+// im2col rows of tc_plan_fprop_thin (one 64-row block for Cp = 4, four for Cp = 16)
+int tc_plan_wgrad_thin(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Lpad, float *gW, int N, int h, int w, int Cs, int Csp, int Cp, float scale, int accumulate) {
+    REQUIRE(Cp == 4 || Cp == 16, "tc_wgrad_thin: Cp must be 4 or 16 (got %d)", Cp);
+    REQUIRE(Csp % 8 == 0, "tc_wgrad_thin: Csp must be a multiple of 8 (got %d)", Csp);
+    int bw, bh, bn;
+    choose_box(w, h, 64, bw, bh, bn);
+    if (map_thin_gather(planA(pl), Lpad, N, 2 * h, 2 * w, Cp, bw, bh, bn)) return 1;
+    if (map_plain(planB(pl), S, N, h, w, Csp, bw, bh, bn)) return 1;
+    tc::WgradParams p = {};
+    p.box_w = bw; p.box_h = bh; p.box_n = bn;
+    p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh;
+    const int tiles_n = (N + bn - 1) / bn;
+    const int K = 16 * Cp, blocks = K / 64;                    // 64-row blocks of the output (tap-major rows of 64 (u?,v,c) entries)
+    p.a_order = Cp == 4 ? 1 : 0;
+    for (int t = 0; t < 16; ++t) p.g2[t] = (Cp == 16 && t < 4) ? t : 0;
+    p.num_taps = blocks;
+    p.cl_stride = 64; p.cl_valid = 64; p.cs_valid = Cs; p.out_cs_stride = K;
+    p.out = gW; p.scale = scale; p.accumulate = accumulate;
+    pl->flops = 2.0 * N * h * w * (double)Cs * K;
+    return wgrad_common(s, pl, p, blocks, Cs, 64, p.tiles_x * p.tiles_y * tiles_n);
 }
 
 int tc_plan_wgrad_plain(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *L, float *gW, int M, int Cs, int Csp, int Clp, float scale, int accumulate) {

@@ -144,6 +144,22 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const bf16 *__restrict__ 
     }
 }
 
+// dense thin tensor [N,H,W,CP] -> the same with a physical one-pixel border [N,H+2,W+2,CP] (border zeroed once at allocation):
+// the operand layout of the implicit-im2col first layers (conv_tc.cu: map_thin_gather).  One thread per pixel.
+template <int CP>
+__global__ void __launch_bounds__(256) pad_copy_kernel(const bf16 *__restrict__ src, bf16 *__restrict__ dst, int N, int H, int W) {
+    const int64_t total = (int64_t)N * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H), n = (int)(i / ((int64_t)W * H));
+        const int64_t o = ((int64_t)n * (H + 2) + y + 1) * (W + 2) + x + 1;
+        if (CP == 4) reinterpret_cast<uint2 *>(dst)[o] = __ldg(reinterpret_cast<const uint2 *>(src) + i);
+        else {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src) + 2 * i), b = __ldg(reinterpret_cast<const uint4 *>(src) + 2 * i + 1);
+            reinterpret_cast<uint4 *>(dst)[2 * o] = a; reinterpret_cast<uint4 *>(dst)[2 * o + 1] = b;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- batch norm
 // sums -> mean / invstd / running stats / (scale, shift); `fold` column groups are summed (G1's GEMM epilogue
 // accumulates per (tap, channel) column).  Zeroes the accumulators for the next use.
@@ -406,7 +422,7 @@ __device__ __forceinline__ void unpack8b(const uint4 &u, float (&f)[8]) {
 }
 
 // BN backward pass 1: part[cta][0][c] = sum dz, part[cta][1][c] = sum dz * (y - mean[c]),  dz = g * act'(y*scale+shift)
-template <int ACT>
+template <int ACT, bool kAtomic = false>
 __global__ void __launch_bounds__(256, 4) bn_bwd_reduce2_kernel(const bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
         const float *__restrict__ shift, const float *__restrict__ mean, float *__restrict__ part, int Cp, int64_t npix, int vec_per_pix, int C,
         float negval) {
@@ -435,7 +451,9 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce2_kernel(const bf16 *__re
             }
         }
     }
-    fold_and_flush<2, false>(acc, active, part + (size_t)blockIdx.x * 2 * Cp, Cp, C);
+    // kAtomic: `part` is ONE row [2][Cp] of fp32 sums that every CTA adds into (consumed and re-zeroed by bn_bwd_coef_apply_kernel)
+    if (kAtomic) fold_and_flush<2, true>(acc, active, part, Cp, C);
+    else fold_and_flush<2, false>(acc, active, part + (size_t)blockIdx.x * 2 * Cp, Cp, C);
 }
 // sums the partial rows; coefficients for pass 2 + BN parameter gradients.
 // sums_io [2][Cp]: rows > 0: written with the folded sums (the buffer a data-parallel run all-reduces); rows == 0: read.
@@ -483,6 +501,76 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply2_kernel(bf16 *__restrict_
         float sc[8], sh[8], cA[8], cB[8], cD[8];
         load8f(scale, vec * 8, C, sc); load8f(shift, vec * 8, C, sh);
         load8f(coef, vec * 8, C, cA); load8f(coef + C, vec * 8, C, cB); load8f(coef + 2 * C, vec * 8, C, cD);
+        const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * BN_U) {
+            uint4 rg[BN_U], ry[BN_U];
+#pragma unroll
+            for (int u = 0; u < BN_U; ++u) {
+                int64_t p = p0 + u * stride;
+                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = reinterpret_cast<const uint4 *>(g)[vi]; ry[u] = __ldg(reinterpret_cast<const uint4 *>(y) + vi); }
+            }
+#pragma unroll
+            for (int u = 0; u < BN_U; ++u) {
+                int64_t p = p0 + u * stride;
+                if (p < npix) {
+                    float fg[8], fy[8];
+                    unpack8b(rg[u], fg); unpack8b(ry[u], fy);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval);
+                        float r = fmaf(dz, cA[k], fmaf(-fy[k], cB[k], cD[k]));          // all three are 0 on padded lanes
+                        fg[k] = r; acc[0][k] += r;
+                    }
+                    reinterpret_cast<uint4 *>(g)[p * vec_per_pix + vec] = pack8(fg);
+                }
+            }
+        }
+    }
+    if (gb_part) fold_and_flush<1, false>(acc, active, gb_part + (size_t)blockIdx.x * Cp, Cp, C);
+}
+// BN backward pass 2 with the coefficient step folded into its prologue (single GPU): every CTA derives A, B, D of ITS channels
+// from the summed [2][Cp] row left by bn_bwd_reduce2_kernel<ACT, true> (a few fp64 operations per thread), CTA row 0 also
+// accumulates the BN affine gradients, and the last CTA to have read the sums zeroes them for the next use.  Removes the
+// dependent bn_bwd_coef2 launch (~10 us on the critical path) per BN layer and sweep.
+template <int ACT>
+__global__ void __launch_bounds__(256, 3) bn_bwd_coef_apply_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
+        const float *__restrict__ shift, float *__restrict__ sums, const float *__restrict__ gamma, const float *__restrict__ invstd,
+        const float *__restrict__ mean, float *__restrict__ ggamma, float *__restrict__ gbeta, float *__restrict__ gb_part, int Cp,
+        int64_t npix, int vec_per_pix, int C, float negval, double n, unsigned int *__restrict__ done_counter) {
+    __shared__ int is_last;
+    const int vec = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = vec < vec_per_pix;
+    float acc[1][8] = {};
+    float sc[8], sh[8], cA[8], cB[8], cD[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = vec * 8 + k;
+        sc[k] = sh[k] = cA[k] = cB[k] = cD[k] = 0.f;
+        if (active && c < C) {
+            const double s = (double)__ldcg(sums + c), d = (double)__ldcg(sums + Cp + c);
+            const double is = invstd[c], A = is * (double)gamma[c], k1 = is * is * d / n;
+            sc[k] = scale[c]; sh[k] = shift[c];
+            cA[k] = (float)A; cB[k] = (float)(A * k1); cD[k] = (float)(((double)mean[c] * k1 - s / n) * A);
+            if (blockIdx.x == 0 && threadIdx.y == 0) {
+                if (ggamma) ggamma[c] += (float)(d * is);
+                if (gbeta) gbeta[c] += (float)s;
+            }
+        }
+    }
+    __syncthreads();                                   // all reads of `sums` by this CTA are done
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        const unsigned int total = gridDim.x * gridDim.y;
+        const unsigned int k = atomicAdd(done_counter, 1u);
+        is_last = (k == total - 1);
+        if (is_last) *done_counter = 0u;
+    }
+    __syncthreads();
+    if (is_last) {
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        for (int i = tid; i < 2 * Cp; i += blockDim.x * blockDim.y) sums[i] = 0.f;
+    }
+    if (active) {
         const int64_t stride = (int64_t)gridDim.x * blockDim.y;
         for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * BN_U) {
             uint4 rg[BN_U], ry[BN_U];

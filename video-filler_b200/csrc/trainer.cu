@@ -48,6 +48,7 @@ struct Block {
     unsigned long long *bar = nullptr;      // experimental fused BN backward (CENN_BN_BWD_FUSED=1): grid-barrier counter
     float *part = nullptr;                  // per-CTA partial rows of the backward reductions [part_rows][2*Coutp]
     int part_rows = 0;
+    int red_rows = 0;                       // CTA rows of the atomic-sum variant of the BN backward reduction
     float *stats = nullptr, *bsums = nullptr, *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *coef = nullptr;
     float *running = nullptr;               // [2][Cout] running_mean, running_var
     int stats_cols = 0, fold = 1;
@@ -73,6 +74,7 @@ struct Net {
     float *adam_step = nullptr;    // device: lr * sqrt(1-b2^t)/(1-b1^t)
     float lr = 0.f;
     Tensor input;             // fixed input buffer of the net
+    bf16 *inpad = nullptr;    // the same with a one-pixel zero border [N, H+2, W+2, Cp]: operand of the implicit-im2col first layer
 };
 
 struct Op {
@@ -224,6 +226,11 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
     const int N = t->B;
     // input tensor (thin: 3 or 12 channels)
     if (alloc_tensor(t, net.input, N, in_size, in_size, in_C, pad_thin(in_C))) return 1;
+    static const bool thin_im2col = getenv("CENN_THIN_IM2COL") != nullptr;      // 1: explicit col buffer for the first layer (round-1 path)
+    if (!thin_im2col && !specs.empty() && specs[0].type == CONV_S2 && net.input.Cp < 64) {
+        net.inpad = dalloc<bf16>(t, (int64_t)N * (in_size + 2) * (in_size + 2) * net.input.Cp);
+        if (!net.inpad) return 1;
+    }
     Tensor cur = net.input;
     int64_t off = 0, toff = 0;
     net.blocks.resize(specs.size());
@@ -287,13 +294,14 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             const int ty = 256 / tx, gy = (vpp + tx - 1) / tx;
             const int64_t npix = b.Coutp >= 8 ? (int64_t)N * oh * ow : (int64_t)N * oh * ow / 2;
             b.part_rows = (int)std::max<int64_t>(1, std::min<int64_t>((npix + ty * 4 - 1) / (ty * 4), (int64_t)s->sm_count * 4 / gy));
-            // single GPU: a BN layer's backward (reduce -> coefficients -> apply) is ONE cooperatively launched kernel with two grid
-            // barriers (nhwc::bn_bwd_fused_kernel) -> the grid (part_rows x gy CTAs) must be co-resident.  CENN_BN_BWD_FUSED=0
-            // restores the three-launch path; CENN_BN_FUSED_MAX_ELEMS bounds the layer size (default: every layer).
+            // EXPERIMENT (CENN_BN_BWD_FUSED=1, off by default): a BN layer's backward as ONE cooperatively launched kernel with two grid
+            // barriers (nhwc::bn_bwd_fused_kernel); the grid (part_rows x gy CTAs) must be co-resident.  Measured on B200 (round 2):
+            // 44 us per layer against 46 us for the three launches when run alone, and SLOWER inside the step (3.36 vs 3.18 ms)
+            // because a cooperative grid waits until the side streams' GEMM CTAs have left the SMs.  Kept for reference only.
             {
                 const char *e = getenv("CENN_BN_BWD_FUSED"), *m = getenv("CENN_BN_FUSED_MAX_ELEMS");
                 const int64_t max_elems = m ? atoll(m) : (int64_t)1 << 40;
-                if (sp.bn && !(e && atoi(e) == 0) && t->cfg.world_size <= 1 && b.Coutp >= 8 && (int64_t)N * oh * ow * b.Coutp <= max_elems) {
+                if (sp.bn && e && atoi(e) != 0 && t->cfg.world_size <= 1 && b.Coutp >= 8 && (int64_t)N * oh * ow * b.Coutp <= max_elems) {
                     int per_sm_l = 0, per_sm_r = 0;
                     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, nhwc::bn_bwd_fused_kernel<nhwc::ACT_LEAKY>, 256, 2 * tx * 8 * sizeof(float)));
                     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, nhwc::bn_bwd_fused_kernel<nhwc::ACT_RELU>, 256, 2 * tx * 8 * sizeof(float)));
@@ -303,10 +311,12 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                     if (!b.bar) return 1;
                 }
             }
+            { const char *e = getenv("CENN_BN_RED_ROWS"); const int cap = e ? atoi(e) : 2 * s->sm_count;     // fewer CTAs add into the same [2][C] row
+              b.red_rows = std::max(1, std::min(b.part_rows, std::max(1, cap / gy))); }
             b.part = dalloc<float>(t, (int64_t)b.part_rows * 2 * std::max(b.Coutp, 8));
             if (!b.part) return 1;
         }
-        if (b.thin && !(t->infer && sp.type != CONV_S2)) {
+        if (b.thin && !(t->infer && sp.type != CONV_S2) && !(sp.type == CONV_S2 && net.inpad)) {
             b.col_rows = (int64_t)N * b.h * b.w; b.col_k = 16 * b.Clp;
             b.col = dalloc<bf16>(t, b.col_rows * b.col_k);
             if (!b.col) return 1;
@@ -356,7 +366,8 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             TcEpilogue ep_m = ep; ep_m.b_mn = true;
             switch (b.type) {
                 case CONV_S2:
-                    if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, b.a.p, M, b.Cs, (int)b.col_k, b.Csp, ep)) return 1; }
+                    if (b.thin && net.inpad) { if (tc_plan_fprop_thin(s, &b.p_fwd, net.inpad, Wf, b.a.p, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep)) return 1; }
+                    else if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, b.a.p, M, b.Cs, (int)b.col_k, b.Csp, ep)) return 1; }
                     else if (tc_plan_fprop_s2(s, &b.p_fwd, b.in.p, Wf, b.a.p, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep)) return 1;
                     break;
                 case CONV_V4:
@@ -425,9 +436,11 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         TcEpilogue ep_n;
         switch (b.type) {
             case CONV_S2: {
-                if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, fwd_out, M, b.Cs, (int)b.col_k, b.Csp, ep_f)) return 1; }
+                if (b.thin && net.inpad) { if (tc_plan_fprop_thin(s, &b.p_fwd, net.inpad, Wf, fwd_out, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep_f)) return 1; }
+                else if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, fwd_out, M, b.Cs, (int)b.col_k, b.Csp, ep_f)) return 1; }
                 else if (tc_plan_fprop_s2(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep_f)) return 1;
-                if (b.thin) { if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.col, gW, M, b.Cs, b.Csp, (int)b.col_k, 1.f, 1)) return 1; }
+                if (b.thin && net.inpad) { if (tc_plan_wgrad_thin(s, &b.p_wgrad, b.g.p, net.inpad, gW, N, b.h, b.w, b.Cs, b.Csp, b.Clp, 1.f, 1)) return 1; }
+                else if (b.thin) { if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.col, gW, M, b.Cs, b.Csp, (int)b.col_k, 1.f, 1)) return 1; }
                 else if (tc_plan_wgrad_s2(s, &b.p_wgrad, b.g.p, b.in.p, gW, N, b.h, b.w, b.Cs, b.Csp, b.Clp, 1.f, 1)) return 1;
                 if (b.has_dgrad) {
                     REQUIRE(b.Csp % 64 == 0, "block %zu: dgrad needs small-side channels padded to 64 (got %d)", i, b.Csp);
@@ -509,6 +522,18 @@ void emit_im2col(T *t, const Tensor &L, bf16 *col, int h, int w) {
         KLAUNCH(s); return 0;
     });
 }
+// first layer of a net: its thin input -> the bordered copy the implicit-im2col plans read (1.03x the input instead of a 16x col buffer)
+void emit_pad_input(T *t, Net &net) {
+    cenn_state *s = t->s;
+    Net *n = &net;
+    emit(t, "pad_input", [s, n]() {
+        const Tensor &x = n->input;
+        if (x.Cp == 4) nhwc::pad_copy_kernel<4><<<grid1d(s, x.pix()), 256, 0, s->stream>>>(x.p, n->inpad, x.N, x.H, x.W);
+        else if (x.Cp == 16) nhwc::pad_copy_kernel<16><<<grid1d(s, x.pix()), 256, 0, s->stream>>>(x.p, n->inpad, x.N, x.H, x.W);
+        else { cenn_set_error("pad_input: unsupported thin channel count %d", x.Cp); return 1; }
+        KLAUNCH(s); return 0; });
+    t->prog.back().bytes = 2.0 * 2.0 * (double)net.input.pix() * net.input.Cp;
+}
 void reduce_dims(int vec_per_pix, dim3 &block, int &gy) {
     int tx = 1; while (tx < vec_per_pix && tx < 64) tx *= 2;
     block = dim3(tx, 256 / tx);
@@ -529,13 +554,13 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
             nhwc::head_fwd_kernel<<<(B * 32 + 255) / 256, 256, 0, s->stream>>>(in.p, w, bias, b->sig, B, K); KLAUNCH(s); return 0; });
         return;
     }
-    if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
+    if (b->thin && b->type == CONV_S2) { if (net.inpad) emit_pad_input(t, net); else emit_im2col(t, b->in, b->col, b->h, b->w); }
     if (b->bias_exp) {
         const float *bias = master + b->b_off;
         emit(t, "expand_bias", [s, b, bias]() { expand_bias_kernel<<<(16 * b->Clp + 255) / 256, 256, 0, s->stream>>>(bias, b->bias_exp, b->Cout, b->Clp); KLAUNCH(s); return 0; });
     }
     emit_plan(t, "conv_fwd", &b->p_fwd);
-    if (b->bn && train && t->cfg.world_size <= 1 && b->Coutp <= 1024 && b->fold == 1 && getenv("CENN_NO_BN_FUSE") == nullptr) {
+    if (b->bn && train && t->cfg.world_size <= 1 && b->Coutp <= 4096 && getenv("CENN_NO_BN_FUSE") == nullptr) {
         float *gamma = master + b->g_off, *beta = master + b->be_off;
         emit(t, "bn_fin_apply", [s, b, gamma, beta, n_global]() {
             int64_t nvec = b->y.elems() / 8;
@@ -620,13 +645,29 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
                 s->launches++; return 0; });
             t->prog.back().bytes = 5.0 * 2.0 * (double)npix * b->Cout;      // read g, y; (re-read from L2); write g_y: 5 s bytes per element
         } else {
-        emit(t, "bn_bwd_reduce", [s, b, npix, vpp]() {
+        const bool two_launch = !dp && getenv("CENN_BN_BWD_3LAUNCH") == nullptr;   // single GPU: sums by fp32 atomics, coefficients in the apply prologue
+        emit(t, "bn_bwd_reduce", [s, b, npix, vpp, two_launch]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
+            if (two_launch) {
+                auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_LEAKY, true> : nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_RELU, true>;
+                kern<<<dim3(b->red_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->mean,
+                    b->bsums, b->Coutp, npix, vpp, b->Cout, 0.2f);
+                KLAUNCH(s); return 0;
+            }
             auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_RELU>;
             kern<<<dim3(b->part_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->mean,
                 b->part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 2.0 * 2.0 * (double)npix * b->Cout;            // read g, y
+        if (two_launch) {
+            emit(t, "bn_bwd_apply", [s, b, gamma, gg, gbeta, gb_part, npix, vpp, n_global]() {
+                dim3 blk; int gy; reduce_dims(vpp, blk, gy);
+                auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_coef_apply_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_coef_apply_kernel<nhwc::ACT_RELU>;
+                kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->bsums, gamma, b->invstd, b->mean,
+                    gg, gbeta, gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f, n_global, b->done_ctr);
+                KLAUNCH(s); return 0; });
+            t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;        // read g, y; write g_y
+        } else {
         if (dp && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {   // fold this rank's partial rows, then exchange + coefficients in one kernel
             const float inv_world = 1.f / (float)t->cfg.world_size;
             emit(t, "bn_bwd_fold", [s, b]() {
@@ -656,6 +697,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
                 gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;            // read g, y; write g_y
+        }   // coefficient launch + apply
         }   // three-launch path
     } else if (b->Coutp >= 8) {
         emit(t, "act_bwd", [s, b, gb_part, npix, vpp]() {
@@ -1699,7 +1741,7 @@ int inpainter_build_program(cenn_inpainter *p) {
         KLAUNCH(s); return 0; });
     for (size_t i = 0; i < G.blocks.size(); ++i) {
         Block *b = &G.blocks[i];
-        if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
+        if (b->thin && b->type == CONV_S2) { if (G.inpad) emit_pad_input(t, G); else emit_im2col(t, b->in, b->col, b->h, b->w); }
         emit_plan(t, "conv_fwd", &b->p_fwd);
     }
     emit(t, "tiles->nchw", [t, s]() {
