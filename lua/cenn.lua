@@ -37,6 +37,14 @@ int cenn_addcmul(cenn_state *s, float *y, float a, const float *p, const float *
 int cenn_addcdiv(cenn_state *s, float *y, float a, const float *p, const float *q, int64_t n);
 int cenn_sqrt(cenn_state *s, float *x, int64_t n);
 int cenn_normal(cenn_state *s, float *x, int64_t n, float mean, float std, uint64_t seed);
+int cenn_uniform(cenn_state *s, float *x, int64_t n, float a, float b, uint64_t seed);
+int cenn_add_scalar(cenn_state *s, float *x, int64_t n, float a);
+int cenn_cmul(cenn_state *s, float *y, const float *x, int64_t n);
+int cenn_u8_to_float(cenn_state *s, float *dst, const uint8_t *src, int64_t n);
+int cenn_masked_fill(cenn_state *s, float *x, const float *mask, int64_t n, float v);
+int cenn_fill_box(cenn_state *s, float *x, int64_t N, int64_t C, int64_t H, int64_t W, int64_t c0, int64_t c1, int64_t y0, int64_t y1, int64_t x0, int64_t x1, float v);
+int cenn_crop(cenn_state *s, float *dst, const float *src, int64_t N, int64_t C, int64_t H, int64_t W, int64_t y0, int64_t x0, int64_t h, int64_t w);
+int cenn_MaskComposite(cenn_state *s, float *dst, const float *mask, const float *src, int64_t n);
 int cenn_SpatialConvolutionMM_updateOutput(cenn_state *s, const float *input, float *output, const float *weight, const float *bias,
     int64_t batch, int64_t nInputPlane, int64_t inH, int64_t inW, int64_t nOutputPlane, int kW, int kH, int dW, int dH, int padW, int padH);
 int cenn_SpatialConvolutionMM_updateGradInput(cenn_state *s, const float *gradOutput, float *gradInput, const float *weight,
@@ -105,25 +113,155 @@ end
 function CudaTensor:nElement() return numel(self.sz) end
 function CudaTensor:size(d) if d then return self.sz[d] end; return torch.LongStorage(self.sz) end
 function CudaTensor:dim() return #self.sz end
+function CudaTensor:nDimension() return #self.sz end
+function CudaTensor:type(ty)                            -- tensor:type() / tensor:type('torch.FloatTensor') / :typeAs
+  if not ty then return 'torch.CudaTensor' end
+  if ty == 'torch.CudaTensor' then return self end
+  local t = self:float(); return ty == 'torch.FloatTensor' and t or t:type(ty)
+end
+function CudaTensor:typeAs(o) return self:type(torch.type(o) == 'table' and 'torch.CudaTensor' or torch.type(o)) end
+function CudaTensor:cuda() return self end
+function CudaTensor:contiguous() return self end          -- stand-in tensors are always dense
+function CudaTensor:isContiguous() return true end
+function CudaTensor:isSameSizeAs(o) if #self.sz ~= #o.sz then return false end; for i, d in ipairs(self.sz) do if d ~= o.sz[i] then return false end end; return true end
 function CudaTensor:fill(v) check(lib.cenn_fill(cenn.state, self.ptr, self:nElement(), v)); return self end
 function CudaTensor:zero() return self:fill(0) end
 function CudaTensor:mul(a) check(lib.cenn_mul(cenn.state, self.ptr, self:nElement(), a)); return self end
-function CudaTensor:add(a, x) check(lib.cenn_axpy(cenn.state, self.ptr, x.ptr, self:nElement(), a)); return self end
-function CudaTensor:copy(src)                         -- from torch.FloatTensor (H2D) or another CudaTensor (D2D)
+function CudaTensor:div(a) return self:mul(1 / a) end
+-- x:add(s) | x:add(t) | x:add(s, t)   (train.lua:398; train_vid_weighted.lua:526; optim.adam)
+function CudaTensor:add(a, x)
+  if x == nil and type(a) == 'number' then check(lib.cenn_add_scalar(cenn.state, self.ptr, self:nElement(), a)); return self end
+  if x == nil then a, x = 1, a end
+  check(lib.cenn_axpy(cenn.state, self.ptr, x.ptr, self:nElement(), a)); return self
+end
+function CudaTensor:cmul(x) check(lib.cenn_cmul(cenn.state, self.ptr, x.ptr, self:nElement())); return self end              -- train_vid_weighted.lua:496
+-- y:addcmul([a,] p, q) / y:addcdiv([a,] p, q)   (train.lua:394; optim.adam: v:addcmul(1-beta2, g, g), x:addcdiv(-step, m, denom))
+function CudaTensor:addcmul(a, p, q) if q == nil then a, p, q = 1, a, p end; check(lib.cenn_addcmul(cenn.state, self.ptr, a, p.ptr, q.ptr, self:nElement())); return self end
+function CudaTensor:addcdiv(a, p, q) if q == nil then a, p, q = 1, a, p end; check(lib.cenn_addcdiv(cenn.state, self.ptr, a, p.ptr, q.ptr, self:nElement())); return self end
+function CudaTensor:sqrt() check(lib.cenn_sqrt(cenn.state, self.ptr, self:nElement())); return self end
+local seed_ctr = 0
+local function next_seed() seed_ctr = seed_ctr + 1; return (torch.initialSeed() % 2147483647) * 4096 + seed_ctr end          -- one Philox stream per call
+function CudaTensor:normal(mean, std) check(lib.cenn_normal(cenn.state, self.ptr, self:nElement(), mean or 0, std or 1, next_seed())); return self end   -- train.lua:61,64,272
+function CudaTensor:uniform(a, b) check(lib.cenn_uniform(cenn.state, self.ptr, self:nElement(), a or 0, b or 1, next_seed())); return self end        -- train.lua:270
+function CudaTensor:copy(src)                         -- from a host tensor (H2D; ByteTensor masks become {0,1} floats) or a CudaTensor / window (D2D)
   if getmetatable(src) == CudaTensor then check(lib.cenn_copy_d2d(cenn.state, self.ptr, src.ptr, self:nElement() * 4))
-  else src = src:contiguous(); check(lib.cenn_copy_h2d(cenn.state, self.ptr, src:data(), self:nElement() * 4)) end
+  elseif torch.type(src) == 'torch.ByteTensor' then            -- input_mask:copy(real_mask) (train_vid_weighted.lua:391)
+    src = src:contiguous()
+    local p = ffi.new('void*[1]'); check(lib.cenn_malloc(cenn.state, self:nElement(), p))
+    check(lib.cenn_copy_h2d(cenn.state, p[0], src:data(), self:nElement()))
+    check(lib.cenn_u8_to_float(cenn.state, self.ptr, ffi.cast('const uint8_t*', p[0]), self:nElement())); check(lib.cenn_free(cenn.state, p[0]))
+  else src = src:float():contiguous(); check(lib.cenn_copy_h2d(cenn.state, self.ptr, src:data(), self:nElement() * 4)) end
   return self
 end
 function CudaTensor:float()
   local t = torch.FloatTensor(unpack(self.sz))
   check(lib.cenn_copy_d2h(cenn.state, t:data(), self.ptr, self:nElement() * 4)); return t
 end
+function CudaTensor:double() return self:float():double() end
+function CudaTensor:byte() return self:float():byte() end
+function CudaTensor:clone() return cenn.CudaTensor(self.sz):copy(self) end                                   -- train.lua:287,389
+function CudaTensor.new(self_or_size, ...)                -- x.new(size) / x.new() (optim.adam state, nn module buffers)
+  local a = {...}
+  if getmetatable(self_or_size) == CudaTensor then
+    if #a == 0 then return cenn.CudaTensor(0) end
+    if type(a[1]) == 'number' then return cenn.CudaTensor(a) end
+    return cenn.CudaTensor(a[1].totable and a[1]:totable() or a[1])
+  end
+  return cenn.CudaTensor(self_or_size, ...)
+end
 function CudaTensor:resize(...) local sz = {...}
+  if type(sz[1]) ~= 'number' then sz = sz[1].totable and sz[1]:totable() or sz[1] end
   if numel(sz) ~= self:nElement() then local n = cenn.CudaTensor(sz); self.ptr, self.gc = n.ptr, n.gc end
   self.sz = sz; return self
 end
-function CudaTensor:resizeAs(o) return self:resize(unpack(o.sz)) end
+function CudaTensor:resizeAs(o) return self:resize(unpack(o.sz or o:size():totable())) end
+function CudaTensor:view(...)                           -- shares storage (train_vid_weighted.lua:163 mask:view; nn.View)
+  local sz = {...}; if type(sz[1]) ~= 'number' then sz = sz[1]:totable() end
+  local known, neg = 1, nil
+  for i, d in ipairs(sz) do if d == -1 then neg = i else known = known * d end end
+  if neg then sz[neg] = self:nElement() / known end
+  assert(numel(sz) == self:nElement(), 'view: size mismatch')
+  return setmetatable({ sz = sz, ptr = self.ptr, gc = self.gc }, CudaTensor)
+end
+function CudaTensor:viewAs(o) return self:view(unpack(o.sz)) end
+function CudaTensor:narrow(dim, first, n)               -- outermost dimension only (getParameters views, batch slices): shares storage
+  assert(dim == 1, 'narrow: only the first dimension of a dense tensor can be narrowed without a copy')
+  local sz = {unpack(self.sz)}; sz[1] = n
+  return setmetatable({ sz = sz, ptr = self.ptr + (first - 1) * (self:nElement() / self.sz[1]), gc = self.gc }, CudaTensor)
+end
+-- mask arithmetic of the video scripts.  Masks are {0,1} float tensors once on the device (train_vid_weighted.lua:302,391).
+function CudaTensor:maskedFill(mask, v) check(lib.cenn_masked_fill(cenn.state, self.ptr, mask.ptr, self:nElement(), v)); return self end    -- inpaint_utils.lua:45-58
+-- x:maskedSelect(mask) is only ever consumed by y:maskedCopy(mask, sel) with the SAME mask (train_vid_weighted.lua:430-434,
+-- inpaint_utils.lua:79-90): the pair is a composite y = where(mask, x, y), so the selection stays lazy and no compaction runs.
+function CudaTensor:maskedSelect(mask) return { lazy_select = true, src = self, mask = mask } end
+function CudaTensor:maskedCopy(mask, sel)
+  assert(type(sel) == 'table' and sel.lazy_select and sel.mask == mask, 'maskedCopy: expects the result of maskedSelect with the same mask')
+  check(lib.cenn_MaskComposite(cenn.state, self.ptr, mask.ptr, sel.src.ptr, self:nElement())); return self
+end
+-- reductions are only used for logging / display in the scripts: computed on the host copy
+function CudaTensor:min() return self:float():min() end
+function CudaTensor:max() return self:float():max() end
+function CudaTensor:mean() return self:float():mean() end
+function CudaTensor:std() return self:float():std() end
+function CudaTensor:sum() return self:float():sum() end
+function CudaTensor:norm(p) return self:float():norm(p) end
+-- range indexing t[{{},{},{a,b},{c,d}}] (train.lua:287-290,392): a window object that supports :fill / :copy / :clone
+local Window = {}; Window.__index = Window
+local function bounds(t, idx)
+  assert(#t.sz == 4, 'range indexing is implemented for [N,C,H,W] tensors')
+  local b = {}
+  for d = 1, 4 do local r = idx[d] or {}; if type(r) == 'number' then r = {r, r} end; b[d] = { (r[1] or 1) - 1, r[2] or t.sz[d] } end
+  assert(b[1][1] == 0 and b[1][2] == t.sz[1], 'range indexing keeps the whole batch dimension')
+  return b
+end
+function Window:fill(v) local t, b = self.t, self.b
+  check(lib.cenn_fill_box(cenn.state, t.ptr, t.sz[1], t.sz[2], t.sz[3], t.sz[4], b[2][1], b[2][2], b[3][1], b[3][2], b[4][1], b[4][2], v)); return self end
+function Window:clone() local t, b = self.t, self.b
+  assert(b[2][1] == 0 and b[2][2] == t.sz[2], 'window clone keeps all channels')
+  local out = cenn.CudaTensor(t.sz[1], t.sz[2], b[3][2] - b[3][1], b[4][2] - b[4][1])
+  check(lib.cenn_crop(cenn.state, out.ptr, t.ptr, t.sz[1], t.sz[2], t.sz[3], t.sz[4], b[3][1], b[4][1], b[3][2] - b[3][1], b[4][2] - b[4][1])); return out end
+function Window:copy(src) error('window:copy is not used by the scripts on GPU tensors') end
+-- an index that restricts only the FIRST dimension (dst[{{b,b+step-1},{},{}}], dst[b]; inpaint_utils.lua:49-56,93-97) is a dense slice:
+-- it becomes a narrow() view with every tensor method; a 4-D box becomes a Window
+local function first_dim_only(t, k)
+  for d = 2, #t.sz do local r = k[d]; if r ~= nil and (type(r) == 'number' or r[1] ~= nil) then return false end end
+  return true
+end
+CudaTensor.__index = function(t, k)
+  if type(k) == 'number' then local v = t:narrow(1, k, 1); local sz = {unpack(t.sz)}; table.remove(sz, 1); v.sz = sz; return v end   -- dst[b]
+  if type(k) == 'table' then
+    if first_dim_only(t, k) then local r = k[1] or {}; if type(r) == 'number' then r = {r, r} end
+      local a, b = r[1] or 1, r[2] or t.sz[1]; return t:narrow(1, a, b - a + 1) end
+    return setmetatable({ t = t, b = bounds(t, k) }, Window)
+  end
+  return CudaTensor[k]
+end
+CudaTensor.__newindex = function(t, k, v)                -- t[{...}] = scalar
+  if type(k) == 'table' then setmetatable({ t = t, b = bounds(t, k) }, Window):fill(v) else rawset(t, k, v) end
+end
 torch.FloatTensor.cuda = function(self) return cenn.CudaTensor(self:size():totable()):copy(self) end
+torch.ByteTensor.cuda = function(self) return cenn.CudaTensor(self:size():totable()):copy(self) end
+
+require 'nn'
+-- module:cuda() / module:float() (train.lua:254; util.lua:76,81): stock nn.Module:type converts through torch.Tensor.type, which the
+-- stand-in tensor is not part of -- walk the module tree and convert every tensor field in place (shared tensors stay shared)
+local function convert_tree(obj, to_cuda, seen)
+  seen = seen or {}
+  if type(obj) ~= 'table' or seen[obj] then return obj end
+  seen[obj] = true
+  for k, v in pairs(obj) do
+    if to_cuda and torch.isTensor(v) and torch.type(v) ~= 'torch.CudaTensor' then
+      seen[v] = seen[v] or (torch.type(v) == 'torch.LongTensor' and v or v:cuda()); obj[k] = seen[v]
+    elseif not to_cuda and getmetatable(v) == CudaTensor then
+      seen[v] = seen[v] or v:float(); obj[k] = seen[v]
+    elseif type(v) == 'table' and getmetatable(v) ~= CudaTensor then convert_tree(v, to_cuda, seen) end
+  end
+  return obj
+end
+function nn.Module:cuda() return convert_tree(self, true) end
+function nn.Module:float() return convert_tree(self, false) end
+function nn.Criterion:cuda() return convert_tree(self, true) end
+function nn.Criterion:float() return convert_tree(self, false) end
 
 ---------------------------------------------------------------------------------------------- nn modules: THNN -> libcenn
 -- Each updateOutput / updateGradInput / accGradParameters below replaces the `input.THNN.<Op>_<phase>(...)` call of

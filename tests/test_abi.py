@@ -119,3 +119,43 @@ def test_lua_shim_prototypes_match_header():
     declared = set(re.findall(r"\b(cenn_\w+)\s*\(", cdefs))
     for call in set(re.findall(r"\blib\.(cenn_\w+)", lua)):
         assert call in declared, "lua/cenn.lua calls %s without declaring it" % call
+
+
+def _shim_tensor_methods():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lua = open(os.path.join(root, "lua", "cenn.lua")).read()
+    meths = set(re.findall(r"function CudaTensor[:.](\w+)", lua))
+    if "CudaTensor.__index = function" in lua:
+        meths.add("__index")
+    if "CudaTensor.__newindex = function" in lua:
+        meths.add("__newindex")
+    return lua, meths
+
+
+def test_lua_shim_implements_every_tensor_method_the_scripts_call():
+    """`train*.lua run unchanged` needs every method the scripts call on GPU tensors.  The call sites are a committed
+    fixture (tools/scan_lua_methods.py over the reference's Lua files); optim.adam's tensor calls and SURVEY 9.11's list are added."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fx = json.load(open(os.path.join(root, "tests", "golden", "lua_tensor_methods.json")))
+    lua, have = _shim_tensor_methods()
+    need = set(fx["methods"])
+    need |= {"mul", "add", "addcmul", "addcdiv", "sqrt", "copy", "clone", "new", "resizeAs", "zero"}             # optim.adam (SURVEY 9.6)
+    need |= {"float", "fill", "cmul", "normal", "uniform", "maskedSelect", "maskedCopy", "maskedFill", "view", "size", "min", "max", "mean", "std",
+             "nElement", "dim", "resize", "type", "typeAs", "contiguous", "narrow"}                               # SURVEY 9.11 + nn containers
+    missing = sorted(m for m in need if m not in have)
+    assert not missing, "lua/cenn.lua CudaTensor lacks: %s" % missing
+    for c in fx["calls"]:
+        # a 4-D box index yields a Window (fill / clone / copy); an index on the first dimension only yields a narrow() view (every tensor method)
+        if c["indexed"] and c["method"] in ("fill", "clone", "copy"):
+            assert re.search(r"function Window:%s\b" % c["method"], lua), "range-indexed %s:%s (%s:%d) has no Window method" % (c["receiver"], c["method"], c["file"], c["line"])
+    assert "first_dim_only" in lua and "t:narrow(1, a, b - a + 1)" in lua
+    # module:cuda() / :float() and criterion:cuda() (train.lua:254-256; util.lua:76,81)
+    for fn in ("function nn.Module:cuda()", "function nn.Module:float()", "function nn.Criterion:cuda()"):
+        assert fn in lua, fn
+    # the fixture is current when the reference is at hand (it is not on the GPU box)
+    if os.path.isdir("/root/reference"):
+        import sys
+        sys.path.insert(0, os.path.join(root, "tools"))
+        import scan_lua_methods
+        assert sorted({c["method"] for c in scan_lua_methods.scan("/root/reference")}) == fx["methods"]
