@@ -432,6 +432,52 @@ def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, v
     return out
 
 
+def run_oplevel(args, torch, api, st, video, local_rank):
+    """The op-level drop-in path (what train*.lua hit through lua/cenn.lua without edits): nn.* mirror modules calling the THNN-table
+    entries one by one in precision mode CENN_BF16 (tensor-core kernels behind NCHW fp32 tensors), four criterion:forward host
+    syncs per step, host batches copied in by the closures (train.lua:292-296).  Single GPU; wall-clock timing because the path
+    is host-synchronous by construction."""
+    import video_filler_b200.tensor as T
+    from video_filler_b200 import synth, train
+    T.set_precision("bf16")
+    B = args.batch
+    opt = opt_for(B, "video" if video else "image")
+    if video:
+        opt["wtgdl"] = args.wtgdl
+    trn = train.ClosureTrainer(opt, seed=1234)
+    drng = np.random.default_rng(1000)
+    batches = [synth.video_batch(B, 12, 128, opt["maskValue"], drng) if video else synth.image_batch(B, 128, 4, drng) for _ in range(2)]
+    launches0 = C.c_int64()
+    for i in range(max(3, args.warmup)):
+        trn.step(*batches[i % 2])
+    torch.cuda.synchronize()
+    api.cenn_kernel_launches(st, C.byref(launches0))
+    sampler = ClockSampler(local_rank); sampler.start(); sampler.mark_begin()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        losses = trn.step(*batches[i % 2])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.finish()
+    launches1 = C.c_int64(); api.cenn_kernel_launches(st, C.byref(launches1))
+    value = B * args.steps / dt
+    gflop = VIDEO_GFLOP_PER_SAMPLE if video else STEP_GFLOP_PER_SAMPLE
+    hbm, tf_burst, tf_sus, peak_src = peaks()
+    nbytes = int(sum(np.asarray(x).nbytes for x in batches[0]))
+    line = {"metric": "train samples/sec (G+D step)", "value": value, "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": (WORKLOAD_VIDEO % (args.wtgdl, B)) if video else WORKLOAD.replace("batch 256", "batch %d" % B), "global_batch": B, "parallelism": "dp1",
+                       "path": "op-level drop-in path: one THNN-table call per module phase (cenn_<Op>_*), NCHW fp32 tensors converted to NHWC bf16 inside every call, "
+                               "4-5 criterion:forward host syncs per step (the reference's call pattern, train.lua:278-410)",
+                       "l2": "working set exceeds the 126 MB L2", "losses_last_step": {k: (round(v, 5) if v is not None else None) for k, v in losses.items()}},
+            "gpu_launches": int(launches1.value - launches0.value), "clocks": clocks, "step_tflops": gflop * 1e-3 * value,
+            "step_frac_of_bf16_burst": gflop * 1e-3 * value / tf_burst,
+            # the same call IS the end-to-end path: host batches in (H2D inside the closures), loss numbers out every step
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 16}}
+    print(json.dumps(line))
+    sys.stdout.flush()
+
+
 def class_rooflines(prof, hbm, peak_src):
     """Achieved GB/s per class of bandwidth kernel = algorithmic bytes (stated per op by the executor) / CUDA-event time."""
     if not prof or prof.get("bytes") is None:
@@ -469,6 +515,8 @@ def main():
     ap.add_argument("--wtgdl", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video-block", action="store_true", help="skip the `video` sub-block (cfg3 at the same N) of the image line")
+    ap.add_argument("--path", default="fused", choices=["fused", "oplevel"],
+                    help="fused = whole-step executor (cenn_trainer_*); oplevel = the drop-in THNN-table path an unchanged script hits (ClosureTrainer, precision bf16)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -494,6 +542,9 @@ def main():
 
     if args.workload == "infer":
         run_infer(args, torch, dist, api, st, stream, rank, local_rank, world)
+        return
+    if args.path == "oplevel":
+        run_oplevel(args, torch, api, st, video, local_rank)
         return
     B = args.batch
     if world > 1:

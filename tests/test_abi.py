@@ -159,3 +159,17 @@ def test_lua_shim_implements_every_tensor_method_the_scripts_call():
         sys.path.insert(0, os.path.join(root, "tools"))
         import scan_lua_methods
         assert sorted({c["method"] for c in scan_lua_methods.scan("/root/reference")}) == fx["methods"]
+
+
+def test_debug_header_symbols_are_exported_and_kept_out_of_the_boundary():
+    """The probes live in csrc/probes.cu and are declared in include/cenn_debug.h, NOT in the drop-in boundary include/cenn.h."""
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dbg = open(os.path.join(root, "include", "cenn_debug.h")).read()
+    names = re.findall(r"CENN_API\s+int\s+(cenn_debug_\w+)\s*\(", dbg)
+    assert len(names) >= 4
+    assert "cenn_debug_" not in open(os.path.join(root, "include", "cenn.h")).read()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        getattr(lib, n)
+    assert "cenn_debug_" not in open(os.path.join(root, "video-filler_b200", "csrc", "conv_tc.cu")).read()

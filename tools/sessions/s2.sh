@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session 2 (round 2): tests + bench variants + CTA-pair probe.  Run from the repo root under gpurun.
-mkdir -p gpurun_out
+mkdir -p gpurun_out; export CENN_THIN_IM2COL=${CENN_THIN_IM2COL-1}
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s2_pytest.log; tail -4 gpurun_out/s2_pytest.log
 for v in default thinold frac85 bn3; do
   case $v in default) E="X=1";; thinold) E="CENN_THIN_IM2COL=1";; frac85) E="CENN_BN_FRAC=0.85";; bn3) E="CENN_BN_BWD_3LAUNCH=1";; esac

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../include/cenn.h"
@@ -71,6 +72,32 @@ static inline int bw_grid(const cenn_state *s, int64_t work_items, int threads, 
 }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still draining -- its prologue (barrier init, TMEM allocation, descriptor prefetch, launch
+// latency) overlaps the predecessor's tail.  pdl_wait() blocks until the predecessor grid has COMPLETED and its memory is visible:
+// every kernel launched through LK() executes it before its first dependent global access.  pdl_trigger() lets the successor be
+// scheduled as soon as every CTA of this grid has started.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// `LK(kernel, grid, block, smem, stream)(args...)` = `kernel<<<grid, block, smem, stream>>>(args...)`, plus the PDL attribute when
+// enabled (CENN_PDL=0 disables).  Only kernels that call pdl_wait() may be launched this way.
+inline bool cenn_pdl_enabled() { static const bool on = !(getenv("CENN_PDL") && atoi(getenv("CENN_PDL")) == 0); return on; }
+template <typename... KArgs>
+struct CennLauncher {
+    void (*kern)(KArgs...); dim3 grid, block; size_t smem; cudaStream_t stream;
+    template <typename... A> void operator()(A &&...a) const {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = cenn_pdl_enabled() ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(a)...);          // errors surface through cudaGetLastError (KLAUNCH / CK_LAUNCH)
+    }
+};
+template <typename... KArgs>
+inline CennLauncher<KArgs...> LK(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream) { return CennLauncher<KArgs...>{kern, grid, block, smem, stream}; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -41,9 +41,6 @@ struct TcPlan {
     int overwrites = 0;           // wgrad: 1 = the launch stores its result (no accumulation; the target need not be zeroed)
 };
 int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Clp, const TcEpilogue &ep);
-// thin (Cp = 4 / 16) large side stored with a one-pixel zero border [N, 2h+2, 2w+2, Cp]: implicit im2col through overlapping TMA strides
-int tc_plan_fprop_thin(cenn_state *s, TcPlan *pl, const bf16 *Lpad, const bf16 *Wf, bf16 *S, int N, int h, int w, int Cs, int Csp, int Cp, const TcEpilogue &ep);
-int tc_plan_wgrad_thin(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Lpad, float *gW, int N, int h, int w, int Cs, int Csp, int Cp, float scale, int accumulate);
 int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep);
 // patch variant of the dgrad type (w, h >= 8; Csp % 64 == 0; Clp % 64 == 0 or Clp in {4, 16}); returns 2 if the shape is not covered
 int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, bf16 *L, int N, int h, int w, int Csp, int Cl, int Clp, int cl_rows, const TcEpilogue &ep);

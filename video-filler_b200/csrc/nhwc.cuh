@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256) to_nchw_kernel(const bf16 *__restrict__ s
 // 16-byte stores (the destination row segment is 32-byte aligned).
 template <int CP>
 __global__ void __launch_bounds__(256) im2col_kernel(const bf16 *__restrict__ L, bf16 *__restrict__ col, int N, int h, int w) {
+    pdl_trigger(); pdl_wait();
     constexpr int V8 = CP / 4;                                   // 8-byte vectors per pixel
     const int64_t total = (int64_t)N * h * w * 4;                // (pixel, window row u)
     const int H2 = 2 * h, W2 = 2 * w;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const bf16 *__restrict__ L,
 // Cp == 16 (12 stacked channels): one thread per 16-byte chunk of the col row -- (tap, channel half) in K order -- so that
 // both the load (half a pixel, 16-byte aligned) and the store (consecutive threads, consecutive 16 bytes) are full vectors.
 __global__ void __launch_bounds__(256) im2col16_kernel(const bf16 *__restrict__ L, bf16 *__restrict__ col, int N, int h, int w) {
+    pdl_trigger(); pdl_wait();
     const int64_t total = (int64_t)N * h * w * 32;               // (pixel, tap, half)
     const int H2 = 2 * h, W2 = 2 * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -141,22 +143,6 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const bf16 *__restrict__ 
         if ((unsigned)iy < (unsigned)H2 && (unsigned)ix < (unsigned)W2)
             v = __ldg(reinterpret_cast<const uint4 *>(L + (((int64_t)n * H2 + iy) * W2 + ix) * 16) + half);
         reinterpret_cast<uint4 *>(col)[i] = v;
-    }
-}
-
-// dense thin tensor [N,H,W,CP] -> the same with a physical one-pixel border [N,H+2,W+2,CP] (border zeroed once at allocation):
-// the operand layout of the implicit-im2col first layers (conv_tc.cu: map_thin_gather).  One thread per pixel.
-template <int CP>
-__global__ void __launch_bounds__(256) pad_copy_kernel(const bf16 *__restrict__ src, bf16 *__restrict__ dst, int N, int H, int W) {
-    const int64_t total = (int64_t)N * H * W;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % W), y = (int)((i / W) % H), n = (int)(i / ((int64_t)W * H));
-        const int64_t o = ((int64_t)n * (H + 2) + y + 1) * (W + 2) + x + 1;
-        if (CP == 4) reinterpret_cast<uint2 *>(dst)[o] = __ldg(reinterpret_cast<const uint2 *>(src) + i);
-        else {
-            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src) + 2 * i), b = __ldg(reinterpret_cast<const uint4 *>(src) + 2 * i + 1);
-            reinterpret_cast<uint4 *>(dst)[2 * o] = a; reinterpret_cast<uint4 *>(dst)[2 * o + 1] = b;
-        }
     }
 }
 
@@ -284,6 +270,7 @@ __global__ void bn_eval_coef_kernel(const float *__restrict__ gamma, const float
 // a = act(y * scale[c] + shift[c]); vectors of 8 channels
 __global__ void __launch_bounds__(256) bn_apply_act_kernel(const bf16 *__restrict__ y, bf16 *__restrict__ a, const float *__restrict__ scale,
         const float *__restrict__ shift, int64_t nvec, int vec_per_pix, int act, float negval) {
+    pdl_trigger(); pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         int c0 = (int)(i % vec_per_pix) * 8;
         float f[8];
@@ -306,6 +293,7 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_act_kernel(float *__res
         float *__restrict__ mean, float *__restrict__ invstd, float *__restrict__ scale_g, float *__restrict__ shift_g, int C, int Cp, double n,
         double momentum, double eps, const bf16 *__restrict__ y, bf16 *__restrict__ a, int64_t nvec, int vec_per_pix, int act, float negval,
         unsigned int *__restrict__ done_counter) {
+    pdl_trigger(); pdl_wait();
     extern __shared__ float sm_ss[];                   // [2][Cp]
     __shared__ int is_last;
     for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
@@ -426,6 +414,7 @@ template <int ACT, bool kAtomic = false>
 __global__ void __launch_bounds__(256, 4) bn_bwd_reduce2_kernel(const bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
         const float *__restrict__ shift, const float *__restrict__ mean, float *__restrict__ part, int Cp, int64_t npix, int vec_per_pix, int C,
         float negval) {
+    pdl_trigger(); pdl_wait();
     const int vec = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = vec < vec_per_pix;
     float acc[2][8] = {};
@@ -494,6 +483,7 @@ template <int ACT>
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply2_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
         const float *__restrict__ shift, const float *__restrict__ coef, float *__restrict__ gb_part, int Cp,
         int64_t npix, int vec_per_pix, int C, float negval) {
+    pdl_trigger(); pdl_wait();
     const int vec = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = vec < vec_per_pix;
     float acc[1][8] = {};
@@ -537,6 +527,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_coef_apply_kernel(bf16 *__restr
         const float *__restrict__ shift, float *__restrict__ sums, const float *__restrict__ gamma, const float *__restrict__ invstd,
         const float *__restrict__ mean, float *__restrict__ ggamma, float *__restrict__ gbeta, float *__restrict__ gb_part, int Cp,
         int64_t npix, int vec_per_pix, int C, float negval, double n, unsigned int *__restrict__ done_counter) {
+    pdl_trigger(); pdl_wait();
     __shared__ int is_last;
     const int vec = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = vec < vec_per_pix;
@@ -718,6 +709,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_fused_kernel(bf16 *__restrict__
 template <int ACT>
 __global__ void __launch_bounds__(256, 4) act_bwd2_kernel(bf16 *__restrict__ g, const bf16 *__restrict__ a, float *__restrict__ gb_part, int Cp, int64_t npix,
         int vec_per_pix, int C, float negval) {
+    pdl_trigger(); pdl_wait();
     const int vec = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = vec < vec_per_pix;
     float acc[1][8] = {};
@@ -755,6 +747,7 @@ __global__ void __launch_bounds__(256, 4) act_bwd2_kernel(bf16 *__restrict__ g, 
 // dst[c] += sum_r src[r][c] for a list of jobs (one CTA per job): folds the per-CTA partial rows of a whole backward sweep
 struct FoldJob { const float *src; float *dst; int rows, C, stride, fold, fold_stride; };   // fold > 1: column c also sums columns c + k*fold_stride (k < fold)
 __global__ void __launch_bounds__(256) fold_rows_kernel(const FoldJob *__restrict__ jobs) {
+    pdl_trigger(); pdl_wait();
     __shared__ float sh[8][33];
     const FoldJob j = jobs[blockIdx.x];
     const int tx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -783,6 +776,7 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(const FoldJob *__restric
 // out[b] = sigmoid(sum_k x[b,k] w[k] + bias): one warp per sample, 16-byte loads
 __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16 *__restrict__ x, const bf16 *__restrict__ w, const float *__restrict__ bias,
         float *__restrict__ out, int B, int K) {
+    pdl_trigger(); pdl_wait();
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     const uint4 *xr = reinterpret_cast<const uint4 *>(x + (int64_t)warp * K), *wr = reinterpret_cast<const uint4 *>(w);
@@ -799,6 +793,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16 *__restrict__ 
 // BCE against a constant label: loss_acc += -sum(...)/n ; gpre[b] = dL/dx * x(1-x)  (Sigmoid backward)
 __global__ void __launch_bounds__(256) head_bce_kernel(const float *__restrict__ sig, float label, float *__restrict__ gpre, double *__restrict__ loss_acc,
         int B, double inv_n) {
+    pdl_trigger(); pdl_wait();
     __shared__ double sh[32];
     double l = 0.0;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
@@ -812,6 +807,7 @@ __global__ void __launch_bounds__(256) head_bce_kernel(const float *__restrict__
 }
 // gx[b,k] = gpre[b] * w[k]
 __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict__ gpre, const bf16 *__restrict__ w, bf16 *__restrict__ gx, int B, int K) {
+    pdl_trigger(); pdl_wait();
     int64_t nvec = (int64_t)B * K / 8;
     int kv = K / 8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -826,6 +822,7 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
 // gw[k] += sum_b gpre[b] x[b,k] ; gb += sum_b gpre[b]   (grid.x over k-vectors, grid.y over batch slices; fp32 atomics)
 __global__ void __launch_bounds__(128) head_wgrad_kernel(const float *__restrict__ gpre, const bf16 *__restrict__ x, float *__restrict__ gw,
         float *__restrict__ gb, int B, int K) {
+    pdl_trigger(); pdl_wait();
     const int kv = blockIdx.x * blockDim.x + threadIdx.x;
     const int per = (B + gridDim.y - 1) / gridDim.y, b0 = blockIdx.y * per, b1 = min(B, b0 + per);
     if (kv < K / 8) {
@@ -882,6 +879,7 @@ __global__ void __launch_bounds__(256) blend_overlap_kernel(const bf16 *__restri
 __global__ void __launch_bounds__(256) blend_overlap4_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
         bf16 *__restrict__ g, int64_t npix, int H, int W, int C, int ov, float a, float w_in, float w_ring, float two_over_n,
         double inv_n, double *__restrict__ loss_acc) {
+    pdl_trigger(); pdl_wait();
     __shared__ double sh[32];
     float l = 0.f;
     const int64_t npair = npix / 2;
@@ -932,6 +930,7 @@ __global__ void __launch_bounds__(256) blend_masked_kernel(const bf16 *__restric
 __global__ void __launch_bounds__(256) blend_masked8_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
         const bf16 *__restrict__ mask, bf16 *__restrict__ g, int64_t nvec, int vec_per_pix, int C, float a, float wtl2, float lambda, float wtgdl,
         float two_over_n, double inv_n, double *__restrict__ loss_acc) {
+    pdl_trigger(); pdl_wait();
     __shared__ double sh[32];
     float l = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -955,6 +954,7 @@ __global__ void __launch_bounds__(256) blend_masked8_kernel(const bf16 *__restri
 }
 // dst = mask ? src : dst
 __global__ void __launch_bounds__(256) composite_kernel(bf16 *__restrict__ dst, const bf16 *__restrict__ mask, const bf16 *__restrict__ src, int64_t total) {
+    pdl_trigger(); pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         if (__bfloat162float(mask[i]) != 0.f) dst[i] = src[i];
 }
@@ -984,6 +984,7 @@ __global__ void __launch_bounds__(256) gdl_loss_kernel(const bf16 *__restrict__ 
 template <int CP>
 __global__ void __launch_bounds__(256) gdl_loss_vec_kernel(const bf16 *__restrict__ inp, const bf16 *__restrict__ tgt, int64_t N, int H, int W, int C,
         double inv_n, double *__restrict__ loss_acc) {
+    pdl_trigger(); pdl_wait();
     __shared__ double sh[32];
     const int NK = H * (W - 1);
     float l = 0.f;
@@ -1026,6 +1027,7 @@ __global__ void __launch_bounds__(256) gdl_loss_vec_kernel(const bf16 *__restric
 // optim.adam on the master vector + refresh of the bf16 operand copy in the same pass
 __global__ void __launch_bounds__(256) adam_bf16_kernel(float *__restrict__ x, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
         bf16 *__restrict__ xb, int64_t n, float b1, float b2, float eps, const float *__restrict__ step_ptr) {
+    pdl_trigger(); pdl_wait();
     const float step = *step_ptr;
     int64_t n4 = n / 4;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (int64_t)gridDim.x * blockDim.x) {
@@ -1074,6 +1076,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
 }
 // zero a list of (offset, length) segments of a float vector and of its bf16 copy (conv biases, train.lua:279-280)
 __global__ void zero_segments_kernel(float *__restrict__ x, bf16 *__restrict__ xb, const int64_t *__restrict__ seg, int nseg) {
+    pdl_trigger(); pdl_wait();
     int sidx = blockIdx.x;
     if (sidx >= nseg) return;
     int64_t off = seg[2 * sidx], len = seg[2 * sidx + 1];
@@ -1083,6 +1086,7 @@ __global__ void zero_segments_kernel(float *__restrict__ x, bf16 *__restrict__ x
 //   mode 0 (plain)  : dst[k][cs]                                   (K x Csp)
 //   mode 1 (phases) : dst[((ph*cl_rows + cl)*4 + ab)][cs] with k = tap*Clp + cl, tap = u*4+v, (ph,ab) from (u,v)
 __global__ void __launch_bounds__(256) wt_from_wf_kernel(const bf16 *__restrict__ Wf, bf16 *__restrict__ dst, int Cs, int K, int Csp, int Clp, int cl_rows, int mode) {
+    pdl_trigger(); pdl_wait();
     __shared__ bf16 tile[32][34];
     int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8

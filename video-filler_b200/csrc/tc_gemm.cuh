@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "common.cuh"
 
 namespace tc {
 
@@ -176,8 +177,6 @@ struct GatherGemmParams {
     int num_kb, chunks, bk_per_tap, num_taps;
     int A0[4][16], A1[4][16], A2[4][16], A3[4][16];
     int B1[4];
-    int a_order;             // 1: A box coordinates are issued as (A0 + 64c, A2, x0 + A1, y0 + A3, n0): implicit im2col of a thin (4-channel)
-                             //    tensor, whose 128-byte K row is (window row u) x (4 pixels x 4 channels) -- tc_plan_fprop_thin
     int b_mn;                // 1: B is read MN-major straight from the master layout Wf [K rows][N cols] (no transposed copy):
     int Bc[4][16];           //    box (64 n, 64 k) at column Bc[ph][tap] + n_tile*BN + 64*chunk, row 64*c
     int O0[4], O2[4];
@@ -218,7 +217,6 @@ struct WgradParams {
     int accumulate;          // 1: red.add (accumulate / split-K), 0: plain store (requires a single split)
     // gather geometry for L per tap: coords = (chunk*64 + gx0[tap], x0 + gdx[tap], g2[tap], y0 + gdy[tap], n0)
     int gx0[16], gdx[16], g2[16], gdy[16];
-    int a_order;             // 1: L box coordinates are issued as (c0, g2, x0 + gdx, y0 + gdy, n0) (thin implicit im2col, see GatherGemmParams)
 };
 
 static constexpr int GEMM_THREADS = 192;
@@ -310,13 +308,15 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();          // the next kernel of the stream may start its prologue
+    pdl_wait();             // everything above overlapped the previous kernel's tail; its results are needed from here on
 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             long long w_empty = 0, t_begin = prof ? clock64() : 0;
             const int chunks = p.chunks, num_taps = p.num_taps, bk_per_tap = p.bk_per_tap;
-            const bool b_mn = p.b_mn != 0, a_order = p.a_order != 0;
+            const bool b_mn = p.b_mn != 0;
             const int flags = kProbe ? p.dbg_flags : 0;
             const uint32_t tiles_u32 = smem_u32(tiles), full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -331,22 +331,20 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         mbar_wait_u32(empty_u32 + 8u * s, ph ^ 1u);
                         if (prof) w_empty += clock64() - t0;
                         const uint32_t a_dst = tiles_u32 + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES, fb = full_u32 + 8u * s;
-                        // implicit im2col of a 4-channel tensor: the box's second dimension is the window row (a_order)
-                        const int ac1 = a_order ? c4.z : ax, ac2 = a_order ? ax : c4.z;
                         if (kProbe && (flags & 6)) {   // probe: drop one or both operand streams
                             const uint32_t bytes = ((flags & 2) ? 0u : A_BYTES) + ((flags & 4) ? 0u : B_BYTES);
                             if (bytes) mbar_expect_tx_u32(fb, bytes); else mbar_arrive(&full_bar[s]);
-                            if (!(flags & 2)) tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ac1, ac2, ay, tc.n0);
+                            if (!(flags & 2)) tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ax, c4.z, ay, tc.n0);
                             if (!(flags & 4)) tma_load_2d_u32(&tmB, fb, b_dst, bk + c * 64, brow);
                         } else if (b_mn) {
                             mbar_expect_tx_u32(fb, STAGE_BYTES);
-                            tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ac1, ac2, ay, tc.n0);
+                            tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ax, c4.z, ay, tc.n0);
                             const int bcol = bcs[tc.phase * 16 + tap] + tc.nt * BN;
 #pragma unroll
                             for (int ch = 0; ch < (BN >= 64 ? BN / 64 : 1); ++ch) tma_load_2d_u32(&tmB, fb, b_dst + ch * 8192, bcol + ch * 64, c * 64);
                         } else {
                             mbar_expect_tx_u32(fb, STAGE_BYTES);
-                            tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ac1, ac2, ay, tc.n0);
+                            tma_load_5d_u32(&tmA, fb, a_dst, c4.x + c * 64, ax, c4.z, ay, tc.n0);
                             tma_load_2d_u32(&tmB, fb, b_dst, bk + c * 64, brow);
                         }
                         if (++s == stages) { s = 0; ph ^= 1u; }
@@ -690,6 +688,8 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();          // the next kernel of the stream may start its prologue
+    pdl_wait();             // everything above overlapped the previous kernel's tail; its results are needed from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -973,6 +973,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();          // the next kernel of the stream may start its prologue
+    pdl_wait();             // everything above overlapped the previous kernel's tail; its results are needed from here on
     if (nkb <= 0) { __syncthreads(); if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS); return; }
 
     if (warp == 0) {
@@ -995,10 +997,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
                 const uint32_t a_dst = tiles_u32 + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES, fb = full_u32 + 8u * s;
                 mbar_expect_tx_u32(fb, STAGE_BYTES);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (p.a_order) tma_load_5d_u32(&tmL, fb, a_dst + h * BOX_BYTES, ac0[h], a2[h], x0 + adx[h], y0 + ady[h], n0);
-                    else tma_load_5d_u32(&tmL, fb, a_dst + h * BOX_BYTES, ac0[h], x0 + adx[h], a2[h], y0 + ady[h], n0);
-                }
+                for (int h = 0; h < 2; ++h) tma_load_5d_u32(&tmL, fb, a_dst + h * BOX_BYTES, ac0[h], x0 + adx[h], a2[h], y0 + ady[h], n0);
 #pragma unroll
                 for (int c = 0; c < BN / 64; ++c) tma_load_5d_u32(&tmS, fb, b_dst + c * BOX_BYTES, (nt * (BN / 64) + c) * 64, x0, 0, y0, n0);
                 if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++tn; } }

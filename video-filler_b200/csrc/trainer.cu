@@ -74,7 +74,6 @@ struct Net {
     float *adam_step = nullptr;    // device: lr * sqrt(1-b2^t)/(1-b1^t)
     float lr = 0.f;
     Tensor input;             // fixed input buffer of the net
-    bf16 *inpad = nullptr;    // the same with a one-pixel zero border [N, H+2, W+2, Cp]: operand of the implicit-im2col first layer
 };
 
 struct Op {
@@ -226,11 +225,6 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
     const int N = t->B;
     // input tensor (thin: 3 or 12 channels)
     if (alloc_tensor(t, net.input, N, in_size, in_size, in_C, pad_thin(in_C))) return 1;
-    static const bool thin_im2col = getenv("CENN_THIN_IM2COL") != nullptr;      // 1: explicit col buffer for the first layer (round-1 path)
-    if (!thin_im2col && !specs.empty() && specs[0].type == CONV_S2 && net.input.Cp < 64) {
-        net.inpad = dalloc<bf16>(t, (int64_t)N * (in_size + 2) * (in_size + 2) * net.input.Cp);
-        if (!net.inpad) return 1;
-    }
     Tensor cur = net.input;
     int64_t off = 0, toff = 0;
     net.blocks.resize(specs.size());
@@ -316,7 +310,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             b.part = dalloc<float>(t, (int64_t)b.part_rows * 2 * std::max(b.Coutp, 8));
             if (!b.part) return 1;
         }
-        if (b.thin && !(t->infer && sp.type != CONV_S2) && !(sp.type == CONV_S2 && net.inpad)) {
+        if (b.thin && !(t->infer && sp.type != CONV_S2)) {
             b.col_rows = (int64_t)N * b.h * b.w; b.col_k = 16 * b.Clp;
             b.col = dalloc<bf16>(t, b.col_rows * b.col_k);
             if (!b.col) return 1;
@@ -366,8 +360,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             TcEpilogue ep_m = ep; ep_m.b_mn = true;
             switch (b.type) {
                 case CONV_S2:
-                    if (b.thin && net.inpad) { if (tc_plan_fprop_thin(s, &b.p_fwd, net.inpad, Wf, b.a.p, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep)) return 1; }
-                    else if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, b.a.p, M, b.Cs, (int)b.col_k, b.Csp, ep)) return 1; }
+                    if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, b.a.p, M, b.Cs, (int)b.col_k, b.Csp, ep)) return 1; }
                     else if (tc_plan_fprop_s2(s, &b.p_fwd, b.in.p, Wf, b.a.p, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep)) return 1;
                     break;
                 case CONV_V4:
@@ -436,11 +429,9 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         TcEpilogue ep_n;
         switch (b.type) {
             case CONV_S2: {
-                if (b.thin && net.inpad) { if (tc_plan_fprop_thin(s, &b.p_fwd, net.inpad, Wf, fwd_out, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep_f)) return 1; }
-                else if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, fwd_out, M, b.Cs, (int)b.col_k, b.Csp, ep_f)) return 1; }
+                if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, fwd_out, M, b.Cs, (int)b.col_k, b.Csp, ep_f)) return 1; }
                 else if (tc_plan_fprop_s2(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, b.h, b.w, b.Cs, b.Csp, b.Clp, ep_f)) return 1;
-                if (b.thin && net.inpad) { if (tc_plan_wgrad_thin(s, &b.p_wgrad, b.g.p, net.inpad, gW, N, b.h, b.w, b.Cs, b.Csp, b.Clp, 1.f, 1)) return 1; }
-                else if (b.thin) { if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.col, gW, M, b.Cs, b.Csp, (int)b.col_k, 1.f, 1)) return 1; }
+                if (b.thin) { if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.col, gW, M, b.Cs, b.Csp, (int)b.col_k, 1.f, 1)) return 1; }
                 else if (tc_plan_wgrad_s2(s, &b.p_wgrad, b.g.p, b.in.p, gW, N, b.h, b.w, b.Cs, b.Csp, b.Clp, 1.f, 1)) return 1;
                 if (b.has_dgrad) {
                     REQUIRE(b.Csp % 64 == 0, "block %zu: dgrad needs small-side channels padded to 64 (got %d)", i, b.Csp);
@@ -516,23 +507,11 @@ void emit_im2col(T *t, const Tensor &L, bf16 *col, int h, int w) {
     Tensor Lc = L;
     emit(t, "im2col", [s, Lc, col, h, w]() {
         int64_t total = (int64_t)Lc.N * h * w * 4;            // one thread per (pixel, window row)
-        if (Lc.Cp == 4) nhwc::im2col_kernel<4><<<grid1d(s, total), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
-        else if (Lc.Cp == 16) nhwc::im2col16_kernel<<<grid1d(s, total * 8), 256, 0, s->stream>>>(Lc.p, col, Lc.N, h, w);
+        if (Lc.Cp == 4) LK(nhwc::im2col_kernel<4>, dim3(grid1d(s, total)), dim3(256), 0, s->stream)(Lc.p, col, Lc.N, h, w);
+        else if (Lc.Cp == 16) LK(nhwc::im2col16_kernel, dim3(grid1d(s, total * 8)), dim3(256), 0, s->stream)(Lc.p, col, Lc.N, h, w);
         else { cenn_set_error("im2col: unsupported thin channel count %d", Lc.Cp); return 1; }
         KLAUNCH(s); return 0;
     });
-}
-// first layer of a net: its thin input -> the bordered copy the implicit-im2col plans read (1.03x the input instead of a 16x col buffer)
-void emit_pad_input(T *t, Net &net) {
-    cenn_state *s = t->s;
-    Net *n = &net;
-    emit(t, "pad_input", [s, n]() {
-        const Tensor &x = n->input;
-        if (x.Cp == 4) nhwc::pad_copy_kernel<4><<<grid1d(s, x.pix()), 256, 0, s->stream>>>(x.p, n->inpad, x.N, x.H, x.W);
-        else if (x.Cp == 16) nhwc::pad_copy_kernel<16><<<grid1d(s, x.pix()), 256, 0, s->stream>>>(x.p, n->inpad, x.N, x.H, x.W);
-        else { cenn_set_error("pad_input: unsupported thin channel count %d", x.Cp); return 1; }
-        KLAUNCH(s); return 0; });
-    t->prog.back().bytes = 2.0 * 2.0 * (double)net.input.pix() * net.input.Cp;
 }
 void reduce_dims(int vec_per_pix, dim3 &block, int &gy) {
     int tx = 1; while (tx < vec_per_pix && tx < 64) tx *= 2;
@@ -551,10 +530,10 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
         int B = t->B, K = 16 * b->Clp;
         Tensor in = b->in;
         emit(t, "head_fwd", [s, in, w, bias, b, B, K]() {
-            nhwc::head_fwd_kernel<<<(B * 32 + 255) / 256, 256, 0, s->stream>>>(in.p, w, bias, b->sig, B, K); KLAUNCH(s); return 0; });
+            LK(nhwc::head_fwd_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, s->stream)(in.p, w, bias, b->sig, B, K); KLAUNCH(s); return 0; });
         return;
     }
-    if (b->thin && b->type == CONV_S2) { if (net.inpad) emit_pad_input(t, net); else emit_im2col(t, b->in, b->col, b->h, b->w); }
+    if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
     if (b->bias_exp) {
         const float *bias = master + b->b_off;
         emit(t, "expand_bias", [s, b, bias]() { expand_bias_kernel<<<(16 * b->Clp + 255) / 256, 256, 0, s->stream>>>(bias, b->bias_exp, b->Cout, b->Clp); KLAUNCH(s); return 0; });
@@ -564,7 +543,7 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
         float *gamma = master + b->g_off, *beta = master + b->be_off;
         emit(t, "bn_fin_apply", [s, b, gamma, beta, n_global]() {
             int64_t nvec = b->y.elems() / 8;
-            nhwc::bn_finalize_apply_act_kernel<<<grid1d(s, nvec), 256, 2 * b->Coutp * sizeof(float), s->stream>>>(b->stats, b->stats_cols, b->fold, b->Coutp, gamma, beta,
+            LK(nhwc::bn_finalize_apply_act_kernel, dim3(grid1d(s, nvec)), dim3(256), 2 * b->Coutp * sizeof(float), s->stream)(b->stats, b->stats_cols, b->fold, b->Coutp, gamma, beta,
                 b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, b->Coutp, n_global, 0.1, 1e-5,
                 b->y.p, b->a.p, nvec, b->Coutp / 8, b->act, 0.2f, b->done_ctr);
             KLAUNCH(s); return 0; });
@@ -597,7 +576,7 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
         }
         emit(t, "bn_apply_act", [s, b]() {
             int64_t nvec = b->y.elems() / 8;
-            nhwc::bn_apply_act_kernel<<<grid1d(s, nvec), 256, 0, s->stream>>>(b->y.p, b->a.p, b->scale, b->shift, nvec, b->Coutp / 8, b->act, 0.2f);
+            LK(nhwc::bn_apply_act_kernel, dim3(grid1d(s, nvec)), dim3(256), 0, s->stream)(b->y.p, b->a.p, b->scale, b->shift, nvec, b->Coutp / 8, b->act, 0.2f);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 2.0 * 2.0 * (double)b->a.pix() * b->Cout;
     }
@@ -615,9 +594,9 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         Tensor in = b->in;
         bf16 *gx = net.blocks[i - 1].g.p;
         if (want_params) emit(t, "head_wgrad", [s, b, in, grad, B, K]() {
-            nhwc::head_wgrad_kernel<<<dim3((K / 8 + 127) / 128, 16), 128, 0, s->stream>>>(b->gpre, in.p, grad + b->w_off, grad + b->b_off, B, K); KLAUNCH(s); return 0; });
+            LK(nhwc::head_wgrad_kernel, dim3(dim3((K / 8 + 127) / 128, 16)), dim3(128), 0, s->stream)(b->gpre, in.p, grad + b->w_off, grad + b->b_off, B, K); KLAUNCH(s); return 0; });
         emit(t, "head_dgrad", [s, b, w, gx, B, K]() {
-            nhwc::head_dgrad_kernel<<<grid1d(s, (int64_t)B * K / 8), 256, 0, s->stream>>>(b->gpre, w, gx, B, K); KLAUNCH(s); return 0; });
+            LK(nhwc::head_dgrad_kernel, dim3(grid1d(s, (int64_t)B * K / 8)), dim3(256), 0, s->stream)(b->gpre, w, gx, B, K); KLAUNCH(s); return 0; });
         return;
     }
     const int vpp = b->Coutp >= 8 ? b->Coutp / 8 : 1;
@@ -645,17 +624,21 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
                 s->launches++; return 0; });
             t->prog.back().bytes = 5.0 * 2.0 * (double)npix * b->Cout;      // read g, y; (re-read from L2); write g_y: 5 s bytes per element
         } else {
-        const bool two_launch = !dp && getenv("CENN_BN_BWD_3LAUNCH") == nullptr;   // single GPU: sums by fp32 atomics, coefficients in the apply prologue
+        // CENN_BN_BWD_2LAUNCH=1 (off by default): sums by fp32 atomics + coefficients in the apply prologue.  Measured on B200 (round 2):
+        // the prologue's dependent loads and the done-counter cost what the coefficient launch cost (apply 29.6 us vs 17.4 + 11 us per layer)
+        // and the step got 4 % SLOWER (3.29 vs 3.15 ms), so the three-launch chain stays the default.
+        static const bool two_launch_env = getenv("CENN_BN_BWD_2LAUNCH") != nullptr && atoi(getenv("CENN_BN_BWD_2LAUNCH")) != 0;
+        const bool two_launch = !dp && two_launch_env;
         emit(t, "bn_bwd_reduce", [s, b, npix, vpp, two_launch]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
             if (two_launch) {
                 auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_LEAKY, true> : nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_RELU, true>;
-                kern<<<dim3(b->red_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->mean,
+                LK(kern, dim3(dim3(b->red_rows, gy)), dim3(blk), 2 * blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->y.p, b->scale, b->shift, b->mean,
                     b->bsums, b->Coutp, npix, vpp, b->Cout, 0.2f);
                 KLAUNCH(s); return 0;
             }
             auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_RELU>;
-            kern<<<dim3(b->part_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->mean,
+            LK(kern, dim3(dim3(b->part_rows, gy)), dim3(blk), 2 * blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->y.p, b->scale, b->shift, b->mean,
                 b->part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 2.0 * 2.0 * (double)npix * b->Cout;            // read g, y
@@ -663,7 +646,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             emit(t, "bn_bwd_apply", [s, b, gamma, gg, gbeta, gb_part, npix, vpp, n_global]() {
                 dim3 blk; int gy; reduce_dims(vpp, blk, gy);
                 auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_coef_apply_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_coef_apply_kernel<nhwc::ACT_RELU>;
-                kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->bsums, gamma, b->invstd, b->mean,
+                LK(kern, dim3(dim3(b->part_rows, gy)), dim3(blk), blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->y.p, b->scale, b->shift, b->bsums, gamma, b->invstd, b->mean,
                     gg, gbeta, gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f, n_global, b->done_ctr);
                 KLAUNCH(s); return 0; });
             t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;        // read g, y; write g_y
@@ -693,7 +676,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
             // coef is laid out with stride Cout
             auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_apply2_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_apply2_kernel<nhwc::ACT_RELU>;
-            kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->y.p, b->scale, b->shift, b->coef,
+            LK(kern, dim3(dim3(b->part_rows, gy)), dim3(blk), blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->y.p, b->scale, b->shift, b->coef,
                 gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;            // read g, y; write g_y
@@ -703,7 +686,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         emit(t, "act_bwd", [s, b, gb_part, npix, vpp]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
             auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::act_bwd2_kernel<nhwc::ACT_LEAKY> : (b->act == nhwc::ACT_RELU ? nhwc::act_bwd2_kernel<nhwc::ACT_RELU> : nhwc::act_bwd2_kernel<nhwc::ACT_TANH>);
-            kern<<<dim3(b->part_rows, gy), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
+            LK(kern, dim3(dim3(b->part_rows, gy)), dim3(blk), blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->a.p, gb_part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;            // read g, a; write g_y
     } else {
@@ -712,7 +695,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         emit(t, "act_bwd4", [s, b, gb_part, npix]() {
             dim3 blk(1, 256);
             auto kern = b->act == nhwc::ACT_TANH ? nhwc::act_bwd2_kernel<nhwc::ACT_TANH> : (b->act == nhwc::ACT_LEAKY ? nhwc::act_bwd2_kernel<nhwc::ACT_LEAKY> : nhwc::act_bwd2_kernel<nhwc::ACT_RELU>);
-            kern<<<dim3(b->part_rows, 1), blk, blk.x * 8 * sizeof(float), s->stream>>>(b->g.p, b->a.p, gb_part, 8, npix / 2, 1, 8, 0.2f);
+            LK(kern, dim3(dim3(b->part_rows, 1)), dim3(blk), blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->a.p, gb_part, 8, npix / 2, 1, 8, 0.2f);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;
     }
@@ -802,7 +785,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             if (dp_bulk && n->gradbf && cnt % 4 == 0)
                 nhwc::adam_bf16g_kernel<<<grid1d(s, cnt / 4), 256, 0, st>>>(n->master + off, n->gradbf + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
             else
-            nhwc::adam_bf16_kernel<<<grid1d(s, cnt / 4), 256, 0, st>>>(n->master + off, n->grad + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
+            LK(nhwc::adam_bf16_kernel, dim3(grid1d(s, cnt / 4)), dim3(256), 0, st)(n->master + off, n->grad + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 30.0 * (double)cnt;
     }
@@ -823,7 +806,7 @@ void emit_weight_prep(T *t, Net &net) {
         int mode = (b->type == CONV_S2 || b->type == FULL_S2) ? 1 : 0;
         emit(t, "wt_from_wf", [s, b, Wf, K, mode]() {
             dim3 grid((K + 31) / 32, (b->Csp + 31) / 32);
-            nhwc::wt_from_wf_kernel<<<grid, 256, 0, s->stream>>>(Wf, b->Wt, b->Cs, K, b->Csp, b->Clp, b->cl_rows, mode);
+            LK(nhwc::wt_from_wf_kernel, dim3(grid), dim3(256), 0, s->stream)(Wf, b->Wt, b->Cs, K, b->Csp, b->Clp, b->cl_rows, mode);
             KLAUNCH(s); return 0; });
     }
 }
@@ -831,7 +814,7 @@ void emit_zero_bias(T *t, Net &net) {
     cenn_state *s = t->s;
     Net *n = &net;
     emit(t, "zero_conv_bias", [s, n]() {
-        nhwc::zero_segments_kernel<<<n->nbias_seg, 128, 0, s->stream>>>(n->master, n->wbf, n->bias_seg, n->nbias_seg); KLAUNCH(s); return 0; });
+        LK(nhwc::zero_segments_kernel, dim3(n->nbias_seg), dim3(128), 0, s->stream)(n->master, n->wbf, n->bias_seg, n->nbias_seg); KLAUNCH(s); return 0; });
 }
 void emit_fold_gbias(T *t, Net &net) {
     cenn_state *s = t->s;
@@ -844,7 +827,7 @@ void emit_fold_gbias(T *t, Net &net) {
             return cenn_check_cuda(cudaStreamWaitEvent(s->stream, evj, 0), "stream wait", __FILE__, __LINE__); });
     }
     emit(t, "fold_gbias", [s, n]() {
-        nhwc::fold_rows_kernel<<<dim3((unsigned)n->fold_host.size(), 8), 256, 0, s->stream>>>(n->fold_jobs); KLAUNCH(s); return 0; });
+        LK(nhwc::fold_rows_kernel, dim3(dim3((unsigned)n->fold_host.size(), 8)), dim3(256), 0, s->stream)(n->fold_jobs); KLAUNCH(s); return 0; });
 }
 void emit_zero_grad(T *t, Net &net) {
     cenn_state *s = t->s;
@@ -878,7 +861,7 @@ void emit_adam(T *t, Net &net, std::vector<std::pair<int64_t, int64_t>> done = {
     if (net.nparam > cur) rest.push_back({cur, net.nparam - cur});
     emit(t, "adam", [s, n, beta1, rest]() {
         for (auto &x : rest) {
-            nhwc::adam_bf16_kernel<<<grid1d(s, x.second / 4), 256, 0, s->stream>>>(n->master + x.first, n->grad + x.first, n->m + x.first, n->v + x.first, n->wbf + x.first,
+            LK(nhwc::adam_bf16_kernel, dim3(grid1d(s, x.second / 4)), dim3(256), 0, s->stream)(n->master + x.first, n->grad + x.first, n->m + x.first, n->v + x.first, n->wbf + x.first,
                 x.second, beta1, 0.999f, 1e-8f, n->adam_step);
             KLAUNCH(s);
         }
@@ -891,7 +874,7 @@ void emit_bce(T *t, Block *head, float label, int loss_slot, bool want_grad) {
     int B = t->B;
     double *acc = t->loss_acc + loss_slot;
     emit(t, "bce", [s, head, label, acc, B, inv_n, want_grad]() {
-        nhwc::head_bce_kernel<<<(B + 255) / 256, 256, 0, s->stream>>>(head->sig, label, want_grad ? head->gpre : nullptr, acc, B, inv_n); KLAUNCH(s); return 0; });
+        LK(nhwc::head_bce_kernel, dim3((B + 255) / 256), dim3(256), 0, s->stream)(head->sig, label, want_grad ? head->gpre : nullptr, acc, B, inv_n); KLAUNCH(s); return 0; });
 }
 void emit_copy(T *t, const char *name, bf16 *dst, const bf16 *src, int64_t elems) {
     cenn_state *s = t->s;
@@ -984,7 +967,7 @@ int build_program(T *t) {
     if (video && c.weight_nomask == 0.f) {
         emit_copy(t, "d_in<-real", D.input.p, t->real_aux.p, D.input.elems());
         bf16 *dst = D.input.p; const bf16 *m = t->mask.p, *src = lastG->a.p; int64_t total = D.input.elems();
-        emit(t, "composite", [s, dst, m, src, total]() { nhwc::composite_kernel<<<grid1d(s, total), 256, 0, s->stream>>>(dst, m, src, total); KLAUNCH(s); return 0; });
+        emit(t, "composite", [s, dst, m, src, total]() { LK(nhwc::composite_kernel, dim3(grid1d(s, total)), dim3(256), 0, s->stream)(dst, m, src, total); KLAUNCH(s); return 0; });
     } else {
         emit_copy(t, "d_in<-fake", D.input.p, lastG->a.p, D.input.elems());
     }
@@ -1031,7 +1014,7 @@ int build_program(T *t) {
             if (c.wtl2 != 0.f) {
                 emit(t, "blend_overlap", [s, df, fake_in, real, gout, ov, a, w_in, w_ring, n, acc]() {
                     if (fake_in.Cp == 4 && fake_in.pix() % 2 == 0)
-                        nhwc::blend_overlap4_kernel<<<grid1d(s, fake_in.pix() / 2, 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
+                        LK(nhwc::blend_overlap4_kernel, dim3(grid1d(s, fake_in.pix() / 2, 256, 4)), dim3(256), 0, s->stream)(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
                             fake_in.W, fake_in.C, ov, a, w_in, w_ring, (float)(2.0 / n), 1.0 / n, acc);
                     else
                     nhwc::blend_overlap_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
@@ -1046,15 +1029,15 @@ int build_program(T *t) {
                 double ngdl = (double)t->Bglobal * fake_in.C * fake_in.H * (fake_in.W - 1);
                 emit(t, "gdl_loss", [s, fake_in, real, gacc, ngdl]() {
                     const int64_t pairs = (int64_t)fake_in.N * fake_in.H * (fake_in.W - 1);
-                    if (fake_in.Cp == 16) nhwc::gdl_loss_vec_kernel<16><<<grid1d(s, pairs, 256, 4), 256, 0, s->stream>>>(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.C, 1.0 / ngdl, gacc);
-                    else if (fake_in.Cp == 4) nhwc::gdl_loss_vec_kernel<4><<<grid1d(s, pairs, 256, 4), 256, 0, s->stream>>>(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.C, 1.0 / ngdl, gacc);
+                    if (fake_in.Cp == 16) LK(nhwc::gdl_loss_vec_kernel<16>, dim3(grid1d(s, pairs, 256, 4)), dim3(256), 0, s->stream)(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.C, 1.0 / ngdl, gacc);
+                    else if (fake_in.Cp == 4) LK(nhwc::gdl_loss_vec_kernel<4>, dim3(grid1d(s, pairs, 256, 4)), dim3(256), 0, s->stream)(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.C, 1.0 / ngdl, gacc);
                     else
                     nhwc::gdl_loss_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.Cp, fake_in.C, 1.0 / ngdl, gacc);
                     KLAUNCH(s); return 0; });
             }
             emit(t, "blend_masked", [s, df, fake_in, real, mk, gout, a, wtl2, lam, wtgdl, n, acc]() {
                 if (fake_in.Cp % 8 == 0)
-                    nhwc::blend_masked8_kernel<<<grid1d(s, fake_in.elems() / 8, 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems() / 8, fake_in.Cp / 8, fake_in.C,
+                    LK(nhwc::blend_masked8_kernel, dim3(grid1d(s, fake_in.elems() / 8, 256, 4)), dim3(256), 0, s->stream)(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems() / 8, fake_in.Cp / 8, fake_in.C,
                         a, wtl2, lam, wtgdl, (float)(2.0 / n), 1.0 / n, acc);
                 else
                 nhwc::blend_masked_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems(), fake_in.Cp, fake_in.C,
@@ -1110,6 +1093,7 @@ int reduce_sync_point(T *t, const Op &op) {
 }
 int run_ops(T *t, size_t from, size_t to) {
     cenn_state *s = t->s;
+    static const bool sync_each = getenv("CENN_SYNC_EACH_OP") != nullptr;      // debugging: attribute an asynchronous fault to its op
     for (size_t i = from; i < to; ++i) {
         const Op &op = t->prog[i];
         cudaStream_t keep = s->stream;
@@ -1117,6 +1101,10 @@ int run_ops(T *t, size_t from, size_t to) {
         int rc = op.fn() || reduce_sync_point(t, op);
         s->stream = keep;
         if (rc) return 1;
+        if (sync_each) {
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { cenn_set_error("op %zu (%s) failed: %s", i, op.name, cudaGetErrorString(e)); return 1; }
+        }
     }
     return 0;
 }
@@ -1741,7 +1729,7 @@ int inpainter_build_program(cenn_inpainter *p) {
         KLAUNCH(s); return 0; });
     for (size_t i = 0; i < G.blocks.size(); ++i) {
         Block *b = &G.blocks[i];
-        if (b->thin && b->type == CONV_S2) { if (G.inpad) emit_pad_input(t, G); else emit_im2col(t, b->in, b->col, b->h, b->w); }
+        if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
         emit_plan(t, "conv_fwd", &b->p_fwd);
     }
     emit(t, "tiles->nchw", [t, s]() {

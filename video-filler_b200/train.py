@@ -155,13 +155,16 @@ class ClosureTrainer:
         if o["wtgdl"] != 0:
             # loss from GDL (:524); its gradient in the script is criterionMSE:backward (:525), folded into the blend
             self.errG_gdl = self.criterionGDL.forward(self.input_inpainted, self.input_real)
-        if wtl2 != 0:
+        if wtl2 != 0 or o["wtgdl"] != 0:
+            # the GDL branch adds wtgdl * criterionMSE:backward to df_dg UNCONDITIONALLY (train_vid_weighted.lua:523-528), also when wtl2 == 0:
+            # the fused kernel handles wtl2 = 0 (no L2 term, adversarial weight 1)
             loss = C.c_float()
             api().cenn_WeightedMSEBlend_masked(state(), C.c_void_p(df_dg.ptr), C.c_void_p(self.input_inpainted.ptr),
                                                C.c_void_p(self.input_real.ptr), C.c_void_p(self.input_mask.ptr),
                                                df_dg.nelement(), wtl2, o["weight_nomask"], o["wtgdl"], C.byref(loss))
-            self.errG_l2 = loss.value
-            total = (1 - wtl2) * self.errG + wtl2 * self.errG_l2 if 0 < wtl2 < 1 else self.errG + wtl2 * self.errG_l2
+            if wtl2 != 0:
+                self.errG_l2 = loss.value
+                total = (1 - wtl2) * self.errG + wtl2 * self.errG_l2 if 0 < wtl2 < 1 else self.errG + wtl2 * self.errG_l2
         if o["wtgdl"] != 0:
             total = total + o["wtgdl"] * self.errG_gdl
         self.df_dg = df_dg
