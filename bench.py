@@ -29,6 +29,10 @@ STEP_GFLOP_PER_SAMPLE = 3.552          # 3 F_G + 7 F_D pe
 WORKLOAD_VIDEO = "train_vid_weighted 128x128 clips, predLen 4 (12 stacked channels), mask-weighted L2 + GDL (wtgdl %s), batch %d/GPU"
 VIDEO_GFLOP_PER_SAMPLE = 5.242         # cfg3, 3 F_G + 7 F_D per sample
 INFER_GFLOP_PER_TILE = 0.853           # cfg5 generator forward per 128x128 tile
+# BASELINE.json configs[3]: train_deepernet at 256 x 256, global batch 256 split over the ranks (strong scaling)
+WORKLOAD_DEEPER = ("train_deepernet 256x256 clips, predLen 4 (12 stacked channels), mask-weighted L2 (wtgdl %s), nBottleneck 4000 (5x5 bottleneck map), "
+                   "patch discriminator head (25 outputs per sample, each labelled with its sample's label), global batch 256 = %d/GPU")
+DEEPER_GFLOP_PER_SAMPLE = 29.228       # cfg4, 7482.3 GFLOP per 256-sample step
 
 
 def opt_for(batch, variant="image"):
@@ -127,7 +131,7 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_port_step_rate(batch, steps, warmup, threads, variant="image", wtgdl=0.0):
+def cpu_port_step_rate(batch, steps, warmup, threads, variant="image", wtgdl=0.0, fine=128):
     """The reference's gpu=0 path restated on the host cores: the oracle's fDx / fGx / optim.adam step sequence (oracle/step.py,
     train.lua:278-410) with its heavy ops on the PyTorch-CPU engine (oracle/torch_engine.py: oneDNN / MKL -- BASELINE.md section 4).
     Returns (samples/s over `steps` steps, seconds per step, threads in use)."""
@@ -138,6 +142,7 @@ def cpu_port_step_rate(batch, steps, warmup, threads, variant="image", wtgdl=0.0
     kw = dict(batchSize=batch)
     if variant == "video":
         kw["wtgdl"] = wtgdl
+        kw["fineSize"] = fine
     orc = ostep.StepOracle(onets.default_opt(variant, **kw), seed=1234, dtype=np.float32)
     rng = np.random.default_rng(1234)
     batches = [orc.synth_batch(rng) for _ in range(min(2, steps + warmup))]
@@ -160,19 +165,25 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    video = getattr(args, "workload", "image") == "video"
-    full = getattr(args, "batch", None) or (64 if video else 256)
+    wl = getattr(args, "workload", "image")
+    deeper = wl == "deeper"
+    video = wl == "video" or deeper
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    full = getattr(args, "batch", None) or ((256 // world) if deeper else (64 if video else 256))
     threads = host_threads()
     variant = "video" if video else "image"
     wtgdl = getattr(args, "wtgdl", 0.5) if video else 0.0
+    if deeper and wtgdl == 0.5:
+        wtgdl = 0.0
+    fine = 256 if deeper else 128
     nsteps = max(1, args.steps + args.warmup)
-    probe_b = min(16, full)
-    probe_rate, _, _ = cpu_port_step_rate(probe_b, 1, 1, threads, variant, wtgdl)    # per-step fixed costs (Adam over 74 M params) make this pessimistic
+    probe_b = min(8 if deeper else 16, full)
+    probe_rate, _, _ = cpu_port_step_rate(probe_b, 1, 1, threads, variant, wtgdl, fine)    # per-step fixed costs (Adam over 74 M params) make this pessimistic
     batch = full
     if full * nsteps / probe_rate > REF_BUDGET_S:
         batch = int(max(2, min(full, REF_BUDGET_S * probe_rate // nsteps)))
-    rate, sec, n_thr = cpu_port_step_rate(batch, args.steps, args.warmup, threads, variant, wtgdl)
-    workload = (WORKLOAD_VIDEO % (wtgdl, full)) if video else WORKLOAD.replace("batch 256", "batch %d" % full)
+    rate, sec, n_thr = cpu_port_step_rate(batch, args.steps, args.warmup, threads, variant, wtgdl, fine)
+    workload = (WORKLOAD_DEEPER % (wtgdl, full)) if deeper else ((WORKLOAD_VIDEO % (wtgdl, full)) if video else WORKLOAD.replace("batch 256", "batch %d" % full))
     sample = ("each step = the full %d-sample batch" % full) if batch == full else ("each step = %d samples of the %d-sample batch (bounded sample)" % (batch, full))
     line = {
         "impl": "reference", "metric": "train samples/sec (G+D step)", "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
@@ -306,7 +317,7 @@ def wrap_device(ptr, count, dtype, torch):
 
 
 
-def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, steps, warmup, want_profile=True):
+def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, steps, warmup, want_profile=True, fine=128):
     """Time `steps` G+D steps of one workload on this rank.  Returns a dict of raw measurements (device-timed region, end-to-end
     region through the pipelined host API, per-op profile, launch count, clocks); the executor is closed before returning."""
     from video_filler_b200 import synth, train, util
@@ -314,6 +325,7 @@ def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, v
     opt = opt_for(B, "video" if video else "image")
     if video:
         opt["wtgdl"] = args.wtgdl
+    opt["fineSize"] = fine
     trn = train.FusedTrainer(opt, precision="bf16", world_size=world, rank=rank)
     # identical random-init weights on every rank (parameter broadcast = same seed), train.lua:58-67
     rng = np.random.default_rng(1234)
@@ -331,7 +343,7 @@ def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, v
 
     for _ in range(n_batches):
         if video:
-            ctx, center, mask = synth.video_batch(B, 12, 128, opt["maskValue"], drng)
+            ctx, center, mask = synth.video_batch(B, 12, fine, opt["maskValue"], drng)
         else:
             ctx, center = synth.image_batch(B, 128, 4, drng)
             mask = None
@@ -510,8 +522,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default 256 image / 64 video)")
-    ap.add_argument("--workload", default="image", choices=["image", "video", "infer"],
-                    help="image = BASELINE.json configs[1] (the headline); video = configs[2] per GPU; infer = configs[4] sweep")
+    ap.add_argument("--workload", default="image", choices=["image", "video", "deeper", "infer"],
+                    help="image = BASELINE.json configs[1] (the headline); video = configs[2] per GPU; deeper = configs[3] (256x256, global batch 256); infer = configs[4] sweep")
     ap.add_argument("--wtgdl", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video-block", action="store_true", help="skip the `video` sub-block (cfg3 at the same N) of the image line")
@@ -520,9 +532,13 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    video = args.workload == "video"
+    deeper = args.workload == "deeper"
+    video = args.workload == "video" or deeper
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.batch is None and args.workload != "infer":
-        args.batch = 64 if video else 256
+        args.batch = (256 // world_env) if deeper else (64 if video else 256)
+    if deeper and args.wtgdl == 0.5:
+        args.wtgdl = 0.0                 # train_deepernet.lua:27 default
 
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -557,7 +573,7 @@ def main():
         idbuf = idt.cpu().numpy()
         api.cenn_dist_init(st, idbuf.ctypes.data_as(C.c_void_p), world, rank)
 
-    m = measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, args.steps, args.warmup)
+    m = measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, args.steps, args.warmup, fine=256 if deeper else 128)
     vid = None
     if not video and not args.no_video_block:
         # the config the >= 7x scaling target is quoted on (BASELINE.json configs[2]): 64 clips of 12 stacked channels per GPU, at the same N
@@ -575,14 +591,14 @@ def main():
         teardown()
         return
     hbm, tf_burst, tf_sus, peak_src = peaks()
-    gflop_per_sample = VIDEO_GFLOP_PER_SAMPLE if video else STEP_GFLOP_PER_SAMPLE
+    gflop_per_sample = DEEPER_GFLOP_PER_SAMPLE if deeper else (VIDEO_GFLOP_PER_SAMPLE if video else STEP_GFLOP_PER_SAMPLE)
     ms, e2e_ms, prof, losses = m["ms"], m["e2e_ms"], m["prof"], m["losses"]
     value = B * world * args.steps / (ms / 1e3)
     line = {
         "metric": "train samples/sec (G+D step)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(4, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(4, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if deeper else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": (WORKLOAD_VIDEO % (args.wtgdl, B)) if video else WORKLOAD.replace("batch 256", "batch %d" % B), "global_batch": B * world, "parallelism": "dp%d" % world,
+        "config": {"workload": (WORKLOAD_DEEPER % (args.wtgdl, B)) if deeper else ((WORKLOAD_VIDEO % (args.wtgdl, B)) if video else WORKLOAD.replace("batch 256", "batch %d" % B)), "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (>3 GB of activations, weights and optimizer state) exceeds the 126 MB L2; no explicit flush",
                    "timed_region_s": round(ms / 1e3, 4),
                    "losses_last_step": {k: round(v, 5) for k, v in losses.items()} if losses else None},

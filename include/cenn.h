@@ -263,6 +263,13 @@ CENN_API int cenn_trainer_step_clips_host(cenn_trainer *t, const float *frames01
         const uint8_t *flip_host, float maskValue, float *losses_host);
 CENN_API int cenn_trainer_step_clips_host_async(cenn_trainer *t, const float *frames01_host, const uint8_t *mask1_host,
         const uint8_t *flip_host, float maskValue);
+/* Frame mode (remainder): the per-sample hook of the video loader (datavid/donkey_folder.lua:114-129,138-187) on the
+ * device.  frames_u8 [B][nc*predLen][iH][iW] are the decoded frames (image.load = byte / 255), mask_full [iH][iW] the logo mask;
+ * the hook's RANDOM DRAWS stay on the host and arrive as tables: crop[b] = (h1, w1) 0-based top-left of the fineSize crop (:149-151),
+ * flip[b] (:172), blocks[b] = (count <= 10, tlx_0, tly_0, ...) 0-based inside the crop, block side floor(fineSize / 6), used when the
+ * mask crop is all black (:114-129,163-168).  The sample-rejection rule (:152-157) is loader policy and stays with the caller. */
+CENN_API int cenn_trainer_step_frames_host(cenn_trainer *t, const uint8_t *frames_u8_host, int iH, int iW, const uint8_t *mask_full_host,
+        const int *crop_host, const uint8_t *flip_host, const int *blocks_host, float maskValue, float *losses_host);
 /* eval-mode generator forward (test_vid_wholeim.lua:180, demo.lua:68): in [B,Cin,F,F] -> out, host fp32 NCHW */
 CENN_API int cenn_trainer_generator_forward_host(cenn_trainer *t, const float *in_host, float *out_host, int batch);
 /* debugging / parity: copy an internal activation or gradient as fp32 NCHW to the host by name */

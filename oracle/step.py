@@ -34,6 +34,15 @@ class StepOracle:
         self.errD_real = self.errD_fake = None
 
     # -- closures --------------------------------------------------------
+    def _label(self, out, value):
+        """The label tensor BCE receives.  At fineSize 128 the discriminator emits one value per sample and this is the scripts'
+        `label` of batchSize entries (train.lua:236,302,336).  cfg4 (train_deepernet at 256 x 256, SURVEY 8a caveat): the 4x4 head
+        sees an 8x8 map, emits [B,1,5,5], and nn.View(1):setNumInputDims(3) turns that into [25 B, 1] -- BCE's nElement check
+        would reject a label of B entries, so the script cannot run as shipped.  CONVENTION adopted here and in the executor: every
+        one of the 25 patch outputs of a sample carries that sample's label (label tensor of 25 B entries, sizeAverage over
+        25 B), i.e. the patch-discriminator reading of the same net."""
+        return np.full(out.size, value, self.dtype)
+
     def _d_in(self, center):
         return [self.input_ctx, center] if self.opt.get('conditionAdv') else center      # train.lua:300-311
 
@@ -51,15 +60,15 @@ class StepOracle:
         B = real_ctx.shape[0]
         self.input_ctx = nn._q(real_ctx.astype(self.dtype))
         self.input_real_center = nn._q(real_center.astype(self.dtype))
-        label = np.full(B, 1.0, self.dtype)
         out = self.netD.forward(self._d_in(self.input_real_center))
+        label = self._label(out, 1.0)
         self.errD_real = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
         self.netD.backward(self._d_in(self.input_real_center), df_do)
         fake = self.netG.forward(self._g_in())
         self.input_center = fake.copy()
-        label[...] = 0.0
         out = self.netD.forward(self._d_in(self.input_center))
+        label = self._label(out, 0.0)
         self.errD_fake = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
         self.netD.backward(self._d_in(self.input_center), df_do)
@@ -72,8 +81,8 @@ class StepOracle:
         nets.zero_conv_bias(self.netG)
         self.gG[...] = 0
         B = self.input_ctx.shape[0]
-        label = np.full(B, 1.0, self.dtype)
         out = self.netD.output
+        label = self._label(out, 1.0)
         self.errG = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
         df_dg = self.netD.updateGradInput(self._d_in(self.input_center), df_do)
@@ -98,8 +107,8 @@ class StepOracle:
         self.input_ctx = nn._q(real_ctx.astype(self.dtype))
         self.input_real = nn._q(real_full.astype(self.dtype))
         self.input_mask = real_mask.astype(self.dtype)
-        label = np.full(B, 1.0, self.dtype)
         out = self.netD.forward(self.input_real)
+        label = self._label(out, 1.0)
         self.errD_real = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
         self.netD.backward(self.input_real, df_do)
@@ -109,8 +118,8 @@ class StepOracle:
             self.input_inpainted = ops.mask_composite(self.input_real, self.input_mask, fake)
         else:
             self.input_inpainted = fake.copy()
-        label[...] = 0.0
         out = self.netD.forward(self.input_inpainted)
+        label = self._label(out, 0.0)
         self.errD_fake = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
         self.netD.backward(self.input_inpainted, df_do)
@@ -123,8 +132,8 @@ class StepOracle:
         nets.zero_conv_bias(self.netG)
         self.gG[...] = 0
         B = self.input_ctx.shape[0]
-        label = np.full(B, 1.0, self.dtype)
         out = self.netD.output
+        label = self._label(out, 1.0)
         self.errG = self.criterion.forward(out, label)
         df_do = self.criterion.backward(out, label)
         # train_vid_weighted.lua:481 passes input_real; the first module is a conv so values are unused

@@ -82,7 +82,8 @@ def bn_backward(x, gy, gamma, save_mean, save_invstd, running_mean, running_var,
     g = _t(gamma) if gamma is not None else torch.ones(C, dtype=tx.dtype)
     want_p = ggamma is not None or gbeta is not None
     gx, gg, gb = torch.ops.aten.native_batch_norm_backward(
-        _t(gy), tx, g, _t(running_mean), _t(running_var), None if save_mean is None else _t(save_mean),
+        _t(gy), tx, g, None if running_mean is None else _t(running_mean), None if running_var is None else _t(running_var),
+        None if save_mean is None else _t(save_mean),
         None if save_invstd is None else _t(save_invstd), bool(train), eps, [bool(want_gx), want_p, want_p])
     if ggamma is not None:
         ggamma += (scale * gg.numpy()).astype(ggamma.dtype)

@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 def test_reference_arm_prints_the_contract_line(monkeypatch, capsys):
     import bench
-    monkeypatch.setattr(bench, "cpu_port_step_rate", lambda batch, steps, warmup, threads, variant="image", wtgdl=0.0: (batch * 2.0, 0.5, threads))
+    monkeypatch.setattr(bench, "cpu_port_step_rate", lambda batch, steps, warmup, threads, variant="image", wtgdl=0.0, fine=128: (batch * 2.0, 0.5, threads))
     monkeypatch.setenv("RANK", "0")
     bench.run_reference(types.SimpleNamespace(steps=5, warmup=1, gpus=2))
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
@@ -26,7 +26,7 @@ def test_reference_arm_prints_the_contract_line(monkeypatch, capsys):
     # same workload string as our arm (the driver compares them), the full 256-sample batch per step when it fits the time budget
     assert line["config"]["workload"] == bench.WORKLOAD and line["config"]["batch_per_step"] == 256
     # a slow host: each step becomes a bounded sample of the batch, and the line says so
-    monkeypatch.setattr(bench, "cpu_port_step_rate", lambda batch, steps, warmup, threads, variant="image", wtgdl=0.0: (0.5, batch / 0.5, threads))
+    monkeypatch.setattr(bench, "cpu_port_step_rate", lambda batch, steps, warmup, threads, variant="image", wtgdl=0.0, fine=128: (0.5, batch / 0.5, threads))
     bench.run_reference(types.SimpleNamespace(steps=5, warmup=1, gpus=1))
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert 2 <= line["config"]["batch_per_step"] < 256 and "bounded sample" in line["config"]["sample"] and line["config"]["workload"] == bench.WORKLOAD

@@ -66,8 +66,19 @@ def _cos(a, b):
     return float(np.dot(a, b) / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
 
 
-@pytest.mark.parametrize("variant,extra", [("image", {}), ("video", {}), ("video", {"wtgdl": 0.5}), ("video", {"weight_nomask": 0.0})])
-def test_fused_step_matches_oracle(cenn, variant, extra):
+@pytest.fixture
+def fast_oracle():
+    """Big shapes (fineSize 256): the oracle's heavy ops on the PyTorch-CPU engine (pinned to the numpy functions by tests/test_oracle_torch_engine.py)."""
+    from oracle import torch_engine
+    torch_engine.enable()
+    yield
+    torch_engine.disable()
+
+
+# the last case is BASELINE.json configs[3]'s shape family: train_deepernet at 256 x 256 (5x5 bottleneck, 8x8 first decoder map, patch head)
+@pytest.mark.parametrize("variant,extra", [("image", {}), ("video", {}), ("video", {"wtgdl": 0.5}), ("video", {"weight_nomask": 0.0}),
+                                           ("video", {"fineSize": 256, "B": 2, "predLen": 1, "wtgdl": 0.5})])
+def test_fused_step_matches_oracle(cenn, fast_oracle, variant, extra):
     """Losses against the fp64 oracle + SELF-CONSISTENCY of every kernel of the generator's forward and backward:
     each block's conv output, activation, weight gradient, and the (dgrad -> BN/activation backward) chain into the
     previous block are recomputed in fp64 with the oracle's formulas FROM THE EXECUTOR'S OWN STORED TENSORS.
@@ -424,7 +435,7 @@ def _check_d_sweep(trn, blocks, offs, p_fwd, p_bwd, grads, label, B, check_fwd_w
             sig = trn.fetch("D.%d.sig" % bi).astype(np.float64)
             sig_ref = 1.0 / (1.0 + np.exp(-y_ref.reshape(-1)))
             assert np.max(np.abs(sig - sig_ref)) <= 2e-3, (what, "head sigmoid")
-            g_y = _bce_gpre(sig, label, B).reshape(B, 1, 1, 1)
+            g_y = _bce_gpre(sig, label, sig.size).reshape(y_ref.shape)          # one BCE term per patch output (cfg4 convention: 25 per sample at 256 x 256)
         else:
             a = trn.fetch("D.%d.a" % bi).reshape(shapes[bi]).astype(np.float64)
             if bn is not None:
@@ -475,8 +486,8 @@ def trn_in_shape(trn):
     return (o["nc"] * o["predLen"], o["fineSize"], o["fineSize"])
 
 
-@pytest.mark.parametrize("variant", ["image", "video"])
-def test_fused_discriminator_blocks_self_consistent(cenn, variant):
+@pytest.mark.parametrize("variant,extra", [("image", {}), ("video", {}), ("video", {"fineSize": 256, "B": 2, "predLen": 1})])
+def test_fused_discriminator_blocks_self_consistent(cenn, fast_oracle, variant, extra):
     """VERDICT r1 (weak 4): the discriminator's kernels were only checked through the losses.  Here every D block of all three
     sweeps is recomputed in fp64 from the executor's own stored tensors:
       * REAL sweep (fDx, train.lua:303-310): the step program is stopped after the sweep (cenn_trainer_step_until) -- forward,
@@ -484,7 +495,7 @@ def test_fused_discriminator_blocks_self_consistent(cenn, variant):
       * FAKE sweep forward (train.lua:337) and the DGRAD-ONLY sweep of fGx (train.lua:373: updated D weights, fake-pass
         activations and BN statistics, label 1) down to df_dg, after a complete step."""
     import video_filler_b200.tensor as T
-    orc, trn = _pair(variant)
+    orc, trn = _pair(variant, **extra)
     B = orc.opt["batchSize"]
     batch = orc.synth_batch(np.random.default_rng(31))
     pD0 = orc.pD.copy()
@@ -541,3 +552,36 @@ def test_fused_step_at_benchmark_shapes(cenn, variant, kw):
     assert np.linalg.norm(gG) == pytest.approx(np.linalg.norm(orc.gG), rel=5e-2)
     assert np.linalg.norm(gD) == pytest.approx(np.linalg.norm(orc.gD), rel=5e-2)
     trn.close()
+
+
+def test_frame_mode_step_runs_the_loader_hook_on_the_device(cenn):
+    """cenn_trainer_step_frames_host (device-side random crop, mask crop / random-block mask, maskedFill, hflip, rescale:
+    datavid/donkey_folder.lua:114-129,138-187) against oracle/loader.py on identical draws: the step inputs the executor derives
+    are bit-identical (bf16) to the hook's tensors fed through cenn_trainer_step_host, and the step that follows is the same step."""
+    from oracle import loader
+    from video_filler_b200 import models, train
+    B, F, iH, iW = 6, 128, 180, 240
+    kw = dict(batchSize=B, nBottleneck=128, nef=64, ngf=64, ndf=64, predLen=2, wtgdl=0.5)
+    opt = models.default_opt("video", **kw)
+    orc = ostep.StepOracle(onets.default_opt("video", **kw), seed=5, dtype=np.float64)
+    rng = np.random.default_rng(17)
+    frames = rng.integers(0, 256, (B, 6, iH, iW)).astype(np.uint8)
+    mask_full = np.zeros((iH, iW), np.uint8)
+    mask_full[20:70, 150:230] = 255                      # a logo in the upper right corner: some crops miss it -> random blocks
+    crop, flip, blocks = loader.draw_hook_params(B, iH, iW, F, rng)
+    crop[0] = (0, 0); crop[1] = (iH - F, iW - F)          # the extreme origins; sample 0 misses the logo, sample 1 may hit it
+    crop[2] = (10, 100)                                   # certainly overlaps the logo
+    masked, full, mask = loader.train_hook(frames, mask_full, crop, flip, blocks, F, opt["maskValue"])
+    assert mask[0].max() == 1 and mask[2].max() == 1 and not np.array_equal(mask[0], mask[2])
+    res = []
+    for mode in ("host", "frames"):
+        trn = train.FusedTrainer(opt, precision="bf16")
+        trn.set_params(0, orc.pG); trn.set_params(1, orc.pD)
+        losses = trn.step_host(masked, full, mask) if mode == "host" else trn.step_frames_host(frames, mask_full, crop, flip, blocks)
+        res.append((losses, trn.fetch("ctx"), trn.get_grads(1)))
+        trn.close()
+    (l0, ctx0, g0), (l1, ctx1, g1) = res
+    assert np.array_equal(ctx0, ctx1)                     # identical bf16 step inputs on both paths
+    for k, tol in (("errG_l2", 2e-3), ("errG_gdl", 2e-3), ("errD", 5e-3), ("errG", 4e-2)):
+        assert abs(l0[k] - l1[k]) <= tol * max(abs(l0[k]), 1e-3), (k, l0[k], l1[k])
+    assert _cos(g0, g1) >= 0.97

@@ -47,6 +47,8 @@ def test_engine_ops_match_numpy_ops():
         gx1 = torch_engine.bn_backward(x, gyb, gamma, m1, s1, rm1, rv1, train, ggamma=gg1, gbeta=gb1)
         gx2 = ops.bn_backward(x, gyb, gamma, m2, s2, rm2, rv2, train, ggamma=gg2, gbeta=gb2)
         assert rel_err(gx1, gx2) <= 1e-11 and rel_err(gg1, gg2) <= 1e-11 and rel_err(gb1, gb2) <= 1e-11
+        if train:        # the running statistics are optional in training mode (the block checks of tests/test_fused_gpu.py pass None)
+            assert rel_err(torch_engine.bn_backward(x, gyb, gamma, m1, s1, None, None, True), gx2) <= 1e-11
     for f in ("leaky_relu", "relu", "tanh"):
         assert rel_err(getattr(torch_engine, f)(x), getattr(ops, f)(x)) <= 1e-15
     assert rel_err(torch_engine.leaky_relu_grad(x, gyb), ops.leaky_relu_grad(x, gyb)) <= 1e-15

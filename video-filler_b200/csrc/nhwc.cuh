@@ -772,6 +772,69 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(const FoldJob *__restric
     }
 }
 
+// ---------------------------------------------------------------- 4x4 / stride-1 / pad-0 windows on maps larger than 4x4 (fineSize 256: cfg4)
+// The bottleneck convolution, the first decoder layer and the discriminator head are plain GEMMs when their 4x4 window covers the
+// whole map (fineSize 128).  At fineSize 256 (train_deepernet at 256 x 256) the map is 8x8 and the window slides over 5x5 positions:
+// the GEMMs stay, fed by / feeding an explicit window buffer  col[m = (n, oy, ox)][tap = 4u + v][c] = x[n, oy + u, ox + v, c].
+__global__ void __launch_bounds__(256) im2col_v4_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ col, int N, int H, int W, int Cp) {
+    pdl_trigger(); pdl_wait();
+    const int ho = H - 3, wo = W - 3, vpp = Cp / 8;
+    const int64_t total = (int64_t)N * ho * wo * 16 * vpp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % vpp); int64_t r = i / vpp;
+        const int tap = (int)(r & 15); r >>= 4;
+        const int ox = (int)(r % wo), oy = (int)((r / wo) % ho), n = (int)(r / ((int64_t)wo * ho));
+        const int64_t src = (((int64_t)n * H + oy + (tap >> 2)) * W + ox + (tap & 3)) * vpp + cv;
+        reinterpret_cast<uint4 *>(col)[i] = __ldg(reinterpret_cast<const uint4 *>(x) + src);
+    }
+}
+// adjoint: out[n, y, x, c] = bias[c] + sum over the windows (oy, ox) = (y - u, x - v) that cover the pixel of col[(n, oy, ox)][4u + v][c];
+// optional per-channel sum / sum of squares of the STORED (bf16) values -> BN statistics of the first decoder layer.
+// blockDim = (TX channel vectors, TY pixel lanes), grid = (pixel strips, vector groups), as the BN reductions.
+__global__ void __launch_bounds__(256) col2im_v4_kernel(const bf16 *__restrict__ col, bf16 *__restrict__ out, const float *__restrict__ bias, float *__restrict__ stats,
+        int stats_stride, int N, int H, int W, int Cp, int C) {
+    pdl_trigger(); pdl_wait();
+    const int ho = H - 3, wo = W - 3, vpp = Cp / 8;
+    const int vec = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = vec < vpp;
+    float acc[2][8] = {};
+    if (active) {
+        float bv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bv[k] = (bias && vec * 8 + k < C) ? bias[vec * 8 + k] : 0.f;
+        const int64_t npix = (int64_t)N * H * W, stride = (int64_t)gridDim.x * blockDim.y;
+        for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < npix; p += stride) {
+            const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((int64_t)W * H));
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = bv[k];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int oy = y - u;
+                if (oy < 0 || oy >= ho) continue;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int ox = x - v;
+                    if (ox < 0 || ox >= wo) continue;
+                    float t[8];
+                    unpack8(__ldg(reinterpret_cast<const uint4 *>(col) + ((((int64_t)n * ho + oy) * wo + ox) * 16 + u * 4 + v) * vpp + vec), t);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] += t[k];
+                }
+            }
+            const uint4 pk = pack8(f);
+            reinterpret_cast<uint4 *>(out)[p * vpp + vec] = pk;
+            if (stats) {
+                float q[8];
+                unpack8(pk, q);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { acc[0][k] += q[k]; acc[1][k] = fmaf(q[k], q[k], acc[1][k]); }
+            }
+        }
+    }
+    if (stats) fold_and_flush<2, true>(acc, active, stats, stats_stride, C);
+}
+
 // ---------------------------------------------------------------- discriminator head: 4x4 valid conv to 1 channel + Sigmoid + BCE
 // out[b] = sigmoid(sum_k x[b,k] w[k] + bias): one warp per sample, 16-byte loads
 __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16 *__restrict__ x, const bf16 *__restrict__ w, const float *__restrict__ bias,
@@ -1174,6 +1237,43 @@ __global__ void __launch_bounds__(256) clip_prepare_kernel(const float *__restri
                 reinterpret_cast<uint4 *>(maskx + i * CP)[q] = reinterpret_cast<const uint4 *>(vm)[q];
             }
         }
+    }
+}
+
+// Device-side remainder of the video loader's hook (datavid/donkey_folder.lua:114-129,138-170): random crop of the loaded frames and
+// of the logo mask, and the random-block mask that replaces an all-black mask crop.  The RANDOM DRAWS stay on the host (crop origin,
+// block count and corners: torch.uniform / torch.random, :149-150,120-123) and arrive as small integer tables; the pixels never do:
+//   frames_u8 [N][C][iH][iW] (what image.load decodes: byte / 255), mask_full [iH][iW], crop[n] = (h1, w1) 0-based,
+//   blocks[n] = (count, tlx_0, tly_0, ..., tlx_9, tly_9) 0-based inside the crop, block side = floor(F / 6).
+// Output = the clip-mode inputs of clip_prepare_kernel: frames01 [N][C][F][F] and one mask plane per sample.
+__global__ void __launch_bounds__(256) crop_mask_any_kernel(const uint8_t *__restrict__ mask_full, const int *__restrict__ crop, int iW, int F, int *__restrict__ any) {
+    __shared__ int found;
+    if (threadIdx.x == 0) found = 0;
+    __syncthreads();
+    const int n = blockIdx.x, h1 = crop[2 * n], w1 = crop[2 * n + 1];
+    int f = 0;
+    for (int i = threadIdx.x; i < F * F; i += blockDim.x) f |= mask_full[(int64_t)(h1 + i / F) * iW + w1 + i % F] != 0;
+    if (f) found = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) any[n] = found;                   // maskout:max() > 0.5 (:163)
+}
+__global__ void __launch_bounds__(256) frames_to_clips_kernel(const uint8_t *__restrict__ frames_u8, const uint8_t *__restrict__ mask_full, const int *__restrict__ crop,
+        const int *__restrict__ blocks, const int *__restrict__ any, int N, int C, int iH, int iW, int F, float *__restrict__ frames01, uint8_t *__restrict__ mask1) {
+    const int64_t total = (int64_t)N * F * F;
+    const int bs = F / 6;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / ((int64_t)F * F)), r = (int)(i - (int64_t)n * F * F), y = r / F, x = r - y * F;
+        const int h1 = crop[2 * n], w1 = crop[2 * n + 1];
+        const int64_t src = (int64_t)(h1 + y) * iW + w1 + x;
+        bool m;
+        if (any[n]) m = mask_full[src] != 0;
+        else {                                               // randomBlockMask (:114-129)
+            m = false;
+            const int *b = blocks + 21 * n;
+            for (int k = 0; k < b[0]; ++k) { const int tlx = b[1 + 2 * k], tly = b[2 + 2 * k]; m = m || (x >= tlx && x < tlx + bs && y >= tly && y < tly + bs); }
+        }
+        mask1[i] = m ? 1 : 0;
+        for (int c = 0; c < C; ++c) frames01[((int64_t)n * C + c) * F * F + r] = (float)frames_u8[((int64_t)n * C + c) * iH * iW + src] / 255.f;
     }
 }
 

@@ -40,8 +40,12 @@ struct Block {
     // THNN flat offsets
     int64_t t_w_off = 0, t_b_off = 0, t_g_off = -1, t_be_off = -1;
     Tensor in, y, a, g;                     // input, conv output (BN blocks), activation output, gradient buffer
-    bf16 *col = nullptr;                    // im2col of the thin large-side tensor (forward input or backward gradient)
+    bf16 *col = nullptr;                    // im2col of the thin large-side tensor (forward input or backward gradient);
+                                            // V4 blocks on maps larger than 4x4 (fineSize 256): the 4x4 window buffer [M][16*Clp]
+    bf16 *colg = nullptr;                   // V4 blocks, general case: window buffer of the gradient [M][16*Clp] (CONV_V4 / HEAD dgrad output)
     int64_t col_rows = 0, col_k = 0;
+    int P = 1;                              // V4 blocks: window positions per sample (1 at fineSize 128, 25 at fineSize 256)
+    int Mrows = 0;                          // V4 blocks: GEMM rows = batch * P
     bf16 *Wt = nullptr;                     // transposed operand copy
     int cl_rows = 0;
     unsigned int *done_ctr = nullptr;       // bn_finalize_apply_act: CTAs that have consumed the statistics
@@ -156,6 +160,8 @@ struct cenn_trainer {
     uint8_t *in_f = nullptr, *in_f2 = nullptr;
     const uint8_t *cur_f = nullptr;
     float clip_mv = -1.f;                 // maskValue baked into the captured clip-mode graphs
+    // frame mode (cenn_trainer_step_frames_host): whole decoded frames + loader draws in, crop / mask / random blocks on the device
+    uint8_t *fr_u8 = nullptr, *fr_mask = nullptr; int *fr_tab = nullptr; size_t fr_u8_cap = 0, fr_mask_cap = 0;
     bool infer = false;                   // inference engine (cenn_inpainter_*): forward plans only, BN folded into weights and bias
     int infer_n = 0;                      // tiles converted in / out by the current forward call
 };
@@ -238,8 +244,9 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         bool out_small;
         switch (sp.type) {
             case CONV_S2: REQUIRE(cur.H % 2 == 0 && cur.H >= 2, "conv input size %d not even", cur.H); b.h = cur.H / 2; b.w = cur.W / 2; oh = b.h; ow = b.w; out_small = true; break;
-            case CONV_V4: case HEAD: REQUIRE(cur.H == 4 && cur.W == 4, "4x4 valid conv expects a 4x4 input, got %dx%d (fineSize must be 128 for these nets)", cur.H, cur.W); b.h = 1; b.w = 1; oh = 1; ow = 1; out_small = true; break;
-            case FULL_V4: REQUIRE(cur.H == 1 && cur.W == 1, "G1 expects a 1x1 input"); b.h = 1; b.w = 1; oh = 4; ow = 4; out_small = false; break;
+            case CONV_V4: case HEAD: REQUIRE(cur.H >= 4 && cur.W >= 4 && cur.H <= 16, "4x4 valid conv expects a 4x4 .. 16x16 input, got %dx%d", cur.H, cur.W);
+                b.h = cur.H - 3; b.w = cur.W - 3; oh = b.h; ow = b.w; out_small = true; break;
+            case FULL_V4: REQUIRE(cur.H >= 1 && cur.H <= 13, "G1 expects a 1x1 .. 13x13 input, got %dx%d", cur.H, cur.W); b.h = cur.H; b.w = cur.W; oh = cur.H + 3; ow = cur.W + 3; out_small = false; break;
             default: b.h = cur.H; b.w = cur.W; oh = 2 * cur.H; ow = 2 * cur.W; out_small = false; break;
         }
         // channel padding: the large side of an s2 layer is either thin (im2col) or a multiple of 64 (TMA gather)
@@ -257,6 +264,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             b.Clp = sp.Cl <= 16 ? pad_thin(sp.Cl) : round_up(sp.Cl, 64);
             b.Coutp = b.Clp;
         }
+        if (sp.type == CONV_V4 || sp.type == FULL_V4 || sp.type == HEAD) { b.P = b.h * b.w; b.Mrows = N * b.P; }
         b.thin = (sp.type == CONV_S2 || sp.type == FULL_S2) && b.Clp < 64;
         if (sp.type == FULL_S2 || sp.type == CONV_S2) REQUIRE(b.thin || b.Clp % 64 == 0, "block %zu: large-side channels %d not a multiple of 64", i, b.Clp);
         if (sp.type == FULL_S2) REQUIRE(b.Csp % 64 == 0, "block %zu: small-side channels %d not a multiple of 64", i, b.Csp);
@@ -274,7 +282,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         }
         // activations
         if (sp.type == HEAD) {
-            b.sig = dalloc<float>(t, N); b.gpre = dalloc<float>(t, N);
+            b.sig = dalloc<float>(t, b.Mrows); b.gpre = dalloc<float>(t, b.Mrows);
             if (!b.sig || !b.gpre) return 1;
         } else {
             if (sp.bn && !t->infer && alloc_tensor(t, b.y, N, oh, ow, b.Cout, b.Coutp)) return 1;
@@ -310,6 +318,13 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             b.part = dalloc<float>(t, (int64_t)b.part_rows * 2 * std::max(b.Coutp, 8));
             if (!b.part) return 1;
         }
+        if (b.P > 1) {
+            REQUIRE(!t->infer, "the inference engine supports fineSize 128 only");
+            b.col_rows = b.Mrows; b.col_k = 16 * b.Clp;
+            b.col = dalloc<bf16>(t, b.col_rows * b.col_k);
+            if (!b.col) return 1;
+            if (sp.type != FULL_V4) { b.colg = dalloc<bf16>(t, b.col_rows * b.col_k); if (!b.colg) return 1; }
+        }
         if (b.thin && !(t->infer && sp.type != CONV_S2)) {
             b.col_rows = (int64_t)N * b.h * b.w; b.col_k = 16 * b.Clp;
             b.col = dalloc<bf16>(t, b.col_rows * b.col_k);
@@ -325,7 +340,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                 CK(cudaMemcpy(b.running + b.Coutp, ones.data(), b.Coutp * sizeof(float), cudaMemcpyHostToDevice));
             }
         } else if (sp.bn) {
-            b.fold = sp.type == FULL_V4 ? 16 : 1;
+            b.fold = (sp.type == FULL_V4 && b.P == 1) ? 16 : 1;       // G1 on a 1x1 input: the GEMM epilogue accumulates per (tap, channel) column
             b.stats_cols = b.Coutp * b.fold;
             b.stats = dalloc<float>(t, 2 * (int64_t)b.stats_cols);
             b.bsums = dalloc<float>(t, 2 * (int64_t)b.Coutp);
@@ -418,7 +433,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         TcEpilogue ep_f;                       // forward epilogue: bias, then BN statistics or fused activation
         // (conv biases are zero in every training forward -- train.lua:279-280 -- but not when a checkpoint is evaluated)
         ep_f.bias = net.master + b.b_off;
-        if (b.type == FULL_V4) {               // G1: GEMM columns are (tap, channel) -> per-column copy of the channel bias
+        if (b.type == FULL_V4 && b.P == 1) {   // G1 on a 1x1 input: GEMM columns are (tap, channel) -> per-column copy of the channel bias
             b.bias_exp = dalloc<float>(t, 16 * (int64_t)b.Clp);
             if (!b.bias_exp) return 1;
             ep_f.bias = b.bias_exp;
@@ -449,19 +464,26 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                 break;
             }
             case CONV_V4: {
+                // P == 1 (fineSize 128): the 4x4 window is the whole map, the input IS the GEMM operand and the dgrad output IS the previous
+                // block's gradient.  P > 1: both go through the window buffers (im2col_v4 / col2im_v4 around the GEMMs).
                 int K = 16 * b.Clp;
-                if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, b.Cs, K, b.Csp, ep_f)) return 1;
-                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, b.in.p, gW, N, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
-                { TcEpilogue ep_m = ep_n; ep_m.b_mn = true;     // dgrad = g [N,Cs] x Wf [Cs][K]
-                  if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, dgrad_out, N, K, b.Csp, K, ep_m)) return 1; }
+                const int Mr = b.Mrows;
+                const bf16 *a_fwd = b.P > 1 ? b.col : b.in.p;
+                if (tc_plan_gemm(s, &b.p_fwd, a_fwd, Wf, fwd_out, Mr, b.Cs, K, b.Csp, ep_f)) return 1;
+                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, a_fwd, gW, Mr, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
+                { TcEpilogue ep_m = ep_n; ep_m.b_mn = true;     // dgrad = g [M,Cs] x Wf [Cs][K]
+                  if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, b.P > 1 ? b.colg : dgrad_out, Mr, K, b.Csp, K, ep_m)) return 1; }
                 break;
             }
             case FULL_V4: {
                 int K = 16 * b.Clp;
-                { TcEpilogue ep_m = ep_f; ep_m.b_mn = true;     // G1 = in [N,Cs] x Wf [Cs][K]
-                  if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, fwd_out, N, K, b.Csp, K, ep_m)) return 1; }
-                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.in.p, b.g.p, gW, N, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
-                if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, dgrad_out, N, b.Cs, K, b.Csp, ep_n)) return 1;
+                const int Mr = b.Mrows;
+                { TcEpilogue ep_m = ep_f; ep_m.b_mn = true;     // G1 = in [M,Cs] x Wf [Cs][K]
+                  if (b.P > 1) { ep_m.bias = nullptr; ep_m.stats = nullptr; ep_m.act = 0; }      // bias, statistics (and no activation: BN follows) after the overlap-add
+                  if (tc_plan_gemm(s, &b.p_fwd, b.in.p, Wf, b.P > 1 ? b.col : fwd_out, Mr, K, b.Csp, K, ep_m)) return 1; }
+                const bf16 *g_cols = b.P > 1 ? b.col : b.g.p;    // backward: the window buffer is reused for im2col_v4(g_y)
+                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.in.p, g_cols, gW, Mr, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
+                if (tc_plan_gemm(s, &b.p_dgrad, g_cols, Wf, dgrad_out, Mr, b.Cs, K, b.Csp, ep_n)) return 1;
                 break;
             }
             case FULL_S2: {
@@ -513,6 +535,30 @@ void emit_im2col(T *t, const Tensor &L, bf16 *col, int h, int w) {
         KLAUNCH(s); return 0;
     });
 }
+void reduce_dims(int vec_per_pix, dim3 &block, int &gy);
+// 4x4 / stride-1 windows of an [N,H,W,Cp] map (fineSize 256, V4 blocks): x -> col[(n,oy,ox)][tap][c]
+void emit_im2col_v4(T *t, const Tensor &x, bf16 *col) {
+    cenn_state *s = t->s;
+    Tensor xc = x;
+    emit(t, "im2col_v4", [s, xc, col]() {
+        const int64_t total = (int64_t)xc.N * (xc.H - 3) * (xc.W - 3) * 16 * (xc.Cp / 8);
+        LK(nhwc::im2col_v4_kernel, dim3(grid1d(s, total)), dim3(256), 0, s->stream)(xc.p, col, xc.N, xc.H, xc.W, xc.Cp);
+        KLAUNCH(s); return 0; });
+    t->prog.back().bytes = 2.0 * 2.0 * (double)x.N * (x.H - 3) * (x.W - 3) * 16 * x.C;
+}
+// adjoint (overlap-add of the windows) into out [N,H,W,Cp]; optional bias and BN statistics of the stored values
+void emit_col2im_v4(T *t, const bf16 *col, const Tensor &out, const float *bias, float *stats, int stats_stride) {
+    cenn_state *s = t->s;
+    Tensor oc = out;
+    emit(t, "col2im_v4", [s, col, oc, bias, stats, stats_stride]() {
+        const int vpp = oc.Cp / 8;
+        dim3 blk; int gy; reduce_dims(vpp, blk, gy);
+        const int64_t npix = oc.pix();
+        const int rows = (int)std::max<int64_t>(1, std::min<int64_t>((npix + blk.y - 1) / blk.y, (int64_t)s->sm_count * 8 / gy));
+        LK(nhwc::col2im_v4_kernel, dim3(rows, gy), blk, stats ? 2 * blk.x * 8 * sizeof(float) : 0, s->stream)(col, oc.p, bias, stats, stats_stride, oc.N, oc.H, oc.W, oc.Cp, oc.C);
+        KLAUNCH(s); return 0; });
+    t->prog.back().bytes = 2.0 * ((double)out.N * (out.H - 3) * (out.W - 3) * 16 * out.C + (double)out.pix() * out.C);
+}
 void reduce_dims(int vec_per_pix, dim3 &block, int &gy) {
     int tx = 1; while (tx < vec_per_pix && tx < 64) tx *= 2;
     block = dim3(tx, 256 / tx);
@@ -527,10 +573,11 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
     const double n_global = b->type == HEAD ? 1.0 : (double)t->Bglobal * b->a.H * b->a.W;
     if (b->type == HEAD) {
         const bf16 *w = net.wbf + b->w_off; const float *bias = master + b->b_off;
-        int B = t->B, K = 16 * b->Clp;
-        Tensor in = b->in;
-        emit(t, "head_fwd", [s, in, w, bias, b, B, K]() {
-            LK(nhwc::head_fwd_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, s->stream)(in.p, w, bias, b->sig, B, K); KLAUNCH(s); return 0; });
+        int B = b->Mrows, K = 16 * b->Clp;          // one row per 4x4 window (fineSize 128: one per sample)
+        if (b->P > 1) emit_im2col_v4(t, b->in, b->col);
+        const bf16 *x = b->P > 1 ? b->col : b->in.p;
+        emit(t, "head_fwd", [s, x, w, bias, b, B, K]() {
+            LK(nhwc::head_fwd_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, s->stream)(x, w, bias, b->sig, B, K); KLAUNCH(s); return 0; });
         return;
     }
     if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
@@ -538,7 +585,10 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
         const float *bias = master + b->b_off;
         emit(t, "expand_bias", [s, b, bias]() { expand_bias_kernel<<<(16 * b->Clp + 255) / 256, 256, 0, s->stream>>>(bias, b->bias_exp, b->Cout, b->Clp); KLAUNCH(s); return 0; });
     }
+    if (b->type == CONV_V4 && b->P > 1) emit_im2col_v4(t, b->in, b->col);
     emit_plan(t, "conv_fwd", &b->p_fwd);
+    if (b->type == FULL_V4 && b->P > 1)       // overlap-add of the 4x4 windows + bias + BN statistics
+        emit_col2im_v4(t, b->col, b->bn ? b->y : b->a, master + b->b_off, b->bn ? b->stats : nullptr, b->stats_cols);
     if (b->bn && train && t->cfg.world_size <= 1 && b->Coutp <= 4096 && getenv("CENN_NO_BN_FUSE") == nullptr) {
         float *gamma = master + b->g_off, *beta = master + b->be_off;
         emit(t, "bn_fin_apply", [s, b, gamma, beta, n_global]() {
@@ -590,13 +640,14 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
     float *grad = net.grad, *master = net.master;
     if (b->type == HEAD) {
         const bf16 *w = net.wbf + b->w_off;
-        int B = t->B, K = 16 * b->Clp;
-        Tensor in = b->in;
-        bf16 *gx = net.blocks[i - 1].g.p;
-        if (want_params) emit(t, "head_wgrad", [s, b, in, grad, B, K]() {
-            LK(nhwc::head_wgrad_kernel, dim3(dim3((K / 8 + 127) / 128, 16)), dim3(128), 0, s->stream)(b->gpre, in.p, grad + b->w_off, grad + b->b_off, B, K); KLAUNCH(s); return 0; });
+        int B = b->Mrows, K = 16 * b->Clp;
+        const bf16 *x = b->P > 1 ? b->col : b->in.p;
+        bf16 *gx = b->P > 1 ? b->colg : net.blocks[i - 1].g.p;
+        if (want_params) emit(t, "head_wgrad", [s, b, x, grad, B, K]() {
+            LK(nhwc::head_wgrad_kernel, dim3(dim3((K / 8 + 127) / 128, 16)), dim3(128), 0, s->stream)(b->gpre, x, grad + b->w_off, grad + b->b_off, B, K); KLAUNCH(s); return 0; });
         emit(t, "head_dgrad", [s, b, w, gx, B, K]() {
             LK(nhwc::head_dgrad_kernel, dim3(grid1d(s, (int64_t)B * K / 8)), dim3(256), 0, s->stream)(b->gpre, w, gx, B, K); KLAUNCH(s); return 0; });
+        if (b->P > 1) emit_col2im_v4(t, b->colg, net.blocks[i - 1].g, nullptr, nullptr, 0);
         return;
     }
     const int vpp = b->Coutp >= 8 ? b->Coutp / 8 : 1;
@@ -699,6 +750,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;
     }
+    if (b->type == FULL_V4 && b->P > 1 && (want_params || (want_dgrad && b->has_dgrad))) emit_im2col_v4(t, b->g, b->col);
     // weight gradient
     if (want_params) {
         if (b->thin && b->type == FULL_S2) emit_im2col(t, b->g, b->col, b->h, b->w);
@@ -756,6 +808,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
                 return rc; });
             t->prog.back().flops = pl->flops;
         } else emit_plan(t, "dgrad", &b->p_dgrad);
+        if (b->type == CONV_V4 && b->P > 1) emit_col2im_v4(t, b->colg, net.blocks[i - 1].g, nullptr, nullptr, 0);
     }
     // single GPU, generator: once this block's wgrad (side stream) and dgrad (this stream, the last reader of its weights)
     // are queued, its slice of the flat vector can take its Adam update on a third stream while the sweep goes on
@@ -870,8 +923,10 @@ void emit_adam(T *t, Net &net, std::vector<std::pair<int64_t, int64_t>> done = {
 }
 void emit_bce(T *t, Block *head, float label, int loss_slot, bool want_grad) {
     cenn_state *s = t->s;
-    double inv_n = 1.0 / (double)t->Bglobal;
-    int B = t->B;
+    // one BCE term per discriminator output: batchSize at fineSize 128; 25 per sample at fineSize 256, each carrying its sample's
+    // label (the cfg4 label convention, DESIGN.md section 6 / oracle/step.py:_label)
+    double inv_n = 1.0 / ((double)t->Bglobal * head->P);
+    int B = head->Mrows;
     double *acc = t->loss_acc + loss_slot;
     emit(t, "bce", [s, head, label, acc, B, inv_n, want_grad]() {
         LK(nhwc::head_bce_kernel, dim3((B + 255) / 256), dim3(256), 0, s->stream)(head->sig, label, want_grad ? head->gpre : nullptr, acc, B, inv_n); KLAUNCH(s); return 0; });
@@ -1179,7 +1234,8 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     REQUIRE(cfg && out, "cenn_trainer_create: null argument");
     REQUIRE(cfg->precision == CENN_BF16, "the fused executor runs in BF16 tensor-core mode only; use the op-level modules for CENN_FP32");
     REQUIRE(cfg->variant == 0 || cfg->variant == 1, "unknown variant %d", cfg->variant);
-    REQUIRE(cfg->fineSize == 128, "fineSize must be 128 (the 4x4 bottleneck/head of the reference nets), got %d", cfg->fineSize);
+    REQUIRE(cfg->fineSize == 128 || (cfg->fineSize == 256 && cfg->variant == 1),
+            "fineSize must be 128, or 256 for the video / deeper nets (train_deepernet at 256 x 256: 5x5 bottleneck and patch head), got %d", cfg->fineSize);
     REQUIRE(cfg->batchSize >= 1 && cfg->nBottleneck % 8 == 0 && cfg->nef % 64 == 0 && cfg->ngf % 64 == 0 && cfg->ndf % 64 == 0,
             "batchSize >= 1, nBottleneck %% 8 == 0 and nef/ngf/ndf %% 64 == 0 required (got %d, %d, %d/%d/%d)", cfg->batchSize, cfg->nBottleneck, cfg->nef, cfg->ngf, cfg->ndf);
     REQUIRE(cfg->variant == 1 || cfg->overlapPred * 2 <= cfg->fineSize / 2, "overlapPred too large");
@@ -1233,6 +1289,9 @@ int cenn_trainer_destroy(cenn_trainer *t) {
     if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (t->ev_copied[i]) cudaEventDestroy(t->ev_copied[i]); if (t->ev_consumed[i]) cudaEventDestroy(t->ev_consumed[i]); if (t->ev_loss[i]) cudaEventDestroy(t->ev_loss[i]); }
     if (t->pin_loss2) cudaFreeHost(t->pin_loss2);
+    if (t->fr_u8) cudaFree(t->fr_u8);
+    if (t->fr_mask) cudaFree(t->fr_mask);
+    if (t->fr_tab) cudaFree(t->fr_tab);
     for (Net *n : {&t->G, &t->D})
         for (Block &b : n->blocks) { tc_plan_free(&b.p_fwd); tc_plan_free(&b.p_dgrad); tc_plan_free(&b.p_wgrad); }
     if (t->side) { cudaStreamSynchronize(t->side); cudaStreamDestroy(t->side); }
@@ -1471,6 +1530,41 @@ int cenn_trainer_step_clips_host_async(cenn_trainer *t, const float *frames01, c
     return 0;
 }
 
+// Frame-mode step (video variant): the host hands over what the loader holds BEFORE its per-sample hook -- decoded frames (bytes), the
+// full-size logo mask and the hook's random draws (crop origin, hflip, random-block corners) -- and the device runs the hook
+// (datavid/donkey_folder.lua:138-187): crop, mask crop + expand, maskedFill or randomBlockMask, hflip, [0,1] -> [-1,1].
+int cenn_trainer_step_frames_host(cenn_trainer *t, const uint8_t *frames_u8, int iH, int iW, const uint8_t *mask_full, const int *crop,
+                                  const uint8_t *flip, const int *blocks, float maskValue, float *losses) {
+    REQUIRE(t && frames_u8 && mask_full && crop && blocks && losses, "cenn_trainer_step_frames_host: null argument");
+    REQUIRE(t->cfg.variant == 1, "cenn_trainer_step_frames_host: frames belong to the video variant");
+    const int F = t->F, B = t->B, Cc = t->nc;
+    REQUIRE(iH >= F && iW >= F, "cenn_trainer_step_frames_host: frames (%dx%d) smaller than fineSize %d", iH, iW, F);
+    for (int n = 0; n < B; ++n) {
+        REQUIRE(crop[2 * n] >= 0 && crop[2 * n] + F <= iH && crop[2 * n + 1] >= 0 && crop[2 * n + 1] + F <= iW, "crop %d outside the frame", n);
+        REQUIRE(blocks[21 * n] >= 0 && blocks[21 * n] <= 10, "sample %d: at most 10 random blocks (donkey_folder.lua:120)", n);
+    }
+    API_BEGIN(t->s);
+    cenn_state *s = t->s;
+    cudaStream_t st = s->stream;
+    const size_t n_u8 = (size_t)B * Cc * iH * iW, n_mask = (size_t)iH * iW;
+    if (n_u8 > t->fr_u8_cap) { if (t->fr_u8) cudaFree(t->fr_u8); t->fr_u8 = nullptr; CK(cudaMalloc(&t->fr_u8, n_u8)); t->fr_u8_cap = n_u8; }
+    if (n_mask > t->fr_mask_cap) { if (t->fr_mask) cudaFree(t->fr_mask); t->fr_mask = nullptr; CK(cudaMalloc(&t->fr_mask, n_mask)); t->fr_mask_cap = n_mask; }
+    if (!t->fr_tab) CK(cudaMalloc(&t->fr_tab, (size_t)B * (2 + 21 + 1) * sizeof(int)));
+    if (!t->in_f) { t->in_f = dalloc<uint8_t>(t, B); REQUIRE(t->in_f, "trainer: staging allocation failed"); }
+    int *d_crop = t->fr_tab, *d_blocks = t->fr_tab + 2 * B, *d_any = t->fr_tab + 23 * B;
+    CK(cudaMemcpyAsync(t->fr_u8, frames_u8, n_u8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(t->fr_mask, mask_full, n_mask, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_crop, crop, (size_t)B * 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_blocks, blocks, (size_t)B * 21 * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (flip) CK(cudaMemcpyAsync(t->in_f, flip, B, cudaMemcpyHostToDevice, st)); else CK(cudaMemsetAsync(t->in_f, 0, B, st));
+    nhwc::crop_mask_any_kernel<<<B, 256, 0, st>>>(t->fr_mask, d_crop, iW, F, d_any);
+    KLAUNCH(s);
+    nhwc::frames_to_clips_kernel<<<grid1d(s, (int64_t)B * F * F), 256, 0, st>>>(t->fr_u8, t->fr_mask, d_crop, d_blocks, d_any, B, Cc, iH, iW, F, t->in_b, t->in_m);
+    KLAUNCH(s);
+    if (step_clips_device(t, t->in_b, t->in_m, t->in_f, maskValue)) return 1;
+    return cenn_trainer_read_losses(t, losses);
+}
+
 // One step with a CUDA-event pair around every op of the program (on the launching stream); returns the op names
 // ('\n'-separated), their durations and algorithmic FLOPs.  Used by bench.py for the roofline of the dominant kernels.
 int cenn_trainer_profile_step(cenn_trainer *t, const float *a, const float *b, const uint8_t *mask, char *names, int64_t names_cap,
@@ -1673,7 +1767,7 @@ int cenn_trainer_fetch_host(cenn_trainer *t, const char *name, float *dst, int64
         std::string f = nm.substr(dot + 1);
         Block &b = n.blocks[idx];
         if (f == "y") x = b.y; else if (f == "a") x = b.a; else if (f == "g") x = b.g; else if (f == "in") x = b.in;
-        else if (f == "sig") { *count = t->B; REQUIRE(capacity >= t->B && b.sig, "fetch: no sig"); CK(cudaStreamSynchronize(s->stream)); CK(cudaMemcpy(dst, b.sig, t->B * 4, cudaMemcpyDeviceToHost)); return 0; }
+        else if (f == "sig") { *count = b.Mrows; REQUIRE(capacity >= b.Mrows && b.sig, "fetch: no sig"); CK(cudaStreamSynchronize(s->stream)); CK(cudaMemcpy(dst, b.sig, (size_t)b.Mrows * 4, cudaMemcpyDeviceToHost)); return 0; }
         else { cenn_set_error("fetch: unknown field in '%s'", name); return 1; }
     }
     REQUIRE(x.p, "fetch: '%s' has no buffer", name);

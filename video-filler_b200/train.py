@@ -300,6 +300,23 @@ class FusedTrainer:
                                            losses.ctypes.data_as(C.c_void_p))
         return dict(zip(LOSS_NAMES, losses.tolist()))
 
+    def step_frames_host(self, frames_u8, mask_full, crop, flip, blocks, maskValue=None):
+        """Frame-mode step (video variant): decoded frames uint8 [B, nc*predLen, iH, iW], the full-size mask uint8 [iH, iW] and the loader
+        hook's draws (crop int32 [B,2] 0-based, flip uint8 [B] or None, blocks int32 [B,21]); the device runs the hook
+        (datavid/donkey_folder.lua:114-129,138-187)."""
+        frames_u8 = np.ascontiguousarray(frames_u8, np.uint8)
+        mask_full = np.ascontiguousarray(mask_full, np.uint8)
+        crop = np.ascontiguousarray(crop, np.int32)
+        blocks = np.ascontiguousarray(blocks, np.int32)
+        assert frames_u8.ndim == 4 and mask_full.shape == frames_u8.shape[2:] and crop.shape == (frames_u8.shape[0], 2) and blocks.shape == (frames_u8.shape[0], 21)
+        f = np.ascontiguousarray(flip, np.uint8).ctypes.data_as(C.c_void_p) if flip is not None else None
+        mv = float(self.opt["maskValue"] if maskValue is None else maskValue)
+        losses = np.zeros(8, np.float32)
+        api().cenn_trainer_step_frames_host(self.h, frames_u8.ctypes.data_as(C.c_void_p), int(frames_u8.shape[2]), int(frames_u8.shape[3]),
+                                            mask_full.ctypes.data_as(C.c_void_p), crop.ctypes.data_as(C.c_void_p), f, blocks.ctypes.data_as(C.c_void_p), mv,
+                                            losses.ctypes.data_as(C.c_void_p))
+        return dict(zip(LOSS_NAMES, losses.tolist()))
+
     def step_clips_host_async(self, frames01, mask1, flip=None, maskValue=None):
         assert frames01.dtype == np.float32 and frames01.flags.c_contiguous and mask1.dtype == np.uint8 and mask1.flags.c_contiguous
         f = flip.ctypes.data_as(C.c_void_p) if flip is not None else None
