@@ -449,10 +449,24 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * N * h * w * (double)Cl * 16.0 * Csp;
     const int bstage = 4 * BN * 128, out_bytes = BN >= 64 ? 128 * BN * 2 * (BN >= 128 ? 1 : 2) : 0;
-    const int fixed = 1024 + 2 * p.patch_stride + out_bytes + 26 * 8 + 3 * BN * 4 + 64;
-    int stages = (SMEM_LIMIT - fixed) / bstage;
-    if (stages > 8) stages = 8;
-    REQUIRE(stages >= 2, "tc_dgrad_patch: shared memory too small (BN %d)", BN);
+    int npatch = 2, stages;
+    // thin outputs (3 / 12 channels): the weights of all phases are 8 KB per chunk -- resident for the whole CTA -- and the kernel is bound
+    // by the number of S patches (one HBM round trip each) in flight: as many patch buffers as shared memory holds (up to 6)
+    const bool resident = thin && p.n_tiles == 1 && 4 * p.chunks <= 8 && getenv("CENN_PATCH_NO_RESIDENT") == nullptr;
+    const int base_fixed = 1024 + out_bytes + 38 * 8 + 3 * BN * 4 + 64;
+    if (resident) {
+        stages = 4 * p.chunks;
+        npatch = (SMEM_LIMIT - base_fixed - stages * bstage) / p.patch_stride;
+        if (npatch > 6) npatch = 6;
+        REQUIRE(npatch >= 2, "tc_dgrad_patch: shared memory too small for two patches (thin)");
+    } else {
+        stages = (SMEM_LIMIT - base_fixed - 2 * p.patch_stride) / bstage;
+        if (stages > 8) stages = 8;
+        REQUIRE(stages >= 2, "tc_dgrad_patch: shared memory too small (BN %d)", BN);
+    }
+    p.npatch = npatch; p.b_resident = resident ? 1 : 0;
+    memcpy(pl->params, &p, sizeof(p));
+    const int fixed = base_fixed + npatch * p.patch_stride;
     pl->kind = 3; pl->BN = BN; pl->stages = stages;
     pl->smem = (size_t)stages * bstage + fixed;
     const int total = p.m_tiles * p.n_tiles;

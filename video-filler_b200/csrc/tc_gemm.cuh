@@ -634,6 +634,9 @@ struct PatchDgradParams {
     int m_tiles, n_tiles;        // tiles enumerated m fastest
     int tiles_x, tiles_y;        // m-tile -> (tx, ty, tn); box = 8 (x) x bn (samples) x bh (y)
     int bh, bn, bn_log2;
+    int npatch;                  // patch buffers in flight (2 .. 8): a patch is one HBM round trip, thin layers are bound by how many are in flight
+    int b_resident;              // 1: the weight taps of all phases and chunks fit the B stages and do not depend on the tile (one N tile):
+                                 //    loaded once per CTA, stage index = chunk * 4 + phase, never released
     int patch_bytes;             // TMA box bytes: 128 * 10 * bn * (bh + 2)
     int patch_stride;            // patch_bytes rounded up to 1024
     int a_off[4][4];             // byte offset of window (phase, tap ab) inside the patch
@@ -662,13 +665,14 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
     constexpr uint32_t OUT_BYTES = kTma ? 128u * BN * 2u : 0u; // one phase tile
     constexpr int NOUT = BN >= 128 ? 1 : 2;                    // staging buffers (BN = 128: shared memory allows one)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *patch = smem;                                                    // [2][patch_stride]
-    uint8_t *bst = patch + 2 * (size_t)p.patch_stride;                        // [stages][BSTAGE_BYTES]
+    const int npatch = p.npatch;
+    uint8_t *patch = smem;                                                    // [npatch][patch_stride]
+    uint8_t *bst = patch + (size_t)npatch * (size_t)p.patch_stride;           // [stages][BSTAGE_BYTES]
     uint8_t *out_stage = bst + (size_t)stages * BSTAGE_BYTES;                 // [NOUT][OUT_BYTES]
     uint64_t *bars = reinterpret_cast<uint64_t *>(out_stage + NOUT * OUT_BYTES);
-    uint64_t *pfull = bars, *pempty = bars + 2, *bfull = bars + 4, *bempty = bars + 12, *tfull = bars + 20, *tempty = bars + 22;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);            // +192 B
-    float *col_acc = reinterpret_cast<float *>(bars + 26);                    // [2][BN]
+    uint64_t *pfull = bars, *pempty = bars + 8, *bfull = bars + 16, *bempty = bars + 24, *tfull = bars + 32, *tempty = bars + 34;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 36);            // +288 B
+    float *col_acc = reinterpret_cast<float *>(bars + 38);                    // [2][BN]
     float *bias_s = col_acc + 2 * BN;                                         // [BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -678,7 +682,8 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmS); prefetch_tmap(&tmB);
         if (kTma) prefetch_tmap(&tmO);
-        for (int i = 0; i < 2; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], 1); mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < npatch; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], 1); }
         for (int i = 0; i < stages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
         fence_barrier_init();
     }
@@ -697,7 +702,9 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
             const uint32_t pfull_u32 = smem_u32(pfull), pempty_u32 = smem_u32(pempty), bfull_u32 = smem_u32(bfull), bempty_u32 = smem_u32(bempty);
             const int chunks = p.chunks, Csp = p.Csp, cl_rows = p.cl_rows;
             const bool b_mn = p.b_mn != 0;
+            const bool b_res = p.b_resident != 0;
             int pb = 0; uint32_t pph = 0; int s = 0; uint32_t ph = 0;
+            bool first = true;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
                 const int tn = mt / txy, rem = mt - tn * txy, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -706,10 +713,11 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
                     mbar_wait_u32(pempty_u32 + 8u * pb, pph ^ 1u);
                     mbar_expect_tx_u32(pfull_u32 + 8u * pb, (uint32_t)p.patch_bytes);
                     tma_load_4d_u32(&tmS, pfull_u32 + 8u * pb, patch_u32 + (uint32_t)pb * (uint32_t)p.patch_stride, c * 64, x0 - 1, n0, y0 - 1);
-                    if (++pb == 2) { pb = 0; pph ^= 1u; }
+                    if (++pb == npatch) { pb = 0; pph ^= 1u; }
+                    if (b_res && !first) continue;                      // resident weights: loaded with the first tile only
 #pragma unroll
                     for (int phs = 0; phs < 4; ++phs) {
-                        mbar_wait_u32(bempty_u32 + 8u * s, ph ^ 1u);
+                        if (b_res) s = c * 4 + phs; else mbar_wait_u32(bempty_u32 + 8u * s, ph ^ 1u);
                         const uint32_t fb = bfull_u32 + 8u * s, dst = bst_u32 + (uint32_t)s * BSTAGE_BYTES;
                         mbar_expect_tx_u32(fb, BSTAGE_BYTES);
                         const int brow = phs * cl_rows + nt * BN;
@@ -723,9 +731,10 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
 #pragma unroll
                             for (int ab = 0; ab < 4; ++ab) tma_load_2d_u32(&tmB, fb, dst + ab * BTAP_BYTES, ab * Csp + c * 64, brow);
                         }
-                        if (++s == stages) { s = 0; ph ^= 1u; }
+                        if (!b_res && ++s == stages) { s = 0; ph ^= 1u; }
                     }
                 }
+                first = false;
             }
         }
     } else if (warp == 1) {
@@ -743,7 +752,9 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 4; ++j) aoff[i][j] = (uint32_t)p.a_off[i][j] >> 4;
         const int chunks = p.chunks;
+        const bool b_res = p.b_resident != 0;
         int pb = 0; uint32_t pph = 0; int s = 0; uint32_t ph = 0; int set = 0; uint32_t set_ph = 0;
+        bool first = true;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             mbar_wait_u32(tempty_u32 + 8u * set, set_ph ^ 1u);
             tc_fence_after();
@@ -752,7 +763,8 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
                 const uint32_t a_base = patch_lo + (((uint32_t)pb * (uint32_t)p.patch_stride) >> 4);
 #pragma unroll
                 for (int phs = 0; phs < 4; ++phs) {
-                    mbar_wait_u32(bfull_u32 + 8u * s, ph);
+                    if (b_res) { s = c * 4 + phs; if (first) mbar_wait_u32(bfull_u32 + 8u * s, 0u); }
+                    else mbar_wait_u32(bfull_u32 + 8u * s, ph);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)((set * 4 + phs) * BN);
@@ -765,17 +777,18 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
                                 const uint64_t bd = ((uint64_t)hiB << 32) | (b_base + (uint32_t)ab * (BTAP_BYTES >> 4) + b_kstep * k);
                                 umma_f16(d_tmem, ad, bd, idesc, (c | ab | k) != 0);
                             }
-                        umma_commit_u32(bempty_u32 + 8u * s);
+                        if (!b_res) umma_commit_u32(bempty_u32 + 8u * s);
                         if (phs == 3) {
                             umma_commit_u32(pempty_u32 + 8u * pb);
                             if (c == chunks - 1) umma_commit_u32(tfull_u32 + 8u * set);
                         }
                     }
                     __syncwarp();
-                    if (++s == stages) { s = 0; ph ^= 1u; }
+                    if (!b_res && ++s == stages) { s = 0; ph ^= 1u; }
                 }
-                if (++pb == 2) { pb = 0; pph ^= 1u; }
+                if (++pb == npatch) { pb = 0; pph ^= 1u; }
             }
+            first = false;
             if (NSETS == 2) { set ^= 1; set_ph ^= (uint32_t)(set == 0); } else set_ph ^= 1u;
         }
     } else {
@@ -904,20 +917,27 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
                     float bv[16];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) bv[k] = (has_bias && k < ncols) ? __ldg(p.bias + k) : 0.f;
+                    // the two sub-pixel columns px = 0, 1 of one output row are adjacent in memory: one 16-byte (Clp = 4) or four 16-byte
+                    // (Clp = 16) stores per output row instead of two 8-byte / 32-byte halves
 #pragma unroll
-                    for (int phs = 0; phs < 4; ++phs) {
-                        const int py = phs >> 1, px = phs & 1;
-                        __nv_bfloat16 *o = p.out + (((long long)(n0 + rn) * p.H2 + 2 * (y0 + ry) + py) * p.W2 + 2 * (x0 + rx) + px) * Clp;
-                        uint32_t pk[8];
+                    for (int py = 0; py < 2; ++py) {
+                        uint32_t pk[2][8];
 #pragma unroll
-                        for (int k = 0; k < 16; k += 2) {
-                            float f0 = k < ncols ? apply_act(__uint_as_float(r4[phs][k]) + bv[k], act, act_param) : 0.f;
-                            float f1 = k + 1 < ncols ? apply_act(__uint_as_float(r4[phs][k + 1]) + bv[k + 1], act, act_param) : 0.f;
-                            __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-                            pk[k >> 1] = *reinterpret_cast<uint32_t *>(&h);
+                        for (int px = 0; px < 2; ++px)
+#pragma unroll
+                            for (int k = 0; k < 16; k += 2) {
+                                const int phs = py * 2 + px;
+                                float f0 = k < ncols ? apply_act(__uint_as_float(r4[phs][k]) + bv[k], act, act_param) : 0.f;
+                                float f1 = k + 1 < ncols ? apply_act(__uint_as_float(r4[phs][k + 1]) + bv[k + 1], act, act_param) : 0.f;
+                                __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                                pk[px][k >> 1] = *reinterpret_cast<uint32_t *>(&h);
+                            }
+                        __nv_bfloat16 *o = p.out + (((long long)(n0 + rn) * p.H2 + 2 * (y0 + ry) + py) * p.W2 + 2 * (x0 + rx)) * Clp;
+                        if (Clp == 4) *reinterpret_cast<uint4 *>(o) = make_uint4(pk[0][0], pk[0][1], pk[1][0], pk[1][1]);
+                        else {
+                            reinterpret_cast<uint4 *>(o)[0] = make_uint4(pk[0][0], pk[0][1], pk[0][2], pk[0][3]); reinterpret_cast<uint4 *>(o)[1] = make_uint4(pk[0][4], pk[0][5], pk[0][6], pk[0][7]);
+                            reinterpret_cast<uint4 *>(o)[2] = make_uint4(pk[1][0], pk[1][1], pk[1][2], pk[1][3]); reinterpret_cast<uint4 *>(o)[3] = make_uint4(pk[1][4], pk[1][5], pk[1][6], pk[1][7]);
                         }
-                        if (Clp == 4) *reinterpret_cast<uint2 *>(o) = make_uint2(pk[0], pk[1]);
-                        else { reinterpret_cast<uint4 *>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); reinterpret_cast<uint4 *>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]); }
                     }
                 }
             }
