@@ -18,6 +18,8 @@ struct XrCtx {
     unsigned long long *flags[XR_MAX_WORLD];    // flags[r][parity]: last epoch rank r has published
     unsigned long long *epoch;                  // this rank's exchange counter (device memory)
     int world, rank;
+    long long timeout_cycles;                   // a peer that has not published after this many SM cycles traps the kernel (CENN_XR_TIMEOUT_S, default 120 s:
+                                                // long enough for a rank that writes a checkpoint or stalls in its loader, short enough not to hang a box forever)
 };
 
 struct cenn_state {

@@ -138,6 +138,7 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
         bool ok = rc == 0;
         XrCtx x = {}, x2 = {};
         x.world = x2.world = world_size; x.rank = x2.rank = rank;
+        { const char *e = getenv("CENN_XR_TIMEOUT_S"); const double sec = e ? atof(e) : 120.0; x.timeout_cycles = x2.timeout_cycles = (long long)(sec * 2.0e9); }
         for (int r = 0; r < world_size && ok; ++r) {
             void *base = own;
             if (r != rank && cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }

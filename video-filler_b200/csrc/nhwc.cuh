@@ -43,6 +43,7 @@ __device__ __forceinline__ float act_bwd(float a, int act, float negval) {
 // NCHW (float or uint8) -> NHWC bf16 with Cp channels (pad lanes zero); one thread per pixel
 template <typename T>
 __global__ void __launch_bounds__(256) to_nhwc_kernel(const T *__restrict__ src, bf16 *__restrict__ dst, int N, int C, int HW, int Cp) {
+    pdl_trigger(); pdl_wait();
     int64_t total = (int64_t)N * HW;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int n = (int)(i / HW), pix = (int)(i - (int64_t)n * HW);
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) to_nhwc_kernel(const T *__restrict__ src,
 // fast path for 3-channel images (Cp == 4, HW % 4 == 0): one thread converts 4 consecutive pixels -- float4 loads per
 // channel plane, two 16-byte stores
 __global__ void __launch_bounds__(256) to_nhwc4_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, int N, int C, int HW) {
+    pdl_trigger(); pdl_wait();
     const int64_t total = (int64_t)N * HW / 4;
     const int q = HW / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -173,6 +175,7 @@ __global__ void bn_finalize_kernel(float *__restrict__ stats, int stats_stride, 
         const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
         float *__restrict__ invstd, float *__restrict__ scale, float *__restrict__ shift, int C, double n, double momentum, double eps,
         int update_running) {
+    pdl_trigger(); pdl_wait();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     bn_finalize_channel(stats, stats_stride, fold, fold_stride, gamma, beta, running_mean, running_var, mean, invstd, scale, shift, c, n, momentum, eps, update_running);
@@ -219,7 +222,7 @@ __device__ void xr_sum_inplace(float *__restrict__ buf, int n, const XrCtx &x) {
 #pragma unroll
             for (int r = 0; r < XR_MAX_WORLD; ++r)
                 if (pending & (1u << r)) { v[r] = ld_ll(reinterpret_cast<const uint2 *>(x.data[r]) + slot + i); if (v[r].y == tag) pending &= ~(1u << r); }
-            if (clock64() - t0 > 240000000000LL) { printf("cenn: peer exchange timeout (rank %d, exchange %llu, pending mask %x)\n", x.rank, e, pending); __trap(); }
+            if (clock64() - t0 > x.timeout_cycles) { printf("cenn: peer exchange timeout (rank %d, exchange %llu, pending mask %x)\n", x.rank, e, pending); __trap(); }
         }
         float acc = 0.f;                                 // rank order: every replica adds in the same order -> bit-identical sums
 #pragma unroll
@@ -233,6 +236,7 @@ __device__ void xr_sum_inplace(float *__restrict__ buf, int n, const XrCtx &x) {
 __global__ void __launch_bounds__(1024) bn_finalize_xr_kernel(const XrCtx x, float *__restrict__ stats, int stats_stride, int fold, int fold_stride, float *__restrict__ cmp,
         const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ mean,
         float *__restrict__ invstd, float *__restrict__ scale, float *__restrict__ shift, int C, int Cp, double n, double momentum, double eps) {
+    pdl_wait();      // NO early trigger: this kernel spins on its peers; a successor launched early would hold SM slots while it waits (cross-rank deadlock)
     // fold the column groups (G1: 16 taps per channel) locally first: the exchange carries 2*Cp floats
     for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
         float s1 = 0.f, s2 = 0.f;
@@ -250,7 +254,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_xr_kernel(const XrCtx x, flo
 }
 // BN backward sums [2][Cp] (already folded over this rank's CTAs): exchange + coefficients + affine gradients
 __global__ void __launch_bounds__(1024) bn_bwd_coef_xr_kernel(const XrCtx x, float *__restrict__ sums, int Cp, const float *__restrict__ gamma, const float *__restrict__ invstd,
-        const float *__restrict__ mean, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n, float grad_scale) {
+        const float *__restrict__ mean, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n, float grad_scale, int zero_after) {
+    pdl_wait();      // NO early trigger: this kernel spins on its peers; a successor launched early would hold SM slots while it waits (cross-rank deadlock)
     xr_sum_inplace(sums, 2 * Cp, x);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double s = sums[c], d = sums[Cp + c];
@@ -258,6 +263,10 @@ __global__ void __launch_bounds__(1024) bn_bwd_coef_xr_kernel(const XrCtx x, flo
         coef[c] = (float)A; coef[C + c] = (float)(A * k1); coef[2 * C + c] = (float)(((double)mean[c] * k1 - s / n) * A);
         if (ggamma) ggamma[c] += (float)(d * is) * grad_scale;
         if (gbeta) gbeta[c] += (float)s * grad_scale;
+    }
+    if (zero_after) {                      // `sums` is the accumulator bn_bwd_reduce2_kernel<ACT, true> adds into: ready for its next use
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * Cp; i += blockDim.x) sums[i] = 0.f;
     }
 }
 __global__ void bn_eval_coef_kernel(const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ running_mean,
@@ -450,6 +459,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce2_kernel(const bf16 *__re
 //   g_y = dz * A - y * B + D  with  A = invstd*gamma, B = A * invstd^2 * d/n, D = (mean * invstd^2 * d/n - s/n) * A
 __global__ void __launch_bounds__(256) bn_bwd_coef2_kernel(const float *__restrict__ part, int rows, float *__restrict__ sums_io, int Cp, const float *__restrict__ gamma,
         const float *__restrict__ invstd, const float *__restrict__ mean, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n, int emit_coef, float grad_scale) {
+    pdl_trigger(); pdl_wait();
     __shared__ float sh_s[8][33], sh_d[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
     float s0 = 0.f, d0 = 0.f, s1 = 0.f, d1 = 0.f;
@@ -746,9 +756,10 @@ __global__ void __launch_bounds__(256, 4) act_bwd2_kernel(bf16 *__restrict__ g, 
 }
 // dst[c] += sum_r src[r][c] for a list of jobs (one CTA per job): folds the per-CTA partial rows of a whole backward sweep
 struct FoldJob { const float *src; float *dst; int rows, C, stride, fold, fold_stride; };   // fold > 1: column c also sums columns c + k*fold_stride (k < fold)
-__global__ void __launch_bounds__(256) fold_rows_kernel(const FoldJob *__restrict__ jobs) {
+__global__ void __launch_bounds__(1024) fold_rows_kernel(const FoldJob *__restrict__ jobs) {
     pdl_trigger(); pdl_wait();
-    __shared__ float sh[8][33];
+    // 32 channels x 32 row lanes per CTA: the row walk is a chain of dependent L2 loads, so its length (rows / 32) is what costs
+    __shared__ float sh[32][33];
     const FoldJob j = jobs[blockIdx.x];
     const int tx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     for (int c0 = blockIdx.y * 32; c0 < j.C; c0 += gridDim.y * 32) {      // uniform per CTA
@@ -758,7 +769,7 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(const FoldJob *__restric
             for (int f = 0; f < j.fold; ++f) {
                 const float *q = j.src + c + f * j.fold_stride;
                 int r = ry;
-                for (; r + 8 < j.rows; r += 16) { s0 += q[(size_t)r * j.stride]; s1 += q[(size_t)(r + 8) * j.stride]; }
+                for (; r + 32 < j.rows; r += 64) { s0 += q[(size_t)r * j.stride]; s1 += q[(size_t)(r + 32) * j.stride]; }
                 if (r < j.rows) s0 += q[(size_t)r * j.stride];
             }
         }
@@ -766,7 +777,7 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(const FoldJob *__restric
         __syncthreads();
         if (ry == 0 && c < j.C) { float t = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t += sh[i][tx];
+            for (int i = 0; i < 32; ++i) t += sh[i][tx];
             j.dst[c] += t; }
         __syncthreads();
     }
@@ -919,6 +930,7 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float *__restrict
 __global__ void __launch_bounds__(256) blend_overlap_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
         bf16 *__restrict__ g, int64_t npix, int H, int W, int Cp, int C, int ov, float a, float w_in, float w_ring, float two_over_n,
         double inv_n, double *__restrict__ loss_acc) {
+    pdl_trigger(); pdl_wait();
     __shared__ double sh[32];
     double l = 0.0;
     int64_t total = npix * Cp;
@@ -973,6 +985,7 @@ __global__ void __launch_bounds__(256) blend_overlap4_kernel(const bf16 *__restr
 __global__ void __launch_bounds__(256) blend_masked_kernel(const bf16 *__restrict__ df, const bf16 *__restrict__ x, const bf16 *__restrict__ t,
         const bf16 *__restrict__ mask, bf16 *__restrict__ g, int64_t total, int Cp, int C, float a, float wtl2, float lambda, float wtgdl,
         float two_over_n, double inv_n, double *__restrict__ loss_acc) {
+    pdl_trigger(); pdl_wait();
     __shared__ double sh[32];
     double l = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1024,6 +1037,7 @@ __global__ void __launch_bounds__(256) composite_kernel(bf16 *__restrict__ dst, 
 // GDL loss (forward only: the scripts add criterionMSE:backward as its gradient, train_vid_weighted.lua:525), flat-index pairing
 __global__ void __launch_bounds__(256) gdl_loss_kernel(const bf16 *__restrict__ inp, const bf16 *__restrict__ tgt, int64_t N, int H, int W, int Cp, int C,
         double inv_n, double *__restrict__ loss_acc) {
+    pdl_trigger(); pdl_wait();
     __shared__ double sh[32];
     const int NK = H * (W - 1);
     double l = 0.0;
@@ -1108,6 +1122,7 @@ __global__ void __launch_bounds__(256) adam_bf16_kernel(float *__restrict__ x, c
 // Adam with the gradient read from a bf16 bucket (data parallel: the big generator blocks are all-reduced in bf16)
 __global__ void __launch_bounds__(256) adam_bf16g_kernel(float *__restrict__ x, const bf16 *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
         bf16 *__restrict__ xb, int64_t n, float b1, float b2, float eps, const float *__restrict__ step_ptr) {
+    pdl_trigger(); pdl_wait();
     const float step = *step_ptr;
     int64_t n4 = n / 4;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (int64_t)gridDim.x * blockDim.x) {
@@ -1208,6 +1223,7 @@ __global__ void fold_bn_bias_kernel(const float *__restrict__ bias, const float 
 template <int CP>
 __global__ void __launch_bounds__(256) clip_prepare_kernel(const float *__restrict__ frames01, const uint8_t *__restrict__ mask1, const uint8_t *__restrict__ flip,
         float maskValue, int N, int C, int H, int W, bf16 *__restrict__ masked, bf16 *__restrict__ full, bf16 *__restrict__ maskx) {
+    pdl_trigger(); pdl_wait();
     const int HW = H * W;
     const int64_t total = (int64_t)N * HW;
     const float fillv = 2.f * maskValue - 1.f;

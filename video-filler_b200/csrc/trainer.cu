@@ -607,13 +607,13 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
                 // data parallel: the statistics cross NVLink inside the finalize kernel (peer mailboxes), no collective launch
                 const int chain = t->emit_chain;
                 emit(t, "bn_finalize_xr", [t, s, b, gamma, beta, n_global, chain]() {
-                    nhwc::bn_finalize_xr_kernel<<<1, 1024, 0, s->stream>>>((chain == 1 && !t->serial) ? s->xr2 : s->xr, b->stats, b->stats_cols, b->fold, b->Coutp, b->bsums, gamma, beta,
+                    LK(nhwc::bn_finalize_xr_kernel, dim3(1), dim3(1024), 0, s->stream)((chain == 1 && !t->serial) ? s->xr2 : s->xr, b->stats, b->stats_cols, b->fold, b->Coutp, b->bsums, gamma, beta,
                         b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, b->Coutp, n_global, 0.1, 1e-5);
                     KLAUNCH(s); return 0; });
             } else {
             emit(t, "bn_stats_sync", []() { return 0; }, b->stats, 2 * (int64_t)b->stats_cols);
             emit(t, "bn_finalize", [s, b, gamma, beta, n_global]() {
-                nhwc::bn_finalize_kernel<<<(b->Cout + 127) / 128, 128, 0, s->stream>>>(b->stats, b->stats_cols, b->fold, b->Coutp, gamma, beta,
+                LK(nhwc::bn_finalize_kernel, dim3((b->Cout + 127) / 128), dim3(128), 0, s->stream)(b->stats, b->stats_cols, b->fold, b->Coutp, gamma, beta,
                     b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, n_global, 0.1, 1e-5, 1);
                 KLAUNCH(s); return 0; });
             }
@@ -680,9 +680,12 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         // and the step got 4 % SLOWER (3.29 vs 3.15 ms), so the three-launch chain stays the default.
         static const bool two_launch_env = getenv("CENN_BN_BWD_2LAUNCH") != nullptr && atoi(getenv("CENN_BN_BWD_2LAUNCH")) != 0;
         const bool two_launch = !dp && two_launch_env;
-        emit(t, "bn_bwd_reduce", [s, b, npix, vpp, two_launch]() {
+        // data parallel with peer mailboxes: the local sums are accumulated by fp32 atomics straight into the exchange buffer (no fold launch);
+        // replicas stay bit-identical because every rank adds the same published values in rank order
+        const bool dp_atomic = dp && s->xr_enabled && 2 * b->Coutp <= XR_MAXF && getenv("CENN_DP_BN_FOLD") == nullptr;
+        emit(t, "bn_bwd_reduce", [s, b, npix, vpp, two_launch, dp_atomic]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
-            if (two_launch) {
+            if (two_launch || dp_atomic) {
                 auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_LEAKY, true> : nhwc::bn_bwd_reduce2_kernel<nhwc::ACT_RELU, true>;
                 LK(kern, dim3(dim3(b->red_rows, gy)), dim3(blk), 2 * blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->y.p, b->scale, b->shift, b->mean,
                     b->bsums, b->Coutp, npix, vpp, b->Cout, 0.2f);
@@ -702,25 +705,30 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
                 KLAUNCH(s); return 0; });
             t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;        // read g, y; write g_y
         } else {
-        if (dp && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {   // fold this rank's partial rows, then exchange + coefficients in one kernel
+        if (dp_atomic) {
+            const float inv_world = 1.f / (float)t->cfg.world_size;
+            emit(t, "bn_bwd_coef_xr", [s, b, gamma, gg, gbeta, n_global, inv_world]() {
+                LK(nhwc::bn_bwd_coef_xr_kernel, dim3(1), dim3(1024), 0, s->stream)(s->xr, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, inv_world, 1);
+                KLAUNCH(s); return 0; });
+        } else if (dp && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {   // fold this rank's partial rows, then exchange + coefficients in one kernel
             const float inv_world = 1.f / (float)t->cfg.world_size;
             emit(t, "bn_bwd_fold", [s, b]() {
-                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0, 1.f);
+                LK(nhwc::bn_bwd_coef2_kernel, dim3((b->Cout + 31) / 32), dim3(dim3(32, 8)), 0, s->stream)(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0, 1.f);
                 KLAUNCH(s); return 0; });
             emit(t, "bn_bwd_coef_xr", [s, b, gamma, gg, gbeta, n_global, inv_world]() {
-                nhwc::bn_bwd_coef_xr_kernel<<<1, 1024, 0, s->stream>>>(s->xr, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, inv_world);
+                LK(nhwc::bn_bwd_coef_xr_kernel, dim3(1), dim3(1024), 0, s->stream)(s->xr, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, inv_world, 0);
                 KLAUNCH(s); return 0; });
         } else if (dp) {   // fold the partial rows into bsums, all-reduce bsums across ranks, then the coefficients
             emit(t, "bn_bwd_fold", [s, b]() {
-                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0, 1.f);
+                LK(nhwc::bn_bwd_coef2_kernel, dim3((b->Cout + 31) / 32), dim3(dim3(32, 8)), 0, s->stream)(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0, 1.f);
                 KLAUNCH(s); return 0; }, b->bsums, 2 * (int64_t)b->Coutp);
             const float inv_world = 1.f / (float)t->cfg.world_size;
             emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global, inv_world]() {
-                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(nullptr, 0, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1, inv_world);
+                LK(nhwc::bn_bwd_coef2_kernel, dim3((b->Cout + 31) / 32), dim3(dim3(32, 8)), 0, s->stream)(nullptr, 0, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1, inv_world);
                 KLAUNCH(s); return 0; });
         } else {
             emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
-                nhwc::bn_bwd_coef2_kernel<<<(b->Cout + 31) / 32, dim3(32, 8), 0, s->stream>>>(b->part, b->part_rows, nullptr, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1, 1.f);
+                LK(nhwc::bn_bwd_coef2_kernel, dim3((b->Cout + 31) / 32), dim3(dim3(32, 8)), 0, s->stream)(b->part, b->part_rows, nullptr, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1, 1.f);
                 KLAUNCH(s); return 0; });
         }
         emit(t, "bn_bwd_apply", [s, b, gb_part, npix, vpp]() {
@@ -836,7 +844,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
                 st = t->side3;
             }
             if (dp_bulk && n->gradbf && cnt % 4 == 0)
-                nhwc::adam_bf16g_kernel<<<grid1d(s, cnt / 4), 256, 0, st>>>(n->master + off, n->gradbf + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
+                LK(nhwc::adam_bf16g_kernel, dim3(grid1d(s, cnt / 4)), dim3(256), 0, st)(n->master + off, n->gradbf + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
             else
             LK(nhwc::adam_bf16_kernel, dim3(grid1d(s, cnt / 4)), dim3(256), 0, st)(n->master + off, n->grad + off, n->m + off, n->v + off, n->wbf + off, cnt, beta1, 0.999f, 1e-8f, n->adam_step);
             KLAUNCH(s); return 0; });
@@ -880,7 +888,7 @@ void emit_fold_gbias(T *t, Net &net) {
             return cenn_check_cuda(cudaStreamWaitEvent(s->stream, evj, 0), "stream wait", __FILE__, __LINE__); });
     }
     emit(t, "fold_gbias", [s, n]() {
-        LK(nhwc::fold_rows_kernel, dim3(dim3((unsigned)n->fold_host.size(), 8)), dim3(256), 0, s->stream)(n->fold_jobs); KLAUNCH(s); return 0; });
+        LK(nhwc::fold_rows_kernel, dim3((unsigned)n->fold_host.size(), 8), dim3(1024), 0, s->stream)(n->fold_jobs); KLAUNCH(s); return 0; });
 }
 void emit_zero_grad(T *t, Net &net) {
     cenn_state *s = t->s;
@@ -966,8 +974,8 @@ int build_program(T *t) {
         if (video && !t->cur_a) {       // clip mode: masked / full / expanded mask derived on the device from the frames and one mask plane
             const Tensor &m = t->mask;
             const float mv = t->clip_mv;
-            if (a.Cp == 16) nhwc::clip_prepare_kernel<16><<<grid1d(s, a.pix()), 256, 0, s->stream>>>(t->cur_b, t->cur_m, t->cur_f, mv, a.N, a.C, a.H, a.W, a.p, b.p, m.p);
-            else if (a.Cp == 4) nhwc::clip_prepare_kernel<4><<<grid1d(s, a.pix()), 256, 0, s->stream>>>(t->cur_b, t->cur_m, t->cur_f, mv, a.N, a.C, a.H, a.W, a.p, b.p, m.p);
+            if (a.Cp == 16) LK(nhwc::clip_prepare_kernel<16>, dim3(grid1d(s, a.pix())), dim3(256), 0, s->stream)(t->cur_b, t->cur_m, t->cur_f, mv, a.N, a.C, a.H, a.W, a.p, b.p, m.p);
+            else if (a.Cp == 4) LK(nhwc::clip_prepare_kernel<4>, dim3(grid1d(s, a.pix())), dim3(256), 0, s->stream)(t->cur_b, t->cur_m, t->cur_f, mv, a.N, a.C, a.H, a.W, a.p, b.p, m.p);
             else { cenn_set_error("clip mode: unsupported channel padding %d", a.Cp); return 1; }
             KLAUNCH(s);
             return cenn_check_cuda(cudaMemsetAsync(t->loss_acc, 0, 8 * sizeof(double), s->stream), "memset", __FILE__, __LINE__);
@@ -975,12 +983,12 @@ int build_program(T *t) {
         for (const Tensor *x : {&a, &b}) {
             const float *src = x == &a ? t->cur_a : t->cur_b;
             if (x->Cp == 4 && (x->H * x->W) % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
-                nhwc::to_nhwc4_kernel<<<grid1d(s, x->pix() / 4), 256, 0, s->stream>>>(src, x->p, x->N, x->C, x->H * x->W);
+                LK(nhwc::to_nhwc4_kernel, dim3(grid1d(s, x->pix() / 4)), dim3(256), 0, s->stream)(src, x->p, x->N, x->C, x->H * x->W);
             else
-                nhwc::to_nhwc_kernel<float><<<grid1d(s, x->pix()), 256, 0, s->stream>>>(src, x->p, x->N, x->C, x->H * x->W, x->Cp);
+                LK(nhwc::to_nhwc_kernel<float>, dim3(grid1d(s, x->pix())), dim3(256), 0, s->stream)(src, x->p, x->N, x->C, x->H * x->W, x->Cp);
             KLAUNCH(s);
         }
-        if (video) { const Tensor &m = t->mask; nhwc::to_nhwc_kernel<uint8_t><<<grid1d(s, m.pix()), 256, 0, s->stream>>>(t->cur_m, m.p, m.N, m.C, m.H * m.W, m.Cp); KLAUNCH(s); }
+        if (video) { const Tensor &m = t->mask; LK(nhwc::to_nhwc_kernel<uint8_t>, dim3(grid1d(s, m.pix())), dim3(256), 0, s->stream)(t->cur_m, m.p, m.N, m.C, m.H * m.W, m.Cp); KLAUNCH(s); }
         return cenn_check_cuda(cudaMemsetAsync(t->loss_acc, 0, 8 * sizeof(double), s->stream), "memset", __FILE__, __LINE__); });
     // ================= fDx (train.lua:278-350) =================
     emit_zero_bias(t, D); emit_zero_bias(t, G);
@@ -1072,7 +1080,7 @@ int build_program(T *t) {
                         LK(nhwc::blend_overlap4_kernel, dim3(grid1d(s, fake_in.pix() / 2, 256, 4)), dim3(256), 0, s->stream)(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
                             fake_in.W, fake_in.C, ov, a, w_in, w_ring, (float)(2.0 / n), 1.0 / n, acc);
                     else
-                    nhwc::blend_overlap_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
+                    LK(nhwc::blend_overlap_kernel, dim3(grid1d(s, fake_in.elems(), 256, 4)), dim3(256), 0, s->stream)(df.p, fake_in.p, real.p, gout.p, fake_in.pix(), fake_in.H,
                         fake_in.W, fake_in.Cp, fake_in.C, ov, a, w_in, w_ring, (float)(2.0 / n), 1.0 / n, acc);
                     KLAUNCH(s); return 0; });
                 t->prog.back().bytes = 4.0 * 2.0 * (double)fake_in.pix() * fake_in.C;   // read df, x, t; write df (edge weight from indices)
@@ -1087,7 +1095,7 @@ int build_program(T *t) {
                     if (fake_in.Cp == 16) LK(nhwc::gdl_loss_vec_kernel<16>, dim3(grid1d(s, pairs, 256, 4)), dim3(256), 0, s->stream)(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.C, 1.0 / ngdl, gacc);
                     else if (fake_in.Cp == 4) LK(nhwc::gdl_loss_vec_kernel<4>, dim3(grid1d(s, pairs, 256, 4)), dim3(256), 0, s->stream)(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.C, 1.0 / ngdl, gacc);
                     else
-                    nhwc::gdl_loss_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.Cp, fake_in.C, 1.0 / ngdl, gacc);
+                    LK(nhwc::gdl_loss_kernel, dim3(grid1d(s, fake_in.elems(), 256, 4)), dim3(256), 0, s->stream)(fake_in.p, real.p, fake_in.N, fake_in.H, fake_in.W, fake_in.Cp, fake_in.C, 1.0 / ngdl, gacc);
                     KLAUNCH(s); return 0; });
             }
             emit(t, "blend_masked", [s, df, fake_in, real, mk, gout, a, wtl2, lam, wtgdl, n, acc]() {
@@ -1095,7 +1103,7 @@ int build_program(T *t) {
                     LK(nhwc::blend_masked8_kernel, dim3(grid1d(s, fake_in.elems() / 8, 256, 4)), dim3(256), 0, s->stream)(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems() / 8, fake_in.Cp / 8, fake_in.C,
                         a, wtl2, lam, wtgdl, (float)(2.0 / n), 1.0 / n, acc);
                 else
-                nhwc::blend_masked_kernel<<<grid1d(s, fake_in.elems(), 256, 4), 256, 0, s->stream>>>(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems(), fake_in.Cp, fake_in.C,
+                LK(nhwc::blend_masked_kernel, dim3(grid1d(s, fake_in.elems(), 256, 4)), dim3(256), 0, s->stream)(df.p, fake_in.p, real.p, mk.p, gout.p, fake_in.elems(), fake_in.Cp, fake_in.C,
                     a, wtl2, lam, wtgdl, (float)(2.0 / n), 1.0 / n, acc);
                 KLAUNCH(s); return 0; });
             t->prog.back().bytes = 5.0 * 2.0 * (double)fake_in.pix() * fake_in.C;   // read df, x, t, mask; write df
@@ -1728,7 +1736,7 @@ int cenn_trainer_generator_forward_host(cenn_trainer *t, const float *in, float 
     int64_t n_in = (int64_t)batch * gi.C * gi.H * gi.W;
     CK(cudaMemsetAsync(t->in_a, 0, t->n_a * 4, s->stream));
     CK(cudaMemcpyAsync(t->in_a, in, n_in * 4, cudaMemcpyHostToDevice, s->stream));
-    nhwc::to_nhwc_kernel<float><<<grid1d(s, gi.pix()), 256, 0, s->stream>>>(t->in_a, gi.p, gi.N, gi.C, gi.H * gi.W, gi.Cp);
+    LK(nhwc::to_nhwc_kernel<float>, dim3(grid1d(s, gi.pix())), dim3(256), 0, s->stream)(t->in_a, gi.p, gi.N, gi.C, gi.H * gi.W, gi.Cp);
     KLAUNCH(s);
     size_t mark = t->prog.size();
     for (size_t i = 0; i < G.blocks.size(); ++i) emit_forward(t, G, i, false);
@@ -1818,8 +1826,8 @@ int inpainter_build_program(cenn_inpainter *p) {
         if (!t->cur_a) return 0;
         const Tensor &gi = t->G.input;
         const int n = t->infer_n;
-        if (gi.Cp == 4 && (gi.H * gi.W) % 4 == 0) nhwc::to_nhwc4_kernel<<<grid1d(s, (int64_t)n * gi.H * gi.W / 4), 256, 0, s->stream>>>(t->cur_a, gi.p, n, gi.C, gi.H * gi.W);
-        else nhwc::to_nhwc_kernel<float><<<grid1d(s, (int64_t)n * gi.H * gi.W), 256, 0, s->stream>>>(t->cur_a, gi.p, n, gi.C, gi.H * gi.W, gi.Cp);
+        if (gi.Cp == 4 && (gi.H * gi.W) % 4 == 0) LK(nhwc::to_nhwc4_kernel, dim3(grid1d(s, (int64_t)n * gi.H * gi.W / 4)), dim3(256), 0, s->stream)(t->cur_a, gi.p, n, gi.C, gi.H * gi.W);
+        else LK(nhwc::to_nhwc_kernel<float>, dim3(grid1d(s, (int64_t)n * gi.H * gi.W)), dim3(256), 0, s->stream)(t->cur_a, gi.p, n, gi.C, gi.H * gi.W, gi.Cp);
         KLAUNCH(s); return 0; });
     for (size_t i = 0; i < G.blocks.size(); ++i) {
         Block *b = &G.blocks[i];
