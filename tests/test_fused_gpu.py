@@ -585,3 +585,23 @@ def test_frame_mode_step_runs_the_loader_hook_on_the_device(cenn):
     for k, tol in (("errG_l2", 2e-3), ("errG_gdl", 2e-3), ("errD", 5e-3), ("errG", 4e-2)):
         assert abs(l0[k] - l1[k]) <= tol * max(abs(l0[k]), 1e-3), (k, l0[k], l1[k])
     assert _cos(g0, g1) >= 0.97
+
+
+def test_fused_wide_net_at_the_real_bottleneck(cenn, fast_oracle):
+    """train_wholeim_input.lua:40-43 as shipped: nef = ngf = 192, ndf = 128, nBottleneck 6400 (VERDICT r1 missing 3: the wide net had only
+    been run at nBottleneck 640).  fp32 oracle (330 M generator parameters), two samples."""
+    from video_filler_b200 import models, train
+    kw = dict(batchSize=2, nBottleneck=6400, nef=192, ngf=192, ndf=128, predLen=1, weight_nomask=1.0)
+    orc = ostep.StepOracle(onets.default_opt("video", **kw), seed=77, dtype=np.float32)
+    trn = train.FusedTrainer(models.default_opt("video", **kw), precision="bf16")
+    assert trn.param_count(0) == orc.pG.size and trn.param_count(1) == orc.pD.size
+    trn.set_params(0, orc.pG); trn.set_params(1, orc.pD)
+    batch = orc.synth_batch(np.random.default_rng(5))
+    lo, lg = orc.step(*batch), trn.step_host(*batch)
+    for k in ("errD_real", "errG_l2", "errG_total"):
+        assert lg[k] == pytest.approx(lo[k], rel=2e-2), k
+    for k in ("errD_fake", "errD", "errG"):
+        assert lg[k] == pytest.approx(lo[k], rel=8e-2), k          # BatchNorm over two samples at the bottleneck
+    gG = trn.get_grads(0)
+    assert np.all(np.isfinite(gG)) and _cos(gG, orc.gG) >= 0.9
+    trn.close()
