@@ -425,13 +425,41 @@ def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, v
         if dist:
             dist.barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        e2e_u8_ms = None
+        if not video:
+            # the same end-to-end loop from DECODED BYTES (cenn_trainer_step_images_u8_host_async): what the image loader holds before its
+            # division by 255; rescale, centre clone and mean fill (train.lua:286-290) run on the device
+            u8 = []
+            for _ in range(n_batches):
+                img = drng.integers(0, 256, (B, 3, 128, 128)).astype(np.uint8)
+                pu = pin(img.nbytes)
+                hu = np.ctypeslib.as_array((C.c_uint8 * img.size).from_address(pu.value)); hu[:] = img.ravel()
+                u8.append(hu)
+            for i in range(4):
+                trn.step_images_u8_host_async(u8[i % n_batches])
+                if i > 0:
+                    trn.wait_losses()
+            trn.wait_losses()
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                trn.step_images_u8_host_async(u8[i % n_batches])
+                if i > 0:
+                    trn.wait_losses()
+            trn.wait_losses()
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            e2e_u8_ms = (time.perf_counter() - t0) * 1e3
         # ---- per-op CUDA-event profile for the rooflines of the dominant kernels (every rank runs it: it contains the exchanges)
         prof = trn.profile_step(host[0][2].ptr, host[0][3].ptr, host[0][6], repeats=3) if want_profile else None
         torch.cuda.synchronize()
-    t_ms = torch.tensor([ms, e2e_ms], device="cuda")
+    t_ms = torch.tensor([ms, e2e_ms, e2e_u8_ms if e2e_u8_ms is not None else 0.0], device="cuda")
     if dist:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    out = {"ms": float(t_ms[0].item()), "e2e_ms": float(t_ms[1].item()), "losses": losses, "launches": int(launches1.value - launches0.value),
+    out = {"ms": float(t_ms[0].item()), "e2e_ms": float(t_ms[1].item()), "e2e_u8_ms": float(t_ms[2].item()) if e2e_u8_ms is not None else None, "losses": losses, "launches": int(launches1.value - launches0.value),
            "clocks": clocks, "prof": prof, "h2d_bytes": int(host[0][4]), "nG": nG, "nD": nD, "B": B, "steps": steps}
     # the step's CUDA graph holds the NCCL communicator: release the executor (and this workload's buffers) before anything else
     trn.close()
@@ -608,7 +636,11 @@ def main():
         "step_frac_of_bf16_sustained": gflop_per_sample * 1e-3 * value / (tf_sus * world),
         "step_frac_of_bf16_burst": gflop_per_sample * 1e-3 * value / (tf_burst * world),
     }
-    line["e2e"] = {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": 32}
+    line["e2e"] = {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": 32,
+                   "call": "cenn_trainer_step_clips_host_async (frames + one mask plane per clip)" if video else "cenn_trainer_step_host_async (the loader's FloatTensor batches: real_ctx + real_center)"}
+    if m.get("e2e_u8_ms"):
+        line["e2e_bytes"] = {"value": B * world * args.steps / (m["e2e_u8_ms"] / 1e3), "unit": "samples/s", "h2d_bytes_per_step": B * 3 * 128 * 128, "d2h_bytes_per_step": 32,
+                             "call": "cenn_trainer_step_images_u8_host_async (decoded bytes in; rescale, centre clone and mean fill on the device)"}
     if vid is not None:
         vvalue = 64 * world * args.steps / (vid["ms"] / 1e3)
         line["video"] = {"workload": WORKLOAD_VIDEO % (args.wtgdl, 64), "value": vvalue, "unit": "samples/s", "ms_per_step": vid["ms"] / args.steps,

@@ -268,6 +268,11 @@ CENN_API int cenn_trainer_step_clips_host_async(cenn_trainer *t, const float *fr
  * the hook's RANDOM DRAWS stay on the host and arrive as tables: crop[b] = (h1, w1) 0-based top-left of the fineSize crop (:149-151),
  * flip[b] (:172), blocks[b] = (count <= 10, tlx_0, tly_0, ...) 0-based inside the crop, block side floor(fineSize / 6), used when the
  * mask crop is all black (:114-129,163-168).  The sample-rejection rule (:152-157) is loader policy and stays with the caller. */
+/* Byte-image steps (image variant): images_u8 [B][3][fineSize][fineSize] = the loader's crop as decoded bytes (image.load yields byte / 255,
+ * data/donkey_folder.lua:70-88 then rescales to [-1,1]); the device rescales, clones the centre (real_center) and mean-fills it
+ * (real_ctx), train.lua:286-290.  12.6 MB of H2D per 256-sample step instead of 62.9 MB.  The async form pipelines like step_host_async. */
+CENN_API int cenn_trainer_step_images_u8_host(cenn_trainer *t, const uint8_t *images_u8_host, float *losses_host);
+CENN_API int cenn_trainer_step_images_u8_host_async(cenn_trainer *t, const uint8_t *images_u8_host);
 CENN_API int cenn_trainer_step_frames_host(cenn_trainer *t, const uint8_t *frames_u8_host, int iH, int iW, const uint8_t *mask_full_host,
         const int *crop_host, const uint8_t *flip_host, const int *blocks_host, float maskValue, float *losses_host);
 /* eval-mode generator forward (test_vid_wholeim.lua:180, demo.lua:68): in [B,Cin,F,F] -> out, host fp32 NCHW */

@@ -429,6 +429,10 @@ int cenn_trainer_get_bn_stats_host(cenn_trainer *t, int net, float *stats_host);
 int cenn_trainer_step_host(cenn_trainer *t, const float *a_host, const float *b_host, const uint8_t *mask_host, float *losses_host);
 int cenn_trainer_step_host_async(cenn_trainer *t, const float *a_host, const float *b_host, const uint8_t *mask_host);
 int cenn_trainer_wait_losses(cenn_trainer *t, float *losses_host);
+int cenn_trainer_step_clips_host(cenn_trainer *t, const float *frames01_host, const uint8_t *mask1_host, const uint8_t *flip_host, float maskValue, float *losses_host);
+int cenn_trainer_step_frames_host(cenn_trainer *t, const uint8_t *frames_u8_host, int iH, int iW, const uint8_t *mask_full_host,
+    const int *crop_host, const uint8_t *flip_host, const int *blocks_host, float maskValue, float *losses_host);
+int cenn_trainer_step_images_u8_host(cenn_trainer *t, const uint8_t *images_u8_host, float *losses_host);
 typedef struct cenn_inpainter cenn_inpainter;
 typedef struct cenn_inpainter_config { int variant, batch, fineSize, nBottleneck, nef, ngf, nc, inputLen; } cenn_inpainter_config;
 int cenn_inpainter_create(cenn_state *s, const cenn_inpainter_config *cfg, cenn_inpainter **out);
@@ -464,6 +468,22 @@ end
 -- one G+D step; returns errD, errG, errG_l2 as printed at train.lua:443-450 (host FloatTensors in, like the data loader delivers them)
 function Trainer:step(a, b, mask)
   check(lib.cenn_trainer_step_host(self.h, a:data(), b:data(), mask and mask:data() or nil, self.losses:data()))
+  return self.losses[1], self.losses[2], self.losses[3]
+end
+-- byte inputs: the image loader's crop as a ByteTensor [B,3,F,F] (rescale, centre clone, mean fill of train.lua:286-290 on the device) ...
+function Trainer:stepBytes(images_u8)
+  check(lib.cenn_trainer_step_images_u8_host(self.h, images_u8:data(), self.losses:data())); return self.losses[1], self.losses[2], self.losses[3]
+end
+-- ... the video loader's sample after its crop (frames in [0,1], one mask plane per clip, hflip flags: datavid/donkey_folder.lua:161-187) ...
+function Trainer:stepClips(frames01, mask1, flip, maskValue)
+  check(lib.cenn_trainer_step_clips_host(self.h, frames01:data(), mask1:data(), flip and flip:data() or nil, maskValue, self.losses:data()))
+  return self.losses[1], self.losses[2], self.losses[3]
+end
+-- ... or whole decoded frames plus the hook's random draws (crop origins IntTensor [B,2], flip ByteTensor [B], block tables IntTensor [B,21]):
+-- crop, mask crop / random-block mask, maskedFill, hflip and rescale of datavid/donkey_folder.lua:114-129,138-187 on the device
+function Trainer:stepFrames(frames_u8, mask_full, crop, flip, blocks, maskValue)
+  check(lib.cenn_trainer_step_frames_host(self.h, frames_u8:data(), frames_u8:size(3), frames_u8:size(4), mask_full:data(), crop:data(),
+        flip and flip:data() or nil, blocks:data(), maskValue, self.losses:data()))
   return self.losses[1], self.losses[2], self.losses[3]
 end
 -- write parameters and running statistics back into the nn modules (before util.save, util.lua:72-97)

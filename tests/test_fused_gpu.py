@@ -605,3 +605,35 @@ def test_fused_wide_net_at_the_real_bottleneck(cenn, fast_oracle):
     gG = trn.get_grads(0)
     assert np.all(np.isfinite(gG)) and _cos(gG, orc.gG) >= 0.9
     trn.close()
+
+
+def test_byte_image_step_equals_float_step(cenn):
+    """cenn_trainer_step_images_u8_host (rescale, centre clone, mean fill on the device: train.lua:286-290) against cenn_trainer_step_host
+    fed with the same images prepared on the host the way the script does."""
+    from video_filler_b200 import models, train, util
+    kw = dict(batchSize=6, nBottleneck=128, nef=64, ngf=64, ndf=64)
+    opt = models.default_opt("image", **kw)
+    rng = np.random.default_rng(3)
+    pG = util.params_flat(util.weights_init(util.describe_netG(opt), rng))
+    pD = util.params_flat(util.weights_init(util.describe_netD(opt), rng))
+    img = rng.integers(0, 256, (6, 3, 128, 128)).astype(np.uint8)
+    real = img.astype(np.float32) / np.float32(255) * np.float32(2) - np.float32(1)
+    center = real[:, :, 32:96, 32:96].copy()
+    ctx = real.copy()
+    for c, v in enumerate(onets.MEAN_FILL):
+        ctx[:, c, 36:92, 36:92] = v                         # overlapPred = 4
+    res = []
+    for mode in ("float", "u8"):
+        trn = train.FusedTrainer(opt, precision="bf16")
+        trn.set_params(0, pG); trn.set_params(1, pD)
+        losses = trn.step_host(ctx, center) if mode == "float" else trn.step_images_u8_host(img)
+        res.append((losses, trn.fetch("ctx"), trn.fetch("D.0.in") if False else None, trn.get_grads(1)))
+        if mode == "u8":
+            trn.step_images_u8_host_async(img); l2 = trn.wait_losses()
+            assert np.isfinite(list(l2.values())).all()
+        trn.close()
+    (l0, c0, _, g0), (l1, c1, _, g1) = res
+    assert np.array_equal(c0, c1)                           # identical bf16 real_ctx on both paths
+    for k, tol in (("errG_l2", 2e-3), ("errD_real", 2e-3), ("errD", 5e-3), ("errG", 4e-2)):
+        assert abs(l0[k] - l1[k]) <= tol * max(abs(l0[k]), 1e-3), (k, l0[k], l1[k])
+    assert _cos(g0, g1) >= 0.97

@@ -1256,6 +1256,30 @@ __global__ void __launch_bounds__(256) clip_prepare_kernel(const float *__restri
     }
 }
 
+// Image variant, byte input: what train.lua:286-290 does to a loader batch, from the DECODED BYTES (image.load = byte / 255, then the
+// loader's mul(2):add(-1), data/donkey_folder.lua:84-86): real_center = centre F/2 x F/2 crop, real_ctx = image with the centre minus an
+// `ov`-wide ring filled with the mean colour (2*117/255-1, 2*104/255-1, 2*123/255-1).  NHWC bf16 with Cp = 4.
+__global__ void __launch_bounds__(256) image_u8_prepare_kernel(const uint8_t *__restrict__ img, int N, int F, int ov, bf16 *__restrict__ ctx, bf16 *__restrict__ center) {
+    pdl_trigger(); pdl_wait();
+    const int64_t total = (int64_t)N * F * F;
+    const int q = F / 4, h = F / 2;
+    const float fill[3] = {2.f * 117.f / 255.f - 1.f, 2.f * 104.f / 255.f - 1.f, 2.f * 123.f / 255.f - 1.f};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / ((int64_t)F * F)), r = (int)(i - (int64_t)n * F * F), y = r / F, x = r - y * F;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = (float)img[((int64_t)n * 3 + c) * F * F + r] / 255.f * 2.f - 1.f;
+        const bool in_center = y >= q && y < q + h && x >= q && x < q + h;
+        if (in_center) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], 0.f);
+            *reinterpret_cast<uint2 *>(center + (((int64_t)n * h + (y - q)) * h + (x - q)) * 4) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+        }
+        if (y >= q + ov && y < q + h - ov && x >= q + ov && x < q + h - ov) { v[0] = fill[0]; v[1] = fill[1]; v[2] = fill[2]; }
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], 0.f);
+        *reinterpret_cast<uint2 *>(ctx + i * 4) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+    }
+}
+
 // Device-side remainder of the video loader's hook (datavid/donkey_folder.lua:114-129,138-170): random crop of the loaded frames and
 // of the logo mask, and the random-block mask that replaces an all-black mask crop.  The RANDOM DRAWS stay on the host (crop origin,
 // block count and corners: torch.uniform / torch.random, :149-150,120-123) and arrive as small integer tables; the pixels never do:

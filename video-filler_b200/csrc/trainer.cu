@@ -971,6 +971,12 @@ int build_program(T *t) {
     // -- inputs: fp32 NCHW (+ uint8 mask) -> NHWC bf16
     emit(t, "convert_inputs", [t, s, video]() {
         const Tensor &a = t->real_ctx, &b = t->real_aux;
+        if (!video && !t->cur_a) {      // byte-image mode (cenn_trainer_step_images_u8_*): centre crop + mean fill on the device
+            if (a.Cp != 4 || a.C != 3) { cenn_set_error("byte-image mode needs 3-channel images"); return 1; }
+            LK(nhwc::image_u8_prepare_kernel, dim3(grid1d(s, a.pix())), dim3(256), 0, s->stream)(reinterpret_cast<const uint8_t *>(t->cur_b), a.N, a.H, t->cfg.overlapPred, a.p, b.p);
+            KLAUNCH(s);
+            return cenn_check_cuda(cudaMemsetAsync(t->loss_acc, 0, 8 * sizeof(double), s->stream), "memset", __FILE__, __LINE__);
+        }
         if (video && !t->cur_a) {       // clip mode: masked / full / expanded mask derived on the device from the frames and one mask plane
             const Tensor &m = t->mask;
             const float mv = t->clip_mv;
@@ -1488,6 +1494,51 @@ int cenn_trainer_wait_losses(cenn_trainer *t, float *losses) {
     CK(cudaEventSynchronize(t->ev_loss[i]));
     memcpy(losses, t->pin_loss2 + 8 * i, 8 * sizeof(float));
     t->async_read++;
+    return 0;
+}
+
+// Byte-image steps (image variant): the host hands over the loader's crop as DECODED BYTES [B,3,F,F] (what image.load yields before its
+// division by 255); the device applies the loader's rescale to [-1,1] (data/donkey_folder.lua:84-86) and train.lua:286-290 (centre clone,
+// mean fill).  A quarter of the H2D bytes of the FloatTensor form, and one tensor instead of two.
+static int step_images_u8_device(cenn_trainer *t, const uint8_t *img_dev) {
+    t->cur_a = nullptr; t->cur_b = reinterpret_cast<const float *>(img_dev); t->cur_m = nullptr;
+    int64_t before = t->s->launches;
+    int rc = run_step(t);
+    t->launches_per_step = t->s->launches - before;
+    return rc;
+}
+int cenn_trainer_step_images_u8_host(cenn_trainer *t, const uint8_t *images_u8, float *losses) {
+    REQUIRE(t && images_u8 && losses, "cenn_trainer_step_images_u8_host: null argument");
+    REQUIRE(t->cfg.variant == 0, "cenn_trainer_step_images_u8_host: byte images belong to the image variant");
+    API_BEGIN(t->s);
+    CK(cudaMemcpyAsync(t->in_a, images_u8, (size_t)t->n_a, cudaMemcpyHostToDevice, t->s->stream));      // n_a bytes: one byte per element of real_ctx
+    if (step_images_u8_device(t, reinterpret_cast<const uint8_t *>(t->in_a))) return 1;
+    return cenn_trainer_read_losses(t, losses);
+}
+int cenn_trainer_step_images_u8_host_async(cenn_trainer *t, const uint8_t *images_u8) {
+    REQUIRE(t && images_u8, "cenn_trainer_step_images_u8_host_async: null argument");
+    REQUIRE(t->cfg.variant == 0, "cenn_trainer_step_images_u8_host_async: byte images belong to the image variant");
+    API_BEGIN(t->s);
+    REQUIRE(t->async_issued - t->async_read < 2, "cenn_trainer_step_images_u8_host_async: two steps already in flight; call cenn_trainer_wait_losses");
+    cudaStream_t st = t->s->stream;
+    if (!t->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&t->ev_copied[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&t->ev_consumed[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&t->ev_loss[i], cudaEventDisableTiming)); }
+        t->in_a2 = dalloc<float>(t, t->n_a); t->in_b2 = dalloc<float>(t, t->n_b);
+        REQUIRE(t->in_a2 && t->in_b2, "trainer: staging allocation failed");
+        CK(cudaMallocHost(&t->pin_loss2, 2 * 8 * sizeof(float)));
+    }
+    const int i = (int)(t->async_issued & 1);
+    float *da = i ? t->in_a2 : t->in_a;
+    if (t->consumed_valid[i]) CK(cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[i], 0));
+    CK(cudaMemcpyAsync(da, images_u8, (size_t)t->n_a, cudaMemcpyHostToDevice, t->copy_stream));
+    CK(cudaEventRecord(t->ev_copied[i], t->copy_stream));
+    CK(cudaStreamWaitEvent(st, t->ev_copied[i], 0));
+    if (step_images_u8_device(t, reinterpret_cast<const uint8_t *>(da))) return 1;
+    CK(cudaEventRecord(t->ev_consumed[i], st)); t->consumed_valid[i] = true;
+    CK(cudaMemcpyAsync(t->pin_loss2 + 8 * i, t->loss_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(t->ev_loss[i], st));
+    t->async_issued++;
     return 0;
 }
 

@@ -300,6 +300,17 @@ class FusedTrainer:
                                            losses.ctypes.data_as(C.c_void_p))
         return dict(zip(LOSS_NAMES, losses.tolist()))
 
+    def step_images_u8_host(self, images_u8):
+        """Byte-image step (image variant): uint8 [B, 3, F, F]; the device rescales to [-1,1], clones the centre and mean-fills it (train.lua:286-290)."""
+        images_u8 = np.ascontiguousarray(images_u8, np.uint8)
+        losses = np.zeros(8, np.float32)
+        api().cenn_trainer_step_images_u8_host(self.h, images_u8.ctypes.data_as(C.c_void_p), losses.ctypes.data_as(C.c_void_p))
+        return dict(zip(LOSS_NAMES, losses.tolist()))
+
+    def step_images_u8_host_async(self, images_u8):
+        assert images_u8.dtype == np.uint8 and images_u8.flags.c_contiguous
+        api().cenn_trainer_step_images_u8_host_async(self.h, images_u8.ctypes.data_as(C.c_void_p))
+
     def step_frames_host(self, frames_u8, mask_full, crop, flip, blocks, maskValue=None):
         """Frame-mode step (video variant): decoded frames uint8 [B, nc*predLen, iH, iW], the full-size mask uint8 [iH, iW] and the loader
         hook's draws (crop int32 [B,2] 0-based, flip uint8 [B] or None, blocks int32 [B,21]); the device runs the hook
