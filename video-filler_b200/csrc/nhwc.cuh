@@ -453,6 +453,65 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce2_kernel(const bf16 *__re
     if (kAtomic) fold_and_flush<2, true>(acc, active, part, Cp, C);
     else fold_and_flush<2, false>(acc, active, part + (size_t)blockIdx.x * 2 * Cp, Cp, C);
 }
+// BN backward pass 1 WITH the coefficient step (single GPU): every CTA adds its partial sums into one [2][Cp] row (fp32 atomics), and the
+// LAST CTA to finish (threadfence + counter) turns the completed sums into the pass-2 coefficients and the BN affine gradients, zeroes the
+// row and the counter for the next use.  Removes the dependent bn_bwd_coef2 launch (~10 us on the critical path per BN layer and sweep)
+// without touching the apply kernel (putting the coefficients into ITS prologue cost as much as the launch: profiles/r2_notes.md).
+template <int ACT>
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_coef_kernel(const bf16 *__restrict__ g, const bf16 *__restrict__ y, const float *__restrict__ scale,
+        const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
+        float *__restrict__ sums, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int Cp, int64_t npix, int vec_per_pix,
+        int C, float negval, double n, unsigned int *__restrict__ done_counter) {
+    pdl_trigger(); pdl_wait();
+    __shared__ int is_last;
+    const int vec = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = vec < vec_per_pix;
+    float acc[2][8] = {};
+    if (active) {
+        float mu[8], sc[8], sh[8];
+        load8f(mean, vec * 8, C, mu); load8f(scale, vec * 8, C, sc); load8f(shift, vec * 8, C, sh);
+        const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+        for (int64_t p0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p0 < npix; p0 += stride * BN_U) {
+            uint4 rg[BN_U], ry[BN_U];
+#pragma unroll
+            for (int u = 0; u < BN_U; ++u) {
+                int64_t p = p0 + u * stride;
+                if (p < npix) { int64_t vi = p * vec_per_pix + vec; rg[u] = __ldg(reinterpret_cast<const uint4 *>(g) + vi); ry[u] = __ldg(reinterpret_cast<const uint4 *>(y) + vi); }
+            }
+#pragma unroll
+            for (int u = 0; u < BN_U; ++u) {
+                if (p0 + u * stride < npix) {
+                    float fg[8], fy[8];
+                    unpack8b(rg[u], fg); unpack8b(ry[u], fy);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { float dz = fg[k] * dact_z<ACT>(fmaf(fy[k], sc[k], sh[k]), negval); acc[0][k] += dz; acc[1][k] = fmaf(dz, fy[k] - mu[k], acc[1][k]); }
+                }
+            }
+        }
+    }
+    fold_and_flush<2, true>(acc, active, sums, Cp, C);
+    __syncthreads();                                   // this CTA's atomics are issued
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int total = gridDim.x * gridDim.y;
+        const unsigned int k = atomicAdd(done_counter, 1u);
+        is_last = (k == total - 1);
+        if (is_last) { *done_counter = 0u; __threadfence(); }
+    }
+    __syncthreads();
+    if (!is_last) return;
+    for (int c = tid; c < Cp; c += nthr) {
+        const double s = (double)__ldcg(sums + c), d = (double)__ldcg(sums + Cp + c);
+        sums[c] = 0.f; sums[Cp + c] = 0.f;
+        if (c < C) {
+            const double is = invstd[c], A = is * (double)gamma[c], k1 = is * is * d / n;
+            coef[c] = (float)A; coef[C + c] = (float)(A * k1); coef[2 * C + c] = (float)(((double)mean[c] * k1 - s / n) * A);
+            if (ggamma) ggamma[c] += (float)(d * is);
+            if (gbeta) gbeta[c] += (float)s;
+        }
+    }
+}
 // sums the partial rows; coefficients for pass 2 + BN parameter gradients.
 // sums_io [2][Cp]: rows > 0: written with the folded sums (the buffer a data-parallel run all-reduces); rows == 0: read.
 // block = (32 channels, 8 row lanes); grid = ceil(C / 32).  coef for pass 2 is stored pre-combined:

@@ -683,6 +683,19 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         // data parallel with peer mailboxes: the local sums are accumulated by fp32 atomics straight into the exchange buffer (no fold launch);
         // replicas stay bit-identical because every rank adds the same published values in rank order
         const bool dp_atomic = dp && s->xr_enabled && 2 * b->Coutp <= XR_MAXF && getenv("CENN_DP_BN_FOLD") == nullptr;
+        // single GPU (default): pass 1 and the coefficient step in one launch (the last CTA finishes the sums); CENN_BN_BWD_3LAUNCH=1 restores
+        // reduce -> coefficients -> apply
+        static const bool fuse_coef_env = getenv("CENN_BN_BWD_3LAUNCH") == nullptr;
+        const bool fuse_coef = !dp && !two_launch && fuse_coef_env;
+        if (fuse_coef) {
+            emit(t, "bn_bwd_reduce", [s, b, gamma, gg, gbeta, npix, vpp, n_global]() {
+                dim3 blk; int gy; reduce_dims(vpp, blk, gy);
+                auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce_coef_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_reduce_coef_kernel<nhwc::ACT_RELU>;
+                LK(kern, dim3(b->red_rows, gy), blk, 2 * blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->y.p, b->scale, b->shift, b->mean, b->invstd, gamma,
+                    b->bsums, b->coef, gg, gbeta, b->Coutp, npix, vpp, b->Cout, 0.2f, n_global, b->done_ctr);
+                KLAUNCH(s); return 0; });
+            t->prog.back().bytes = 2.0 * 2.0 * (double)npix * b->Cout;        // read g, y
+        } else
         emit(t, "bn_bwd_reduce", [s, b, npix, vpp, two_launch, dp_atomic]() {
             dim3 blk; int gy; reduce_dims(vpp, blk, gy);
             if (two_launch || dp_atomic) {
@@ -726,7 +739,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global, inv_world]() {
                 LK(nhwc::bn_bwd_coef2_kernel, dim3((b->Cout + 31) / 32), dim3(dim3(32, 8)), 0, s->stream)(nullptr, 0, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1, inv_world);
                 KLAUNCH(s); return 0; });
-        } else {
+        } else if (!fuse_coef) {
             emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
                 LK(nhwc::bn_bwd_coef2_kernel, dim3((b->Cout + 31) / 32), dim3(dim3(32, 8)), 0, s->stream)(b->part, b->part_rows, nullptr, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, 1, 1.f);
                 KLAUNCH(s); return 0; });
