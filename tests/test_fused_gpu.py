@@ -589,9 +589,9 @@ def test_frame_mode_step_runs_the_loader_hook_on_the_device(cenn):
 
 def test_fused_wide_net_at_the_real_bottleneck(cenn, fast_oracle):
     """train_wholeim_input.lua:40-43 as shipped: nef = ngf = 192, ndf = 128, nBottleneck 6400 (VERDICT r1 missing 3: the wide net had only
-    been run at nBottleneck 640).  fp32 oracle (330 M generator parameters), two samples."""
+    been run at nBottleneck 640).  fp32 oracle (365 M generator parameters), four samples."""
     from video_filler_b200 import models, train
-    kw = dict(batchSize=2, nBottleneck=6400, nef=192, ngf=192, ndf=128, predLen=1, weight_nomask=1.0)
+    kw = dict(batchSize=4, nBottleneck=6400, nef=192, ngf=192, ndf=128, predLen=1, weight_nomask=1.0)
     orc = ostep.StepOracle(onets.default_opt("video", **kw), seed=77, dtype=np.float32)
     trn = train.FusedTrainer(models.default_opt("video", **kw), precision="bf16")
     assert trn.param_count(0) == orc.pG.size and trn.param_count(1) == orc.pD.size
@@ -601,7 +601,7 @@ def test_fused_wide_net_at_the_real_bottleneck(cenn, fast_oracle):
     for k in ("errD_real", "errG_l2", "errG_total"):
         assert lg[k] == pytest.approx(lo[k], rel=2e-2), k
     for k in ("errD_fake", "errD", "errG"):
-        assert lg[k] == pytest.approx(lo[k], rel=8e-2), k          # BatchNorm over two samples at the bottleneck
+        assert lg[k] == pytest.approx(lo[k], rel=1e-1), k          # BatchNorm over four values per channel at the 1x1 bottleneck: a flipped bf16 rounding moves a normalised value by O(1)
     gG = trn.get_grads(0)
     assert np.all(np.isfinite(gG)) and _cos(gG, orc.gG) >= 0.9
     trn.close()

@@ -454,10 +454,15 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
     // by the number of S patches (one HBM round trip each) in flight: as many patch buffers as shared memory holds (up to 6)
     const bool resident = thin && p.n_tiles == 1 && 4 * p.chunks <= 8 && getenv("CENN_PATCH_NO_RESIDENT") == nullptr;
     const int base_fixed = 1024 + out_bytes + 38 * 8 + 3 * BN * 4 + 64;
+    int per_sm = 1;
     if (resident) {
         stages = 4 * p.chunks;
-        npatch = (SMEM_LIMIT - base_fixed - stages * bstage) / p.patch_stride;
-        if (npatch > 6) npatch = 6;
+        // measured (round 2): six patches in flight barely help (E1's dead dgrad 133 -> 126 us): the variant is bound by its two single-thread issue
+        // loops and its per-lane epilogue (55 tiles of 2.3 us per CTA), so two CTAs share an SM when half the shared memory holds >= 2 patches
+        const int half = (SMEM_LIMIT + 1024) / 2 - 1024;
+        const int np2 = (half - base_fixed - stages * bstage) / p.patch_stride;
+        if (np2 >= 2 && getenv("CENN_THIN_ONE_CTA") == nullptr) { per_sm = 2; npatch = np2 > 4 ? 4 : np2; }
+        else { npatch = (SMEM_LIMIT - base_fixed - stages * bstage) / p.patch_stride; if (npatch > 6) npatch = 6; }
         REQUIRE(npatch >= 2, "tc_dgrad_patch: shared memory too small for two patches (thin)");
     } else {
         stages = (SMEM_LIMIT - base_fixed - 2 * p.patch_stride) / bstage;
@@ -470,7 +475,7 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
     pl->kind = 3; pl->BN = BN; pl->stages = stages;
     pl->smem = (size_t)stages * bstage + fixed;
     const int total = p.m_tiles * p.n_tiles;
-    pl->grid[0] = (unsigned)(total < s->sm_count ? total : s->sm_count); pl->grid[1] = 1; pl->grid[2] = 1;
+    pl->grid[0] = (unsigned)(total < s->sm_count * per_sm ? total : s->sm_count * per_sm); pl->grid[1] = 1; pl->grid[2] = 1;
     switch (BN) {
         case 16: return set_attr_patch_dgrad<16>();
         case 64: return set_attr_patch_dgrad<64>();

@@ -653,7 +653,7 @@ struct PatchDgradParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, BN <= 16 ? 2 : 1)      // thin outputs: two co-resident CTAs per SM (the per-tile issue loops, not bytes, bound that variant)
 patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ PatchDgradParams p, int stages) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
