@@ -10,7 +10,7 @@
 #include "../../include/cenn.h"
 
 // One-shot all-reduce over NVLink peer memory (dist.cu / nhwc.cuh xr_sum_inplace): every rank owns a mailbox
-// [2 parities][XR_MAXF] 8-byte {value, exchange tag} words; peers' mailboxes are mapped with CUDA IPC.
+// [2 parities][world source rows][XR_MAXF] 8-byte {value, exchange tag} words; peers' mailboxes are mapped with CUDA IPC.
 static const int XR_MAXF = 16384;       // floats per exchange (2 x 8192 statistics columns)
 static const int XR_MAX_WORLD = 16;
 struct XrCtx {
@@ -18,6 +18,7 @@ struct XrCtx {
     unsigned long long *flags[XR_MAX_WORLD];    // flags[r][parity]: last epoch rank r has published
     unsigned long long *epoch;                  // this rank's exchange counter (device memory)
     int world, rank;
+    int push;                                   // 1: store into the peers' mailboxes and poll local memory (default); 0: publish locally, poll the peers
     long long timeout_cycles;                   // a peer that has not published after this many SM cycles traps the kernel (CENN_XR_TIMEOUT_S, default 120 s:
                                                 // long enough for a rank that writes a checkpoint or stalls in its loader, short enough not to hang a box forever)
 };

@@ -119,7 +119,7 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
     // here just leaves xr_enabled = false and those exchanges stay on NCCL.
     do {
         if (!g_nccl.all_gather || world_size > XR_MAX_WORLD || getenv("CENN_NO_XR")) break;
-        const size_t half = (size_t)2 * XR_MAXF * 8 + 256;                // one mailbox: 2 parity slots of {value, tag} words (+ spare)
+        const size_t half = (size_t)2 * world_size * XR_MAXF * 8 + 256;   // one mailbox: 2 parity slots x one row per source rank of {value, tag} words (+ spare)
         const size_t bytes = 2 * half;                                  // two independent mailbox sequences
         void *own = nullptr, *hbuf = nullptr;
         if (cudaMalloc(&own, bytes) != cudaSuccess) { cudaGetLastError(); break; }
@@ -138,14 +138,15 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
         bool ok = rc == 0;
         XrCtx x = {}, x2 = {};
         x.world = x2.world = world_size; x.rank = x2.rank = rank;
+        x.push = x2.push = getenv("CENN_XR_PULL") ? 0 : 1;
         { const char *e = getenv("CENN_XR_TIMEOUT_S"); const double sec = e ? atof(e) : 120.0; x.timeout_cycles = x2.timeout_cycles = (long long)(sec * 2.0e9); }
         for (int r = 0; r < world_size && ok; ++r) {
             void *base = own;
             if (r != rank && cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
             x.data[r] = reinterpret_cast<float *>(base);
-            x.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + (size_t)2 * XR_MAXF * 8);
+            x.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + (size_t)2 * world_size * XR_MAXF * 8);
             x2.data[r] = reinterpret_cast<float *>(reinterpret_cast<char *>(base) + half);
-            x2.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + half + (size_t)2 * XR_MAXF * 8);
+            x2.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + half + (size_t)2 * world_size * XR_MAXF * 8);
         }
         // every rank must learn whether ALL ranks succeeded (a partial set-up would deadlock the exchange)
         float *flag_dev = nullptr; float flag_host = ok ? 0.f : 1.f;

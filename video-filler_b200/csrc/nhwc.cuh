@@ -182,10 +182,11 @@ __global__ void bn_finalize_kernel(float *__restrict__ stats, int stats_stride, 
 }
 
 // ---------------------------------------------------------------- one-shot all-reduce over NVLink peer memory
-// buf[0..n) <- sum over ranks, in place, by ONE CTA: publish the local values in this rank's mailbox (parity slot of
-// the exchange counter) and add the peers' payloads read straight from their HBM over NVLink as soon as they carry
-// this exchange's tag.  All ranks add in rank order, so replicas get bit-identical sums.  Two parity slots suffice: a
-// rank can publish exchange e+2 only after it saw every peer's flag e+1, which a peer raises after reading e.
+// buf[0..n) <- sum over ranks, in place, by ONE CTA: push the local values into every peer's mailbox (parity slot of
+// the exchange counter, row of this rank) over NVLink and add the peers' payloads from the LOCAL mailbox as soon as
+// they carry this exchange's tag.  All ranks add in rank order, so replicas get bit-identical sums.  Two parity slots
+// suffice: a rank pushes exchange e+2 only after it received every peer's e+1 words, which a peer sends after it has
+// finished reading exchange e.
 // Replaces a NCCL all-reduce launch (~10-25 us at 8 ranks) by ~3 us inside the consumer kernel.
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
@@ -208,20 +209,32 @@ __device__ void xr_sum_inplace(float *__restrict__ buf, int n, const XrCtx &x) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const unsigned long long e = *x.epoch + 1;
     const unsigned int tag = (unsigned int)e;           // never 0 within 2^32 exchanges; mailboxes start zeroed
-    const size_t slot = (size_t)(e & 1) * XR_MAXF;
-    uint2 *own = reinterpret_cast<uint2 *>(x.data[x.rank]) + slot;
-    for (int i = tid; i < n; i += nthr) st_ll(own + i, buf[i], tag);
+    // mailbox of rank r: [parity][source rank][XR_MAXF] words.  PUSH: this rank stores its values into its own row of
+    // EVERY rank's mailbox (remote stores are fire-and-forget: one NVLink crossing), then polls its LOCAL mailbox --
+    // a poll costs an L2 hit instead of an NVLink round trip, and the wait after the slowest peer has written is one
+    // crossing, not a round trip plus the poll period.
+    const size_t slot = (size_t)(e & 1) * x.world * XR_MAXF;
+    const size_t mine = slot + (size_t)x.rank * XR_MAXF;
+    for (int i = tid; i < n; i += nthr) {
+        const float v = buf[i];
+#pragma unroll
+        for (int r = 0; r < XR_MAX_WORLD; ++r)
+            if (r < x.world && (x.push ? r != x.rank : r == x.rank)) st_ll(reinterpret_cast<uint2 *>(x.data[r]) + mine + i, v, tag);
+    }
+    // pull mode (CENN_XR_PULL=1, the round-1 protocol, kept for A/B runs): publish locally, poll the peers' memory
+    const uint2 *local = reinterpret_cast<const uint2 *>(x.data[x.rank]) + slot;
+#define XR_SRC(r) ((x.push ? local : reinterpret_cast<const uint2 *>(x.data[r]) + slot) + (size_t)(r) * XR_MAXF)
     for (int i = tid; i < n; i += nthr) {
         uint2 v[XR_MAX_WORLD];
         unsigned int pending = 0;
 #pragma unroll
         for (int r = 0; r < XR_MAX_WORLD; ++r)
-            if (r < x.world && r != x.rank) { v[r] = ld_ll(reinterpret_cast<const uint2 *>(x.data[r]) + slot + i); if (v[r].y != tag) pending |= 1u << r; }
+            if (r < x.world && r != x.rank) { v[r] = ld_ll(XR_SRC(r) + i); if (v[r].y != tag) pending |= 1u << r; }
         long long t0 = clock64();
         while (pending) {
 #pragma unroll
             for (int r = 0; r < XR_MAX_WORLD; ++r)
-                if (pending & (1u << r)) { v[r] = ld_ll(reinterpret_cast<const uint2 *>(x.data[r]) + slot + i); if (v[r].y == tag) pending &= ~(1u << r); }
+                if (pending & (1u << r)) { v[r] = ld_ll(XR_SRC(r) + i); if (v[r].y == tag) pending &= ~(1u << r); }
             if (clock64() - t0 > x.timeout_cycles) { printf("cenn: peer exchange timeout (rank %d, exchange %llu, pending mask %x)\n", x.rank, e, pending); __trap(); }
         }
         float acc = 0.f;                                 // rank order: every replica adds in the same order -> bit-identical sums
@@ -229,6 +242,7 @@ __device__ void xr_sum_inplace(float *__restrict__ buf, int n, const XrCtx &x) {
         for (int r = 0; r < XR_MAX_WORLD; ++r) if (r < x.world) acc += (r == x.rank) ? buf[i] : __uint_as_float(v[r].x);
         buf[i] = acc;
     }
+#undef XR_SRC
     __syncthreads();
     if (tid == 0) *x.epoch = e;
 }
