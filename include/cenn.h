@@ -212,6 +212,10 @@ typedef struct cenn_trainer_config {
     int world_size;    /* data-parallel replicas; batch statistics / criteria use batchSize*world_size */
     int rank;
     int dead_dgrad;    /* 1: also compute the first-layer dgrads the reference computes and discards */
+    /* train.lua's optional branches (image variant, fineSize 128; the video scripts force both off, train_deepernet.lua:55-58) */
+    int noiseGen;      /* train.lua:109-124: a 1x1 conv of a noise vector [B,nz,1,1] is joined to the bottleneck (cenn_trainer_set_noise_*) */
+    int nz;            /* length of the noise vector (train.lua:11, default 100) */
+    int conditionAdv;  /* train.lua:158-180: netD takes {context, prediction}: two 5x5/stride-2 first-layer convs joined along channels */
 } cenn_trainer_config;
 
 enum { CENN_NET_G = 0, CENN_NET_D = 1 };
@@ -244,6 +248,11 @@ CENN_API int cenn_trainer_wait_losses(cenn_trainer *t, float *losses_host /*[CEN
  * losses stay on the device until cenn_trainer_read_losses */
 CENN_API int cenn_trainer_step_device(cenn_trainer *t, const float *a_dev, const float *b_dev, const uint8_t *mask_dev);
 CENN_API int cenn_trainer_read_losses(cenn_trainer *t, float *losses_host);
+/* noiseGen: the noise draw of the NEXT step(s), fp32 [batchSize, nz] (train.lua:319-323 redraws `noise` inside fDx; here the caller
+ * draws it -- noise:uniform(-1,1) / noise:normal(0,1) -- and hands it over before each step call).  Stream-ordered copy into the
+ * executor's own buffer: the source may be reused as soon as the call returns (host form) / the copy has run (device form). */
+CENN_API int cenn_trainer_set_noise_host(cenn_trainer *t, const float *noise_host);
+CENN_API int cenn_trainer_set_noise_device(cenn_trainer *t, const float *noise_dev);
 /* phase-split form for data parallelism: the host inserts all-reduces between phases
  * (phase list and the buffers to reduce are described in DESIGN.md section "multi-GPU") */
 CENN_API int cenn_trainer_grad_buffer(cenn_trainer *t, int net, float **grads_dev, int64_t *count);

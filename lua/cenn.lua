@@ -417,7 +417,7 @@ function GDL:updateGradInput() return self.gradInput end
 -- (`local eng = cenn.Inpainter(opt, net)` ... `eng:sweep(images01, mask)`).
 ffi.cdef[[
 typedef struct cenn_trainer_config { int variant, batchSize, fineSize, nBottleneck, nef, ngf, ndf, nc, predLen, overlapPred;
-    float wtl2, weight_nomask, wtgdl, lr, beta1; int precision, world_size, rank, dead_dgrad; } cenn_trainer_config;
+    float wtl2, weight_nomask, wtgdl, lr, beta1; int precision, world_size, rank, dead_dgrad, noiseGen, nz, conditionAdv; } cenn_trainer_config;
 int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trainer **out);
 int cenn_trainer_destroy(cenn_trainer *t);
 int cenn_trainer_param_count(cenn_trainer *t, int net, int64_t *count);
@@ -433,6 +433,7 @@ int cenn_trainer_step_clips_host(cenn_trainer *t, const float *frames01_host, co
 int cenn_trainer_step_frames_host(cenn_trainer *t, const uint8_t *frames_u8_host, int iH, int iW, const uint8_t *mask_full_host,
     const int *crop_host, const uint8_t *flip_host, const int *blocks_host, float maskValue, float *losses_host);
 int cenn_trainer_step_images_u8_host(cenn_trainer *t, const uint8_t *images_u8_host, float *losses_host);
+int cenn_trainer_set_noise_host(cenn_trainer *t, const float *noise_host);
 typedef struct cenn_inpainter cenn_inpainter;
 typedef struct cenn_inpainter_config { int variant, batch, fineSize, nBottleneck, nef, ngf, nc, inputLen; } cenn_inpainter_config;
 int cenn_inpainter_create(cenn_state *s, const cenn_inpainter_config *cfg, cenn_inpainter **out);
@@ -458,7 +459,8 @@ local Trainer = torch.class('cenn.Trainer')
 function Trainer:__init(opt, netG, netD, world_size, rank)
   local video = opt.predLen ~= nil
   local cfg = ffi.new('cenn_trainer_config', {video and 1 or 0, opt.batchSize, opt.fineSize, opt.nBottleneck, opt.nef, opt.ngf, opt.ndf, opt.nc or 3,
-    opt.predLen or 1, opt.overlapPred or 0, opt.wtl2, opt.weight_nomask or 0, opt.wtgdl or 0, opt.lr, opt.beta1, 1, world_size or 1, rank or 0, 1})
+    opt.predLen or 1, opt.overlapPred or 0, opt.wtl2, opt.weight_nomask or 0, opt.wtgdl or 0, opt.lr, opt.beta1, 1, world_size or 1, rank or 0, 1,
+    opt.noiseGen and 1 or 0, opt.nz or 100, opt.conditionAdv and 1 or 0})
   local h = ffi.new('cenn_trainer*[1]'); check(lib.cenn_trainer_create(S(), cfg, h)); self.h = ffi.gc(h[0], lib.cenn_trainer_destroy)
   self.netG, self.netD = netG, netD
   self.pG, self.pD = netG:getParameters(), netD:getParameters()          -- train.lua:262-263: the flat vectors are the interchange format
@@ -466,7 +468,9 @@ function Trainer:__init(opt, netG, netD, world_size, rank)
   self.losses = torch.FloatTensor(8)
 end
 -- one G+D step; returns errD, errG, errG_l2 as printed at train.lua:443-450 (host FloatTensors in, like the data loader delivers them)
-function Trainer:step(a, b, mask)
+-- opt.noiseGen: pass the step's noise draw (train.lua:319-323) as the 4th argument, a FloatTensor [B, nz, 1, 1]
+function Trainer:step(a, b, mask, noise)
+  if noise then check(lib.cenn_trainer_set_noise_host(self.h, noise:data())) end
   check(lib.cenn_trainer_step_host(self.h, a:data(), b:data(), mask and mask:data() or nil, self.losses:data()))
   return self.losses[1], self.losses[2], self.losses[3]
 end

@@ -146,3 +146,24 @@ def test_noisegen_conditionadv_trees_roundtrip_and_match_oracle_layout(tmp_path)
         assert np.array_equal(util.params_flat(back), flat)
         join = [m for m in back.walk() if m.classname == "nn.JoinTable"][0]
         assert join.attrs["dimension"] == 2
+
+
+def test_cyclic_tables_keep_identity_and_empty_tables_map_to_lists(tmp_path):
+    """ADVICE r1 (t7 reader): a back-reference taken while a list-like table is still being read (nngraph gModules are cyclic: node ->
+    children -> node) must end up pointing at the SAME object the table became, and the 0-entry table has one fixed mapping."""
+    node = t7.TorchObject("nngraph.Node", {"id": 1})
+    children = [node, t7.TorchObject("nngraph.Node", {"id": 2})]
+    node.fields["children"] = children          # cycle: children[0].children is children
+    root = {"nodes": children, "empty": [], "first": node}
+    p = str(tmp_path / "cyc.t7")
+    t7.save(p, root)
+    back = t7.load(p)
+    assert isinstance(back["nodes"], list) and len(back["nodes"]) == 2
+    assert back["nodes"][0] is back["first"]
+    assert back["first"].fields["children"] is back["nodes"]          # not a stale dict copy
+    assert back["nodes"][0].fields["children"][1].fields["id"] == 2
+    assert back["empty"] == [] and isinstance(back["empty"], list)
+    # an object whose field table is empty keeps an empty dict of fields
+    p2 = str(tmp_path / "e.t7")
+    t7.save(p2, t7.TorchObject("nn.Identity", {}))
+    assert t7.load(p2).fields == {}

@@ -19,7 +19,8 @@ class TrainerConfig(C.Structure):
                 ("nef", C.c_int), ("ngf", C.c_int), ("ndf", C.c_int), ("nc", C.c_int), ("predLen", C.c_int),
                 ("overlapPred", C.c_int), ("wtl2", C.c_float), ("weight_nomask", C.c_float), ("wtgdl", C.c_float),
                 ("lr", C.c_float), ("beta1", C.c_float), ("precision", C.c_int), ("world_size", C.c_int),
-                ("rank", C.c_int), ("dead_dgrad", C.c_int)]
+                ("rank", C.c_int), ("dead_dgrad", C.c_int),
+                ("noiseGen", C.c_int), ("nz", C.c_int), ("conditionAdv", C.c_int)]
 
 
 class InpainterConfig(C.Structure):

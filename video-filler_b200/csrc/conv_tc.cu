@@ -484,11 +484,13 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
 }
 
 // ------------------------------------------------------------------ P4: plain GEMM
-int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep) {
+int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *out, int M, int Nc, int K, int ldo, const TcEpilogue &ep, int lda) {
     REQUIRE(K % 8 == 0, "tc_gemm: K must be a multiple of 8 (got %d)", K);
+    if (lda <= 0) lda = K;                 // row pitch of A in elements (a column slice of a wider matrix: lda > K, columns >= K are never read)
+    REQUIRE(lda >= K && lda % 8 == 0, "tc_gemm: lda must be a multiple of 8 and >= K (got %d, K %d)", lda, K);
     uint64_t rowsA = (uint64_t)(M > 128 ? M : 128);
     uint64_t dims[5] = {(uint64_t)K, rowsA, 1, 1, 1};
-    uint64_t st[4] = {(uint64_t)K * 2, (uint64_t)K * 2 * rowsA, (uint64_t)K * 2 * rowsA, (uint64_t)K * 2 * rowsA};
+    uint64_t st[4] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * rowsA, (uint64_t)lda * 2 * rowsA, (uint64_t)lda * 2 * rowsA};
     uint32_t box[5] = {64, 128, 1, 1, 1};
     (void)rowsA;
     dims[1] = (uint64_t)M;                 // the true extent: rows >= M are out of bounds -> zero filled

@@ -1463,4 +1463,90 @@ __global__ void __launch_bounds__(256) wholeim_scatter_kernel(const bf16 *__rest
     }
 }
 
+// ---------------------------------------------------------------- train.lua's optional branches (noiseGen / conditionAdv)
+// noiseGen (train.lua:109-124): a 1x1 convolution of the noise vector runs beside the encoder and nn.JoinTable(2) appends its nz outputs
+// to the nBottleneck encoder outputs before the bottleneck BN.  The joined tensor is the bottleneck block's conv output y [B][pitch]:
+// the encoder GEMM writes columns [0, col0), this kernel columns [col0, col0 + nz) and their BN statistics (of the STORED bf16 values,
+// as the GEMM epilogues do).  One CTA per output channel (nz is ~100: 2.5 MFLOP at batch 256).
+__global__ void __launch_bounds__(128) noise_fwd_kernel(const float *__restrict__ noise, const bf16 *__restrict__ w, const float *__restrict__ bias,
+        bf16 *__restrict__ y, int pitch, int col0, int B, int nz, float *__restrict__ stats, int stats_stride) {
+    pdl_trigger(); pdl_wait();
+    const int j = blockIdx.x;
+    __shared__ float red[2][4];
+    float s1 = 0.f, s2 = 0.f;
+    for (int n = threadIdx.x; n < B; n += blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < nz; ++k) acc = fmaf(__bfloat162float(__float2bfloat16(noise[(int64_t)n * nz + k])), __bfloat162float(w[(int64_t)j * nz + k]), acc);
+        const bf16 h = __float2bfloat16(acc + bias[j]);
+        y[(int64_t)n * pitch + col0 + j] = h;
+        const float v = __bfloat162float(h);
+        s1 += v; s2 = fmaf(v, v, s2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0 && stats) {
+        atomicAdd(stats + col0 + j, red[0][0] + red[0][1] + red[0][2] + red[0][3]);
+        atomicAdd(stats + stats_stride + col0 + j, red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+    }
+}
+// gradWeight[j][k] += sum_n g_y[n][col0 + j] * noise[n][k]   (the branch's gradBias comes from the block's partial column sums)
+__global__ void __launch_bounds__(128) noise_wgrad_kernel(const bf16 *__restrict__ g, int pitch, int col0, const float *__restrict__ noise,
+        float *__restrict__ gw, int B, int nz) {
+    pdl_trigger(); pdl_wait();
+    const int j = blockIdx.x;
+    extern __shared__ float gcol[];              // [B]
+    for (int n = threadIdx.x; n < B; n += blockDim.x) gcol[n] = __bfloat162float(g[(int64_t)n * pitch + col0 + j]);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nz; k += blockDim.x) {
+        float acc = 0.f;
+        for (int n = 0; n < B; ++n) acc = fmaf(gcol[n], __bfloat162float(__float2bfloat16(noise[(int64_t)n * nz + k])), acc);
+        gw[(int64_t)j * nz + k] += acc;
+    }
+}
+// conditionAdv (train.lua:158-180): the discriminator's first layer is a pair of 5x5 / stride-2 convolutions (context: pad 2 on 128x128,
+// prediction: pad 34 on 64x64, both giving 64x64 maps) joined along the channel axis.  Both run as GEMMs over an explicit window buffer
+// col[m = (n, oy, ox)][k = 4 * (5u + v) + c] of a 4-channel-padded image, K padded from 100 to 128 with zeros.
+static const int K5 = 128;
+__global__ void __launch_bounds__(256) im2col5_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ col, int N, int H, int W, int OH, int OW, int pad) {
+    pdl_trigger(); pdl_wait();
+    const int64_t total = (int64_t)N * OH * OW * 16;         // one 16-byte vector (two taps) per thread
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i & 15); int64_t r = i >> 4;
+        const int ox = (int)(r % OW), oy = (int)((r / OW) % OH), n = (int)(r / ((int64_t)OW * OH));
+        uint2 v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int tap = 2 * j + h, u = tap / 5, vv = tap - 5 * u;
+            const int iy = 2 * oy - pad + u, ix = 2 * ox - pad + vv;
+            v[h] = make_uint2(0u, 0u);
+            if (tap < 25 && iy >= 0 && iy < H && ix >= 0 && ix < W) v[h] = __ldg(reinterpret_cast<const uint2 *>(x) + ((int64_t)n * H + iy) * W + ix);
+        }
+        reinterpret_cast<uint4 *>(col)[i] = make_uint4(v[0].x, v[0].y, v[1].x, v[1].y);
+    }
+}
+// adjoint of im2col5 (gather form): gx[n, iy, ix, c] = sum over the taps (u, v) with iy + pad - u and ix + pad - v even and in range
+__global__ void __launch_bounds__(256) col2im5_kernel(const bf16 *__restrict__ col, bf16 *__restrict__ gx, int N, int H, int W, int OH, int OW, int pad) {
+    pdl_trigger(); pdl_wait();
+    const int64_t total = (int64_t)N * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % W), iy = (int)((i / W) % H), n = (int)(i / ((int64_t)W * H));
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int u = (iy + pad) & 1; u < 5; u += 2) {
+            const int oy = (iy + pad - u) >> 1;
+            if (oy < 0 || oy >= OH) continue;
+            for (int v = (ix + pad) & 1; v < 5; v += 2) {
+                const int ox = (ix + pad - v) >> 1;
+                if (ox < 0 || ox >= OW) continue;
+                const uint2 w = __ldg(reinterpret_cast<const uint2 *>(col + (((int64_t)n * OH + oy) * OW + ox) * K5 + 4 * (5 * u + v)));
+                acc[0] += __uint_as_float(w.x << 16); acc[1] += __uint_as_float(w.x & 0xFFFF0000u);
+                acc[2] += __uint_as_float(w.y << 16); acc[3] += __uint_as_float(w.y & 0xFFFF0000u);
+            }
+        }
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+        reinterpret_cast<uint2 *>(gx)[i] = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+    }
+}
+
 }  // namespace nhwc

@@ -18,7 +18,7 @@
 
 namespace {
 
-enum BlockType { CONV_S2, CONV_V4, FULL_S2, FULL_V4, HEAD };
+enum BlockType { CONV_S2, CONV_V4, FULL_S2, FULL_V4, HEAD, JOIN5 };
 
 struct Tensor {
     bf16 *p = nullptr;
@@ -39,6 +39,17 @@ struct Block {
     int64_t w_off = 0, b_off = 0, g_off = -1, be_off = -1, w_count = 0;
     // THNN flat offsets
     int64_t t_w_off = 0, t_b_off = 0, t_g_off = -1, t_be_off = -1;
+    // noiseGen (train.lua:109-124), bottleneck block only: nz extra channels appended to the conv output by a 1x1 convolution of the noise
+    // vector; Cout / Coutp / the BN cover Cs + nz channels, the block's own conv (weights, bias, GEMMs) the first Cs
+    int nz = 0;
+    int64_t nw_off = 0, nb_off = 0, t_nw_off = 0, t_nb_off = 0;
+    // conditionAdv (train.lua:158-180), JOIN5 block: the context branch's operands (the block's own fields describe the prediction branch;
+    // the master weight is one [2*Cs][K5] matrix, context rows first, and one bias vector of 2*Cs entries)
+    Tensor in2;                             // the context image (the trainer's real_ctx)
+    bf16 *col2 = nullptr;                   // window buffer of the context branch
+    int64_t t_w2_off = 0, t_b2_off = 0;
+    int pad5 = 0, pad5_2 = 0;
+    int nbias() const { return Cout - nz; }
     Tensor in, y, a, g;                     // input, conv output (BN blocks), activation output, gradient buffer
     bf16 *col = nullptr;                    // im2col of the thin large-side tensor (forward input or backward gradient);
                                             // V4 blocks on maps larger than 4x4 (fineSize 256): the 4x4 window buffer [M][16*Clp]
@@ -60,6 +71,7 @@ struct Block {
     float *bias_exp = nullptr;              // G1: bias expanded over the 16 taps
     float *bias_inf = nullptr;              // inference engine: conv bias with the BN shift folded in (per GEMM column)
     TcPlan p_fwd, p_dgrad, p_wgrad;
+    TcPlan p_fwd2, p_wgrad2;                // JOIN5: context branch
     bool has_dgrad = false;
 };
 
@@ -162,6 +174,8 @@ struct cenn_trainer {
     float clip_mv = -1.f;                 // maskValue baked into the captured clip-mode graphs
     // frame mode (cenn_trainer_step_frames_host): whole decoded frames + loader draws in, crop / mask / random blocks on the device
     uint8_t *fr_u8 = nullptr, *fr_mask = nullptr; int *fr_tab = nullptr; size_t fr_u8_cap = 0, fr_mask_cap = 0;
+    float *noise = nullptr;               // noiseGen: this step's noise draw [B][nz] fp32 (cenn_trainer_set_noise_*)
+    bool join_ctx_done = false;           // program construction: the context branch of conditionAdv's first layer has been emitted for this step
     bool infer = false;                   // inference engine (cenn_inpainter_*): forward plans only, BN folded into weights and bias
     int infer_n = 0;                      // tiles converted in / out by the current forward call
 };
@@ -188,7 +202,7 @@ int pad_thin(int C) { return C <= 4 ? 4 : (C <= 16 ? 16 : round_up(C, 64)); }
 int pad_wide(int C) { return C % 64 == 0 ? C : (C < 64 ? 64 : round_up(C, 8)); }
 
 // ---- network description -------------------------------------------------------------------------------------
-struct Spec { BlockType type; int Cs, Cl; bool bn; int act; };
+struct Spec { BlockType type; int Cs, Cl; bool bn; int act; int nz = 0; };
 
 std::vector<Spec> spec_G(const cenn_trainer_config &c) {
     int nc = c.variant == 1 ? c.nc * c.predLen : c.nc, nef = c.nef, ngf = c.ngf, nB = c.nBottleneck;
@@ -198,8 +212,9 @@ std::vector<Spec> spec_G(const cenn_trainer_config &c) {
     v.push_back({CONV_S2, nef * 2, nef, true, nhwc::ACT_LEAKY});
     v.push_back({CONV_S2, nef * 4, nef * 2, true, nhwc::ACT_LEAKY});
     v.push_back({CONV_S2, nef * 8, nef * 4, true, nhwc::ACT_LEAKY});
-    v.push_back({CONV_V4, nB, nef * 8, true, nhwc::ACT_LEAKY});       // E6 + netG's BN(nBottleneck) + LeakyReLU
-    v.push_back({FULL_V4, nB, ngf * 8, true, nhwc::ACT_RELU});        // G1: Cs = nBottleneck (input), Cl = ngf*8
+    const int nz = (c.variant == 0 && c.noiseGen) ? c.nz : 0;         // train.lua:109-124: [encoder | 1x1 conv of the noise] -> BN(nBottleneck + nz)
+    v.push_back({CONV_V4, nB, nef * 8, true, nhwc::ACT_LEAKY, nz});   // E6 + netG's BN(nz_size) + LeakyReLU
+    v.push_back({FULL_V4, nB + nz, ngf * 8, true, nhwc::ACT_RELU});   // G1: Cs = nz_size (input), Cl = ngf*8
     v.push_back({FULL_S2, ngf * 8, ngf * 4, true, nhwc::ACT_RELU});
     v.push_back({FULL_S2, ngf * 4, ngf * 2, true, nhwc::ACT_RELU});
     v.push_back({FULL_S2, ngf * 2, ngf, true, nhwc::ACT_RELU});
@@ -213,6 +228,9 @@ std::vector<Spec> spec_D(const cenn_trainer_config &c) {
     if (c.variant == 1) {
         v.push_back({CONV_S2, ndf / 2, nc, false, nhwc::ACT_LEAKY});
         v.push_back({CONV_S2, ndf, ndf / 2, false, nhwc::ACT_LEAKY});
+    } else if (c.conditionAdv) {                                       // train.lua:158-180: D also sees the context
+        v.push_back({JOIN5, ndf, nc, false, nhwc::ACT_LEAKY});        // two 5x5 / stride-2 convs -> JoinTable(2) -> LeakyReLU: 2*ndf x 64 x 64
+        v.push_back({CONV_S2, ndf, ndf * 2, true, nhwc::ACT_LEAKY});
     } else {
         v.push_back({CONV_S2, ndf, nc, false, nhwc::ACT_LEAKY});
     }
@@ -246,17 +264,24 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             case CONV_S2: REQUIRE(cur.H % 2 == 0 && cur.H >= 2, "conv input size %d not even", cur.H); b.h = cur.H / 2; b.w = cur.W / 2; oh = b.h; ow = b.w; out_small = true; break;
             case CONV_V4: case HEAD: REQUIRE(cur.H >= 4 && cur.W >= 4 && cur.H <= 16, "4x4 valid conv expects a 4x4 .. 16x16 input, got %dx%d", cur.H, cur.W);
                 b.h = cur.H - 3; b.w = cur.W - 3; oh = b.h; ow = b.w; out_small = true; break;
+            case JOIN5: REQUIRE(i == 0 && t->real_ctx.p && t->real_ctx.H == 2 * cur.H && cur.Cp == 4 && t->real_ctx.Cp == 4 && sp.Cs % 64 == 0,
+                                "conditionAdv: the joined first layer needs a 4-channel-padded prediction of half the context size and ndf %% 64 == 0");
+                b.h = cur.H; b.w = cur.W; oh = b.h; ow = b.w; out_small = false; b.in2 = t->real_ctx; b.pad5 = 2 + cur.H / 2; b.pad5_2 = 2; break;
             case FULL_V4: REQUIRE(cur.H >= 1 && cur.H <= 13, "G1 expects a 1x1 .. 13x13 input, got %dx%d", cur.H, cur.W); b.h = cur.H; b.w = cur.W; oh = cur.H + 3; ow = cur.W + 3; out_small = false; break;
             default: b.h = cur.H; b.w = cur.W; oh = 2 * cur.H; ow = 2 * cur.W; out_small = false; break;
         }
         // channel padding: the large side of an s2 layer is either thin (im2col) or a multiple of 64 (TMA gather)
-        if (out_small) { b.Clp = cur.Cp; REQUIRE(cur.C == sp.Cl, "channel mismatch at block %zu", i); }
+        if (out_small || sp.type == JOIN5) { b.Clp = cur.Cp; REQUIRE(cur.C == sp.Cl, "channel mismatch at block %zu", i); }
         else { b.Csp = cur.Cp; REQUIRE(cur.C == sp.Cs, "channel mismatch at block %zu", i); }
         bool next_needs_wide = false;   // does the next block gather this output as its large side?
         if (i + 1 < specs.size() && specs[i + 1].type == CONV_S2) next_needs_wide = true;
-        if (out_small) {
-            b.Cout = sp.Cs;
-            b.Csp = sp.type == HEAD ? 1 : (next_needs_wide ? pad_wide(sp.Cs) : round_up(sp.Cs, 8));
+        if (sp.type == JOIN5) {
+            b.Cout = 2 * sp.Cs; b.Csp = b.Coutp = 2 * sp.Cs;
+        } else if (out_small) {
+            if (sp.nz) REQUIRE(sp.type == CONV_V4 && cur.H == 4 && sp.Cs % 8 == 0, "noiseGen: the noise branch joins a 1x1 bottleneck (fineSize 128) with nBottleneck %% 8 == 0");
+            b.nz = sp.nz;
+            b.Cout = sp.Cs + sp.nz;
+            b.Csp = sp.type == HEAD ? 1 : (next_needs_wide ? pad_wide(b.Cout) : round_up(b.Cout, 8));
             if (sp.type == CONV_S2 && b.Csp % 64 != 0 && b.Csp > 16 && next_needs_wide) b.Csp = round_up(b.Csp, 64);
             b.Coutp = b.Csp;
         } else {
@@ -269,11 +294,28 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         if (sp.type == FULL_S2 || sp.type == CONV_S2) REQUIRE(b.thin || b.Clp % 64 == 0, "block %zu: large-side channels %d not a multiple of 64", i, b.Clp);
         if (sp.type == FULL_S2) REQUIRE(b.Csp % 64 == 0, "block %zu: small-side channels %d not a multiple of 64", i, b.Csp);
         // parameters: weight master [Cs][16][Clp] then bias[Cout]; BN gamma, beta
-        b.w_off = off; b.w_count = (int64_t)sp.Cs * 16 * b.Clp; off += b.w_count; off = (off + 7) & ~int64_t(7);
-        b.b_off = off; off += b.Cout; off = (off + 7) & ~int64_t(7);
-        bias_segs.push_back(b.b_off); bias_segs.push_back(b.Cout);
+        // (G1's weight rows are padded to the input pitch Csp: rows >= Cs stay zero -- the K extent of its GEMMs is the pitch)
+        b.w_off = off;
+        b.w_count = sp.type == JOIN5 ? (int64_t)2 * sp.Cs * nhwc::K5 : (int64_t)(sp.type == FULL_V4 ? b.Csp : sp.Cs) * 16 * b.Clp;
+        off += b.w_count; off = (off + 7) & ~int64_t(7);
+        b.b_off = off; off += b.nbias(); off = (off + 7) & ~int64_t(7);
+        bias_segs.push_back(b.b_off); bias_segs.push_back(b.nbias());
+        if (sp.type == JOIN5) {                 // ParallelTable{context conv, prediction conv}: [w, b] of the context branch first
+            b.t_w2_off = toff; toff += (int64_t)sp.Cs * sp.Cl * 25;
+            b.t_b2_off = toff; toff += sp.Cs;
+            b.t_w_off = toff; toff += (int64_t)sp.Cs * sp.Cl * 25;
+            b.t_b_off = toff; toff += sp.Cs;
+        } else {
         b.t_w_off = toff; toff += (int64_t)sp.Cs * sp.Cl * 16;
-        b.t_b_off = toff; toff += b.Cout;
+        b.t_b_off = toff; toff += b.nbias();
+        }
+        if (b.nz) {                             // netG_noise's 1x1 conv follows netE in Module:getParameters order, before the joined BN
+            b.nw_off = off; off += (int64_t)b.nz * b.nz; off = (off + 7) & ~int64_t(7);
+            b.nb_off = off; off += b.nz; off = (off + 7) & ~int64_t(7);
+            bias_segs.push_back(b.nb_off); bias_segs.push_back(b.nz);
+            b.t_nw_off = toff; toff += (int64_t)b.nz * b.nz;
+            b.t_nb_off = toff; toff += b.nz;
+        }
         if (sp.bn) {
             b.g_off = off; off += b.Cout; off = (off + 7) & ~int64_t(7);
             b.be_off = off; off += b.Cout; off = (off + 7) & ~int64_t(7);
@@ -324,6 +366,12 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
             b.col = dalloc<bf16>(t, b.col_rows * b.col_k);
             if (!b.col) return 1;
             if (sp.type != FULL_V4) { b.colg = dalloc<bf16>(t, b.col_rows * b.col_k); if (!b.colg) return 1; }
+        }
+        if (sp.type == JOIN5) {
+            REQUIRE(!t->infer, "the inference engine builds generators only");
+            b.col_rows = (int64_t)N * oh * ow; b.col_k = nhwc::K5;
+            b.col = dalloc<bf16>(t, b.col_rows * b.col_k); b.col2 = dalloc<bf16>(t, b.col_rows * b.col_k); b.colg = dalloc<bf16>(t, b.col_rows * b.col_k);
+            if (!b.col || !b.col2 || !b.colg) return 1;
         }
         if (b.thin && !(t->infer && sp.type != CONV_S2)) {
             b.col_rows = (int64_t)N * b.h * b.w; b.col_k = 16 * b.Clp;
@@ -394,7 +442,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                         if (tc_plan_dgrad_s2(s, &b.p_fwd, b.in.p, b.Wt, b.a.p, N, b.h, b.w, b.Csp, b.Clp, b.Clp, b.cl_rows, ep)) return 1;
                     }
                     break;
-                case HEAD: REQUIRE(false, "the inference engine builds generators only");
+                case HEAD: case JOIN5: REQUIRE(false, "the inference engine builds generators only");
             }
         }
         return 0;
@@ -412,9 +460,10 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
     for (Block &b : net.blocks) {
         if (b.type == HEAD) continue;
         nhwc::FoldJob j;
-        j.src = b.part; j.dst = net.grad + b.b_off; j.rows = b.part_rows; j.C = b.Cout;
+        j.src = b.part; j.dst = net.grad + b.b_off; j.rows = b.part_rows; j.C = b.nbias();
         if (b.Coutp >= 8) { j.stride = b.Coutp; j.fold = 1; j.fold_stride = 0; } else { j.stride = 8; j.fold = 2; j.fold_stride = 4; }
         net.fold_host.push_back(j);
+        if (b.nz) { j.src = b.part + b.nbias(); j.dst = net.grad + b.nb_off; j.C = b.nz; net.fold_host.push_back(j); }   // the noise conv's gradBias
     }
     net.fold_jobs = dalloc<nhwc::FoldJob>(t, net.fold_host.size());
     if (!net.fold_jobs) return 1;
@@ -472,7 +521,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                 if (tc_plan_gemm(s, &b.p_fwd, a_fwd, Wf, fwd_out, Mr, b.Cs, K, b.Csp, ep_f)) return 1;
                 if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p, a_fwd, gW, Mr, b.Cs, b.Csp, K, 1.f, acc_mode)) return 1;
                 { TcEpilogue ep_m = ep_n; ep_m.b_mn = true;     // dgrad = g [M,Cs] x Wf [Cs][K]
-                  if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, b.P > 1 ? b.colg : dgrad_out, Mr, K, b.Csp, K, ep_m)) return 1; }
+                  if (tc_plan_gemm(s, &b.p_dgrad, b.g.p, Wf, b.P > 1 ? b.colg : dgrad_out, Mr, K, b.nz ? b.Cs : b.Csp, K, ep_m, b.Csp)) return 1; }
                 break;
             }
             case FULL_V4: {
@@ -505,6 +554,22 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
                 }
                 break;
             }
+            case JOIN5: {
+                // forward: a[:, 0:Cs] = leaky(col2 x Wctx^T + b), a[:, Cs:2Cs] = leaky(col x Wpred^T + b); weights K-major [Cs][K5] per branch
+                const int K = nhwc::K5, Cs = b.Cs;
+                TcEpilogue ep2 = ep_f, ep1 = ep_f;
+                ep1.bias = net.master + b.b_off + Cs;
+                if (tc_plan_gemm(s, &b.p_fwd2, b.col2, Wf, fwd_out, M, Cs, K, 2 * Cs, ep2)) return 1;
+                if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf + (int64_t)Cs * K, fwd_out + Cs, M, Cs, K, 2 * Cs, ep1)) return 1;
+                if (tc_plan_wgrad_plain(s, &b.p_wgrad2, b.g.p, b.col2, gW, M, Cs, 2 * Cs, K, 1.f, 1)) return 1;
+                if (tc_plan_wgrad_plain(s, &b.p_wgrad, b.g.p + Cs, b.col, gW + (int64_t)Cs * K, M, Cs, 2 * Cs, K, 1.f, 1)) return 1;
+                // gradient w.r.t. the prediction (fGx, train.lua:369-371 takes df_dg[2]): window gradients = g[:, Cs:2Cs] x Wpred, then the overlap-add
+                { TcEpilogue ep_m = ep_n; ep_m.b_mn = true;
+                  if (tc_plan_gemm(s, &b.p_dgrad, b.g.p + Cs, Wf + (int64_t)Cs * K, b.colg, M, K, Cs, K, ep_m, 2 * Cs)) return 1; }
+                if (!dgrad_out) { dgrad_out = dalloc<bf16>(t, b.in.elems()); if (!dgrad_out) return 1; }
+                if (&net == &t->D) { t->df_dg = b.in; t->df_dg.p = dgrad_out; }
+                break;
+            }
             case HEAD: break;
         }
     }
@@ -534,6 +599,22 @@ void emit_im2col(T *t, const Tensor &L, bf16 *col, int h, int w) {
         else { cenn_set_error("im2col: unsupported thin channel count %d", Lc.Cp); return 1; }
         KLAUNCH(s); return 0;
     });
+}
+// 5x5 / stride-2 windows of a 4-channel-padded image (conditionAdv's first layer): x -> col[(n,oy,ox)][K5]
+void emit_im2col5(T *t, const Tensor &x, bf16 *col, int oh, int ow, int pad) {
+    cenn_state *s = t->s;
+    Tensor xc = x;
+    emit(t, "im2col5", [s, xc, col, oh, ow, pad]() {
+        LK(nhwc::im2col5_kernel, dim3(grid1d(s, (int64_t)xc.N * oh * ow * 16)), dim3(256), 0, s->stream)(xc.p, col, xc.N, xc.H, xc.W, oh, ow, pad);
+        KLAUNCH(s); return 0; });
+    t->prog.back().bytes = 2.0 * ((double)x.N * oh * ow * nhwc::K5 + (double)x.pix() * 4);
+}
+void emit_col2im5(T *t, const bf16 *col, const Tensor &gx, int oh, int ow, int pad) {
+    cenn_state *s = t->s;
+    Tensor gc = gx;
+    emit(t, "col2im5", [s, col, gc, oh, ow, pad]() {
+        LK(nhwc::col2im5_kernel, dim3(grid1d(s, gc.pix())), dim3(256), 0, s->stream)(col, gc.p, gc.N, gc.H, gc.W, oh, ow, pad);
+        KLAUNCH(s); return 0; });
 }
 void reduce_dims(int vec_per_pix, dim3 &block, int &gy);
 // 4x4 / stride-1 windows of an [N,H,W,Cp] map (fineSize 256, V4 blocks): x -> col[(n,oy,ox)][tap][c]
@@ -580,6 +661,18 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
             LK(nhwc::head_fwd_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, s->stream)(x, w, bias, b->sig, B, K); KLAUNCH(s); return 0; });
         return;
     }
+    if (b->type == JOIN5) {
+        // the context branch depends only on the context image and D's weights, both unchanged between the real and the fake sweep of fDx:
+        // its window buffer and its half of the joined activation are computed by the first sweep of a step only (ctx_done)
+        if (!t->join_ctx_done) {
+            emit_im2col5(t, b->in2, b->col2, b->h, b->w, b->pad5_2);
+            emit_plan(t, "conv_fwd", &b->p_fwd2);
+            t->join_ctx_done = true;
+        }
+        emit_im2col5(t, b->in, b->col, b->h, b->w, b->pad5);
+        emit_plan(t, "conv_fwd", &b->p_fwd);
+        return;
+    }
     if (b->thin && b->type == CONV_S2) emit_im2col(t, b->in, b->col, b->h, b->w);
     if (b->bias_exp) {
         const float *bias = master + b->b_off;
@@ -587,6 +680,13 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
     }
     if (b->type == CONV_V4 && b->P > 1) emit_im2col_v4(t, b->in, b->col);
     emit_plan(t, "conv_fwd", &b->p_fwd);
+    if (b->nz) {                              // noiseGen: the 1x1 conv of the noise vector fills columns [Cs, Cs + nz) of the joined tensor (after the
+        const bf16 *w = net.wbf + b->nw_off;  // encoder GEMM, whose last N tile zero-fills up to its tile edge) and adds their BN statistics
+        const float *bias = master + b->nb_off;
+        emit(t, "noise_fwd", [t, s, b, w, bias]() {
+            LK(nhwc::noise_fwd_kernel, dim3(b->nz), dim3(128), 0, s->stream)(t->noise, w, bias, b->y.p, b->Coutp, b->Cs, t->B, b->nz, b->stats, b->stats_cols);
+            KLAUNCH(s); return 0; });
+    }
     if (b->type == FULL_V4 && b->P > 1)       // overlap-add of the 4x4 windows + bias + BN statistics
         emit_col2im_v4(t, b->col, b->bn ? b->y : b->a, master + b->b_off, b->bn ? b->stats : nullptr, b->stats_cols);
     if (b->bn && train && t->cfg.world_size <= 1 && b->Coutp <= 4096 && getenv("CENN_NO_BN_FUSE") == nullptr) {
@@ -770,6 +870,36 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             LK(kern, dim3(dim3(b->part_rows, 1)), dim3(blk), blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->a.p, gb_part, 8, npix / 2, 1, 8, 0.2f);
             KLAUNCH(s); return 0; });
         t->prog.back().bytes = 3.0 * 2.0 * (double)npix * b->Cout;
+    }
+    if (b->nz && want_params) {
+        float *gw = grad + b->nw_off;
+        emit(t, "noise_wgrad", [t, s, b, gw]() {
+            LK(nhwc::noise_wgrad_kernel, dim3(b->nz), dim3(128), (size_t)t->B * sizeof(float), s->stream)(b->g.p, b->Coutp, b->Cs, t->noise, gw, t->B, b->nz);
+            KLAUNCH(s); return 0; });
+    }
+    if (b->type == JOIN5) {
+        // both branches' weight gradients on the side stream; the window gradient + overlap-add of the prediction branch only where the
+        // caller uses it (fGx: netD:updateGradInput, train.lua:369-371).  The gradInputs netD:backward computes in fDx and discards
+        // (both branches) are not computed.
+        if (want_params)
+            for (TcPlan *pl : {&b->p_wgrad2, &b->p_wgrad}) {
+                cudaEvent_t evf; cudaEventCreateWithFlags(&evf, cudaEventDisableTiming); t->events.push_back(evf);
+                t->flops_per_step += pl->flops;
+                emit(t, "wgrad", [t, s, evf, pl]() {
+                    if (t->serial) return tc_launch(s, pl);
+                    if (cenn_check_cuda(cudaEventRecord(evf, s->stream), "event record", __FILE__, __LINE__)) return 1;
+                    if (cenn_check_cuda(cudaStreamWaitEvent(t->side, evf, 0), "stream wait", __FILE__, __LINE__)) return 1;
+                    cudaStream_t keep = s->stream; s->stream = t->side;
+                    int rc = tc_launch(s, pl);
+                    s->stream = keep;
+                    return rc; });
+                t->prog.back().flops = pl->flops;
+            }
+        else if (want_dgrad) {
+            emit_plan(t, "dgrad", &b->p_dgrad);
+            emit_col2im5(t, b->colg, t->df_dg, b->h, b->w, b->pad5);
+        }
+        return;
     }
     if (b->type == FULL_V4 && b->P > 1 && (want_params || (want_dgrad && b->has_dgrad))) emit_im2col_v4(t, b->g, b->col);
     // weight gradient
@@ -979,6 +1109,7 @@ int build_program(T *t) {
     Block *headD = &D.blocks.back();
     Block *lastG = &G.blocks.back();
     t->prog.clear();
+    t->join_ctx_done = false;
     t->g_buckets.clear(); t->d_buckets.clear();
     t->flops_per_step = 0;
     // -- inputs: fp32 NCHW (+ uint8 mask) -> NHWC bf16
@@ -1069,11 +1200,13 @@ int build_program(T *t) {
         cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
         float *g = D.grad;
         emit(t, "gradD_sync", [s, rest, g, ev]() {
+            // the bucket all-reduces (bulk communicator, comm_stream) finish first: two communicators are never in flight at once
+            // (NCCL documents concurrent collectives on two communicators as a hang risk unless both kernels can be co-resident)
+            if (cenn_check_cuda(cudaEventRecord(ev, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
+            if (cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev, 0), "stream wait", __FILE__, __LINE__)) return 1;
             if (cenn_dist_group(1)) return 1;
             for (auto &x : rest) if (cenn_dist_all_reduce_on(s, g + x.first, x.second, 0, s->stream)) return 1;
-            if (cenn_dist_group(0)) return 1;
-            if (cenn_check_cuda(cudaEventRecord(ev, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
-            return cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev, 0), "stream wait", __FILE__, __LINE__); });
+            return cenn_dist_group(0); });
     }
     emit_adam_step(t, D);
     emit_adam(t, D);
@@ -1151,11 +1284,13 @@ int build_program(T *t) {
         cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
         float *g = G.grad;
         emit(t, "gradG_sync", [s, rest, g, ev]() {
+            // the bucket all-reduces (bulk communicator, comm_stream) finish first: two communicators are never in flight at once
+            // (NCCL documents concurrent collectives on two communicators as a hang risk unless both kernels can be co-resident)
+            if (cenn_check_cuda(cudaEventRecord(ev, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
+            if (cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev, 0), "stream wait", __FILE__, __LINE__)) return 1;
             if (cenn_dist_group(1)) return 1;
             for (auto &x : rest) if (cenn_dist_all_reduce_on(s, g + x.first, x.second, 0, s->stream)) return 1;
-            if (cenn_dist_group(0)) return 1;
-            if (cenn_check_cuda(cudaEventRecord(ev, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
-            return cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev, 0), "stream wait", __FILE__, __LINE__); });
+            return cenn_dist_group(0); });
     }
     emit_adam(t, G, t->g_early);
     emit_weight_prep(t, G);
@@ -1266,6 +1401,9 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     REQUIRE(cfg->batchSize >= 1 && cfg->nBottleneck % 8 == 0 && cfg->nef % 64 == 0 && cfg->ngf % 64 == 0 && cfg->ndf % 64 == 0,
             "batchSize >= 1, nBottleneck %% 8 == 0 and nef/ngf/ndf %% 64 == 0 required (got %d, %d, %d/%d/%d)", cfg->batchSize, cfg->nBottleneck, cfg->nef, cfg->ngf, cfg->ndf);
     REQUIRE(cfg->variant == 1 || cfg->overlapPred * 2 <= cfg->fineSize / 2, "overlapPred too large");
+    REQUIRE(!(cfg->noiseGen || cfg->conditionAdv) || (cfg->variant == 0 && cfg->fineSize == 128),
+            "noiseGen / conditionAdv are options of train.lua (image variant, fineSize 128); the video scripts force them off (train_deepernet.lua:55-58)");
+    REQUIRE(!cfg->noiseGen || (cfg->nz >= 1 && cfg->nz <= 1024), "noiseGen: nz must be in 1..1024 (got %d)", cfg->nz);
     REQUIRE(cfg->variant == 0 || cfg->overlapPred == 0, "video variant requires overlapPred == 0 (train_vid_weighted.lua:509)");
     int ncv = cfg->variant == 1 ? cfg->nc * cfg->predLen : cfg->nc;
     REQUIRE(ncv >= 1 && ncv <= 16, "1..16 input channels supported (nc*predLen = %d)", ncv);
@@ -1277,12 +1415,13 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     const bool video = cfg->variant == 1;
     const int dsize = video ? t->F : t->F / 2;
     int rc = 0;
+    rc = rc || alloc_tensor(t, t->real_ctx, t->B, t->F, t->F, ncv, pad_thin(ncv));      // (conditionAdv's first D layer reads it directly)
+    if (t->cfg.noiseGen) { t->noise = dalloc<float>(t, (int64_t)t->B * t->cfg.nz); rc = rc || !t->noise; }
     rc = rc || build_net(t, t->D, spec_D(*cfg), dsize, ncv, true, false);
     rc = rc || build_net(t, t->G, spec_G(*cfg), t->F, ncv, cfg->dead_dgrad != 0, true);
     if (rc) { cenn_trainer_destroy(t); return 1; }
     t->G.lr = (cfg->wtl2 > 0.f && cfg->wtl2 < 1.f) ? cfg->lr * 10.f : cfg->lr;   // train.lua:219-226
     t->D.lr = cfg->lr;
-    rc = rc || alloc_tensor(t, t->real_ctx, t->B, t->F, t->F, ncv, pad_thin(ncv));
     rc = rc || alloc_tensor(t, t->real_aux, t->B, dsize, dsize, ncv, pad_thin(ncv));
     if (video) rc = rc || alloc_tensor(t, t->mask, t->B, t->F, t->F, ncv, pad_thin(ncv));
     t->n_a = (int64_t)t->B * ncv * t->F * t->F; t->n_b = (int64_t)t->B * ncv * dsize * dsize; t->n_m = video ? t->n_a : 0;
@@ -1320,7 +1459,7 @@ int cenn_trainer_destroy(cenn_trainer *t) {
     if (t->fr_mask) cudaFree(t->fr_mask);
     if (t->fr_tab) cudaFree(t->fr_tab);
     for (Net *n : {&t->G, &t->D})
-        for (Block &b : n->blocks) { tc_plan_free(&b.p_fwd); tc_plan_free(&b.p_dgrad); tc_plan_free(&b.p_wgrad); }
+        for (Block &b : n->blocks) { tc_plan_free(&b.p_fwd); tc_plan_free(&b.p_dgrad); tc_plan_free(&b.p_wgrad); tc_plan_free(&b.p_fwd2); tc_plan_free(&b.p_wgrad2); }
     if (t->side) { cudaStreamSynchronize(t->side); cudaStreamDestroy(t->side); }
     if (t->side2) { cudaStreamSynchronize(t->side2); cudaStreamDestroy(t->side2); }
     if (t->side3) { cudaStreamSynchronize(t->side3); cudaStreamDestroy(t->side3); }
@@ -1346,19 +1485,47 @@ int cenn_trainer_param_count(cenn_trainer *t, int net, int64_t *count) {
 static void thnn_to_master(const Net &n, const float *flat, std::vector<float> &m) {
     m.assign(n.nparam, 0.f);
     for (const Block &b : n.blocks) {
+        if (b.type == JOIN5) {           // [Cs][nc][5][5] per branch -> [2*Cs][K5], k = 4 * tap + c; context rows first
+            for (int br = 0; br < 2; ++br)
+                for (int cs = 0; cs < b.Cs; ++cs) {
+                    for (int cl = 0; cl < b.Cl; ++cl)
+                        for (int tp = 0; tp < 25; ++tp)
+                            m[b.w_off + ((int64_t)br * b.Cs + cs) * nhwc::K5 + 4 * tp + cl] = flat[(br ? b.t_w_off : b.t_w2_off) + ((int64_t)cs * b.Cl + cl) * 25 + tp];
+                    m[b.b_off + br * b.Cs + cs] = flat[(br ? b.t_b_off : b.t_b2_off) + cs];
+                }
+            continue;
+        }
+        if (b.nz) {
+            for (int64_t i = 0; i < (int64_t)b.nz * b.nz; ++i) m[b.nw_off + i] = flat[b.t_nw_off + i];
+            for (int c = 0; c < b.nz; ++c) m[b.nb_off + c] = flat[b.t_nb_off + c];
+        }
         for (int cs = 0; cs < b.Cs; ++cs)
             for (int cl = 0; cl < b.Cl; ++cl)
                 for (int tp = 0; tp < 16; ++tp) m[b.w_off + ((int64_t)cs * 16 + tp) * b.Clp + cl] = flat[b.t_w_off + ((int64_t)cs * b.Cl + cl) * 16 + tp];
-        for (int c = 0; c < b.Cout; ++c) m[b.b_off + c] = flat[b.t_b_off + c];
+        for (int c = 0; c < b.nbias(); ++c) m[b.b_off + c] = flat[b.t_b_off + c];
         if (b.bn) for (int c = 0; c < b.Cout; ++c) { m[b.g_off + c] = flat[b.t_g_off + c]; m[b.be_off + c] = flat[b.t_be_off + c]; }
     }
 }
 static void master_to_thnn(const Net &n, const std::vector<float> &m, float *flat) {
     for (const Block &b : n.blocks) {
+        if (b.type == JOIN5) {
+            for (int br = 0; br < 2; ++br)
+                for (int cs = 0; cs < b.Cs; ++cs) {
+                    for (int cl = 0; cl < b.Cl; ++cl)
+                        for (int tp = 0; tp < 25; ++tp)
+                            flat[(br ? b.t_w_off : b.t_w2_off) + ((int64_t)cs * b.Cl + cl) * 25 + tp] = m[b.w_off + ((int64_t)br * b.Cs + cs) * nhwc::K5 + 4 * tp + cl];
+                    flat[(br ? b.t_b_off : b.t_b2_off) + cs] = m[b.b_off + br * b.Cs + cs];
+                }
+            continue;
+        }
+        if (b.nz) {
+            for (int64_t i = 0; i < (int64_t)b.nz * b.nz; ++i) flat[b.t_nw_off + i] = m[b.nw_off + i];
+            for (int c = 0; c < b.nz; ++c) flat[b.t_nb_off + c] = m[b.nb_off + c];
+        }
         for (int cs = 0; cs < b.Cs; ++cs)
             for (int cl = 0; cl < b.Cl; ++cl)
                 for (int tp = 0; tp < 16; ++tp) flat[b.t_w_off + ((int64_t)cs * b.Cl + cl) * 16 + tp] = m[b.w_off + ((int64_t)cs * 16 + tp) * b.Clp + cl];
-        for (int c = 0; c < b.Cout; ++c) flat[b.t_b_off + c] = m[b.b_off + c];
+        for (int c = 0; c < b.nbias(); ++c) flat[b.t_b_off + c] = m[b.b_off + c];
         if (b.bn) for (int c = 0; c < b.Cout; ++c) { flat[b.t_g_off + c] = m[b.g_off + c]; flat[b.t_be_off + c] = m[b.be_off + c]; }
     }
 }
@@ -1446,6 +1613,16 @@ static int step_clips_device(cenn_trainer *t, const float *frames, const uint8_t
     t->launches_per_step = t->s->launches - before;
     return rc;
 }
+static int set_noise(cenn_trainer *t, const float *noise, cudaMemcpyKind kind) {
+    REQUIRE(t && noise, "cenn_trainer_set_noise: null argument");
+    REQUIRE(t->noise, "cenn_trainer_set_noise: the executor was built without noiseGen");
+    API_BEGIN(t->s);
+    CK(cudaMemcpyAsync(t->noise, noise, (size_t)t->B * t->cfg.nz * sizeof(float), kind, t->s->stream));
+    if (kind == cudaMemcpyHostToDevice) CK(cudaStreamSynchronize(t->s->stream));     // the host buffer may be reused on return
+    return 0;
+}
+int cenn_trainer_set_noise_host(cenn_trainer *t, const float *noise) { return set_noise(t, noise, cudaMemcpyHostToDevice); }
+int cenn_trainer_set_noise_device(cenn_trainer *t, const float *noise) { return set_noise(t, noise, cudaMemcpyDeviceToDevice); }
 int cenn_trainer_read_losses(cenn_trainer *t, float *losses) {
     REQUIRE(t && losses, "cenn_trainer_read_losses: null argument");
     API_BEGIN(t->s);

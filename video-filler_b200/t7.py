@@ -171,6 +171,7 @@ class _Reader:
     def __init__(self, f):
         self.f = f
         self.objects = {}
+        self.stale = {}            # id(dict registered while reading) -> (dict, the list it became): patched by load()
 
     def _read(self, fmt, n):
         b = self.f.read(n)
@@ -212,10 +213,14 @@ class _Reader:
             for _ in range(n):
                 k = self.obj()
                 d[k] = self.obj()
+            # Lua has one table type; here a table whose keys are exactly 1..n is a list, and so is the EMPTY table (the writer emits
+            # both [] and {} as a 0-entry table: one fixed mapping keeps a round trip stable).  A back-reference taken while the body
+            # was being read (cyclic structures: nngraph gModules) still points at `d`: it is patched after the whole file is read.
             keys = list(d.keys())
-            if keys and all(isinstance(k, int) for k in keys) and sorted(keys) == list(range(1, len(keys) + 1)):
+            if all(isinstance(k, int) for k in keys) and sorted(keys) == list(range(1, len(keys) + 1)):
                 lst = [d[i] for i in range(1, len(keys) + 1)]
                 self.objects[idx] = lst
+                self.stale[id(d)] = (d, lst)
                 return lst
             return d
         if t == TYPE_TORCH:
@@ -232,7 +237,7 @@ class _Reader:
                 o = TorchObject(cls)
                 self.objects[idx] = o
                 fields = self.obj()
-                o.fields = fields if isinstance(fields, dict) else {"_payload": fields}
+                o.fields = fields if isinstance(fields, dict) else ({} if fields == [] else {"_payload": fields})
                 return o
             self.objects[idx] = o
             return o
@@ -258,7 +263,33 @@ class _Reader:
         return np.lib.stride_tricks.as_strided(np.asarray(st)[off:], shape=size, strides=[s * dt.itemsize for s in stride]).copy()
 
 
+def _patch_stale(root, stale):
+    """Replace every reference to a table dict that turned out to be a list (see _Reader.obj) -- identity and aliasing survive."""
+    if not stale:
+        return root
+    fix = lambda v: stale[id(v)][1] if isinstance(v, dict) and id(v) in stale and stale[id(v)][0] is v else v
+    seen, todo = set(), [root]
+    while todo:
+        o = todo.pop()
+        if id(o) in seen:
+            continue
+        seen.add(id(o))
+        if isinstance(o, list):
+            for i, v in enumerate(o):
+                o[i] = fix(v)
+            todo.extend(v for v in o if isinstance(v, (list, dict, TorchObject)))
+        elif isinstance(o, dict):
+            for k in list(o.keys()):
+                o[k] = fix(o[k])
+            todo.extend(v for v in o.values() if isinstance(v, (list, dict, TorchObject)))
+        elif isinstance(o, TorchObject):
+            o.fields = fix(o.fields) if isinstance(fix(o.fields), dict) else o.fields
+            todo.append(o.fields)
+    return fix(root)
+
+
 def load(path):
     """torch.load(path)."""
     with open(path, "rb") as f:
-        return _Reader(f).obj()
+        r = _Reader(f)
+        return _patch_stale(r.obj(), r.stale)

@@ -214,7 +214,8 @@ class FusedTrainer:
             nBottleneck=opt["nBottleneck"], nef=opt["nef"], ngf=opt["ngf"], ndf=opt["ndf"], nc=opt["nc"],
             predLen=opt.get("predLen", 1), overlapPred=opt["overlapPred"], wtl2=opt["wtl2"],
             weight_nomask=opt.get("weight_nomask", 0.0), wtgdl=opt.get("wtgdl", 0.0), lr=opt["lr"], beta1=opt["beta1"],
-            precision={"fp32": 0, "bf16": 1}[precision], world_size=world_size, rank=rank, dead_dgrad=dead_dgrad)
+            precision={"fp32": 0, "bf16": 1}[precision], world_size=world_size, rank=rank, dead_dgrad=dead_dgrad,
+            noiseGen=1 if opt.get("noiseGen") else 0, nz=opt.get("nz", 100), conditionAdv=1 if opt.get("conditionAdv") else 0)
         self.cfg = cfg
         h = C.c_void_p()
         api().cenn_trainer_create(state(), C.byref(cfg), C.byref(h))
@@ -267,8 +268,16 @@ class FusedTrainer:
         assert stats.size == self.bn_stat_count(net)
         api().cenn_trainer_set_bn_stats_host(self.h, net, stats.ctypes.data_as(C.c_void_p))
 
-    def step_host(self, a, b, mask=None):
+    def set_noise(self, noise):
+        """noiseGen: the noise draw [B, nz(,1,1)] of the next step (train.lua:319-323 redraws it inside fDx; here the caller draws it)."""
+        noise = np.ascontiguousarray(noise, np.float32)
+        assert noise.size == self.opt["batchSize"] * self.opt.get("nz", 100)
+        api().cenn_trainer_set_noise_host(self.h, noise.ctypes.data_as(C.c_void_p))
+
+    def step_host(self, a, b, mask=None, noise=None):
         """One step from host fp32 NCHW arrays (H2D + step + D2H of the losses)."""
+        if noise is not None:
+            self.set_noise(noise)
         a = np.ascontiguousarray(a, np.float32)
         b = np.ascontiguousarray(b, np.float32)
         m = np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.c_void_p) if mask is not None else None
