@@ -20,7 +20,9 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("variant,env", [("image", {}), ("video", {}), ("image", {"CENN_NO_XR": "1"}), ("image", {"CENN_FP32_BUCKETS": "1"})])
+# ("image+branches": train.lua's noiseGen + conditionAdv options; the flag is not an environment variable and is stripped below)
+@pytest.mark.parametrize("variant,env", [("image", {}), ("video", {}), ("image", {"CENN_NO_XR": "1"}), ("image", {"CENN_FP32_BUCKETS": "1"}),
+                                         ("image", {"CENN_XR_PULL": "1"}), ("image", {"--branches": "1"})])
 def test_data_parallel_step_equals_global_batch_step(variant, env):
     n = _ngpu()
     if n < 2:
@@ -29,6 +31,9 @@ def test_data_parallel_step_equals_global_batch_step(variant, env):
     port = 29500 + (hash((variant, tuple(sorted(env)))) % 400)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", "dp_parity.py"), "--variant", variant]
+    env = dict(env)
+    if env.pop("--branches", None):
+        cmd.append("--branches")
     e = dict(os.environ); e.update(env)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=e, cwd=ROOT)
     lines = [l for l in r.stdout.splitlines() if l.startswith("DP_PARITY ")]

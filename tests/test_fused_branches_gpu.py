@@ -23,7 +23,8 @@ B, NB, NZ = 8, 256, 100
 
 def _pair(**extra):
     from video_filler_b200 import models, train
-    kw = dict(batchSize=B, nBottleneck=NB, nef=64, ngf=64, ndf=64, **extra)
+    kw = dict(batchSize=B, nBottleneck=NB, nef=64, ngf=64, ndf=64)
+    kw.update(extra)
     orc = ostep.StepOracle(onets.default_opt("image", **kw), seed=1234, dtype=np.float64)
     trn = train.FusedTrainer(models.default_opt("image", **kw), precision="bf16")
     assert trn.param_count(0) == orc.pG.size and trn.param_count(1) == orc.pD.size
@@ -67,7 +68,9 @@ def fast_oracle():
     torch_engine.disable()
 
 
-@pytest.mark.parametrize("extra", [{"noiseGen": 1, "nz": NZ}, {"conditionAdv": 1}, {"noiseGen": 1, "nz": NZ, "conditionAdv": 1}])
+# (last case: the shipped defaults nBottleneck 4000 + nz 100 -> 4100 joined channels, pitch 4104: the > 4096-channel BN path)
+@pytest.mark.parametrize("extra", [{"noiseGen": 1, "nz": NZ}, {"conditionAdv": 1}, {"noiseGen": 1, "nz": NZ, "conditionAdv": 1},
+                                   {"noiseGen": 1, "nz": NZ, "nBottleneck": 4000}])
 def test_fused_step_with_optional_branches_matches_oracle(cenn, fast_oracle, extra):
     orc, trn = _pair(**extra)
     batch, noise = _batch(orc, np.random.default_rng(4321), extra.get("noiseGen"))

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--per-rank", type=int, default=8)
     ap.add_argument("--nB", type=int, default=256)
     ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--branches", action="store_true", help="image variant with noiseGen + conditionAdv (train.lua:109-124,158-180)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -60,6 +61,8 @@ def main():
     kw = dict(nBottleneck=args.nB, nef=64, ngf=64, ndf=64)
     if args.variant == "video":
         kw.update(predLen=2, wtgdl=0.5)
+    if args.branches:
+        kw.update(noiseGen=1, nz=100, conditionAdv=1)
     opt_l = models.default_opt(args.variant, batchSize=Bl, **kw)
     opt_g = models.default_opt(args.variant, batchSize=Bg, **kw)
     rng = np.random.default_rng(7)
@@ -67,15 +70,17 @@ def main():
     pD = util.params_flat(util.weights_init(util.describe_netD(opt_g), rng))
     drng = np.random.default_rng(11)
     batches = []
+    noises = []
     for _ in range(args.steps):
         batches.append(synth.image_batch(Bg, 128, 4, drng) if args.variant == "image" else synth.video_batch(Bg, 6, 128, opt_g["maskValue"], drng))
+        noises.append(drng.uniform(-1, 1, (Bg, 100)).astype(np.float32) if args.branches else None)       # each rank takes its rows of the global draw
 
     trn = train.FusedTrainer(opt_l, precision="bf16", world_size=world, rank=rank)
     trn.set_params(0, pG); trn.set_params(1, pD)
     sl = slice(Bl * rank, Bl * rank + Bl)
     losses, bn_after_1, params_after_1 = [], None, None
     for i, b in enumerate(batches):
-        losses.append(trn.step_host(*[np.ascontiguousarray(x[sl]) for x in b]))
+        losses.append(trn.step_host(*[np.ascontiguousarray(x[sl]) for x in b], noise=None if noises[i] is None else noises[i][sl]))
         if i == 0:
             bn_after_1 = (trn.get_bn_stats(0), trn.get_bn_stats(1))
             params_after_1 = (trn.get_params(0), trn.get_params(1))
@@ -89,7 +94,7 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
 
-    out = {"variant": args.variant, "world": world, "per_rank": Bl, "steps": args.steps, "env": {k: os.environ.get(k) for k in ("CENN_NO_XR", "CENN_FP32_BUCKETS")},
+    out = {"variant": args.variant, "branches": bool(args.branches), "world": world, "per_rank": Bl, "steps": args.steps, "env": {k: os.environ.get(k) for k in ("CENN_NO_XR", "CENN_FP32_BUCKETS")},
            "replicas_bit_identical": len(set(digests)) == 1, "ok": True, "checks": {}}
     fail = []
     if rank == 0:
@@ -104,7 +109,7 @@ def main():
         ref.set_params(0, pG); ref.set_params(1, pD)
         ref_losses = []
         for i, b in enumerate(batches):
-            ref_losses.append(ref.step_host(*b))
+            ref_losses.append(ref.step_host(*b, noise=noises[i]))
             if i == 0:
                 chk = out["checks"]
                 chk["bn_G_rel"] = rel_err(bn_after_1[0], ref.get_bn_stats(0)); chk["bn_D_rel"] = rel_err(bn_after_1[1], ref.get_bn_stats(1))
