@@ -102,7 +102,7 @@ int set_attr_wgrad() {
 int config_gather(cenn_state *s, TcPlan *pl, int BN, int num_kb, int total_tiles) {
     const int stage_bytes = 128 * 128 + BN * 128;
     const int out_bytes = BN >= 64 ? 128 * BN * 2 : 0;
-    const int fixed = 1024 /*align*/ + out_bytes + 176 /*barriers, tmem slot*/ + 68 * 16 + 256 /*tap tables*/ + 3 * BN * 4 + (BN == 32 ? 4 * 32 * 33 * 4 : 0) + 64;
+    const int fixed = 1024 /*align*/ + out_bytes + 176 /*barriers, tmem slot*/ + 68 * 16 + 256 /*tap tables*/ + 6 * BN * 4 + (BN == 32 ? 4 * 32 * 33 * 4 : 0) + 64;
     // Two co-resident CTAs per SM when the tile is narrow (BN <= 128: 2 x 2*BN TMEM columns fit): the two single-thread
     // loops of a CTA (TMA issue, MMA issue) are instruction-latency bound, a second CTA doubles the issue capacity.
     int per_sm = (BN <= 128 && total_tiles > s->sm_count) ? 2 : 1;
@@ -165,6 +165,7 @@ void fill_epilogue(tc::GatherGemmParams &p, const TcEpilogue &ep, bf16 *out) {
     p.dbg = reinterpret_cast<unsigned long long *>(ep.dbg); p.dbg_flags = ep.dbg_flags;
     p.bias = ep.bias; p.stats = ep.stats; p.stats_stride = ep.stats_stride; p.act = ep.act; p.act_param = ep.act_param;
     p.out_bf16 = ep.no_bf16 ? nullptr : out;
+    p.bwd_y = ep.bwd_y; p.bwd_scale = ep.bwd_scale; p.bwd_shift = ep.bwd_shift; p.bwd_mean = ep.bwd_mean; p.bwd_act = ep.bwd_act; p.bwd_negval = ep.bwd_negval;
 }
 
 // tap geometry of the 4x4 / stride-2 / pad-1 window: input row 2*oy - 1 + u = 2*(oy + DYS[u]) + PYS[u]
@@ -257,7 +258,7 @@ int tc_unpack_grad_add(cenn_state *s, const float *g, float *gw, int Cs, int Cl,
 
 // ------------------------------------------------------------------ plan storage helpers
 static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap larger than the plan slot");
-static_assert(sizeof(tc::GatherGemmParams) <= 1536 && sizeof(tc::WgradParams) <= 1536 && sizeof(tc::PatchDgradParams) <= 1536, "kernel params larger than the plan slot");
+static_assert(sizeof(tc::GatherGemmParams) <= 1664 && sizeof(tc::WgradParams) <= 1664 && sizeof(tc::PatchDgradParams) <= 1664, "kernel params larger than the plan slot");
 static CUtensorMap *planA(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmA); }
 static CUtensorMap *planB(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmB); }
 static CUtensorMap *planO(TcPlan *pl) { return reinterpret_cast<CUtensorMap *>(pl->tmO); }
@@ -346,6 +347,7 @@ int tc_plan_fprop_s2(cenn_state *s, TcPlan *pl, const bf16 *L, const bf16 *Wf, b
     p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cs;
     p.sX = Csp; p.sY = (long long)w * Csp; p.sN = (long long)h * w * Csp;
     fill_epilogue(p, ep, S);
+    REQUIRE(!ep.bwd_y || BN >= 64, "tc_fprop_s2: BN-backward sums need an N tile of 64 or more");
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * N * h * w * (double)Cs * 16.0 * Clp;
     return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles);
@@ -392,6 +394,7 @@ int tc_plan_dgrad_s2(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt, b
     p.sX = 2LL * Clp; p.sY = 2LL * W2 * Clp; p.sN = (long long)H2 * W2 * Clp;
     for (int ph = 0; ph < 4; ++ph) p.phase_off[ph] = ((long long)(ph >> 1) * W2 + (ph & 1)) * Clp;
     fill_epilogue(p, ep, L);
+    REQUIRE(!ep.bwd_y || BN >= 64, "tc_dgrad_s2: BN-backward sums need an N tile of 64 or more");
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * N * h * w * (double)Cl * 16.0 * Csp;
     return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles * 4);
@@ -446,6 +449,8 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
     p.out_w = w; p.out_h = h; p.out_n = N; p.n_valid = Cl; p.Clp = Clp; p.H2 = H2; p.W2 = W2;
     p.out = ep.no_bf16 ? nullptr : L;
     p.bias = ep.bias; p.stats = ep.stats; p.stats_stride = ep.stats_stride; p.act = ep.act; p.act_param = ep.act_param;
+    p.bwd_y = ep.bwd_y; p.bwd_scale = ep.bwd_scale; p.bwd_shift = ep.bwd_shift; p.bwd_mean = ep.bwd_mean; p.bwd_act = ep.bwd_act; p.bwd_negval = ep.bwd_negval;
+    REQUIRE(!ep.bwd_y || BN >= 64, "tc_dgrad_patch: BN-backward sums need an N tile of 64 or more");
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * N * h * w * (double)Cl * 16.0 * Csp;
     const int bstage = 4 * BN * 128, out_bytes = BN >= 64 ? 128 * BN * 2 * (BN >= 128 ? 1 : 2) : 0;
@@ -453,7 +458,7 @@ int tc_plan_dgrad_patch(cenn_state *s, TcPlan *pl, const bf16 *S, const bf16 *Wt
     // thin outputs (3 / 12 channels): the weights of all phases are 8 KB per chunk -- resident for the whole CTA -- and the kernel is bound
     // by the number of S patches (one HBM round trip each) in flight: as many patch buffers as shared memory holds (up to 6)
     const bool resident = thin && p.n_tiles == 1 && 4 * p.chunks <= 8 && getenv("CENN_PATCH_NO_RESIDENT") == nullptr;
-    const int base_fixed = 1024 + out_bytes + 38 * 8 + 3 * BN * 4 + 64;
+    const int base_fixed = 1024 + out_bytes + 38 * 8 + 6 * BN * 4 + 64;
     int per_sm = 1;
     if (resident) {
         stages = 4 * p.chunks;
@@ -518,6 +523,7 @@ int tc_plan_gemm(cenn_state *s, TcPlan *pl, const bf16 *A, const bf16 *B, bf16 *
     p.out_w = M; p.out_h = 1; p.out_n = 1; p.n_valid = Nc;
     p.sX = ldo; p.sY = 0; p.sN = 0;
     fill_epilogue(p, ep, out);
+    REQUIRE(!ep.bwd_y || BN >= 64, "tc_gemm: BN-backward sums need an N tile of 64 or more");
     memcpy(pl->params, &p, sizeof(p));
     pl->flops = 2.0 * M * (double)Nc * K;
     return config_gather(s, pl, BN, p.num_kb, p.m_tiles * p.n_tiles);

@@ -21,6 +21,12 @@ struct TcEpilogue {
     bool no_bf16 = false;
     void *dbg = nullptr;           // optional per-role cycle counters (debug probe)
     int dbg_flags = 0;             // probe only, see tc::GatherGemmParams::dbg_flags
+    // BN-backward sums of the consumer block taken in the epilogue (tc::GatherGemmParams::bwd_y): `stats` / `stats_stride` name the
+    // [2][stride] accumulator (fp32 atomics; zeroed by whoever consumes it), N tile >= 64 only
+    const bf16 *bwd_y = nullptr;
+    const float *bwd_scale = nullptr, *bwd_shift = nullptr, *bwd_mean = nullptr;
+    int bwd_act = 0;
+    float bwd_negval = 0.2f;
     bool b_mn = false;             // dgrad-type / plain GEMM: the weight operand is the MASTER layout Wf [Cs][16*Clp] (or [K][Nc], row stride
                                    // = Nc) read MN-major, instead of a transposed K-major copy (N tile >= 64 only)
 };
@@ -35,7 +41,7 @@ struct TcPlan {
     alignas(64) unsigned char tmA[128];
     alignas(64) unsigned char tmB[128];
     alignas(64) unsigned char tmO[128];   // output tile store (gather GEMM, BN >= 64)
-    alignas(16) unsigned char params[1536];
+    alignas(16) unsigned char params[1664];
     void *kb_dev = nullptr;       // owned device k-block table (gather GEMM)
     double flops = 0;             // algorithmic FLOPs of one launch
     int overwrites = 0;           // wgrad: 1 = the launch stores its result (no accumulation; the target need not be zeroed)

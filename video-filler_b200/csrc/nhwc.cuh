@@ -526,6 +526,22 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_coef_kernel(const bf16 *
         }
     }
 }
+// the coefficient step alone, from sums that a dgrad GEMM epilogue accumulated (tc::bwd_sums_slab): pass-2 coefficients, BN affine gradients,
+// sums re-zeroed for the next use
+__global__ void __launch_bounds__(256) bn_bwd_coef_sums_kernel(float *__restrict__ sums, int Cp, const float *__restrict__ gamma, const float *__restrict__ invstd,
+        const float *__restrict__ mean, float *__restrict__ coef, float *__restrict__ ggamma, float *__restrict__ gbeta, int C, double n) {
+    pdl_trigger(); pdl_wait();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cp) return;
+    const double s = (double)sums[c], d = (double)sums[Cp + c];
+    sums[c] = 0.f; sums[Cp + c] = 0.f;
+    if (c < C) {
+        const double is = invstd[c], A = is * (double)gamma[c], k1 = is * is * d / n;
+        coef[c] = (float)A; coef[C + c] = (float)(A * k1); coef[2 * C + c] = (float)(((double)mean[c] * k1 - s / n) * A);
+        if (ggamma) ggamma[c] += (float)(d * is);
+        if (gbeta) gbeta[c] += (float)s;
+    }
+}
 // sums the partial rows; coefficients for pass 2 + BN parameter gradients.
 // sums_io [2][Cp]: rows > 0: written with the folded sums (the buffer a data-parallel run all-reduces); rows == 0: read.
 // block = (32 channels, 8 row lanes); grid = ceil(C / 32).  coef for pass 2 is stored pre-combined:

@@ -196,6 +196,13 @@ struct GatherGemmParams {
     int stats_stride;
     int act;                 // applied after bias, before the store (stats are taken before the activation)
     float act_param;
+    // [opt] BN-backward sums of the CONSUMER of this output: the output is dLoss/d(activation output) of a BN + activation block whose conv
+    // output is bwd_y (same geometry as the output).  With dz = out * act'(y * scale + shift):  stats[c] += sum dz,
+    // stats[stats_stride + c] += sum dz * (y - mean)  -- the first pass of the BN backward, taken from the tile while it is in shared memory
+    const __nv_bfloat16 *bwd_y;
+    const float *bwd_scale, *bwd_shift, *bwd_mean;
+    int bwd_act;
+    float bwd_negval;
     unsigned long long *dbg; // [opt] per-role cycle counters of CTA 0 (tools/gemm_probe.py)
     int dbg_flags;           // probe only: 1 = issue no MMAs, 2 = no A loads, 4 = no B loads (isolates the TMA feed / the MMA rate)
 };
@@ -255,6 +262,29 @@ __device__ __forceinline__ float apply_act(float f, int act, float param) {
     return f;
 }
 
+// derivative of the consumer's activation from its pre-activation z (nhwc::dact_z): LeakyReLU / ReLU only (the BN blocks' activations)
+__device__ __forceinline__ float bwd_gate(float z, int act, float negval) { return z > 0.f ? 1.f : (act == ACT_LEAKY ? negval : 0.f); }
+// one slab (64 columns) of the BN-backward sums over this warp's 32 tile rows: lane l owns columns 2l, 2l+1; `my_off` is this lane's OWN row
+// offset into y (elements, first column of the n-tile; < 0: row outside the tensor); g comes from the staged bf16 tile
+__device__ __forceinline__ void bwd_sums_slab(const uint8_t *slab, const __nv_bfloat16 *y, long long my_off, int cc, const float *bwd_c, int BNc,
+        int act, float negval, int lane, float *col_acc) {
+    const float sc_a = bwd_c[cc], sc_b = bwd_c[cc + 1], sh_a = bwd_c[BNc + cc], sh_b = bwd_c[BNc + cc + 1], mu_a = bwd_c[2 * BNc + cc], mu_b = bwd_c[2 * BNc + cc + 1];
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+        const long long off = __shfl_sync(0xffffffffu, my_off, r);
+        if (off < 0) continue;                          // warp-uniform
+        const uint32_t wv = *reinterpret_cast<const uint32_t *>(slab + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2));
+        const uint32_t yv = __ldg(reinterpret_cast<const unsigned int *>(y + off + cc));
+        const float ga = __uint_as_float(wv << 16), gb = __uint_as_float(wv & 0xFFFF0000u);
+        const float ya = __uint_as_float(yv << 16), yb = __uint_as_float(yv & 0xFFFF0000u);
+        const float dza = ga * bwd_gate(fmaf(ya, sc_a, sh_a), act, negval), dzb = gb * bwd_gate(fmaf(yb, sc_b, sh_b), act, negval);
+        s1a += dza; s2a = fmaf(dza, ya - mu_a, s2a); s1b += dzb; s2b = fmaf(dzb, yb - mu_b, s2b);
+    }
+    atomicAdd(&col_acc[cc], s1a); atomicAdd(&col_acc[cc + 1], s1b);
+    atomicAdd(&col_acc[BNc + cc], s2a); atomicAdd(&col_acc[BNc + cc + 1], s2b);
+}
+
 template <int BN, bool kProbe>
 __global__ void __launch_bounds__(GEMM_THREADS, BN <= 128 ? 2 : 1)
 gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
@@ -281,7 +311,8 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int *bcs = reinterpret_cast<int *>(phc + 4);                                   // [4][16] B column offsets (MN-major B)
     float *col_acc = reinterpret_cast<float *>(bcs + 64);                           // [2][BN] per-CTA column sums for BN statistics
     float *bias_s = col_acc + 2 * BN;                                              // [BN] bias of the current n-tile
-    float *stage_f = bias_s + BN;                                                  // BN == 32 only: [4 warps][32][33] transposition buffer
+    float *bwd_c = bias_s + BN;                                                    // [3][BN] scale, shift, mean of the consumer BN (bwd_y mode)
+    float *stage_f = bwd_c + 3 * BN;                                               // BN == 32 only: [4 warps][32][33] transposition buffer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_phase = p.m_tiles * p.n_tiles;
@@ -418,6 +449,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int rx = row & bw_mask, ry = (row >> p.bw_log2) & bh_mask, rn = row >> bwh_log2;
         const int act = p.act; const float act_param = p.act_param;
         const bool has_bias = p.bias != nullptr, has_stats = p.stats != nullptr;
+        const bool bwd = kTma && has_stats && p.bwd_y != nullptr;
         int acc = 0; uint32_t acc_ph = 0;
         int stat_key = -1;                               // n-tile the per-CTA column sums belong to
         long long w_tfull = 0, t_begin = prof ? clock64() : 0;
@@ -448,6 +480,10 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if constexpr (kTma) {
                 // ---- bf16 tile -> swizzled smem slabs -> one TMA store per 64-column slab
                 if (has_bias) for (int i = et; i < BN; i += 128) { const int c = nt * BN + i; bias_s[i] = c < p.n_valid ? __ldg(p.bias + c) : 0.f; }
+                if (bwd) for (int i = et; i < BN; i += 128) {
+                    const int c = nt * BN + i; const bool ok = c < p.n_valid;
+                    bwd_c[i] = ok ? __ldg(p.bwd_scale + c) : 0.f; bwd_c[BN + i] = ok ? __ldg(p.bwd_shift + c) : 0.f; bwd_c[2 * BN + i] = ok ? __ldg(p.bwd_mean + c) : 0.f;
+                }
                 if (et == 0) bulk_wait_read0();          // the previous tile's stores have finished reading out_stage
                 epi_bar_sync();
                 const int last_c0 = ((ncols + 31) >> 5) * 32 - 32;
@@ -514,7 +550,12 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         *reinterpret_cast<uint4 *>(slab_row + (((cb + i) ^ (row & 7)) << 4)) = pk;
                     }
                 }
-                if (has_stats) {
+                if (bwd) {
+                    __syncwarp();
+                    const long long my_off = row_ok ? (long long)(n0 + rn) * p.sN + (long long)(y0 + ry) * p.sY + (long long)(x0 + rx) * p.sX + p.phase_off[tc.phase] + (long long)nt * BN : -1;
+                    for (int sl = 0; sl * 64 < ncols; ++sl)
+                        bwd_sums_slab(out_stage + (size_t)sl * (128 * 128) + (size_t)(q * 32) * 128, p.bwd_y, my_off, sl * 64 + 2 * lane, bwd_c, BN, p.bwd_act, p.bwd_negval, lane, col_acc);
+                } else if (has_stats) {
                     // column sums of the STORED (bf16-rounded) values: lane l owns columns 2l, 2l+1 of each slab, over this warp's 32 rows
                     __syncwarp();
                     for (int sl = 0; sl * 64 < ncols; ++sl) {
@@ -650,6 +691,13 @@ struct PatchDgradParams {
     const float *bias;
     float *stats; int stats_stride;
     int act; float act_param;
+    // [opt] BN-backward sums of the CONSUMER of this output: the output is dLoss/d(activation output) of a BN + activation block whose conv
+    // output is bwd_y (same geometry as the output).  With dz = out * act'(y * scale + shift):  stats[c] += sum dz,
+    // stats[stats_stride + c] += sum dz * (y - mean)  -- the first pass of the BN backward, taken from the tile while it is in shared memory
+    const __nv_bfloat16 *bwd_y;
+    const float *bwd_scale, *bwd_shift, *bwd_mean;
+    int bwd_act;
+    float bwd_negval;
 };
 
 template <int BN>
@@ -674,6 +722,7 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 36);            // +288 B
     float *col_acc = reinterpret_cast<float *>(bars + 38);                    // [2][BN]
     float *bias_s = col_acc + 2 * BN;                                         // [BN]
+    float *bwd_c = bias_s + BN;                                               // [3][BN] scale, shift, mean of the consumer BN (bwd_y mode)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
@@ -797,6 +846,7 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
         const int rx = row & 7, rn = (row >> 3) & (p.bn - 1), ry = row >> (3 + p.bn_log2);
         const int act = p.act; const float act_param = p.act_param;
         const bool has_bias = p.bias != nullptr, has_stats = p.stats != nullptr;
+        const bool bwd = kTma && has_stats && p.bwd_y != nullptr;
         int set = 0; uint32_t set_ph = 0;
         int stat_key = -1;
         int ob = 0;                                       // staging buffer of the next phase tile
@@ -822,6 +872,10 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
             int ncols = p.n_valid - nt * BN; ncols = ncols > BN ? BN : ncols;
             if constexpr (kTma) {
                 if (has_bias) for (int i = et; i < BN; i += 128) { const int c = nt * BN + i; bias_s[i] = c < p.n_valid ? __ldg(p.bias + c) : 0.f; }
+                if (bwd) for (int i = et; i < BN; i += 128) {
+                    const int c = nt * BN + i; const bool ok = c < p.n_valid;
+                    bwd_c[i] = ok ? __ldg(p.bwd_scale + c) : 0.f; bwd_c[BN + i] = ok ? __ldg(p.bwd_shift + c) : 0.f; bwd_c[2 * BN + i] = ok ? __ldg(p.bwd_mean + c) : 0.f;
+                }
                 const int last_c0 = ((ncols + 31) >> 5) * 32 - 32;
 #pragma unroll 1
                 for (int phs = 0; phs < 4; ++phs) {
@@ -877,7 +931,12 @@ patch_dgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
                             *reinterpret_cast<uint4 *>(slab_row + (((cb + i) ^ (row & 7)) << 4)) = pk;
                         }
                     }
-                    if (has_stats) {
+                    if (bwd) {
+                        __syncwarp();
+                        const long long my_off = row_ok ? (((long long)(n0 + rn) * p.H2 + 2 * (y0 + ry) + (phs >> 1)) * p.W2 + 2 * (x0 + rx) + (phs & 1)) * p.Clp + (long long)nt * BN : -1;
+                        for (int sl = 0; sl * 64 < ncols; ++sl)
+                            bwd_sums_slab(stage + (size_t)sl * (128 * 128) + (size_t)(q * 32) * 128, p.bwd_y, my_off, sl * 64 + 2 * lane, bwd_c, BN, p.bwd_act, p.bwd_negval, lane, col_acc);
+                    } else if (has_stats) {
                         __syncwarp();
                         for (int sl = 0; sl * 64 < ncols; ++sl) {
                             const uint8_t *slab = stage + (size_t)sl * (128 * 128) + (size_t)(q * 32) * 128;

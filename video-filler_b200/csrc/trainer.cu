@@ -67,6 +67,8 @@ struct Block {
     float *stats = nullptr, *bsums = nullptr, *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *coef = nullptr;
     float *running = nullptr;               // [2][Cout] running_mean, running_var
     int stats_cols = 0, fold = 1;
+    bool bwd_epi = false;                   // the first pass of this block's BN backward (sum dz, sum dz (y - mean)) is taken by the epilogue of the
+                                            // dgrad GEMM that produces g (the NEXT block's p_dgrad) straight into bsums: no bn_bwd_reduce launch
     float *sig = nullptr, *gpre = nullptr;  // head
     float *bias_exp = nullptr;              // G1: bias expanded over the 16 taps
     float *bias_inf = nullptr;              // inference engine: conv bias with the BN shift folded in (per GEMM column)
@@ -491,6 +493,20 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         else { ep_f.act = b.act; ep_f.act_param = 0.2f; }
         bf16 *fwd_out = b.bn ? b.y.p : b.a.p;
         TcEpilogue ep_n;
+        // EXPERIMENT (CENN_BWD_EPI=1, off by default): BN-backward sums of the previous block from this block's dgrad epilogue -- the dgrad output
+        // must be the previous block's gradient tensor itself, with GEMM columns = channels (not the window buffers / (tap, channel) columns of
+        // the 4x4 valid layers).  Correct (tests pass with it on) but much SLOWER on B200 (round 2: image step 4.24 vs 2.98 ms, video 3.42 vs
+        // 2.77 ms): the epilogue's four warps read y with a few dozen loads in flight where the stand-alone reduction keeps thousands, and a
+        // CTA has only one or two tiles to hide that latency behind; staging y by TMA would need the shared memory the operand ring uses.
+        if (prev && prev->bn && dgrad_out && b.has_dgrad && getenv("CENN_BWD_EPI") != nullptr && getenv("CENN_BN_BWD_3LAUNCH") == nullptr &&
+            getenv("CENN_BN_BWD_2LAUNCH") == nullptr && !prev->bar && prev->Coutp % 64 == 0 &&
+            ((b.type == CONV_S2 && !b.thin) || b.type == FULL_S2 || (b.type == FULL_V4 && b.P == 1)) &&
+            (t->cfg.world_size <= 1 || (s->xr_enabled && 2 * prev->Coutp <= XR_MAXF && getenv("CENN_DP_BN_FOLD") == nullptr))) {
+            ep_n.stats = prev->bsums; ep_n.stats_stride = prev->Coutp;
+            ep_n.bwd_y = prev->y.p; ep_n.bwd_scale = prev->scale; ep_n.bwd_shift = prev->shift; ep_n.bwd_mean = prev->mean;
+            ep_n.bwd_act = prev->act; ep_n.bwd_negval = 0.2f;
+            prev->bwd_epi = true;
+        }
         switch (b.type) {
             case CONV_S2: {
                 if (b.thin) { if (tc_plan_gemm(s, &b.p_fwd, b.col, Wf, fwd_out, M, b.Cs, (int)b.col_k, b.Csp, ep_f)) return 1; }
@@ -787,7 +803,14 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         // reduce -> coefficients -> apply
         static const bool fuse_coef_env = getenv("CENN_BN_BWD_3LAUNCH") == nullptr;
         const bool fuse_coef = !dp && !two_launch && fuse_coef_env;
-        if (fuse_coef) {
+        if (b->bwd_epi && !dp) {
+            // the sums are already in bsums (epilogue of the dgrad GEMM that wrote g): coefficients + affine gradients, sums re-zeroed
+            emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
+                LK(nhwc::bn_bwd_coef_sums_kernel, dim3((b->Coutp + 255) / 256), dim3(256), 0, s->stream)(b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global);
+                KLAUNCH(s); return 0; });
+        } else if (b->bwd_epi) {
+            // (data parallel: bn_bwd_coef_xr below exchanges and re-zeroes the same accumulator)
+        } else if (fuse_coef) {
             emit(t, "bn_bwd_reduce", [s, b, gamma, gg, gbeta, npix, vpp, n_global]() {
                 dim3 blk; int gy; reduce_dims(vpp, blk, gy);
                 auto kern = b->act == nhwc::ACT_LEAKY ? nhwc::bn_bwd_reduce_coef_kernel<nhwc::ACT_LEAKY> : nhwc::bn_bwd_reduce_coef_kernel<nhwc::ACT_RELU>;
@@ -808,7 +831,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             LK(kern, dim3(dim3(b->part_rows, gy)), dim3(blk), 2 * blk.x * 8 * sizeof(float), s->stream)(b->g.p, b->y.p, b->scale, b->shift, b->mean,
                 b->part, b->Coutp, npix, vpp, b->Cout, 0.2f);
             KLAUNCH(s); return 0; });
-        t->prog.back().bytes = 2.0 * 2.0 * (double)npix * b->Cout;            // read g, y
+        if (!b->bwd_epi && !fuse_coef) t->prog.back().bytes = 2.0 * 2.0 * (double)npix * b->Cout;            // read g, y
         if (two_launch) {
             emit(t, "bn_bwd_apply", [s, b, gamma, gg, gbeta, gb_part, npix, vpp, n_global]() {
                 dim3 blk; int gy; reduce_dims(vpp, blk, gy);
