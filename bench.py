@@ -317,7 +317,7 @@ def wrap_device(ptr, count, dtype, torch):
 
 
 
-def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, steps, warmup, want_profile=True, fine=128):
+def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, steps, warmup, want_profile=True, fine=128, bn_local=0, want_e2e=True):
     """Time `steps` G+D steps of one workload on this rank.  Returns a dict of raw measurements (device-timed region, end-to-end
     region through the pipelined host API, per-op profile, launch count, clocks); the executor is closed before returning."""
     from video_filler_b200 import synth, train, util
@@ -326,7 +326,7 @@ def measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, v
     if video:
         opt["wtgdl"] = args.wtgdl
     opt["fineSize"] = fine
-    trn = train.FusedTrainer(opt, precision="bf16", world_size=world, rank=rank)
+    trn = train.FusedTrainer(opt, precision="bf16", world_size=world, rank=rank, bn_local=bn_local)
     # identical random-init weights on every rank (parameter broadcast = same seed), train.lua:58-67
     rng = np.random.default_rng(1234)
     nG, nD = trn.param_count(0), trn.param_count(1)
@@ -555,6 +555,7 @@ def main():
     ap.add_argument("--wtgdl", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video-block", action="store_true", help="skip the `video` sub-block (cfg3 at the same N) of the image line")
+    ap.add_argument("--no-local-bn-block", action="store_true", help="N > 1: skip the `local_bn` sub-block (the same step with per-rank BN statistics)")
     ap.add_argument("--path", default="fused", choices=["fused", "oplevel"],
                     help="fused = whole-step executor (cenn_trainer_*); oplevel = the drop-in THNN-table path an unchanged script hits (ClosureTrainer, precision bf16)")
     args = ap.parse_args()
@@ -606,6 +607,14 @@ def main():
     if not video and not args.no_video_block:
         # the config the >= 7x scaling target is quoted on (BASELINE.json configs[2]): 64 clips of 12 stacked channels per GPU, at the same N
         vid = measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, True, 64, args.steps, args.warmup, want_profile=False)
+    loc = locv = None
+    if world > 1 and not deeper and not args.no_local_bn_block:
+        # the same workload(s) with per-rank BN statistics (cfg.bn_local: the usual distributed-data-parallel semantics -- every rank normalises
+        # with its own 256 / 64 samples, as one reference process at that batchSize does; no statistics cross the ranks).  The headline `value`
+        # stays the global-batch-statistics step, which equals one executor at N x batchSize (tests/test_dp_multi_gpu.py).
+        loc = measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, video, B, args.steps, args.warmup, want_profile=False, bn_local=1)
+        if vid is not None:
+            locv = measure_train(args, torch, dist, api, st, stream, rank, local_rank, world, True, 64, args.steps, args.warmup, want_profile=False, bn_local=1)
 
     def teardown():
         # ordered teardown, then a NORMAL interpreter exit (atexit hooks run): executors are already closed by measure_train
@@ -647,6 +656,14 @@ def main():
                          "global_batch": 64 * world, "step_tflops": VIDEO_GFLOP_PER_SAMPLE * 1e-3 * vvalue, "gpu_launches": vid["launches"],
                          "e2e": {"value": 64 * world * args.steps / (vid["e2e_ms"] / 1e3), "unit": "samples/s", "h2d_bytes_per_step": vid["h2d_bytes"], "d2h_bytes_per_step": 32},
                          "clocks": vid["clocks"]}
+    if loc is not None:
+        line["local_bn"] = {"semantics": "per-rank BN batch statistics (cfg.bn_local = 1): no statistics exchange, gradients and losses all-reduced",
+                            "value": B * world * args.steps / (loc["ms"] / 1e3), "unit": "samples/s", "ms_per_step": loc["ms"] / args.steps,
+                            "e2e": {"value": B * world * args.steps / (loc["e2e_ms"] / 1e3), "unit": "samples/s", "h2d_bytes_per_step": loc["h2d_bytes"], "d2h_bytes_per_step": 32},
+                            "gpu_launches": loc["launches"]}
+        if locv is not None:
+            line["local_bn"]["video"] = {"value": 64 * world * args.steps / (locv["ms"] / 1e3), "unit": "samples/s", "ms_per_step": locv["ms"] / args.steps,
+                                         "e2e": {"value": 64 * world * args.steps / (locv["e2e_ms"] / 1e3), "unit": "samples/s"}}
     if prof:
         tc_ms, tc_flops, tc_n = prof["tc_ms"], prof["tc_flops"], prof["tc_launches"]
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0

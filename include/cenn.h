@@ -216,6 +216,11 @@ typedef struct cenn_trainer_config {
     int noiseGen;      /* train.lua:109-124: a 1x1 conv of a noise vector [B,nz,1,1] is joined to the bottleneck (cenn_trainer_set_noise_*) */
     int nz;            /* length of the noise vector (train.lua:11, default 100) */
     int conditionAdv;  /* train.lua:158-180: netD takes {context, prediction}: two 5x5/stride-2 first-layer convs joined along channels */
+    /* data parallel (world_size > 1) only.  0 (default): BN batch statistics are those of the GLOBAL batch, exchanged across the ranks inside the
+     * step -- N ranks at batchSize equal one executor at N*batchSize (tests/test_dp_multi_gpu.py).  1: every rank normalises with its OWN
+     * batchSize samples, as one reference process would (the usual distributed-data-parallel semantics): no statistics cross the ranks, only
+     * gradients and losses; running statistics are per rank (save rank 0's). */
+    int bn_local;
 } cenn_trainer_config;
 
 enum { CENN_NET_G = 0, CENN_NET_D = 1 };

@@ -417,7 +417,7 @@ function GDL:updateGradInput() return self.gradInput end
 -- (`local eng = cenn.Inpainter(opt, net)` ... `eng:sweep(images01, mask)`).
 ffi.cdef[[
 typedef struct cenn_trainer_config { int variant, batchSize, fineSize, nBottleneck, nef, ngf, ndf, nc, predLen, overlapPred;
-    float wtl2, weight_nomask, wtgdl, lr, beta1; int precision, world_size, rank, dead_dgrad, noiseGen, nz, conditionAdv; } cenn_trainer_config;
+    float wtl2, weight_nomask, wtgdl, lr, beta1; int precision, world_size, rank, dead_dgrad, noiseGen, nz, conditionAdv, bn_local; } cenn_trainer_config;
 int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trainer **out);
 int cenn_trainer_destroy(cenn_trainer *t);
 int cenn_trainer_param_count(cenn_trainer *t, int net, int64_t *count);
@@ -460,7 +460,7 @@ function Trainer:__init(opt, netG, netD, world_size, rank)
   local video = opt.predLen ~= nil
   local cfg = ffi.new('cenn_trainer_config', {video and 1 or 0, opt.batchSize, opt.fineSize, opt.nBottleneck, opt.nef, opt.ngf, opt.ndf, opt.nc or 3,
     opt.predLen or 1, opt.overlapPred or 0, opt.wtl2, opt.weight_nomask or 0, opt.wtgdl or 0, opt.lr, opt.beta1, 1, world_size or 1, rank or 0, 1,
-    opt.noiseGen and 1 or 0, opt.nz or 100, opt.conditionAdv and 1 or 0})
+    opt.noiseGen and 1 or 0, opt.nz or 100, opt.conditionAdv and 1 or 0, opt.bn_local and 1 or 0})
   local h = ffi.new('cenn_trainer*[1]'); check(lib.cenn_trainer_create(S(), cfg, h)); self.h = ffi.gc(h[0], lib.cenn_trainer_destroy)
   self.netG, self.netD = netG, netD
   self.pG, self.pD = netG:getParameters(), netD:getParameters()          -- train.lua:262-263: the flat vectors are the interchange format

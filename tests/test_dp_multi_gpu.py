@@ -20,9 +20,10 @@ def _ngpu():
         return 0
 
 
-# ("image+branches": train.lua's noiseGen + conditionAdv options; the flag is not an environment variable and is stripped below)
+# ("--branches": train.lua's noiseGen + conditionAdv options, "--bn-local": per-rank BN statistics; flags of tools/dp_parity.py, not
+# environment variables: stripped below)
 @pytest.mark.parametrize("variant,env", [("image", {}), ("video", {}), ("image", {"CENN_NO_XR": "1"}), ("image", {"CENN_FP32_BUCKETS": "1"}),
-                                         ("image", {"CENN_XR_PULL": "1"}), ("image", {"--branches": "1"})])
+                                         ("image", {"CENN_XR_PULL": "1"}), ("image", {"--branches": "1"}), ("image", {"--bn-local": "1"}), ("video", {"--bn-local": "1"})])
 def test_data_parallel_step_equals_global_batch_step(variant, env):
     n = _ngpu()
     if n < 2:
@@ -32,8 +33,9 @@ def test_data_parallel_step_equals_global_batch_step(variant, env):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", "dp_parity.py"), "--variant", variant]
     env = dict(env)
-    if env.pop("--branches", None):
-        cmd.append("--branches")
+    for flag in ("--branches", "--bn-local"):
+        if env.pop(flag, None):
+            cmd.append(flag)
     e = dict(os.environ); e.update(env)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=e, cwd=ROOT)
     lines = [l for l in r.stdout.splitlines() if l.startswith("DP_PARITY ")]

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--per-rank", type=int, default=8)
     ap.add_argument("--nB", type=int, default=256)
     ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--bn-local", action="store_true", help="cfg.bn_local = 1: per-rank BN statistics (DDP semantics); checked against one single-GPU executor per shard")
     ap.add_argument("--branches", action="store_true", help="image variant with noiseGen + conditionAdv (train.lua:109-124,158-180)")
     args = ap.parse_args()
     import torch
@@ -75,6 +76,8 @@ def main():
         batches.append(synth.image_batch(Bg, 128, 4, drng) if args.variant == "image" else synth.video_batch(Bg, 6, 128, opt_g["maskValue"], drng))
         noises.append(drng.uniform(-1, 1, (Bg, 100)).astype(np.float32) if args.branches else None)       # each rank takes its rows of the global draw
 
+    if args.bn_local:
+        return bn_local_check(args, dist, api, st, train, opt_l, pG, pD, batches, rank, world, Bl)
     trn = train.FusedTrainer(opt_l, precision="bf16", world_size=world, rank=rank)
     trn.set_params(0, pG); trn.set_params(1, pD)
     sl = slice(Bl * rank, Bl * rank + Bl)
@@ -135,6 +138,72 @@ def main():
             a, b = all_losses[0][i]["errG_l2"], ref_losses[i]["errG_l2"]
             if not np.isfinite(list(all_losses[0][i].values())).all() or abs(a - b) > 5e-2 * abs(b):
                 fail.append("step %d errG_l2: %r vs %r" % (i + 1, a, b))
+        out["ok"] = not fail
+        out["failures"] = fail
+        print("DP_PARITY " + json.dumps(out))
+    api.cenn_dist_shutdown(st)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and fail:
+        sys.exit(1)
+
+
+def bn_local_check(args, dist, api, st, train, opt_l, pG, pD, batches, rank, world, Bl):
+    """cfg.bn_local: rank r normalises with its own shard, so after ONE step from common weights
+      * rank r's BN running statistics equal those of a single-GPU executor (world 1, batch Bl) run on shard r,
+      * the all-reduced losses are the mean over the shards of the single-GPU losses (every loss is a batch mean),
+      * the all-reduced gradients are the mean of the single-GPU gradients;
+    and the replicas' parameters stay bit-identical over the following steps (the statistics do not)."""
+    trn = train.FusedTrainer(opt_l, precision="bf16", world_size=world, rank=rank, bn_local=1)
+    trn.set_params(0, pG); trn.set_params(1, pD)
+    sl = slice(Bl * rank, Bl * rank + Bl)
+    losses, bn1, g1 = [], None, None
+    for i, b in enumerate(batches):
+        losses.append(trn.step_host(*[np.ascontiguousarray(x[sl]) for x in b]))
+        if i == 0:
+            bn1 = (trn.get_bn_stats(0), trn.get_bn_stats(1)); g1 = (trn.get_grads(0), trn.get_grads(1))
+    digest = hashlib.sha256(trn.get_params(0).tobytes() + trn.get_params(1).tobytes()).hexdigest()
+    digests, all_losses = [None] * world, [None] * world
+    dist.all_gather_object(digests, digest)
+    dist.all_gather_object(all_losses, losses)
+    trn.close()
+    # this rank's shard on a plain single-GPU executor
+    ref = train.FusedTrainer(opt_l, precision="bf16")
+    ref.set_params(0, pG); ref.set_params(1, pD)
+    rl = ref.step_host(*[np.ascontiguousarray(x[sl]) for x in batches[0]])
+    rbn, rg = (ref.get_bn_stats(0), ref.get_bn_stats(1)), (ref.get_grads(0), ref.get_grads(1))
+    ref.close()
+    mine = {"bn_G_rel": rel_err(bn1[0], rbn[0]), "bn_D_rel": rel_err(bn1[1], rbn[1]), "loss": rl, "gG": rg[0], "gD": rg[1]}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    out = {"variant": args.variant, "bn_local": True, "world": world, "per_rank": Bl, "replicas_bit_identical": len(set(digests)) == 1, "checks": {}}
+    fail = []
+    if rank == 0:
+        if not out["replicas_bit_identical"]:
+            fail.append("parameters differ between ranks after %d steps" % len(batches))
+        for r in range(world):
+            out["checks"]["bn_rel_rank%d" % r] = [gathered[r]["bn_G_rel"], gathered[r]["bn_D_rel"]]
+            if gathered[r]["bn_G_rel"] > 5e-3 or gathered[r]["bn_D_rel"] > 5e-3:
+                fail.append("rank %d BN running statistics differ from the single-GPU run on its shard: %r" % (r, out["checks"]["bn_rel_rank%d" % r]))
+            if all_losses[r] != all_losses[0]:
+                fail.append("losses differ between rank 0 and rank %d" % r)
+        # Exactly comparable are the quantities computed BEFORE the first Adam update (fDx: the discriminator losses and gradients, the L2 term of
+        # the unchanged generator); fGx runs behind D's update, which uses the AVERAGED gradient here and the shard's own in the single-GPU runs,
+        # so errG and G's gradients only have to stay close.  Bounds: run-to-run spread of this 8-sample-per-rank GAN step (fp32 atomics order
+        # flips bf16 roundings; BN over 8 samples amplifies them) -- the same spread tests/test_dp_gpu.py quantifies.
+        for k, tol in (("errD_real", 5e-3), ("errD_fake", 1e-2), ("errD", 1e-2), ("errG_l2", 5e-3), ("errG", 4e-2), ("errG_total", 1e-2)):
+            m = float(np.mean([gathered[r]["loss"][k] for r in range(world)]))
+            out["checks"]["loss_" + k] = [all_losses[0][0][k], m]
+            if abs(all_losses[0][0][k] - m) > tol * max(abs(m), 1e-3):
+                fail.append("step-1 %s %r is not the mean of the shard losses %r (tol %g)" % (k, all_losses[0][0][k], m, tol))
+        for name, g, key, cmin in (("G", g1[0], "gG", 0.95), ("D", g1[1], "gD", 0.98)):
+            m = np.mean([gathered[r][key] for r in range(world)], axis=0)
+            out["checks"]["grad_%s" % name] = [cos(g, m), float(np.linalg.norm(g) / max(np.linalg.norm(m), 1e-30))]
+            if cos(g, m) < cmin or abs(np.linalg.norm(g) / np.linalg.norm(m) - 1) > 3e-2:
+                fail.append("gradients of %s are not the mean of the shard gradients: %r" % (name, out["checks"]["grad_%s" % name]))
+        for i in range(len(batches)):
+            if not np.isfinite(list(all_losses[0][i].values())).all():
+                fail.append("non-finite loss at step %d" % (i + 1))
         out["ok"] = not fail
         out["failures"] = fail
         print("DP_PARITY " + json.dumps(out))

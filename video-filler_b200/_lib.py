@@ -20,7 +20,7 @@ class TrainerConfig(C.Structure):
                 ("overlapPred", C.c_int), ("wtl2", C.c_float), ("weight_nomask", C.c_float), ("wtgdl", C.c_float),
                 ("lr", C.c_float), ("beta1", C.c_float), ("precision", C.c_int), ("world_size", C.c_int),
                 ("rank", C.c_int), ("dead_dgrad", C.c_int),
-                ("noiseGen", C.c_int), ("nz", C.c_int), ("conditionAdv", C.c_int)]
+                ("noiseGen", C.c_int), ("nz", C.c_int), ("conditionAdv", C.c_int), ("bn_local", C.c_int)]
 
 
 class InpainterConfig(C.Structure):

@@ -186,6 +186,12 @@ namespace {
 
 typedef cenn_trainer T;
 
+// data parallel: are the BN batch statistics those of the GLOBAL batch (exchanged across ranks: the step equals one executor at batchSize *
+// world_size) or of this rank's own batch (cfg.bn_local: the usual distributed-data-parallel semantics -- no exchange, every rank normalises
+// with its batchSize samples exactly as one reference process would; running statistics are per rank)?
+static inline bool bn_sync(const T *t) { return t->cfg.world_size > 1 && !t->cfg.bn_local; }
+static inline double bn_batch(const T *t) { return bn_sync(t) ? (double)t->Bglobal : (double)t->B; }
+
 template <typename X>
 X *dalloc(T *t, int64_t n, bool zero = true) {
     void *p = nullptr;
@@ -501,7 +507,7 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
         if (prev && prev->bn && dgrad_out && b.has_dgrad && getenv("CENN_BWD_EPI") != nullptr && getenv("CENN_BN_BWD_3LAUNCH") == nullptr &&
             getenv("CENN_BN_BWD_2LAUNCH") == nullptr && !prev->bar && prev->Coutp % 64 == 0 &&
             ((b.type == CONV_S2 && !b.thin) || b.type == FULL_S2 || (b.type == FULL_V4 && b.P == 1)) &&
-            (t->cfg.world_size <= 1 || (s->xr_enabled && 2 * prev->Coutp <= XR_MAXF && getenv("CENN_DP_BN_FOLD") == nullptr))) {
+            (!bn_sync(t) || (s->xr_enabled && 2 * prev->Coutp <= XR_MAXF && getenv("CENN_DP_BN_FOLD") == nullptr))) {
             ep_n.stats = prev->bsums; ep_n.stats_stride = prev->Coutp;
             ep_n.bwd_y = prev->y.p; ep_n.bwd_scale = prev->scale; ep_n.bwd_shift = prev->shift; ep_n.bwd_mean = prev->mean;
             ep_n.bwd_act = prev->act; ep_n.bwd_negval = 0.2f;
@@ -667,7 +673,7 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
     cenn_state *s = t->s;
     Block *b = &net.blocks[i];
     float *master = net.master;
-    const double n_global = b->type == HEAD ? 1.0 : (double)t->Bglobal * b->a.H * b->a.W;
+    const double n_global = b->type == HEAD ? 1.0 : bn_batch(t) * b->a.H * b->a.W;
     if (b->type == HEAD) {
         const bf16 *w = net.wbf + b->w_off; const float *bias = master + b->b_off;
         int B = b->Mrows, K = 16 * b->Clp;          // one row per 4x4 window (fineSize 128: one per sample)
@@ -705,7 +711,7 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
     }
     if (b->type == FULL_V4 && b->P > 1)       // overlap-add of the 4x4 windows + bias + BN statistics
         emit_col2im_v4(t, b->col, b->bn ? b->y : b->a, master + b->b_off, b->bn ? b->stats : nullptr, b->stats_cols);
-    if (b->bn && train && t->cfg.world_size <= 1 && b->Coutp <= 4096 && getenv("CENN_NO_BN_FUSE") == nullptr) {
+    if (b->bn && train && !bn_sync(t) && b->Coutp <= 4096 && getenv("CENN_NO_BN_FUSE") == nullptr) {
         float *gamma = master + b->g_off, *beta = master + b->be_off;
         emit(t, "bn_fin_apply", [s, b, gamma, beta, n_global]() {
             int64_t nvec = b->y.elems() / 8;
@@ -719,7 +725,7 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
     if (b->bn) {
         float *gamma = master + b->g_off, *beta = master + b->be_off;
         if (train) {
-            if (t->cfg.world_size > 1 && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {
+            if (bn_sync(t) && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {
                 // data parallel: the statistics cross NVLink inside the finalize kernel (peer mailboxes), no collective launch
                 const int chain = t->emit_chain;
                 emit(t, "bn_finalize_xr", [t, s, b, gamma, beta, n_global, chain]() {
@@ -727,7 +733,7 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
                         b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, b->Coutp, n_global, 0.1, 1e-5);
                     KLAUNCH(s); return 0; });
             } else {
-            emit(t, "bn_stats_sync", []() { return 0; }, b->stats, 2 * (int64_t)b->stats_cols);
+            emit(t, "bn_stats_sync", []() { return 0; }, bn_sync(t) ? b->stats : nullptr, 2 * (int64_t)b->stats_cols);
             emit(t, "bn_finalize", [s, b, gamma, beta, n_global]() {
                 LK(nhwc::bn_finalize_kernel, dim3((b->Cout + 127) / 128), dim3(128), 0, s->stream)(b->stats, b->stats_cols, b->fold, b->Coutp, gamma, beta,
                     b->running, b->running + b->Coutp, b->mean, b->invstd, b->scale, b->shift, b->Cout, n_global, 0.1, 1e-5, 1);
@@ -771,10 +777,11 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
     const int64_t npix = b->a.pix();
     const bool dp = t->cfg.world_size > 1;
     if (b->bn) {
-        const double n_global = (double)t->Bglobal * b->a.H * b->a.W;
+        const double n_global = bn_batch(t) * b->a.H * b->a.W;
+        const bool dpb = bn_sync(t);          // the BN sums cross the ranks (global-batch statistics); false with cfg.bn_local
         float *gamma = master + b->g_off;
         float *gg = want_params ? grad + b->g_off : nullptr, *gbeta = want_params ? grad + b->be_off : nullptr;
-        if (b->bar && !dp) {       // single-launch path (nhwc::bn_bwd_fused_kernel), cooperative launch
+        if (b->bar && !dpb) {       // single-launch path (nhwc::bn_bwd_fused_kernel), cooperative launch
             const int want_gb = want_params ? 1 : 0;
             emit(t, "bn_bwd_fused", [s, b, gamma, gg, gbeta, want_gb, npix, vpp, n_global]() {
                 dim3 blk; int gy; reduce_dims(vpp, blk, gy);
@@ -795,15 +802,15 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         // the prologue's dependent loads and the done-counter cost what the coefficient launch cost (apply 29.6 us vs 17.4 + 11 us per layer)
         // and the step got 4 % SLOWER (3.29 vs 3.15 ms), so the three-launch chain stays the default.
         static const bool two_launch_env = getenv("CENN_BN_BWD_2LAUNCH") != nullptr && atoi(getenv("CENN_BN_BWD_2LAUNCH")) != 0;
-        const bool two_launch = !dp && two_launch_env;
+        const bool two_launch = !dpb && two_launch_env;
         // data parallel with peer mailboxes: the local sums are accumulated by fp32 atomics straight into the exchange buffer (no fold launch);
         // replicas stay bit-identical because every rank adds the same published values in rank order
-        const bool dp_atomic = dp && s->xr_enabled && 2 * b->Coutp <= XR_MAXF && getenv("CENN_DP_BN_FOLD") == nullptr;
+        const bool dp_atomic = dpb && s->xr_enabled && 2 * b->Coutp <= XR_MAXF && getenv("CENN_DP_BN_FOLD") == nullptr;
         // single GPU (default): pass 1 and the coefficient step in one launch (the last CTA finishes the sums); CENN_BN_BWD_3LAUNCH=1 restores
         // reduce -> coefficients -> apply
         static const bool fuse_coef_env = getenv("CENN_BN_BWD_3LAUNCH") == nullptr;
-        const bool fuse_coef = !dp && !two_launch && fuse_coef_env;
-        if (b->bwd_epi && !dp) {
+        const bool fuse_coef = !dpb && !two_launch && fuse_coef_env;
+        if (b->bwd_epi && !dpb) {
             // the sums are already in bsums (epilogue of the dgrad GEMM that wrote g): coefficients + affine gradients, sums re-zeroed
             emit(t, "bn_bwd_coef", [s, b, gamma, gg, gbeta, n_global]() {
                 LK(nhwc::bn_bwd_coef_sums_kernel, dim3((b->Coutp + 255) / 256), dim3(256), 0, s->stream)(b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global);
@@ -846,7 +853,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             emit(t, "bn_bwd_coef_xr", [s, b, gamma, gg, gbeta, n_global, inv_world]() {
                 LK(nhwc::bn_bwd_coef_xr_kernel, dim3(1), dim3(1024), 0, s->stream)(s->xr, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, inv_world, 1);
                 KLAUNCH(s); return 0; });
-        } else if (dp && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {   // fold this rank's partial rows, then exchange + coefficients in one kernel
+        } else if (dpb && s->xr_enabled && 2 * b->Coutp <= XR_MAXF) {   // fold this rank's partial rows, then exchange + coefficients in one kernel
             const float inv_world = 1.f / (float)t->cfg.world_size;
             emit(t, "bn_bwd_fold", [s, b]() {
                 LK(nhwc::bn_bwd_coef2_kernel, dim3((b->Cout + 31) / 32), dim3(dim3(32, 8)), 0, s->stream)(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0, 1.f);
@@ -854,7 +861,7 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
             emit(t, "bn_bwd_coef_xr", [s, b, gamma, gg, gbeta, n_global, inv_world]() {
                 LK(nhwc::bn_bwd_coef_xr_kernel, dim3(1), dim3(1024), 0, s->stream)(s->xr, b->bsums, b->Coutp, gamma, b->invstd, b->mean, b->coef, gg, gbeta, b->Cout, n_global, inv_world, 0);
                 KLAUNCH(s); return 0; });
-        } else if (dp) {   // fold the partial rows into bsums, all-reduce bsums across ranks, then the coefficients
+        } else if (dpb) {   // fold the partial rows into bsums, all-reduce bsums across ranks, then the coefficients
             emit(t, "bn_bwd_fold", [s, b]() {
                 LK(nhwc::bn_bwd_coef2_kernel, dim3((b->Cout + 31) / 32), dim3(dim3(32, 8)), 0, s->stream)(b->part, b->part_rows, b->bsums, b->Coutp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, b->Cout, 1.0, 0, 1.f);
                 KLAUNCH(s); return 0; }, b->bsums, 2 * (int64_t)b->Coutp);
@@ -1169,7 +1176,7 @@ int build_program(T *t) {
     // The generator forward does not depend on the discriminator's real sweep (and vice versa): it runs as a second chain
     // on its own stream; each chain's small BN kernels / peer exchanges fill the other's gaps.  (Not with NCCL-only
     // data parallelism: one communicator must not be driven from two streams.)
-    const bool two_chains = !(c.world_size > 1 && !s->xr_enabled) && getenv("CENN_ONE_CHAIN") == nullptr;
+    const bool two_chains = !(bn_sync(t) && !s->xr_enabled) && getenv("CENN_ONE_CHAIN") == nullptr;
     cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     if (two_chains) {
         cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming);

@@ -207,7 +207,7 @@ def dp_step(trainer, a_ptr, b_ptr, mask_ptr, all_reduce):
 class FusedTrainer:
     """Whole-step executor (cenn_trainer_*): one call per G+D step, host or device inputs."""
 
-    def __init__(self, opt, precision="bf16", world_size=1, rank=0, dead_dgrad=1):
+    def __init__(self, opt, precision="bf16", world_size=1, rank=0, dead_dgrad=1, bn_local=0):
         self.opt = opt
         cfg = _lib.TrainerConfig(
             variant=0 if opt["variant"] == "image" else 1, batchSize=opt["batchSize"], fineSize=opt["fineSize"],
@@ -215,7 +215,7 @@ class FusedTrainer:
             predLen=opt.get("predLen", 1), overlapPred=opt["overlapPred"], wtl2=opt["wtl2"],
             weight_nomask=opt.get("weight_nomask", 0.0), wtgdl=opt.get("wtgdl", 0.0), lr=opt["lr"], beta1=opt["beta1"],
             precision={"fp32": 0, "bf16": 1}[precision], world_size=world_size, rank=rank, dead_dgrad=dead_dgrad,
-            noiseGen=1 if opt.get("noiseGen") else 0, nz=opt.get("nz", 100), conditionAdv=1 if opt.get("conditionAdv") else 0)
+            noiseGen=1 if opt.get("noiseGen") else 0, nz=opt.get("nz", 100), conditionAdv=1 if opt.get("conditionAdv") else 0, bn_local=int(bn_local))
         self.cfg = cfg
         h = C.c_void_p()
         api().cenn_trainer_create(state(), C.byref(cfg), C.byref(h))
