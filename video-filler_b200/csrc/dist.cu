@@ -114,7 +114,12 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
     NcclComm comm2 = nullptr;
     if (nccl_check(g_nccl.init_rank(&comm2, world_size, id2, rank), "ncclCommInitRank (bulk)")) return 1;
     s->comm2 = comm2;
-    CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    {   // the bucket all-reduces are the longest chain behind the last weight gradient: their CTAs go ahead of the queued GEMM CTAs (CENN_COMM_PRIO=0: default priority)
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const char *e = getenv("CENN_COMM_PRIO");
+        CK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, (e && atoi(e) == 0) ? 0 : prio_hi));
+    }
     // peer mailboxes for the latency-bound BN-statistics exchanges (35 per step): CUDA IPC over NVLink.  Any failure
     // here just leaves xr_enabled = false and those exchanges stay on NCCL.
     do {

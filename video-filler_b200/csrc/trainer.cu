@@ -67,6 +67,7 @@ struct Block {
     float *stats = nullptr, *bsums = nullptr, *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *coef = nullptr;
     float *running = nullptr;               // [2][Cout] running_mean, running_var
     int stats_cols = 0, fold = 1;
+    std::vector<cudaEvent_t> ar_ev;         // data parallel: one event per chunk of this block's gradient bucket (recorded behind the chunk's all-reduce)
     bool bwd_epi = false;                   // the first pass of this block's BN backward (sum dz, sum dz (y - mean)) is taken by the epilogue of the
                                             // dgrad GEMM that produces g (the NEXT block's p_dgrad) straight into bsums: no bn_bwd_reduce launch
     float *sig = nullptr, *gpre = nullptr;  // head
@@ -754,6 +755,17 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
     }
 }
 
+// smallest weight block (elements) that gets its own gradient bucket / early Adam (generator) or bucket (discriminator, second sweep)
+// The generator's first-layer gradInput is dead (the reference computes and discards it).  As the LAST kernel of the step's side stream it
+// was exposed at the step's tail (0.13 ms of a 2.98 ms step); nothing observable depends on it, so the program computes it at the START of
+// the following step instead -- from the previous step's E1 gradient, beside the low-occupancy opening of the step.  Same FLOPs per step,
+// one step late, result discarded either way.  CENN_DEAD_DGRAD_INLINE=1 restores the in-place position.
+static bool defer_dead_dgrad() { static const bool v = getenv("CENN_DEAD_DGRAD_INLINE") == nullptr; return v; }
+static int64_t g_bucket_min() { static const int64_t v = (int64_t)1 << (getenv("CENN_G_BUCKET_LOG2") ? atoi(getenv("CENN_G_BUCKET_LOG2")) : 20); return v; }
+// chunks of one bucket (elements): multiples of 4, the last one takes the remainder
+static int bucket_chunks(int64_t cnt) { static const int v = getenv("CENN_BUCKET_CHUNKS") ? atoi(getenv("CENN_BUCKET_CHUNKS")) : 4; return (cnt >= ((int64_t)1 << 23) && v > 1) ? v : 1; }
+static int64_t chunk_off(int64_t cnt, int nch, int c) { return c >= nch ? cnt : ((cnt / nch) & ~int64_t(3)) * c; }
+static int64_t d_bucket_min() { static const int64_t v = (int64_t)1 << (getenv("CENN_D_BUCKET_LOG2") ? atoi(getenv("CENN_D_BUCKET_LOG2")) : 18); return v; }
 // backward of one block: b->g holds dLoss/d(activation output); produces parameter gradients (if want_params)
 // and the previous block's gradient (if the block has a dgrad plan and want_dgrad)
 void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) {
@@ -954,26 +966,39 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         }
         // data parallel, generator: the big weight gradients start their all-reduce now, on the bulk communicator's stream,
         // and overlap the rest of the backward sweep (E6 + G1 are 92 % of the 285 MB)
-        const bool bucket_g = &net == &t->G && b->w_count >= (1 << 20), bucket_d = &net == &t->D && t->d_bucket_sweep && b->w_count >= (1 << 18);
+        const bool bucket_g = &net == &t->G && b->w_count >= g_bucket_min(), bucket_d = &net == &t->D && t->d_bucket_sweep && b->w_count >= d_bucket_min();
         if (dp && s->comm2 && (bucket_g || bucket_d)) {
             cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
             float *ptr = grad + b->w_off; int64_t cnt = b->w_count;
             (bucket_g ? t->g_buckets : t->d_buckets).push_back({b->w_off, b->w_count});
             // generator buckets with an early Adam behind them travel as bf16 (half the NVLink bytes); Adam reads the bf16 sum
             bf16 *pbf = (net.gradbf && cnt % 4 == 0 && getenv("CENN_NO_EARLY_ADAM") == nullptr) ? net.gradbf + b->w_off : nullptr;
-            emit(t, "grad_bucket_ar", [t, s, ev, ptr, pbf, cnt]() {
+            // the two 32.8 M-element blocks (E6, G1) travel in chunks: the early Adam of chunk k (third stream) overlaps the all-reduce of chunk
+            // k + 1, so the chain behind the last weight gradient ends with a quarter of an Adam pass instead of a whole one
+            const int nch = bucket_chunks(cnt);
+            if (bucket_g) { for (int c = 0; c < nch; ++c) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); t->events.push_back(e); b->ar_ev.push_back(e); } }
+            emit(t, "grad_bucket_ar", [t, s, b, ev, ptr, pbf, cnt, nch, bucket_g]() {
                 if (cenn_check_cuda(cudaEventRecord(ev, t->serial ? s->stream : t->side), "event record", __FILE__, __LINE__)) return 1;
                 if (cenn_check_cuda(cudaStreamWaitEvent(s->comm_stream, ev, 0), "stream wait", __FILE__, __LINE__)) return 1;
-                if (!pbf) return cenn_dist_all_reduce_bulk(s, ptr, cnt);
-                nhwc::f32_to_bf16_vec_kernel<<<grid1d(s, cnt / 4), 256, 0, s->comm_stream>>>(ptr, pbf, cnt / 4);
-                KLAUNCH(s);
-                return cenn_dist_all_reduce_bulk_bf16(s, pbf, cnt); });
+                for (int c = 0; c < nch; ++c) {
+                    const int64_t o = chunk_off(cnt, nch, c), n = chunk_off(cnt, nch, c + 1) - o;
+                    if (!pbf) { if (cenn_dist_all_reduce_bulk(s, ptr + o, n)) return 1; }
+                    else {
+                        nhwc::f32_to_bf16_vec_kernel<<<grid1d(s, n / 4), 256, 0, s->comm_stream>>>(ptr + o, pbf + o, n / 4);
+                        KLAUNCH(s);
+                        if (cenn_dist_all_reduce_bulk_bf16(s, pbf + o, n)) return 1;
+                    }
+                    if (bucket_g && cenn_check_cuda(cudaEventRecord(b->ar_ev[c], s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
+                }
+                return 0; });
         }
     } else if (b->thin && b->type == FULL_S2 && want_dgrad && b->has_dgrad) {
         emit_im2col(t, b->g, b->col, b->h, b->w);
     }
     if (want_dgrad && b->has_dgrad) {
-        if (i == 0 && want_params) {
+        if (i == 0 && want_params && &net == &t->G && defer_dead_dgrad()) {
+            // emitted at the START of the step program (build_program): see there
+        } else if (i == 0 && want_params) {
             // first block of a net in a parameter sweep: the reference computes this gradInput and discards it (dead_dgrad); nothing waits for
             // it, so it runs on the side stream after the block's wgrad instead of on the critical path
             cudaEvent_t evf; cudaEventCreateWithFlags(&evf, cudaEventDisableTiming); t->events.push_back(evf);
@@ -996,13 +1021,28 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
     // (E6 + G1 hold 92 % of the parameters: ~0.3 ms of HBM-bound work moved off the critical path)
     // (data parallel: same, chained behind the block's bucket all-reduce on the bulk communicator's stream)
     const bool dp_bulk = dp && s->comm2 != nullptr;
-    if (want_params && (!dp || dp_bulk) && &net == &t->G && b->w_count >= (1 << 20) && getenv("CENN_NO_EARLY_ADAM") == nullptr) {
+    if (want_params && (!dp || dp_bulk) && &net == &t->G && b->w_count >= g_bucket_min() && getenv("CENN_NO_EARLY_ADAM") == nullptr) {
         cudaEvent_t e1, e2; cudaEventCreateWithFlags(&e1, cudaEventDisableTiming); cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
         t->events.push_back(e1); t->events.push_back(e2);
         Net *n = &net; const int64_t off = b->w_off, cnt = b->w_count; const float beta1 = t->cfg.beta1;
         t->g_early.push_back({off, cnt});
-        emit(t, "adam_early", [t, s, n, e1, e2, off, cnt, beta1, dp_bulk]() {
+        emit(t, "adam_early", [t, s, b, n, e1, e2, off, cnt, beta1, dp_bulk]() {
             cudaStream_t st = s->stream;
+            if (dp_bulk && !b->ar_ev.empty()) {      // third stream: behind this block's dgrad, chunk by chunk behind the chunk's all-reduce (comm_stream)
+                if (cenn_check_cuda(cudaEventRecord(e1, s->stream), "event record", __FILE__, __LINE__)) return 1;
+                if (cenn_check_cuda(cudaStreamWaitEvent(t->side3, e1, 0), "stream wait", __FILE__, __LINE__)) return 1;
+                const int nch = (int)b->ar_ev.size();
+                for (int c = 0; c < nch; ++c) {
+                    const int64_t o = off + chunk_off(cnt, nch, c), nn = chunk_off(cnt, nch, c + 1) - chunk_off(cnt, nch, c);
+                    if (cenn_check_cuda(cudaStreamWaitEvent(t->side3, b->ar_ev[c], 0), "stream wait", __FILE__, __LINE__)) return 1;
+                    if (n->gradbf && cnt % 4 == 0)
+                        LK(nhwc::adam_bf16g_kernel, dim3(grid1d(s, nn / 4)), dim3(256), 0, t->side3)(n->master + o, n->gradbf + o, n->m + o, n->v + o, n->wbf + o, nn, beta1, 0.999f, 1e-8f, n->adam_step);
+                    else
+                        LK(nhwc::adam_bf16_kernel, dim3(grid1d(s, nn / 4)), dim3(256), 0, t->side3)(n->master + o, n->grad + o, n->m + o, n->v + o, n->wbf + o, nn, beta1, 0.999f, 1e-8f, n->adam_step);
+                    KLAUNCH(s);
+                }
+                return 0;
+            }
             if (dp_bulk) {                           // third stream: waits for this block's bucket all-reduce (comm_stream) and its dgrad
                 if (cenn_check_cuda(cudaEventRecord(e1, s->stream), "event record", __FILE__, __LINE__)) return 1;
                 if (cenn_check_cuda(cudaEventRecord(e2, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;   // after the all-reduce
@@ -1173,6 +1213,20 @@ int build_program(T *t) {
     // ================= fDx (train.lua:278-350) =================
     emit_zero_bias(t, D); emit_zero_bias(t, G);
     emit_zero_grad(t, D);
+    if (c.dead_dgrad && defer_dead_dgrad() && !G.blocks.empty() && G.blocks[0].has_dgrad) {
+        cudaEvent_t evf; cudaEventCreateWithFlags(&evf, cudaEventDisableTiming); t->events.push_back(evf);
+        TcPlan *pl = &G.blocks[0].p_dgrad;
+        t->flops_per_step += pl->flops;
+        emit(t, "dgrad", [t, s, evf, pl]() {          // dead gradInput of the generator's first layer, one step late (defer_dead_dgrad)
+            if (t->serial) return tc_launch(s, pl);
+            if (cenn_check_cuda(cudaEventRecord(evf, s->stream), "event record", __FILE__, __LINE__)) return 1;
+            if (cenn_check_cuda(cudaStreamWaitEvent(t->side, evf, 0), "stream wait", __FILE__, __LINE__)) return 1;
+            cudaStream_t keep = s->stream; s->stream = t->side;
+            int rc = tc_launch(s, pl);
+            s->stream = keep;
+            return rc; });
+        t->prog.back().flops = pl->flops;
+    }
     // The generator forward does not depend on the discriminator's real sweep (and vice versa): it runs as a second chain
     // on its own stream; each chain's small BN kernels / peer exchanges fill the other's gaps.  (Not with NCCL-only
     // data parallelism: one communicator must not be driven from two streams.)
@@ -1902,14 +1956,17 @@ int cenn_trainer_timeline_step(cenn_trainer *t, const float *a, const float *b, 
     CK(cudaEventRecord(ev[2 * n], st));
     // the side streams start behind the base event so that every elapsed time is non-negative
     for (cudaStream_t x : {t->side, t->side2, t->side3}) CK(cudaStreamWaitEvent(x, ev[2 * n], 0));
+    if (s->comm_stream) CK(cudaStreamWaitEvent(s->comm_stream, ev[2 * n], 0));
     for (size_t i = 0; i < n; ++i) {
         const Op &op = t->prog[i];
-        // ops that hop to a side stream themselves (wgrad, dead dgrad, early Adam) are bracketed on that stream
+        // ops that hop to a side stream themselves (wgrad, dead dgrad, early Adam; data parallel: the bucket all-reduces on the bulk
+        // communicator's stream, id 4) are bracketed on that stream
         const bool on_side = !strcmp(op.name, "wgrad") || (!strcmp(op.name, "dgrad") && false);
         const bool on_side3 = !strcmp(op.name, "adam_early");
+        const bool on_comm = !strcmp(op.name, "grad_bucket_ar") && s->comm_stream;
         cudaStream_t run = op.chain == 1 ? t->side2 : st;
-        cudaStream_t where = on_side ? t->side : (on_side3 ? t->side3 : run);
-        stream_id[i] = where == st ? 0 : (where == t->side ? 1 : (where == t->side2 ? 2 : 3));
+        cudaStream_t where = on_side ? t->side : (on_side3 ? t->side3 : (on_comm ? s->comm_stream : run));
+        stream_id[i] = where == st ? 0 : (where == t->side ? 1 : (where == t->side2 ? 2 : (where == t->side3 ? 3 : 4)));
         cudaStream_t keep = s->stream;
         s->stream = run;
         if (where == run) CK(cudaEventRecord(ev[2 * i], where));
@@ -1920,12 +1977,12 @@ int cenn_trainer_timeline_step(cenn_trainer *t, const float *a, const float *b, 
         CK(cudaEventRecord(ev[2 * i + 1], where));
     }
     CK(cudaDeviceSynchronize());
-    float last_end[4] = {0.f, 0.f, 0.f, 0.f};
+    float last_end[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (size_t i = 0; i < n; ++i) {
         float a0 = 0.f, a1 = 0.f;
         CK(cudaEventElapsedTime(&a1, ev[2 * n], ev[2 * i + 1]));
         const Op &op = t->prog[i];
-        const bool hop = !strcmp(op.name, "wgrad") || !strcmp(op.name, "adam_early");
+        const bool hop = !strcmp(op.name, "wgrad") || !strcmp(op.name, "adam_early") || stream_id[i] == 4;
         if (hop) a0 = last_end[stream_id[i]]; else CK(cudaEventElapsedTime(&a0, ev[2 * n], ev[2 * i]));
         t_start[i] = a0; t_end[i] = a1;
         last_end[stream_id[i]] = a1;
