@@ -23,7 +23,9 @@ def _ngpu():
 # ("--branches": train.lua's noiseGen + conditionAdv options, "--bn-local": per-rank BN statistics; flags of tools/dp_parity.py, not
 # environment variables: stripped below)
 @pytest.mark.parametrize("variant,env", [("image", {}), ("video", {}), ("image", {"CENN_NO_XR": "1"}), ("image", {"CENN_FP32_BUCKETS": "1"}),
-                                         ("image", {"CENN_XR_PULL": "1"}), ("image", {"--branches": "1"}), ("image", {"--bn-local": "1"}), ("video", {"--bn-local": "1"})])
+                                         ("image", {"CENN_XR_PULL": "1"}), ("image", {"--branches": "1"}), ("image", {"--bn-local": "1"}), ("video", {"--bn-local": "1"}),
+                                         # nBottleneck 4000: E6 / G1 are 32.8 M elements each -> the sharded reduce + Adam over peer memory; and the same on NCCL buckets
+                                         ("image", {"--nB": "4000", "--per-rank": "4"}), ("image", {"--nB": "4000", "--per-rank": "4", "CENN_NO_SHARD_ADAM": "1"})])
 def test_data_parallel_step_equals_global_batch_step(variant, env):
     n = _ngpu()
     if n < 2:
@@ -36,6 +38,9 @@ def test_data_parallel_step_equals_global_batch_step(variant, env):
     for flag in ("--branches", "--bn-local"):
         if env.pop(flag, None):
             cmd.append(flag)
+    for flag in ("--nB", "--per-rank"):
+        if flag in env:
+            cmd += [flag, env.pop(flag)]
     e = dict(os.environ); e.update(env)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=e, cwd=ROOT)
     lines = [l for l in r.stdout.splitlines() if l.startswith("DP_PARITY ")]

@@ -88,7 +88,10 @@ def main():
             bn_after_1 = (trn.get_bn_stats(0), trn.get_bn_stats(1))
             params_after_1 = (trn.get_params(0), trn.get_params(1))
     pGr, pDr = trn.get_params(0), trn.get_params(1)
-    digest = hashlib.sha256(pGr.tobytes() + pDr.tobytes() + trn.get_bn_stats(0).tobytes() + trn.get_bn_stats(1).tobytes()).hexdigest()
+    # eval-mode generator forward of one fixed input with THIS rank's operand copies (the bf16 weights the kernels read: with the sharded
+    # reduce + Adam of the big blocks they are written by the peers, and get_params reads the fp32 shards from their owners)
+    probe = trn.generator_forward(np.ascontiguousarray(batches[0][0][:Bl]))
+    digest = hashlib.sha256(pGr.tobytes() + pDr.tobytes() + trn.get_bn_stats(0).tobytes() + trn.get_bn_stats(1).tobytes() + probe.tobytes()).hexdigest()
     digests = [None] * world
     dist.all_gather_object(digests, digest)
     all_losses = [None] * world

@@ -45,6 +45,7 @@ struct cenn_state {
     bool xr_enabled = false;              // peer mailboxes mapped: BN statistics are exchanged inside the finalize kernels
     XrCtx xr = {};                        // exchanges issued from the compute stream
     XrCtx xr2 = {};                       // a second, independent mailbox sequence for a concurrent chain (trainer side stream)
+    XrCtx xr3 = {};                       // a third one for the communication stream (barriers around the sharded reduce + Adam kernel)
     void *xr_own = nullptr;
 };
 static const int RED_SLOTS = 64;
@@ -56,6 +57,9 @@ void *cenn_workspace2(cenn_state *s, size_t bytes);
 int cenn_dist_all_reduce_on(cenn_state *s, void *buf, int64_t count, int is_double, cudaStream_t stream);
 int cenn_dist_all_reduce_bulk(cenn_state *s, float *buf, int64_t count);
 int cenn_dist_all_reduce_bulk_bf16(cenn_state *s, void *buf, int64_t count);
+int cenn_dist_ipc_map(cenn_state *s, void *base, void **peers /*[XR_MAX_WORLD]*/);   // collective: peers[r] = rank r's allocation (CUDA IPC)
+void cenn_dist_ipc_unmap(cenn_state *s, void **peers);
+int cenn_dist_barrier(cenn_state *s);
 int cenn_dist_group(int begin);       // ncclGroupStart / ncclGroupEnd   // second communicator, s->comm_stream
 
 #define CK(expr) do { if (cenn_check_cuda((expr), #expr, __FILE__, __LINE__)) return 1; } while (0)

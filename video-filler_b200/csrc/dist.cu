@@ -80,6 +80,52 @@ int cenn_dist_all_reduce_bulk_bf16(cenn_state *s, void *buf, int64_t count) {
     return nccl_check(g_nccl.all_reduce(buf, buf, (size_t)count, NCCL_BFLOAT16, NCCL_SUM, s->comm2, s->comm_stream), "ncclAllReduce (bulk, bf16)");
 }
 
+// Map one device allocation of every rank into this process (CUDA IPC over NVLink): peers[r] = rank r's `base` (peers[rank] = base).
+// Collective over the first communicator (every rank calls it in the same order); returns 1 and leaves nothing mapped if any rank failed.
+int cenn_dist_ipc_map(cenn_state *s, void *base, void **peers) {
+    if (!s->comm || !g_nccl.all_gather || s->world > XR_MAX_WORLD) { cenn_set_error("cenn_dist_ipc_map: no communicator"); return 1; }
+    const int world = s->world, rank = s->rank;
+    cudaIpcMemHandle_t mine;
+    bool ok = cudaIpcGetMemHandle(&mine, base) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+    std::vector<cudaIpcMemHandle_t> all(world);
+    void *hbuf = nullptr;
+    if (cudaMalloc(&hbuf, sizeof(mine) * (world + 1)) != cudaSuccess) { cenn_set_error("cenn_dist_ipc_map: allocation failed"); return 1; }
+    char *send = (char *)hbuf + sizeof(mine) * world;
+    cudaMemcpy(send, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    if (g_nccl.all_gather(send, hbuf, sizeof(mine), NCCL_UINT8, s->comm, s->stream) != 0) ok = false;
+    cudaStreamSynchronize(s->stream);
+    cudaMemcpy(all.data(), hbuf, sizeof(mine) * world, cudaMemcpyDeviceToHost);
+    cudaFree(hbuf);
+    for (int r = 0; r < world; ++r) peers[r] = nullptr;
+    for (int r = 0; r < world && ok; ++r) {
+        if (r == rank) { peers[r] = base; continue; }
+        if (cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); peers[r] = nullptr; ok = false; }
+    }
+    float *flag_dev = nullptr; float flag_host = ok ? 0.f : 1.f;
+    cudaMalloc(&flag_dev, sizeof(float)); cudaMemcpy(flag_dev, &flag_host, sizeof(float), cudaMemcpyHostToDevice);
+    g_nccl.all_reduce(flag_dev, flag_dev, 1, NCCL_FLOAT32, NCCL_SUM, s->comm, s->stream);
+    cudaStreamSynchronize(s->stream);
+    cudaMemcpy(&flag_host, flag_dev, sizeof(float), cudaMemcpyDeviceToHost); cudaFree(flag_dev);
+    if (flag_host != 0.f) { cenn_dist_ipc_unmap(s, peers); cenn_set_error("cenn_dist_ipc_map: CUDA IPC mapping failed on at least one rank"); return 1; }
+    return 0;
+}
+void cenn_dist_ipc_unmap(cenn_state *s, void **peers) {
+    for (int r = 0; r < s->world && r < XR_MAX_WORLD; ++r) { if (r != s->rank && peers[r]) cudaIpcCloseMemHandle(peers[r]); peers[r] = nullptr; }
+}
+// host-level barrier over the ranks (a one-element all-reduce + stream synchronisation); 0 if there is no communicator
+int cenn_dist_barrier(cenn_state *s) {
+    if (!s->comm) return 0;
+    float *d = nullptr;
+    if (cudaMalloc(&d, sizeof(float)) != cudaSuccess) return 1;
+    cudaMemset(d, 0, sizeof(float));
+    int rc = g_nccl.all_reduce(d, d, 1, NCCL_FLOAT32, NCCL_SUM, s->comm, s->stream);
+    cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    return rc != 0;
+}
+
+
 extern "C" {
 
 int cenn_dist_unique_id(void *id128_host) {
@@ -114,18 +160,18 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
     NcclComm comm2 = nullptr;
     if (nccl_check(g_nccl.init_rank(&comm2, world_size, id2, rank), "ncclCommInitRank (bulk)")) return 1;
     s->comm2 = comm2;
-    {   // the bucket all-reduces are the longest chain behind the last weight gradient: their CTAs go ahead of the queued GEMM CTAs (CENN_COMM_PRIO=0: default priority)
+    {   // CENN_COMM_PRIO=1: highest stream priority for the bucket all-reduces (measured at N = 2: no effect on the step, so the default stays 0)
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         const char *e = getenv("CENN_COMM_PRIO");
-        CK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, (e && atoi(e) == 0) ? 0 : prio_hi));
+        CK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, (e && atoi(e) != 0) ? prio_hi : 0));
     }
     // peer mailboxes for the latency-bound BN-statistics exchanges (35 per step): CUDA IPC over NVLink.  Any failure
     // here just leaves xr_enabled = false and those exchanges stay on NCCL.
     do {
         if (!g_nccl.all_gather || world_size > XR_MAX_WORLD || getenv("CENN_NO_XR")) break;
         const size_t half = (size_t)2 * world_size * XR_MAXF * 8 + 256;   // one mailbox: 2 parity slots x one row per source rank of {value, tag} words (+ spare)
-        const size_t bytes = 2 * half;                                  // two independent mailbox sequences
+        const size_t bytes = 3 * half;                                  // three independent mailbox sequences (main chain, second chain, communication stream)
         void *own = nullptr, *hbuf = nullptr;
         if (cudaMalloc(&own, bytes) != cudaSuccess) { cudaGetLastError(); break; }
         cudaMemset(own, 0, bytes);
@@ -141,10 +187,10 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
         cudaMemcpy(all.data(), hbuf, sizeof(mine) * world_size, cudaMemcpyDeviceToHost);
         cudaFree(hbuf);
         bool ok = rc == 0;
-        XrCtx x = {}, x2 = {};
-        x.world = x2.world = world_size; x.rank = x2.rank = rank;
-        x.push = x2.push = getenv("CENN_XR_PULL") ? 0 : 1;
-        { const char *e = getenv("CENN_XR_TIMEOUT_S"); const double sec = e ? atof(e) : 120.0; x.timeout_cycles = x2.timeout_cycles = (long long)(sec * 2.0e9); }
+        XrCtx x = {}, x2 = {}, x3 = {};
+        x.world = x2.world = x3.world = world_size; x.rank = x2.rank = x3.rank = rank;
+        x.push = x2.push = x3.push = getenv("CENN_XR_PULL") ? 0 : 1;
+        { const char *e = getenv("CENN_XR_TIMEOUT_S"); const double sec = e ? atof(e) : 120.0; x.timeout_cycles = x2.timeout_cycles = x3.timeout_cycles = (long long)(sec * 2.0e9); }
         for (int r = 0; r < world_size && ok; ++r) {
             void *base = own;
             if (r != rank && cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
@@ -152,6 +198,8 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
             x.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + (size_t)2 * world_size * XR_MAXF * 8);
             x2.data[r] = reinterpret_cast<float *>(reinterpret_cast<char *>(base) + half);
             x2.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + half + (size_t)2 * world_size * XR_MAXF * 8);
+            x3.data[r] = reinterpret_cast<float *>(reinterpret_cast<char *>(base) + 2 * half);
+            x3.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(base) + 2 * half + (size_t)2 * world_size * XR_MAXF * 8);
         }
         // every rank must learn whether ALL ranks succeeded (a partial set-up would deadlock the exchange)
         float *flag_dev = nullptr; float flag_host = ok ? 0.f : 1.f;
@@ -161,9 +209,9 @@ int cenn_dist_init(cenn_state *s, const void *id128_host, int world_size, int ra
         cudaMemcpy(&flag_host, flag_dev, sizeof(float), cudaMemcpyDeviceToHost); cudaFree(flag_dev);
         if (flag_host != 0.f) { for (int r = 0; r < world_size; ++r) if (r != rank && x.data[r]) cudaIpcCloseMemHandle(x.data[r]); cudaFree(own); break; }
         unsigned long long *ep = nullptr;
-        cudaMalloc(&ep, 2 * sizeof(*ep)); cudaMemset(ep, 0, 2 * sizeof(*ep));
-        x.epoch = ep; x2.epoch = ep + 1;
-        s->xr = x; s->xr2 = x2; s->xr_own = own; s->xr_enabled = true;
+        cudaMalloc(&ep, 3 * sizeof(*ep)); cudaMemset(ep, 0, 3 * sizeof(*ep));
+        x.epoch = ep; x2.epoch = ep + 1; x3.epoch = ep + 2;
+        s->xr = x; s->xr2 = x2; s->xr3 = x3; s->xr_own = own; s->xr_enabled = true;
     } while (0);
     return 0;
 }

@@ -1479,6 +1479,59 @@ __global__ void __launch_bounds__(256) wholeim_scatter_kernel(const bf16 *__rest
     }
 }
 
+// ---------------------------------------------------------------- data parallel: sharded gradient reduction + Adam over peer memory
+// The two 32.8 M-element generator blocks (E6, G1: 92 % of the gradient bytes) do not go through an all-reduce.  Every rank owns 1/N of each
+// block.  After all ranks have converted their local gradient to bf16 (barrier), the owner READS its shard of every peer's gradient over
+// NVLink (peer loads), adds in rank order (fp32), applies Adam to its shard of master / m / v, and WRITES the updated bf16 weights into every
+// rank's operand copy (peer stores); a second barrier closes the exchange.  NVLink bytes equal a bf16 ring all-reduce's, the Adam pass
+// shrinks to 1/N of the block per rank, and the chain behind the last weight gradient is one short kernel instead of two NCCL all-reduces
+// and a full Adam pass.  fp32 master / m / v of a shard live on its owner only (cenn_trainer_get_params_host reads them from there).
+struct ShardPeers { const bf16 *grad[XR_MAX_WORLD]; bf16 *wbf[XR_MAX_WORLD]; };
+__device__ __forceinline__ uint4 ld_cv16(const void *p) {
+    uint4 v; asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v;
+}
+// one-CTA barrier across the ranks on a mailbox sequence: everything this rank's stream did before it is visible to a peer that has passed it
+__global__ void __launch_bounds__(32) xr_barrier_kernel(const XrCtx x) {
+    __shared__ float token;
+    if (threadIdx.x == 0) token = 1.f;
+    __threadfence_system();
+    __syncthreads();
+    xr_sum_inplace(&token, 1, x);
+}
+__global__ void __launch_bounds__(256) shard_reduce_adam_kernel(const ShardPeers pp, int world, float *__restrict__ x, float *__restrict__ gsum, float *__restrict__ m,
+        float *__restrict__ v, int64_t begin, int64_t count, float b1, float b2, float eps, const float *__restrict__ step_ptr) {
+    // pointers are relative to the block's first element; this rank owns [begin, begin + count), count % 8 == 0
+    const float step = *step_ptr;
+    const int64_t n8 = count / 8;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n8; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = begin + 8 * j;
+        float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < XR_MAX_WORLD; ++r)
+            if (r < world) {                                   // rank order: every owner adds its shard the same way, replicas of wbf are bit-identical
+                const uint4 u = ld_cv16(pp.grad[r] + i);
+                float f[8]; unpack8b(u, f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] += f[k];
+            }
+        float X[8], M[8], V[8];
+        *reinterpret_cast<float4 *>(X) = *reinterpret_cast<const float4 *>(x + i); *reinterpret_cast<float4 *>(X + 4) = *reinterpret_cast<const float4 *>(x + i + 4);
+        *reinterpret_cast<float4 *>(M) = *reinterpret_cast<const float4 *>(m + i); *reinterpret_cast<float4 *>(M + 4) = *reinterpret_cast<const float4 *>(m + i + 4);
+        *reinterpret_cast<float4 *>(V) = *reinterpret_cast<const float4 *>(v + i); *reinterpret_cast<float4 *>(V + 4) = *reinterpret_cast<const float4 *>(v + i + 4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { M[k] = M[k] * b1 + (1.f - b1) * g[k]; V[k] = V[k] * b2 + (1.f - b2) * g[k] * g[k]; X[k] -= step * M[k] / (sqrtf(V[k]) + eps); }
+        *reinterpret_cast<float4 *>(x + i) = *reinterpret_cast<float4 *>(X); *reinterpret_cast<float4 *>(x + i + 4) = *reinterpret_cast<float4 *>(X + 4);
+        *reinterpret_cast<float4 *>(m + i) = *reinterpret_cast<float4 *>(M); *reinterpret_cast<float4 *>(m + i + 4) = *reinterpret_cast<float4 *>(M + 4);
+        *reinterpret_cast<float4 *>(v + i) = *reinterpret_cast<float4 *>(V); *reinterpret_cast<float4 *>(v + i + 4) = *reinterpret_cast<float4 *>(V + 4);
+        if (gsum) { *reinterpret_cast<float4 *>(gsum + i) = *reinterpret_cast<float4 *>(g); *reinterpret_cast<float4 *>(gsum + i + 4) = *reinterpret_cast<float4 *>(g + 4); }
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(X[0], X[1]), h1 = __floats2bfloat162_rn(X[2], X[3]), h2 = __floats2bfloat162_rn(X[4], X[5]), h3 = __floats2bfloat162_rn(X[6], X[7]);
+        const uint4 pk = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1), *reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+#pragma unroll
+        for (int r = 0; r < XR_MAX_WORLD; ++r)
+            if (r < world) *reinterpret_cast<uint4 *>(pp.wbf[r] + i) = pk;
+    }
+}
+
 // ---------------------------------------------------------------- train.lua's optional branches (noiseGen / conditionAdv)
 // noiseGen (train.lua:109-124): a 1x1 convolution of the noise vector runs beside the encoder and nn.JoinTable(2) appends its nz outputs
 // to the nBottleneck encoder outputs before the bottleneck BN.  The joined tensor is the bottleneck block's conv output y [B][pitch]:

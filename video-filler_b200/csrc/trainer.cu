@@ -85,6 +85,11 @@ struct Net {
     float *master = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
     bf16 *wbf = nullptr;
     bf16 *gradbf = nullptr;   // data parallel: bf16 copies of the big weight-gradient blocks (what crosses NVLink)
+    // data parallel, sharded reduce + Adam (nhwc::shard_reduce_adam_kernel): the allocations behind master / grad / wbf / gradbf and the
+    // peers' mappings of the same allocations (CUDA IPC); peer pointer of X on rank r = ipc_X[r] + (X - base_X)
+    void *base_master = nullptr, *base_grad = nullptr, *base_wbf = nullptr;
+    void *ipc_master[XR_MAX_WORLD] = {}, *ipc_grad[XR_MAX_WORLD] = {}, *ipc_wbf[XR_MAX_WORLD] = {}, *ipc_gradbf[XR_MAX_WORLD] = {};
+    std::vector<std::pair<int64_t, int64_t>> shard_blocks;   // (offset, count) of the weight blocks whose master / m / v are sharded over the ranks
     int64_t *bias_seg = nullptr;
     int nbias_seg = 0;
     nhwc::FoldJob *fold_jobs = nullptr;   // device: one job per block (conv gradBias <- partial rows)
@@ -177,6 +182,7 @@ struct cenn_trainer {
     float clip_mv = -1.f;                 // maskValue baked into the captured clip-mode graphs
     // frame mode (cenn_trainer_step_frames_host): whole decoded frames + loader draws in, crop / mask / random blocks on the device
     uint8_t *fr_u8 = nullptr, *fr_mask = nullptr; int *fr_tab = nullptr; size_t fr_u8_cap = 0, fr_mask_cap = 0;
+    bool shard_ok = false;                // data parallel: the peers' generator buffers are mapped (sharded reduce + Adam of the big blocks)
     float *noise = nullptr;               // noiseGen: this step's noise draw [B][nz] fp32 (cenn_trainer_set_noise_*)
     bool join_ctx_done = false;           // program construction: the context branch of conditionAdv's first layer has been emitted for this step
     bool infer = false;                   // inference engine (cenn_inpainter_*): forward plans only, BN folded into weights and bias
@@ -416,10 +422,10 @@ int build_net(T *t, Net &net, const std::vector<Spec> &specs, int in_size, int i
     net.nparam_thnn = toff;
     // The Adam kernel streams these five arrays at identical offsets; with identically aligned bases all five streams
     // would walk the same HBM channel sequence in lock step (observed: 3x slower).  Skew the bases by odd multiples of 256 B.
-    auto skewed = [&](int k) -> float * { float *p = dalloc<float>(t, off + 8 * 65536); return p ? p + (size_t)k * (33856 + 64) : nullptr; };
-    net.master = skewed(0);
-    if (!t->infer) { net.grad = skewed(1); net.m = skewed(2); net.v = skewed(3); }
-    { bf16 *p = dalloc<bf16>(t, off + 8 * 65536); net.wbf = p ? p + (size_t)4 * (33856 + 64) * 2 : nullptr; }
+    auto skewed = [&](int k, void **base) -> float * { float *p = dalloc<float>(t, off + 8 * 65536); if (base) *base = p; return p ? p + (size_t)k * (33856 + 64) : nullptr; };
+    net.master = skewed(0, &net.base_master);
+    if (!t->infer) { net.grad = skewed(1, &net.base_grad); net.m = skewed(2, nullptr); net.v = skewed(3, nullptr); }
+    { bf16 *p = dalloc<bf16>(t, off + 8 * 65536); net.base_wbf = p; net.wbf = p ? p + (size_t)4 * (33856 + 64) * 2 : nullptr; }
     net.adam_t = dalloc<long long>(t, 1); net.adam_step = dalloc<float>(t, 1);
     if (!net.master || !net.wbf || !net.adam_t || !net.adam_step) return 1;
     if (t->infer) {
@@ -761,9 +767,17 @@ void emit_forward(T *t, Net &net, size_t i, bool train) {
 // the following step instead -- from the previous step's E1 gradient, beside the low-occupancy opening of the step.  Same FLOPs per step,
 // one step late, result discarded either way.  CENN_DEAD_DGRAD_INLINE=1 restores the in-place position.
 static bool defer_dead_dgrad() { static const bool v = getenv("CENN_DEAD_DGRAD_INLINE") == nullptr; return v; }
+// sharded reduce + Adam (data parallel): blocks of at least 2^23 elements whose count is a multiple of 8; rank r owns [shard_begin(r), shard_begin(r + 1))
+static bool shard_block(const T *t, const Net &net, int64_t cnt) { return t->shard_ok && &net == &t->G && cnt >= ((int64_t)1 << 23) && cnt % 8 == 0; }
+static int64_t shard_begin(int64_t cnt, int world, int r) { const int64_t per = (((cnt + world - 1) / world) + 7) & ~int64_t(7); return std::min<int64_t>(cnt, per * r); }
+template <typename X> static X *peer_ptr(void *const *ipc, int r, const void *base, const X *local) {
+    return reinterpret_cast<X *>(reinterpret_cast<char *>(ipc[r]) + (reinterpret_cast<const char *>(local) - reinterpret_cast<const char *>(base)));
+}
 static int64_t g_bucket_min() { static const int64_t v = (int64_t)1 << (getenv("CENN_G_BUCKET_LOG2") ? atoi(getenv("CENN_G_BUCKET_LOG2")) : 20); return v; }
 // chunks of one bucket (elements): multiples of 4, the last one takes the remainder
-static int bucket_chunks(int64_t cnt) { static const int v = getenv("CENN_BUCKET_CHUNKS") ? atoi(getenv("CENN_BUCKET_CHUNKS")) : 4; return (cnt >= ((int64_t)1 << 23) && v > 1) ? v : 1; }
+// (EXPERIMENT, default 1 = off: with CENN_BUCKET_CHUNKS=4 the step at N = 2 went from 3.33 to 3.43 ms, with 8 to 3.73 ms -- every extra NCCL
+// launch costs more than the Adam pipelining saves)
+static int bucket_chunks(int64_t cnt) { static const int v = getenv("CENN_BUCKET_CHUNKS") ? atoi(getenv("CENN_BUCKET_CHUNKS")) : 1; return (cnt >= ((int64_t)1 << 23) && v > 1) ? v : 1; }
 static int64_t chunk_off(int64_t cnt, int nch, int c) { return c >= nch ? cnt : ((cnt / nch) & ~int64_t(3)) * c; }
 static int64_t d_bucket_min() { static const int64_t v = (int64_t)1 << (getenv("CENN_D_BUCKET_LOG2") ? atoi(getenv("CENN_D_BUCKET_LOG2")) : 18); return v; }
 // backward of one block: b->g holds dLoss/d(activation output); produces parameter gradients (if want_params)
@@ -967,14 +981,26 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
         // data parallel, generator: the big weight gradients start their all-reduce now, on the bulk communicator's stream,
         // and overlap the rest of the backward sweep (E6 + G1 are 92 % of the 285 MB)
         const bool bucket_g = &net == &t->G && b->w_count >= g_bucket_min(), bucket_d = &net == &t->D && t->d_bucket_sweep && b->w_count >= d_bucket_min();
-        if (dp && s->comm2 && (bucket_g || bucket_d)) {
+        if (dp && s->comm2 && bucket_g && shard_block(t, net, b->w_count)) {
+            // sharded reduce + Adam: only the bf16 conversion here (behind the wgrad); the exchange itself follows this block's dgrad, the last
+            // reader of the operand copy that the peers will overwrite
+            cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
+            float *ptr = grad + b->w_off; bf16 *pbf = net.gradbf + b->w_off; const int64_t cnt = b->w_count;
+            t->g_buckets.push_back({b->w_off, b->w_count});
+            emit(t, "grad_shard_cvt", [t, s, ev, ptr, pbf, cnt]() {
+                if (cenn_check_cuda(cudaEventRecord(ev, t->serial ? s->stream : t->side), "event record", __FILE__, __LINE__)) return 1;
+                if (cenn_check_cuda(cudaStreamWaitEvent(s->comm_stream, ev, 0), "stream wait", __FILE__, __LINE__)) return 1;
+                nhwc::f32_to_bf16_vec_kernel<<<grid1d(s, cnt / 4), 256, 0, s->comm_stream>>>(ptr, pbf, cnt / 4);
+                KLAUNCH(s); return 0; });
+            t->prog.back().bytes = 6.0 * (double)cnt;
+        } else if (dp && s->comm2 && (bucket_g || bucket_d)) {
             cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
             float *ptr = grad + b->w_off; int64_t cnt = b->w_count;
             (bucket_g ? t->g_buckets : t->d_buckets).push_back({b->w_off, b->w_count});
             // generator buckets with an early Adam behind them travel as bf16 (half the NVLink bytes); Adam reads the bf16 sum
             bf16 *pbf = (net.gradbf && cnt % 4 == 0 && getenv("CENN_NO_EARLY_ADAM") == nullptr) ? net.gradbf + b->w_off : nullptr;
-            // the two 32.8 M-element blocks (E6, G1) travel in chunks: the early Adam of chunk k (third stream) overlaps the all-reduce of chunk
-            // k + 1, so the chain behind the last weight gradient ends with a quarter of an Adam pass instead of a whole one
+            // optional (bucket_chunks): the two 32.8 M-element blocks (E6, G1) travel in chunks, the early Adam of chunk k (third stream) overlaps
+            // the all-reduce of chunk k + 1
             const int nch = bucket_chunks(cnt);
             if (bucket_g) { for (int c = 0; c < nch; ++c) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); t->events.push_back(e); b->ar_ev.push_back(e); } }
             emit(t, "grad_bucket_ar", [t, s, b, ev, ptr, pbf, cnt, nch, bucket_g]() {
@@ -1021,7 +1047,30 @@ void emit_backward(T *t, Net &net, size_t i, bool want_params, bool want_dgrad) 
     // (E6 + G1 hold 92 % of the parameters: ~0.3 ms of HBM-bound work moved off the critical path)
     // (data parallel: same, chained behind the block's bucket all-reduce on the bulk communicator's stream)
     const bool dp_bulk = dp && s->comm2 != nullptr;
-    if (want_params && (!dp || dp_bulk) && &net == &t->G && b->w_count >= g_bucket_min() && getenv("CENN_NO_EARLY_ADAM") == nullptr) {
+    if (want_params && dp_bulk && shard_block(t, net, b->w_count)) {
+        cudaEvent_t e1; cudaEventCreateWithFlags(&e1, cudaEventDisableTiming); t->events.push_back(e1);
+        Net *n = &net; const int64_t off = b->w_off, cnt = b->w_count; const float beta1 = t->cfg.beta1;
+        const int world = t->cfg.world_size, rank = t->cfg.rank;
+        t->g_early.push_back({off, cnt});
+        net.shard_blocks.push_back({off, cnt});
+        nhwc::ShardPeers pp = {};
+        for (int r = 0; r < world; ++r) { pp.grad[r] = peer_ptr<bf16>(net.ipc_gradbf, r, net.gradbf, net.gradbf + off); pp.wbf[r] = peer_ptr<bf16>(net.ipc_wbf, r, net.base_wbf, net.wbf + off); }
+        const int64_t begin = shard_begin(cnt, world, rank), mine = shard_begin(cnt, world, rank + 1) - begin;
+        emit(t, "shard_adam", [t, s, n, e1, pp, world, off, begin, mine, beta1]() {
+            // communication stream, behind this block's dgrad: barrier (every rank has converted its gradient and no longer reads its operand
+            // copy) -> owner reduces + updates its shard and stores the new bf16 weights everywhere -> barrier (my operand copy is complete)
+            if (cenn_check_cuda(cudaEventRecord(e1, s->stream), "event record", __FILE__, __LINE__)) return 1;
+            if (cenn_check_cuda(cudaStreamWaitEvent(s->comm_stream, e1, 0), "stream wait", __FILE__, __LINE__)) return 1;
+            nhwc::xr_barrier_kernel<<<1, 32, 0, s->comm_stream>>>(s->xr3); KLAUNCH(s);
+            if (mine > 0) {
+                nhwc::shard_reduce_adam_kernel<<<grid1d(s, mine / 8), 256, 0, s->comm_stream>>>(pp, world, n->master + off, n->grad + off, n->m + off, n->v + off,
+                    begin, mine, beta1, 0.999f, 1e-8f, n->adam_step);
+                KLAUNCH(s);
+            }
+            nhwc::xr_barrier_kernel<<<1, 32, 0, s->comm_stream>>>(s->xr3); KLAUNCH(s);
+            return 0; });
+        t->prog.back().bytes = (28.0 + 4.0) * (double)mine + 2.0 * 2.0 * (double)mine * (world - 1);
+    } else if (want_params && (!dp || dp_bulk) && &net == &t->G && b->w_count >= g_bucket_min() && getenv("CENN_NO_EARLY_ADAM") == nullptr) {
         cudaEvent_t e1, e2; cudaEventCreateWithFlags(&e1, cudaEventDisableTiming); cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
         t->events.push_back(e1); t->events.push_back(e2);
         Net *n = &net; const int64_t off = b->w_off, cnt = b->w_count; const float beta1 = t->cfg.beta1;
@@ -1524,6 +1573,21 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     if (cudaStreamCreateWithPriority(&t->side3, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
     if (cudaStreamCreateWithPriority(&t->side2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
     if (cudaStreamCreateWithPriority(&t->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
+    // data parallel: map the peers' generator buffers for the sharded reduce + Adam of the big blocks (collective: every rank takes the same
+    // decisions -- same configuration and environment).  Any failure leaves the NCCL bucket path in place.
+    if (t->cfg.world_size > 1 && s->comm && s->comm2 && s->xr_enabled && t->G.gradbf && getenv("CENN_NO_EARLY_ADAM") == nullptr && getenv("CENN_NO_SHARD_ADAM") == nullptr) {
+        bool any = false;
+        for (const Block &b : t->G.blocks) any = any || (b.w_count >= ((int64_t)1 << 23) && b.w_count % 8 == 0);
+        if (any) {
+            Net &n = t->G;
+            bool ok = cenn_dist_ipc_map(s, n.gradbf, n.ipc_gradbf) == 0;
+            ok = ok && cenn_dist_ipc_map(s, n.base_wbf, n.ipc_wbf) == 0;
+            ok = ok && cenn_dist_ipc_map(s, n.base_master, n.ipc_master) == 0;
+            ok = ok && cenn_dist_ipc_map(s, n.base_grad, n.ipc_grad) == 0;
+            if (!ok) { fprintf(stderr, "cenn: peer mapping of the generator buffers failed (%s); gradient buckets stay on NCCL\n", cenn_last_error()); }
+            t->shard_ok = ok;
+        }
+    }
     if (build_program(t)) { cenn_trainer_destroy(t); return 1; }
     int64_t before = s->launches;
     (void)before;
@@ -1536,6 +1600,13 @@ int cenn_trainer_destroy(cenn_trainer *t) {
     cudaSetDevice(t->s->device);
     cudaStreamSynchronize(t->s->stream);
     for (auto &g : t->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
+    if (t->shard_ok) {       // peers may still read / write this rank's buffers, and this rank theirs: everyone finishes, then everyone unmaps, then frees
+        cudaDeviceSynchronize();
+        cenn_dist_barrier(t->s);
+        cenn_dist_ipc_unmap(t->s, t->G.ipc_gradbf); cenn_dist_ipc_unmap(t->s, t->G.ipc_wbf); cenn_dist_ipc_unmap(t->s, t->G.ipc_master); cenn_dist_ipc_unmap(t->s, t->G.ipc_grad);
+        cenn_dist_barrier(t->s);
+        t->shard_ok = false;
+    }
     if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (t->ev_copied[i]) cudaEventDestroy(t->ev_copied[i]); if (t->ev_consumed[i]) cudaEventDestroy(t->ev_consumed[i]); if (t->ev_loss[i]) cudaEventDestroy(t->ev_loss[i]); }
     if (t->pin_loss2) cudaFreeHost(t->pin_loss2);
@@ -1630,6 +1701,19 @@ static int get_vec(cenn_trainer *t, Net &n, const float *dev, float *flat) {
     std::vector<float> m(n.nparam);
     CK(cudaMemcpyAsync(m.data(), dev, n.nparam * sizeof(float), cudaMemcpyDeviceToHost, t->s->stream));
     CK(cudaStreamSynchronize(t->s->stream));
+    if (t->shard_ok && !n.shard_blocks.empty() && (dev == n.master || dev == n.grad)) {
+        // sharded blocks: the fp32 master copy / the reduced gradient of a shard lives on its owner -- read it from there (one-sided peer copy;
+        // valid once this rank's step has completed: its closing barrier means every owner has finished its update)
+        void *const *ipc = dev == n.master ? n.ipc_master : n.ipc_grad;
+        const void *base = dev == n.master ? n.base_master : n.base_grad;
+        const int world = t->cfg.world_size, rank = t->cfg.rank;
+        for (const auto &sb : n.shard_blocks)
+            for (int r = 0; r < world; ++r) {
+                if (r == rank) continue;
+                const int64_t b0 = shard_begin(sb.second, world, r), b1 = shard_begin(sb.second, world, r + 1);
+                if (b1 > b0) CK(cudaMemcpy(m.data() + sb.first + b0, peer_ptr<float>(ipc, r, base, dev + sb.first + b0), (size_t)(b1 - b0) * sizeof(float), cudaMemcpyDefault));
+            }
+    }
     master_to_thnn(n, m, flat);
     return 0;
 }
@@ -1963,7 +2047,7 @@ int cenn_trainer_timeline_step(cenn_trainer *t, const float *a, const float *b, 
         // communicator's stream, id 4) are bracketed on that stream
         const bool on_side = !strcmp(op.name, "wgrad") || (!strcmp(op.name, "dgrad") && false);
         const bool on_side3 = !strcmp(op.name, "adam_early");
-        const bool on_comm = !strcmp(op.name, "grad_bucket_ar") && s->comm_stream;
+        const bool on_comm = (!strcmp(op.name, "grad_bucket_ar") || !strcmp(op.name, "grad_shard_cvt") || !strcmp(op.name, "shard_adam")) && s->comm_stream;
         cudaStream_t run = op.chain == 1 ? t->side2 : st;
         cudaStream_t where = on_side ? t->side : (on_side3 ? t->side3 : (on_comm ? s->comm_stream : run));
         stream_id[i] = where == st ? 0 : (where == t->side ? 1 : (where == t->side2 ? 2 : (where == t->side3 ? 3 : 4)));
