@@ -90,6 +90,8 @@ def main():
     pGr, pDr = trn.get_params(0), trn.get_params(1)
     # eval-mode generator forward of one fixed input with THIS rank's operand copies (the bf16 weights the kernels read: with the sharded
     # reduce + Adam of the big blocks they are written by the peers, and get_params reads the fp32 shards from their owners)
+    if args.branches:
+        trn.set_noise(noises[0][:Bl])               # the probe must see the same noise on every rank (each rank trained on its own rows)
     probe = trn.generator_forward(np.ascontiguousarray(batches[0][0][:Bl]))
     digest = hashlib.sha256(pGr.tobytes() + pDr.tobytes() + trn.get_bn_stats(0).tobytes() + trn.get_bn_stats(1).tobytes() + probe.tobytes()).hexdigest()
     digests = [None] * world
