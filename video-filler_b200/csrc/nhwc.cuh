@@ -1532,6 +1532,44 @@ __global__ void __launch_bounds__(256) shard_reduce_adam_kernel(const ShardPeers
     }
 }
 
+// The leftover ranges of a gradient vector (everything outside the buckets: ~1.3 M elements of the generator, ~0.15 M of the discriminator) are
+// latency-bound: an 8-rank NCCL all-reduce of them costs ~0.1 ms at the step's tail.  Same scheme as above without the optimizer: the ranges
+// are flattened into one index space of 16-byte units, rank r owns units [r * per, (r + 1) * per), reads them from every rank (peer loads,
+// rank order -> every replica gets bit-identical sums), and stores the sum into every rank's vector (peer stores).  In place: an element is
+// read and written by its owner only.  A mailbox barrier before (all gradients complete) and after (all stores landed) on the same stream.
+struct PeerVec { float *p[XR_MAX_WORLD]; };
+struct PeerSegs { long long off[16], cnt[16]; int n; };      // every off / cnt is a multiple of 4 floats
+__global__ void __launch_bounds__(256) peer_allreduce_f32_kernel(const PeerVec pv, const PeerSegs sg, int world, int rank) {
+    long long units = 0;
+    for (int k = 0; k < sg.n; ++k) units += sg.cnt[k] / 4;
+    const long long per = (units + world - 1) / world, u0 = per * rank, u1 = u0 + per < units ? u0 + per : units;
+    for (long long u = u0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; u < u1; u += (long long)gridDim.x * blockDim.x) {
+        long long r = u; int k = 0;
+        while (k < sg.n - 1 && r >= sg.cnt[k] / 4) { r -= sg.cnt[k] / 4; ++k; }
+        const long long i = sg.off[k] + 4 * r;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < XR_MAX_WORLD; ++q)
+            if (q < world) {
+                float4 v;
+                asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(pv.p[q] + i) : "memory");
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+#pragma unroll
+        for (int q = 0; q < XR_MAX_WORLD; ++q)
+            if (q < world) *reinterpret_cast<float4 *>(pv.p[q] + i) = acc;
+    }
+}
+// the 8 loss accumulators (doubles; the outputs are floats): one mailbox exchange instead of an NCCL launch
+__global__ void __launch_bounds__(32) losses_xr_kernel(const XrCtx x, double *__restrict__ acc) {
+    __shared__ float buf[8];
+    if (threadIdx.x < 8) buf[threadIdx.x] = (float)acc[threadIdx.x];
+    __syncthreads();
+    xr_sum_inplace(buf, 8, x);
+    __syncthreads();
+    if (threadIdx.x < 8) acc[threadIdx.x] = (double)buf[threadIdx.x];
+}
+
 // ---------------------------------------------------------------- train.lua's optional branches (noiseGen / conditionAdv)
 // noiseGen (train.lua:109-124): a 1x1 convolution of the noise vector runs beside the encoder and nn.JoinTable(2) appends its nz outputs
 // to the nBottleneck encoder outputs before the bottleneck BN.  The joined tensor is the bottleneck block's conv output y [B][pitch]:

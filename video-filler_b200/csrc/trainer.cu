@@ -182,6 +182,7 @@ struct cenn_trainer {
     float clip_mv = -1.f;                 // maskValue baked into the captured clip-mode graphs
     // frame mode (cenn_trainer_step_frames_host): whole decoded frames + loader draws in, crop / mask / random blocks on the device
     uint8_t *fr_u8 = nullptr, *fr_mask = nullptr; int *fr_tab = nullptr; size_t fr_u8_cap = 0, fr_mask_cap = 0;
+    bool peer_ar_ok = false;              // data parallel: both nets' gradient vectors are mapped on every rank (peer all-reduce of the leftover ranges)
     bool shard_ok = false;                // data parallel: the peers' generator buffers are mapped (sharded reduce + Adam of the big blocks)
     float *noise = nullptr;               // noiseGen: this step's noise draw [B][nz] fp32 (cenn_trainer_set_noise_*)
     bool join_ctx_done = false;           // program construction: the context branch of conditionAdv's first layer has been emitted for this step
@@ -1219,6 +1220,28 @@ __global__ void finish_losses_kernel(const double *__restrict__ acc, float *__re
     out[CENN_LOSS_ERRG_TOTAL] = (float)total; out[7] = 0.f;
 }
 
+// leftover gradient ranges summed over the ranks through peer memory (nhwc::peer_allreduce_f32_kernel) on the compute stream; false if the
+// ranges do not fit the kernel's segment table (the caller then uses NCCL)
+bool emit_peer_allreduce(T *t, const char *name, Net &net, const std::vector<std::pair<int64_t, int64_t>> &rest, cudaEvent_t ev_buckets) {
+    cenn_state *s = t->s;
+    if (!t->peer_ar_ok || rest.size() > 16) return false;
+    nhwc::PeerSegs sg = {};
+    for (const auto &x : rest) { if (x.first % 4 || x.second % 4) return false; sg.off[sg.n] = x.first; sg.cnt[sg.n] = x.second; ++sg.n; }
+    nhwc::PeerVec pv = {};
+    const int world = t->cfg.world_size, rank = t->cfg.rank;
+    for (int r = 0; r < world; ++r) pv.p[r] = peer_ptr<float>(net.ipc_grad, r, net.base_grad, net.grad);
+    int64_t total = 0; for (const auto &x : rest) total += x.second;
+    emit(t, name, [s, pv, sg, world, rank, total, ev_buckets]() {
+        // the bucket all-reduces (bulk communicator, comm_stream) and the sharded blocks finish first
+        if (cenn_check_cuda(cudaEventRecord(ev_buckets, s->comm_stream), "event record", __FILE__, __LINE__)) return 1;
+        if (cenn_check_cuda(cudaStreamWaitEvent(s->stream, ev_buckets, 0), "stream wait", __FILE__, __LINE__)) return 1;
+        nhwc::xr_barrier_kernel<<<1, 32, 0, s->stream>>>(s->xr); KLAUNCH(s);
+        nhwc::peer_allreduce_f32_kernel<<<grid1d(s, (total / 4 + world - 1) / world), 256, 0, s->stream>>>(pv, sg, world, rank); KLAUNCH(s);
+        nhwc::xr_barrier_kernel<<<1, 32, 0, s->stream>>>(s->xr); KLAUNCH(s);
+        return 0; });
+    return true;
+}
+
 // ---- the step program ---------------------------------------------------------------------------------------------
 int build_program(T *t) {
     cenn_state *s = t->s;
@@ -1332,6 +1355,7 @@ int build_program(T *t) {
         if (D.nparam > cur) rest.push_back({cur, D.nparam - cur});
         cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
         float *g = D.grad;
+        if (emit_peer_allreduce(t, "gradD_sync", D, rest, ev)) {} else
         emit(t, "gradD_sync", [s, rest, g, ev]() {
             // the bucket all-reduces (bulk communicator, comm_stream) finish first: two communicators are never in flight at once
             // (NCCL documents concurrent collectives on two communicators as a hang risk unless both kernels can be co-resident)
@@ -1416,6 +1440,7 @@ int build_program(T *t) {
         if (G.nparam > cur) rest.push_back({cur, G.nparam - cur});
         cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); t->events.push_back(ev);
         float *g = G.grad;
+        if (emit_peer_allreduce(t, "gradG_sync", G, rest, ev)) {} else
         emit(t, "gradG_sync", [s, rest, g, ev]() {
             // the bucket all-reduces (bulk communicator, comm_stream) finish first: two communicators are never in flight at once
             // (NCCL documents concurrent collectives on two communicators as a hang risk unless both kernels can be co-resident)
@@ -1428,6 +1453,9 @@ int build_program(T *t) {
     emit_adam(t, G, t->g_early);
     emit_weight_prep(t, G);
     float wtl2 = c.wtl2, wtgdl = c.wtgdl;
+    if (c.world_size > 1 && s->xr_enabled && getenv("CENN_NO_PEER_AR") == nullptr)      // the 8 accumulators cross the ranks through the mailboxes
+        emit(t, "losses_sync", [t, s]() { nhwc::losses_xr_kernel<<<1, 32, 0, s->stream>>>(s->xr, t->loss_acc); KLAUNCH(s); return 0; });
+    else
     emit(t, "losses_sync", []() { return 0; }, reinterpret_cast<float *>(t->loss_acc), 0 /* doubles: reduced separately */);
     emit(t, "finish_losses", [t, s, wtl2, wtgdl]() { finish_losses_kernel<<<1, 32, 0, s->stream>>>(t->loss_acc, t->loss_out, wtl2, wtgdl); KLAUNCH(s); return 0; });
     return 0;
@@ -1575,7 +1603,13 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
     if (cudaStreamCreateWithPriority(&t->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cenn_set_error("trainer: side stream creation failed"); cenn_trainer_destroy(t); return 1; }
     // data parallel: map the peers' generator buffers for the sharded reduce + Adam of the big blocks (collective: every rank takes the same
     // decisions -- same configuration and environment).  Any failure leaves the NCCL bucket path in place.
-    if (t->cfg.world_size > 1 && s->comm && s->comm2 && s->xr_enabled && t->G.gradbf && getenv("CENN_NO_EARLY_ADAM") == nullptr && getenv("CENN_NO_SHARD_ADAM") == nullptr) {
+    if (t->cfg.world_size > 1 && s->comm && s->comm2 && s->xr_enabled && getenv("CENN_NO_PEER_AR") == nullptr) {
+        bool ok = cenn_dist_ipc_map(s, t->G.base_grad, t->G.ipc_grad) == 0;
+        ok = ok && cenn_dist_ipc_map(s, t->D.base_grad, t->D.ipc_grad) == 0;
+        if (!ok) fprintf(stderr, "cenn: peer mapping of the gradient vectors failed (%s); leftover gradient ranges stay on NCCL\n", cenn_last_error());
+        t->peer_ar_ok = ok;
+    }
+    if (t->peer_ar_ok && t->G.gradbf && getenv("CENN_NO_EARLY_ADAM") == nullptr && getenv("CENN_NO_SHARD_ADAM") == nullptr) {
         bool any = false;
         for (const Block &b : t->G.blocks) any = any || (b.w_count >= ((int64_t)1 << 23) && b.w_count % 8 == 0);
         if (any) {
@@ -1583,7 +1617,6 @@ int cenn_trainer_create(cenn_state *s, const cenn_trainer_config *cfg, cenn_trai
             bool ok = cenn_dist_ipc_map(s, n.gradbf, n.ipc_gradbf) == 0;
             ok = ok && cenn_dist_ipc_map(s, n.base_wbf, n.ipc_wbf) == 0;
             ok = ok && cenn_dist_ipc_map(s, n.base_master, n.ipc_master) == 0;
-            ok = ok && cenn_dist_ipc_map(s, n.base_grad, n.ipc_grad) == 0;
             if (!ok) { fprintf(stderr, "cenn: peer mapping of the generator buffers failed (%s); gradient buckets stay on NCCL\n", cenn_last_error()); }
             t->shard_ok = ok;
         }
@@ -1600,12 +1633,13 @@ int cenn_trainer_destroy(cenn_trainer *t) {
     cudaSetDevice(t->s->device);
     cudaStreamSynchronize(t->s->stream);
     for (auto &g : t->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
-    if (t->shard_ok) {       // peers may still read / write this rank's buffers, and this rank theirs: everyone finishes, then everyone unmaps, then frees
+    if (t->shard_ok || t->peer_ar_ok) {       // peers may still read / write this rank's buffers, and this rank theirs: everyone finishes, then everyone unmaps, then frees
         cudaDeviceSynchronize();
         cenn_dist_barrier(t->s);
         cenn_dist_ipc_unmap(t->s, t->G.ipc_gradbf); cenn_dist_ipc_unmap(t->s, t->G.ipc_wbf); cenn_dist_ipc_unmap(t->s, t->G.ipc_master); cenn_dist_ipc_unmap(t->s, t->G.ipc_grad);
+        cenn_dist_ipc_unmap(t->s, t->D.ipc_grad);
         cenn_dist_barrier(t->s);
-        t->shard_ok = false;
+        t->shard_ok = false; t->peer_ar_ok = false;
     }
     if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (t->ev_copied[i]) cudaEventDestroy(t->ev_copied[i]); if (t->ev_consumed[i]) cudaEventDestroy(t->ev_consumed[i]); if (t->ev_loss[i]) cudaEventDestroy(t->ev_loss[i]); }
