@@ -348,7 +348,9 @@ def test_clip_mode_step_equals_three_tensor_step(cenn):
     assert not np.array_equal(ctx1, ctx2)                                # the flags do something
     # identical inputs: what is left is the run-to-run spread of the executor (order of fp32 atomics); errG is evaluated after
     # D's Adam update and inherits the spread of D's gradients
-    for k, tol in (("errG_l2", 2e-3), ("errG_gdl", 2e-3), ("errD", 5e-3), ("errG", 4e-2)):
+    # (errD: a handful of samples per BN batch -- one flipped bf16 rounding in a statistic moves the discriminator's loss by up to ~1 %;
+    # observed spread between two runs on identical inputs: 0.1-0.8 %)
+    for k, tol in (("errG_l2", 2e-3), ("errG_gdl", 2e-3), ("errD", 1.5e-2), ("errG", 4e-2)):
         assert abs(l0[k] - l1[k]) <= tol * max(abs(l0[k]), 1e-3), (k, l0[k], l1[k])
     assert _cos(g0, g1) >= 0.97
     with pytest.raises(Exception, match="video variant"):
@@ -582,7 +584,7 @@ def test_frame_mode_step_runs_the_loader_hook_on_the_device(cenn):
         trn.close()
     (l0, ctx0, g0), (l1, ctx1, g1) = res
     assert np.array_equal(ctx0, ctx1)                     # identical bf16 step inputs on both paths
-    for k, tol in (("errG_l2", 2e-3), ("errG_gdl", 2e-3), ("errD", 5e-3), ("errG", 4e-2)):
+    for k, tol in (("errG_l2", 2e-3), ("errG_gdl", 2e-3), ("errD", 1.5e-2), ("errG", 4e-2)):
         assert abs(l0[k] - l1[k]) <= tol * max(abs(l0[k]), 1e-3), (k, l0[k], l1[k])
     assert _cos(g0, g1) >= 0.97
 
@@ -634,6 +636,6 @@ def test_byte_image_step_equals_float_step(cenn):
         trn.close()
     (l0, c0, _, g0), (l1, c1, _, g1) = res
     assert np.array_equal(c0, c1)                           # identical bf16 real_ctx on both paths
-    for k, tol in (("errG_l2", 2e-3), ("errD_real", 2e-3), ("errD", 5e-3), ("errG", 4e-2)):
+    for k, tol in (("errG_l2", 2e-3), ("errD_real", 2e-3), ("errD", 1.5e-2), ("errG", 4e-2)):
         assert abs(l0[k] - l1[k]) <= tol * max(abs(l0[k]), 1e-3), (k, l0[k], l1[k])
     assert _cos(g0, g1) >= 0.97
