@@ -270,11 +270,11 @@ def test_fused_step_ragged_batch(cenn, variant, B):
 
 def test_losses_after_100_steps_match_oracle_fixture(cenn):
     """north_star: losses after 100 steps within 1 %.  The oracle's 100 fp32 steps at the CPU config (batch 64, nBottleneck
-    4000) are a committed fixture (tools/parity_steps.py --make-golden); the executor replays the same seeded batches."""
+    4000) are a committed fixture (tests/tools/parity_steps.py --make-golden); the executor replays the same seeded batches."""
     import os
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, os.path.join(root, "tools"))
+    sys.path.insert(0, os.path.join(root, "tests", "tools"))
     import parity_steps
     if not os.path.exists(parity_steps.GOLDEN):
         pytest.skip("tests/golden/losses_100.npz not generated")
@@ -288,7 +288,7 @@ def test_losses_after_100_steps_match_oracle_fixture(cenn):
     assert s["errG_total"]["rel_at_last_step"] <= 3e-2 and s["errG_total"]["rel_of_mean_last10"] <= 1e-2
     assert s["errG_l2"]["max_rel_all_steps"] <= 5e-2          # measured 3.2 % at the worst step (profiles/r1_parity_steps.json)
     # adversarial terms: the first step is a pure function of the inputs; later the GAN game amplifies rounding differences.
-    # CONTROL (tools/parity_steps.py --control -> tests/golden/parity_control.json): three CPU runs of the same oracle step sequence
+    # CONTROL (tests/tools/parity_steps.py --control -> tests/golden/parity_control.json): three CPU runs of the same oracle step sequence
     # that differ from the golden run only at rounding level (other summation order, weights perturbed by one fp32 ulp, fp64)
     # drift from it by 13-44 % (errD) and 10-33 % (errG) at step 100 and by 2-33 % in the mean over the last ten steps.  A single step of
     # these terms is a coin flip (errD swings between 0.1 and 6 from step to step on every arm: two builds of the executor measured

@@ -1,6 +1,6 @@
 """Per-layer diagnostics of the fused executor against the oracle (run on a GPU box)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import nets as onets, step as ostep
 import video_filler_b200.tensor as T

@@ -1,7 +1,7 @@
 """Isolate the executor's backward kernels: gate agreement with the (bf16-emulating) oracle, and weight gradients
 recomputed in fp64 from the executor's OWN stored tensors (so upstream differences cancel)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import nets as onets, step as ostep, ops, nn as onn
 import video_filler_b200.tensor as T

@@ -4,8 +4,8 @@ north_star: "losses after 100 steps within 1 %".  The oracle's 100 steps take ~2
 where CPU time is free and committed as a fixture; the GPU side replays the same seeded batches through the fused
 executor (BF16 tensor-core mode) and compares.
 
-    python tools/parity_steps.py --make-golden      # oracle (fp32, the reference's gpu=0 arithmetic) -> tests/golden/losses_100.npz
-    python tools/parity_steps.py                    # executor on cuda:0 vs the fixture; writes gpurun_out/parity_steps.json
+    python tests/tools/parity_steps.py --make-golden      # oracle (fp32, the reference's gpu=0 arithmetic) -> tests/golden/losses_100.npz
+    python tests/tools/parity_steps.py                    # executor on cuda:0 vs the fixture; writes gpurun_out/parity_steps.json
 
 Batches: video_filler_b200.synth.image_batch with numpy PCG64 seed 1234, one fresh batch per step; weights
 util.weights_init with seed 1234 (train.lua:58-67).  Both sides start from the identical flat parameter vectors.
@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden", "losses_100.npz")
 NAMES = ("errD", "errG", "errG_l2", "errD_real", "errD_fake", "errG_total")
